@@ -1,0 +1,670 @@
+// nbk.cu — libnbk: the C ABI of include/nbk.h over the sweep engine of sweep.cuh.
+// sm_100a only; no CPU fallback (nbk_create fails without a CUDA device).
+#include "../../include/nbk.h"
+#include "sweep.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace nbk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct nbk_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int64_t launches = 0;
+  std::string err;
+  // device workspaces
+  DevBuf d_m, d_q, d_vel, d_aux_in, d_packed, d_aux, d_partial, d_out[4], d_scalar;
+  // resident bodies
+  int resident_n = 0;
+  DevBuf d_res_m, d_res_packed;
+  // pinned host staging for scalar read-back
+  double *h_scalar = nullptr;
+};
+
+namespace {
+
+int fail(nbk_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ctx, NBK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+int reserve(nbk_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return NBK_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess)
+    return fail(ctx, NBK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  return NBK_OK;
+}
+
+#define TRY(expr)               \
+  do {                          \
+    int rc_ = (expr);           \
+    if (rc_ != NBK_OK) return rc_; \
+  } while (0)
+
+int check_ranges(nbk_ctx *ctx, int n, int t0, int t1, int s0, int s1) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || t0 < 0 || t1 < t0 || t1 > n || s0 < 0 || s1 < s0 || s1 > n)
+    return fail(ctx, NBK_ERR_ARG, "bad ranges: n=%d targets=[%d,%d) sources=[%d,%d)", n, t0, t1,
+                s0, s1);
+  return NBK_OK;
+}
+
+// ---- sweep launcher --------------------------------------------------------------------------
+template <class Op, int IPT, int MINB> struct Launcher {
+  static int occupancy(nbk_ctx *ctx, int *occ) {
+    static int cached = -1;
+    if (cached < 0) {
+      constexpr size_t smem = SweepCfg<Op, IPT>::smem_bytes;
+      CK(cudaFuncSetAttribute(sweep_kernel<Op, IPT, MINB>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int o = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sweep_kernel<Op, IPT, MINB>, NT, smem));
+      if (o < 1) return fail(ctx, NBK_ERR_CUDA, "sweep kernel does not fit on an SM");
+      cached = o;
+    }
+    *occ = cached;
+    return NBK_OK;
+  }
+
+  // P.packed, ranges, scalars and outputs must be set; fills the tiling fields and launches.
+  static int run(nbk_ctx *ctx, SweepParams P, cudaStream_t st, bool time_it) {
+    constexpr int TI = NT * IPT;
+    const int nt = P.t1 - P.t0, ns = P.s1 - P.s0;
+    if (nt == 0) return NBK_OK;
+    int occ = 0;
+    TRY(occupancy(ctx, &occ));
+    P.n_it = (nt + TI - 1) / TI;
+    P.n_jt = (ns + TJ - 1) / TJ;
+    if (P.n_jt == 0) return fail(ctx, NBK_ERR_ARG, "empty source range");
+    P.units = (long long)P.n_it * P.n_jt;
+    long long G = (long long)ctx->sm_count * occ;
+    if (G > P.units) G = P.units;
+    P.units_per_cta = (P.units + G - 1) / G;
+    G = (P.units + P.units_per_cta - 1) / P.units_per_cta;  // drop empty trailing CTAs
+    TRY(reserve(ctx, ctx->d_partial, (size_t)2 * G * Op::NACC * TI * sizeof(double)));
+    P.partial = (double *)ctx->d_partial.p;
+    if (time_it) CK(cudaEventRecord(ctx->ev0, st));
+    sweep_kernel<Op, IPT, MINB>
+        <<<(unsigned)G, NT, SweepCfg<Op, IPT>::smem_bytes, st>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (P.units_per_cta % P.n_jt != 0) {  // some i-tile's sources are split over CTAs
+      fixup_kernel<Op, IPT><<<P.n_it, TI, 0, st>>>(P);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    if (time_it) {
+      CK(cudaEventRecord(ctx->ev1, st));
+      ctx->ev_valid = true;
+    }
+    return NBK_OK;
+  }
+};
+
+using K1 = Launcher<OpGradV, 2, 4>;
+using K2 = Launcher<OpGradVDGradV, 2, 4>;
+using K3 = Launcher<OpV, 2, 4>;
+using K4 = Launcher<OpKick<false>, 2, 4>;
+using K4T = Launcher<OpKick<true>, 2, 3>;
+
+// ---- O(N) device helpers ---------------------------------------------------------------------
+__global__ void zero_kernel(double *p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+__global__ void fill_kernel(double *p, size_t n, double v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Deterministic single-CTA sum of x[0..n) (fixed tree shape): Energy's final scalar.
+__global__ void __launch_bounds__(1024) sum_kernel(const double *__restrict__ x, int n,
+                                                   double *out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ke[i] = |p_i|^2 / (2 m_i)  (energy.ml:57-58)
+__global__ void kinetic_kernel(int n, const double *__restrict__ m, const double *__restrict__ p,
+                               double *__restrict__ ke) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+  double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+  ke[i] = __ddiv_rn(n2, __dmul_rn(2.0, m[i]));
+}
+
+// Pure-DFMA throughput probe: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double seed, double *sink) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+         a6 = seed + 6, a7 = seed + 7;
+  const double b = 1.0000001, c = 1e-9;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, b, c);
+      a1 = fma(a1, b, c);
+      a2 = fma(a2, b, c);
+      a3 = fma(a3, b, c);
+      a4 = fma(a4, b, c);
+      a5 = fma(a5, b, c);
+      a6 = fma(a6, b, c);
+      a7 = fma(a7, b, c);
+    }
+  }
+  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) sink[0] = s;
+}
+
+int upload(nbk_ctx *ctx, DevBuf &b, const double *h, size_t count) {
+  TRY(reserve(ctx, b, count * sizeof(double)));
+  if (count) CK(cudaMemcpyAsync(b.p, h, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return NBK_OK;
+}
+
+int download(nbk_ctx *ctx, double *h, const DevBuf &b, size_t count) {
+  if (count) CK(cudaMemcpyAsync(h, b.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return NBK_OK;
+}
+
+int pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, const double *d_vel,
+         int is_velocity, double *d_packed, cudaStream_t st) {
+  if (n == 0) return NBK_OK;
+  pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_m, d_q, d_vel, is_velocity, d_packed);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+// Upload (m, q, vel) from the host and pack them into ctx->d_packed.
+int stage_bodies(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
+                 int is_velocity) {
+  if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
+  TRY(upload(ctx, ctx->d_m, m, n));
+  TRY(upload(ctx, ctx->d_q, q, 3 * (size_t)n));
+  if (vel) TRY(upload(ctx, ctx->d_vel, vel, 3 * (size_t)n));
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  return pack(ctx, n, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
+              vel ? (const double *)ctx->d_vel.p : nullptr, is_velocity,
+              (double *)ctx->d_packed.p, ctx->stream);
+}
+
+SweepParams base_params(const double *packed, double eps2, int t0, int t1, int s0, int s1) {
+  SweepParams P;
+  memset(&P, 0, sizeof P);
+  P.packed = packed;
+  P.eps2 = eps2;
+  P.t0 = t0;
+  P.t1 = t1;
+  P.s0 = s0;
+  P.s1 = s1;
+  return P;
+}
+
+int sync(nbk_ctx *ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NBK_OK;
+}
+
+// ---- sweeps on an already packed device array, results to host ---------------------------------
+int run_grad_v(nbk_ctx *ctx, const double *packed, double eps2, int t0, int t1, int s0, int s1,
+               double *gsum) {
+  const size_t nt = (size_t)(t1 - t0);
+  if (nt == 0) return NBK_OK;
+  if (!gsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  TRY(reserve(ctx, ctx->d_out[0], 3 * nt * sizeof(double)));
+  if (s1 == s0) {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, 3 * nt * sizeof(double), ctx->stream));
+  } else {
+    SweepParams P = base_params(packed, eps2, t0, t1, s0, s1);
+    P.out[0] = (double *)ctx->d_out[0].p;
+    TRY(K1::run(ctx, P, ctx->stream, true));
+  }
+  TRY(download(ctx, gsum, ctx->d_out[0], 3 * nt));
+  return sync(ctx);
+}
+
+int run_grad_v_dgrad_v(nbk_ctx *ctx, const double *packed, double eps2, int t0, int t1, int s0,
+                       int s1, double *gsum, double *dgsum) {
+  const size_t nt = (size_t)(t1 - t0);
+  if (nt == 0) return NBK_OK;
+  if (!gsum || !dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  TRY(reserve(ctx, ctx->d_out[0], 3 * nt * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], 3 * nt * sizeof(double)));
+  if (s1 == s0) {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, 3 * nt * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_out[1].p, 0, 3 * nt * sizeof(double), ctx->stream));
+  } else {
+    SweepParams P = base_params(packed, eps2, t0, t1, s0, s1);
+    P.out[0] = (double *)ctx->d_out[0].p;
+    P.out[1] = (double *)ctx->d_out[1].p;
+    TRY(K2::run(ctx, P, ctx->stream, true));
+  }
+  TRY(download(ctx, gsum, ctx->d_out[0], 3 * nt));
+  TRY(download(ctx, dgsum, ctx->d_out[1], 3 * nt));
+  return sync(ctx);
+}
+
+int run_v(nbk_ctx *ctx, const double *packed, double eps2, int t0, int t1, int s0, int s1,
+          double *phi, double *total) {
+  const size_t nt = (size_t)(t1 - t0);
+  if (nt == 0) {
+    if (total) *total = 0.0;
+    return NBK_OK;
+  }
+  TRY(reserve(ctx, ctx->d_out[0], nt * sizeof(double)));
+  if (s1 == s0) {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, nt * sizeof(double), ctx->stream));
+  } else {
+    SweepParams P = base_params(packed, eps2, t0, t1, s0, s1);
+    P.out[0] = (double *)ctx->d_out[0].p;
+    TRY(K3::run(ctx, P, ctx->stream, true));
+  }
+  if (phi) TRY(download(ctx, phi, ctx->d_out[0], nt));
+  if (total) {
+    TRY(reserve(ctx, ctx->d_scalar, 64));
+    sum_kernel<<<1, 1024, 0, ctx->stream>>>((const double *)ctx->d_out[0].p, (int)nt,
+                                            (double *)ctx->d_scalar.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  }
+  TRY(sync(ctx));
+  if (total) *total = ctx->h_scalar[0];
+  return NBK_OK;
+}
+
+int run_kick(nbk_ctx *ctx, const double *packed, double eta, double dt, int t0, int t1, int s0,
+             int s1, double *dv, double *tmin) {
+  const size_t nt = (size_t)(t1 - t0);
+  if (nt == 0) return NBK_OK;
+  if (!dv) return fail(ctx, NBK_ERR_ARG, "null output");
+  TRY(reserve(ctx, ctx->d_out[0], 3 * nt * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], nt * sizeof(double)));
+  if (s1 == s0) {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, 3 * nt * sizeof(double), ctx->stream));
+    if (tmin) {
+      fill_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
+          (double *)ctx->d_out[1].p, nt, __builtin_inf());
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+  } else {
+    SweepParams P = base_params(packed, 0.0, t0, t1, s0, s1);
+    P.dt = dt;
+    P.eta = eta;
+    P.out[0] = (double *)ctx->d_out[0].p;
+    P.out[1] = (double *)ctx->d_out[1].p;
+    if (tmin) TRY(K4T::run(ctx, P, ctx->stream, true));
+    else TRY(K4::run(ctx, P, ctx->stream, true));
+  }
+  TRY(download(ctx, dv, ctx->d_out[0], 3 * nt));
+  if (tmin) TRY(download(ctx, tmin, ctx->d_out[1], nt));
+  return sync(ctx);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *nbk_version(void) { return "libnbk 0.1 (sm_100a)"; }
+
+const char *nbk_last_error(const nbk_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int nbk_create(nbk_ctx **out, int device) {
+  nbk_ctx *ctx = nullptr;  // CK() reports into g_create_error while ctx == NULL
+  if (!out) return fail(nullptr, NBK_ERR_ARG, "nbk_create: null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, NBK_ERR_CUDA,
+                "nbk_create: no CUDA device (%s); libnbk has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(nullptr, NBK_ERR_ARG, "nbk_create: device %d out of range [0,%d)", device, count);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, NBK_ERR_CUDA,
+                "nbk_create: device %d is sm_%d%d; libnbk is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+  nbk_ctx *c = new (std::nothrow) nbk_ctx();
+  if (!c) return fail(nullptr, NBK_ERR_NOMEM, "nbk_create: out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaError_t e2 = cudaEventCreate(&c->ev0);
+  cudaError_t e3 = cudaEventCreate(&c->ev1);
+  cudaError_t e4 = cudaMallocHost((void **)&c->h_scalar, 64);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    nbk_destroy(c);
+    return fail(nullptr, NBK_ERR_CUDA, "nbk_create: stream/event/pinned allocation failed");
+  }
+  *out = c;
+  return NBK_OK;
+}
+
+void nbk_destroy(nbk_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
+                    &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
+                    &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed};
+  for (DevBuf *b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->h_scalar) cudaFreeHost(c->h_scalar);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int nbk_sm_count(const nbk_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t nbk_launch_count(const nbk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int nbk_last_kernel_ms(nbk_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return NBK_ERR_ARG;
+  if (!ctx->ev_valid) return fail(ctx, NBK_ERR_STATE, "no sweep has been timed yet");
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return NBK_OK;
+}
+
+// ---- host-buffer sweeps ----------------------------------------------------------------------
+int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2, int t0,
+                   int t1, int s0, int s1, double *gsum) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
+  return run_grad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum);
+}
+
+int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q,
+                           const double *p, double eps2, int t0, int t1, int s0, int s1,
+                           double *gsum, double *dgsum) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
+  TRY(stage_bodies(ctx, n, m, q, p, 0));
+  return run_grad_v_dgrad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum,
+                            dgsum);
+}
+
+int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2, int t0, int t1,
+              int s0, int s1, double *phi, double *total) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) {
+    if (total) *total = 0.0;
+    return NBK_OK;
+  }
+  TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
+  return run_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, phi, total);
+}
+
+int nbk_energy(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+               double eps2, double *ke, double *pe) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0) return fail(ctx, NBK_ERR_ARG, "n < 0");
+  CK(cudaSetDevice(ctx->device));
+  if (ke) *ke = 0.0;
+  if (pe) *pe = 0.0;
+  if (n == 0) return NBK_OK;
+  if (ke && !p) return fail(ctx, NBK_ERR_ARG, "kinetic energy needs momenta");
+  if (pe) {
+    double tot = 0.0;
+    TRY(nbk_v_sum(ctx, n, m, q, eps2, 0, n, 0, n, nullptr, &tot));
+    *pe = 0.5 * tot;
+  }
+  if (ke) {
+    TRY(upload(ctx, ctx->d_m, m, n));
+    TRY(upload(ctx, ctx->d_vel, p, 3 * (size_t)n));
+    TRY(reserve(ctx, ctx->d_out[0], (size_t)n * sizeof(double)));
+    TRY(reserve(ctx, ctx->d_scalar, 64));
+    kinetic_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+        n, (const double *)ctx->d_m.p, (const double *)ctx->d_vel.p, (double *)ctx->d_out[0].p);
+    CK(cudaGetLastError());
+    sum_kernel<<<1, 1024, 0, ctx->stream>>>((const double *)ctx->d_out[0].p, n,
+                                            (double *)ctx->d_scalar.p);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    TRY(sync(ctx));
+    *ke = ctx->h_scalar[0];
+  }
+  return NBK_OK;
+}
+
+int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const double *v,
+                 double eta, double dt, int t0, int t1, int s0, int s1, double *dv,
+                 double *tmin) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  if (tmin && !v) return fail(ctx, NBK_ERR_ARG, "time-scale needs velocities");
+  TRY(stage_bodies(ctx, n, m, q, v, 1));
+  return run_kick(ctx, (const double *)ctx->d_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
+}
+
+int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int, const double *, const double *,
+                                     const double *, const double *, const double *,
+                                     const double *, double, double, int, int, int, int,
+                                     double *, double *) {
+  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_dgrad_v_sum_predicted: not built yet");
+}
+
+int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int, const double *, const double *,
+                                   const double *, int, const double *, const double *, double,
+                                   int, int, int, int, double *, double *, double *, double *) {
+  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_dgrad_v_sum_tangent: not built yet");
+}
+
+int nbk_grad_v_sum_tangent(nbk_ctx *ctx, int, const double *, const double *, int,
+                           const double *, double, int, int, int, int, double *, double *) {
+  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_sum_tangent: not built yet");
+}
+
+// ---- device-resident bodies --------------------------------------------------------------------
+int nbk_bodies_upload(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
+                      int is_velocity) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || !m || !q) return fail(ctx, NBK_ERR_ARG, "nbk_bodies_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  TRY(upload(ctx, ctx->d_res_m, m, n));
+  TRY(upload(ctx, ctx->d_q, q, 3 * (size_t)n));
+  if (vel) TRY(upload(ctx, ctx->d_vel, vel, 3 * (size_t)n));
+  TRY(reserve(ctx, ctx->d_res_packed, (size_t)n * PK * sizeof(double)));
+  TRY(pack(ctx, n, (const double *)ctx->d_res_m.p, (const double *)ctx->d_q.p,
+           vel ? (const double *)ctx->d_vel.p : nullptr, is_velocity,
+           (double *)ctx->d_res_packed.p, ctx->stream));
+  TRY(sync(ctx));
+  ctx->resident_n = n;
+  return NBK_OK;
+}
+
+int nbk_bodies_update(nbk_ctx *ctx, int i0, int i1, const double *q, const double *vel,
+                      int is_velocity) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (i0 < 0 || i1 < i0 || i1 > ctx->resident_n || !q)
+    return fail(ctx, NBK_ERR_ARG, "nbk_bodies_update: bad range [%d,%d) of %d", i0, i1,
+                ctx->resident_n);
+  CK(cudaSetDevice(ctx->device));
+  const int cnt = i1 - i0;
+  if (cnt == 0) return NBK_OK;
+  TRY(upload(ctx, ctx->d_q, q, 3 * (size_t)cnt));
+  if (vel) TRY(upload(ctx, ctx->d_vel, vel, 3 * (size_t)cnt));
+  TRY(pack(ctx, cnt, (const double *)ctx->d_res_m.p + i0, (const double *)ctx->d_q.p,
+           vel ? (const double *)ctx->d_vel.p : nullptr, is_velocity,
+           (double *)ctx->d_res_packed.p + (size_t)i0 * PK, ctx->stream));
+  return sync(ctx);
+}
+
+int nbk_resident_count(const nbk_ctx *ctx) { return ctx ? ctx->resident_n : 0; }
+
+#define NEED_RESIDENT()                                                            \
+  do {                                                                             \
+    if (!ctx) return NBK_ERR_ARG;                                                  \
+    if (ctx->resident_n == 0)                                                      \
+      return fail(ctx, NBK_ERR_STATE, "no resident bodies: call nbk_bodies_upload"); \
+    TRY(check_ranges(ctx, ctx->resident_n, t0, t1, s0, s1));                       \
+    CK(cudaSetDevice(ctx->device));                                                \
+  } while (0)
+
+int nbk_resident_grad_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1,
+                            double *gsum) {
+  NEED_RESIDENT();
+  return run_grad_v(ctx, (const double *)ctx->d_res_packed.p, eps2, t0, t1, s0, s1, gsum);
+}
+
+int nbk_resident_grad_v_dgrad_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1,
+                                    double *gsum, double *dgsum) {
+  NEED_RESIDENT();
+  return run_grad_v_dgrad_v(ctx, (const double *)ctx->d_res_packed.p, eps2, t0, t1, s0, s1, gsum,
+                            dgsum);
+}
+
+int nbk_resident_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1, double *phi,
+                       double *total) {
+  NEED_RESIDENT();
+  return run_v(ctx, (const double *)ctx->d_res_packed.p, eps2, t0, t1, s0, s1, phi, total);
+}
+
+int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, int s0, int s1,
+                          double *dv, double *tmin) {
+  NEED_RESIDENT();
+  return run_kick(ctx, (const double *)ctx->d_res_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
+}
+
+// ---- raw device-pointer API ----------------------------------------------------------------------
+int nbk_dev_pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, const double *d_vel,
+                 int is_velocity, double *d_packed, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || !d_m || !d_q || !d_packed || ((uintptr_t)d_packed & 15))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_pack: bad arguments (d_packed must be 16-byte aligned)");
+  CK(cudaSetDevice(ctx->device));
+  return pack(ctx, n, d_m, d_q, d_vel, is_velocity, d_packed,
+              stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+#define DEV_COMMON()                                                                     \
+  do {                                                                                   \
+    TRY(check_ranges(ctx, n_total, t0, t1, s0, s1));                                     \
+    if (!d_packed || ((uintptr_t)d_packed & 15))                                         \
+      return fail(ctx, NBK_ERR_ARG, "d_packed must be a 16-byte aligned device pointer"); \
+    CK(cudaSetDevice(ctx->device));                                                      \
+    if (t1 == t0 || s1 == s0) return NBK_OK;                                             \
+  } while (0)
+
+int nbk_dev_grad_v_dgrad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2,
+                               int t0, int t1, int s0, int s1, double *d_gsum, double *d_dgsum,
+                               int accumulate, void *stream) {
+  DEV_COMMON();
+  if (!d_gsum || !d_dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
+  P.out[0] = d_gsum;
+  P.out[1] = d_dgsum;
+  P.accumulate = accumulate;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return K2::run(ctx, P, st, false);
+}
+
+int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0,
+                       int t1, int s0, int s1, double *d_gsum, int accumulate, void *stream) {
+  DEV_COMMON();
+  if (!d_gsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
+  P.out[0] = d_gsum;
+  P.accumulate = accumulate;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return K1::run(ctx, P, st, false);
+}
+
+int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0, int t1,
+                  int s0, int s1, double *d_phi, int accumulate, void *stream) {
+  DEV_COMMON();
+  if (!d_phi) return fail(ctx, NBK_ERR_ARG, "null output");
+  SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
+  P.out[0] = d_phi;
+  P.accumulate = accumulate;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return K3::run(ctx, P, st, false);
+}
+
+int nbk_fp64_peak(nbk_ctx *ctx, int iters, double *tflops, float *ms) {
+  if (!ctx || !tflops || !ms || iters <= 0) return NBK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  TRY(reserve(ctx, ctx->d_scalar, 64));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(16, 1.0, (double *)ctx->d_scalar.p);
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, 1.0, (double *)ctx->d_scalar.p);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaGetLastError());
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  ctx->ev_valid = false;
+  ctx->launches += 2;
+  double flop = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flop / ((double)*ms * 1e-3) / 1e12;
+  return NBK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,505 @@
+// sweep.cuh — the one sweep engine every O(N^2) pair loop of the path runs on (sm_100a only).
+//
+// Shape: targets x sources is cut into units of TI targets x TJ sources.
+// Units are numbered i-tile-major and dealt to a PERSISTENT grid of G = (#SMs x resident
+// CTAs/SM) CTAs in equal contiguous runs ("stream-K" over the source axis), so the grid is
+// always full whatever N is and a handful of targets still spreads its sources over the whole
+// chip.  Inside a CTA each thread owns IPT targets in registers (i-parallel); source tiles
+// (TJ packed bodies = TJ*64 B, contiguous) are staged into shared memory by the TMA engine
+// (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP / SYNCS) through a STAGES-deep
+// full/empty ring, and every lane reads the same source with broadcast LDS.128.
+// Accumulators stay in registers for a whole run of source tiles.  A run that covers a
+// complete source range writes final results; a partial run writes its accumulators to a
+// per-CTA slot and a small fix-up kernel combines the slots of each i-tile in ascending
+// source order - fixed order, so results are reproducible run to run (no atomics).
+//
+// No tensor cores: a pair interaction is not a contraction.  The bound is the FP64 pipe.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nbk {
+
+constexpr int PK = 8;            // doubles per packed body {x,y,z,m,vx,vy,vz,0}
+constexpr int NT = 128;          // threads per CTA
+constexpr int TJ = 128;          // sources per tile (8 KB per stage)
+constexpr int STAGES = 3;
+
+// ---- PTX helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NBK_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NBK_DONE_%=;\n"
+      "bra NBK_WAIT_%=;\n"
+      "NBK_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// 1/sqrt(x): MUFU.RSQ64H seed (~2^-22 relative) + one third-order step
+// y = y0 (1 + e/2 + 3 e^2/8), e = 1 - x y0^2: error ~ (5/16) e^3 < 2^-64, so the result is
+// the correctly rounded value to within the last two roundings.  2 DMUL + 3 DFMA.  No
+// denormal/huge-exponent slow path: r^2 of a physical configuration is a normal number, and
+// x = 0 (two distinct coincident bodies, eps2 = 0) yields NaN - the reference gives inf/NaN
+// there too (base.ml:77-80).
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  double t = x * y0;
+  double e = fma(-t, y0, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = e * y0;
+  return fma(p, q, y0);
+}
+
+// ---- sweep parameters ----------------------------------------------------------------------
+struct SweepParams {
+  const double *packed;  // [n_total][PK]
+  const double *aux;     // second packed array (tangent directions / unused)
+  int aux_stride;        // doubles between successive directions in aux
+  int K;                 // tangent directions
+  int t0, t1, s0, s1;
+  int n_it, n_jt;             // tiles along targets / sources
+  long long units;            // n_it * n_jt
+  long long units_per_cta;    // ceil(units / G)
+  double eps2, dt, eta;
+  double *partial;  // [2*G][NACC][TI]
+  double *out[4];   // op-specific outputs (device)
+  int accumulate;
+};
+
+// ---- pair operations -----------------------------------------------------------------------
+// Each op: NACC accumulators per target, Tgt = the target's registers, pair() = one
+// interaction with the source held in (a,b,c,d) = packed body as 4 double2, combine() for
+// the fix-up, store() = final write with the reference's sign/scale convention.
+
+// Base.grad_v summed (base.ml:73-80): acc = sum m_j (q_j - q_i) / s^3; gsum_i = -m_i acc.
+struct OpGradV {
+  static constexpr int NACC = 3;
+  static constexpr int ND2 = 2;  // double2 loads per source: (x,y) (z,m)
+  struct Tgt {
+    double x, y, z;
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+  }
+  __device__ __forceinline__ static void zero(double *acc) { acc[0] = acc[1] = acc[2] = 0.0; }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              bool self, const SweepParams &P) {
+    double2 a = sj[0], b = sj[1];
+    double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
+    double r2 = fma(dx, dx, P.eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double mj = b.y;
+    if (CHECK) {
+      r2 = self ? 1.0 : r2;
+      mj = self ? 0.0 : mj;
+    }
+    double y = rsqrt_nr(r2);
+    double w = (mj * y) * (y * y);
+    acc[0] = fma(w, dx, acc[0]);
+    acc[1] = fma(w, dy, acc[1]);
+    acc[2] = fma(w, dz, acc[2]);
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) {
+    a[0] += b[0];
+    a[1] += b[1];
+    a[2] += b[2];
+  }
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    double s = -P.packed[(size_t)ig * PK + 3];
+    double *o = P.out[0] + 3 * (size_t)(ig - P.t0);
+    for (int k = 0; k < 3; ++k) o[k] = P.accumulate ? o[k] + s * acc[k] : s * acc[k];
+  }
+};
+
+// Base.grad_v_dgrad_v summed (base.ml:91-110).  With d = q_j - q_i, u = v_j - v_i, v = p/m:
+//   acc  = sum m_j d / s^3                         gsum_i  = -m_i acc
+//   jerk = sum m_j (u - 3 (d.u) d / s^2) / s^3     dgsum_i = -m_i jerk
+// 6 DADD + 8 DMUL + 17 DFMA + 1 MUFU per interaction.
+struct OpGradVDGradV {
+  static constexpr int NACC = 6;
+  static constexpr int ND2 = 4;
+  struct Tgt {
+    double x, y, z, vx, vy, vz;
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+    t.vx = pk[4];
+    t.vy = pk[5];
+    t.vz = pk[6];
+  }
+  __device__ __forceinline__ static void zero(double *acc) {
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+  }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              bool self, const SweepParams &P) {
+    double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
+    double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
+    double ux = c.x - t.vx, uy = c.y - t.vy, uz = d.x - t.vz;
+    double r2 = fma(dx, dx, P.eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double rv = dx * ux;
+    rv = fma(dy, uy, rv);
+    rv = fma(dz, uz, rv);
+    double mj = b.y;
+    if (CHECK) {
+      r2 = self ? 1.0 : r2;
+      mj = self ? 0.0 : mj;
+    }
+    double y = rsqrt_nr(r2);
+    double y2 = y * y;
+    double w = (mj * y) * y2;
+    double a3 = (rv * y2) * -3.0;
+    acc[0] = fma(w, dx, acc[0]);
+    acc[1] = fma(w, dy, acc[1]);
+    acc[2] = fma(w, dz, acc[2]);
+    double tx = fma(a3, dx, ux), ty = fma(a3, dy, uy), tz = fma(a3, dz, uz);
+    acc[3] = fma(w, tx, acc[3]);
+    acc[4] = fma(w, ty, acc[4]);
+    acc[5] = fma(w, tz, acc[5]);
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) {
+    for (int k = 0; k < 6; ++k) a[k] += b[k];
+  }
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    double s = -P.packed[(size_t)ig * PK + 3];
+    double *g = P.out[0] + 3 * (size_t)(ig - P.t0);
+    double *dg = P.out[1] + 3 * (size_t)(ig - P.t0);
+    for (int k = 0; k < 3; ++k) {
+      g[k] = P.accumulate ? g[k] + s * acc[k] : s * acc[k];
+      dg[k] = P.accumulate ? dg[k] + s * acc[3 + k] : s * acc[3 + k];
+    }
+  }
+};
+
+// Base.v summed (base.ml:60-63): acc = sum m_j / s; phi_i = -m_i acc.
+struct OpV {
+  static constexpr int NACC = 1;
+  static constexpr int ND2 = 2;
+  struct Tgt {
+    double x, y, z;
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+  }
+  __device__ __forceinline__ static void zero(double *acc) { acc[0] = 0.0; }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              bool self, const SweepParams &P) {
+    double2 a = sj[0], b = sj[1];
+    double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
+    double r2 = fma(dx, dx, P.eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double mj = b.y;
+    if (CHECK) {
+      r2 = self ? 1.0 : r2;
+      mj = self ? 0.0 : mj;
+    }
+    acc[0] = fma(mj, rsqrt_nr(r2), acc[0]);
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) { a[0] += b[0]; }
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    double s = -P.packed[(size_t)ig * PK + 3];
+    double *o = P.out[0] + (size_t)(ig - P.t0);
+    o[0] = P.accumulate ? o[0] + s * acc[0] : s * acc[0];
+  }
+};
+
+// Leapfrog.kick summed (leapfrog.ml:70-104), pre-kick velocities.  The velocity half uses
+// the fast rsqrt (dv_i = dt * sum m_j d / r^3, unsoftened); the time-scale half repeats the
+// reference's IEEE operation sequence with correctly rounded sqrt/div and no contraction, so
+// each pair's tscale - and therefore the min - is bit-identical to the reference formula.
+template <bool WITH_TSCALE> struct OpKick {
+  static constexpr int NACC = WITH_TSCALE ? 4 : 3;
+  static constexpr int ND2 = WITH_TSCALE ? 4 : 2;
+  struct Tgt {
+    double x, y, z, vx, vy, vz, m;
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+    t.m = pk[3];
+    t.vx = pk[4];
+    t.vy = pk[5];
+    t.vz = pk[6];
+  }
+  __device__ __forceinline__ static void zero(double *acc) {
+    acc[0] = acc[1] = acc[2] = 0.0;
+    if (WITH_TSCALE) acc[3] = __longlong_as_double(0x7ff0000000000000LL);
+  }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              bool self, const SweepParams &P) {
+    double2 a = sj[0], b = sj[1];
+    double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
+    double r2e = __dmul_rn(dx, dx);
+    r2e = __dadd_rn(r2e, __dmul_rn(dy, dy));
+    r2e = __dadd_rn(r2e, __dmul_rn(dz, dz));  // leapfrog.ml:80 association
+    double mj = b.y;
+    double r2 = r2e;
+    if (CHECK) {
+      r2 = self ? 1.0 : r2;
+      mj = self ? 0.0 : mj;
+    }
+    double y = rsqrt_nr(r2);
+    double w = (mj * y) * (y * y);
+    acc[0] = fma(w, dx, acc[0]);
+    acc[1] = fma(w, dy, acc[1]);
+    acc[2] = fma(w, dz, acc[2]);
+    if (WITH_TSCALE) {
+      double2 c = sj[2], d = sj[3];
+      double ux = c.x - t.vx, uy = c.y - t.vy, uz = d.x - t.vz;
+      double vsq = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), __dmul_rn(uz, uz));
+      double vdr = __dadd_rn(__dadd_rn(__dmul_rn(dx, ux), __dmul_rn(dy, uy)), __dmul_rn(dz, uz));
+      double r = __dsqrt_rn(r2e);
+      double r3 = __dmul_rn(r2e, r);
+      double mtot = __dadd_rn(t.m, b.y);
+      double tff = __dmul_rn(P.eta, __dsqrt_rn(__ddiv_rn(r3, mtot)));
+      double tc = __dmul_rn(P.eta, __dsqrt_rn(__ddiv_rn(r2e, vsq)));
+      double svdr = __ddiv_rn(vdr, r2e);
+      double dtff = __dmul_rn(__dmul_rn(1.5, svdr), tff);
+      double dtc = __dmul_rn(__dmul_rn(svdr, tc),
+                             __dadd_rn(1.0, __ddiv_rn(mtot, __dmul_rn(vsq, r))));
+      tff = fabs(__ddiv_rn(tff, __dsub_rn(1.0, __dmul_rn(0.5, dtff))));
+      tc = fabs(__ddiv_rn(tc, __dsub_rn(1.0, __dmul_rn(0.5, dtc))));
+      double ts = (tff < tc) ? tff : tc;
+      bool skip = CHECK ? self : false;
+      if (!skip && acc[3] > ts) acc[3] = ts;  // NaN ts leaves acc[3] alone, leapfrog.ml:103
+    }
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) {
+    a[0] += b[0];
+    a[1] += b[1];
+    a[2] += b[2];
+    if (WITH_TSCALE)
+      if (a[3] > b[3]) a[3] = b[3];
+  }
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    double *o = P.out[0] + 3 * (size_t)(ig - P.t0);
+    for (int k = 0; k < 3; ++k) o[k] = P.dt * acc[k];
+    if (WITH_TSCALE) P.out[1][ig - P.t0] = acc[3];
+  }
+};
+
+// ---- the sweep kernel ----------------------------------------------------------------------
+template <class Op, int IPT> struct SweepCfg {
+  static constexpr int TI = NT * IPT;
+  static constexpr size_t smem_bytes = (size_t)STAGES * TJ * PK * sizeof(double) + 2 * STAGES * 8;
+};
+
+template <class Op, int IPT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
+  constexpr int TI = NT * IPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TJ * PK * 8);
+  uint64_t *empty = full + STAGES;
+
+  const int tid = threadIdx.x;
+  const long long u_begin = (long long)blockIdx.x * P.units_per_cta;
+  long long u_end = u_begin + P.units_per_cta;
+  if (u_end > P.units) u_end = P.units;
+  const int ntiles = (int)(u_end - u_begin);  // source tiles this CTA streams (>= 1)
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NT / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Producer side (thread 0): tile k of this CTA is unit u_begin+k -> source tile jt.
+  auto issue = [&](int k) {
+    long long u = u_begin + k;
+    int jt = (int)(u % P.n_jt);
+    int j0 = P.s0 + jt * TJ;
+    int cnt = min(TJ, P.s1 - j0);
+    int st = k % STAGES;
+    uint32_t bytes = (uint32_t)cnt * PK * 8;
+    mbar_arrive_expect_tx(&full[st], bytes);
+    tma_bulk_g2s(tiles + (size_t)st * TJ * PK, P.packed + (size_t)j0 * PK, bytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int k = 0; k < STAGES - 1 && k < ntiles; ++k) issue(k);
+  }
+
+  typename Op::Tgt tg[IPT];
+  double acc[IPT][Op::NACC];
+  int ig[IPT];
+  int seg_it = -1, seg_jt0 = 0;
+  const int head_it = (int)(u_begin / P.n_jt);
+
+  auto flush = [&](int it, int jt0, int jt_last) {
+    const bool complete = (jt0 == 0) && (jt_last == P.n_jt - 1);
+    if (complete) {
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        int i = P.t0 + it * TI + r * NT + tid;
+        if (i < P.t1) Op::store(P, i, acc[r]);
+      }
+    } else {
+      const int slot = 2 * blockIdx.x + (it == head_it ? 0 : 1);
+      double *dst = P.partial + (size_t)slot * Op::NACC * TI;
+#pragma unroll
+      for (int r = 0; r < IPT; ++r)
+#pragma unroll
+        for (int c = 0; c < Op::NACC; ++c) dst[c * TI + r * NT + tid] = acc[r][c];
+    }
+  };
+
+  for (int k = 0; k < ntiles; ++k) {
+    const long long u = u_begin + k;
+    const int it = (int)(u / P.n_jt);
+    const int jt = (int)(u - (long long)it * P.n_jt);
+    if (it != seg_it) {
+      if (seg_it >= 0) flush(seg_it, seg_jt0, P.n_jt - 1);
+      seg_it = it;
+      seg_jt0 = jt;
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        int i = P.t0 + it * TI + r * NT + tid;
+        ig[r] = i;
+        int ic = i < P.t1 ? i : P.t1 - 1;  // clamp: lanes past the end compute, never store
+        Op::load(tg[r], P.packed + (size_t)ic * PK, P);
+        Op::zero(acc[r]);
+      }
+    }
+    // keep STAGES-1 tiles in flight: refill the stage tile k-1 just vacated
+    if (tid == 0) {
+      int kk = k + STAGES - 1;
+      if (kk < ntiles) {
+        if (kk >= STAGES) mbar_wait(&empty[kk % STAGES], ((kk / STAGES) & 1) ^ 1);
+        issue(kk);
+      }
+    }
+    const int st = k % STAGES;
+    mbar_wait(&full[st], (k / STAGES) & 1);
+
+    const int j0 = P.s0 + jt * TJ;
+    const int cnt = min(TJ, P.s1 - j0);
+    const double2 *sj = reinterpret_cast<const double2 *>(tiles + (size_t)st * TJ * PK);
+    const int i_lo = P.t0 + it * TI;
+    const bool diag = (j0 < i_lo + TI) && (j0 + cnt > i_lo);
+    if (diag) {
+#pragma unroll 2
+      for (int jj = 0; jj < cnt; ++jj) {
+#pragma unroll
+        for (int r = 0; r < IPT; ++r)
+          Op::template pair<true>(tg[r], acc[r], sj + jj * (PK / 2), (j0 + jj) == ig[r], P);
+      }
+    } else {
+#pragma unroll 4
+      for (int jj = 0; jj < cnt; ++jj) {
+#pragma unroll
+        for (int r = 0; r < IPT; ++r)
+          Op::template pair<false>(tg[r], acc[r], sj + jj * (PK / 2), false, P);
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+  }
+  // last run: ends at the CTA's last unit
+  {
+    const long long ul = u_end - 1;
+    const int jt_last = (int)(ul - (long long)seg_it * P.n_jt);
+    flush(seg_it, seg_jt0, jt_last);
+  }
+}
+
+// Fix-up: combine, per i-tile, the partial slots of the CTAs that shared its source range,
+// in ascending CTA (= ascending source) order.  One thread per target.
+template <class Op, int IPT>
+__global__ void __launch_bounds__(NT *IPT) fixup_kernel(const SweepParams P) {
+  constexpr int TI = NT * IPT;
+  const int it = blockIdx.x;
+  const long long u_lo = (long long)it * P.n_jt, u_hi = u_lo + P.n_jt - 1;
+  const int c_lo = (int)(u_lo / P.units_per_cta), c_hi = (int)(u_hi / P.units_per_cta);
+  if (c_lo == c_hi) return;  // the tile ran complete inside one CTA: already stored
+  const int lane = threadIdx.x;
+  const int i = P.t0 + it * TI + lane;
+  if (i >= P.t1) return;
+  double acc[Op::NACC], part[Op::NACC];
+  Op::zero(acc);
+  for (int c = c_lo; c <= c_hi; ++c) {
+    const int head_it = (int)(((long long)c * P.units_per_cta) / P.n_jt);
+    const int slot = 2 * c + (it == head_it ? 0 : 1);
+    const double *src = P.partial + (size_t)slot * Op::NACC * TI;
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k) part[k] = src[k * TI + lane];
+    Op::combine(acc, part);
+  }
+  Op::store(P, i, acc);
+}
+
+// ---- O(N) helpers ----------------------------------------------------------------------------
+// Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
+// reference performs per pair (base.ml:93-97), done once per body.
+__global__ void pack_kernel(int n, const double *__restrict__ m, const double *__restrict__ q,
+                            const double *__restrict__ vel, int is_velocity,
+                            double *__restrict__ packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double mi = m[i];
+  double2 *o = reinterpret_cast<double2 *>(packed + (size_t)i * PK);
+  double vx = 0.0, vy = 0.0, vz = 0.0;
+  if (vel) {
+    vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+    if (!is_velocity) {
+      vx = __ddiv_rn(vx, mi);
+      vy = __ddiv_rn(vy, mi);
+      vz = __ddiv_rn(vz, mi);
+    }
+  }
+  o[0] = make_double2(q[3 * i], q[3 * i + 1]);
+  o[1] = make_double2(q[3 * i + 2], mi);
+  o[2] = make_double2(vx, vy);
+  o[3] = make_double2(vz, 0.0);
+}
+
+}  // namespace nbk

@@ -1,0 +1,308 @@
+"""nbk — Python (ctypes) binding of libnbk's C ABI (include/nbk.h).
+
+This is the harness-side mirror of what the OCaml `external` stubs of INTEGRATION.md bind: the
+same entry points, numpy arrays standing in for Bigarray.Array1 (float64, c_layout).  It is
+plumbing only — every sweep runs in the CUDA library; there is NO CPU fallback: if
+libnbk.so is missing or no B200 is visible, loading / `Context()` raises.
+
+Error convention follows the reference's (OCaml exceptions): a non-zero
+return code raises `NbkError` (the stub's `Failure (nbk_last_error ctx)`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libnbk.so")
+PACKED_DOUBLES = 8
+
+_d, _i, _f = C.c_double, C.c_int, C.c_float
+_pd = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/nbk.h declares.
+SYMBOLS = {
+    "nbk_create": (_i, [C.POINTER(_vp), _i]),
+    "nbk_destroy": (None, [_vp]),
+    "nbk_last_error": (C.c_char_p, [_vp]),
+    "nbk_version": (C.c_char_p, []),
+    "nbk_sm_count": (_i, [_vp]),
+    "nbk_launch_count": (C.c_int64, [_vp]),
+    "nbk_last_kernel_ms": (_i, [_vp, C.POINTER(_f)]),
+    "nbk_grad_v_sum": (_i, [_vp, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd]),
+    "nbk_grad_v_dgrad_v_sum": (_i, [_vp, _i, _pd, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_v_sum": (_i, [_vp, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_energy": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd, _pd]),
+    "nbk_kick_sum": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_grad_v_dgrad_v_sum_predicted": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d,
+                                              _i, _i, _i, _i, _pd, _pd]),
+    "nbk_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _i, _pd, _pd, _pd, _i, _pd, _pd, _d,
+                                            _i, _i, _i, _i, _pd, _pd, _pd, _pd]),
+    "nbk_grad_v_sum_tangent": (_i, [_vp, _i, _pd, _pd, _i, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_bodies_upload": (_i, [_vp, _i, _pd, _pd, _pd, _i]),
+    "nbk_bodies_update": (_i, [_vp, _i, _i, _pd, _pd, _i]),
+    "nbk_resident_count": (_i, [_vp]),
+    "nbk_resident_grad_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd]),
+    "nbk_resident_grad_v_dgrad_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_resident_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_resident_kick_sum": (_i, [_vp, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_dev_pack": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "nbk_dev_grad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_dev_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
+}
+
+
+class NbkError(RuntimeError):
+    """Raised on any non-zero libnbk return code (the OCaml stubs raise Failure)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libnbk error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen libnbk.so and declare every symbol of include/nbk.h.  Needs no GPU."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _arr(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        a = a.reshape(shape)
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_pd)
+
+
+class Context:
+    """One libnbk context = one GPU (nbk_create / nbk_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = _vp()
+        rc = self._lib.nbk_create(C.byref(h), device)
+        if rc != 0:
+            raise NbkError(rc, self._lib.nbk_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nbk_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NbkError(rc, self._lib.nbk_last_error(self._h).decode())
+
+    # -------------------------------------------------------------- info
+    @property
+    def sm_count(self):
+        return self._lib.nbk_sm_count(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.nbk_launch_count(self._h)
+
+    def last_kernel_ms(self):
+        ms = _f()
+        self._ck(self._lib.nbk_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def fp64_peak(self, iters=20000):
+        tf, ms = _d(), _f()
+        self._ck(self._lib.nbk_fp64_peak(self._h, iters, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+    # -------------------------------------------------------------- host-buffer sweeps
+    @staticmethod
+    def _rng(n, targets, sources):
+        t0, t1 = targets if targets is not None else (0, n)
+        s0, s1 = sources if sources is not None else (0, n)
+        return int(t0), int(t1), int(s0), int(s1)
+
+    def grad_v_sum(self, m, q, eps2=0.0, targets=None, sources=None):
+        m, q = _arr(m), _arr(q)
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        g = np.empty((max(t1 - t0, 0), 3))
+        self._ck(self._lib.nbk_grad_v_sum(self._h, n, _p(m), _p(q), eps2, t0, t1, s0, s1, _p(g)))
+        return g
+
+    def grad_v_dgrad_v_sum(self, m, q, p, eps2=0.0, targets=None, sources=None):
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        g, dg = np.empty((max(t1 - t0, 0), 3)), np.empty((max(t1 - t0, 0), 3))
+        self._ck(self._lib.nbk_grad_v_dgrad_v_sum(self._h, n, _p(m), _p(q), _p(p), eps2, t0, t1,
+                                                  s0, s1, _p(g), _p(dg)))
+        return g, dg
+
+    def v_sum(self, m, q, eps2=0.0, targets=None, sources=None, want_phi=True):
+        m, q = _arr(m), _arr(q)
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        phi = np.empty(max(t1 - t0, 0)) if want_phi else None
+        tot = _d()
+        self._ck(self._lib.nbk_v_sum(self._h, n, _p(m), _p(q), eps2, t0, t1, s0, s1, _p(phi),
+                                     C.byref(tot)))
+        return phi, tot.value
+
+    def energy(self, m, q, p, eps2=0.0):
+        """(ke, pe) = Energy.total_kinetic_energy, total_potential_energy (energy.ml:57-73)."""
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        ke, pe = _d(), _d()
+        self._ck(self._lib.nbk_energy(self._h, len(m), _p(m), _p(q), _p(p), eps2, C.byref(ke),
+                                      C.byref(pe)))
+        return ke.value, pe.value
+
+    def kick_sum(self, m, q, v, eta, dt, targets=None, sources=None, want_tmin=True):
+        m, q, v = _arr(m), _arr(q), _arr(v)
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        dv = np.empty((max(t1 - t0, 0), 3))
+        tmin = np.empty(max(t1 - t0, 0)) if want_tmin else None
+        self._ck(self._lib.nbk_kick_sum(self._h, n, _p(m), _p(q), _p(v), eta, dt, t0, t1, s0, s1,
+                                        _p(dv), _p(tmin)))
+        return dv, tmin
+
+    def grad_v_dgrad_v_sum_predicted(self, t, m, q, p, f, df, nt, eps2=0.0, targets=None,
+                                     sources=None):
+        t, m, q, p, f, df = (_arr(a) for a in (t, m, q, p, f, df))
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        g, dg = np.empty((max(t1 - t0, 0), 3)), np.empty((max(t1 - t0, 0), 3))
+        self._ck(self._lib.nbk_grad_v_dgrad_v_sum_predicted(
+            self._h, n, _p(t), _p(m), _p(q), _p(p), _p(f), _p(df), nt, eps2, t0, t1, s0, s1,
+            _p(g), _p(dg)))
+        return g, dg
+
+    def grad_v_dgrad_v_sum_tangent(self, m, q, p, dq, dp, eps2=0.0, targets=None, sources=None):
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        n = len(m)
+        dq, dp = _arr(dq).reshape(-1, n, 3), _arr(dp).reshape(-1, n, 3)
+        K = dq.shape[0]
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        nt = max(t1 - t0, 0)
+        g, dg = np.empty((nt, 3)), np.empty((nt, 3))
+        gt, dgt = np.empty((K, nt, 3)), np.empty((K, nt, 3))
+        self._ck(self._lib.nbk_grad_v_dgrad_v_sum_tangent(
+            self._h, n, _p(m), _p(q), _p(p), K, _p(dq), _p(dp), eps2, t0, t1, s0, s1, _p(g),
+            _p(dg), _p(gt), _p(dgt)))
+        return g, dg, gt, dgt
+
+    def grad_v_sum_tangent(self, m, q, dq, eps2=0.0, targets=None, sources=None):
+        m, q = _arr(m), _arr(q)
+        n = len(m)
+        dq = _arr(dq).reshape(-1, n, 3)
+        K = dq.shape[0]
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        nt = max(t1 - t0, 0)
+        g, gt = np.empty((nt, 3)), np.empty((K, nt, 3))
+        self._ck(self._lib.nbk_grad_v_sum_tangent(self._h, n, _p(m), _p(q), K, _p(dq), eps2, t0,
+                                                  t1, s0, s1, _p(g), _p(gt)))
+        return g, gt
+
+    # -------------------------------------------------------------- resident bodies
+    def bodies_upload(self, m, q, vel, is_velocity=False):
+        m, q = _arr(m), _arr(q)
+        vel = None if vel is None else _arr(vel)
+        self._ck(self._lib.nbk_bodies_upload(self._h, len(m), _p(m), _p(q), _p(vel),
+                                             int(is_velocity)))
+
+    def bodies_update(self, i0, i1, q, vel, is_velocity=False):
+        q = _arr(q)
+        vel = None if vel is None else _arr(vel)
+        self._ck(self._lib.nbk_bodies_update(self._h, i0, i1, _p(q), _p(vel), int(is_velocity)))
+
+    @property
+    def resident_count(self):
+        return self._lib.nbk_resident_count(self._h)
+
+    def resident_grad_v_sum(self, eps2=0.0, targets=None, sources=None):
+        t0, t1, s0, s1 = self._rng(self.resident_count, targets, sources)
+        g = np.empty((max(t1 - t0, 0), 3))
+        self._ck(self._lib.nbk_resident_grad_v_sum(self._h, eps2, t0, t1, s0, s1, _p(g)))
+        return g
+
+    def resident_grad_v_dgrad_v_sum(self, eps2=0.0, targets=None, sources=None):
+        t0, t1, s0, s1 = self._rng(self.resident_count, targets, sources)
+        g, dg = np.empty((max(t1 - t0, 0), 3)), np.empty((max(t1 - t0, 0), 3))
+        self._ck(self._lib.nbk_resident_grad_v_dgrad_v_sum(self._h, eps2, t0, t1, s0, s1, _p(g),
+                                                           _p(dg)))
+        return g, dg
+
+    def resident_v_sum(self, eps2=0.0, targets=None, sources=None, want_phi=True):
+        t0, t1, s0, s1 = self._rng(self.resident_count, targets, sources)
+        phi = np.empty(max(t1 - t0, 0)) if want_phi else None
+        tot = _d()
+        self._ck(self._lib.nbk_resident_v_sum(self._h, eps2, t0, t1, s0, s1, _p(phi),
+                                              C.byref(tot)))
+        return phi, tot.value
+
+    def resident_kick_sum(self, eta, dt, targets=None, sources=None, want_tmin=True):
+        t0, t1, s0, s1 = self._rng(self.resident_count, targets, sources)
+        dv = np.empty((max(t1 - t0, 0), 3))
+        tmin = np.empty(max(t1 - t0, 0)) if want_tmin else None
+        self._ck(self._lib.nbk_resident_kick_sum(self._h, eta, dt, t0, t1, s0, s1, _p(dv),
+                                                 _p(tmin)))
+        return dv, tmin
+
+    # -------------------------------------------------------------- raw device pointers
+    # Arguments are integer device addresses (e.g. torch.Tensor.data_ptr()) and an integer
+    # cudaStream_t (torch.cuda.current_stream().cuda_stream); 0 = the context's own stream.
+    def dev_pack(self, n, d_m, d_q, d_vel, is_velocity, d_packed, stream=0):
+        self._ck(self._lib.nbk_dev_pack(self._h, n, d_m, d_q, d_vel or None, int(is_velocity),
+                                        d_packed, stream or None))
+
+    def dev_grad_v_dgrad_v_sum(self, d_packed, n_total, eps2, targets, sources, d_gsum, d_dgsum,
+                               accumulate=False, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum(self._h, d_packed, n_total, eps2, t0, t1,
+                                                      s0, s1, d_gsum, d_dgsum, int(accumulate),
+                                                      stream or None))
+
+    def dev_grad_v_sum(self, d_packed, n_total, eps2, targets, sources, d_gsum, accumulate=False,
+                       stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_sum(self._h, d_packed, n_total, eps2, t0, t1, s0, s1,
+                                              d_gsum, int(accumulate), stream or None))
+
+    def dev_v_sum(self, d_packed, n_total, eps2, targets, sources, d_phi, accumulate=False,
+                  stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_v_sum(self._h, d_packed, n_total, eps2, t0, t1, s0, s1, d_phi,
+                                         int(accumulate), stream or None))

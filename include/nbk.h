@@ -1,0 +1,178 @@
+/* nbk.h — C ABI of libnbk, the B200 (sm_100a) implementation of farr/direct-nbody's O(N^2)
+ * pairwise-gravity hot path.
+ *
+ * The reference (100 % OCaml, /root/reference) has no FFI boundary: its pair functions
+ * Base.v / Base.grad_v / Base.grad_v_dgrad_v (base.ml:60-110) and Leapfrog.kick
+ * (leapfrog.ml:70-104) are called once per pair from double loops inside each integrator.
+ * A per-pair FFI is useless for a GPU, so this ABI hoists the boundary to the LOOP: every
+ * entry point below replaces one of the reference's pair loops and is what an OCaml
+ * `external` stub over Bigarray.Array1 (float64, c_layout) binds (INTEGRATION.md shows the
+ * stubs).  Plain pointers and sizes only; no CUDA, torch or C++ types.
+ *
+ * Array conventions (all caller-owned, contiguous, IEEE binary64):
+ *   m[n]   masses            (B.m b)
+ *   q[3n]  positions,  q[3*i+k] = (B.q b_i).(k)
+ *   p[3n]  momenta,    p[3*i+k] = (B.p b_i).(k)      (Leapfrog: v[3n] velocities)
+ * A sweep works on TARGETS i in [t0,t1) and SOURCES j in [s0,s1), both index ranges into the
+ * same body array; a body never interacts with itself (excluded BY INDEX, so eps2 = 0 works
+ * and two distinct coincident bodies still give inf/NaN like the reference).  Outputs are
+ * indexed from the first target: out[3*(i-t0)+k].
+ *
+ * Sums are accumulated on the GPU in a fixed, run-to-run reproducible order that differs from
+ * the reference's ascending-j order; results agree with the reference arithmetic to <= 1e-12
+ * relative per body (tests/), not bit for bit.  Exception: nbk_kick_sum's tmin, a min over
+ * pair values computed with the reference's exact IEEE operation sequence, is bit-exact
+ * against the pre-kick-velocity evaluation of leapfrog.ml:94-104.
+ *
+ * Errors: every function returns NBK_OK (0) or a negative code; nbk_last_error gives text.
+ * An OCaml stub raises Failure (nbk_last_error ctx) on non-zero (the reference's error
+ * convention is exceptions).  The library never retains caller pointers past
+ * a call, never calls back, and assumes one calling thread per context.
+ * There is NO CPU fallback: without a CUDA device nbk_create fails with NBK_ERR_CUDA.
+ */
+#ifndef NBK_H
+#define NBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBK_OK 0
+#define NBK_ERR_ARG (-1)   /* bad argument (null pointer, bad range, n too large) */
+#define NBK_ERR_CUDA (-2)  /* CUDA runtime error (text in nbk_last_error) */
+#define NBK_ERR_NOMEM (-3) /* host or device allocation failed */
+#define NBK_ERR_STATE (-4) /* call sequence error (e.g. no resident bodies uploaded) */
+
+typedef struct nbk_ctx nbk_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+
+/* Creates a context bound to CUDA device `device` (ordinal).  Owns one stream, all device
+ * workspaces and pinned staging buffers; they grow on demand. */
+int nbk_create(nbk_ctx **ctx, int device);
+void nbk_destroy(nbk_ctx *ctx);
+/* Text of the last error on ctx; with ctx == NULL, of the last failed nbk_create. */
+const char *nbk_last_error(const nbk_ctx *ctx);
+const char *nbk_version(void);
+/* Number of SMs, and kernel launches issued by this context so far (bench.py's gpu_launches). */
+int nbk_sm_count(const nbk_ctx *ctx);
+int64_t nbk_launch_count(const nbk_ctx *ctx);
+/* Device time in ms of the most recent sweep's dominant kernel (CUDA events on the context's
+ * stream, recorded around the sweep kernel + fix-up only). */
+int nbk_last_kernel_ms(nbk_ctx *ctx, float *ms);
+
+/* ---- host-buffer sweeps: one call = one reference pair loop ------------------------------- */
+
+/* gsum[3*(i-t0)+k] = sum_{j in [s0,s1), j != i} (Base.grad_v m_i q_i m_j q_j).(k)
+ * Replaces the Base.grad_v loops of Omelyan_advancer.OA.b_operate / c_operate
+ * (omelyan_advancer.ml:44-56, 67-94) and Advancer.A.interact_bodies (advancer.ml:207-236):
+ * grad_v is antisymmetric bit for bit, so the reference's symmetric i<j loop equals these
+ * per-target sums. */
+int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2, int t0,
+                   int t1, int s0, int s1, double *gsum);
+
+/* gsum, dgsum = sum_{j != i} Base.grad_v_dgrad_v m_i q_i p_i m_j q_j p_j  (base.ml:91-110).
+ * Replaces Hermite.start_bs' pair loop (hermite.ml:154-167: f_i = -gsum_i, df_i = -dgsum_i)
+ * and Advancer.A.initialize_before_first_step's (advancer.ml:369-393).  THE METRIC KERNEL. */
+int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q,
+                           const double *p, double eps2, int t0, int t1, int s0, int s1,
+                           double *gsum, double *dgsum);
+
+/* phi[i-t0] = sum_{j in [s0,s1), j != i} Base.v m_i q_i m_j q_j  (base.ml:60-63); the `pe`
+ * accumulator of Analysis.bodies_to_el_phase_space (analysis.ml:909-914).  phi may be NULL.
+ * If total != NULL, *total = sum_i phi[i] (so Energy.total_potential_energy, energy.ml:66-73,
+ * is 0.5 * total for t = s = [0,n)). */
+int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2, int t0, int t1,
+              int s0, int s1, double *phi, double *total);
+
+/* Energy.Make(B).total_kinetic_energy / total_potential_energy (energy.ml:57-73): *ke and
+ * *pe (either may be NULL; p may be NULL when ke is).  energy = *ke + *pe (energy.ml:75-78). */
+int nbk_energy(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+               double eps2, double *ke, double *pe);
+
+/* Leapfrog.kick (leapfrog.ml:70-104) summed over sources, every pair evaluated from the
+ * velocities at call time ("pre-kick" order).  For target i:
+ *   dv[3*(i-t0)+k] = sum_j (m_j * (dt / r^3)) * (q_j - q_i).(k)     (unsoftened, :83-90)
+ *   tmin[i-t0]     = min_j tscale(i,j)  (leapfrog.ml:94-104; NaN ignored; +inf if no source)
+ * tmin may be NULL (and eta is then unused): the eta = infinity fast path of
+ * Leapfrog.advance_const_dt (leapfrog.ml:160-165).  Replaces the kick loops
+ * leapfrog.ml:132-136 and :151-155. */
+int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const double *v,
+                 double eta, double dt, int t0, int t1, int s0, int s1, double *dv,
+                 double *tmin);
+
+/* Hermite.advance_body's loop (hermite.ml:106-115): every body is first predicted to time
+ * `nt` (predict_position_into / predict_momentum_into, hermite.ml:53-72) from its own
+ * (t,q,p,f,df), then gsum/dgsum as in nbk_grad_v_dgrad_v_sum over the predicted bodies
+ * (fp = -gsum, dfp = -dgsum).  t[n], f[3n], df[3n] as in Hermite.b (hermite.ml:20-29). */
+int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int n, const double *t, const double *m,
+                                     const double *q, const double *p, const double *f,
+                                     const double *df, double nt, double eps2, int t0, int t1,
+                                     int s0, int s1, double *gsum, double *dgsum);
+
+/* Tangent (first-order forward-mode) of nbk_grad_v_dgrad_v_sum for K directions:
+ * DFloatBase.grad_v_dgrad_v (dFloat_advancer.ml:66-81) accumulated as in
+ * DFloat_hermite.start_bs (dFloat_hermite.ml:177-186).  dq, dp are [K][3n] (direction
+ * major); masses and eps2 carry no tangent (dFloat_hermite.ml:36-46).  Outputs: value sums
+ * gsum, dgsum [3*nt] (either may be NULL) and tangent sums gsum_tan, dgsum_tan [K][3*nt]. */
+int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q,
+                                   const double *p, int K, const double *dq, const double *dp,
+                                   double eps2, int t0, int t1, int s0, int s1, double *gsum,
+                                   double *dgsum, double *gsum_tan, double *dgsum_tan);
+
+/* Tangent of nbk_grad_v_sum (DFloatBase.grad_v, dFloat_advancer.ml:57-64). */
+int nbk_grad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q, int K,
+                           const double *dq, double eps2, int t0, int t1, int s0, int s1,
+                           double *gsum, double *gsum_tan);
+
+/* ---- device-resident bodies: small-active-set callers keep the N bodies on the GPU -------- */
+
+/* Uploads and packs n bodies; `vel` is momenta (is_velocity = 0, the BODY convention) or
+ * velocities (is_velocity = 1, the Leapfrog.b convention, leapfrog.ml:5-12). */
+int nbk_bodies_upload(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
+                      int is_velocity);
+/* Overwrites bodies [i0,i1) (q and vel are [3*(i1-i0)]; masses unchanged). */
+int nbk_bodies_update(nbk_ctx *ctx, int i0, int i1, const double *q, const double *vel,
+                      int is_velocity);
+int nbk_resident_count(const nbk_ctx *ctx);
+int nbk_resident_grad_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1,
+                            double *gsum);
+int nbk_resident_grad_v_dgrad_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1,
+                                    double *gsum, double *dgsum);
+int nbk_resident_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1, double *phi,
+                       double *total);
+int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, int s0, int s1,
+                          double *dv, double *tmin);
+
+/* ---- raw device-pointer API (one rank of a multi-GPU job; bench.py / torch harness) ------- */
+
+/* A packed body is 8 doubles {x, y, z, m, vx, vy, vz, 0} (64 B): the layout j-tiles are
+ * bulk-copied into shared memory in.  All pointers are device pointers on ctx's device;
+ * `stream` is a cudaStream_t cast to void* (NULL = the context's own stream). */
+#define NBK_PACKED_DOUBLES 8
+int nbk_dev_pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, const double *d_vel,
+                 int is_velocity, double *d_packed, void *stream);
+/* Targets are d_packed[t0..t1), sources d_packed[s0..s1) of one array of n_total packed
+ * bodies (after an all-gather: the full system; targets = this rank's shard).
+ * accumulate != 0 adds onto d_gsum / d_dgsum instead of overwriting (used to split one sweep
+ * into a local-sources part overlapped with the all-gather and a remote-sources part). */
+int nbk_dev_grad_v_dgrad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2,
+                               int t0, int t1, int s0, int s1, double *d_gsum, double *d_dgsum,
+                               int accumulate, void *stream);
+int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0,
+                       int t1, int s0, int s1, double *d_gsum, int accumulate, void *stream);
+int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0, int t1,
+                  int s0, int s1, double *d_phi, int accumulate, void *stream);
+
+/* FP64 DFMA-throughput microbenchmark on ctx's device (the measured FP64 peak the roofline
+ * fraction is quoted against): runs `iters` dependent-chain-free DFMA per thread on a full
+ * grid; returns TFLOP/s (2 flop per DFMA) in *tflops and the kernel time in *ms. */
+int nbk_fp64_peak(nbk_ctx *ctx, int iters, double *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBK_H */

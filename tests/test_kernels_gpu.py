@@ -1,0 +1,146 @@
+"""GPU parity of the sweep kernels, through the C ABI, against the oracle on the same seeded
+inputs.  Tolerance: north_star's 1e-12 relative per body (|x_gpu - x_ref|_2 / |x_ref|_2);
+integer-like outputs (the kick's min time-scale) are bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def rel_err(a, b):
+    num = np.linalg.norm(a - b, axis=-1)
+    den = np.linalg.norm(b, axis=-1)
+    return float(np.max(num / den))
+
+
+@pytest.mark.parametrize("n", [2, 3, 257, 1024, 4096])
+@pytest.mark.parametrize("eps", [0.0, 0.04, 0.4])
+def test_grad_v_dgrad_v_sum_matches_oracle(ctx, oracle, n, eps):
+    m, q, p = oracle.make_plummer(n, 20243)
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, eps * eps)
+    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps * eps)
+    assert rel_err(g, g_ref) <= TOL
+    assert rel_err(dg, dg_ref) <= TOL
+
+
+@pytest.mark.parametrize("n", [2, 3, 257, 1024, 4096])
+@pytest.mark.parametrize("eps", [0.0, 0.04, 0.4])
+def test_grad_v_sum_matches_oracle(ctx, oracle, n, eps):
+    m, q, p = oracle.make_plummer(n, 20241)
+    g_ref = oracle.grad_v_sum(m, q, eps * eps)
+    g = ctx.grad_v_sum(m, q, eps * eps)
+    assert rel_err(g, g_ref) <= TOL
+
+
+@pytest.mark.parametrize("n", [2, 3, 257, 1024, 4096])
+@pytest.mark.parametrize("eps", [0.0, 0.04])
+def test_v_sum_and_energy_match_oracle(ctx, oracle, n, eps):
+    m, q, p = oracle.make_plummer(n, 20244)
+    phi_ref = oracle.v_sum(m, q, eps * eps)
+    phi, tot = ctx.v_sum(m, q, eps * eps)
+    assert np.max(np.abs(phi - phi_ref) / np.abs(phi_ref)) <= TOL
+    pe_ref = oracle.total_potential_energy(m, q, eps * eps)
+    ke_ref = oracle.total_kinetic_energy(m, p)
+    ke, pe = ctx.energy(m, q, p, eps * eps)
+    assert abs(pe - pe_ref) <= TOL * abs(pe_ref)
+    assert abs(0.5 * tot - pe_ref) <= TOL * abs(pe_ref)
+    assert abs(ke - ke_ref) <= TOL * abs(ke_ref)
+
+
+@pytest.mark.parametrize("n", [2, 3, 257, 1024])
+def test_kick_sum_matches_oracle(ctx, oracle, n):
+    m, q, p = oracle.make_hot_spherical(n, 20242)
+    v = p / m[:, None]
+    for eta, dt in [(1e-3, 1e-4), (1e-3, 0.0), (np.inf, 1e-4)]:
+        dv_ref, tmin_ref = oracle.kick_sum(m, q, v, eta, dt)
+        dv, tmin = ctx.kick_sum(m, q, v, eta, dt)
+        if dt != 0.0:
+            assert rel_err(dv, dv_ref) <= TOL
+        else:
+            assert not dv.any()
+        # min over pairs of the reference's exact IEEE sequence: bit-exact
+        assert np.array_equal(tmin, tmin_ref)
+        dv2, none = ctx.kick_sum(m, q, v, eta, dt, want_tmin=False)
+        assert none is None and np.array_equal(dv2, dv)
+
+
+@pytest.mark.parametrize("ranges", [((0, 1), (0, 1000)), ((5, 6), (0, 1000)), ((0, 1000), (17, 18)),
+                                    ((100, 400), (0, 1000)), ((0, 1000), (300, 900)),
+                                    ((250, 260), (255, 700)), ((0, 0), (0, 1000)),
+                                    ((0, 1000), (40, 40)), ((999, 1000), (0, 999))])
+def test_rectangular_ranges(ctx, oracle, ranges):
+    """targets x sources rectangles incl. single targets, empty ranges and self-overlap."""
+    tg, sr = ranges
+    m, q, p = oracle.make_plummer(1000, 7)
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
+    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
+    assert g.shape == g_ref.shape
+    if g.size and sr[1] > sr[0]:
+        scale = np.linalg.norm(g_ref, axis=1).max()
+        assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * scale
+        scale = np.linalg.norm(dg_ref, axis=1).max()
+        assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * scale
+    else:
+        assert not g.any() and not dg.any()
+    phi_ref = oracle.v_sum(m, q, 0.0, targets=tg, sources=sr)
+    phi, tot = ctx.v_sum(m, q, 0.0, targets=tg, sources=sr)
+    assert np.allclose(phi, phi_ref, rtol=TOL, atol=0.0)
+
+
+def test_run_to_run_reproducible(ctx, oracle):
+    m, q, p = oracle.make_plummer(3000, 11)
+    a = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    b = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_coincident_bodies_give_nonfinite_like_reference(ctx, oracle):
+    m, q, p = oracle.make_plummer(64, 3)
+    q[5] = q[9]
+    g_ref, _ = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    g, _ = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    bad_ref = ~np.isfinite(g_ref).all(axis=1)
+    bad = ~np.isfinite(g).all(axis=1)
+    assert bad_ref[5] and bad_ref[9] and bad_ref.sum() == 2
+    assert np.array_equal(bad, bad_ref)
+
+
+def test_momentum_conservation_full_size(ctx, oracle):
+    """Size-independent property at a size the oracle cannot sweep in seconds: sum_i gsum_i = 0
+    and sum_i dgsum_i = 0 (Newton's third law), relative to sum_i |gsum_i|."""
+    n = 32768
+    m, q, p = oracle.make_plummer(n, 5)
+    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    assert np.linalg.norm(g.sum(0)) <= 1e-12 * np.linalg.norm(g, axis=1).sum()
+    assert np.linalg.norm(dg.sum(0)) <= 1e-12 * np.linalg.norm(dg, axis=1).sum()
+    # and a sampled slice against the oracle
+    sl = (12345, 12345 + 64)
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=sl)
+    assert rel_err(g[sl[0]:sl[1]], g_ref) <= TOL
+    assert rel_err(dg[sl[0]:sl[1]], dg_ref) <= TOL
+
+
+def test_resident_bodies_and_update(ctx, oracle):
+    m, q, p = oracle.make_plummer(2000, 13)
+    ctx.bodies_upload(m, q, p)
+    g, dg = ctx.resident_grad_v_dgrad_v_sum(0.0, targets=(10, 20))
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(10, 20))
+    assert rel_err(g, g_ref) <= TOL and rel_err(dg, dg_ref) <= TOL
+    q2, p2 = q.copy(), p.copy()
+    q2[100:110] += 0.01
+    p2[100:110] *= 1.1
+    ctx.bodies_update(100, 110, q2[100:110], p2[100:110])
+    g, dg = ctx.resident_grad_v_dgrad_v_sum(0.0, targets=(95, 115))
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q2, p2, 0.0, targets=(95, 115))
+    assert rel_err(g, g_ref) <= TOL and rel_err(dg, dg_ref) <= TOL
+
+
+def test_argument_errors_raise(ctx, oracle):
+    import nbk
+    m, q, p = oracle.make_plummer(16, 1)
+    with pytest.raises(nbk.NbkError):
+        ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(0, 17))
+    with pytest.raises(nbk.NbkError):
+        ctx.grad_v_sum(m, q, 0.0, sources=(5, 3))
