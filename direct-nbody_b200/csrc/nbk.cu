@@ -29,6 +29,7 @@ struct nbk_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int64_t launches = 0;
+  int shape = 0;
   std::string err;
   // device workspaces
   DevBuf d_m, d_q, d_vel, d_aux_in, d_packed, d_aux, d_partial, d_out[4], d_scalar;
@@ -88,15 +89,15 @@ int check_ranges(nbk_ctx *ctx, int n, int t0, int t1, int s0, int s1) {
 }
 
 // ---- sweep launcher --------------------------------------------------------------------------
-template <class Op, int IPT, int MINB> struct Launcher {
+template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
   static int occupancy(nbk_ctx *ctx, int *occ) {
     static int cached = -1;
     if (cached < 0) {
-      constexpr size_t smem = SweepCfg<Op, IPT>::smem_bytes;
-      CK(cudaFuncSetAttribute(sweep_kernel<Op, IPT, MINB>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      auto kern = sweep_kernel<Op, NT, IPT, MINB, UNROLL>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)SWEEP_SMEM_BYTES));
       int o = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sweep_kernel<Op, IPT, MINB>, NT, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NT, SWEEP_SMEM_BYTES));
       if (o < 1) return fail(ctx, NBK_ERR_CUDA, "sweep kernel does not fit on an SM");
       cached = o;
     }
@@ -109,11 +110,11 @@ template <class Op, int IPT, int MINB> struct Launcher {
     constexpr int TI = NT * IPT;
     const int nt = P.t1 - P.t0, ns = P.s1 - P.s0;
     if (nt == 0) return NBK_OK;
+    if (ns == 0) return fail(ctx, NBK_ERR_ARG, "empty source range");
     int occ = 0;
     TRY(occupancy(ctx, &occ));
     P.n_it = (nt + TI - 1) / TI;
     P.n_jt = (ns + TJ - 1) / TJ;
-    if (P.n_jt == 0) return fail(ctx, NBK_ERR_ARG, "empty source range");
     P.units = (long long)P.n_it * P.n_jt;
     long long G = (long long)ctx->sm_count * occ;
     if (G > P.units) G = P.units;
@@ -122,12 +123,11 @@ template <class Op, int IPT, int MINB> struct Launcher {
     TRY(reserve(ctx, ctx->d_partial, (size_t)2 * G * Op::NACC * TI * sizeof(double)));
     P.partial = (double *)ctx->d_partial.p;
     if (time_it) CK(cudaEventRecord(ctx->ev0, st));
-    sweep_kernel<Op, IPT, MINB>
-        <<<(unsigned)G, NT, SweepCfg<Op, IPT>::smem_bytes, st>>>(P);
+    sweep_kernel<Op, NT, IPT, MINB, UNROLL><<<(unsigned)G, NT, SWEEP_SMEM_BYTES, st>>>(P);
     CK(cudaGetLastError());
     ctx->launches++;
     if (P.units_per_cta % P.n_jt != 0) {  // some i-tile's sources are split over CTAs
-      fixup_kernel<Op, IPT><<<P.n_it, TI, 0, st>>>(P);
+      fixup_kernel<Op, TI><<<P.n_it, TI, 0, st>>>(P);
       CK(cudaGetLastError());
       ctx->launches++;
     }
@@ -139,11 +139,50 @@ template <class Op, int IPT, int MINB> struct Launcher {
   }
 };
 
-using K1 = Launcher<OpGradV, 2, 4>;
-using K2 = Launcher<OpGradVDGradV, 2, 4>;
-using K3 = Launcher<OpV, 2, 4>;
-using K4 = Launcher<OpKick<false>, 2, 4>;
-using K4T = Launcher<OpKick<true>, 2, 3>;
+// Tile shapes.  "large": 1 CTA/SM of 256 threads x 4 targets each - two
+// warps per scheduler, so consecutive FMAs of one warp issue back to back and the operand reuse
+// cache works, and one source is fetched from shared memory once per 4 interactions.
+// "medium"/"small" trade that for less padding when there are few targets.
+enum Shape { SHAPE_AUTO = 0, SHAPE_LARGE = 1, SHAPE_MEDIUM = 2, SHAPE_SMALL = 3 };
+
+int pick_shape(const nbk_ctx *ctx, int nt) {
+  if (ctx->shape != SHAPE_AUTO) return ctx->shape;
+  auto waste = [&](int ti) {
+    int padded = (nt + ti - 1) / ti * ti;
+    return (double)(padded - nt) / (double)padded;
+  };
+  if (nt >= 2048 && waste(1024) <= 0.125) return SHAPE_LARGE;
+  if (nt >= 256 && waste(256) <= 0.25) return SHAPE_MEDIUM;
+  return SHAPE_SMALL;
+}
+
+template <class Op>
+int run_op(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  switch (pick_shape(ctx, P.t1 - P.t0)) {
+    case SHAPE_LARGE: return Launcher<Op, 256, 4, 1, 4>::run(ctx, P, st, time_it);
+    case SHAPE_MEDIUM: return Launcher<Op, 128, 2, 4, 4>::run(ctx, P, st, time_it);
+    default: return Launcher<Op, 128, 1, 6, 4>::run(ctx, P, st, time_it);
+  }
+}
+
+// The time-scale kick is register-hungry (IEEE sqrt/div sequences): smaller shapes.
+template <>
+int run_op<OpKick<true>>(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  switch (pick_shape(ctx, P.t1 - P.t0)) {
+    case SHAPE_LARGE:
+    case SHAPE_MEDIUM: return Launcher<OpKick<true>, 128, 2, 3, 2>::run(ctx, P, st, time_it);
+    default: return Launcher<OpKick<true>, 128, 1, 4, 2>::run(ctx, P, st, time_it);
+  }
+}
+
+struct K1 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpGradV>(c, P, s, t); } };
+struct K3 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpV>(c, P, s, t); } };
+struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<false>>(c, P, s, t); } };
+struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<true>>(c, P, s, t); } };
+
+int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  return run_op<OpGradVDGradVB<1>>(ctx, P, st, time_it);
+}
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
 __global__ void zero_kernel(double *p, size_t n) {
@@ -286,7 +325,7 @@ int run_grad_v_dgrad_v(nbk_ctx *ctx, const double *packed, double eps2, int t0, 
     SweepParams P = base_params(packed, eps2, t0, t1, s0, s1);
     P.out[0] = (double *)ctx->d_out[0].p;
     P.out[1] = (double *)ctx->d_out[1].p;
-    TRY(K2::run(ctx, P, ctx->stream, true));
+    TRY(run_k2(ctx, P, ctx->stream, true));
   }
   TRY(download(ctx, gsum, ctx->d_out[0], 3 * nt));
   TRY(download(ctx, dgsum, ctx->d_out[1], 3 * nt));
@@ -600,8 +639,7 @@ int nbk_dev_pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, cons
   if (n < 0 || !d_m || !d_q || !d_packed || ((uintptr_t)d_packed & 15))
     return fail(ctx, NBK_ERR_ARG, "nbk_dev_pack: bad arguments (d_packed must be 16-byte aligned)");
   CK(cudaSetDevice(ctx->device));
-  return pack(ctx, n, d_m, d_q, d_vel, is_velocity, d_packed,
-              stream ? (cudaStream_t)stream : ctx->stream);
+  return pack(ctx, n, d_m, d_q, d_vel, is_velocity, d_packed, (cudaStream_t)stream);
 }
 
 #define DEV_COMMON()                                                                     \
@@ -622,8 +660,8 @@ int nbk_dev_grad_v_dgrad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total
   P.out[0] = d_gsum;
   P.out[1] = d_dgsum;
   P.accumulate = accumulate;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return K2::run(ctx, P, st, false);
+  cudaStream_t st = (cudaStream_t)stream;
+  return run_k2(ctx, P, st, false);
 }
 
 int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0,
@@ -633,7 +671,7 @@ int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double
   SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
   P.out[0] = d_gsum;
   P.accumulate = accumulate;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = (cudaStream_t)stream;
   return K1::run(ctx, P, st, false);
 }
 
@@ -644,8 +682,15 @@ int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2
   SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
   P.out[0] = d_phi;
   P.accumulate = accumulate;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st = (cudaStream_t)stream;
   return K3::run(ctx, P, st, false);
+}
+
+int nbk_tune(nbk_ctx *ctx, int variant) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (variant < 0 || variant > 3) return fail(ctx, NBK_ERR_ARG, "nbk_tune: no shape %d", variant);
+  ctx->shape = variant;
+  return NBK_OK;
 }
 
 int nbk_fp64_peak(nbk_ctx *ctx, int iters, double *tflops, float *ms) {

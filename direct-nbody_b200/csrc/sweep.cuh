@@ -21,7 +21,6 @@
 namespace nbk {
 
 constexpr int PK = 8;            // doubles per packed body {x,y,z,m,vx,vy,vz,0}
-constexpr int NT = 128;          // threads per CTA
 constexpr int TJ = 128;          // sources per tile (8 KB per stage)
 constexpr int STAGES = 3;
 
@@ -325,13 +324,117 @@ template <bool WITH_TSCALE> struct OpKick {
   }
 };
 
-// ---- the sweep kernel ----------------------------------------------------------------------
-template <class Op, int IPT> struct SweepCfg {
-  static constexpr int TI = NT * IPT;
-  static constexpr size_t smem_bytes = (size_t)STAGES * TJ * PK * sizeof(double) + 2 * STAGES * 8;
+// One source against the IPT targets of a thread.  Ops may provide a batched form
+// (Op::BATCHED) that walks the IPT interactions phase by phase, so that the instruction
+// stream handed to ptxas already interleaves independent interactions and keeps FMAs that
+// share a register operand adjacent ("operand bandwidth").
+template <class Op, class = void> struct has_batched { static constexpr bool value = false; };
+template <class Op> struct has_batched<Op, decltype((void)Op::BATCHED)> {
+  static constexpr bool value = true;
 };
 
-template <class Op, int IPT, int MINB>
+template <class Op, bool CHECK, int IPT>
+__device__ __forceinline__ void pairs(const typename Op::Tgt (&tg)[IPT],
+                                      double (&acc)[IPT][Op::NACC], const double2 *sj, int jg,
+                                      const int (&ig)[IPT], const SweepParams &P) {
+  if constexpr (has_batched<Op>::value) {
+    Op::template pairs<CHECK, IPT>(tg, acc, sj, jg, ig, P);
+  } else {
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) Op::template pair<CHECK>(tg[r], acc[r], sj, jg == ig[r], P);
+  }
+}
+
+// Batched acc+jerk: same arithmetic as OpGradVDGradV::pair except the last rsqrt step is
+// y = y0 + y0 (e p) (two distinct register operands) instead of y0 + p (e y0).
+template <int FLAVOUR> struct OpGradVDGradVB : OpGradVDGradV {
+  static constexpr int BATCHED = 1;
+  template <bool CHECK, int IPT>
+  __device__ __forceinline__ static void pairs(const Tgt (&t)[IPT], double (&acc)[IPT][6],
+                                               const double2 *sj, int jg, const int (&ig)[IPT],
+                                               const SweepParams &P) {
+    const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
+    double dx[IPT], dy[IPT], dz[IPT], ux[IPT], uy[IPT], uz[IPT], r2[IPT], rv[IPT], mj[IPT];
+    double y[IPT], w[IPT], a3[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      dx[r] = a.x - t[r].x;
+      dy[r] = a.y - t[r].y;
+      dz[r] = b.x - t[r].z;
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      r2[r] = fma(dx[r], dx[r], P.eps2);
+      r2[r] = fma(dy[r], dy[r], r2[r]);
+      r2[r] = fma(dz[r], dz[r], r2[r]);
+      mj[r] = b.y;
+      if (CHECK) {
+        const bool self = jg == ig[r];
+        r2[r] = self ? 1.0 : r2[r];
+        mj[r] = self ? 0.0 : mj[r];
+      }
+    }
+    double y0[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[r]) : "d"(r2[r]));
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      ux[r] = c.x - t[r].vx;
+      uy[r] = c.y - t[r].vy;
+      uz[r] = d.x - t[r].vz;
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      rv[r] = dx[r] * ux[r];
+      rv[r] = fma(dy[r], uy[r], rv[r]);
+      rv[r] = fma(dz[r], uz[r], rv[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      double tt = r2[r] * y0[r];
+      double e = fma(-tt, y0[r], 1.0);
+      double pp = fma(0.375, e, 0.5);
+      if (FLAVOUR & 1) {
+        double q = e * pp;
+        y[r] = fma(y0[r], q, y0[r]);
+      } else {
+        double q = e * y0[r];
+        y[r] = fma(pp, q, y0[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      double y2 = y[r] * y[r];
+      w[r] = (mj[r] * y[r]) * y2;
+      a3[r] = (rv[r] * y2) * -3.0;
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      acc[r][0] = fma(w[r], dx[r], acc[r][0]);
+      acc[r][1] = fma(w[r], dy[r], acc[r][1]);
+      acc[r][2] = fma(w[r], dz[r], acc[r][2]);
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      ux[r] = fma(a3[r], dx[r], ux[r]);
+      uy[r] = fma(a3[r], dy[r], uy[r]);
+      uz[r] = fma(a3[r], dz[r], uz[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      acc[r][3] = fma(w[r], ux[r], acc[r][3]);
+      acc[r][4] = fma(w[r], uy[r], acc[r][4]);
+      acc[r][5] = fma(w[r], uz[r], acc[r][5]);
+    }
+  }
+};
+
+// ---- the sweep kernel ----------------------------------------------------------------------
+constexpr size_t SWEEP_SMEM_BYTES = (size_t)STAGES * TJ * PK * sizeof(double) + 2 * STAGES * 8;
+
+// NT threads per CTA, IPT targets per thread (i-tile TI = NT*IPT), MINB resident CTAs per SM
+// asked of the register allocator, UNROLL = source-loop unroll of the off-diagonal path.
+template <class Op, int NT, int IPT, int MINB, int UNROLL>
 __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
   constexpr int TI = NT * IPT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -428,18 +531,12 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
     const bool diag = (j0 < i_lo + TI) && (j0 + cnt > i_lo);
     if (diag) {
 #pragma unroll 2
-      for (int jj = 0; jj < cnt; ++jj) {
-#pragma unroll
-        for (int r = 0; r < IPT; ++r)
-          Op::template pair<true>(tg[r], acc[r], sj + jj * (PK / 2), (j0 + jj) == ig[r], P);
-      }
+      for (int jj = 0; jj < cnt; ++jj)
+        pairs<Op, true, IPT>(tg, acc, sj + jj * (PK / 2), j0 + jj, ig, P);
     } else {
-#pragma unroll 4
-      for (int jj = 0; jj < cnt; ++jj) {
-#pragma unroll
-        for (int r = 0; r < IPT; ++r)
-          Op::template pair<false>(tg[r], acc[r], sj + jj * (PK / 2), false, P);
-      }
+#pragma unroll UNROLL
+      for (int jj = 0; jj < cnt; ++jj)
+        pairs<Op, false, IPT>(tg, acc, sj + jj * (PK / 2), j0 + jj, ig, P);
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[st]);
@@ -454,9 +551,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
 
 // Fix-up: combine, per i-tile, the partial slots of the CTAs that shared its source range,
 // in ascending CTA (= ascending source) order.  One thread per target.
-template <class Op, int IPT>
-__global__ void __launch_bounds__(NT *IPT) fixup_kernel(const SweepParams P) {
-  constexpr int TI = NT * IPT;
+template <class Op, int TI>
+__global__ void __launch_bounds__(TI) fixup_kernel(const SweepParams P) {
   const int it = blockIdx.x;
   const long long u_lo = (long long)it * P.n_jt, u_hi = u_lo + P.n_jt - 1;
   const int c_lo = (int)(u_lo / P.units_per_cta), c_hi = (int)(u_hi / P.units_per_cta);

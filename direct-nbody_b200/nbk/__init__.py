@@ -53,6 +53,7 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "nbk_dev_grad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
     "nbk_dev_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_tune": (_i, [_vp, _i]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
 
@@ -141,6 +142,9 @@ class Context:
         ms = _f()
         self._ck(self._lib.nbk_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def tune(self, variant):
+        self._ck(self._lib.nbk_tune(self._h, variant))
 
     def fp64_peak(self, iters=20000):
         tf, ms = _d(), _f()
@@ -283,7 +287,7 @@ class Context:
 
     # -------------------------------------------------------------- raw device pointers
     # Arguments are integer device addresses (e.g. torch.Tensor.data_ptr()) and an integer
-    # cudaStream_t (torch.cuda.current_stream().cuda_stream); 0 = the context's own stream.
+    # cudaStream_t (torch.cuda.current_stream().cuda_stream); 0 = the legacy default stream.
     def dev_pack(self, n, d_m, d_q, d_vel, is_velocity, d_packed, stream=0):
         self._ck(self._lib.nbk_dev_pack(self._h, n, d_m, d_q, d_vel or None, int(is_velocity),
                                         d_packed, stream or None))

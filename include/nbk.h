@@ -151,7 +151,8 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
 
 /* A packed body is 8 doubles {x, y, z, m, vx, vy, vz, 0} (64 B): the layout j-tiles are
  * bulk-copied into shared memory in.  All pointers are device pointers on ctx's device;
- * `stream` is a cudaStream_t cast to void* (NULL = the context's own stream). */
+ * `stream` is a cudaStream_t cast to void* (NULL = the legacy default stream, as in
+ * every CUDA API); work is enqueued, not waited for. */
 #define NBK_PACKED_DOUBLES 8
 int nbk_dev_pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, const double *d_vel,
                  int is_velocity, double *d_packed, void *stream);
@@ -166,6 +167,12 @@ int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double
                        int t1, int s0, int s1, double *d_gsum, int accumulate, void *stream);
 int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0, int t1,
                   int s0, int s1, double *d_phi, int accumulate, void *stream);
+
+/* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
+ * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).
+ * Results do not depend on the shape beyond summation order.  A knob for profiles/ and
+ * tests; callers never need it. */
+int nbk_tune(nbk_ctx *ctx, int variant);
 
 /* FP64 DFMA-throughput microbenchmark on ctx's device (the measured FP64 peak the roofline
  * fraction is quoted against): runs `iters` dependent-chain-free DFMA per thread on a full

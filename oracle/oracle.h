@@ -17,6 +17,8 @@ extern "C" {
 #endif
 
 int oracle_num_threads(void);
+/* test-run guard: step loops stop early past this many steps (default 2e8) */
+void oracle_set_step_cap(long cap);
 
 /* sweeps.c */
 void oracle_start_bs_sweep(int n, const double *m, const double *q, const double *p,

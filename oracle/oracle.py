@@ -53,6 +53,7 @@ def _declare(L):
         f.argtypes = list(args)
 
     sig("oracle_num_threads", _i)
+    sig("oracle_set_step_cap", None, C.c_long)
     sig("oracle_start_bs_sweep", None, _i, _pd, _pd, _pd, _d, _pd, _pd)
     sig("oracle_start_bs_sweep_omp", None, _i, _pd, _pd, _pd, _d, _pd, _pd)
     sig("oracle_grad_v_sum", None, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd)
@@ -99,6 +100,10 @@ def _ip(a):
 
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def set_step_cap(cap: int) -> None:
+    lib().oracle_set_step_cap(cap)
 
 
 def num_threads() -> int:

@@ -144,3 +144,26 @@ def test_argument_errors_raise(ctx, oracle):
         ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(0, 17))
     with pytest.raises(nbk.NbkError):
         ctx.grad_v_sum(m, q, 0.0, sources=(5, 3))
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+def test_every_tile_shape_matches_oracle(ctx, oracle, shape):
+    """All three tile shapes (nbk_tune) on a size that is ragged for each of them."""
+    n = 2500
+    m, q, p = oracle.make_plummer(n, 77)
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 1e-4)
+    phi_ref = oracle.v_sum(m, q, 1e-4)
+    gg_ref = oracle.grad_v_sum(m, q, 1e-4)
+    ctx.tune(shape)
+    try:
+        g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 1e-4)
+        phi, _ = ctx.v_sum(m, q, 1e-4)
+        gg = ctx.grad_v_sum(m, q, 1e-4)
+        sub = ctx.grad_v_dgrad_v_sum(m, q, p, 1e-4, targets=(1000, 1003), sources=(500, 2400))
+    finally:
+        ctx.tune(0)
+    assert rel_err(g, g_ref) <= TOL and rel_err(dg, dg_ref) <= TOL
+    assert rel_err(gg, gg_ref) <= TOL
+    assert np.max(np.abs(phi - phi_ref) / np.abs(phi_ref)) <= TOL
+    sub_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 1e-4, targets=(1000, 1003), sources=(500, 2400))
+    assert rel_err(sub[0], sub_ref[0]) <= TOL and rel_err(sub[1], sub_ref[1]) <= TOL
