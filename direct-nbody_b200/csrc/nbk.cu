@@ -32,7 +32,8 @@ struct nbk_ctx {
   int shape = 0;
   std::string err;
   // device workspaces
-  DevBuf d_m, d_q, d_vel, d_aux_in, d_packed, d_aux, d_partial, d_out[4], d_scalar;
+  DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_out[4],
+      d_scalar;
   // resident bodies
   int resident_n = 0;
   DevBuf d_res_m, d_res_packed;
@@ -94,10 +95,10 @@ template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
     static int cached = -1;
     if (cached < 0) {
       auto kern = sweep_kernel<Op, NT, IPT, MINB, UNROLL>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)SWEEP_SMEM_BYTES));
+      constexpr size_t smem = sweep_smem_bytes(naux_of<Op>::value);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int o = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NT, SWEEP_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NT, smem));
       if (o < 1) return fail(ctx, NBK_ERR_CUDA, "sweep kernel does not fit on an SM");
       cached = o;
     }
@@ -123,7 +124,8 @@ template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
     TRY(reserve(ctx, ctx->d_partial, (size_t)2 * G * Op::NACC * TI * sizeof(double)));
     P.partial = (double *)ctx->d_partial.p;
     if (time_it) CK(cudaEventRecord(ctx->ev0, st));
-    sweep_kernel<Op, NT, IPT, MINB, UNROLL><<<(unsigned)G, NT, SWEEP_SMEM_BYTES, st>>>(P);
+    sweep_kernel<Op, NT, IPT, MINB, UNROLL>
+        <<<(unsigned)G, NT, sweep_smem_bytes(naux_of<Op>::value), st>>>(P);
     CK(cudaGetLastError());
     ctx->launches++;
     if (P.units_per_cta % P.n_jt != 0) {  // some i-tile's sources are split over CTAs
@@ -156,8 +158,36 @@ int pick_shape(const nbk_ctx *ctx, int nt) {
   return SHAPE_SMALL;
 }
 
+// Source-parallel path for a handful of targets (sweep.cuh, small_kernel).
+constexpr int SMALL_NTG = 4;       // targets per launch group
+constexpr int SMALL_MAX_NT = 32;   // use it up to this many targets
+
+template <class Op> int run_small(nbk_ctx *ctx, SweepParams P, cudaStream_t st, bool time_it) {
+  const int nt = P.t1 - P.t0, ns = P.s1 - P.s0;
+  int ncta = (ns + 255) / 256;
+  const int cap = ctx->sm_count * 4;
+  if (ncta > cap) ncta = cap;
+  TRY(reserve(ctx, ctx->d_partial, (size_t)nt * ncta * Op::NACC * sizeof(double)));
+  P.partial = (double *)ctx->d_partial.p;
+  if (time_it) CK(cudaEventRecord(ctx->ev0, st));
+  for (int g0 = P.t0; g0 < P.t1; g0 += SMALL_NTG) {
+    small_kernel<Op, SMALL_NTG><<<ncta, 256, 0, st>>>(P, g0, ncta);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  small_fix_kernel<Op><<<(nt + 63) / 64, 64, 0, st>>>(P, ncta);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (time_it) {
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+  }
+  return NBK_OK;
+}
+
 template <class Op>
 int run_op(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  if (ctx->shape == SHAPE_AUTO && P.t1 - P.t0 <= SMALL_MAX_NT) return run_small<Op>(ctx, P, st, time_it);
   switch (pick_shape(ctx, P.t1 - P.t0)) {
     case SHAPE_LARGE: return Launcher<Op, 256, 4, 1, 4>::run(ctx, P, st, time_it);
     case SHAPE_MEDIUM: return Launcher<Op, 128, 2, 4, 4>::run(ctx, P, st, time_it);
@@ -168,6 +198,8 @@ int run_op(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
 // The time-scale kick is register-hungry (IEEE sqrt/div sequences): smaller shapes.
 template <>
 int run_op<OpKick<true>>(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  if (ctx->shape == SHAPE_AUTO && P.t1 - P.t0 <= SMALL_MAX_NT)
+    return run_small<OpKick<true>>(ctx, P, st, time_it);
   switch (pick_shape(ctx, P.t1 - P.t0)) {
     case SHAPE_LARGE:
     case SHAPE_MEDIUM: return Launcher<OpKick<true>, 128, 2, 3, 2>::run(ctx, P, st, time_it);
@@ -182,6 +214,16 @@ struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bo
 
 int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
   return run_op<OpGradVDGradVB<1>>(ctx, P, st, time_it);
+}
+
+// Tangent sweeps: aux tiles make the stage (1+KT) x 8 KB; one shape per KT.
+template <int KT, bool JERK>
+int run_tangent(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st) {
+  if constexpr (KT == 1) {
+    if (P.t1 - P.t0 >= 256)
+      return Launcher<OpTangent<KT, JERK>, 128, 2, 2, 1>::run(ctx, P, st, true);
+  }
+  return Launcher<OpTangent<KT, JERK>, 128, 1, 2, 1>::run(ctx, P, st, true);
 }
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
@@ -441,7 +483,8 @@ void nbk_destroy(nbk_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf *bufs[] = {&c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
+  DevBuf *bufs[] = {&c->d_t,     &c->d_f,      &c->d_df,     &c->d_aux_in2,
+                    &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
                     &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed};
   for (DevBuf *b : bufs)
@@ -543,22 +586,130 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
   return run_kick(ctx, (const double *)ctx->d_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
 }
 
-int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int, const double *, const double *,
-                                     const double *, const double *, const double *,
-                                     const double *, double, double, int, int, int, int,
-                                     double *, double *) {
-  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_dgrad_v_sum_predicted: not built yet");
+int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int n, const double *t, const double *m,
+                                     const double *q, const double *p, const double *f,
+                                     const double *df, double nt, double eps2, int t0, int t1,
+                                     int s0, int s1, double *gsum, double *dgsum) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  if (!t || !m || !q || !p || !f || !df) return fail(ctx, NBK_ERR_ARG, "null body array");
+  TRY(upload(ctx, ctx->d_m, m, n));
+  TRY(upload(ctx, ctx->d_q, q, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_vel, p, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_t, t, n));
+  TRY(upload(ctx, ctx->d_f, f, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_df, df, 3 * (size_t)n));
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  predict_pack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+      n, (const double *)ctx->d_t.p, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
+      (const double *)ctx->d_vel.p, (const double *)ctx->d_f.p, (const double *)ctx->d_df.p, nt,
+      (double *)ctx->d_packed.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return run_grad_v_dgrad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum,
+                            dgsum);
 }
 
-int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int, const double *, const double *,
-                                   const double *, int, const double *, const double *, double,
-                                   int, int, int, int, double *, double *, double *, double *) {
-  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_dgrad_v_sum_tangent: not built yet");
+namespace {
+// Shared body of the two tangent entry points.
+int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p, int K,
+                   const double *dq, const double *dp, double eps2, int t0, int t1, int s0,
+                   int s1, double *gsum, double *dgsum, double *gsum_tan, double *dgsum_tan,
+                   bool jerk) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (K < 0 || (K > 0 && (!dq || !gsum_tan || (jerk && (!dp || !dgsum_tan)))))
+    return fail(ctx, NBK_ERR_ARG, "tangent sweep: bad direction arguments");
+  if (n == 0 || t1 == t0) return NBK_OK;
+  const size_t nt = (size_t)(t1 - t0), n3 = 3 * (size_t)n;
+  TRY(stage_bodies(ctx, n, m, q, jerk ? p : nullptr, 0));
+  if (gsum || dgsum) {  // value sums from the plain kernels
+    if (jerk) {
+      TRY(reserve(ctx, ctx->d_out[2], 3 * nt * sizeof(double)));
+      TRY(reserve(ctx, ctx->d_out[3], 3 * nt * sizeof(double)));
+      if (s1 > s0) {
+        SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1);
+        P.out[0] = (double *)ctx->d_out[2].p;
+        P.out[1] = (double *)ctx->d_out[3].p;
+        TRY(run_k2(ctx, P, ctx->stream, false));
+      } else {
+        CK(cudaMemsetAsync(ctx->d_out[2].p, 0, 3 * nt * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_out[3].p, 0, 3 * nt * sizeof(double), ctx->stream));
+      }
+      if (gsum) TRY(download(ctx, gsum, ctx->d_out[2], 3 * nt));
+      if (dgsum) TRY(download(ctx, dgsum, ctx->d_out[3], 3 * nt));
+    } else if (gsum) {
+      TRY(reserve(ctx, ctx->d_out[2], 3 * nt * sizeof(double)));
+      if (s1 > s0) {
+        SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1);
+        P.out[0] = (double *)ctx->d_out[2].p;
+        TRY(K1::run(ctx, P, ctx->stream, false));
+      } else {
+        CK(cudaMemsetAsync(ctx->d_out[2].p, 0, 3 * nt * sizeof(double), ctx->stream));
+      }
+      TRY(download(ctx, gsum, ctx->d_out[2], 3 * nt));
+    }
+  }
+  if (K == 0) return sync(ctx);
+  // directions: upload, pack into aux[K][n][8]
+  TRY(reserve(ctx, ctx->d_aux, (size_t)K * n * PK * sizeof(double)));
+  TRY(upload(ctx, ctx->d_aux_in, dq, (size_t)K * n3));
+  if (jerk) TRY(upload(ctx, ctx->d_aux_in2, dp, (size_t)K * n3));
+  for (int k = 0; k < K; ++k) {
+    pack_aux_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+        n, (const double *)ctx->d_m.p, (const double *)ctx->d_aux_in.p + (size_t)k * n3,
+        jerk ? (const double *)ctx->d_aux_in2.p + (size_t)k * n3 : nullptr, 0,
+        (double *)ctx->d_aux.p + (size_t)k * n * PK);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  TRY(reserve(ctx, ctx->d_out[0], (size_t)K * 3 * nt * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], (size_t)K * 3 * nt * sizeof(double)));
+  if (s1 == s0) {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, (size_t)K * 3 * nt * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_out[1].p, 0, (size_t)K * 3 * nt * sizeof(double), ctx->stream));
+  } else {
+    for (int k0 = 0; k0 < K;) {
+      const int kt = (K - k0 >= 3) ? 3 : 1;
+      SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1);
+      P.aux = (const double *)ctx->d_aux.p + (size_t)k0 * n * PK;
+      P.aux_stride = n * PK;
+      P.K = kt;
+      P.out[0] = (double *)ctx->d_out[0].p + (size_t)k0 * 3 * nt;
+      P.out[1] = (double *)ctx->d_out[1].p + (size_t)k0 * 3 * nt;
+      if (jerk) {
+        if (kt == 3) TRY((run_tangent<3, true>(ctx, P, ctx->stream)));
+        else TRY((run_tangent<1, true>(ctx, P, ctx->stream)));
+      } else {
+        if (kt == 3) TRY((run_tangent<3, false>(ctx, P, ctx->stream)));
+        else TRY((run_tangent<1, false>(ctx, P, ctx->stream)));
+      }
+      k0 += kt;
+    }
+  }
+  TRY(download(ctx, gsum_tan, ctx->d_out[0], (size_t)K * 3 * nt));
+  if (jerk) TRY(download(ctx, dgsum_tan, ctx->d_out[1], (size_t)K * 3 * nt));
+  return sync(ctx);
+}
+}  // namespace
+
+int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q,
+                                   const double *p, int K, const double *dq, const double *dp,
+                                   double eps2, int t0, int t1, int s0, int s1, double *gsum,
+                                   double *dgsum, double *gsum_tan, double *dgsum_tan) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
+  return tangent_common(ctx, n, m, q, p, K, dq, dp, eps2, t0, t1, s0, s1, gsum, dgsum, gsum_tan,
+                        dgsum_tan, true);
 }
 
-int nbk_grad_v_sum_tangent(nbk_ctx *ctx, int, const double *, const double *, int,
-                           const double *, double, int, int, int, int, double *, double *) {
-  return fail(ctx, NBK_ERR_STATE, "nbk_grad_v_sum_tangent: not built yet");
+int nbk_grad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q, int K,
+                           const double *dq, double eps2, int t0, int t1, int s0, int s1,
+                           double *gsum, double *gsum_tan) {
+  if (!ctx) return NBK_ERR_ARG;
+  return tangent_common(ctx, n, m, q, nullptr, K, dq, nullptr, eps2, t0, t1, s0, s1, gsum,
+                        nullptr, gsum_tan, nullptr, false);
 }
 
 // ---- device-resident bodies --------------------------------------------------------------------

@@ -110,7 +110,7 @@ struct OpGradV {
   struct Tgt {
     double x, y, z;
   };
-  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
     t.y = pk[1];
     t.z = pk[2];
@@ -118,7 +118,7 @@ struct OpGradV {
   __device__ __forceinline__ static void zero(double *acc) { acc[0] = acc[1] = acc[2] = 0.0; }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
-                                              bool self, const SweepParams &P) {
+                                              const double2 *, bool self, const SweepParams &P) {
     double2 a = sj[0], b = sj[1];
     double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
     double r2 = fma(dx, dx, P.eps2);
@@ -157,7 +157,7 @@ struct OpGradVDGradV {
   struct Tgt {
     double x, y, z, vx, vy, vz;
   };
-  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
     t.y = pk[1];
     t.z = pk[2];
@@ -170,7 +170,7 @@ struct OpGradVDGradV {
   }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
-                                              bool self, const SweepParams &P) {
+                                              const double2 *, bool self, const SweepParams &P) {
     double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
     double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
     double ux = c.x - t.vx, uy = c.y - t.vy, uz = d.x - t.vz;
@@ -218,7 +218,7 @@ struct OpV {
   struct Tgt {
     double x, y, z;
   };
-  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
     t.y = pk[1];
     t.z = pk[2];
@@ -226,7 +226,7 @@ struct OpV {
   __device__ __forceinline__ static void zero(double *acc) { acc[0] = 0.0; }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
-                                              bool self, const SweepParams &P) {
+                                              const double2 *, bool self, const SweepParams &P) {
     double2 a = sj[0], b = sj[1];
     double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
     double r2 = fma(dx, dx, P.eps2);
@@ -257,7 +257,7 @@ template <bool WITH_TSCALE> struct OpKick {
   struct Tgt {
     double x, y, z, vx, vy, vz, m;
   };
-  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &) {
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
     t.y = pk[1];
     t.z = pk[2];
@@ -272,7 +272,7 @@ template <bool WITH_TSCALE> struct OpKick {
   }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
-                                              bool self, const SweepParams &P) {
+                                              const double2 *, bool self, const SweepParams &P) {
     double2 a = sj[0], b = sj[1];
     double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
     double r2e = __dmul_rn(dx, dx);
@@ -333,15 +333,23 @@ template <class Op> struct has_batched<Op, decltype((void)Op::BATCHED)> {
   static constexpr bool value = true;
 };
 
+template <class Op, class = void> struct naux_of { static constexpr int value = 0; };
+template <class Op> struct naux_of<Op, decltype((void)Op::NAUX)> {
+  static constexpr int value = Op::NAUX;
+};
+
+// sa = this source's slot in the first aux tile; successive aux tiles are TJ*PK doubles apart.
 template <class Op, bool CHECK, int IPT>
 __device__ __forceinline__ void pairs(const typename Op::Tgt (&tg)[IPT],
-                                      double (&acc)[IPT][Op::NACC], const double2 *sj, int jg,
-                                      const int (&ig)[IPT], const SweepParams &P) {
+                                      double (&acc)[IPT][Op::NACC], const double2 *sj,
+                                      const double2 *sa, int jg, const int (&ig)[IPT],
+                                      const SweepParams &P) {
   if constexpr (has_batched<Op>::value) {
     Op::template pairs<CHECK, IPT>(tg, acc, sj, jg, ig, P);
   } else {
 #pragma unroll
-    for (int r = 0; r < IPT; ++r) Op::template pair<CHECK>(tg[r], acc[r], sj, jg == ig[r], P);
+    for (int r = 0; r < IPT; ++r)
+      Op::template pair<CHECK>(tg[r], acc[r], sj, sa, jg == ig[r], P);
   }
 }
 
@@ -429,17 +437,138 @@ template <int FLAVOUR> struct OpGradVDGradVB : OpGradVDGradV {
   }
 };
 
+// Tangent (first-order forward mode) of the acc / acc+jerk sums for KT directions per pass:
+// DFloatBase.grad_v / grad_v_dgrad_v (dFloat_advancer.ml:57-81) summed as in
+// dFloat_hermite.ml:177-186.  Direction k's packed array aux[k] holds per body
+// {dq_x, dq_y, dq_z, 0, dv_x, dv_y, dv_z, 0}, dv = dp / m (masses and eps2 carry no tangent,
+// dFloat_hermite.ml:36-46).  With e = dq_j - dq_i, g = dv_j - dv_i, c1 = d.e, c2 = e.u + d.g:
+//   dA = sum w (e - 3 y^2 c1 d)
+//   dJ = sum w (g + a3 e + da3 d - 3 y^2 c1 (u + a3 d)),  da3 = -3 y^2 c2 + 6 (d.u) y^4 c1
+// (checked against central differences in tests/).  Accumulators hold the
+// tangents only; the value sums come from the plain kernels.
+template <int KT, bool JERK> struct OpTangent {
+  static constexpr int NAUX = KT;
+  static constexpr int NC = JERK ? 6 : 3;
+  static constexpr int NACC = NC * KT;
+  struct Tgt {
+    double x, y, z, vx, vy, vz;
+    double e[KT][3], g[KT][3];
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &P,
+                                              int i) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+    t.vx = pk[4];
+    t.vy = pk[5];
+    t.vz = pk[6];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const double *a = P.aux + (size_t)k * P.aux_stride + (size_t)i * PK;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t.e[k][c] = a[c];
+        t.g[k][c] = JERK ? a[4 + c] : 0.0;
+      }
+    }
+  }
+  __device__ __forceinline__ static void zero(double *acc) {
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              const double2 *sa, bool self,
+                                              const SweepParams &P) {
+    const double2 a = sj[0], b = sj[1];
+    const double d[3] = {a.x - t.x, a.y - t.y, b.x - t.z};
+    double r2 = fma(d[0], d[0], P.eps2);
+    r2 = fma(d[1], d[1], r2);
+    r2 = fma(d[2], d[2], r2);
+    double mj = b.y;
+    if (CHECK) {
+      r2 = self ? 1.0 : r2;
+      mj = self ? 0.0 : mj;
+    }
+    const double y = rsqrt_nr(r2);
+    const double y2 = y * y;
+    const double w = (mj * y) * y2;
+    const double m3y2 = -3.0 * y2;
+    double u[3] = {0.0, 0.0, 0.0}, tt[3] = {0.0, 0.0, 0.0}, rv = 0.0, a3 = 0.0;
+    if (JERK) {
+      const double2 c = sj[2], dd = sj[3];
+      u[0] = c.x - t.vx;
+      u[1] = c.y - t.vy;
+      u[2] = dd.x - t.vz;
+      rv = fma(d[2], u[2], fma(d[1], u[1], d[0] * u[0]));
+      a3 = rv * m3y2;
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3) tt[c3] = fma(a3, d[c3], u[c3]);
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const double2 *ak = sa + (size_t)k * (TJ * PK / 2);
+      const double2 a0 = ak[0], a1 = ak[1];
+      const double e[3] = {a0.x - t.e[k][0], a0.y - t.e[k][1], a1.x - t.e[k][2]};
+      const double c1 = fma(d[2], e[2], fma(d[1], e[1], d[0] * e[0]));
+      const double b1 = m3y2 * c1;
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3)
+        acc[k * NC + c3] = fma(w, fma(b1, d[c3], e[c3]), acc[k * NC + c3]);
+      if (JERK) {
+        const double2 a2 = ak[2], a3v = ak[3];
+        const double g[3] = {a2.x - t.g[k][0], a2.y - t.g[k][1], a3v.x - t.g[k][2]};
+        double c2 = fma(e[2], u[2], fma(e[1], u[1], e[0] * u[0]));
+        c2 = fma(d[2], g[2], fma(d[1], g[1], fma(d[0], g[0], c2)));
+        // da3 = -3 y2 (c2 - 2 rv y2 c1)
+        const double da3 = m3y2 * fma(-2.0 * (rv * y2), c1, c2);
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+          double s = fma(b1, tt[c3], g[c3]);
+          s = fma(a3, e[c3], s);
+          s = fma(da3, d[c3], s);
+          acc[k * NC + 3 + c3] = fma(w, s, acc[k * NC + 3 + c3]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) {
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) a[k] += b[k];
+  }
+  // out[0] = gsum_tan [K][3 nt], out[1] = dgsum_tan [K][3 nt], already offset to this pass.
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    const double s = -P.packed[(size_t)ig * PK + 3];
+    const size_t nt3 = 3 * (size_t)(P.t1 - P.t0);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      double *g = P.out[0] + (size_t)k * nt3 + 3 * (size_t)(ig - P.t0);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] = s * acc[k * NC + c];
+      if (JERK) {
+        double *dg = P.out[1] + (size_t)k * nt3 + 3 * (size_t)(ig - P.t0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dg[c] = s * acc[k * NC + 3 + c];
+      }
+    }
+  }
+};
+
 // ---- the sweep kernel ----------------------------------------------------------------------
-constexpr size_t SWEEP_SMEM_BYTES = (size_t)STAGES * TJ * PK * sizeof(double) + 2 * STAGES * 8;
+constexpr size_t sweep_smem_bytes(int naux) {
+  return (size_t)STAGES * TJ * PK * sizeof(double) * (1 + naux) + 2 * STAGES * 8;
+}
 
 // NT threads per CTA, IPT targets per thread (i-tile TI = NT*IPT), MINB resident CTAs per SM
 // asked of the register allocator, UNROLL = source-loop unroll of the off-diagonal path.
 template <class Op, int NT, int IPT, int MINB, int UNROLL>
 __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
   constexpr int TI = NT * IPT;
+  constexpr int NAUX = naux_of<Op>::value;
+  constexpr int STAGE_DOUBLES = TJ * PK * (1 + NAUX);  // base tile, then NAUX aux tiles
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TJ * PK * 8);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8);
   uint64_t *empty = full + STAGES;
 
   const int tid = threadIdx.x;
@@ -465,8 +594,13 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
     int cnt = min(TJ, P.s1 - j0);
     int st = k % STAGES;
     uint32_t bytes = (uint32_t)cnt * PK * 8;
-    mbar_arrive_expect_tx(&full[st], bytes);
-    tma_bulk_g2s(tiles + (size_t)st * TJ * PK, P.packed + (size_t)j0 * PK, bytes, &full[st]);
+    double *dst = tiles + (size_t)st * STAGE_DOUBLES;
+    mbar_arrive_expect_tx(&full[st], bytes * (1 + NAUX));
+    tma_bulk_g2s(dst, P.packed + (size_t)j0 * PK, bytes, &full[st]);
+#pragma unroll
+    for (int a = 0; a < NAUX; ++a)
+      tma_bulk_g2s(dst + (size_t)(1 + a) * TJ * PK,
+                   P.aux + (size_t)a * P.aux_stride + (size_t)j0 * PK, bytes, &full[st]);
   };
   if (tid == 0) {
     for (int k = 0; k < STAGES - 1 && k < ntiles; ++k) issue(k);
@@ -509,7 +643,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
         int i = P.t0 + it * TI + r * NT + tid;
         ig[r] = i;
         int ic = i < P.t1 ? i : P.t1 - 1;  // clamp: lanes past the end compute, never store
-        Op::load(tg[r], P.packed + (size_t)ic * PK, P);
+        Op::load(tg[r], P.packed + (size_t)ic * PK, P, ic);
         Op::zero(acc[r]);
       }
     }
@@ -526,17 +660,18 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
 
     const int j0 = P.s0 + jt * TJ;
     const int cnt = min(TJ, P.s1 - j0);
-    const double2 *sj = reinterpret_cast<const double2 *>(tiles + (size_t)st * TJ * PK);
+    const double2 *sj = reinterpret_cast<const double2 *>(tiles + (size_t)st * STAGE_DOUBLES);
+    const double2 *sa = sj + TJ * (PK / 2);
     const int i_lo = P.t0 + it * TI;
     const bool diag = (j0 < i_lo + TI) && (j0 + cnt > i_lo);
     if (diag) {
 #pragma unroll 2
       for (int jj = 0; jj < cnt; ++jj)
-        pairs<Op, true, IPT>(tg, acc, sj + jj * (PK / 2), j0 + jj, ig, P);
+        pairs<Op, true, IPT>(tg, acc, sj + jj * (PK / 2), sa + jj * (PK / 2), j0 + jj, ig, P);
     } else {
 #pragma unroll UNROLL
       for (int jj = 0; jj < cnt; ++jj)
-        pairs<Op, false, IPT>(tg, acc, sj + jj * (PK / 2), j0 + jj, ig, P);
+        pairs<Op, false, IPT>(tg, acc, sj + jj * (PK / 2), sa + jj * (PK / 2), j0 + jj, ig, P);
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[st]);
@@ -573,6 +708,81 @@ __global__ void __launch_bounds__(TI) fixup_kernel(const SweepParams P) {
   Op::store(P, i, acc);
 }
 
+// ---- few targets: source-parallel kernel -----------------------------------------------------
+// Hermite.advance_body (one target, hermite.ml:106-115) and the small active blocks of
+// Advancer.A / Leapfrog have 1..a few dozen targets: too few for i-parallel lanes.  Here every
+// thread owns SOURCES (grid-stride over [s0,s1), one coalesced 64-byte read each), loops over a
+// group of NTG targets held in registers, and the per-target sums are reduced across the warp
+// with shuffles, across warps through shared memory, and across CTAs by small_fix_kernel - all
+// in a fixed order.  partial layout: [target][cta][NACC].
+template <class Op, int NTG>
+__global__ void __launch_bounds__(256) small_kernel(const SweepParams P, int tg0, int ncta) {
+  static_assert(naux_of<Op>::value == 0, "source-parallel kernel has no aux tiles");
+  __shared__ double red[8][NTG * Op::NACC];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  typename Op::Tgt tg[NTG];
+  double acc[NTG][Op::NACC];
+  int ig[NTG];
+#pragma unroll
+  for (int r = 0; r < NTG; ++r) {
+    int i = tg0 + r;
+    ig[r] = i < P.t1 ? i : -1;
+    int ic = i < P.t1 ? i : P.t1 - 1;
+    Op::load(tg[r], P.packed + (size_t)ic * PK, P, ic);
+    Op::zero(acc[r]);
+  }
+  for (int j = P.s0 + blockIdx.x * 256 + tid; j < P.s1; j += ncta * 256) {
+    double2 src[PK / 2];
+    const double2 *gp = reinterpret_cast<const double2 *>(P.packed + (size_t)j * PK);
+#pragma unroll
+    for (int c = 0; c < PK / 2; ++c) src[c] = gp[c];
+#pragma unroll
+    for (int r = 0; r < NTG; ++r) Op::template pair<true>(tg[r], acc[r], src, src, j == ig[r], P);
+  }
+#pragma unroll
+  for (int r = 0; r < NTG; ++r) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double other[Op::NACC];
+#pragma unroll
+      for (int c = 0; c < Op::NACC; ++c) other[c] = __shfl_down_sync(0xffffffffu, acc[r][c], off);
+      Op::combine(acc[r], other);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < Op::NACC; ++c) red[warp][r * Op::NACC + c] = acc[r][c];
+    }
+  }
+  __syncthreads();
+  if (tid < NTG && tg0 + tid < P.t1) {
+    double a[Op::NACC], b[Op::NACC];
+#pragma unroll
+    for (int c = 0; c < Op::NACC; ++c) a[c] = red[0][tid * Op::NACC + c];
+    for (int w = 1; w < 8; ++w) {
+#pragma unroll
+      for (int c = 0; c < Op::NACC; ++c) b[c] = red[w][tid * Op::NACC + c];
+      Op::combine(a, b);
+    }
+    double *dst = P.partial + ((size_t)(tg0 + tid - P.t0) * ncta + blockIdx.x) * Op::NACC;
+#pragma unroll
+    for (int c = 0; c < Op::NACC; ++c) dst[c] = a[c];
+  }
+}
+
+template <class Op> __global__ void small_fix_kernel(const SweepParams P, int ncta) {
+  const int i = P.t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.t1) return;
+  double a[Op::NACC], b[Op::NACC];
+  Op::zero(a);
+  const double *src = P.partial + (size_t)(i - P.t0) * ncta * Op::NACC;
+  for (int c = 0; c < ncta; ++c) {
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k) b[k] = src[(size_t)c * Op::NACC + k];
+    Op::combine(a, b);
+  }
+  Op::store(P, i, a);
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.
@@ -596,6 +806,63 @@ __global__ void pack_kernel(int n, const double *__restrict__ m, const double *_
   o[1] = make_double2(q[3 * i + 2], mi);
   o[2] = make_double2(vx, vy);
   o[3] = make_double2(vz, 0.0);
+}
+
+// Tangent direction (dq, dp|dv) -> {dq, 0, dv, 0}, dv = dp / m.
+__global__ void pack_aux_kernel(int n, const double *__restrict__ m, const double *__restrict__ dq,
+                                const double *__restrict__ dvel, int is_velocity,
+                                double *__restrict__ aux) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 *o = reinterpret_cast<double2 *>(aux + (size_t)i * PK);
+  double vx = 0.0, vy = 0.0, vz = 0.0;
+  if (dvel) {
+    vx = dvel[3 * i], vy = dvel[3 * i + 1], vz = dvel[3 * i + 2];
+    if (!is_velocity) {
+      double mi = m[i];
+      vx = __ddiv_rn(vx, mi);
+      vy = __ddiv_rn(vy, mi);
+      vz = __ddiv_rn(vz, mi);
+    }
+  }
+  o[0] = make_double2(dq[3 * i], dq[3 * i + 1]);
+  o[1] = make_double2(dq[3 * i + 2], 0.0);
+  o[2] = make_double2(vx, vy);
+  o[3] = make_double2(vz, 0.0);
+}
+
+// Hermite predictor fused with the pack (hermite.ml:53-72): body i is predicted from its own
+// (t, q, p, f, df) to time nt with the reference's exact operation sequence (no contraction),
+//   qp = q + pc p + fc f + dfc df,  pc = dt/m, fc = pc dt 0.5, dfc = fc dt / 3
+//   pp = p + dt f + (dt dt 0.5) df
+// and stored as {qp, m, pp/m}.
+__global__ void predict_pack_kernel(int n, const double *__restrict__ t,
+                                    const double *__restrict__ m, const double *__restrict__ q,
+                                    const double *__restrict__ p, const double *__restrict__ f,
+                                    const double *__restrict__ df, double nt,
+                                    double *__restrict__ packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mi = m[i];
+  const double dt = __dsub_rn(nt, t[i]);
+  const double pc = __ddiv_rn(dt, mi);
+  const double fc = __dmul_rn(__dmul_rn(pc, dt), 0.5);
+  const double dfc = __ddiv_rn(__dmul_rn(fc, dt), 3.0);
+  const double pdfc = __dmul_rn(__dmul_rn(dt, dt), 0.5);
+  double qp[3], vp[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double qk = q[3 * i + k], pk = p[3 * i + k], fk = f[3 * i + k], dfk = df[3 * i + k];
+    qp[k] = __dadd_rn(__dadd_rn(__dadd_rn(qk, __dmul_rn(pc, pk)), __dmul_rn(fc, fk)),
+                      __dmul_rn(dfc, dfk));
+    const double pp = __dadd_rn(__dadd_rn(pk, __dmul_rn(dt, fk)), __dmul_rn(pdfc, dfk));
+    vp[k] = __ddiv_rn(pp, mi);
+  }
+  double2 *o = reinterpret_cast<double2 *>(packed + (size_t)i * PK);
+  o[0] = make_double2(qp[0], qp[1]);
+  o[1] = make_double2(qp[2], mi);
+  o[2] = make_double2(vp[0], vp[1]);
+  o[3] = make_double2(vp[2], 0.0);
 }
 
 }  // namespace nbk

@@ -167,3 +167,82 @@ def test_every_tile_shape_matches_oracle(ctx, oracle, shape):
     assert np.max(np.abs(phi - phi_ref) / np.abs(phi_ref)) <= TOL
     sub_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 1e-4, targets=(1000, 1003), sources=(500, 2400))
     assert rel_err(sub[0], sub_ref[0]) <= TOL and rel_err(sub[1], sub_ref[1]) <= TOL
+
+
+@pytest.mark.parametrize("nt", [1, 2, 5, 31, 32, 33])
+def test_few_targets_source_parallel_path(ctx, oracle, nt):
+    """1..32 targets take the source-parallel kernel; 33 the i-parallel one."""
+    n = 3000
+    m, q, p = oracle.make_plummer(n, 21)
+    tg = (1234, 1234 + nt)
+    for sr in [(0, n), (100, 2999), (1230, 1240)]:
+        g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
+        g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
+        sc_g = np.linalg.norm(g_ref, axis=1).max() + 1e-300
+        sc_dg = np.linalg.norm(dg_ref, axis=1).max() + 1e-300
+        assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * sc_g
+        assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * sc_dg
+    v = p / m[:, None]
+    dv_ref, tmin_ref = oracle.kick_sum(m, q, v, 1e-3, 1e-4, targets=tg)
+    dv, tmin = ctx.kick_sum(m, q, v, 1e-3, 1e-4, targets=tg)
+    assert rel_err(dv, dv_ref) <= TOL and np.array_equal(tmin, tmin_ref)
+    phi_ref = oracle.v_sum(m, q, 0.0, targets=tg)
+    phi, _ = ctx.v_sum(m, q, 0.0, targets=tg)
+    assert np.allclose(phi, phi_ref, rtol=TOL, atol=0)
+    gg = ctx.grad_v_sum(m, q, 0.01, targets=tg)
+    assert rel_err(gg, oracle.grad_v_sum(m, q, 0.01, targets=tg)) <= TOL
+
+
+@pytest.mark.parametrize("n,ib", [(2, 0), (17, 3), (1024, 1000)])
+def test_hermite_advance_body_loop(ctx, oracle, n, ib):
+    """nbk_grad_v_dgrad_v_sum_predicted = the loop of Hermite.advance_body (hermite.ml:106-115):
+    predict every body to nt, then fp = -gsum, dfp = -dgsum; checked against the oracle's
+    advance_body through the corrector outputs f, df (hermite.ml:128-129)."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 31)) if n > 2 else \
+        oracle.make_plummer(n, 31)
+    f, df = oracle.start_bs_sweep(m, q, p, 0.0)
+    rng = np.random.default_rng(5)
+    t = rng.uniform(0.0, 1e-3, n)            # bodies sit at different times
+    h = rng.uniform(1e-3, 2e-3, n)
+    ref = oracle.hermite_advance_body(t, m, q, p, h, f, df, ib, 1e-4, 0.0)
+    nt = t[ib] + h[ib]
+    g, dg = ctx.grad_v_dgrad_v_sum_predicted(t, m, q, p, f, df, nt, 0.0, targets=(ib, ib + 1))
+    assert rel_err(-g[0], ref["f"]) <= TOL and rel_err(-dg[0], ref["df"]) <= TOL
+    # rectangular form, all targets
+    if n <= 17:
+        gall, dgall = ctx.grad_v_dgrad_v_sum_predicted(t, m, q, p, f, df, nt, 0.0)
+        assert rel_err(gall[ib], g[0]) <= 1e-14
+
+
+@pytest.mark.parametrize("n", [2, 3, 300, 2000])
+@pytest.mark.parametrize("K", [1, 3, 6])
+def test_tangent_sums_match_dual_number_oracle(ctx, oracle, n, K):
+    """K tangent directions against the oracle's Dual restatement of DFloatBase
+    (dFloat_advancer.ml:57-81).  The dual-number library itself is unpinned upstream
+    (SURVEY.md §8c), so the tolerance is on the tangent sums' own scale."""
+    m, q, p = oracle.make_plummer(n, 41)
+    rng = np.random.default_rng(20245)
+    dq = rng.standard_normal((K, n, 3))
+    dp = rng.standard_normal((K, n, 3)) * m[None, :, None]
+    eps2 = 1e-4
+    g, dg, gt, dgt = ctx.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, eps2)
+    g2, gt2 = ctx.grad_v_sum_tangent(m, q, dq, eps2)
+    for k in range(K):
+        rg, rdg, rgt, rdgt = oracle.grad_v_dgrad_v_sum_tangent(m, q, p, dq[k], dp[k], eps2)
+        assert rel_err(g, rg) <= TOL and rel_err(dg, rdg) <= TOL
+        assert rel_err(gt[k], rgt) <= 1e-11 and rel_err(dgt[k], rdgt) <= 1e-11
+        r2g, r2gt = oracle.grad_v_sum_tangent(m, q, dq[k], eps2)
+        assert rel_err(g2, r2g) <= TOL and rel_err(gt2[k], r2gt) <= 1e-11
+
+
+def test_tangent_matches_finite_differences(ctx, oracle):
+    m, q, p = oracle.make_plummer(64, 43)
+    rng = np.random.default_rng(1)
+    dq = rng.standard_normal((1, 64, 3))
+    dp = rng.standard_normal((1, 64, 3)) * m[None, :, None]
+    _, _, gt, dgt = ctx.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, 1e-2)
+    hstep = 1e-6
+    gp, dgp = ctx.grad_v_dgrad_v_sum(m, q + hstep * dq[0], p + hstep * dp[0], 1e-2)
+    gm, dgm = ctx.grad_v_dgrad_v_sum(m, q - hstep * dq[0], p - hstep * dp[0], 1e-2)
+    assert rel_err(gt[0], (gp - gm) / (2 * hstep)) < 1e-6
+    assert rel_err(dgt[0], (dgp - dgm) / (2 * hstep)) < 1e-6
