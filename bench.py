@@ -132,35 +132,22 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
-    shard = (n + world - 1) // world
-    t0, t1 = min(rank * shard, n), min((rank + 1) * shard, n)
+    from nbk.sharded import ShardedAccJerk, make_plan
+    plan = make_plan(n, world, rank)
+    t0, t1 = plan.t0, plan.t1
     ctx = nbk.Context(local)
     m, q, p = nbh.make_plummer(n, SEED)  # same seeded bodies on every rank
 
-    # ---- device-resident state: this rank's shard of packed (q, v, m); all-gather target
+    # ---- device-resident state: this rank's shard of packed (q, v, m) inside the gather buffer
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-    d_m = torch.from_numpy(m).to(dev)
-    d_q = torch.from_numpy(q).to(dev)
-    d_p = torch.from_numpy(p).to(dev)
-    npad = shard * world
-    packed_all = torch.zeros(npad, nbk.PACKED_DOUBLES, dtype=torch.float64, device=dev)
-    packed_loc = torch.zeros(shard, nbk.PACKED_DOUBLES, dtype=torch.float64, device=dev)
-    if t1 > t0:
-        ctx.dev_pack(t1 - t0, d_m[t0:t1].data_ptr(), d_q[t0:t1].data_ptr(), d_p[t0:t1].data_ptr(),
-                     False, packed_loc.data_ptr(), sptr)
-    g = torch.zeros(max(t1 - t0, 1), 3, dtype=torch.float64, device=dev)
-    dg = torch.zeros_like(g)
+    sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))
+    sh.load_local(m, q, p)
+    g, dg = sh.g, sh.dg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
-        if world > 1:
-            dist.all_gather_into_tensor(packed_all, packed_loc)
-            src = packed_all
-        else:
-            src = packed_loc
-        ctx.dev_grad_v_dgrad_v_sum(src.data_ptr(), n, 0.0, (t0, t1), (0, n), g.data_ptr(),
-                                   dg.data_ptr(), False, sptr)
+        sh.step(0.0)
 
     def barrier():
         if world > 1:
@@ -196,7 +183,7 @@ def run_ours(args):
     # ---- dominant kernel alone (this rank's share), live CUDA events, for the roofline
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
-    src = packed_all if world > 1 else packed_loc
+    src = sh.packed_all
     for k in range(args.steps):
         flush.zero_()
         kev[k][0].record(stream)
@@ -256,8 +243,9 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Plummer sphere N={n}, Hermite acc+jerk sweep "
                                    "(BASELINE.json configs[2])", "n": n, "eps": 0.0, "seed": SEED,
-                       "sharding": f"targets/{world}, NCCL all-gather of packed (q,v,m) per step"
-                       if world > 1 else "single GPU",
+                       "sharding": (f"targets/{world}, NCCL all-gather of packed (q,v,m) per step"
+                                    + (", overlapped with the local-source sweep" if args.overlap
+                                       else "")) if world > 1 else "single GPU",
                        "l2": "flushed between timed iterations (256 MiB write)"},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
@@ -294,6 +282,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--overlap", type=int, default=0,
+                    help="1: sweep local sources while the all-gather is in flight")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

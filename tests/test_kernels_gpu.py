@@ -246,3 +246,26 @@ def test_tangent_matches_finite_differences(ctx, oracle):
     gm, dgm = ctx.grad_v_dgrad_v_sum(m, q - hstep * dq[0], p - hstep * dp[0], 1e-2)
     assert rel_err(gt[0], (gp - gm) / (2 * hstep)) < 1e-6
     assert rel_err(dgt[0], (dgp - dgm) / (2 * hstep)) < 1e-6
+
+
+def test_sharded_driver_single_rank(ctx, oracle):
+    """nbk/sharded.py with the real kernel on one GPU (world 1): device-pointer API, torch
+    stream, packed layout."""
+    import torch
+    from nbk.sharded import ShardedAccJerk, make_plan
+    n = 5000
+    m, q, p = oracle.make_plummer(n, 20243)
+    sh = ShardedAccJerk(make_plan(n, 1, 0), torch.device("cuda", 0), ctx=ctx)
+    sh.load_local(m, q, p)
+    g, dg = sh.step(0.0)
+    torch.cuda.synchronize()
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    assert rel_err(g.cpu().numpy(), g_ref) <= TOL and rel_err(dg.cpu().numpy(), dg_ref) <= TOL
+    # split into source pieces with accumulate, as the overlap path does
+    g2, dg2 = torch.zeros_like(g), torch.zeros_like(dg)
+    s = torch.cuda.current_stream().cuda_stream
+    for k, (s0, s1) in enumerate([(1000, 3000), (0, 1000), (3000, n)]):
+        ctx.dev_grad_v_dgrad_v_sum(sh.packed_all.data_ptr(), n, 0.0, (0, n), (s0, s1),
+                                   g2.data_ptr(), dg2.data_ptr(), k > 0, s)
+    torch.cuda.synchronize()
+    assert rel_err(g2.cpu().numpy(), g_ref) <= TOL and rel_err(dg2.cpu().numpy(), dg_ref) <= TOL
