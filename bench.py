@@ -109,7 +109,7 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print_line(line)
 
 
 def run_ours(args):
@@ -268,7 +268,7 @@ def run_ours(args):
                 "value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port",
                 "sample": f"symmetric i<j acc+jerk sweep over the first {args.cpu_sample} bodies of "
                           f"the same Plummer workload ({cpu_dt:.2f} s wall, OpenMP, all host threads)"}
-        print(json.dumps(line), flush=True)
+        print_line(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -286,10 +286,25 @@ def main():
                     help="1: sweep local sources while the all-gather is in flight")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout must carry exactly ONE JSON line: route everything libraries print there (NCCL's
+    # version banner, ...) to stderr and give print_line() the real stdout back.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def print_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
