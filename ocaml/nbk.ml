@@ -1,0 +1,60 @@
+(* nbk.ml — OCaml binding of libnbk (include/nbk.h) for farr/direct-nbody.
+
+   NOT COMPILED HERE (no OCaml toolchain in the build image); see nbk_stubs.c.  Drop this file
+   and nbk_stubs.c into the reference tree, add Nbk to nbody.mllib, and link with
+   -lnbk (INTEGRATION.md has the myocamlbuild.ml lines).
+
+   [range] is (t0, t1, s0, s1): targets [t0,t1) x sources [s0,s1), indices into the body
+   array; outputs are indexed from t0.  Every function raises [Failure msg] on error. *)
+
+open Bigarray
+
+type ctx
+type vec = (float, float64_elt, c_layout) Array1.t
+type range = int * int * int * int
+
+external create : int -> ctx = "nbk_ml_create"
+
+external grad_v_sum : ctx -> vec -> vec -> float -> range -> vec -> unit
+  = "nbk_ml_grad_v_sum_bc" "nbk_ml_grad_v_sum"
+
+external grad_v_dgrad_v_sum : ctx -> vec -> vec -> vec -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_grad_v_dgrad_v_sum_bc" "nbk_ml_grad_v_dgrad_v_sum"
+
+external grad_v_dgrad_v_sum_predicted :
+  ctx -> vec -> vec -> vec -> vec -> vec -> vec -> float -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_predicted_bc" "nbk_ml_predicted"
+
+external energy : ctx -> vec -> vec -> vec -> float -> float * float = "nbk_ml_energy"
+
+external v_sum : ctx -> vec -> vec -> float -> range -> vec -> float
+  = "nbk_ml_v_sum_bc" "nbk_ml_v_sum"
+
+external kick_sum : ctx -> vec -> vec -> vec -> float -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_kick_sum_bc" "nbk_ml_kick_sum"
+
+external grad_v_dgrad_v_sum_tangent :
+  ctx -> vec -> vec -> vec -> int -> vec -> vec -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_tangent_bc" "nbk_ml_tangent"
+
+(* One context per process, created on first use (the reference is single-threaded and keeps
+   its configuration in globals such as Base.eps2, base.ml:20-34). *)
+let the_ctx = lazy (create 0)
+let ctx () = Lazy.force the_ctx
+
+let vec n = Array1.create float64 c_layout n
+
+(* Packing helpers: the reference keeps bodies as records of 3-element float arrays
+   (SURVEY.md §8 a16); O(N) copies either side of an O(N^2) sweep. *)
+let pack3 get bs =
+  let n = Array.length bs in
+  let a = vec (3 * n) in
+  Array.iteri (fun i b -> let v = get b in
+                for k = 0 to 2 do a.{3 * i + k} <- v.(k) done) bs;
+  a
+
+let pack1 get bs =
+  let n = Array.length bs in
+  let a = vec n in
+  Array.iteri (fun i b -> a.{i} <- get b) bs;
+  a

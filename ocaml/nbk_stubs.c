@@ -1,0 +1,172 @@
+/* nbk_stubs.c — OCaml <-> libnbk glue: the C side of the `external` declarations in nbk.ml.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S BUILD IMAGE: the image has no OCaml toolchain (no ocaml,
+ * ocamlfind, ocamlbuild, opam or dune), so <caml/...> headers are absent.  These sources are
+ * what a maintainer of farr/direct-nbody adds to the reference tree; they are mechanical
+ * (unbox arguments, call include/nbk.h, raise Failure on a non-zero code) and every call
+ * they make is exercised here through the same C ABI from Python/C++ (tests/).
+ *
+ * All arrays are Bigarray.Array1 of float64, c_layout (bigarray is already linked for every
+ * target of the reference, _tags:5-11), so Caml_ba_data_val gives the double* libnbk wants
+ * without copying.  libnbk never calls back into OCaml and never keeps a pointer past the
+ * call, so no root registration is needed; the calls are long (an O(N^2) sweep), so the
+ * runtime lock could be released around them, but the reference is single-threaded
+ *  and nothing is gained.
+ */
+#include <caml/alloc.h>
+#include <caml/bigarray.h>
+#include <caml/custom.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+
+#include "nbk.h"
+
+#define Ctx_val(v) (*((nbk_ctx **)Data_custom_val(v)))
+#define D(v) ((double *)Caml_ba_data_val(v))
+
+static void ctx_finalize(value v) {
+  if (Ctx_val(v)) nbk_destroy(Ctx_val(v));
+  Ctx_val(v) = NULL;
+}
+
+static struct custom_operations ctx_ops = {"org.nbk.ctx",       ctx_finalize,
+                                           custom_compare_default, custom_hash_default,
+                                           custom_serialize_default, custom_deserialize_default,
+                                           custom_compare_ext_default, custom_fixed_length_default};
+
+static void check(nbk_ctx *ctx, int rc) {
+  if (rc != NBK_OK) caml_failwith(nbk_last_error(ctx)); /* reference convention: exceptions */
+}
+
+CAMLprim value nbk_ml_create(value device) {
+  CAMLparam1(device);
+  CAMLlocal1(v);
+  nbk_ctx *ctx = NULL;
+  int rc = nbk_create(&ctx, Int_val(device));
+  if (rc != NBK_OK) caml_failwith(nbk_last_error(NULL));
+  v = caml_alloc_custom(&ctx_ops, sizeof(nbk_ctx *), 0, 1);
+  Ctx_val(v) = ctx;
+  CAMLreturn(v);
+}
+
+/* external grad_v_sum : ctx -> m -> q -> eps2:float -> range(t0,t1,s0,s1) -> gsum -> unit */
+CAMLprim value nbk_ml_grad_v_sum(value ctx, value m, value q, value eps2, value rng,
+                                 value gsum) {
+  CAMLparam5(ctx, m, q, eps2, rng);
+  CAMLxparam1(gsum);
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx),
+        nbk_grad_v_sum(Ctx_val(ctx), n, D(m), D(q), Double_val(eps2), Int_val(Field(rng, 0)),
+                       Int_val(Field(rng, 1)), Int_val(Field(rng, 2)), Int_val(Field(rng, 3)),
+                       D(gsum)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_grad_v_sum_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_grad_v_sum(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
+/* external grad_v_dgrad_v_sum : ctx -> m -> q -> p -> eps2 -> range -> gsum -> dgsum -> unit */
+CAMLprim value nbk_ml_grad_v_dgrad_v_sum(value ctx, value m, value q, value p, value eps2,
+                                         value rng, value gsum, value dgsum) {
+  CAMLparam5(ctx, m, q, p, eps2);
+  CAMLxparam3(rng, gsum, dgsum);
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx),
+        nbk_grad_v_dgrad_v_sum(Ctx_val(ctx), n, D(m), D(q), D(p), Double_val(eps2),
+                               Int_val(Field(rng, 0)), Int_val(Field(rng, 1)),
+                               Int_val(Field(rng, 2)), Int_val(Field(rng, 3)), D(gsum),
+                               D(dgsum)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_grad_v_dgrad_v_sum_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_grad_v_dgrad_v_sum(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+}
+
+/* external grad_v_dgrad_v_sum_predicted :
+     ctx -> t -> m -> q -> p -> f -> df -> nt:float -> eps2 -> range -> gsum -> dgsum -> unit */
+CAMLprim value nbk_ml_predicted_bc(value *a, int n) {
+  (void)n;
+  int nb = (int)Caml_ba_array_val(a[2])->dim[0];
+  value rng = a[9];
+  check(Ctx_val(a[0]),
+        nbk_grad_v_dgrad_v_sum_predicted(Ctx_val(a[0]), nb, D(a[1]), D(a[2]), D(a[3]), D(a[4]),
+                                         D(a[5]), D(a[6]), Double_val(a[7]), Double_val(a[8]),
+                                         Int_val(Field(rng, 0)), Int_val(Field(rng, 1)),
+                                         Int_val(Field(rng, 2)), Int_val(Field(rng, 3)), D(a[10]),
+                                         D(a[11])));
+  return Val_unit;
+}
+CAMLprim value nbk_ml_predicted(value a0, value a1, value a2, value a3, value a4, value a5,
+                                value a6, value a7, value a8, value a9, value a10, value a11) {
+  value a[12] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11};
+  return nbk_ml_predicted_bc(a, 12);
+}
+
+/* external energy : ctx -> m -> q -> p -> eps2 -> float * float   (ke, pe) */
+CAMLprim value nbk_ml_energy(value ctx, value m, value q, value p, value eps2) {
+  CAMLparam5(ctx, m, q, p, eps2);
+  CAMLlocal1(res);
+  double ke = 0.0, pe = 0.0;
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx), nbk_energy(Ctx_val(ctx), n, D(m), D(q), D(p), Double_val(eps2), &ke, &pe));
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, caml_copy_double(ke));
+  Store_field(res, 1, caml_copy_double(pe));
+  CAMLreturn(res);
+}
+
+/* external v_sum : ctx -> m -> q -> eps2 -> range -> phi -> float (sum of phi) */
+CAMLprim value nbk_ml_v_sum(value ctx, value m, value q, value eps2, value rng, value phi) {
+  CAMLparam5(ctx, m, q, eps2, rng);
+  CAMLxparam1(phi);
+  double total = 0.0;
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx),
+        nbk_v_sum(Ctx_val(ctx), n, D(m), D(q), Double_val(eps2), Int_val(Field(rng, 0)),
+                  Int_val(Field(rng, 1)), Int_val(Field(rng, 2)), Int_val(Field(rng, 3)), D(phi),
+                  &total));
+  CAMLreturn(caml_copy_double(total));
+}
+CAMLprim value nbk_ml_v_sum_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_v_sum(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
+/* external kick_sum : ctx -> m -> q -> v -> eta -> dt -> range -> dv -> tmin -> unit */
+CAMLprim value nbk_ml_kick_sum_bc(value *a, int n) {
+  (void)n;
+  int nb = (int)Caml_ba_array_val(a[1])->dim[0];
+  value rng = a[6];
+  check(Ctx_val(a[0]),
+        nbk_kick_sum(Ctx_val(a[0]), nb, D(a[1]), D(a[2]), D(a[3]), Double_val(a[4]),
+                     Double_val(a[5]), Int_val(Field(rng, 0)), Int_val(Field(rng, 1)),
+                     Int_val(Field(rng, 2)), Int_val(Field(rng, 3)), D(a[7]), D(a[8])));
+  return Val_unit;
+}
+CAMLprim value nbk_ml_kick_sum(value a0, value a1, value a2, value a3, value a4, value a5,
+                               value a6, value a7, value a8) {
+  value a[9] = {a0, a1, a2, a3, a4, a5, a6, a7, a8};
+  return nbk_ml_kick_sum_bc(a, 9);
+}
+
+/* external grad_v_dgrad_v_sum_tangent :
+     ctx -> m -> q -> p -> k:int -> dq -> dp -> eps2 -> range -> gsum_tan -> dgsum_tan -> unit */
+CAMLprim value nbk_ml_tangent_bc(value *a, int n) {
+  (void)n;
+  int nb = (int)Caml_ba_array_val(a[1])->dim[0];
+  value rng = a[8];
+  check(Ctx_val(a[0]),
+        nbk_grad_v_dgrad_v_sum_tangent(Ctx_val(a[0]), nb, D(a[1]), D(a[2]), D(a[3]), Int_val(a[4]),
+                                       D(a[5]), D(a[6]), Double_val(a[7]), Int_val(Field(rng, 0)),
+                                       Int_val(Field(rng, 1)), Int_val(Field(rng, 2)),
+                                       Int_val(Field(rng, 3)), NULL, NULL, D(a[9]), D(a[10])));
+  return Val_unit;
+}
+CAMLprim value nbk_ml_tangent(value a0, value a1, value a2, value a3, value a4, value a5,
+                              value a6, value a7, value a8, value a9, value a10) {
+  value a[11] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10};
+  return nbk_ml_tangent_bc(a, 11);
+}
