@@ -37,6 +37,9 @@ struct nbk_ctx {
   // resident bodies
   int resident_n = 0;
   DevBuf d_res_m, d_res_packed;
+  // resident Hermite state
+  int hermite_n = 0;
+  DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
   // pinned host staging for scalar read-back
   double *h_scalar = nullptr;
 };
@@ -486,7 +489,8 @@ void nbk_destroy(nbk_ctx *c) {
   DevBuf *bufs[] = {&c->d_t,     &c->d_f,      &c->d_df,     &c->d_aux_in2,
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
                     &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
-                    &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed};
+                    &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
+                    &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -781,6 +785,65 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
                           double *dv, double *tmin) {
   NEED_RESIDENT();
   return run_kick(ctx, (const double *)ctx->d_res_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
+}
+
+// ---- device-resident Hermite state -------------------------------------------------------------
+int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, const double *q,
+                       const double *p, const double *f, const double *df) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n <= 0 || !t || !m || !q || !p || !f || !df)
+    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::string buf((size_t)n * HB * sizeof(double), '\0');
+  double *h = reinterpret_cast<double *>(&buf[0]);
+  for (int i = 0; i < n; ++i) {
+    double *r = h + (size_t)i * HB;
+    r[0] = t[i];
+    r[1] = m[i];
+    for (int k = 0; k < 3; ++k) {
+      r[2 + k] = q[3 * i + k];
+      r[5 + k] = p[3 * i + k];
+      r[8 + k] = f[3 * i + k];
+      r[11 + k] = df[3 * i + k];
+    }
+  }
+  const int nblk = (n + 255) / 256;
+  TRY(reserve(ctx, ctx->d_hstate, (size_t)n * HB * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_hpartial, (size_t)nblk * 6 * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_hticket, 64));
+  TRY(reserve(ctx, ctx->d_hout, 64));
+  CK(cudaMemcpyAsync(ctx->d_hstate.p, h, (size_t)n * HB * sizeof(double), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_hticket.p, 0, 64, ctx->stream));
+  TRY(sync(ctx));
+  ctx->hermite_n = n;
+  return NBK_OK;
+}
+
+int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
+                         const double *upd_state, double *gsum, double *dgsum) {
+  if (!ctx) return NBK_ERR_ARG;
+  const int n = ctx->hermite_n;
+  if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state: call nbk_hermite_upload");
+  if (i < 0 || i >= n || upd >= n || (upd >= 0 && !upd_state) || !gsum || !dgsum)
+    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_body_sum: bad arguments (i=%d upd=%d n=%d)", i, upd, n);
+  HermiteUpd u;
+  memset(&u, 0, sizeof u);
+  if (upd >= 0) memcpy(u.s, upd_state, sizeof u.s);
+  const int nblk = (n + 255) / 256;
+  hermite_body_kernel<<<nblk, 256, 0, ctx->stream>>>(
+      (double *)ctx->d_hstate.p, n, i, nt, eps2, upd, u, (double *)ctx->d_hpartial.p,
+      (unsigned int *)ctx->d_hticket.p, (double *)ctx->d_hout.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_hout.p, 6 * sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  TRY(sync(ctx));
+  for (int k = 0; k < 3; ++k) {
+    gsum[k] = ctx->h_scalar[k];
+    dgsum[k] = ctx->h_scalar[3 + k];
+  }
+  return NBK_OK;
 }
 
 // ---- raw device-pointer API ----------------------------------------------------------------------

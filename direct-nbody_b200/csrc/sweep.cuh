@@ -783,6 +783,112 @@ template <class Op> __global__ void small_fix_kernel(const SweepParams P, int nc
   Op::store(P, i, a);
 }
 
+// ---- Hermite.advance_body on device-resident state ------------------------------------------
+// Resident Hermite.b (hermite.ml:20-29) as 16 doubles per body:
+// {t, m, q[3], p[3], f[3], df[3], 0, 0}.  One launch = one force evaluation of
+// Hermite.advance_body (hermite.ml:95-115): optionally overwrite body `upd` with the result
+// of the previous step (passed by value, so no separate copy or launch), predict every body
+// to time nt with the reference's operation sequence (hermite.ml:53-72), sum
+// grad_v_dgrad_v(target i, j) over j != i source-parallel, reduce in fixed order; the last
+// CTA to finish (ticket counter) adds the per-CTA partials in CTA order and writes the result.
+constexpr int HB = 16;
+struct HermiteUpd {
+  double s[13];  // t, q[3], p[3], f[3], df[3]
+};
+
+__device__ __forceinline__ void hermite_predict(const double *r, double nt, double &m,
+                                                double (&qp)[3], double (&vp)[3]) {
+  m = r[1];
+  const double dt = __dsub_rn(nt, r[0]);
+  const double pc = __ddiv_rn(dt, m);
+  const double fc = __dmul_rn(__dmul_rn(pc, dt), 0.5);
+  const double dfc = __ddiv_rn(__dmul_rn(fc, dt), 3.0);
+  const double pdfc = __dmul_rn(__dmul_rn(dt, dt), 0.5);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double qk = r[2 + k], pk = r[5 + k], fk = r[8 + k], dfk = r[11 + k];
+    qp[k] = __dadd_rn(__dadd_rn(__dadd_rn(qk, __dmul_rn(pc, pk)), __dmul_rn(fc, fk)),
+                      __dmul_rn(dfc, dfk));
+    const double pp = __dadd_rn(__dadd_rn(pk, __dmul_rn(dt, fk)), __dmul_rn(pdfc, dfk));
+    vp[k] = __ddiv_rn(pp, m);
+  }
+}
+
+__global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ state, int n,
+                                                           int it, double nt, double eps2,
+                                                           int upd, const HermiteUpd u,
+                                                           double *__restrict__ partial,
+                                                           unsigned int *__restrict__ ticket,
+                                                           double *__restrict__ out) {
+  __shared__ double red[8][6];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x * 256 + tid;
+  SweepParams P;
+  P.eps2 = eps2;
+  auto fetch = [&](int b, double *r) {
+    const double2 *g = reinterpret_cast<const double2 *>(state + (size_t)b * HB);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      double2 v = g[c];
+      r[2 * c] = v.x;
+      r[2 * c + 1] = v.y;
+    }
+    if (b == upd) {
+      r[0] = u.s[0];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) r[2 + c] = u.s[1 + c];
+    }
+  };
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  {
+    double rt[14], mt, qt[3], vt[3];
+    fetch(it, rt);
+    hermite_predict(rt, nt, mt, qt, vt);
+    OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+    if (j < n) {
+      double rj[14], mj, qj[3], vj[3];
+      fetch(j, rj);
+      if (j == upd) {  // persist the previous step's result for later launches
+        double *w = state + (size_t)j * HB;
+        w[0] = rj[0];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) w[2 + c] = rj[2 + c];
+      }
+      hermite_predict(rj, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, j == it, P);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+  __syncthreads();
+  if (tid < 6) {
+    double a = red[0][tid];
+    for (int w = 1; w < 8; ++w) a += red[w][tid];
+    partial[(size_t)blockIdx.x * 6 + tid] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && tid < 6) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) a += __ldcg(&partial[(size_t)b * 6 + tid]);
+    // gsum = -m_i acc (gradient convention of Base.grad_v_dgrad_v)
+    const double mi = state[(size_t)it * HB + 1];
+    out[tid] = -mi * a;
+    if (tid == 0) *ticket = 0u;
+  }
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

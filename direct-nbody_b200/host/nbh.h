@@ -42,6 +42,55 @@ int nbh_add_mass_disc(int n, uint64_t seed, double heavyfrac, double heavyfac, d
 int nbh_rescale_to_standard_units(nbk_ctx *ctx, int n, double *m, double *q, double *p,
                                   double eps2);
 
+/* ---- Energy.Make(B) (energy.ml:55-82) ------------------------------------------------------ */
+/* total_kinetic_energy, total_potential_energy; energy = *ke + *pe (energy.ml:75-78). */
+int nbh_energy(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+               double eps2, double *ke, double *pe);
+/* Analysis.bodies_to_el_phase_space (analysis.ml:904-919): el[4n] = {E, E/m, |L|, |L|/m}. */
+int nbh_bodies_to_el_phase_space(nbk_ctx *ctx, int n, const double *m, const double *q,
+                                 const double *p, double eps2, double *el);
+
+/* ---- Omelyan_advancer.OA.advance h bs (omelyan_advancer.ml:96-104) -------------------------- */
+int nbh_omelyan_advance(nbk_ctx *ctx, int n, const double *m, double *q, double *p, double *t,
+                        double h, double eps2);
+
+/* ---- Leapfrog (leapfrog.ml:113-165): flat image of Leapfrog.b array ------------------------ */
+/* advance bs dt eta: output order is the reference's (sorted by dt_max); id[] follows. */
+int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
+                         double *q, double *v, double dt, double eta, long *nkicks);
+int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max,
+                                  double *m, double *q, double *v, double dt, int nsteps);
+
+/* ---- Hermite.advance bs dt sf (hermite.ml:180-189): flat image of Hermite.b array ----------- */
+/* Output in id order (hermite.ml:136); *nsteps is bumped like Base.nsteps (hermite.ml:124). */
+int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, double *q, double *p,
+                        double *h, double *f, double *df, double dt, double sf, double eps2,
+                        long *nsteps);
+
+/* ---- Advancer.A.advance ?extpot bs dt sf (advancer.ml:422-428) ------------------------------ */
+/* state[i*35..] = {t, m, q[3], p[3], h, hmax, t0, dVdq0[3], dVdq1[3], dVdq2[3], p0[3], q0[3],
+ * q1[3], q2[3], cs[3]}: the Advancer.A.body record (advancer.ml:27-45); fresh bodies carry NaN
+ * after p (A.make, advancer.ml:98-116).  extpot = gradient of an external potential
+ * (`?extpot : b -> float array`), or NULL.  Output order: sorted by hmax, id[] follows.
+ * stats (may be NULL) receives {interact_bodies calls, pair interactions evaluated}. */
+#define NBH_ADV_STRIDE 35
+typedef void (*nbh_extpot_fn)(void *arg, double m, const double *q, const double *p, double *gv);
+int nbh_advancer_advance(nbk_ctx *ctx, int n, int *id, double *state, double dt, double sf,
+                         double eps2, nbh_extpot_fn extpot, void *extpot_arg, long *stats);
+/* The field of test/advance_test.ml:39-46 (Plummer, M = 1, eps = 0.1) and its potential energy. */
+void nbh_extpot_plummer_test(void *arg, double m, const double *q, const double *p, double *gv);
+double nbh_extpot_plummer_test_energy(int n, const double *m, const double *q);
+
+/* ---- Integrator.Make(B)(A).constant_sf_integrate (integrator.ml:58-84) over Advancer.A ------ */
+/* Steps by min(ci, max_dt) with A.advance until t >= t0 + dt; after each step the relative
+ * energy error against the initial energy is checked: > max_eg_err returns NBH_ERR_EG (the
+ * reference raises Eg_err with the last good state: state/id are left at that state).
+ * energy_errors (may be NULL, capacity cap) receives the error after every step; *nerr their
+ * number. */
+int nbh_constant_sf_integrate(nbk_ctx *ctx, int n, int *id, double *state, double dt, double ci,
+                              double sf, double max_eg_err, double eps2, double *energy_errors,
+                              int cap, int *nerr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,8 @@ _d, _i = C.c_double, C.c_int
 _pd = C.POINTER(C.c_double)
 _vp = C.c_void_p
 _u64 = C.c_uint64
+_pi = C.POINTER(C.c_int)
+_pl = C.POINTER(C.c_long)
 
 SYMBOLS = {
     "nbh_last_error": (C.c_char_p, []),
@@ -27,7 +29,17 @@ SYMBOLS = {
     "nbh_adjust_frame": (_i, [_i, _pd, _pd, _pd]),
     "nbh_add_mass_disc": (_i, [_i, _u64, _d, _d, _pd, _pd]),
     "nbh_rescale_to_standard_units": (_i, [_vp, _i, _pd, _pd, _pd, _d]),
+    "nbh_energy": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd, _pd]),
+    "nbh_bodies_to_el_phase_space": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd]),
+    "nbh_omelyan_advance": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _d, _d]),
+    "nbh_leapfrog_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _d, _pl]),
+    "nbh_leapfrog_advance_const_dt": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _i]),
+    "nbh_hermite_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d, _d, _pl]),
+    "nbh_advancer_advance": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _vp, _vp, _pl]),
+    "nbh_extpot_plummer_test_energy": (_d, [_i, _pd, _pd]),
+    "nbh_constant_sf_integrate": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _d, _d, _pd, _i, _pi]),
 }
+ADV_STRIDE = 35
 
 
 class NbhError(RuntimeError):
@@ -103,3 +115,182 @@ def rescale_to_standard_units(ctx: nbk.Context, m, q, p, eps2=0.0):
     m, q, p = (np.array(a, dtype=np.float64, order="C") for a in (m, q, p))
     _ck(load_library().nbh_rescale_to_standard_units(ctx._h, len(m), _p(m), _p(q), _p(p), eps2))
     return m, q, p
+
+
+def _ip(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_pi)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ------------------------------------------------------------------ Energy / Analysis
+def energy(ctx, m, q, p, eps2=0.0):
+    """Energy.Make(B).energy split as (ke, pe) (energy.ml:57-78)."""
+    m, q, p = _f(m), _f(q), _f(p)
+    ke, pe = _d(), _d()
+    _ck(load_library().nbh_energy(ctx._h, len(m), _p(m), _p(q), _p(p), eps2, C.byref(ke),
+                                  C.byref(pe)))
+    return ke.value, pe.value
+
+
+def bodies_to_el_phase_space(ctx, m, q, p, eps2=0.0):
+    m, q, p = _f(m), _f(q), _f(p)
+    el = np.empty((len(m), 4))
+    _ck(load_library().nbh_bodies_to_el_phase_space(ctx._h, len(m), _p(m), _p(q), _p(p), eps2,
+                                                    _p(el)))
+    return el
+
+
+# ------------------------------------------------------------------ Omelyan_advancer.OA
+def omelyan_advance(ctx, m, q, p, t, h, eps2=0.0):
+    """OA.advance h bs (omelyan_advancer.ml:96-104): functional, returns (q, p, t)."""
+    m = _f(m)
+    q, p = _f(q).copy(), _f(p).copy()
+    tt = _d(t)
+    _ck(load_library().nbh_omelyan_advance(ctx._h, len(m), _p(m), _p(q), _p(p), C.byref(tt), h,
+                                           eps2))
+    return q, p, tt.value
+
+
+# ------------------------------------------------------------------ Leapfrog
+class LeapfrogState:
+    """Flat image of a Leapfrog.b array; Leapfrog.make sets t = 0, dt_max = 0, v = p / m
+    (leapfrog.ml:28-34)."""
+
+    def __init__(self, m, q, p):
+        n = len(m)
+        self.id = np.arange(1, n + 1, dtype=np.int32)
+        self.t, self.dt_max = np.zeros(n), np.zeros(n)
+        self.m, self.q = _f(m).copy(), _f(q).copy()
+        self.v = _f(p) / self.m[:, None]
+        self.nkicks = 0
+
+    @property
+    def p(self):  # leapfrog.ml:20
+        return self.v * self.m[:, None]
+
+    def copy(self):
+        import copy
+        return copy.deepcopy(self)
+
+
+def leapfrog_advance(ctx, s, dt, eta):
+    o = s.copy()
+    nk = C.c_long(0)
+    _ck(load_library().nbh_leapfrog_advance(ctx._h, len(o.m), _ip(o.id), _p(o.t), _p(o.dt_max),
+                                            _p(o.m), _p(o.q), _p(o.v), dt, eta, C.byref(nk)))
+    o.nkicks = nk.value
+    return o
+
+
+def leapfrog_advance_const_dt(ctx, s, dt, nsteps):
+    o = s.copy()
+    _ck(load_library().nbh_leapfrog_advance_const_dt(ctx._h, len(o.m), _ip(o.id), _p(o.t),
+                                                     _p(o.dt_max), _p(o.m), _p(o.q), _p(o.v), dt,
+                                                     nsteps))
+    return o
+
+
+# ------------------------------------------------------------------ Hermite
+class HermiteState:
+    """Flat image of a Hermite.b array (hermite.ml:20-29); Hermite.make sets h = -1."""
+
+    def __init__(self, m, q, p, t=0.0):
+        n = len(m)
+        self.id = np.arange(1, n + 1, dtype=np.int32)
+        self.t = np.full(n, float(t))
+        self.m, self.q, self.p = _f(m).copy(), _f(q).copy(), _f(p).copy()
+        self.h = np.full(n, -1.0)
+        self.f, self.df = np.zeros((n, 3)), np.zeros((n, 3))
+        self.nsteps = 0
+
+    def copy(self):
+        import copy
+        return copy.deepcopy(self)
+
+
+def hermite_advance(ctx, s, dt, sf, eps2=0.0):
+    o = s.copy()
+    ns = C.c_long(o.nsteps)
+    _ck(load_library().nbh_hermite_advance(ctx._h, len(o.m), _ip(o.id), _p(o.t), _p(o.m), _p(o.q),
+                                           _p(o.p), _p(o.h), _p(o.f), _p(o.df), dt, sf, eps2,
+                                           C.byref(ns)))
+    o.nsteps = ns.value
+    return o
+
+
+# ------------------------------------------------------------------ Advancer.A / Integrator
+class AdvancerState:
+    """Flat image of an Advancer.A.body array (advancer.ml:27-45); A.make leaves everything
+    after p as NaN (advancer.ml:98-116)."""
+
+    def __init__(self, m, q, p, t=0.0):
+        n = len(m)
+        self.id = np.arange(n, dtype=np.int32)
+        self.state = np.full((n, ADV_STRIDE), np.nan)
+        self.state[:, 0] = t
+        self.state[:, 1] = m
+        self.state[:, 2:5] = q
+        self.state[:, 5:8] = p
+        self.stats = (0, 0)
+
+    t = property(lambda s: s.state[:, 0])
+    m = property(lambda s: s.state[:, 1])
+    q = property(lambda s: np.ascontiguousarray(s.state[:, 2:5]))
+    p = property(lambda s: np.ascontiguousarray(s.state[:, 5:8]))
+    hmax = property(lambda s: s.state[:, 9])
+
+    def copy(self):
+        import copy
+        o = copy.deepcopy(self)
+        o.state = np.ascontiguousarray(o.state)
+        return o
+
+
+def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None):
+    """Advancer.A.advance ?extpot bs dt sf; extpot is None or "plummer_test"
+    (the field of test/advance_test.ml:39-46)."""
+    o = s.copy()
+    stats = (C.c_long * 2)(0, 0)
+    fn = None
+    if extpot == "plummer_test":
+        fn = C.cast(load_library().nbh_extpot_plummer_test, _vp)
+    elif extpot is not None:
+        raise ValueError("extpot: None or 'plummer_test'")
+    _ck(load_library().nbh_advancer_advance(ctx._h, len(o.id), _ip(o.id), _p(o.state), dt, sf,
+                                            eps2, fn, None, stats))
+    o.stats = (stats[0], stats[1])
+    return o
+
+
+def extpot_plummer_test_energy(m, q):
+    m, q = _f(m), _f(q)
+    return load_library().nbh_extpot_plummer_test_energy(len(m), _p(m), _p(q))
+
+
+class EgErr(RuntimeError):
+    """Integrator.Eg_err (integrator.ml:33): carries the last good state."""
+
+    def __init__(self, state, errors):
+        super().__init__("energy error bound exceeded")
+        self.state, self.errors = state, errors
+
+
+def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0):
+    """Integrator.Make(B)(Advancer.A).constant_sf_integrate (integrator.ml:58-84).  Returns
+    (final state, energy errors after each step); raises EgErr like the reference."""
+    o = s.copy()
+    cap = 4096
+    errs = np.zeros(cap)
+    nerr = C.c_int(0)
+    rc = load_library().nbh_constant_sf_integrate(ctx._h, len(o.id), _ip(o.id), _p(o.state), dt,
+                                                  ci, sf, max_eg_err, eps2, _p(errs), cap,
+                                                  C.byref(nerr))
+    e = errs[:min(nerr.value, cap)].copy()
+    if rc == -11:
+        raise EgErr(o, e)
+    _ck(rc)
+    return o, e

@@ -49,6 +49,8 @@ SYMBOLS = {
     "nbk_resident_grad_v_dgrad_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_kick_sum": (_i, [_vp, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd]),
+    "nbk_hermite_body_sum": (_i, [_vp, _i, _d, _d, _i, _pd, _pd, _pd]),
     "nbk_dev_pack": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "nbk_dev_grad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -284,6 +286,18 @@ class Context:
         self._ck(self._lib.nbk_resident_kick_sum(self._h, eta, dt, t0, t1, s0, s1, _p(dv),
                                                  _p(tmin)))
         return dv, tmin
+
+    # -------------------------------------------------------------- resident Hermite state
+    def hermite_upload(self, t, m, q, p, f, df):
+        t, m, q, p, f, df = (_arr(a) for a in (t, m, q, p, f, df))
+        self._ck(self._lib.nbk_hermite_upload(self._h, len(m), _p(t), _p(m), _p(q), _p(p), _p(f),
+                                              _p(df)))
+
+    def hermite_body_sum(self, i, nt, eps2=0.0, upd=-1, upd_state=None):
+        g, dg = np.empty(3), np.empty(3)
+        us = None if upd_state is None else _arr(upd_state)
+        self._ck(self._lib.nbk_hermite_body_sum(self._h, i, nt, eps2, upd, _p(us), _p(g), _p(dg)))
+        return g, dg
 
     # -------------------------------------------------------------- raw device pointers
     # Arguments are integer device addresses (e.g. torch.Tensor.data_ptr()) and an integer

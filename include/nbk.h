@@ -147,6 +147,19 @@ int nbk_resident_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1
 int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, int s0, int s1,
                           double *dv, double *tmin);
 
+/* ---- device-resident Hermite state: one body steps at a time (hermite.ml:95-130, 171-178) --- */
+
+/* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n]. */
+int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, const double *q,
+                       const double *p, const double *f, const double *df);
+/* One Hermite.advance_body force evaluation on the resident state: first overwrites body
+ * `upd` (if upd >= 0) with upd_state[13] = {t, q[3], p[3], f[3], df[3]} - the result of the
+ * previous step - then predicts every body to time nt (hermite.ml:53-72) and returns
+ * gsum[3], dgsum[3] for target i over all other bodies (fp = -gsum, dfp = -dgsum,
+ * hermite.ml:106-115).  One kernel launch + a 48-byte read-back per step. */
+int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
+                         const double *upd_state, double *gsum, double *dgsum);
+
 /* ---- raw device-pointer API (one rank of a multi-GPU job; bench.py / torch harness) ------- */
 
 /* A packed body is 8 doubles {x, y, z, m, vx, vy, vz, 0} (64 B): the layout j-tiles are
