@@ -230,11 +230,6 @@ int run_tangent(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st) {
 }
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
-__global__ void zero_kernel(double *p, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0.0;
-}
-
 __global__ void fill_kernel(double *p, size_t n, double v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -789,7 +784,7 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
 
 // ---- device-resident Hermite state -------------------------------------------------------------
 int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, const double *q,
-                       const double *p, const double *f, const double *df) {
+                       const double *p, const double *hh, const double *f, const double *df) {
   if (!ctx) return NBK_ERR_ARG;
   if (n <= 0 || !t || !m || !q || !p || !f || !df)
     return fail(ctx, NBK_ERR_ARG, "nbk_hermite_upload: bad arguments");
@@ -806,6 +801,8 @@ int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, co
       r[8 + k] = f[3 * i + k];
       r[11 + k] = df[3 * i + k];
     }
+    r[14] = hh ? hh[i] : 0.0;
+    r[15] = 0.0;  // re-insertion stamp (hermite_resident_kernel)
   }
   const int nblk = (n + 255) / 256;
   TRY(reserve(ctx, ctx->d_hstate, (size_t)n * HB * sizeof(double)));
@@ -842,6 +839,61 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
   for (int k = 0; k < 3; ++k) {
     gsum[k] = ctx->h_scalar[k];
     dgsum[k] = ctx->h_scalar[3 + k];
+  }
+  return NBK_OK;
+}
+
+int nbk_hermite_resident_max(void) { return HRES_MAX_N; }
+
+int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, double eps2,
+                                 long max_steps, long *nsteps) {
+  if (!ctx) return NBK_ERR_ARG;
+  const int n = ctx->hermite_n;
+  if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state: call nbk_hermite_upload");
+  if (n > HRES_MAX_N)
+    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n, HRES_MAX_N);
+  CK(cudaSetDevice(ctx->device));
+  const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
+  CK(cudaFuncSetAttribute(hermite_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  TRY(reserve(ctx, ctx->d_scalar, 64));
+  hermite_resident_kernel<<<1, HRES_THREADS, smem, ctx->stream>>>(
+      (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+      (long long *)ctx->d_scalar.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  TRY(sync(ctx));
+  long long steps;
+  memcpy(&steps, ctx->h_scalar, sizeof steps);
+  if (nsteps) *nsteps = (long)steps;
+  if (steps >= (long long)max_steps && max_steps > 0)
+    return fail(ctx, NBK_ERR_STATE, "Hermite step cap (%ld) reached before stop_time", max_steps);
+  return NBK_OK;
+}
+
+int nbk_hermite_download(nbk_ctx *ctx, double *t, double *q, double *p, double *h, double *f,
+                         double *df) {
+  if (!ctx) return NBK_ERR_ARG;
+  const int n = ctx->hermite_n;
+  if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state");
+  CK(cudaSetDevice(ctx->device));
+  std::string buf((size_t)n * HB * sizeof(double), '\0');
+  double *hb = reinterpret_cast<double *>(&buf[0]);
+  CK(cudaMemcpyAsync(hb, ctx->d_hstate.p, (size_t)n * HB * sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  TRY(sync(ctx));
+  for (int i = 0; i < n; ++i) {
+    const double *r = hb + (size_t)i * HB;
+    if (t) t[i] = r[0];
+    if (h) h[i] = r[14];
+    for (int k = 0; k < 3; ++k) {
+      if (q) q[3 * i + k] = r[2 + k];
+      if (p) p[3 * i + k] = r[5 + k];
+      if (f) f[3 * i + k] = r[8 + k];
+      if (df) df[3 * i + k] = r[11 + k];
+    }
   }
   return NBK_OK;
 }

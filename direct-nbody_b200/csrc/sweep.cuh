@@ -889,6 +889,193 @@ __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ 
   }
 }
 
+// ---- Hermite.advance_bodies + finish_bs entirely on the device ---------------------------------
+// The reference steps ONE body at a time (hermite.ml:171-178): pop the body with the earliest
+// next time, predict everybody to that time, 1 x (N-1) acc+jerk, correct, new time step,
+// re-insert.  A kernel launch per step costs ~10 us; this persistent single-CTA kernel keeps
+// the whole Hermite.b array in SHARED MEMORY (136 B per body, N <= HRES_MAX_N) and runs the loop
+// on the device: per step two block reductions (arg-min of next time, 6 force sums), one
+// thread doing the corrector - about 1.5 us per step.
+// Scheduling follows the reference's list semantics: earliest next time first, and among equal
+// next times the most recently re-inserted first (List.merge puts the new body before equal
+// elements, hermite.ml:178), initial ties by array order (stable sort, :187); finish_bs
+// (hermite.ml:132-143) then steps every body to stop_time in that same order.
+// Record slots: 0 t, 1 m, 2-4 q, 5-7 p, 8-10 f, 11-13 df, 14 h, 15 re-insertion stamp.
+constexpr int HRES_THREADS = 512;
+constexpr int HRES_STRIDE = 17;   // odd stride: conflict-free per-thread rows
+constexpr int HRES_MAX_N = 1536;
+
+__global__ void __launch_bounds__(HRES_THREADS, 1)
+    hermite_resident_kernel(double *__restrict__ state, int n, double stop_time, double eta,
+                            double eps2, long long max_steps, long long *__restrict__ nsteps_out) {
+  extern __shared__ double rec[];  // [n][HRES_STRIDE]; slot 16 = done flag
+  __shared__ double red[HRES_THREADS / 32][6];
+  __shared__ double key_nt[HRES_THREADS / 32], key_st[HRES_THREADS / 32];
+  __shared__ int key_idx[HRES_THREADS / 32];
+  __shared__ int sel_idx;
+  __shared__ double sel_nt;
+  constexpr int NW = HRES_THREADS / 32;
+  constexpr int NONE = 0x7fffffff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SweepParams P;
+  P.eps2 = eps2;
+  for (int j = tid; j < n; j += HRES_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rec[j * HRES_STRIDE + c] = state[(size_t)j * HB + c];
+    rec[j * HRES_STRIDE + 16] = 0.0;
+  }
+  __syncthreads();
+  long long steps = 0, stamp = 0;
+  bool finishing = false;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  auto better = [](double ont, double ost, int oidx, double knt, double kst, int kidx) {
+    return oidx != NONE &&
+           (kidx == NONE || (ont < knt) ||
+            (ont == knt && (ost > kst || (ost == kst && oidx < kidx))));
+  };
+  for (;;) {
+    // ---- 1. arg-min over unfinished bodies of (next time asc, stamp desc, index asc)
+    double knt = INF, kst = -INF;
+    int kidx = NONE;
+    for (int j = tid; j < n; j += HRES_THREADS) {
+      const double *r = rec + j * HRES_STRIDE;
+      if (r[16] != 0.0) continue;
+      const double nt = r[0] + r[14];
+      if (better(nt, r[15], j, knt, kst, kidx)) {
+        knt = nt;
+        kst = r[15];
+        kidx = j;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ont = __shfl_down_sync(0xffffffffu, knt, off);
+      const double ost = __shfl_down_sync(0xffffffffu, kst, off);
+      const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
+      if (better(ont, ost, oidx, knt, kst, kidx)) {
+        knt = ont;
+        kst = ost;
+        kidx = oidx;
+      }
+    }
+    if (lane == 0) {
+      key_nt[warp] = knt;
+      key_st[warp] = kst;
+      key_idx[warp] = kidx;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      knt = lane < NW ? key_nt[lane] : INF;
+      kst = lane < NW ? key_st[lane] : -INF;
+      kidx = lane < NW ? key_idx[lane] : NONE;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ont = __shfl_down_sync(0xffffffffu, knt, off);
+        const double ost = __shfl_down_sync(0xffffffffu, kst, off);
+        const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
+        if (better(ont, ost, oidx, knt, kst, kidx)) {
+          knt = ont;
+          kst = ost;
+          kidx = oidx;
+        }
+      }
+      if (lane == 0) {
+        sel_idx = kidx;
+        sel_nt = knt;
+      }
+    }
+    __syncthreads();
+    const int it = sel_idx;
+    if (it == NONE) break;  // every body finished
+    if (!finishing) {
+      if (steps >= max_steps) break;
+      if (sel_nt > stop_time) finishing = true;  // advance_bodies -> finish_bs (:172-173)
+    }
+    double *tr = rec + it * HRES_STRIDE;
+    // finish_bs: {b with h = stop_time - b.t}; every thread computes the same value
+    const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    double mt, qt[3], vt[3];
+    hermite_predict(tr, nt, mt, qt, vt);
+    // ---- 2. 1 x (N-1) acc+jerk over predicted bodies (hermite.ml:106-115)
+    const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = tid; j < n; j += HRES_THREADS) {
+      double mj, qj[3], vj[3];
+      hermite_predict(rec + j * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, j == it, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+    __syncthreads();
+    // ---- 3. one thread: corrector (hermite.ml:116-123), new time step (hermite.ml:87-93)
+    ++steps;
+    ++stamp;
+    if (tid == 0) {
+      double fp[3], dfp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double a = 0.0, d = 0.0;
+        for (int w = 0; w < NW; ++w) {
+          a += red[w][c];
+          d += red[w][3 + c];
+        }
+        fp[c] = mt * a;  // f = -gsum = m_i * acc
+        dfp[c] = mt * d;
+      }
+      const double m = mt;
+      double qn[3], pn[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+        pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                          __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+        qn[c] = __dadd_rn(
+            __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+      }
+      // timescale eta m q_new qp fp h, with qp = the target's predicted position
+      const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+      const double rr = __dsqrt_rn(
+          __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      const double fn = __dsqrt_rn(__dadd_rn(
+          __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+      double hn;
+      if (rr == 0.0) {
+        hn = __dmul_rn(h, 1.189207115002721);  // 2 ** 0.25
+      } else {
+        const double x =
+            __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+        hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));  // x ** 0.25
+      }
+      tr[0] = nt;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tr[2 + c] = qn[c];
+        tr[5 + c] = pn[c];
+        tr[8 + c] = fp[c];
+        tr[11 + c] = dfp[c];
+      }
+      tr[14] = hn;
+      tr[15] = (double)stamp;
+      if (finishing) tr[16] = 1.0;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += HRES_THREADS)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) state[(size_t)j * HB + c] = rec[j * HRES_STRIDE + c];
+  if (tid == 0) *nsteps_out = steps;
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

@@ -44,6 +44,8 @@ double timescale(double eta, double m, const double *q, const double *qp, const 
   return h * std::pow(eta * square(h) * fn / (m * r), 0.25);
 }
 
+int g_hermite_mode = 0;  // 0 auto, 1 host scheduler (launch per step), 2 device-resident loop
+
 struct Herm {
   nbk_ctx *ctx;
   double eps2;
@@ -97,6 +99,8 @@ struct Herm {
 
 extern "C" {
 
+void nbh_set_hermite_mode(int mode) { g_hermite_mode = mode; }
+
 int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, double *q, double *p,
                         double *h, double *f, double *df, double dt, double sf, double eps2,
                         long *nsteps) {
@@ -142,8 +146,54 @@ int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, doub
         dd[3 * i + k] = pool[i].df[k];
       }
     }
+    std::vector<double> hh(n);
+    for (int i = 0; i < n; ++i) hh[i] = pool[i].h;
     NBH_TRY(ck(ctx, nbk_hermite_upload(ctx, n, tt.data(), mm.data(), qq.data(), pp.data(),
-                                       ff.data(), dd.data())));
+                                       hh.data(), ff.data(), dd.data())));
+  }
+  // Small systems: the whole advance_bodies / finish_bs loop runs on the device (one
+  // persistent kernel, nbk_hermite_advance_resident); larger ones step from the host scheduler
+  // below with one launch per advance_body.
+  if (g_hermite_mode != 1 && (g_hermite_mode == 2 || n <= nbk_hermite_resident_max())) {
+    double tmin = pool[0].t + pool[0].h;
+    int imin = 0;
+    for (int i = 1; i < n; ++i)
+      if (pool[i].t + pool[i].h < tmin) {
+        tmin = pool[i].t + pool[i].h;
+        imin = i;
+      }
+    const double stop = pool[imin].t + dt;  // (List.hd sorted).t +. dt, hermite.ml:188
+    long ns = 0;
+    NBH_TRY(ck(ctx, nbk_hermite_advance_resident(ctx, stop, sf, eps2, 1L << 40, &ns)));
+    *nsteps += ns;
+    NBH_TRY(ck(ctx, nbk_hermite_download(ctx, t, q, p, h, f, df)));
+    // Array.fast_sort compare_id (hermite.ml:136): device rows are in input order
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return id[a] < id[b]; });
+    bool sorted = true;
+    for (int i = 0; i < n; ++i) sorted = sorted && perm[i] == i;
+    if (!sorted) {
+      auto permute1 = [&](double *x) {
+        std::vector<double> c(x, x + n);
+        for (int i = 0; i < n; ++i) x[i] = c[perm[i]];
+      };
+      auto permute3 = [&](double *x) {
+        std::vector<double> c(x, x + 3 * (size_t)n);
+        for (int i = 0; i < n; ++i)
+          for (int k = 0; k < 3; ++k) x[3 * i + k] = c[3 * perm[i] + k];
+      };
+      std::vector<int> ic(id, id + n);
+      for (int i = 0; i < n; ++i) id[i] = ic[perm[i]];
+      permute1(t);
+      permute1(m);
+      permute1(h);
+      permute3(q);
+      permute3(p);
+      permute3(f);
+      permute3(df);
+    }
+    return 0;
   }
   // List.fast_sort compare_next_time (hermite.ml:187), stable
   std::vector<HBody *> order(n);

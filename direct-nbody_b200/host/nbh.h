@@ -63,6 +63,9 @@ int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, doubl
 
 /* ---- Hermite.advance bs dt sf (hermite.ml:180-189): flat image of Hermite.b array ----------- */
 /* Output in id order (hermite.ml:136); *nsteps is bumped like Base.nsteps (hermite.ml:124). */
+/* 0 (default): device-resident stepping loop when n <= nbk_hermite_resident_max(), else the
+ * host scheduler with one kernel launch per advance_body; 1 / 2 force either. */
+void nbh_set_hermite_mode(int mode);
 int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, double *q, double *p,
                         double *h, double *f, double *df, double dt, double sf, double eps2,
                         long *nsteps);

@@ -212,7 +212,10 @@ class HermiteState:
         return copy.deepcopy(self)
 
 
-def hermite_advance(ctx, s, dt, sf, eps2=0.0):
+def hermite_advance(ctx, s, dt, sf, eps2=0.0, mode=0):
+    """Hermite.advance bs dt sf.  mode 0: automatic; 1: host scheduler, one launch per step;
+    2: the whole stepping loop on the device (n <= nbk_hermite_resident_max())."""
+    load_library().nbh_set_hermite_mode(mode)
     o = s.copy()
     ns = C.c_long(o.nsteps)
     _ck(load_library().nbh_hermite_advance(ctx._h, len(o.m), _ip(o.id), _p(o.t), _p(o.m), _p(o.q),

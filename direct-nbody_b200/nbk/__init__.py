@@ -49,7 +49,10 @@ SYMBOLS = {
     "nbk_resident_grad_v_dgrad_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_kick_sum": (_i, [_vp, _d, _d, _i, _i, _i, _i, _pd, _pd]),
-    "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd]),
+    "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd]),
+    "nbk_hermite_resident_max": (_i, []),
+    "nbk_hermite_advance_resident": (_i, [_vp, _d, _d, _d, C.c_long, C.POINTER(C.c_long)]),
+    "nbk_hermite_download": (_i, [_vp, _pd, _pd, _pd, _pd, _pd, _pd]),
     "nbk_hermite_body_sum": (_i, [_vp, _i, _d, _d, _i, _pd, _pd, _pd]),
     "nbk_dev_pack": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -288,10 +291,23 @@ class Context:
         return dv, tmin
 
     # -------------------------------------------------------------- resident Hermite state
-    def hermite_upload(self, t, m, q, p, f, df):
+    def hermite_upload(self, t, m, q, p, f, df, h=None):
         t, m, q, p, f, df = (_arr(a) for a in (t, m, q, p, f, df))
-        self._ck(self._lib.nbk_hermite_upload(self._h, len(m), _p(t), _p(m), _p(q), _p(p), _p(f),
-                                              _p(df)))
+        h = None if h is None else _arr(h)
+        self._ck(self._lib.nbk_hermite_upload(self._h, len(m), _p(t), _p(m), _p(q), _p(p), _p(h),
+                                              _p(f), _p(df)))
+
+    def hermite_advance_resident(self, stop_time, eta, eps2=0.0, max_steps=1 << 40):
+        ns = C.c_long(0)
+        self._ck(self._lib.nbk_hermite_advance_resident(self._h, stop_time, eta, eps2, max_steps,
+                                                        C.byref(ns)))
+        return ns.value
+
+    def hermite_download(self, n):
+        t, h = np.empty(n), np.empty(n)
+        q, p, f, df = (np.empty((n, 3)) for _ in range(4))
+        self._ck(self._lib.nbk_hermite_download(self._h, _p(t), _p(q), _p(p), _p(h), _p(f), _p(df)))
+        return t, q, p, h, f, df
 
     def hermite_body_sum(self, i, nt, eps2=0.0, upd=-1, upd_state=None):
         g, dg = np.empty(3), np.empty(3)

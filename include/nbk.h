@@ -149,9 +149,10 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
 
 /* ---- device-resident Hermite state: one body steps at a time (hermite.ml:95-130, 171-178) --- */
 
-/* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n]. */
+/* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n] and
+ * the time steps h[n] (may be NULL: zeros). */
 int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, const double *q,
-                       const double *p, const double *f, const double *df);
+                       const double *p, const double *h, const double *f, const double *df);
 /* One Hermite.advance_body force evaluation on the resident state: first overwrites body
  * `upd` (if upd >= 0) with upd_state[13] = {t, q[3], p[3], f[3], df[3]} - the result of the
  * previous step - then predicts every body to time nt (hermite.ml:53-72) and returns
@@ -159,6 +160,18 @@ int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, co
  * hermite.ml:106-115).  One kernel launch + a 48-byte read-back per step. */
 int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
                          const double *upd_state, double *gsum, double *dgsum);
+/* Hermite.advance_bodies + finish_bs (hermite.ml:132-143, 171-178) run ENTIRELY on the device
+ * by one persistent kernel over the resident state (n <= nbk_hermite_resident_max()): steps
+ * single bodies in the reference's list order until every next time exceeds stop_time, then
+ * steps every body to stop_time.  *nsteps = advance_body calls made (Base.nsteps,
+ * hermite.ml:124).  Stops early, returning NBK_ERR_STATE, after max_steps steps of the first
+ * phase (the reference would loop forever when h underflows). */
+int nbk_hermite_resident_max(void);
+int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, double eps2,
+                                 long max_steps, long *nsteps);
+/* Reads the resident state back (any pointer may be NULL). */
+int nbk_hermite_download(nbk_ctx *ctx, double *t, double *q, double *p, double *h, double *f,
+                         double *df);
 
 /* ---- raw device-pointer API (one rank of a multi-GPU job; bench.py / torch harness) ------- */
 

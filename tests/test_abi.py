@@ -27,6 +27,18 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.nbk_version()
 
 
+def test_host_mirror_library_exports_its_header():
+    """libnbh (C++ mirror of the OCaml integrators) exports every function of host/nbh.h."""
+    import nbh
+    src = open(os.path.join(ROOT, "direct-nbody_b200", "host", "nbh.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(nbh_[a-z0-9_]+)\s*\(", src)))
+    lib = nbh.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(nbh.SYMBOLS) <= set(declared)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

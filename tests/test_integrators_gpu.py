@@ -133,9 +133,12 @@ def test_leapfrog_adaptive_energy_scaling(ctx, oracle, seed):
     assert np.sqrt(8.0) < out[0] / out[1] < np.sqrt(32.0)
 
 
-def test_hermite_short_run_matches_oracle(ctx, oracle, plummer64):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_hermite_short_run_matches_oracle(ctx, oracle, plummer64, mode):
+    """mode 1: host scheduler + one launch per advance_body; mode 2: the whole loop in one
+    persistent kernel (hermite_resident_kernel)."""
     m, q, p = plummer64
-    a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 0.0625, 1e-5)
+    a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 0.0625, 1e-5, mode=mode)
     b = oracle.hermite_advance(oracle.HermiteState(m, q, p), 0.0625, 1e-5)
     assert np.array_equal(a.id, b.id) and np.array_equal(a.t, b.t)
     assert abs(a.nsteps - b.nsteps) <= max(2, b.nsteps // 1000)
@@ -157,6 +160,27 @@ def test_hermite_energy_error_agrees_with_oracle(ctx, oracle, eta):
         assert ea < 50 * eta ** 1.2 + 1e-12
         assert 0.1 < (ea + 1e-13) / (eb + 1e-13) < 10.0, (ea, eb)
     assert np.all(sa.t == 1.0)
+
+
+def test_hermite_config0_n1024_energy_error(ctx, oracle):
+    """BASELINE configs[0]: Plummer N = 1024 equal-mass, 4th-order Hermite for 1 N-body time
+    unit, energy error against the oracle's run of the same bodies (device-resident loop)."""
+    import time
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(1024, 20240))
+    e0 = oracle.energy(m, q, p)
+    t0 = time.perf_counter()
+    a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 1.0, 1e-4)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = oracle.hermite_advance(oracle.HermiteState(m, q, p), 1.0, 1e-4)
+    t_cpu = time.perf_counter() - t0
+    ea = abs((sum(nbh.energy(ctx, a.m, a.q, a.p)) - e0) / e0)
+    eb = abs((oracle.energy(b.m, b.q, b.p) - e0) / e0)
+    print(f"config0: steps gpu {a.nsteps} cpu {b.nsteps}; dE/E gpu {ea:.3e} cpu {eb:.3e}; "
+          f"wall gpu {t_gpu:.2f}s cpu {t_cpu:.2f}s")
+    assert np.all(a.t == 1.0) and ea < 1e-4
+    assert abs(a.nsteps - b.nsteps) <= 0.02 * b.nsteps
+    assert 0.1 < (ea + 1e-12) / (eb + 1e-12) < 10.0
 
 
 @pytest.mark.parametrize("seed", [5, 6, 7])
