@@ -44,6 +44,7 @@ double timescale(double eta, double m, const double *q, const double *qp, const 
   return h * std::pow(eta * square(h) * fn / (m * r), 0.25);
 }
 
+long g_step_cap = 1L << 40;  // guard against the reference's runaway step-size collapse
 int g_hermite_mode = 0;  // 0 auto, 1 host scheduler (launch per step), 2 device-resident loop
 
 struct Herm {
@@ -100,6 +101,7 @@ struct Herm {
 extern "C" {
 
 void nbh_set_hermite_mode(int mode) { g_hermite_mode = mode; }
+void nbh_set_step_cap(long cap) { g_step_cap = cap; }
 
 int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, double *q, double *p,
                         double *h, double *f, double *df, double dt, double sf, double eps2,
@@ -164,7 +166,7 @@ int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, doub
       }
     const double stop = pool[imin].t + dt;  // (List.hd sorted).t +. dt, hermite.ml:188
     long ns = 0;
-    NBH_TRY(ck(ctx, nbk_hermite_advance_resident(ctx, stop, sf, eps2, 1L << 40, &ns)));
+    NBH_TRY(ck(ctx, nbk_hermite_advance_resident(ctx, stop, sf, eps2, g_step_cap, &ns)));
     *nsteps += ns;
     NBH_TRY(ck(ctx, nbk_hermite_download(ctx, t, q, p, h, f, df)));
     // Array.fast_sort compare_id (hermite.ml:136): device rows are in input order
@@ -206,6 +208,7 @@ int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, doub
   H.eps2 = eps2;
   // advance_bodies (hermite.ml:171-178)
   while (!(next_time(*order[0]) > stop_time)) {
+    if (*nsteps > g_step_cap) return fail(NBK_ERR_STATE, "Hermite.advance: step cap reached");
     HBody *head = order[0];
     NBH_TRY(H.advance_body(sf, *head, nsteps));
     // List.merge compare_next_time [new_b] tl: before the first e with cmp(new_b, e) <= 0

@@ -66,6 +66,9 @@ int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, doubl
 /* 0 (default): device-resident stepping loop when n <= nbk_hermite_resident_max(), else the
  * host scheduler with one kernel launch per advance_body; 1 / 2 force either. */
 void nbh_set_hermite_mode(int mode);
+/* Guard: Hermite.advance fails with NBK_ERR_STATE after this many steps (the reference loops
+ * forever when its step-size formula collapses); default 2^40. */
+void nbh_set_step_cap(long cap);
 int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, double *q, double *p,
                         double *h, double *f, double *df, double dt, double sf, double eps2,
                         long *nsteps);

@@ -23,12 +23,15 @@ def pytest_configure(config):
 def oracle():
     from oracle import oracle as O
     O.build()
+    O.set_step_cap(20_000_000)  # the reference's step loops can spin forever on bad (eta, state)
     return O
 
 
 @pytest.fixture(scope="session")
 def ctx():
+    import nbh
     import nbk
     c = nbk.Context(0)  # raises loudly without libnbk.so or without a B200
+    nbh.load_library().nbh_set_step_cap(20_000_000)
     yield c
     c.close()
