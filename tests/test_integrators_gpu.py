@@ -199,9 +199,12 @@ def test_hermite_config0_n1024_energy_error(ctx, oracle):
     eb = abs((oracle.energy(b.m, b.q, b.p) - e0) / e0)
     print(f"config0: steps gpu {a.nsteps} cpu {b.nsteps}; dE/E gpu {ea:.3e} cpu {eb:.3e}; "
           f"wall gpu {t_gpu:.2f}s cpu {t_cpu:.2f}s")
-    assert np.all(a.t == 1.0) and ea < 1e-4
+    # At eta = 1e-4 and eps = 0 the reference's own step criterion loses a close encounter
+    # (dE/E ~ 1.7 in the oracle): what is asserted is that the GPU run reproduces the
+    # reference's error, not that the error is small.
+    assert np.all(a.t == 1.0)
     assert abs(a.nsteps - b.nsteps) <= 0.02 * b.nsteps
-    assert 0.1 < (ea + 1e-12) / (eb + 1e-12) < 10.0
+    assert 0.5 < (ea + 1e-12) / (eb + 1e-12) < 2.0
 
 
 @pytest.mark.parametrize("seed", [5, 6, 7])
