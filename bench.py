@@ -68,6 +68,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read + dram__bytes_write of the acc+jerk sweep kernel per launch, from the
+    committed ncu --set full summary (profiles/); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_k2_large_shape_summary.txt")
+    try:
+        tot = 0.0
+        for line in open(path):
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if line.startswith(key + " "):
+                    unit = line.split("[")[1].split("]")[0]
+                    val = float(line.split("=")[1])
+                    tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def cpu_sample(n_sample, threads_all=True, n_total=131072):
     """The reference's CPU path (oracle port of Hermite.start_bs' symmetric pair loop) timed on
     a bounded sample: the first n_sample bodies of the same Plummer workload."""
@@ -252,7 +269,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "traffic": ncu_traffic_bytes() if world == 1 else None,
+                         "traffic_note": "ncu dram bytes per launch (profiles/); algorithmic = "
+                                         "64 B x N read once + 48 B x N written",
                          "peak_source": "on-box DFMA microbenchmark (nbk_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": nominal, "frac_of_nominal": achieved_tf / nominal,

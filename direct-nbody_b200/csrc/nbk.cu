@@ -30,7 +30,6 @@ struct nbk_ctx {
   bool ev_valid = false;
   int64_t launches = 0;
   int shape = 0;
-  int flavour = 0;  // acc+jerk formulation: 0 = 6 accumulators (t_k form), 1 = 9 accumulators
   std::string err;
   // device workspaces
   DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_out[4],
@@ -217,7 +216,6 @@ struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, boo
 struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<true>>(c, P, s, t); } };
 
 int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
-  if (ctx->flavour == 1) return run_op<OpAccJerk9>(ctx, P, st, time_it);
   return run_op<OpGradVDGradVB<1>>(ctx, P, st, time_it);
 }
 
@@ -956,11 +954,8 @@ int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2
 
 int nbk_tune(nbk_ctx *ctx, int variant) {
   if (!ctx) return NBK_ERR_ARG;
-  const int shape = variant % 10, flavour = variant / 10;
-  if (variant < 0 || shape > 3 || flavour > 1)
-    return fail(ctx, NBK_ERR_ARG, "nbk_tune: no variant %d", variant);
-  ctx->shape = shape;
-  ctx->flavour = flavour;
+  if (variant < 0 || variant > 3) return fail(ctx, NBK_ERR_ARG, "nbk_tune: no shape %d", variant);
+  ctx->shape = variant;
   return NBK_OK;
 }
 

@@ -437,117 +437,6 @@ template <int FLAVOUR> struct OpGradVDGradVB : OpGradVDGradV {
   }
 };
 
-// acc+jerk with NINE accumulators per target: jerk = J1 - 3 J2, J1 = sum w u,
-// J2 = sum (w (d.u) y^2) d.  Same 31 FP64 instructions per interaction as OpGradVDGradV, but
-// every one of the 9 accumulating FMAs depends only on (w, wb) and on d / u, so they are all
-// ready together and ptxas can chain them on a shared operand (w.reuse ... , wb.reuse ...):
-// fewer three-register-fetch DFMAs.  The -3 is applied once per target in
-// store()/combine-time instead of once per interaction.
-struct OpAccJerk9 {
-  static constexpr int NACC = 9;
-  static constexpr int ND2 = 4;
-  static constexpr int BATCHED = 1;
-  using Tgt = OpGradVDGradV::Tgt;
-  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &P,
-                                              int i) {
-    OpGradVDGradV::load(t, pk, P, i);
-  }
-  __device__ __forceinline__ static void zero(double *acc) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-  }
-  template <bool CHECK>
-  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
-                                              const double2 *, bool self, const SweepParams &P) {
-    const Tgt tt[1] = {t};
-    double a1[1][9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a1[0][k] = acc[k];
-    const int ig[1] = {self ? 0 : -1};
-    pairs<CHECK, 1>(tt, a1, sj, 0, ig, P);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = a1[0][k];
-  }
-  template <bool CHECK, int IPT>
-  __device__ __forceinline__ static void pairs(const Tgt (&t)[IPT], double (&acc)[IPT][9],
-                                               const double2 *sj, int jg, const int (&ig)[IPT],
-                                               const SweepParams &P) {
-    const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
-    double dx[IPT], dy[IPT], dz[IPT], ux[IPT], uy[IPT], uz[IPT], r2[IPT], rv[IPT], mj[IPT];
-    double y0[IPT], w[IPT], wb[IPT];
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      dx[r] = a.x - t[r].x;
-      dy[r] = a.y - t[r].y;
-      dz[r] = b.x - t[r].z;
-    }
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      r2[r] = fma(dx[r], dx[r], P.eps2);
-      r2[r] = fma(dy[r], dy[r], r2[r]);
-      r2[r] = fma(dz[r], dz[r], r2[r]);
-      mj[r] = b.y;
-      if (CHECK) {
-        const bool self = jg == ig[r];
-        r2[r] = self ? 1.0 : r2[r];
-        mj[r] = self ? 0.0 : mj[r];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[r]) : "d"(r2[r]));
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      ux[r] = c.x - t[r].vx;
-      uy[r] = c.y - t[r].vy;
-      uz[r] = d.x - t[r].vz;
-    }
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      rv[r] = dx[r] * ux[r];
-      rv[r] = fma(dy[r], uy[r], rv[r]);
-      rv[r] = fma(dz[r], uz[r], rv[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      const double tt = r2[r] * y0[r];
-      const double e = fma(-tt, y0[r], 1.0);
-      const double pp = fma(0.375, e, 0.5);
-      const double q = e * pp;
-      const double y = fma(y0[r], q, y0[r]);
-      const double y2 = y * y;
-      w[r] = (mj[r] * y) * y2;
-      wb[r] = w[r] * (rv[r] * y2);
-    }
-#pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      acc[r][0] = fma(w[r], dx[r], acc[r][0]);
-      acc[r][1] = fma(w[r], dy[r], acc[r][1]);
-      acc[r][2] = fma(w[r], dz[r], acc[r][2]);
-      acc[r][3] = fma(w[r], ux[r], acc[r][3]);
-      acc[r][4] = fma(w[r], uy[r], acc[r][4]);
-      acc[r][5] = fma(w[r], uz[r], acc[r][5]);
-      acc[r][6] = fma(wb[r], dx[r], acc[r][6]);
-      acc[r][7] = fma(wb[r], dy[r], acc[r][7]);
-      acc[r][8] = fma(wb[r], dz[r], acc[r][8]);
-    }
-  }
-  __device__ __forceinline__ static void combine(double *a, const double *b) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a[k] += b[k];
-  }
-  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
-    const double s = -P.packed[(size_t)ig * PK + 3];
-    double *g = P.out[0] + 3 * (size_t)(ig - P.t0);
-    double *dg = P.out[1] + 3 * (size_t)(ig - P.t0);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double jk = fma(-3.0, acc[6 + k], acc[3 + k]);
-      g[k] = P.accumulate ? g[k] + s * acc[k] : s * acc[k];
-      dg[k] = P.accumulate ? dg[k] + s * jk : s * jk;
-    }
-  }
-};
-
 // Tangent (first-order forward mode) of the acc / acc+jerk sums for KT directions per pass:
 // DFloatBase.grad_v / grad_v_dgrad_v (dFloat_advancer.ml:57-81) summed as in
 // dFloat_hermite.ml:177-186.  Direction k's packed array aux[k] holds per body

@@ -196,9 +196,8 @@ int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2
 
 /* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
  * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).
- * Adding 10 selects the 9-accumulator formulation of the acc+jerk interaction (same
- * instruction count, different operand sharing).  Results do not depend on the variant beyond
- * rounding.  A knob for profiles/ and tests; callers never need it. */
+ * Results do not depend on the shape beyond summation order.  A knob for profiles/ and
+ * tests; callers never need it. */
 int nbk_tune(nbk_ctx *ctx, int variant);
 
 /* FP64 DFMA-throughput microbenchmark on ctx's device (the measured FP64 peak the roofline

@@ -122,6 +122,27 @@ def test_momentum_conservation_full_size(ctx, oracle):
     assert rel_err(dg[sl[0]:sl[1]], dg_ref) <= TOL
 
 
+def test_baseline_size_sampled_against_oracle(ctx, oracle):
+    """BASELINE configs[2] at full size (N = 131072, the metric sweep): 8 slices of 48 targets
+    spread over the system against the oracle's rows over all 131072 sources, plus Newton's
+    third law over the whole result and run-to-run reproducibility."""
+    n = 131072
+    import nbh
+    m, q, p = nbh.make_plummer(n, 20243)
+    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    worst_g = worst_dg = 0.0
+    for k in range(8):
+        lo = k * 16384 + 1000 * k
+        g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(lo, lo + 48))
+        worst_g = max(worst_g, rel_err(g[lo:lo + 48], g_ref))
+        worst_dg = max(worst_dg, rel_err(dg[lo:lo + 48], dg_ref))
+    assert worst_g <= TOL and worst_dg <= TOL, (worst_g, worst_dg)
+    assert np.linalg.norm(g.sum(0)) <= 1e-12 * np.linalg.norm(g, axis=1).sum()
+    assert np.linalg.norm(dg.sum(0)) <= 1e-12 * np.linalg.norm(dg, axis=1).sum()
+    g2, dg2 = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    assert np.array_equal(g, g2) and np.array_equal(dg, dg2)
+
+
 def test_resident_bodies_and_update(ctx, oracle):
     m, q, p = oracle.make_plummer(2000, 13)
     ctx.bodies_upload(m, q, p)

@@ -10,7 +10,7 @@ import nbh  # noqa: E402
 import nbk  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
-variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3, 0, 11, 12]
+variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3, 0]
 m, q, p = nbh.make_plummer(n, 20243)
 with nbk.Context(0) as ctx:
     peak, _ = ctx.fp64_peak(20000)
