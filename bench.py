@@ -36,36 +36,64 @@ SEED = 20243                     # 20240 + config index 3
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons DURING the timed region: NVML (pynvml, ~5 ms
+    period) so that even a 40 ms timed region gets samples; falls back to polling nvidia-smi."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        if len(f) >= 6:
+            self.sm.append(float(f[0]))
+            self.mx.append(float(f[1]))
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k in range(4):
+                if f[2 + k].lower().startswith("active"):
+                    self.reasons.add(names[k])
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.005 if self.nvml else 0.1)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for s in self.samples for k in range(4)
-                          if len(s) >= 6 and s[2 + k].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def ncu_traffic_bytes():
