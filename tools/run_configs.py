@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[1], [3], [4] (and [0]) at their stated sizes on one B200, each beside a
+bounded run of the oracle: timings and energy errors, one JSON object per config
+(-> profiles/r1_configs.json).  configs[2] is bench.py.
+
+usage: tools/run_configs.py [out.json] [--quick]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+import numpy as np  # noqa: E402
+import nbh  # noqa: E402
+import nbk  # noqa: E402
+from oracle import oracle as O  # noqa: E402  (checker only: energy errors beside the GPU's)
+
+quick = "--quick" in sys.argv
+out_path = next((a for a in sys.argv[1:] if not a.startswith("--")), None)
+O.set_step_cap(50_000_000)
+res = []
+with nbk.Context(0) as ctx:
+    # ---- configs[0]: Plummer N=1024, Hermite, 1 N-body time unit
+    m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(1024, 20240))
+    e0 = sum(nbh.energy(ctx, m, q, p))
+    for eta in (1e-4,) if quick else (1e-4, 1e-5):
+        t0 = time.perf_counter()
+        a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 1.0, eta)
+        tg = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        b = O.hermite_advance(O.HermiteState(m, q, p), 1.0, eta)
+        tc = time.perf_counter() - t0
+        res.append({"config": 0, "what": "Hermite.advance, Plummer N=1024, 1 time unit, device-resident loop",
+                    "eta": eta, "steps_gpu": a.nsteps, "steps_oracle": b.nsteps,
+                    "dE_gpu": abs((sum(nbh.energy(ctx, a.m, a.q, a.p)) - e0) / e0),
+                    "dE_oracle": abs((O.energy(b.m, b.q, b.p) - e0) / e0),
+                    "wall_gpu_s": tg, "wall_oracle_1core_s": tc, "us_per_step_gpu": 1e6 * tg / a.nsteps})
+        print(res[-1], flush=True)
+
+    # ---- configs[1]: Plummer N=16384, leapfrog (const dt DKD), energy error vs reference
+    n = 16384
+    m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(n, 20241))
+    s = nbh.LeapfrogState(m, q, p)
+    s.dt_max[:] = np.inf  # skip the reference's sub-step ladder on fresh bodies
+    nst = 16 if quick else 64
+    t0 = time.perf_counter()
+    a = nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 1024, nst)
+    tg = time.perf_counter() - t0
+    ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
+    # oracle on the first 4096 bodies of the same system, same dt and steps
+    n_o = 4096
+    mo, qo, po = O.rescale_to_standard_units(m[:n_o], q[:n_o], p[:n_o])
+    so = O.LeapfrogState(mo, qo, po)
+    so.dt_max[:] = np.inf
+    sg = nbh.LeapfrogState(mo, qo, po)
+    sg.dt_max[:] = np.inf
+    t0 = time.perf_counter()
+    bo = O.leapfrog_advance_const_dt(so, 1.0 / 1024, nst)
+    tc = time.perf_counter() - t0
+    bg = nbh.leapfrog_advance_const_dt(ctx, sg, 1.0 / 1024, nst)
+    res.append({"config": 1, "what": f"Leapfrog.advance_const_dt dt=1/1024 x {nst}, Plummer N=16384",
+                "dE_gpu_n16384": abs((ke + pe + 0.25) / 0.25), "ms_per_step_gpu": 1e3 * tg / nst,
+                "n_oracle": n_o, "dE_gpu_n4096": abs((sum(nbh.energy(ctx, bg.m, bg.q, bg.p)) + 0.25) / 0.25),
+                "dE_oracle_n4096": abs((O.energy(bo.m, bo.q, bo.p) + 0.25) / 0.25),
+                "max_rel_pos_diff_n4096": float(np.max(np.linalg.norm(bg.q - bo.q, axis=1) /
+                                                       np.linalg.norm(bo.q, axis=1))),
+                "ms_per_step_oracle_1core_n4096": 1e3 * tc / nst})
+    print(res[-1], flush=True)
+
+    # ---- configs[3]: two-mass Plummer N=65536, Omelyan advancer, per-step energy diagnostics
+    n = 16384 if quick else 65536
+    m, q, p = nbh.make_plummer(n, 20243 + 1)
+    m, q, p = nbh.add_mass_disc(m, q, p, 20244)
+    m, q, p = nbh.adjust_frame(m, q, p)
+    m, q, p = nbh.rescale_to_standard_units(ctx, m, q, p)
+    e0 = sum(nbh.energy(ctx, m, q, p))
+    t, errs, t_step, t_diag = 0.0, [], 0.0, 0.0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        q, p, t = nbh.omelyan_advance(ctx, m, q, p, t, 1.0 / 256)
+        t_step += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        e = sum(nbh.energy(ctx, m, q, p))
+        el = nbh.bodies_to_el_phase_space(ctx, m, q, p)
+        t_diag += time.perf_counter() - t0
+        errs.append(abs((e - e0) / e0))
+    res.append({"config": 3, "what": f"OA.advance h=1/256 x 4, two-mass Plummer N={n}, energy + per-body E_i each step",
+                "dE_per_step": errs, "ms_per_step_gpu": 1e3 * t_step / 4,
+                "ms_diagnostics_per_step_gpu": 1e3 * t_diag / 4,
+                "sum_Ei_minus_KE_minus_2PE": float(abs(el[:, 0].sum() - (e + nbh.energy(ctx, m, q, p)[1])))})
+    print(res[-1], flush=True)
+
+    # ---- configs[4]: tangent (variational) forces, N=32768
+    n = 8192 if quick else 32768
+    m, q, p = nbh.make_plummer(n, 20245)
+    rng = np.random.default_rng(20245)
+    for K in (1, 6):
+        dq = rng.standard_normal((K, n, 3))
+        dp = rng.standard_normal((K, n, 3)) * m[None, :, None]
+        ctx.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, 0.0)
+        t0 = time.perf_counter()
+        g, dg, gt, dgt = ctx.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, 0.0)
+        tg = time.perf_counter() - t0
+        sl = (1000, 1016)
+        rg, rdg, rgt, rdgt = O.grad_v_dgrad_v_sum_tangent(m, q, p, dq[0], dp[0], 0.0, targets=sl)
+        err = float(np.max(np.linalg.norm(dgt[0][sl[0]:sl[1]] - rdgt, axis=1) / np.linalg.norm(rdgt, axis=1)))
+        res.append({"config": 4, "what": f"acc+jerk tangent sums, K={K} directions, Plummer N={n} (host-buffer call)",
+                    "K": K, "wall_s": tg, "tangent_interactions_per_s": K * n * (n - 1.0) / tg,
+                    "max_rel_err_vs_dual_oracle_16_targets": err})
+        print(res[-1], flush=True)
+if out_path:
+    json.dump(res, open(out_path, "w"), indent=1)
