@@ -222,11 +222,12 @@ int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
 // Tangent sweeps: aux tiles make the stage (1+KT) x 8 KB; one shape per KT.
 template <int KT, bool JERK>
 int run_tangent(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st) {
+  const bool time_it = (st == ctx->stream);
   if constexpr (KT == 1) {
     if (P.t1 - P.t0 >= 256)
-      return Launcher<OpTangent<KT, JERK>, 128, 2, 2, 1>::run(ctx, P, st, true);
+      return Launcher<OpTangent<KT, JERK>, 128, 2, 2, 1>::run(ctx, P, st, time_it);
   }
-  return Launcher<OpTangent<KT, JERK>, 128, 1, 2, 1>::run(ctx, P, st, true);
+  return Launcher<OpTangent<KT, JERK>, 128, 1, 2, 1>::run(ctx, P, st, time_it);
 }
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
@@ -950,6 +951,42 @@ int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2
   P.accumulate = accumulate;
   cudaStream_t st = (cudaStream_t)stream;
   return K3::run(ctx, P, st, false);
+}
+
+int nbk_dev_pack_aux(nbk_ctx *ctx, int n, const double *d_m, const double *d_dq,
+                     const double *d_dp, double *d_aux, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || !d_m || !d_dq || !d_aux || ((uintptr_t)d_aux & 15))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_pack_aux: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  pack_aux_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_m, d_dq, d_dp, 0, d_aux);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_dev_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, const double *d_packed, const double *d_aux,
+                                       int n_total, int K, double eps2, int t0, int t1, int s0,
+                                       int s1, double *d_gsum_tan, double *d_dgsum_tan,
+                                       void *stream) {
+  DEV_COMMON();
+  if (K <= 0 || !d_aux || ((uintptr_t)d_aux & 15) || !d_gsum_tan || !d_dgsum_tan)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_grad_v_dgrad_v_sum_tangent: bad arguments");
+  const size_t nt = (size_t)(t1 - t0);
+  for (int k0 = 0; k0 < K;) {
+    const int kt = (K - k0 >= 3) ? 3 : 1;
+    SweepParams P = base_params(d_packed, eps2, t0, t1, s0, s1);
+    P.aux = d_aux + (size_t)k0 * n_total * PK;
+    P.aux_stride = n_total * PK;
+    P.K = kt;
+    P.out[0] = d_gsum_tan + (size_t)k0 * 3 * nt;
+    P.out[1] = d_dgsum_tan + (size_t)k0 * 3 * nt;
+    if (kt == 3) TRY((run_tangent<3, true>(ctx, P, (cudaStream_t)stream)));
+    else TRY((run_tangent<1, true>(ctx, P, (cudaStream_t)stream)));
+    k0 += kt;
+  }
+  return NBK_OK;
 }
 
 int nbk_tune(nbk_ctx *ctx, int variant) {

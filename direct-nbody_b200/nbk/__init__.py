@@ -58,6 +58,9 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "nbk_dev_grad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
     "nbk_dev_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_dev_pack_aux": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nbk_dev_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _i, _i, _vp, _vp,
+                                                _vp]),
     "nbk_tune": (_i, [_vp, _i]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
@@ -328,6 +331,17 @@ class Context:
         self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum(self._h, d_packed, n_total, eps2, t0, t1,
                                                       s0, s1, d_gsum, d_dgsum, int(accumulate),
                                                       stream or None))
+
+    def dev_pack_aux(self, n, d_m, d_dq, d_dp, d_aux, stream=0):
+        self._ck(self._lib.nbk_dev_pack_aux(self._h, n, d_m, d_dq, d_dp or None, d_aux,
+                                            stream or None))
+
+    def dev_grad_v_dgrad_v_sum_tangent(self, d_packed, d_aux, n_total, K, eps2, targets, sources,
+                                       d_gsum_tan, d_dgsum_tan, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum_tangent(
+            self._h, d_packed, d_aux, n_total, K, eps2, t0, t1, s0, s1, d_gsum_tan, d_dgsum_tan,
+            stream or None))
 
     def dev_grad_v_sum(self, d_packed, n_total, eps2, targets, sources, d_gsum, accumulate=False,
                        stream=0):

@@ -122,3 +122,60 @@ class ShardedAccJerk:
             self._sweep(self.packed_all, pl.n, eps2, (pl.t0, pl.t1), (pl.t1, pl.n), self.g,
                         self.dg, True)
         return self.g, self.dg
+
+
+class ShardedTangent:
+    """One rank of the sharded tangent (variational) acc+jerk sums for K directions
+    (dFloat_hermite.ml:177-186 over all bodies; BASELINE configs[4]).  Exchange step: an in-place
+    all-gather of the packed bodies and of the K packed direction arrays."""
+
+    def __init__(self, plan: ShardPlan, K: int, device, ctx, group=None):
+        import torch
+        import torch.distributed as dist
+        self.plan, self.K, self.device, self.ctx, self.group = plan, K, device, ctx, group
+        self.torch, self.dist = torch, dist
+        npad = max(plan.npad, 1)
+        self.packed_all = torch.zeros(npad, PACKED, dtype=torch.float64, device=device)
+        # direction-major [K][npad][8] so that the kernel's aux stride is npad*8
+        self.aux_all = torch.zeros(K, npad, PACKED, dtype=torch.float64, device=device)
+        lo = plan.rank * plan.shard
+        self.lo = lo
+        self.gt = torch.zeros(K, max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.dgt = torch.zeros_like(self.gt)
+
+    def load_local(self, m, q, p, dq, dp):
+        """m,q,p: full-system host arrays; dq, dp: [K][n][3] host arrays."""
+        torch, pl = self.torch, self.plan
+        if pl.count == 0:
+            return
+        sl = slice(pl.t0, pl.t1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        d_m = torch.as_tensor(m[sl]).to(self.device).contiguous()
+        d_q = torch.as_tensor(q[sl]).to(self.device).contiguous()
+        d_p = torch.as_tensor(p[sl]).to(self.device).contiguous()
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+                          self.packed_all[self.lo:].data_ptr(), stream)
+        keep = [d_m, d_q, d_p]
+        for k in range(self.K):
+            d_dq = torch.as_tensor(dq[k][sl]).to(self.device).contiguous()
+            d_dp = torch.as_tensor(dp[k][sl]).to(self.device).contiguous()
+            self.ctx.dev_pack_aux(pl.count, d_m.data_ptr(), d_dq.data_ptr(), d_dp.data_ptr(),
+                                  self.aux_all[k, self.lo:].data_ptr(), stream)
+            keep += [d_dq, d_dp]
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self, eps2: float = 0.0):
+        pl, dist = self.plan, self.dist
+        if pl.world > 1:
+            dist.all_gather_into_tensor(self.packed_all, self.packed_all[self.lo:self.lo + pl.shard],
+                                        group=self.group)
+            for k in range(self.K):
+                dist.all_gather_into_tensor(self.aux_all[k],
+                                            self.aux_all[k, self.lo:self.lo + pl.shard],
+                                            group=self.group)
+        if pl.count:
+            stream = self.torch.cuda.current_stream(self.device).cuda_stream
+            self.ctx.dev_grad_v_dgrad_v_sum_tangent(
+                self.packed_all.data_ptr(), self.aux_all.data_ptr(), pl.npad, self.K, eps2,
+                (pl.t0, pl.t1), (0, pl.n), self.gt.data_ptr(), self.dgt.data_ptr(), stream)
+        return self.gt, self.dgt

@@ -194,6 +194,16 @@ int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double
 int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0, int t1,
                   int s0, int s1, double *d_phi, int accumulate, void *stream);
 
+/* Tangent sweep on device pointers (one rank of a sharded DFloat_pushforward force evaluation,
+ * BASELINE configs[4]).  d_aux is [K][n_total][8]: direction k's rows {dq, 0, dv, 0} built by
+ * nbk_dev_pack_aux (dv = dp / m).  Outputs d_gsum_tan, d_dgsum_tan are [K][3 (t1-t0)]. */
+int nbk_dev_pack_aux(nbk_ctx *ctx, int n, const double *d_m, const double *d_dq,
+                     const double *d_dp, double *d_aux, void *stream);
+int nbk_dev_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, const double *d_packed, const double *d_aux,
+                                       int n_total, int K, double eps2, int t0, int t1, int s0,
+                                       int s1, double *d_gsum_tan, double *d_dgsum_tan,
+                                       void *stream);
+
 /* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
  * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).
  * Results do not depend on the shape beyond summation order.  A knob for profiles/ and
