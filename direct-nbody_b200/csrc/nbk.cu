@@ -198,18 +198,6 @@ int run_op(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
   }
 }
 
-// The time-scale kick is register-hungry (IEEE sqrt/div sequences): smaller shapes.
-template <>
-int run_op<OpKick<true>>(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
-  if (ctx->shape == SHAPE_AUTO && P.t1 - P.t0 <= SMALL_MAX_NT)
-    return run_small<OpKick<true>>(ctx, P, st, time_it);
-  switch (pick_shape(ctx, P.t1 - P.t0)) {
-    case SHAPE_LARGE:
-    case SHAPE_MEDIUM: return Launcher<OpKick<true>, 128, 2, 3, 2>::run(ctx, P, st, time_it);
-    default: return Launcher<OpKick<true>, 128, 1, 4, 2>::run(ctx, P, st, time_it);
-  }
-}
-
 struct K1 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpGradV>(c, P, s, t); } };
 struct K3 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpV>(c, P, s, t); } };
 struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<false>>(c, P, s, t); } };
