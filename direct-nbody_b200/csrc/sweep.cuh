@@ -82,17 +82,6 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
   return fma(p, q, y0);
 }
 
-// 1/x: MUFU.RCP64H seed + two Newton steps (4 DFMA), ~1e-16 relative.  Used only where a
-// result need not be the correctly rounded quotient (the kick's time-scale filter).
-__device__ __forceinline__ double rcp_nr(double x) {
-  double y0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-  double e = fma(-x, y0, 1.0);
-  y0 = fma(y0, e, y0);
-  e = fma(-x, y0, 1.0);
-  return fma(y0, e, y0);
-}
-
 // ---- sweep parameters ----------------------------------------------------------------------
 struct SweepParams {
   const double *packed;  // [n_total][PK]
@@ -310,20 +299,21 @@ template <bool WITH_TSCALE> struct OpKick {
       // relative).  Only a pair whose estimate comes within 0.1 % of the running minimum - or
       // is NaN/inf - can change the result, and only then is the reference's exact IEEE
       // sequence evaluated (~ln N times per target), so the minimum stays bit-exact.
+      // With y = 1/r: tff = eta rsqrt(mtot y^3), tc = eta rsqrt(vsq y^2), and
+      // |t / D| > T  <=>  |t| > T |D| needs no division.  Two MUFU + ~25 FP64 ops.
       bool need_exact;
       {
-        const double yv = rsqrt_nr(vsq);  // 1/|u|
-        const double ra = r2e * y;        // |d|
-        const double xa = (r2e * ra) * rcp_nr(mtot);
-        const double tffa = P.eta * (xa * rsqrt_nr(xa));
-        const double tca = P.eta * (ra * yv);
-        const double sva = vdr * (y * y);
-        const double dffa = 1.5 * sva * tffa;
-        const double dca = (sva * tca) * fma(mtot * (yv * yv), y, 1.0);
-        const double t1 = fabs(tffa * rcp_nr(fma(-0.5, dffa, 1.0)));
-        const double t2 = fabs(tca * rcp_nr(fma(-0.5, dca, 1.0)));
-        const double tsa = (t1 < t2) ? t1 : t2;
-        need_exact = !(tsa > acc[3] * 1.001);  // NaN or inf on either side -> exact path
+        const double y2 = y * y;
+        const double za = mtot * (y2 * y);  // mtot / r^3
+        const double tffa = P.eta * rsqrt_nr(za);
+        const double qa = rsqrt_nr(vsq * y2);  // r / |u|
+        const double tca = P.eta * qa;
+        const double sva = vdr * y2;
+        const double d1 = fma(-0.75 * sva, tffa, 1.0);
+        const double d2 = fma(-0.5 * (sva * tca), fma(za, qa * qa, 1.0), 1.0);
+        const double T = acc[3] * 1.001;
+        // any NaN / inf makes a comparison false -> exact path
+        need_exact = !((fabs(tffa) > T * fabs(d1)) && (fabs(tca) > T * fabs(d2)));
       }
       const bool skip = CHECK ? self : false;
       if (need_exact && !skip) {
