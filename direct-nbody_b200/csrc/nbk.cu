@@ -771,6 +771,40 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
   return run_kick(ctx, (const double *)ctx->d_res_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
 }
 
+int nbk_resident_leapfrog_steps(nbk_ctx *ctx, double dt, int nsteps, double *q, double *v) {
+  if (!ctx) return NBK_ERR_ARG;
+  const int n = ctx->resident_n;
+  if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident bodies: call nbk_bodies_upload");
+  if (nsteps < 0) return fail(ctx, NBK_ERR_ARG, "nbk_resident_leapfrog_steps: nsteps < 0");
+  CK(cudaSetDevice(ctx->device));
+  double *packed = (double *)ctx->d_res_packed.p;
+  TRY(reserve(ctx, ctx->d_out[0], 3 * (size_t)n * sizeof(double)));
+  const double dt2 = dt / 2.0;  // leapfrog.ml:121
+  const int nb = (n + 255) / 256;
+  for (int s = 0; s < nsteps; ++s) {
+    leapfrog_drift_kernel<<<nb, 256, 0, ctx->stream>>>(packed, n, dt2);
+    SweepParams P = base_params(packed, 0.0, 0, n, 0, n);
+    P.dt = dt;
+    P.out[0] = (double *)ctx->d_out[0].p;
+    TRY(K4::run(ctx, P, ctx->stream, s == nsteps - 1));
+    leapfrog_apply_kick_kernel<<<nb, 256, 0, ctx->stream>>>(packed, (const double *)ctx->d_out[0].p, n);
+    leapfrog_drift_kernel<<<nb, 256, 0, ctx->stream>>>(packed, n, dt2);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+  }
+  if (q || v) {
+    TRY(reserve(ctx, ctx->d_q, 3 * (size_t)n * sizeof(double)));
+    TRY(reserve(ctx, ctx->d_vel, 3 * (size_t)n * sizeof(double)));
+    unpack_kernel<<<nb, 256, 0, ctx->stream>>>(packed, n, (double *)ctx->d_q.p,
+                                               (double *)ctx->d_vel.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (q) TRY(download(ctx, q, ctx->d_q, 3 * (size_t)n));
+    if (v) TRY(download(ctx, v, ctx->d_vel, 3 * (size_t)n));
+  }
+  return sync(ctx);
+}
+
 // ---- device-resident Hermite state -------------------------------------------------------------
 int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, const double *q,
                        const double *p, const double *hh, const double *f, const double *df) {

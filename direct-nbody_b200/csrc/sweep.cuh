@@ -1098,6 +1098,37 @@ __global__ void __launch_bounds__(HRES_THREADS, 1)
   if (tid == 0) *nsteps_out = steps;
 }
 
+// ---- Leapfrog DKD on device-resident packed bodies (leapfrog.ml:64-68, 129-137) ----------------
+// drift: q <- q + dt v with the reference's separate multiply and add.
+__global__ void leapfrog_drift_kernel(double *__restrict__ packed, int n, double dt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = packed + (size_t)i * PK;
+  b[0] = __dadd_rn(b[0], __dmul_rn(dt, b[4]));
+  b[1] = __dadd_rn(b[1], __dmul_rn(dt, b[5]));
+  b[2] = __dadd_rn(b[2], __dmul_rn(dt, b[6]));
+}
+// kick: v <- v + dv (dv = dt * sum_j m_j d / r^3 from the kick sweep).
+__global__ void leapfrog_apply_kick_kernel(double *__restrict__ packed,
+                                           const double *__restrict__ dv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = packed + (size_t)i * PK;
+  b[4] = __dadd_rn(b[4], dv[3 * i]);
+  b[5] = __dadd_rn(b[5], dv[3 * i + 1]);
+  b[6] = __dadd_rn(b[6], dv[3 * i + 2]);
+}
+__global__ void unpack_kernel(const double *__restrict__ packed, int n, double *__restrict__ q,
+                              double *__restrict__ v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *b = packed + (size_t)i * PK;
+  for (int k = 0; k < 3; ++k) {
+    q[3 * i + k] = b[k];
+    v[3 * i + k] = b[4 + k];
+  }
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

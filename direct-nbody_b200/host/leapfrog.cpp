@@ -16,6 +16,8 @@ namespace {
 
 using namespace nbh;
 
+int g_leapfrog_resident = 1;  // const-dt steady state on the device (0: host loop, one sweep per step)
+
 struct LBody {
   int id;
   double t, dt_max, m, q[3], v[3];
@@ -148,6 +150,8 @@ void store(const Leap &L, int *id, double *t, double *dt_max, double *m, double 
 
 extern "C" {
 
+void nbh_set_leapfrog_resident(int on) { g_leapfrog_resident = on; }
+
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks) {
   Leap L;
@@ -171,7 +175,32 @@ int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, doubl
   Leap L;
   L.ctx = ctx;
   load(L, n, id, t, dt_max, m, q, v);
-  for (int s = 0; s < nsteps; ++s) NBH_TRY(L.advance_subsystem(dt, INFINITY, n));
+  for (int s = 0; s < nsteps; ++s) {
+    // Steady state: every body has dt_max >= dt, so find_can_advance_index returns 0, the
+    // recursion is empty and each remaining call is one plain DKD step over all bodies with
+    // dt_max left at infinity and the order untouched (leapfrog.ml:119-142).  Run all of them
+    // on the device without coming back to the host.
+    bool steady = true;
+    for (const LBody &b : L.bs) steady = steady && !(b.dt_max < dt);
+    if (steady && g_leapfrog_resident) {
+      const int rest = nsteps - s;
+      L.pack(n);
+      NBH_TRY(ck(ctx, nbk_bodies_upload(ctx, n, L.m.data(), L.q.data(), L.v.data(), 1)));
+      NBH_TRY(ck(ctx, nbk_resident_leapfrog_steps(ctx, dt, rest, L.q.data(), L.v.data())));
+      const double dt2 = dt / 2.0;
+      for (int i = 0; i < n; ++i) {
+        LBody &b = L.bs[i];
+        for (int k = 0; k < 3; ++k) {
+          b.q[k] = L.q[3 * i + k];
+          b.v[k] = L.v[3 * i + k];
+        }
+        for (int r = 0; r < rest; ++r) b.t = (b.t + dt2) + dt2;  // two drifts per step
+        b.dt_max = INFINITY;
+      }
+      break;
+    }
+    NBH_TRY(L.advance_subsystem(dt, INFINITY, n));
+  }
   store(L, id, t, dt_max, m, q, v);
   return 0;
 }

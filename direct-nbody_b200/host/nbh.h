@@ -58,6 +58,9 @@ int nbh_omelyan_advance(nbk_ctx *ctx, int n, const double *m, double *q, double 
 /* advance bs dt eta: output order is the reference's (sorted by dt_max); id[] follows. */
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks);
+/* 1 (default): once every body has dt_max >= dt the remaining const-dt steps run on the device
+ * (nbk_resident_leapfrog_steps); 0: every step goes through the host recursion. */
+void nbh_set_leapfrog_resident(int on);
 int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max,
                                   double *m, double *q, double *v, double dt, int nsteps);
 

@@ -186,7 +186,8 @@ def leapfrog_advance(ctx, s, dt, eta):
     return o
 
 
-def leapfrog_advance_const_dt(ctx, s, dt, nsteps):
+def leapfrog_advance_const_dt(ctx, s, dt, nsteps, resident=True):
+    load_library().nbh_set_leapfrog_resident(int(resident))
     o = s.copy()
     _ck(load_library().nbh_leapfrog_advance_const_dt(ctx._h, len(o.m), _ip(o.id), _p(o.t),
                                                      _p(o.dt_max), _p(o.m), _p(o.q), _p(o.v), dt,

@@ -49,6 +49,7 @@ SYMBOLS = {
     "nbk_resident_grad_v_dgrad_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_kick_sum": (_i, [_vp, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_resident_leapfrog_steps": (_i, [_vp, _d, _i, _pd, _pd]),
     "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd]),
     "nbk_hermite_resident_max": (_i, []),
     "nbk_hermite_advance_resident": (_i, [_vp, _d, _d, _d, C.c_long, C.POINTER(C.c_long)]),
@@ -292,6 +293,12 @@ class Context:
         self._ck(self._lib.nbk_resident_kick_sum(self._h, eta, dt, t0, t1, s0, s1, _p(dv),
                                                  _p(tmin)))
         return dv, tmin
+
+    def resident_leapfrog_steps(self, dt, nsteps):
+        n = self.resident_count
+        q, v = np.empty((n, 3)), np.empty((n, 3))
+        self._ck(self._lib.nbk_resident_leapfrog_steps(self._h, dt, nsteps, _p(q), _p(v)))
+        return q, v
 
     # -------------------------------------------------------------- resident Hermite state
     def hermite_upload(self, t, m, q, p, f, df, h=None):

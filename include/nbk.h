@@ -147,6 +147,12 @@ int nbk_resident_v_sum(nbk_ctx *ctx, double eps2, int t0, int t1, int s0, int s1
 int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, int s0, int s1,
                           double *dv, double *tmin);
 
+/* nsteps plain drift-kick-drift steps of size dt on the resident bodies (uploaded with
+ * is_velocity = 1), entirely on the device: the steady state of Leapfrog.advance_const_dt
+ * (leapfrog.ml:160-165 with every body active: drift dt/2, all-pairs kick, drift dt/2,
+ * leapfrog.ml:129-137).  q, v (may be NULL) receive the final positions and velocities. */
+int nbk_resident_leapfrog_steps(nbk_ctx *ctx, double dt, int nsteps, double *q, double *v);
+
 /* ---- device-resident Hermite state: one body steps at a time (hermite.ml:95-130, 171-178) --- */
 
 /* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n] and

@@ -106,6 +106,22 @@ def test_leapfrog_const_dt_matches_oracle_and_reference_test(ctx, oracle, seed):
     assert np.sqrt(32.0) < de[0] / de[1] < np.sqrt(128.0)
 
 
+def test_leapfrog_const_dt_device_resident_steps(ctx, oracle):
+    """Steady-state const-dt steps on the device (nbk_resident_leapfrog_steps) against the host
+    recursion with one sweep per step, and against the oracle."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(777, 20241))
+    s = nbh.LeapfrogState(m, q, p)
+    s.dt_max[:] = np.inf
+    a = nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 512, 12, resident=True)
+    b = nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 512, 12, resident=False)
+    so = oracle.LeapfrogState(m, q, p)
+    so.dt_max[:] = np.inf
+    c = oracle.leapfrog_advance_const_dt(so, 1.0 / 512, 12)
+    assert np.array_equal(a.t, b.t) and np.array_equal(a.t, c.t) and np.all(np.isinf(a.dt_max))
+    assert np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v)   # same kernels, same order
+    assert rel(a.q, c.q) <= 1e-13 and rel(a.v, c.v) <= 1e-11
+
+
 def test_leapfrog_initial_timescales_bit_exact(ctx, oracle):
     """Leapfrog.advance's dt = 0 sweep (leapfrog.ml:151-155): dt_max from the GPU equals the
     sequential reference loop bit for bit, hence the same sorted order."""
