@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,6 +40,7 @@ struct nbk_ctx {
   DevBuf d_res_m, d_res_packed;
   // resident Hermite state
   int hermite_n = 0;
+  int hermite_threads = 0;  // 0 auto, 512 forces the 512-thread stepping kernel (NBK_HERMITE_THREADS)
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
   // pinned host staging for scalar read-back
   double *h_scalar = nullptr;
@@ -454,6 +456,7 @@ int nbk_create(nbk_ctx **out, int device) {
   if (!c) return fail(nullptr, NBK_ERR_NOMEM, "nbk_create: out of host memory");
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char *e = getenv("NBK_HERMITE_THREADS")) c->hermite_threads = atoi(e);
   cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   cudaError_t e2 = cudaEventCreate(&c->ev0);
   cudaError_t e3 = cudaEventCreate(&c->ev1);
@@ -877,12 +880,21 @@ int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, dou
     return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n, HRES_MAX_N);
   CK(cudaSetDevice(ctx->device));
   const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
-  CK(cudaFuncSetAttribute(hermite_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)smem));
   TRY(reserve(ctx, ctx->d_scalar, 64));
-  hermite_resident_kernel<<<1, HRES_THREADS, smem, ctx->stream>>>(
-      (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
-      (long long *)ctx->d_scalar.p);
+  // one body per thread up to 1024 bodies (the N = 1024 reference case), else 512 threads
+  if (n > 512 && ctx->hermite_threads != 512) {
+    CK(cudaFuncSetAttribute(hermite_resident_kernel<1024>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hermite_resident_kernel<1024><<<1, 1024, smem, ctx->stream>>>(
+        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+        (long long *)ctx->d_scalar.p);
+  } else {
+    CK(cudaFuncSetAttribute(hermite_resident_kernel<512>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hermite_resident_kernel<512><<<1, 512, smem, ctx->stream>>>(
+        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+        (long long *)ctx->d_scalar.p);
+  }
   CK(cudaGetLastError());
   ctx->launches++;
   CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,

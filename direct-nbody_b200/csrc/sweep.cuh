@@ -82,6 +82,17 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
   return fma(p, q, y0);
 }
 
+// 1/x: MUFU.RCP64H seed + two Newton steps (4 DFMA), ~1 ulp.  For places that need speed and
+// not the correctly rounded quotient (the device-resident Hermite predictor).
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  double e = fma(-x, y0, 1.0);
+  y0 = fma(y0, e, y0);
+  e = fma(-x, y0, 1.0);
+  return fma(y0, e, y0);
+}
+
 // ---- sweep parameters ----------------------------------------------------------------------
 struct SweepParams {
   const double *packed;  // [n_total][PK]
@@ -836,6 +847,26 @@ __device__ __forceinline__ void hermite_predict(const double *r, double nt, doub
   }
 }
 
+// Same predictor with 1/m and 1/3 as multiplications (no IEEE divisions): a few ulp from the
+// reference's sequence, used only inside the device-resident stepping loop where the five
+// divisions per body per step are the critical path.
+__device__ __forceinline__ void hermite_predict_fast(const double *r, double nt, double &m,
+                                                     double (&qp)[3], double (&vp)[3]) {
+  m = r[1];
+  const double im = rcp_nr(m);
+  const double dt = nt - r[0];
+  const double pc = dt * im;
+  const double fc = (pc * dt) * 0.5;
+  const double dfc = (fc * dt) * (1.0 / 3.0);
+  const double pdfc = (dt * dt) * 0.5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double qk = r[2 + k], pk = r[5 + k], fk = r[8 + k], dfk = r[11 + k];
+    qp[k] = fma(dfc, dfk, fma(fc, fk, fma(pc, pk, qk)));
+    vp[k] = fma(pdfc, dfk, fma(dt, fk, pk)) * im;
+  }
+}
+
 __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ state, int n,
                                                            int it, double nt, double eps2,
                                                            int upd, const HermiteUpd u,
@@ -923,10 +954,10 @@ __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ 
 // elements, hermite.ml:178), initial ties by array order (stable sort, :187); finish_bs
 // (hermite.ml:132-143) then steps every body to stop_time in that same order.
 // Record slots: 0 t, 1 m, 2-4 q, 5-7 p, 8-10 f, 11-13 df, 14 h, 15 re-insertion stamp.
-constexpr int HRES_THREADS = 512;
 constexpr int HRES_STRIDE = 17;   // odd stride: conflict-free per-thread rows
 constexpr int HRES_MAX_N = 1536;
 
+template <int HRES_THREADS>
 __global__ void __launch_bounds__(HRES_THREADS, 1)
     hermite_resident_kernel(double *__restrict__ state, int n, double stop_time, double eta,
                             double eps2, long long max_steps, long long *__restrict__ nsteps_out) {
@@ -1018,13 +1049,13 @@ __global__ void __launch_bounds__(HRES_THREADS, 1)
     const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
     const double nt = __dadd_rn(tr[0], h);
     double mt, qt[3], vt[3];
-    hermite_predict(tr, nt, mt, qt, vt);
+    hermite_predict_fast(tr, nt, mt, qt, vt);
     // ---- 2. 1 x (N-1) acc+jerk over predicted bodies (hermite.ml:106-115)
     const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int j = tid; j < n; j += HRES_THREADS) {
       double mj, qj[3], vj[3];
-      hermite_predict(rec + j * HRES_STRIDE, nt, mj, qj, vj);
+      hermite_predict_fast(rec + j * HRES_STRIDE, nt, mj, qj, vj);
       const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
                               make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
       OpGradVDGradV::pair<true>(tg, acc, src, src, j == it, P);
