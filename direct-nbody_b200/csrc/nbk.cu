@@ -40,7 +40,7 @@ struct nbk_ctx {
   DevBuf d_res_m, d_res_packed;
   // resident Hermite state
   int hermite_n = 0;
-  int hermite_threads = 0;  // 0 auto, 512 forces the 512-thread stepping kernel (NBK_HERMITE_THREADS)
+  int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size (NBK_HERMITE_THREADS)
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
   // pinned host staging for scalar read-back
   double *h_scalar = nullptr;
@@ -881,19 +881,20 @@ int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, dou
   CK(cudaSetDevice(ctx->device));
   const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
   TRY(reserve(ctx, ctx->d_scalar, 64));
-  // one body per thread up to 1024 bodies (the N = 1024 reference case), else 512 threads
-  if (n > 512 && ctx->hermite_threads != 512) {
-    CK(cudaFuncSetAttribute(hermite_resident_kernel<1024>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hermite_resident_kernel<1024><<<1, 1024, smem, ctx->stream>>>(
-        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
-        (long long *)ctx->d_scalar.p);
-  } else {
-    CK(cudaFuncSetAttribute(hermite_resident_kernel<512>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hermite_resident_kernel<512><<<1, 512, smem, ctx->stream>>>(
-        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
-        (long long *)ctx->d_scalar.p);
+  // Threads of the single stepping CTA: the per-step cost is dominated by barriers and the two
+  // block reductions, so fewer, busier warps win (measured on B200: profiles/).
+  int nth = ctx->hermite_threads ? ctx->hermite_threads : (n <= 128 ? 128 : 256);
+  auto launch = [&](auto kern, int threads) -> int {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, threads, smem, ctx->stream>>>((double *)ctx->d_hstate.p, n, stop_time, eta, eps2,
+                                            (long long)max_steps, (long long *)ctx->d_scalar.p);
+    return NBK_OK;
+  };
+  switch (nth) {
+    case 128: TRY(launch(hermite_resident_kernel<128>, 128)); break;
+    case 512: TRY(launch(hermite_resident_kernel<512>, 512)); break;
+    case 1024: TRY(launch(hermite_resident_kernel<1024>, 1024)); break;
+    default: TRY(launch(hermite_resident_kernel<256>, 256)); break;
   }
   CK(cudaGetLastError());
   ctx->launches++;
