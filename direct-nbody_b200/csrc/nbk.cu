@@ -577,6 +577,72 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
   return run_kick(ctx, (const double *)ctx->d_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
 }
 
+int nbk_interact_sum(nbk_ctx *ctx, int n, int na, const double *m, const double *q, double eps2,
+                     double *S) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || na < 0 || na > n || !S)
+    return fail(ctx, NBK_ERR_ARG, "nbk_interact_sum: bad arguments (n=%d, na=%d)", n, na);
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
+  TRY(reserve(ctx, ctx->d_out[0], 3 * (size_t)n * sizeof(double)));
+  double *out = (double *)ctx->d_out[0].p;
+  const double *packed = (const double *)ctx->d_packed.p;
+  if (na == 0) {
+    CK(cudaMemsetAsync(out, 0, 3 * (size_t)n * sizeof(double), ctx->stream));
+  } else {
+    SweepParams P = base_params(packed, eps2, 0, na, 0, n);  // active targets x everybody
+    P.out[0] = out;
+    TRY(K1::run(ctx, P, ctx->stream, true));
+    if (n > na) {  // passive targets x active sources
+      SweepParams Q = base_params(packed, eps2, na, n, 0, na);
+      Q.out[0] = out + 3 * (size_t)na;
+      TRY(K1::run(ctx, Q, ctx->stream, false));
+    }
+  }
+  TRY(download(ctx, S, ctx->d_out[0], 3 * (size_t)n));
+  return sync(ctx);
+}
+
+int nbk_kick_block_sum(nbk_ctx *ctx, int iend, int ibegin, const double *m, const double *q,
+                       const double *v, double eta, double dt, double *dv, double *tmin) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (iend < 0 || ibegin < 0 || ibegin > iend || !dv)
+    return fail(ctx, NBK_ERR_ARG, "nbk_kick_block_sum: bad arguments (ibegin=%d, iend=%d)", ibegin,
+                iend);
+  CK(cudaSetDevice(ctx->device));
+  if (iend == 0) return NBK_OK;
+  if (tmin && !v) return fail(ctx, NBK_ERR_ARG, "time-scale needs velocities");
+  const size_t n = (size_t)iend;
+  TRY(stage_bodies(ctx, iend, m, q, v, 1));
+  TRY(reserve(ctx, ctx->d_out[0], 3 * n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], n * sizeof(double)));
+  double *o0 = (double *)ctx->d_out[0].p, *o1 = (double *)ctx->d_out[1].p;
+  const double *packed = (const double *)ctx->d_packed.p;
+  auto sweep = [&](int t0, int t1, int s0, int s1, bool time_it) -> int {
+    SweepParams P = base_params(packed, 0.0, t0, t1, s0, s1);
+    P.dt = dt;
+    P.eta = eta;
+    P.out[0] = o0 + 3 * (size_t)t0;
+    P.out[1] = o1 + t0;
+    return tmin ? K4T::run(ctx, P, ctx->stream, time_it) : K4::run(ctx, P, ctx->stream, time_it);
+  };
+  if (ibegin == iend) {
+    CK(cudaMemsetAsync(o0, 0, 3 * n * sizeof(double), ctx->stream));
+    if (tmin) {
+      fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(o1, n, __builtin_inf());
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+  } else {
+    TRY(sweep(ibegin, iend, 0, iend, true));                    // active x everybody
+    if (ibegin > 0) TRY(sweep(0, ibegin, ibegin, iend, false));  // passive x active
+  }
+  TRY(download(ctx, dv, ctx->d_out[0], 3 * n));
+  if (tmin) TRY(download(ctx, tmin, ctx->d_out[1], n));
+  return sync(ctx);
+}
+
 int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int n, const double *t, const double *m,
                                      const double *q, const double *p, const double *f,
                                      const double *df, double nt, double eps2, int t0, int t1,

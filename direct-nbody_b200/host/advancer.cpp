@@ -4,7 +4,7 @@
 // logic with the reference's association order; the pair loops run on the GPU:
 //   initialize_before_first_step (:369-393)  -> nbk_grad_v_dgrad_v_sum, then
 //       dVdq0 = c0 (g - h dg), dVdq1 = c1 (g - h/2 dg), dVdq2 = c2 g
-//   interact_bodies (:207-236)               -> two rectangular nbk_grad_v_sum sweeps:
+//   interact_bodies (:207-236)               -> nbk_interact_sum = two rectangular sweeps:
 //       active targets [imin,imax) x sources [imin,n); passive targets [imax,n) x [imin,imax);
 //       dVdqK_x += (vC cs_x[K]) S_x    (grad_v is antisymmetric bit for bit)
 // Only bodies [imin,n) are shipped per call.  The follow_flag print branch (:343-347) is
@@ -90,10 +90,7 @@ struct Adv {
       m[i] = bs[imin + i].m;
       for (int k = 0; k < 3; ++k) q[3 * i + k] = bs[imin + i].q[k];
     }
-    NBH_TRY(ck(ctx, nbk_grad_v_sum(ctx, nn, m.data(), q.data(), eps2, 0, na, 0, nn, S.data())));
-    if (nn > na)
-      NBH_TRY(ck(ctx, nbk_grad_v_sum(ctx, nn, m.data(), q.data(), eps2, na, nn, 0, na,
-                                     S.data() + 3 * (size_t)na)));
+    NBH_TRY(ck(ctx, nbk_interact_sum(ctx, nn, na, m.data(), q.data(), eps2, S.data())));
     for (int i = 0; i < nn; ++i) {
       ABody &b = bs[imin + i];
       const double c0 = vC * b.cs[0], c1 = vC * b.cs[1], c2 = vC * b.cs[2];

@@ -1,7 +1,7 @@
 // leapfrog.cpp — host mirror of Leapfrog (leapfrog.ml:64-68, 106-165): drift, sort_sub,
 // find_can_advance_index, advance_subsystem, advance, advance_const_dt.  The block recursion,
 // drifts and sorts are host logic as in the reference; the two kick loops
-// (leapfrog.ml:132-136, 151-155) are nbk_kick_sum sweeps.
+// (leapfrog.ml:132-136, 151-155) are nbk_kick_block_sum calls (two rectangular kick sweeps).
 //
 // The kernel evaluates every pair of a sweep from the velocities at sweep start (SURVEY.md
 // §3.3), so velocity kicks agree with the reference's sequential loop to rounding and dt_max
@@ -87,18 +87,9 @@ struct Leap {
     const bool ts = !(std::isinf(eta) && eta > 0);
     dv.resize(3 * (size_t)iend);
     tm.resize(iend);
-    NBH_TRY(ck(ctx, nbk_kick_sum(ctx, iend, m.data(), q.data(), v.data(), eta, dt, ibegin, iend,
-                                 0, iend, dv.data(), ts ? tm.data() : nullptr)));
-    std::vector<double> dva(dv.begin(), dv.begin() + 3 * (size_t)(iend - ibegin));
-    std::vector<double> tma(tm.begin(), tm.begin() + (iend - ibegin));
-    if (ibegin > 0) {
-      NBH_TRY(ck(ctx, nbk_kick_sum(ctx, iend, m.data(), q.data(), v.data(), eta, dt, 0, ibegin,
-                                   ibegin, iend, dv.data(), ts ? tm.data() : nullptr)));
-      apply(0, ibegin, ts);
-    }
-    dv.swap(dva);
-    tm.swap(tma);
-    apply(ibegin, iend, ts);
+    NBH_TRY(ck(ctx, nbk_kick_block_sum(ctx, iend, ibegin, m.data(), q.data(), v.data(), eta, dt,
+                                       dv.data(), ts ? tm.data() : nullptr)));
+    apply(0, iend, ts);
     nkicks += 1;
     return 0;
   }

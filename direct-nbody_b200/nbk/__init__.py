@@ -37,6 +37,8 @@ SYMBOLS = {
     "nbk_v_sum": (_i, [_vp, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_energy": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd, _pd]),
     "nbk_kick_sum": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_interact_sum": (_i, [_vp, _i, _i, _pd, _pd, _d, _pd]),
+    "nbk_kick_block_sum": (_i, [_vp, _i, _i, _pd, _pd, _pd, _d, _d, _pd, _pd]),
     "nbk_grad_v_dgrad_v_sum_predicted": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d,
                                               _i, _i, _i, _i, _pd, _pd]),
     "nbk_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _i, _pd, _pd, _pd, _i, _pd, _pd, _d,
@@ -210,6 +212,21 @@ class Context:
         tmin = np.empty(max(t1 - t0, 0)) if want_tmin else None
         self._ck(self._lib.nbk_kick_sum(self._h, n, _p(m), _p(q), _p(v), eta, dt, t0, t1, s0, s1,
                                         _p(dv), _p(tmin)))
+        return dv, tmin
+
+    def interact_sum(self, m, q, na, eps2=0.0):
+        m, q = _arr(m), _arr(q)
+        S = np.empty((len(m), 3))
+        self._ck(self._lib.nbk_interact_sum(self._h, len(m), na, _p(m), _p(q), eps2, _p(S)))
+        return S
+
+    def kick_block_sum(self, m, q, v, eta, dt, ibegin, want_tmin=True):
+        m, q, v = _arr(m), _arr(q), _arr(v)
+        n = len(m)
+        dv = np.empty((n, 3))
+        tmin = np.empty(n) if want_tmin else None
+        self._ck(self._lib.nbk_kick_block_sum(self._h, n, ibegin, _p(m), _p(q), _p(v), eta, dt,
+                                              _p(dv), _p(tmin)))
         return dv, tmin
 
     def grad_v_dgrad_v_sum_predicted(self, t, m, q, p, f, df, nt, eps2=0.0, targets=None,

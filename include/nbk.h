@@ -104,6 +104,22 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
                  double eta, double dt, int t0, int t1, int s0, int s1, double *dv,
                  double *tmin);
 
+/* The whole pair loop of Advancer.A.interact_bodies (advancer.ml:213-235) in one call, for the
+ * bodies the caller ships ([imin, n) of the reference, re-indexed from 0) of which the first
+ * `na` are the active block:
+ *   i <  na:  S_i = sum_{j in [0,n), j != i} Base.grad_v(i, j)     (active x everybody)
+ *   i >= na:  S_i = sum_{j in [0,na)}        Base.grad_v(i, j)     (passive x active)
+ * so that dVdqK_i += (vC cs_i.(K)) S_i.  One upload, two sweeps, one read-back. */
+int nbk_interact_sum(nbk_ctx *ctx, int n, int na, const double *m, const double *q, double eps2,
+                     double *S);
+
+/* The whole kick loop of Leapfrog.advance_subsystem (leapfrog.ml:132-136: for i in
+ * [ibegin,iend), j in [0,i)) in one call, pre-kick order: for the bodies [0,iend),
+ *   i >= ibegin: sources [0,iend) \ {i};   i < ibegin: sources [ibegin,iend).
+ * dv[3 iend], tmin[iend] (tmin may be NULL) as in nbk_kick_sum. */
+int nbk_kick_block_sum(nbk_ctx *ctx, int iend, int ibegin, const double *m, const double *q,
+                       const double *v, double eta, double dt, double *dv, double *tmin);
+
 /* Hermite.advance_body's loop (hermite.ml:106-115): every body is first predicted to time
  * `nt` (predict_position_into / predict_momentum_into, hermite.ml:53-72) from its own
  * (t,q,p,f,df), then gsum/dgsum as in nbk_grad_v_dgrad_v_sum over the predicted bodies

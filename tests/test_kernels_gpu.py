@@ -290,3 +290,31 @@ def test_sharded_driver_single_rank(ctx, oracle):
                                    g2.data_ptr(), dg2.data_ptr(), k > 0, s)
     torch.cuda.synchronize()
     assert rel_err(g2.cpu().numpy(), g_ref) <= TOL and rel_err(dg2.cpu().numpy(), dg_ref) <= TOL
+
+
+@pytest.mark.parametrize("n,na", [(300, 1), (300, 7), (300, 300), (2000, 40), (64, 0)])
+def test_interact_and_kick_block_calls(ctx, oracle, n, na):
+    """nbk_interact_sum = the pair loop of Advancer.A.interact_bodies (advancer.ml:213-235) and
+    nbk_kick_block_sum = Leapfrog's kick loop (leapfrog.ml:132-136), each two rectangles in
+    one call, against the oracle's rectangular sums."""
+    m, q, p = oracle.make_plummer(n, 17)
+    S = ctx.interact_sum(m, q, na, 1e-4)
+    ref = np.zeros((n, 3))
+    if na:
+        ref[:na] = oracle.grad_v_sum(m, q, 1e-4, targets=(0, na), sources=(0, n))
+        if n > na:
+            ref[na:] = oracle.grad_v_sum(m, q, 1e-4, targets=(na, n), sources=(0, na))
+        assert rel_err(S, ref) <= TOL
+    else:
+        assert not S.any()
+    v = p / m[:, None]
+    ib = n - na  # active block = the LAST na bodies [ib, n)
+    dv, tmin = ctx.kick_block_sum(m, q, v, 1e-3, 1e-4, ib)
+    if na:
+        dv_a, tm_a = oracle.kick_sum(m, q, v, 1e-3, 1e-4, targets=(ib, n), sources=(0, n))
+        assert rel_err(dv[ib:], dv_a) <= TOL and np.array_equal(tmin[ib:], tm_a)
+        if ib > 0:
+            dv_p, tm_p = oracle.kick_sum(m, q, v, 1e-3, 1e-4, targets=(0, ib), sources=(ib, n))
+            assert rel_err(dv[:ib], dv_p) <= TOL and np.array_equal(tmin[:ib], tm_p)
+    else:
+        assert not dv.any() and np.all(np.isinf(tmin))
