@@ -3,6 +3,7 @@
 #include "../../include/nbk.h"
 #include "sweep.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -575,6 +576,112 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
   if (tmin && !v) return fail(ctx, NBK_ERR_ARG, "time-scale needs velocities");
   TRY(stage_bodies(ctx, n, m, q, v, 1));
   return run_kick(ctx, (const double *)ctx->d_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
+}
+
+int nbk_binary_scan(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+                    double eps2, double threshold, int t0, int t1, int s0, int s1, double *emin,
+                    int *partner, int *count) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  const int nt = t1 - t0;
+  if (n == 0 || nt == 0) return NBK_OK;
+  if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
+  TRY(stage_bodies(ctx, n, m, q, p, 0));
+  index_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((double *)ctx->d_packed.p, n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  for (int k = 0; k < 3; ++k) TRY(reserve(ctx, ctx->d_out[k], (size_t)nt * sizeof(double)));
+  std::string hbuf((size_t)nt * 3 * sizeof(double), '\0');
+  double *h = reinterpret_cast<double *>(&hbuf[0]);
+  if (s1 == s0) {
+    for (int i = 0; i < nt; ++i) {
+      h[i] = __builtin_inf();
+      h[nt + i] = -1.0;
+      h[2 * nt + i] = 0.0;
+    }
+  } else {
+    SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1);
+    P.dt = threshold;
+    for (int k = 0; k < 3; ++k) P.out[k] = (double *)ctx->d_out[k].p;
+    TRY(run_op<OpBinary>(ctx, P, ctx->stream, true));
+    for (int k = 0; k < 3; ++k)
+      CK(cudaMemcpyAsync(h + (size_t)k * nt, ctx->d_out[k].p, (size_t)nt * sizeof(double),
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+  }
+  for (int i = 0; i < nt; ++i) {
+    if (emin) emin[i] = h[i];
+    if (partner) partner[i] = (int)h[nt + i];
+    if (count) count[i] = (int)h[2 * nt + i];
+  }
+  return NBK_OK;
+}
+
+int nbk_binary_list(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+                    double eps2, double threshold, int max_pairs, int *pi, int *pj, double *e,
+                    int *npairs) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || max_pairs < 0 || !npairs || (max_pairs > 0 && (!pi || !pj || !e)))
+    return fail(ctx, NBK_ERR_ARG, "nbk_binary_list: bad arguments");
+  *npairs = 0;
+  if (n < 2) return NBK_OK;
+  std::string cbuf((size_t)n * sizeof(int), '\0');
+  int *cnt = reinterpret_cast<int *>(&cbuf[0]);
+  TRY(nbk_binary_scan(ctx, n, m, q, p, eps2, threshold, 0, n, 0, n, nullptr, nullptr, cnt));
+  std::string fbuf((size_t)n * sizeof(int), '\0');
+  int *flagged = reinterpret_cast<int *>(&fbuf[0]);
+  int nf = 0;
+  for (int i = 0; i < n; ++i)
+    if (cnt[i] > 0) flagged[nf++] = i;
+  if (nf == 0) return NBK_OK;
+  // d_packed still holds the staged, indexed bodies of the scan
+  TRY(reserve(ctx, ctx->d_aux_in, (size_t)nf * sizeof(int)));
+  TRY(reserve(ctx, ctx->d_out[0], (size_t)(max_pairs + 1) * sizeof(int)));
+  TRY(reserve(ctx, ctx->d_out[1], (size_t)(max_pairs + 1) * sizeof(int)));
+  TRY(reserve(ctx, ctx->d_out[2], (size_t)(max_pairs + 1) * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_scalar, 64));
+  CK(cudaMemcpyAsync(ctx->d_aux_in.p, flagged, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_scalar.p, 0, 64, ctx->stream));
+  binary_list_kernel<<<nf, 256, 0, ctx->stream>>>(
+      (const double *)ctx->d_packed.p, n, (const int *)ctx->d_aux_in.p, eps2, threshold, max_pairs,
+      (int *)ctx->d_out[0].p, (int *)ctx->d_out[1].p, (double *)ctx->d_out[2].p,
+      (int *)ctx->d_scalar.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  int found = 0;
+  CK(cudaMemcpyAsync(&found, ctx->d_scalar.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  *npairs = found;
+  const int take = found < max_pairs ? found : max_pairs;
+  if (take > 0) {
+    CK(cudaMemcpyAsync(pi, ctx->d_out[0].p, (size_t)take * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pj, ctx->d_out[1].p, (size_t)take * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(e, ctx->d_out[2].p, (size_t)take * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+    // the kernel appends in arrival order: sort into the reference's loop order (i, then j)
+    std::string obuf((size_t)take * sizeof(int), '\0');
+    int *ord = reinterpret_cast<int *>(&obuf[0]);
+    for (int k = 0; k < take; ++k) ord[k] = k;
+    std::sort(ord, ord + take, [&](int a, int b) {
+      return pi[a] != pi[b] ? pi[a] < pi[b] : pj[a] < pj[b];
+    });
+    std::string t1((size_t)take * sizeof(int), '\0'), t2((size_t)take * sizeof(int), '\0'),
+        t3((size_t)take * sizeof(double), '\0');
+    int *si = reinterpret_cast<int *>(&t1[0]), *sj = reinterpret_cast<int *>(&t2[0]);
+    double *se = reinterpret_cast<double *>(&t3[0]);
+    for (int k = 0; k < take; ++k) {
+      si[k] = pi[ord[k]];
+      sj[k] = pj[ord[k]];
+      se[k] = e[ord[k]];
+    }
+    memcpy(pi, si, (size_t)take * sizeof(int));
+    memcpy(pj, sj, (size_t)take * sizeof(int));
+    memcpy(e, se, (size_t)take * sizeof(double));
+  }
+  if (found > max_pairs)
+    return fail(ctx, NBK_ERR_ARG, "nbk_binary_list: %d pairs found, room for %d", found, max_pairs);
+  return NBK_OK;
 }
 
 int nbk_interact_sum(nbk_ctx *ctx, int n, int na, const double *m, const double *q, double eps2,

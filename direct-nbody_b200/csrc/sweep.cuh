@@ -357,6 +357,70 @@ template <bool WITH_TSCALE> struct OpKick {
   }
 };
 
+// Analysis.binary_energy scanned over sources (analysis.ml:809-822, the pair function of
+// Analysis.binaries / binaries_threshold / tightest_binary, analysis.ml:836-876):
+//   e(i,j) = 0.5 mu |v_j - v_i|^2 + Base.v(i,j),  mu = m_i m_j / (m_i + m_j)
+// evaluated with the reference's IEEE operation sequence (no contraction), so the decisions
+// e < threshold and the minimum are bit-exact.  Per target: acc[0] = min_j e(i,j),
+// acc[1] = the partner index attaining it (lowest index on ties), acc[2] = #{j : e < thr}.
+// P.dt carries the threshold.
+struct OpBinary {
+  static constexpr int NACC = 3;
+  static constexpr int ND2 = 4;
+  struct Tgt {
+    double x, y, z, vx, vy, vz, m;
+  };
+  __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
+    t.x = pk[0];
+    t.y = pk[1];
+    t.z = pk[2];
+    t.m = pk[3];
+    t.vx = pk[4];
+    t.vy = pk[5];
+    t.vz = pk[6];
+  }
+  __device__ __forceinline__ static void zero(double *acc) {
+    acc[0] = __longlong_as_double(0x7ff0000000000000LL);
+    acc[1] = -1.0;
+    acc[2] = 0.0;
+  }
+  template <bool CHECK>
+  __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
+                                              const double2 *, bool self, const SweepParams &P) {
+    if (self) return;
+    const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
+    const double ux = __dsub_rn(c.x, t.vx), uy = __dsub_rn(c.y, t.vy), uz = __dsub_rn(d.x, t.vz);
+    const double dx = __dsub_rn(t.x, a.x), dy = __dsub_rn(t.y, a.y), dz = __dsub_rn(t.z, b.x);
+    const double mj = b.y;
+    const double mu = __ddiv_rn(__dmul_rn(t.m, mj), __dadd_rn(t.m, mj));
+    const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), __dmul_rn(uz, uz));
+    const double ke = __dmul_rn(__dmul_rn(0.5, mu), v2);
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double r = __dsqrt_rn(__dadd_rn(r2, P.eps2));
+    const double pe = __ddiv_rn(__dmul_rn(-t.m, mj), r);
+    const double e = __dadd_rn(ke, pe);
+    // the packed source carries its global index in slot 7 (see nbk_binary_scan)
+    const double jidx = d.y;
+    if (e < acc[0] || (e == acc[0] && jidx < acc[1])) {
+      acc[0] = e;
+      acc[1] = jidx;
+    }
+    if (e < P.dt) acc[2] += 1.0;
+  }
+  __device__ __forceinline__ static void combine(double *a, const double *b) {
+    if (b[0] < a[0] || (b[0] == a[0] && b[1] >= 0.0 && (a[1] < 0.0 || b[1] < a[1]))) {
+      a[0] = b[0];
+      a[1] = b[1];
+    }
+    a[2] += b[2];
+  }
+  __device__ __forceinline__ static void store(const SweepParams &P, int ig, const double *acc) {
+    P.out[0][ig - P.t0] = acc[0];
+    P.out[1][ig - P.t0] = acc[1];
+    P.out[2][ig - P.t0] = acc[2];
+  }
+};
+
 // One source against the IPT targets of a thread.  Ops may provide a batched form
 // (Op::BATCHED) that walks the IPT interactions phase by phase, so that the instruction
 // stream handed to ptxas already interleaves independent interactions and keeps FMAs that
@@ -1127,6 +1191,44 @@ __global__ void __launch_bounds__(HRES_THREADS, 1)
 #pragma unroll
     for (int c = 0; c < 16; ++c) state[(size_t)j * HB + c] = rec[j * HRES_STRIDE + c];
   if (tid == 0) *nsteps_out = steps;
+}
+
+// ---- Analysis.binaries support ------------------------------------------------------------------
+// Slot 7 of a packed body := its global index (OpBinary reports partners by index).
+__global__ void index_kernel(double *__restrict__ packed, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[(size_t)i * PK + 7] = (double)i;
+}
+
+// Lists the pairs (i, j > i) with binary_energy < thr for the flagged targets (those whose
+// scan count is non-zero; there are few): one CTA per flagged target, threads stride over j.
+// Pairs are appended in arrival order; the caller sorts them.  Same IEEE sequence as OpBinary.
+__global__ void __launch_bounds__(256) binary_list_kernel(const double *__restrict__ packed, int n,
+                                                          const int *__restrict__ flagged,
+                                                          double eps2, double thr, int max_pairs,
+                                                          int *__restrict__ pi, int *__restrict__ pj,
+                                                          double *__restrict__ pe,
+                                                          int *__restrict__ npairs) {
+  const int i = flagged[blockIdx.x];
+  OpBinary::Tgt t;
+  SweepParams P;
+  P.eps2 = eps2;
+  P.dt = thr;
+  OpBinary::load(t, packed + (size_t)i * PK, P, i);
+  for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+    double acc[3];
+    OpBinary::zero(acc);
+    OpBinary::pair<true>(t, acc, reinterpret_cast<const double2 *>(packed + (size_t)j * PK),
+                         nullptr, false, P);
+    if (acc[2] > 0.0) {
+      const int slot = atomicAdd(npairs, 1);
+      if (slot < max_pairs) {
+        pi[slot] = i;
+        pj[slot] = j;
+        pe[slot] = acc[0];
+      }
+    }
+  }
 }
 
 // ---- Leapfrog DKD on device-resident packed bodies (leapfrog.ml:64-68, 129-137) ----------------

@@ -37,6 +37,10 @@ SYMBOLS = {
     "nbk_v_sum": (_i, [_vp, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_energy": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd, _pd]),
     "nbk_kick_sum": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _i, _i, _i, _i, _pd, _pd]),
+    "nbk_binary_scan": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _i, _i, _i, _i, _pd, C.POINTER(_i),
+                             C.POINTER(_i)]),
+    "nbk_binary_list": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _i, C.POINTER(_i), C.POINTER(_i), _pd,
+                             C.POINTER(_i)]),
     "nbk_interact_sum": (_i, [_vp, _i, _i, _pd, _pd, _d, _pd]),
     "nbk_kick_block_sum": (_i, [_vp, _i, _i, _pd, _pd, _pd, _d, _d, _pd, _pd]),
     "nbk_grad_v_dgrad_v_sum_predicted": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d,
@@ -213,6 +217,31 @@ class Context:
         self._ck(self._lib.nbk_kick_sum(self._h, n, _p(m), _p(q), _p(v), eta, dt, t0, t1, s0, s1,
                                         _p(dv), _p(tmin)))
         return dv, tmin
+
+    def binary_scan(self, m, q, p, eps2=0.0, threshold=0.0, targets=None, sources=None):
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        n = len(m)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        nt = max(t1 - t0, 0)
+        emin = np.empty(nt)
+        partner, count = np.empty(nt, dtype=np.int32), np.empty(nt, dtype=np.int32)
+        ip = C.POINTER(_i)
+        self._ck(self._lib.nbk_binary_scan(self._h, n, _p(m), _p(q), _p(p), eps2, threshold, t0, t1,
+                                           s0, s1, _p(emin), partner.ctypes.data_as(ip),
+                                           count.ctypes.data_as(ip)))
+        return emin, partner, count
+
+    def binary_list(self, m, q, p, eps2=0.0, threshold=0.0, max_pairs=1 << 20):
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        pi, pj = np.empty(max_pairs, dtype=np.int32), np.empty(max_pairs, dtype=np.int32)
+        e = np.empty(max_pairs)
+        npairs = _i(0)
+        ip = C.POINTER(_i)
+        self._ck(self._lib.nbk_binary_list(self._h, len(m), _p(m), _p(q), _p(p), eps2, threshold,
+                                           max_pairs, pi.ctypes.data_as(ip), pj.ctypes.data_as(ip),
+                                           _p(e), C.byref(npairs)))
+        k = npairs.value
+        return pi[:k].copy(), pj[:k].copy(), e[:k].copy()
 
     def interact_sum(self, m, q, na, eps2=0.0):
         m, q = _arr(m), _arr(q)

@@ -104,6 +104,24 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
                  double eta, double dt, int t0, int t1, int s0, int s1, double *dv,
                  double *tmin);
 
+/* Analysis.binary_energy (analysis.ml:809-822) scanned over sources, the O(N^2) loop of
+ * Analysis.binaries / binaries_threshold / tightest_binary (analysis.ml:836-876).  For target i:
+ *   emin[i-t0]    = min_j e(i,j)      (+inf if there is no source)
+ *   partner[i-t0] = the j attaining it (lowest j on ties; -1 if none)
+ *   count[i-t0]   = #{ j : e(i,j) < threshold }
+ * e is evaluated with the reference's IEEE operation sequence, so comparisons and minima are
+ * bit-exact; any output pointer may be NULL.  binaries uses threshold 0, binaries_threshold
+ * -|eg|; tightest_binary is the global minimum of emin over targets with emin < 0. */
+int nbk_binary_scan(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+                    double eps2, double threshold, int t0, int t1, int s0, int s1, double *emin,
+                    int *partner, int *count);
+/* The pairs themselves: every (i, j > i) with e(i,j) < threshold, in the reference's loop
+ * order (i ascending, then j), at most max_pairs of them; *npairs = the number found (an error
+ * is returned if it exceeds max_pairs, with the first max_pairs in arrival order). */
+int nbk_binary_list(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+                    double eps2, double threshold, int max_pairs, int *pi, int *pj, double *e,
+                    int *npairs);
+
 /* The whole pair loop of Advancer.A.interact_bodies (advancer.ml:213-235) in one call, for the
  * bodies the caller ships ([imin, n) of the reference, re-indexed from 0) of which the first
  * `na` are the active block:

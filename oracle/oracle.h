@@ -44,6 +44,9 @@ void oracle_kick_block(int n, const double *m, const double *q, double *v, doubl
 void oracle_kick_sum(int n, const double *m, const double *q, const double *v, double eta,
                      double dt, int t0, int t1, int s0, int s1, double *dv, double *tmin);
 
+int oracle_binaries(int n, const double *m, const double *q, const double *p, double eps2,
+                    double thr, int max_pairs, int *pi, int *pj, double *e);
+
 /* quad.c (binary128 truth) */
 void oracle_grad_v_dgrad_v_sum_quad(int n, const double *m, const double *q, const double *p,
                                     double eps2, int t0, int t1, int s0, int s1, double *gsum,

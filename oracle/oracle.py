@@ -66,6 +66,7 @@ def _declare(L):
     sig("oracle_kick_all_pairs", None, _i, _pd, _pd, _pd, _pd, _d, _d)
     sig("oracle_kick_block", None, _i, _pd, _pd, _pd, _pd, _d, _d, _i, _i)
     sig("oracle_kick_sum", None, _i, _pd, _pd, _pd, _d, _d, _i, _i, _i, _i, _pd, _pd)
+    sig("oracle_binaries", _i, _i, _pd, _pd, _pd, _d, _d, _i, _pi, _pi, _pd)
     sig("oracle_grad_v_dgrad_v_sum_quad", None, _i, _pd, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd)
     sig("oracle_v_sum_quad", None, _i, _pd, _pd, _d, _i, _i, _i, _i, _pd)
     sig("oracle_total_potential_energy_quad", _d, _i, _pd, _pd, _d)
@@ -243,6 +244,16 @@ def kick_sum(m, q, v, eta, dt, targets=None, sources=None):
     dv, tmin = np.empty((t1 - t0, 3)), np.empty(t1 - t0)
     lib().oracle_kick_sum(n, _p(m), _p(q), _p(v), eta, dt, t0, t1, s0, s1, _p(dv), _p(tmin))
     return dv, tmin
+
+
+def binaries(m, q, p, eps2=0.0, threshold=0.0, max_pairs=1 << 20):
+    """Analysis.binaries / binaries_threshold (analysis.ml:836-861): (i, j, e) in loop order."""
+    m, q, p = _f(m), _f(q), _f(p)
+    pi, pj = np.empty(max_pairs, dtype=np.int32), np.empty(max_pairs, dtype=np.int32)
+    e = np.empty(max_pairs)
+    k = lib().oracle_binaries(len(m), _p(m), _p(q), _p(p), eps2, threshold, max_pairs, _ip(pi),
+                              _ip(pj), _p(e))
+    return pi[:k].copy(), pj[:k].copy(), e[:k].copy()
 
 
 def grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, eps2=0.0, targets=None, sources=None):

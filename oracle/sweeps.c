@@ -253,3 +253,35 @@ void oracle_kick_sum(int n, const double *m, const double *q, const double *v, d
     tmin[i - t0] = tm;
   }
 }
+
+/* analysis.ml:809-822  binary_energy b1 b2 */
+static inline double ob_binary_energy(double eps2, double m1, const double *q1, const double *p1,
+                                      double m2, const double *q2, const double *p2) {
+  double vrel[3];
+  for (int i = 0; i < 3; ++i) vrel[i] = p2[i] / m2 - p1[i] / m1;
+  double mu = m1 * m2 / (m1 + m2);
+  double ke = 0.5 * mu * ob_dot(vrel, vrel);
+  double pe = ob_v(eps2, m1, q1, m2, q2);
+  return ke + pe;
+}
+
+/* analysis.ml:836-861  binaries (thr = 0) / binaries_threshold (thr = -|eg|): every pair i<j
+ * with binary_energy < thr, reported in LOOP order (the reference conses, so its list is this
+ * order reversed).  Returns the number found; stores at most max_pairs. */
+int oracle_binaries(int n, const double *m, const double *q, const double *p, double eps2,
+                    double thr, int max_pairs, int *pi, int *pj, double *e) {
+  int k = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      double en = ob_binary_energy(eps2, m[i], q + 3 * i, p + 3 * i, m[j], q + 3 * j, p + 3 * j);
+      if (en < thr) {
+        if (k < max_pairs) {
+          pi[k] = i;
+          pj[k] = j;
+          e[k] = en;
+        }
+        ++k;
+      }
+    }
+  return k;
+}

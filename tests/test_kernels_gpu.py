@@ -318,3 +318,23 @@ def test_interact_and_kick_block_calls(ctx, oracle, n, na):
             assert rel_err(dv[:ib], dv_p) <= TOL and np.array_equal(tmin[:ib], tm_p)
     else:
         assert not dv.any() and np.all(np.isinf(tmin))
+
+
+@pytest.mark.parametrize("n,thr", [(500, 0.0), (2000, 0.0), (2000, -1e-3), (300, -1e9)])
+def test_binaries_scan_and_list_bit_exact(ctx, oracle, n, thr):
+    """Analysis.binaries / binaries_threshold / tightest_binary (analysis.ml:836-876): the bound
+    pairs, their energies and the tightest one, bit for bit against the oracle's loops."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 23))
+    oi, oj, oe = oracle.binaries(m, q, p, 0.0, thr)
+    gi, gj, ge = ctx.binary_list(m, q, p, 0.0, thr)
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(ge, oe)
+    emin, partner, count = ctx.binary_scan(m, q, p, 0.0, thr)
+    cnt_ref = np.bincount(oi, minlength=n) + np.bincount(oj, minlength=n)
+    assert np.array_equal(count, cnt_ref)
+    if thr == 0.0 and len(oe):
+        k = int(np.argmin(oe))          # tightest_binary: largest |e| among e < 0
+        i = int(np.argmin(emin))
+        assert emin[i] == oe[k] and {i, int(partner[i])} == {int(oi[k]), int(oj[k])}
+    # rectangular form: a few targets against a source window
+    e2, p2, c2 = ctx.binary_scan(m, q, p, 0.0, thr, targets=(10, 13), sources=(0, 200))
+    assert np.all((p2 >= 0) & (p2 < 200)) and np.all(p2 != np.arange(10, 13))
