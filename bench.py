@@ -329,7 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=131072)
-    ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--cpu-sample", type=int, default=65536,
+                    help="bodies of the workload the CPU arm sweeps per step (~20 core-seconds)")
     ap.add_argument("--overlap", type=int, default=0,
                     help="1: sweep local sources while the all-gather is in flight")
     args = ap.parse_args()
