@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 using namespace nbk;
 
@@ -45,6 +46,9 @@ struct nbk_ctx {
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
   // pinned host staging for scalar read-back
   double *h_scalar = nullptr;
+  // single-process multi-GPU (nbk_create_multi): further contexts, one per extra device
+  std::vector<nbk_ctx *> peers;
+  cudaEvent_t ev_ready = nullptr;
 };
 
 namespace {
@@ -98,17 +102,19 @@ int check_ranges(nbk_ctx *ctx, int n, int t0, int t1, int s0, int s1) {
 // ---- sweep launcher --------------------------------------------------------------------------
 template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
   static int occupancy(nbk_ctx *ctx, int *occ) {
-    static int cached = -1;
-    if (cached < 0) {
+    // the shared-memory attribute is per device: cache per device ordinal
+    static int cached[64] = {0};
+    int &slot = cached[ctx->device & 63];
+    if (slot <= 0) {
       auto kern = sweep_kernel<Op, NT, IPT, MINB, UNROLL>;
       constexpr size_t smem = sweep_smem_bytes(naux_of<Op>::value);
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int o = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NT, smem));
       if (o < 1) return fail(ctx, NBK_ERR_CUDA, "sweep kernel does not fit on an SM");
-      cached = o;
+      slot = o;
     }
-    *occ = cached;
+    *occ = slot;
     return NBK_OK;
   }
 
@@ -425,6 +431,49 @@ int run_kick(nbk_ctx *ctx, const double *packed, double eta, double dt, int t0, 
 
 }  // namespace
 
+// ---- single-process multi-GPU: targets sharded over the devices of a multi context ----------
+// The host has all bodies, so the exchange step is a broadcast: bodies are uploaded and packed
+// once on the first device and copied to the others over NVLink (cudaMemcpyPeerAsync), every
+// device sweeps its slice of the targets over all sources, and each slice is read back into
+// its place in the caller's arrays.  All launches are issued before any read-back so the
+// devices run concurrently.
+struct Slice {
+  nbk_ctx *c;
+  int a, b;  // targets [a, b) of this device
+};
+
+int multi_plan(nbk_ctx *ctx, int t0, int t1, std::vector<Slice> &out) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  const int nt = t1 - t0;
+  int per = (nt + ndev - 1) / ndev;
+  per = (per + 1023) / 1024 * 1024;  // whole large tiles per device
+  for (int d = 0; d < ndev; ++d) {
+    nbk_ctx *c = d == 0 ? ctx : ctx->peers[d - 1];
+    int a = t0 + d * per, b = t0 + (d + 1) * per;
+    if (a > t1) a = t1;
+    if (b > t1) b = t1;
+    out.push_back({c, a, b});
+  }
+  return NBK_OK;
+}
+
+// Stage on device 0 and broadcast the packed array to the peers.
+int multi_stage(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
+                int is_velocity) {
+  CK(cudaSetDevice(ctx->device));
+  TRY(stage_bodies(ctx, n, m, q, vel, is_velocity));
+  CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+  const size_t bytes = (size_t)n * PK * sizeof(double);
+  for (nbk_ctx *peer : ctx->peers) {
+    CK(cudaSetDevice(peer->device));
+    TRY(reserve(peer, peer->d_packed, bytes));
+    CK(cudaStreamWaitEvent(peer->stream, ctx->ev_ready, 0));
+    CK(cudaMemcpyPeerAsync(peer->d_packed.p, peer->device, ctx->d_packed.p, ctx->device, bytes,
+                           peer->stream));
+  }
+  return NBK_OK;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -462,7 +511,9 @@ int nbk_create(nbk_ctx **out, int device) {
   cudaError_t e2 = cudaEventCreate(&c->ev0);
   cudaError_t e3 = cudaEventCreate(&c->ev1);
   cudaError_t e4 = cudaMallocHost((void **)&c->h_scalar, 64);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+  cudaError_t e5 = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess ||
+      e5 != cudaSuccess) {
     nbk_destroy(c);
     return fail(nullptr, NBK_ERR_CUDA, "nbk_create: stream/event/pinned allocation failed");
   }
@@ -470,9 +521,44 @@ int nbk_create(nbk_ctx **out, int device) {
   return NBK_OK;
 }
 
+int nbk_create_multi(nbk_ctx **out, int ndev, const int *devices) {
+  nbk_ctx *ctx = nullptr;
+  if (!out || ndev < 1) return fail(nullptr, NBK_ERR_ARG, "nbk_create_multi: bad arguments");
+  *out = nullptr;
+  nbk_ctx *root = nullptr;
+  TRY(nbk_create(&root, devices ? devices[0] : 0));
+  for (int d = 1; d < ndev; ++d) {
+    nbk_ctx *peer = nullptr;
+    int rc = nbk_create(&peer, devices ? devices[d] : d);
+    if (rc != NBK_OK) {
+      nbk_destroy(root);
+      return rc;
+    }
+    root->peers.push_back(peer);
+    // direct NVLink copies between the devices (ignore "already enabled")
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, peer->device, root->device);
+    if (can) {
+      cudaSetDevice(peer->device);
+      cudaDeviceEnablePeerAccess(root->device, 0);
+      cudaSetDevice(root->device);
+      cudaDeviceEnablePeerAccess(peer->device, 0);
+      cudaGetLastError();
+    }
+  }
+  CK(cudaSetDevice(root->device));
+  *out = root;
+  return NBK_OK;
+}
+
+int nbk_device_count(const nbk_ctx *ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
+
 void nbk_destroy(nbk_ctx *c) {
   if (!c) return;
+  for (nbk_ctx *peer : c->peers) nbk_destroy(peer);
+  c->peers.clear();
   cudaSetDevice(c->device);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->d_t,     &c->d_f,      &c->d_df,     &c->d_aux_in2,
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
@@ -505,6 +591,32 @@ int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double
   TRY(check_ranges(ctx, n, t0, t1, s0, s1));
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return NBK_OK;
+  if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
+    if (!gsum) return fail(ctx, NBK_ERR_ARG, "null output");
+    TRY(multi_stage(ctx, n, m, q, nullptr, 1));
+    std::vector<Slice> sl;
+    TRY(multi_plan(ctx, t0, t1, sl));
+    for (Slice &s : sl) {
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
+      int rc = reserve(c, c->d_out[0], 3 * (size_t)(s.b - s.a) * sizeof(double));
+      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      P.out[0] = (double *)c->d_out[0].p;
+      if (rc == NBK_OK) rc = K1::run(c, P, c->stream, true);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+    }
+    for (Slice &s : sl) {
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      cudaSetDevice(c->device);
+      int rc = download(c, gsum + 3 * (size_t)(s.a - t0), c->d_out[0], 3 * (size_t)(s.b - s.a));
+      if (rc == NBK_OK) rc = sync(c);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+    }
+    CK(cudaSetDevice(ctx->device));
+    return NBK_OK;
+  }
   TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
   return run_grad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum);
 }
@@ -516,6 +628,37 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return NBK_OK;
   if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
+  if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
+    if (!gsum || !dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
+    TRY(multi_stage(ctx, n, m, q, p, 0));
+    std::vector<Slice> sl;
+    TRY(multi_plan(ctx, t0, t1, sl));
+    for (Slice &s : sl) {
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
+      const size_t cnt = 3 * (size_t)(s.b - s.a) * sizeof(double);
+      int rc = reserve(c, c->d_out[0], cnt);
+      if (rc == NBK_OK) rc = reserve(c, c->d_out[1], cnt);
+      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      P.out[0] = (double *)c->d_out[0].p;
+      P.out[1] = (double *)c->d_out[1].p;
+      if (rc == NBK_OK) rc = run_k2(c, P, c->stream, true);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+    }
+    for (Slice &s : sl) {
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      cudaSetDevice(c->device);
+      const size_t cnt = 3 * (size_t)(s.b - s.a);
+      int rc = download(c, gsum + 3 * (size_t)(s.a - t0), c->d_out[0], cnt);
+      if (rc == NBK_OK) rc = download(c, dgsum + 3 * (size_t)(s.a - t0), c->d_out[1], cnt);
+      if (rc == NBK_OK) rc = sync(c);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+    }
+    CK(cudaSetDevice(ctx->device));
+    return NBK_OK;
+  }
   TRY(stage_bodies(ctx, n, m, q, p, 0));
   return run_grad_v_dgrad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum,
                             dgsum);
@@ -527,6 +670,43 @@ int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2
   CK(cudaSetDevice(ctx->device));
   if (n == 0) {
     if (total) *total = 0.0;
+    return NBK_OK;
+  }
+  if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
+    TRY(multi_stage(ctx, n, m, q, nullptr, 1));
+    std::vector<Slice> sl;
+    TRY(multi_plan(ctx, t0, t1, sl));
+    for (Slice &s : sl) {  // launch everywhere first
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
+      int rc = reserve(c, c->d_out[0], (size_t)(s.b - s.a) * sizeof(double));
+      if (rc == NBK_OK) rc = reserve(c, c->d_scalar, 64);
+      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      P.out[0] = (double *)c->d_out[0].p;
+      if (rc == NBK_OK) rc = K3::run(c, P, c->stream, true);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+      if (total) {
+        sum_kernel<<<1, 1024, 0, c->stream>>>((const double *)c->d_out[0].p, s.b - s.a,
+                                              (double *)c->d_scalar.p);
+        c->launches++;
+        cudaMemcpyAsync(c->h_scalar, c->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost,
+                        c->stream);
+      }
+    }
+    double tot = 0.0;
+    for (Slice &s : sl) {  // then collect, in device order (fixed summation order)
+      if (s.b == s.a) continue;
+      nbk_ctx *c = s.c;
+      cudaSetDevice(c->device);
+      int rc = NBK_OK;
+      if (phi) rc = download(c, phi + (size_t)(s.a - t0), c->d_out[0], (size_t)(s.b - s.a));
+      if (rc == NBK_OK) rc = sync(c);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+      if (total) tot += c->h_scalar[0];
+    }
+    if (total) *total = tot;
+    CK(cudaSetDevice(ctx->device));
     return NBK_OK;
   }
   TRY(stage_bodies(ctx, n, m, q, nullptr, 1));

@@ -26,6 +26,8 @@ _vp = C.c_void_p
 # name -> (restype, argtypes): every symbol include/nbk.h declares.
 SYMBOLS = {
     "nbk_create": (_i, [C.POINTER(_vp), _i]),
+    "nbk_create_multi": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),
+    "nbk_device_count": (_i, [_vp]),
     "nbk_destroy": (None, [_vp]),
     "nbk_last_error": (C.c_char_p, [_vp]),
     "nbk_version": (C.c_char_p, []),
@@ -118,10 +120,17 @@ def _p(a):
 class Context:
     """One libnbk context = one GPU (nbk_create / nbk_destroy)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
+        """device: one GPU.  devices=[d0, d1, ...]: a single-process multi-GPU context
+        (nbk_create_multi) whose host-buffer sweeps shard their targets over those GPUs."""
         self._lib = load_library()
         h = _vp()
-        rc = self._lib.nbk_create(C.byref(h), device)
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._lib.nbk_create_multi(C.byref(h), len(devices), arr)
+            device = devices[0]
+        else:
+            rc = self._lib.nbk_create(C.byref(h), device)
         if rc != 0:
             raise NbkError(rc, self._lib.nbk_last_error(None).decode())
         self._h = h
@@ -145,6 +154,10 @@ class Context:
             raise NbkError(rc, self._lib.nbk_last_error(self._h).decode())
 
     # -------------------------------------------------------------- info
+    @property
+    def device_count(self):
+        return self._lib.nbk_device_count(self._h)
+
     @property
     def sm_count(self):
         return self._lib.nbk_sm_count(self._h)

@@ -53,6 +53,15 @@ typedef struct nbk_ctx nbk_ctx;
 /* Creates a context bound to CUDA device `device` (ordinal).  Owns one stream, all device
  * workspaces and pinned staging buffers; they grow on demand. */
 int nbk_create(nbk_ctx **ctx, int device);
+/* Single-process multi-GPU context over ndev devices (devices[] = their ordinals, or NULL for
+ * 0..ndev-1) - what a single OCaml process uses to drive the GPUs of one box.  It behaves like
+ * a context on the first device, except that the host-buffer sweeps nbk_grad_v_dgrad_v_sum,
+ * nbk_grad_v_sum, nbk_v_sum and nbk_energy shard their TARGETS over all the devices: bodies are
+ * uploaded and packed once, broadcast to the other devices over NVLink, every device sweeps its
+ * slice over all sources, and the slices are read back into place.  Results are independent of
+ * ndev (each target's sum is formed by one device in the same order). */
+int nbk_create_multi(nbk_ctx **ctx, int ndev, const int *devices);
+int nbk_device_count(const nbk_ctx *ctx);
 void nbk_destroy(nbk_ctx *ctx);
 /* Text of the last error on ctx; with ctx == NULL, of the last failed nbk_create. */
 const char *nbk_last_error(const nbk_ctx *ctx);

@@ -338,3 +338,28 @@ def test_binaries_scan_and_list_bit_exact(ctx, oracle, n, thr):
     # rectangular form: a few targets against a source window
     e2, p2, c2 = ctx.binary_scan(m, q, p, 0.0, thr, targets=(10, 13), sources=(0, 200))
     assert np.all((p2 >= 0) & (p2 < 200)) and np.all(p2 != np.arange(10, 13))
+
+
+def test_single_process_multi_gpu_context(oracle):
+    """nbk_create_multi: one process, several GPUs, targets sharded by the library.  Results must
+    be IDENTICAL to the single-GPU context (each target is summed by one device in the same
+    order).  Needs >= 2 GPUs; on a 1-GPU box the 1-device multi context is exercised."""
+    import torch
+    import nbk
+    ndev = min(torch.cuda.device_count(), 4)
+    n = 5000
+    m, q, p = oracle.make_plummer(n, 29)
+    with nbk.Context(0) as one, nbk.Context(devices=list(range(ndev))) as multi:
+        assert multi.device_count == ndev
+        a = one.grad_v_dgrad_v_sum(m, q, p, 1e-4)
+        b = multi.grad_v_dgrad_v_sum(m, q, p, 1e-4)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(one.grad_v_sum(m, q, 0.0), multi.grad_v_sum(m, q, 0.0))
+        pa, ta = one.v_sum(m, q, 0.0)
+        pb, tb = multi.v_sum(m, q, 0.0)
+        assert np.array_equal(pa, pb) and abs(ta - tb) <= 1e-13 * abs(ta)
+        sub = multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
+        ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
+        assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
+        ke, pe = multi.energy(m, q, p, 0.0)
+        assert abs(pe - oracle.total_potential_energy(m, q)) <= 1e-12 * abs(pe)

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Single-process multi-GPU context (nbk_create_multi): the metric sweep through the HOST-buffer
+call at N = 131072 on 1..all GPUs of the box, wall-clock per call (H2D + broadcast + sweeps +
+D2H)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import nbh  # noqa: E402
+import nbk  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+m, q, p = nbh.make_plummer(n, 20243)
+ref = None
+g = 1
+while g <= torch.cuda.device_count():
+    with nbk.Context(devices=list(range(g))) as ctx:
+        ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            out = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
+        dt = (time.perf_counter() - t0) / 5
+    if ref is None:
+        ref = out
+    same = np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
+    print(f"{g} GPU(s), one process: {1e3 * dt:.2f} ms per host-buffer call = "
+          f"{n * (n - 1.0) / dt / 1e9:.1f} G interactions/s, identical to 1 GPU: {same}")
+    g *= 2
