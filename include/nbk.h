@@ -58,8 +58,8 @@ int nbk_create(nbk_ctx **ctx, int device);
  * a context on the first device, except that the host-buffer sweeps nbk_grad_v_dgrad_v_sum,
  * nbk_grad_v_sum, nbk_v_sum and nbk_energy shard their TARGETS over all the devices: bodies are
  * uploaded and packed once, broadcast to the other devices over NVLink, every device sweeps its
- * slice over all sources, and the slices are read back into place.  Results are independent of
- * ndev (each target's sum is formed by one device in the same order). */
+ * slice over all sources, and the slices are read back into place.  Results depend on ndev
+ * only at rounding level (where a target's source range is cut into runs). */
 int nbk_create_multi(nbk_ctx **ctx, int ndev, const int *devices);
 int nbk_device_count(const nbk_ctx *ctx);
 void nbk_destroy(nbk_ctx *ctx);

@@ -15,6 +15,10 @@ type range = int * int * int * int
 
 external create : int -> ctx = "nbk_ml_create"
 
+(* [create_multi ndev]: one context driving GPUs 0..ndev-1 from this single process; the
+   host-buffer sweeps shard their targets over them (nbk_create_multi). *)
+external create_multi : int -> ctx = "nbk_ml_create_multi"
+
 external grad_v_sum : ctx -> vec -> vec -> float -> range -> vec -> unit
   = "nbk_ml_grad_v_sum_bc" "nbk_ml_grad_v_sum"
 

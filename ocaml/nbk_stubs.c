@@ -50,6 +50,17 @@ CAMLprim value nbk_ml_create(value device) {
   CAMLreturn(v);
 }
 
+CAMLprim value nbk_ml_create_multi(value ndev) {
+  CAMLparam1(ndev);
+  CAMLlocal1(v);
+  nbk_ctx *ctx = NULL;
+  int rc = nbk_create_multi(&ctx, Int_val(ndev), NULL);
+  if (rc != NBK_OK) caml_failwith(nbk_last_error(NULL));
+  v = caml_alloc_custom(&ctx_ops, sizeof(nbk_ctx *), 0, 1);
+  Ctx_val(v) = ctx;
+  CAMLreturn(v);
+}
+
 /* external grad_v_sum : ctx -> m -> q -> eps2:float -> range(t0,t1,s0,s1) -> gsum -> unit */
 CAMLprim value nbk_ml_grad_v_sum(value ctx, value m, value q, value eps2, value rng,
                                  value gsum) {

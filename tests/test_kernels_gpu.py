@@ -341,9 +341,10 @@ def test_binaries_scan_and_list_bit_exact(ctx, oracle, n, thr):
 
 
 def test_single_process_multi_gpu_context(oracle):
-    """nbk_create_multi: one process, several GPUs, targets sharded by the library.  Results must
-    be IDENTICAL to the single-GPU context (each target is summed by one device in the same
-    order).  Needs >= 2 GPUs; on a 1-GPU box the 1-device multi context is exercised."""
+    """nbk_create_multi: one process, several GPUs, targets sharded by the library.  Results
+    agree with the single-GPU context to rounding (a target's sources are cut into runs at
+    different places when the grid serves fewer targets).  Needs >= 2 GPUs; on a 1-GPU box the
+    1-device multi context is exercised."""
     import torch
     import nbk
     ndev = min(torch.cuda.device_count(), 4)
@@ -353,11 +354,13 @@ def test_single_process_multi_gpu_context(oracle):
         assert multi.device_count == ndev
         a = one.grad_v_dgrad_v_sum(m, q, p, 1e-4)
         b = multi.grad_v_dgrad_v_sum(m, q, p, 1e-4)
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-        assert np.array_equal(one.grad_v_sum(m, q, 0.0), multi.grad_v_sum(m, q, 0.0))
+        assert rel_err(b[0], a[0]) <= 1e-13 and rel_err(b[1], a[1]) <= 1e-13
+        assert rel_err(multi.grad_v_sum(m, q, 0.0), one.grad_v_sum(m, q, 0.0)) <= 1e-13
         pa, ta = one.v_sum(m, q, 0.0)
         pb, tb = multi.v_sum(m, q, 0.0)
-        assert np.array_equal(pa, pb) and abs(ta - tb) <= 1e-13 * abs(ta)
+        assert np.allclose(pa, pb, rtol=1e-13, atol=0) and abs(ta - tb) <= 1e-13 * abs(ta)
+        g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 1e-4)
+        assert rel_err(b[0], g_ref) <= TOL and rel_err(b[1], dg_ref) <= TOL
         sub = multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
         ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
         assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
