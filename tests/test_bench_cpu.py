@@ -1,0 +1,47 @@
+"""CPU: the reference arm of bench.py (`--impl reference`, the oracle port timed on host cores)
+prints exactly one JSON line with the contract's keys; the GPU arm refuses to run without a GPU
+instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT,
+                          capture_output=True, text=True, timeout=300, env=e)
+
+
+def test_reference_arm_json_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "2048",
+             "--n", "8192")
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "interactions/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+             env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_gpu_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = _run("--steps", "1")
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
