@@ -44,6 +44,8 @@ struct nbk_ctx {
   int hermite_n = 0;
   int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size (NBK_HERMITE_THREADS)
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
+  double *h_hres = nullptr, *d_hres = nullptr;  // mapped pinned result slot of the per-step kernel
+  double hseq = 0.0;
   // pinned host staging for scalar read-back
   double *h_scalar = nullptr;
   // single-process multi-GPU (nbk_create_multi): further contexts, one per extra device
@@ -568,6 +570,7 @@ void nbk_destroy(nbk_ctx *c) {
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
+  if (c->h_hres) cudaFreeHost(c->h_hres);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1207,17 +1210,31 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
   memset(&u, 0, sizeof u);
   if (upd >= 0) memcpy(u.s, upd_state, sizeof u.s);
   const int nblk = (n + 255) / 256;
+  if (!ctx->h_hres) {
+    CK(cudaHostAlloc((void **)&ctx->h_hres, 64, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&ctx->d_hres, ctx->h_hres, 0));
+    memset(ctx->h_hres, 0, 64);
+  }
+  const double seq = (ctx->hseq += 1.0);
   hermite_body_kernel<<<nblk, 256, 0, ctx->stream>>>(
       (double *)ctx->d_hstate.p, n, i, nt, eps2, upd, u, (double *)ctx->d_hpartial.p,
-      (unsigned int *)ctx->d_hticket.p, (double *)ctx->d_hout.p);
+      (unsigned int *)ctx->d_hticket.p, ctx->d_hres, seq);
   CK(cudaGetLastError());
   ctx->launches++;
-  CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_hout.p, 6 * sizeof(double), cudaMemcpyDeviceToHost,
-                     ctx->stream));
-  TRY(sync(ctx));
+  // spin on the sequence number the kernel writes last; fall back to the stream on errors
+  volatile double *flag = ctx->h_hres + 7;
+  for (unsigned long spins = 0; *flag != seq; ++spins) {
+    if ((spins & 0xfffff) == 0xfffff) {
+      cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady)
+        return fail(ctx, NBK_ERR_CUDA, "hermite_body_kernel failed: %s", cudaGetErrorString(q));
+      if (q == cudaSuccess && *flag != seq)
+        return fail(ctx, NBK_ERR_CUDA, "hermite_body_kernel finished without publishing");
+    }
+  }
   for (int k = 0; k < 3; ++k) {
-    gsum[k] = ctx->h_scalar[k];
-    dgsum[k] = ctx->h_scalar[3 + k];
+    gsum[k] = ctx->h_hres[k];
+    dgsum[k] = ctx->h_hres[3 + k];
   }
   return NBK_OK;
 }

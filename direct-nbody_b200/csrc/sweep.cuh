@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ 
                                                            int upd, const HermiteUpd u,
                                                            double *__restrict__ partial,
                                                            unsigned int *__restrict__ ticket,
-                                                           double *__restrict__ out) {
+                                                           double *out, double seq) {
   __shared__ double red[8][6];
   __shared__ bool last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1001,8 +1001,18 @@ __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ 
     for (unsigned b = 0; b < gridDim.x; ++b) a += __ldcg(&partial[(size_t)b * 6 + tid]);
     // gsum = -m_i acc (gradient convention of Base.grad_v_dgrad_v)
     const double mi = state[(size_t)it * HB + 1];
+    // `out` is host memory mapped into the device (zero-copy): the host spins on out[7] == seq
+    // instead of paying a D2H copy and a stream synchronisation per step.
     out[tid] = -mi * a;
+    __threadfence_system();
     if (tid == 0) *ticket = 0u;
+  }
+  if (last) {
+    __syncwarp();
+    if (tid == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile double *>(out + 7) = seq;
+    }
   }
 }
 
