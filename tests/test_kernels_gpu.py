@@ -366,3 +366,39 @@ def test_single_process_multi_gpu_context(oracle):
         assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
         ke, pe = multi.energy(m, q, p, 0.0)
         assert abs(pe - oracle.total_potential_energy(m, q)) <= 1e-12 * abs(pe)
+
+
+def test_fuzz_rectangles_all_shapes(ctx, oracle):
+    """Random sizes, target/source rectangles, softenings and tile shapes: exercises the stream-K
+    split points and the fix-up's slot rule at many (n_it, n_jt, units_per_cta) combinations."""
+    rng = np.random.default_rng(20240)
+    try:
+        for case in range(40):
+            n = int(rng.integers(2, 3500))
+            m, q, p = oracle.make_plummer(n, 1000 + case)
+            m = m * rng.uniform(0.5, 2.0, n)            # unequal masses
+            p = p * (m * n)[:, None]
+            t0 = int(rng.integers(0, n))
+            t1 = int(rng.integers(t0 + 1, n + 1))
+            s0 = int(rng.integers(0, n))
+            s1 = int(rng.integers(s0 + 1, n + 1))
+            eps2 = float(rng.choice([0.0, 1e-6, 1e-2]))
+            ctx.tune(int(rng.integers(0, 4)))
+            g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, eps2, targets=(t0, t1), sources=(s0, s1))
+            g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps2, targets=(t0, t1), sources=(s0, s1))
+            sg = np.linalg.norm(g_ref, axis=1).max() + 1e-300
+            sdg = np.linalg.norm(dg_ref, axis=1).max() + 1e-300
+            assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * sg, (case, n, t0, t1, s0, s1)
+            assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * sdg, (case, n, t0, t1, s0, s1)
+            phi_ref = oracle.v_sum(m, q, eps2, targets=(t0, t1), sources=(s0, s1))
+            phi, tot = ctx.v_sum(m, q, eps2, targets=(t0, t1), sources=(s0, s1))
+            assert np.allclose(phi, phi_ref, rtol=TOL, atol=1e-300), (case, n, t0, t1, s0, s1)
+            assert abs(tot - phi_ref.sum()) <= 1e-12 * np.abs(phi_ref).sum() + 1e-300
+            v = p / m[:, None]
+            dv_ref, tm_ref = oracle.kick_sum(m, q, v, 1e-2, 1e-3, targets=(t0, t1), sources=(s0, s1))
+            dv, tm = ctx.kick_sum(m, q, v, 1e-2, 1e-3, targets=(t0, t1), sources=(s0, s1))
+            sdv = np.linalg.norm(dv_ref, axis=1).max() + 1e-300
+            assert np.max(np.linalg.norm(dv - dv_ref, axis=1)) <= TOL * sdv, (case, n, t0, t1, s0, s1)
+            assert np.array_equal(tm, tm_ref), (case, n, t0, t1, s0, s1)
+    finally:
+        ctx.tune(0)
