@@ -42,7 +42,7 @@ struct nbk_ctx {
   DevBuf d_res_m, d_res_packed;
   // resident Hermite state
   int hermite_n = 0;
-  int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size (NBK_HERMITE_THREADS)
+  int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size, -8 the cluster kernel (NBK_HERMITE_THREADS)
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
   double *h_hres = nullptr, *d_hres = nullptr;  // mapped pinned result slot of the per-step kernel
   double hseq = 0.0;
@@ -1239,18 +1239,39 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
   return NBK_OK;
 }
 
-int nbk_hermite_resident_max(void) { return HRES_MAX_N; }
+int nbk_hermite_resident_max(void) { return HCL_MAX_N; }
 
 int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, double eps2,
                                  long max_steps, long *nsteps) {
   if (!ctx) return NBK_ERR_ARG;
   const int n = ctx->hermite_n;
   if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state: call nbk_hermite_upload");
-  if (n > HRES_MAX_N)
-    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n, HRES_MAX_N);
+  if (n > HCL_MAX_N)
+    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n, HCL_MAX_N);
   CK(cudaSetDevice(ctx->device));
-  const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
   TRY(reserve(ctx, ctx->d_scalar, 64));
+  if (n > HRES_MAX_N || ctx->hermite_threads == -8) {
+    // thread-block cluster of 8 CTAs, state split over their shared memories (DSMEM exchange)
+    const int per = (n + HCL_CTAS - 1) / HCL_CTAS;
+    const size_t csmem = (size_t)per * HRES_STRIDE * sizeof(double);
+    CK(cudaFuncSetAttribute(hermite_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)csmem));
+    hermite_cluster_kernel<<<HCL_CTAS, HCL_THREADS, csmem, ctx->stream>>>(
+        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+        (long long *)ctx->d_scalar.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    TRY(sync(ctx));
+    long long csteps;
+    memcpy(&csteps, ctx->h_scalar, sizeof csteps);
+    if (nsteps) *nsteps = (long)csteps;
+    if (csteps >= (long long)max_steps && max_steps > 0)
+      return fail(ctx, NBK_ERR_STATE, "Hermite step cap (%ld) reached before stop_time", max_steps);
+    return NBK_OK;
+  }
+  const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
   // Threads of the single stepping CTA: the per-step cost is dominated by barriers and the two
   // block reductions, so fewer, busier warps win (measured on B200: profiles/).
   int nth = ctx->hermite_threads ? ctx->hermite_threads : (n <= 128 ? 128 : 256);

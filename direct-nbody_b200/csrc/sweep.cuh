@@ -15,6 +15,7 @@
 //
 // No tensor cores: a pair interaction is not a contraction.  The bound is the FP64 pipe.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1201,6 +1202,219 @@ __global__ void __launch_bounds__(HRES_THREADS, 1)
 #pragma unroll
     for (int c = 0; c < 16; ++c) state[(size_t)j * HB + c] = rec[j * HRES_STRIDE + c];
   if (tid == 0) *nsteps_out = steps;
+}
+
+// ---- the same stepping loop on a thread-block CLUSTER (1536 < N <= 12288) ----------------------
+// Eight CTAs (one cluster, eight SMs) each keep an eighth of the Hermite.b array in their own
+// shared memory and talk through distributed shared memory (DSMEM) - two cluster barriers per
+// step instead of a kernel launch:
+//   post:  every CTA finds its earliest unfinished body and stores that body's key and whole
+//          record into slot [rank] of the candidate table of ALL eight CTAs          (DSMEM)
+//   sync A
+//   pick:  every CTA picks the same winner from its copy of the table (so it already holds the
+//          stepped body's record), predicts its own bodies, sums its part of the 1 x (N-1)
+//          acc+jerk and stores the six partial sums into the OWNER CTA's table      (DSMEM)
+//   sync B
+//   owner: adds the eight partials in rank order, corrector + new time step, updates its record.
+constexpr int HCL_CTAS = 8;
+constexpr int HCL_THREADS = 256;
+constexpr int HCL_PER_CTA = 1536;
+constexpr int HCL_MAX_N = HCL_CTAS * HCL_PER_CTA;
+constexpr int HCL_CAND = 20;  // nt, stamp, index, then the 16-double record, pad
+
+__global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 1)
+    hermite_cluster_kernel(double *__restrict__ state, int n, double stop_time, double eta,
+                           double eps2, long long max_steps, long long *__restrict__ nsteps_out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slot 16 = done flag
+  __shared__ double cand[HCL_CTAS][HCL_CAND];
+  __shared__ double part[HCL_CTAS][6];
+  __shared__ double red[HCL_THREADS / 32][6];
+  __shared__ double key_nt[HCL_THREADS / 32], key_st[HCL_THREADS / 32];
+  __shared__ int key_idx[HCL_THREADS / 32];
+  constexpr int NW = HCL_THREADS / 32;
+  constexpr int NONE = 0x7fffffff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + HCL_CTAS - 1) / HCL_CTAS;
+  const int j_lo = min(rank * per, n), j_hi = min(j_lo + per, n), nloc = j_hi - j_lo;
+  SweepParams P;
+  P.eps2 = eps2;
+  for (int l = tid; l < nloc; l += HCL_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rec[l * HRES_STRIDE + c] = state[(size_t)(j_lo + l) * HB + c];
+    rec[l * HRES_STRIDE + 16] = 0.0;
+  }
+  __syncthreads();
+  long long steps = 0, stamp = 0;
+  bool finishing = false;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  auto better = [](double ont, double ost, int oidx, double knt, double kst, int kidx) {
+    return oidx != NONE &&
+           (kidx == NONE || (ont < knt) ||
+            (ont == knt && (ost > kst || (ost == kst && oidx < kidx))));
+  };
+  for (;;) {
+    // ---- post: local arg-min (next time asc, stamp desc, global index asc)
+    double knt = INF, kst = -INF;
+    int kidx = NONE;
+    for (int l = tid; l < nloc; l += HCL_THREADS) {
+      const double *r = rec + l * HRES_STRIDE;
+      if (r[16] != 0.0) continue;
+      const double nt = r[0] + r[14];
+      if (better(nt, r[15], j_lo + l, knt, kst, kidx)) {
+        knt = nt;
+        kst = r[15];
+        kidx = j_lo + l;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ont = __shfl_down_sync(0xffffffffu, knt, off);
+      const double ost = __shfl_down_sync(0xffffffffu, kst, off);
+      const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
+      if (better(ont, ost, oidx, knt, kst, kidx)) {
+        knt = ont;
+        kst = ost;
+        kidx = oidx;
+      }
+    }
+    if (lane == 0) {
+      key_nt[warp] = knt;
+      key_st[warp] = kst;
+      key_idx[warp] = kidx;
+    }
+    __syncthreads();
+    {  // every thread reduces the NW warp keys (cheap) so all know the CTA's candidate
+      knt = key_nt[0];
+      kst = key_st[0];
+      kidx = key_idx[0];
+      for (int w = 1; w < NW; ++w)
+        if (better(key_nt[w], key_st[w], key_idx[w], knt, kst, kidx)) {
+          knt = key_nt[w];
+          kst = key_st[w];
+          kidx = key_idx[w];
+        }
+    }
+    if (tid < HCL_CTAS * HCL_CAND) {
+      const int dst = tid / HCL_CAND, slot = tid % HCL_CAND;
+      double v = 0.0;
+      if (slot == 0) v = knt;
+      else if (slot == 1) v = kst;
+      else if (slot == 2) v = (kidx == NONE) ? -1.0 : (double)kidx;
+      else if (slot < 19 && kidx != NONE) v = rec[(kidx - j_lo) * HRES_STRIDE + (slot - 3)];
+      double *remote = cluster.map_shared_rank(&cand[0][0], dst);
+      remote[rank * HCL_CAND + slot] = v;
+    }
+    cluster.sync();  // A
+    // ---- pick: the same winner everywhere
+    int it = NONE, owner = 0;
+    {
+      double bnt = INF, bst = -INF;
+      for (int r = 0; r < HCL_CTAS; ++r) {
+        const int idx = cand[r][2] < 0.0 ? NONE : (int)cand[r][2];
+        if (better(cand[r][0], cand[r][1], idx, bnt, bst, it)) {
+          bnt = cand[r][0];
+          bst = cand[r][1];
+          it = idx;
+          owner = r;
+        }
+      }
+      if (it == NONE) break;  // every body finished (uniform over the cluster)
+      if (!finishing) {
+        if (steps >= max_steps) break;
+        if (bnt > stop_time) finishing = true;
+      }
+    }
+    const double *tr = &cand[owner][3];
+    const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    double mt, qt[3], vt[3];
+    hermite_predict_fast(tr, nt, mt, qt, vt);
+    const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = tid; l < nloc; l += HCL_THREADS) {
+      double mj, qj[3], vj[3];
+      hermite_predict_fast(rec + l * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, (j_lo + l) == it, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+    __syncthreads();
+    if (tid < 6) {
+      double a = red[0][tid];
+      for (int w = 1; w < NW; ++w) a += red[w][tid];
+      double *remote = cluster.map_shared_rank(&part[0][0], owner);
+      remote[rank * 6 + tid] = a;
+    }
+    cluster.sync();  // B
+    ++steps;
+    ++stamp;
+    // ---- owner: corrector (hermite.ml:116-123) and new time step (hermite.ml:87-93)
+    if (rank == owner && tid == 0) {
+      double fp[3], dfp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double a = 0.0, d = 0.0;
+        for (int r = 0; r < HCL_CTAS; ++r) {
+          a += part[r][c];
+          d += part[r][3 + c];
+        }
+        fp[c] = mt * a;
+        dfp[c] = mt * d;
+      }
+      double *wr = rec + (it - j_lo) * HRES_STRIDE;
+      const double m = mt;
+      double qn[3], pn[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+        pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                          __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+        qn[c] = __dadd_rn(
+            __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+      }
+      const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+      const double rr = __dsqrt_rn(
+          __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      const double fn = __dsqrt_rn(__dadd_rn(
+          __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+      double hn;
+      if (rr == 0.0) {
+        hn = __dmul_rn(h, 1.189207115002721);
+      } else {
+        const double x =
+            __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+        hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));
+      }
+      wr[0] = nt;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        wr[2 + c] = qn[c];
+        wr[5 + c] = pn[c];
+        wr[8 + c] = fp[c];
+        wr[11 + c] = dfp[c];
+      }
+      wr[14] = hn;
+      wr[15] = (double)stamp;
+      if (finishing) wr[16] = 1.0;
+    }
+    __syncthreads();  // the owner's next arg-min must see the update; uniform in every CTA
+  }
+  cluster.sync();  // nobody leaves while a peer may still write into its shared memory
+  for (int l = tid; l < nloc; l += HCL_THREADS)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) state[(size_t)(j_lo + l) * HB + c] = rec[l * HRES_STRIDE + c];
+  if (rank == 0 && tid == 0) *nsteps_out = steps;
 }
 
 // ---- Analysis.binaries support ------------------------------------------------------------------

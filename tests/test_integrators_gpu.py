@@ -268,3 +268,18 @@ def test_integrator_checkpoints_and_eg_err(ctx, oracle):
     with pytest.raises(nbh.EgErr) as ei:
         nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01)
     assert np.all(ei.value.state.t == 0.0) and len(ei.value.errors) == 1
+
+
+def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
+    """1536 < N <= 12288: the stepping loop runs on an 8-CTA thread-block cluster with the state
+    split over the CTAs' shared memories (DSMEM).  Same steps as the launch-per-step path and
+    the oracle."""
+    n = 2000
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 20246))
+    a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 0.004, 1e-4, mode=2)   # cluster
+    b = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), 0.004, 1e-4, mode=1)   # host scheduler
+    c = oracle.hermite_advance(oracle.HermiteState(m, q, p), 0.004, 1e-4)
+    assert np.all(a.t == 0.004) and np.array_equal(a.id, c.id)
+    assert abs(a.nsteps - c.nsteps) <= 2 and abs(b.nsteps - c.nsteps) <= 2
+    assert rel(a.q, c.q) <= 1e-10 and rel(a.p, c.p) <= 1e-8
+    assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8
