@@ -402,3 +402,45 @@ def test_fuzz_rectangles_all_shapes(ctx, oracle):
             assert np.array_equal(tm, tm_ref), (case, n, t0, t1, s0, s1)
     finally:
         ctx.tune(0)
+
+
+@pytest.mark.parametrize("n,tg,sr", [(1000, (0, 1000), (0, 1000)), (777, (5, 770), (3, 775)),
+                                     (3001, (0, 3001), (0, 3001)), (130, (129, 130), (0, 130))])
+def test_device_api_writes_stay_in_bounds(ctx, oracle, n, tg, sr):
+    """compute-sanitizer is closed on this pool, so out-of-bounds device writes are looked for
+    directly: every output of the device-pointer API sits between sentinel-filled guard bands,
+    for ragged sizes in every tile shape."""
+    import torch
+    dev = torch.device("cuda", 0)
+    m, q, p = oracle.make_plummer(n, 31)
+    s = torch.cuda.current_stream().cuda_stream
+    d_m, d_q, d_p = (torch.from_numpy(a).to(dev) for a in (m, q, p))
+    G = 4096                                   # guard doubles either side
+    SENT = -7.25e77
+    nt = tg[1] - tg[0]
+
+    def guarded(count):
+        t = torch.full((count + 2 * G,), SENT, dtype=torch.float64, device=dev)
+        return t, t[G:G + count]
+
+    pk_full, pk = guarded(8 * n)
+    ctx.dev_pack(n, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False, pk.data_ptr(), s)
+    outs = []
+    try:
+        for shape in (0, 1, 2, 3):
+            ctx.tune(shape)
+            g_full, g = guarded(3 * nt)
+            dg_full, dg = guarded(3 * nt)
+            ph_full, ph = guarded(nt)
+            ctx.dev_grad_v_dgrad_v_sum(pk.data_ptr(), n, 0.0, tg, sr, g.data_ptr(), dg.data_ptr(), False, s)
+            ctx.dev_grad_v_sum(pk.data_ptr(), n, 0.0, tg, sr, g.data_ptr(), True, s)
+            ctx.dev_v_sum(pk.data_ptr(), n, 0.0, tg, sr, ph.data_ptr(), False, s)
+            outs += [g_full, dg_full, ph_full]
+        torch.cuda.synchronize()
+    finally:
+        ctx.tune(0)
+    for t in outs + [pk_full]:
+        assert bool((t[:G] == SENT).all()) and bool((t[-G:] == SENT).all())
+        assert not bool((t[G:-G] == SENT).any())
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
+    assert rel_err(outs[-2][G:-G].reshape(-1, 3).cpu().numpy(), dg_ref) <= TOL
