@@ -40,6 +40,9 @@ struct nbk_ctx {
   // resident bodies
   int resident_n = 0;
   DevBuf d_res_m, d_res_packed;
+  // resident Advancer.A records
+  int adv_n = 0;
+  DevBuf d_adv, d_adv2;
   // resident Hermite state
   int hermite_n = 0;
   int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size, -8 the cluster kernel (NBK_HERMITE_THREADS)
@@ -566,7 +569,8 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
                     &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
-                    &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout};
+                    &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
+                    &c->d_adv,    &c->d_adv2};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -1162,6 +1166,167 @@ int nbk_resident_leapfrog_steps(nbk_ctx *ctx, double dt, int nsteps, double *q, 
     if (v) TRY(download(ctx, v, ctx->d_vel, 3 * (size_t)n));
   }
   return sync(ctx);
+}
+
+// ---- device-resident Advancer.A records ----------------------------------------------------------
+#define NEED_ADV()                                                                          \
+  do {                                                                                      \
+    if (!ctx) return NBK_ERR_ARG;                                                           \
+    if (ctx->adv_n == 0)                                                                    \
+      return fail(ctx, NBK_ERR_STATE, "no resident Advancer.A records: call nbk_adv_upload"); \
+    CK(cudaSetDevice(ctx->device));                                                         \
+  } while (0)
+
+int nbk_adv_upload(nbk_ctx *ctx, int n, const double *records) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n <= 0 || !records) return fail(ctx, NBK_ERR_ARG, "nbk_adv_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)n * AB * sizeof(double);
+  TRY(reserve(ctx, ctx->d_adv, bytes));
+  TRY(reserve(ctx, ctx->d_adv2, bytes));
+  CK(cudaMemcpyAsync(ctx->d_adv.p, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TRY(sync(ctx));
+  ctx->adv_n = n;
+  return NBK_OK;
+}
+
+int nbk_adv_download(nbk_ctx *ctx, int i0, int i1, double *records) {
+  NEED_ADV();
+  if (i0 < 0 || i1 < i0 || i1 > ctx->adv_n || !records)
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_download: bad range [%d,%d)", i0, i1);
+  if (i1 == i0) return NBK_OK;
+  CK(cudaMemcpyAsync(records, (const double *)ctx->d_adv.p + (size_t)i0 * AB,
+                     (size_t)(i1 - i0) * AB * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+
+int nbk_adv_permute(nbk_ctx *ctx, int count, const int *perm) {
+  NEED_ADV();
+  if (count < 0 || count > ctx->adv_n || (count > 0 && !perm))
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_permute: bad arguments");
+  if (count == 0) return NBK_OK;
+  TRY(reserve(ctx, ctx->d_aux_in, (size_t)count * sizeof(int)));
+  CK(cudaMemcpyAsync(ctx->d_aux_in.p, perm, (size_t)count * sizeof(int), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  const size_t elems = (size_t)count * AB;
+  adv_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ctx->stream>>>(
+      (const double *)ctx->d_adv.p, (double *)ctx->d_adv2.p, (const int *)ctx->d_aux_in.p, count);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->d_adv.p, ctx->d_adv2.p, elems * sizeof(double), cudaMemcpyDeviceToDevice,
+                     ctx->stream));
+  ctx->launches++;
+  // perm lives in caller memory: make sure the copy has been consumed before returning
+  return sync(ctx);
+}
+
+int nbk_adv_begin_step(nbk_ctx *ctx, int imin, int imax, double hnew) {
+  NEED_ADV();
+  if (imin < 0 || imax < imin || imax > ctx->adv_n)
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_begin_step: bad range [%d,%d)", imin, imax);
+  if (imax == imin) return NBK_OK;
+  adv_begin_kernel<<<(imax - imin + 127) / 128, 128, 0, ctx->stream>>>((double *)ctx->d_adv.p, imin,
+                                                                        imax, hnew);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_adv_interact(nbk_ctx *ctx, int imin, int imax, double t, double vC, double eps2) {
+  NEED_ADV();
+  const int n = ctx->adv_n;
+  if (imin < 0 || imax < imin || imax > n)
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_interact: bad range [%d,%d)", imin, imax);
+  const int nn = n - imin, na = imax - imin;
+  if (nn == 0) return NBK_OK;
+  TRY(reserve(ctx, ctx->d_packed, (size_t)nn * PK * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[0], 3 * (size_t)nn * sizeof(double)));
+  double *packed = (double *)ctx->d_packed.p, *S = (double *)ctx->d_out[0].p;
+  adv_predict_pack_kernel<<<(nn + 127) / 128, 128, 0, ctx->stream>>>((double *)ctx->d_adv.p, imin, n,
+                                                                      t, packed);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (na == 0) return NBK_OK;
+  SweepParams P = base_params(packed, eps2, 0, na, 0, nn);  // active x everybody
+  P.out[0] = S;
+  TRY(K1::run(ctx, P, ctx->stream, false));
+  if (nn > na) {  // passive x active
+    SweepParams Q = base_params(packed, eps2, na, nn, 0, na);
+    Q.out[0] = S + 3 * (size_t)na;
+    TRY(K1::run(ctx, Q, ctx->stream, false));
+  }
+  adv_accumulate_kernel<<<(nn + 127) / 128, 128, 0, ctx->stream>>>((double *)ctx->d_adv.p, imin, n,
+                                                                    vC, S);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;  // enqueued only: the next read-back synchronises
+}
+
+int nbk_adv_finish(nbk_ctx *ctx, int imin, int imax, double t, double *records) {
+  NEED_ADV();
+  if (imin < 0 || imax < imin || imax > ctx->adv_n)
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_finish: bad range [%d,%d)", imin, imax);
+  if (imax == imin) return NBK_OK;
+  adv_finish_kernel<<<(imax - imin + 127) / 128, 128, 0, ctx->stream>>>((double *)ctx->d_adv.p, imin,
+                                                                         imax, t);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (records) return nbk_adv_download(ctx, imin, imax, records);
+  return NBK_OK;
+}
+
+int nbk_adv_get_t(nbk_ctx *ctx, int i, double *t) {
+  NEED_ADV();
+  if (i < 0 || i >= ctx->adv_n || !t) return fail(ctx, NBK_ERR_ARG, "nbk_adv_get_t: bad index %d", i);
+  CK(cudaMemcpyAsync(ctx->h_scalar, (const double *)ctx->d_adv.p + (size_t)i * AB, sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  TRY(sync(ctx));
+  *t = ctx->h_scalar[0];
+  return NBK_OK;
+}
+
+int nbk_adv_init_first(nbk_ctx *ctx, double eps2) {
+  NEED_ADV();
+  const int n = ctx->adv_n;
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[0], 3 * (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], 3 * (size_t)n * sizeof(double)));
+  adv_pack_full_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const double *)ctx->d_adv.p, n,
+                                                                  (double *)ctx->d_packed.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (n > 1) {
+    SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, 0, n, 0, n);
+    P.out[0] = (double *)ctx->d_out[0].p;
+    P.out[1] = (double *)ctx->d_out[1].p;
+    TRY(run_k2(ctx, P, ctx->stream, false));
+  } else {
+    CK(cudaMemsetAsync(ctx->d_out[0].p, 0, 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_out[1].p, 0, 3 * sizeof(double), ctx->stream));
+  }
+  adv_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+      (double *)ctx->d_adv.p, n, (const double *)ctx->d_out[0].p, (const double *)ctx->d_out[1].p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe) {
+  NEED_ADV();
+  const int n = ctx->adv_n;
+  // Energy.energy needs only (m, q, p): read them back and reuse the host-buffer path
+  std::string buf((size_t)n * AB * sizeof(double), '\0');
+  double *r = reinterpret_cast<double *>(&buf[0]);
+  TRY(nbk_adv_download(ctx, 0, n, r));
+  std::string mb((size_t)n * 7 * sizeof(double), '\0');
+  double *m = reinterpret_cast<double *>(&mb[0]), *q = m + n, *p = q + 3 * (size_t)n;
+  for (int i = 0; i < n; ++i) {
+    m[i] = r[(size_t)i * AB + 1];
+    for (int k = 0; k < 3; ++k) {
+      q[3 * i + k] = r[(size_t)i * AB + 2 + k];
+      p[3 * i + k] = r[(size_t)i * AB + 5 + k];
+    }
+  }
+  return nbk_energy(ctx, n, m, q, p, eps2, ke, pe);
 }
 
 // ---- device-resident Hermite state -------------------------------------------------------------

@@ -1486,6 +1486,161 @@ __global__ void unpack_kernel(const double *__restrict__ packed, int n, double *
   }
 }
 
+// ---- Advancer.A on device-resident records (advancer.ml:143-252) -------------------------------
+// The Advancer.A.body records (advancer.ml:27-45) stay on the device as [n][35] doubles
+//   0 t, 1 m, 2-4 q, 5-7 p, 8 h, 9 hmax, 10 t0, 11-13 dVdq0, 14-16 dVdq1, 17-19 dVdq2,
+//   20-22 p0, 23-25 q0, 26-28 q1, 29-31 q2, 32-34 cs
+// in the reference's array order; the host keeps only the control flow (block recursion, hmax,
+// sort permutations).  Every formula repeats the reference's operation sequence with IEEE
+// intrinsics (no contraction), so this path is bit-identical to the host mirror.
+constexpr int AB = 35;
+
+// predict_q012 + clear_before_step on rows [imin, imax)  (advancer.ml:143-171)
+__global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, double hnew) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= imax) return;
+  double *b = rec + (size_t)i * AB;
+  const double h = b[8], m = b[1];
+  const double hnew2 = __dmul_rn(hnew, hnew), h2 = __dmul_rn(h, h);
+  const double hnew3 = __dmul_rn(hnew2, hnew), h3 = __dmul_rn(h2, h);
+  const double a0 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(h, hnew)), __dmul_rn(__dmul_rn(8.0, h3), m));
+  const double a1 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(__dmul_rn(2.0, h), hnew)),
+                              __dmul_rn(__dmul_rn(16.0, h3), m));
+  const double a2 = __ddiv_rn(
+      __dmul_rn(hnew2, __dadd_rn(__dadd_rn(__dmul_rn(6.0, h2), __dmul_rn(__dmul_rn(3.0, h), hnew)), hnew2)),
+      __dmul_rn(__dmul_rn(8.0, h3), m));
+  const double b0 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(h, hnew)), __dmul_rn(h3, m));
+  const double b1 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(__dmul_rn(2.0, h), hnew)),
+                              __dmul_rn(__dmul_rn(2.0, h3), m));
+  const double b2 = __ddiv_rn(
+      __dmul_rn(hnew2, __dadd_rn(__dadd_rn(__dmul_rn(3.0, h2), __dmul_rn(__dmul_rn(3.0, h), hnew)), hnew2)),
+      __dmul_rn(h3, m));
+  for (int k = 0; k < 3; ++k) {
+    const double p = b[5 + k], q = b[2 + k];
+    const double v0 = b[11 + k], v1 = b[14 + k], v2 = b[17 + k];
+    b[20 + k] = p;
+    b[23 + k] = q;
+    b[26 + k] = __dsub_rn(
+        __dadd_rn(__dsub_rn(__dadd_rn(q, __ddiv_rn(__dmul_rn(hnew, p), __dmul_rn(2.0, m))),
+                            __dmul_rn(a0, v0)),
+                  __dmul_rn(a1, v1)),
+        __dmul_rn(a2, v2));
+    b[29 + k] = __dsub_rn(
+        __dadd_rn(__dsub_rn(__dadd_rn(q, __ddiv_rn(__dmul_rn(hnew, p), m)), __dmul_rn(b0, v0)),
+                  __dmul_rn(b1, v1)),
+        __dmul_rn(b2, v2));
+  }
+  b[8] = hnew;
+  b[10] = b[0];
+  for (int k = 0; k < 3; ++k) b[11 + k] = b[14 + k] = b[17 + k] = b[32 + k] = 0.0;
+  b[32] = 1.0;
+}
+
+// predict_position for rows [imin, n) to time t (advancer.ml:173-195), then pack {q, m} for the
+// grad_v sweeps, re-indexed from imin.
+__global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int n, double t,
+                                        double *__restrict__ packed) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = rec + (size_t)i * AB;
+  if (b[0] != t) {
+    const double dt = __dsub_rn(t, b[10]), h = b[8];
+    const double h2 = __dmul_rn(h, h);
+    const double c0 = __ddiv_rn(
+        __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(2.0, dt), dt), __dmul_rn(__dmul_rn(3.0, dt), h)), h2), h2);
+    const double c1 = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, dt), __dsub_rn(h, dt)), h2);
+    const double c2 = __ddiv_rn(__dmul_rn(dt, __dsub_rn(__dmul_rn(2.0, dt), h)), h2);
+    b[32] = c0;
+    b[33] = c1;
+    b[34] = c2;
+    for (int k = 0; k < 3; ++k)
+      b[2 + k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, b[23 + k]), __dmul_rn(c1, b[26 + k])),
+                           __dmul_rn(c2, b[29 + k]));
+    b[0] = t;
+  }
+  double2 *o = reinterpret_cast<double2 *>(packed + (size_t)(i - imin) * PK);
+  o[0] = make_double2(b[2], b[3]);
+  o[1] = make_double2(b[4], b[1]);
+  o[2] = make_double2(0.0, 0.0);
+  o[3] = make_double2(0.0, 0.0);
+}
+
+// dVdqK_x += (vC cs_x[K]) S_x for rows [imin, n)  (advancer.ml:216-234 in per-target form)
+__global__ void adv_accumulate_kernel(double *__restrict__ rec, int imin, int n, double vC,
+                                      const double *__restrict__ S) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = rec + (size_t)i * AB;
+  const double c0 = __dmul_rn(vC, b[32]), c1 = __dmul_rn(vC, b[33]), c2 = __dmul_rn(vC, b[34]);
+  for (int k = 0; k < 3; ++k) {
+    const double s = S[3 * (size_t)(i - imin) + k];
+    b[11 + k] = __dadd_rn(b[11 + k], __dmul_rn(c0, s));
+    b[14 + k] = __dadd_rn(b[14 + k], __dmul_rn(c1, s));
+    b[17 + k] = __dadd_rn(b[17 + k], __dmul_rn(c2, s));
+  }
+}
+
+// finish_body on rows [imin, imax)  (advancer.ml:238-252); h_adaptive stays on the host (libm pow)
+__global__ void adv_finish_kernel(double *__restrict__ rec, int imin, int imax, double t) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= imax) return;
+  double *b = rec + (size_t)i * AB;
+  const double cp = __ddiv_rn(b[8], b[1]);
+  const double cV0 = cp, cV1 = __dmul_rn(0.5, cp);
+  for (int k = 0; k < 3; ++k) {
+    const double v0 = b[11 + k], v1 = b[14 + k], v2 = b[17 + k], pi = b[20 + k];
+    b[2 + k] = __dsub_rn(__dsub_rn(__dadd_rn(b[23 + k], __dmul_rn(cp, pi)), __dmul_rn(cV0, v0)),
+                         __dmul_rn(cV1, v1));
+    b[5 + k] = __dsub_rn(__dsub_rn(__dsub_rn(pi, v0), v1), v2);
+  }
+  b[0] = t;
+}
+
+// initialize_before_first_step (advancer.ml:357-393): clear, h := 1, then from the all-pairs
+// acc+jerk sums g, dg: dVdq0 = c0 (g - h dg), dVdq1 = c1 (g - h/2 dg), dVdq2 = c2 g.
+__global__ void adv_init_kernel(double *__restrict__ rec, int n, const double *__restrict__ g,
+                                const double *__restrict__ dg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *b = rec + (size_t)i * AB;
+  const double h = 1.0;
+  const double c0 = __ddiv_rn(h, 6.0), c1 = __ddiv_rn(__dmul_rn(2.0, h), 3.0);
+  const double c2 = c0;
+  b[8] = h;
+  b[32] = 1.0;
+  b[33] = b[34] = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    const double gv = g[3 * (size_t)i + k], dgv = dg[3 * (size_t)i + k];
+    b[11 + k] = __dmul_rn(c0, __dsub_rn(gv, __dmul_rn(h, dgv)));
+    b[14 + k] = __dmul_rn(c1, __dsub_rn(gv, __dmul_rn(__dmul_rn(0.5, h), dgv)));
+    b[17 + k] = __dmul_rn(c2, gv);
+  }
+}
+
+// pack {q, m, p/m} of every record (for the all-pairs sweep of initialize_before_first_step
+// and for Energy.energy on the resident state)
+__global__ void adv_pack_full_kernel(const double *__restrict__ rec, int n,
+                                     double *__restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *b = rec + (size_t)i * AB;
+  const double m = b[1];
+  double2 *o = reinterpret_cast<double2 *>(packed + (size_t)i * PK);
+  o[0] = make_double2(b[2], b[3]);
+  o[1] = make_double2(b[4], m);
+  o[2] = make_double2(__ddiv_rn(b[5], m), __ddiv_rn(b[6], m));
+  o[3] = make_double2(__ddiv_rn(b[7], m), 0.0);
+}
+
+// rows [0, count) := old rows perm[0..count)  (sort_range, advancer.ml:290-297)
+__global__ void adv_gather_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                  const int *__restrict__ perm, int count) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)count * AB) return;
+  const int row = (int)(e / AB), c = (int)(e % AB);
+  dst[e] = src[(size_t)perm[row] * AB + c];
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

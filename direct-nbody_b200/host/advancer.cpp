@@ -292,13 +292,157 @@ struct Adv {
   }
 };
 
+// The same control flow with the body records resident on the device (nbk_adv_*): per
+// interact_bodies nothing crosses PCIe; per block step the host reads one time stamp and the
+// finished rows of the active block (for h_adaptive, whose libm pow must stay on the host to
+// keep the reference's time-step sequence), and sends a permutation when the sort moves rows.
+// Bit-identical to the host-buffer path above (same kernels on the same packed rows, same
+// operation sequences), which tests/ assert.
+struct AdvResident {
+  nbk_ctx *ctx;
+  double eps2;
+  long n_interact = 0, n_pairs = 0;
+  int n = 0;
+  std::vector<double> hmax, recs;
+  std::vector<int> id, perm;
+
+  static void from_record(const double *s, ABody &b) {
+    b.t = s[0];
+    b.m = s[1];
+    b.h = s[8];
+    b.hmax = s[9];
+    b.t0 = s[10];
+    for (int k = 0; k < 3; ++k) {
+      b.q[k] = s[2 + k];
+      b.p[k] = s[5 + k];
+      b.dVdq0[k] = s[11 + k];
+      b.dVdq1[k] = s[14 + k];
+      b.dVdq2[k] = s[17 + k];
+      b.p0[k] = s[20 + k];
+      b.q0[k] = s[23 + k];
+      b.q1[k] = s[26 + k];
+      b.q2[k] = s[29 + k];
+      b.cs[k] = s[32 + k];
+    }
+  }
+
+  int sort_prefix(int imax) {  // sort_range bs hmax_lt 0 imax (stable), rows follow on the device
+    perm.resize(imax);
+    for (int i = 0; i < imax; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return hmax[a] < hmax[b]; });
+    bool identity = true;
+    for (int i = 0; i < imax; ++i) identity = identity && perm[i] == i;
+    if (identity) return 0;
+    NBH_TRY(ck(ctx, nbk_adv_permute(ctx, imax, perm.data())));
+    std::vector<double> h2(imax);
+    std::vector<int> i2(imax);
+    for (int i = 0; i < imax; ++i) {
+      h2[i] = hmax[perm[i]];
+      i2[i] = id[perm[i]];
+    }
+    std::copy(h2.begin(), h2.end(), hmax.begin());
+    std::copy(i2.begin(), i2.end(), id.begin());
+    return 0;
+  }
+
+  int interact(int imin, int imax, double t, double vC) {
+    NBH_TRY(ck(ctx, nbk_adv_interact(ctx, imin, imax, t, vC, eps2)));
+    const long na = imax - imin, nn = n - imin;
+    n_interact += 1;
+    n_pairs += na * (nn - 1) - na * (na - 1) / 2;
+    return 0;
+  }
+
+  int advance_range(int imax, double dt, double sf) {  // advancer.ml:316-350
+    if (hmax[imax - 1] < dt) {
+      NBH_TRY(advance_range(imax, dt / 2.0, sf));
+      NBH_TRY(advance_range(imax, dt / 2.0, sf));
+      return 0;
+    }
+    int imin = imax - 1;
+    while (imin >= 0 && dt < hmax[imin]) --imin;
+    imin = imin + 1;
+    NBH_TRY(ck(ctx, nbk_adv_begin_step(ctx, imin, imax, dt)));
+    double t0 = 0.0;
+    NBH_TRY(ck(ctx, nbk_adv_get_t(ctx, imin, &t0)));  // let t0 = bs.(imin).t
+    NBH_TRY(interact(imin, imax, t0, dt / 6.0));
+    if (imin > 0) NBH_TRY(advance_range(imin, dt / 2.0, sf));
+    NBH_TRY(interact(imin, imax, t0 + 0.5 * dt, 2.0 * dt / 3.0));
+    if (imin > 0) NBH_TRY(advance_range(imin, dt / 2.0, sf));
+    NBH_TRY(interact(imin, imax, t0 + dt, dt / 6.0));
+    const int na = imax - imin;
+    recs.resize((size_t)na * NBH_ADV_STRIDE);
+    NBH_TRY(ck(ctx, nbk_adv_finish(ctx, imin, imax, t0 + dt, recs.data())));
+    for (int k = 0; k < na; ++k) {
+      ABody b;
+      from_record(recs.data() + (size_t)k * NBH_ADV_STRIDE, b);
+      Adv::h_adaptive(sf, b);
+      hmax[imin + k] = b.hmax;
+    }
+    return sort_prefix(imax);
+  }
+
+  int run(int n_, int *id_io, double *state, double dt, double sf) {
+    n = n_;
+    id.assign(id_io, id_io + n);
+    hmax.resize(n);
+    bool any_first = false;
+    for (int i = 0; i < n; ++i) {
+      const double *s = state + (size_t)i * NBH_ADV_STRIDE;
+      hmax[i] = s[9];
+      any_first = any_first || (std::fpclassify(s[8]) != FP_NORMAL);
+    }
+    NBH_TRY(ck(ctx, nbk_adv_upload(ctx, n, state)));
+    if (any_first) {  // initialize_before_first_step (advancer.ml:357-406)
+      NBH_TRY(ck(ctx, nbk_adv_init_first(ctx, eps2)));
+      recs.resize((size_t)n * NBH_ADV_STRIDE);
+      NBH_TRY(ck(ctx, nbk_adv_download(ctx, 0, n, recs.data())));
+      for (int i = 0; i < n; ++i) {
+        ABody b;
+        from_record(recs.data() + (size_t)i * NBH_ADV_STRIDE, b);
+        double fdot[3];
+        for (int j = 0; j < 3; ++j) fdot[j] = b.dVdq0[j] - b.dVdq1[j] + 3.0 * b.dVdq2[j];
+        Adv::assign_timestep(b, 1e-2 * std::pow(sf, 0.33333) * b.h * norm(b.dVdq2) / norm(fdot));
+        hmax[i] = b.hmax;
+      }
+    }
+    NBH_TRY(sort_prefix(n));  // Array.fast_sort hmax_lt bs
+    NBH_TRY(advance_range(n, dt, sf));
+    recs.resize((size_t)n * NBH_ADV_STRIDE);
+    NBH_TRY(ck(ctx, nbk_adv_download(ctx, 0, n, recs.data())));
+    for (int i = 0; i < n; ++i) {
+      double *s = state + (size_t)i * NBH_ADV_STRIDE;
+      std::copy(recs.begin() + (size_t)i * NBH_ADV_STRIDE,
+                recs.begin() + (size_t)(i + 1) * NBH_ADV_STRIDE, s);
+      s[9] = hmax[i];
+      id_io[i] = id[i];
+    }
+    return 0;
+  }
+};
+
+int g_advancer_resident = 1;  // 0: host-buffer path (nbk_interact_sum per interact_bodies)
+
 }  // namespace
 
 extern "C" {
 
+void nbh_set_advancer_resident(int on) { g_advancer_resident = on; }
+
 int nbh_advancer_advance(nbk_ctx *ctx, int n, int *id, double *state, double dt, double sf,
                          double eps2, nbh_extpot_fn extpot, void *extpot_arg, long *stats) {
   if (n <= 0) return fail(NBK_ERR_ARG, "Advancer.A.advance: empty body array");
+  if (g_advancer_resident && !extpot) {  // an external field is a host callback: host path
+    AdvResident R;
+    R.ctx = ctx;
+    R.eps2 = eps2;
+    NBH_TRY(R.run(n, id, state, dt, sf));
+    if (stats) {
+      stats[0] = R.n_interact;
+      stats[1] = R.n_pairs;
+    }
+    return 0;
+  }
   Adv A;
   A.ctx = ctx;
   A.eps2 = eps2;

@@ -254,9 +254,11 @@ class AdvancerState:
         return o
 
 
-def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None):
+def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None, resident=True):
     """Advancer.A.advance ?extpot bs dt sf; extpot is None or "plummer_test"
-    (the field of test/advance_test.ml:39-46)."""
+    (the field of test/advance_test.ml:39-46).  resident: keep the records on the device for
+    the whole advance (default) or ship the bodies per interact_bodies."""
+    load_library().nbh_set_advancer_resident(int(resident))
     o = s.copy()
     stats = (C.c_long * 2)(0, 0)
     fn = None

@@ -58,6 +58,15 @@ SYMBOLS = {
     "nbk_resident_v_sum": (_i, [_vp, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_kick_sum": (_i, [_vp, _d, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_resident_leapfrog_steps": (_i, [_vp, _d, _i, _pd, _pd]),
+    "nbk_adv_upload": (_i, [_vp, _i, _pd]),
+    "nbk_adv_download": (_i, [_vp, _i, _i, _pd]),
+    "nbk_adv_permute": (_i, [_vp, _i, C.POINTER(_i)]),
+    "nbk_adv_begin_step": (_i, [_vp, _i, _i, _d]),
+    "nbk_adv_interact": (_i, [_vp, _i, _i, _d, _d, _d]),
+    "nbk_adv_finish": (_i, [_vp, _i, _i, _d, _pd]),
+    "nbk_adv_get_t": (_i, [_vp, _i, _pd]),
+    "nbk_adv_init_first": (_i, [_vp, _d]),
+    "nbk_adv_energy": (_i, [_vp, _d, _pd, _pd]),
     "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd]),
     "nbk_hermite_resident_max": (_i, []),
     "nbk_hermite_advance_resident": (_i, [_vp, _d, _d, _d, C.c_long, C.POINTER(C.c_long)]),

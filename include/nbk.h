@@ -196,6 +196,35 @@ int nbk_resident_kick_sum(nbk_ctx *ctx, double eta, double dt, int t0, int t1, i
  * leapfrog.ml:129-137).  q, v (may be NULL) receive the final positions and velocities. */
 int nbk_resident_leapfrog_steps(nbk_ctx *ctx, double dt, int nsteps, double *q, double *v);
 
+/* ---- device-resident Advancer.A records (advancer.ml:143-428) -------------------------------- */
+/* The Advancer.A.body array (advancer.ml:27-45) lives on the device as records[n][35] =
+ * {t, m, q[3], p[3], h, hmax, t0, dVdq0[3], dVdq1[3], dVdq2[3], p0[3], q0[3], q1[3], q2[3],
+ * cs[3]} in the reference's array order; the host keeps the control flow of advance_range
+ * (advancer.ml:316-350: block recursion, hmax, sorts) and calls one function per step phase.
+ * Every per-body formula repeats the reference's operation sequence, so results are
+ * bit-identical to doing the same phases on the host around nbk_interact_sum.  Calls are
+ * enqueued; only functions that return data synchronise. */
+int nbk_adv_upload(nbk_ctx *ctx, int n, const double *records);
+/* rows [i0, i1) -> records[(i1-i0)][35] */
+int nbk_adv_download(nbk_ctx *ctx, int i0, int i1, double *records);
+/* sort_range (advancer.ml:290-297): new rows [0,count) := old rows perm[0..count) */
+int nbk_adv_permute(nbk_ctx *ctx, int count, const int *perm);
+/* predict_q012 bs.(i) hnew; clear_before_step bs.(i)  for i in [imin, imax) (advancer.ml:329-332) */
+int nbk_adv_begin_step(nbk_ctx *ctx, int imin, int imax, double hnew);
+/* interact_bodies bs imin imax t vC (advancer.ml:207-236): predict_position of rows [imin,n),
+ * the two rectangular grad_v sweeps, dVdqK += (vC cs.(K)) S - all on the device */
+int nbk_adv_interact(nbk_ctx *ctx, int imin, int imax, double t, double vC, double eps2);
+/* finish_body bs.(i) t for i in [imin, imax) (advancer.ml:238-252); if records != NULL the
+ * finished rows are read back (the host needs q, q2, dVdq2, h, m for h_adaptive, whose libm
+ * pow keeps the time-step sequence identical to the reference's) */
+int nbk_adv_finish(nbk_ctx *ctx, int imin, int imax, double t, double *records);
+int nbk_adv_get_t(nbk_ctx *ctx, int i, double *t);
+/* initialize_before_first_step's all-pairs acc+jerk loop and accumulator set-up
+ * (advancer.ml:357-393) on the device; the host then reads dVdq0-2 to assign the first steps */
+int nbk_adv_init_first(nbk_ctx *ctx, double eps2);
+/* Energy.energy of the resident bodies */
+int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
+
 /* ---- device-resident Hermite state: one body steps at a time (hermite.ml:95-130, 171-178) --- */
 
 /* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n] and

@@ -283,3 +283,25 @@ def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
     assert abs(a.nsteps - c.nsteps) <= 2 and abs(b.nsteps - c.nsteps) <= 2
     assert rel(a.q, c.q) <= 1e-10 and rel(a.p, c.p) <= 1e-8
     assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8
+
+
+@pytest.mark.parametrize("n,span,eps", [(10, 1.0, 0.4), (100, 0.25, 0.04), (1024, 1.0 / 64, 0.01)])
+def test_advancer_device_resident_is_bit_identical_to_host_path(ctx, oracle, n, span, eps):
+    """Advancer.A with the body records resident on the device (nbk_adv_*: predictors,
+    interact_bodies, finish_body and the sort's row moves on the GPU, the block recursion on the
+    host) against the host-buffer path: identical schedule, identical bits; and both beside the
+    oracle."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 5))
+    eps2 = eps * eps
+    a = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=True)
+    b = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=False)
+    c = oracle.advancer_advance(oracle.AdvancerState(m, q, p), span, 1e-4, eps2)
+    assert a.stats == b.stats == c.stats
+    assert np.array_equal(a.id, b.id) and np.array_equal(a.id, c.id)
+    assert np.array_equal(a.state, b.state, equal_nan=True)
+    assert np.all(a.t == span)
+    assert rel(a.q, c.q) <= 1e-9 and rel(a.p, c.p) <= 1e-9
+    # a second advance continues from the carried state (h, hmax, dVdq* all live)
+    a2 = nbh.advancer_advance(ctx, a, span, 1e-4, eps2, resident=True)
+    b2 = nbh.advancer_advance(ctx, b, span, 1e-4, eps2, resident=False)
+    assert np.array_equal(a2.state, b2.state, equal_nan=True) and a2.stats == b2.stats
