@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Times Advancer.A.advance (the integrator bin/nbody.ml and bin/el_mass_segregation.ml run) with
+the records resident on the device against the host-buffer path.
+usage: tools/time_advancer.py N span [eps] [two_mass]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+import numpy as np  # noqa: E402
+import nbh  # noqa: E402
+import nbk  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+span = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0 / 16
+eps = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+two_mass = len(sys.argv) > 4
+with nbk.Context(0) as ctx:
+    m, q, p = nbh.make_plummer(n, 20244)
+    if two_mass:
+        m, q, p = nbh.add_mass_disc(m, q, p, 20244)
+        m, q, p = nbh.adjust_frame(m, q, p)
+    m, q, p = nbh.rescale_to_standard_units(ctx, m, q, p)
+    e0 = sum(nbh.energy(ctx, m, q, p, eps * eps))
+    s0 = nbh.AdvancerState(m, q, p)
+    nbh.advancer_advance(ctx, s0, span / 64, 1e-4, eps * eps)  # warm-up
+    for resident in (True, False):
+        t0 = time.perf_counter()
+        a = nbh.advancer_advance(ctx, s0, span, 1e-4, eps * eps, resident=resident)
+        dt = time.perf_counter() - t0
+        de = abs((sum(nbh.energy(ctx, a.m, a.q, a.p, eps * eps)) - e0) / e0)
+        print(f"N={n} span={span} resident={resident}: {a.stats[0]} interact_bodies calls, "
+              f"{a.stats[1]:.3e} pair interactions in {dt:.3f} s = {1e6 * dt / a.stats[0]:.1f} us/call, "
+              f"dE/E = {de:.3e}")
