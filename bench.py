@@ -177,16 +177,35 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
-    from nbk.sharded import ShardedAccJerk, make_plan
-    plan = make_plan(n, world, rank)
+    from nbk.sharded import PeerShardedAccJerk, ShardedAccJerk, make_plan
+    plan = make_plan(n, world, rank, align=128)
     t0, t1 = plan.t0, plan.t1
     ctx = nbk.Context(local)
     m, q, p = nbh.make_plummer(n, SEED)  # same seeded bodies on every rank
 
-    # ---- device-resident state: this rank's shard of packed (q, v, m) inside the gather buffer
+    # ---- device-resident state: this rank's shard of packed (q, v, m).
+    # exchange "peer" (default for N > 1): the rows stay in a region the other ranks map over
+    # NVLink (CUDA IPC) and the sweep kernel reads remote source tiles itself - no all-gather;
+    # "nccl": in-place all-gather of the packed rows in front of the sweep.
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-    sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))
+    exchange = args.exchange if world > 1 else "none"
+    sh = None
+    if exchange == "peer":
+        try:
+            sh = PeerShardedAccJerk(plan, dev, ctx)
+            peer_ok = 1
+        except Exception as e:  # no IPC/P2P between these devices: every rank must agree
+            print(f"rank {rank}: peer exchange unavailable ({e})", file=sys.stderr)
+            peer_ok = 0
+        flag = torch.tensor([peer_ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not flag.item():
+            if sh is not None:
+                sh.close()
+            sh, exchange = None, "nccl (peer exchange unavailable)"
+    if sh is None:
+        sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))
     sh.load_local(m, q, p)
     g, dg = sh.g, sh.dg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -228,12 +247,23 @@ def run_ours(args):
     # ---- dominant kernel alone (this rank's share), live CUDA events, for the roofline
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
-    src = sh.packed_all
+    if exchange == "peer":
+        barrier()  # every rank's rows are published; the kernel alone needs no flags
+        shards = ctx.make_shards(plan.rank, plan.shard, sh.regions.packed(sh.cur))
+
+        def kernel_only():
+            ctx.dev_grad_v_dgrad_v_sum_peer(shards, n, 0.0, (t0, t1), (0, n), g.data_ptr(),
+                                            dg.data_ptr(), False, sptr)
+    else:
+        src = sh.packed_all
+
+        def kernel_only():
+            ctx.dev_grad_v_dgrad_v_sum(src.data_ptr(), n, 0.0, (t0, t1), (0, n), g.data_ptr(),
+                                       dg.data_ptr(), False, sptr)
     for k in range(args.steps):
         flush.zero_()
         kev[k][0].record(stream)
-        ctx.dev_grad_v_dgrad_v_sum(src.data_ptr(), n, 0.0, (t0, t1), (0, n), g.data_ptr(),
-                                   dg.data_ptr(), False, sptr)
+        kernel_only()
         kev[k][1].record(stream)
     torch.cuda.synchronize()
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
@@ -288,9 +318,13 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Plummer sphere N={n}, Hermite acc+jerk sweep "
                                    "(BASELINE.json configs[2])", "n": n, "eps": 0.0, "seed": SEED,
-                       "sharding": (f"targets/{world}, NCCL all-gather of packed (q,v,m) per step"
-                                    + (", overlapped with the local-source sweep" if args.overlap
-                                       else "")) if world > 1 else "single GPU",
+                       "sharding": (
+                           "single GPU" if world == 1 else
+                           f"targets/{world}, sweep kernel reads remote source tiles from the owning "
+                           "GPU over NVLink (peer memory, CUDA IPC); no all-gather step"
+                           if exchange == "peer" else
+                           f"targets/{world}, NCCL all-gather of packed (q,v,m) per step [{exchange}]"
+                           + (", overlapped with the local-source sweep" if args.overlap else "")),
                        "l2": "flushed between timed iterations (256 MiB write)"},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
@@ -308,7 +342,7 @@ def run_ours(args):
                          "counted_flop_per_interaction": COUNTED_FLOP,
                          "achieved_counted": COUNTED_FLOP * k_inter / (k_ms * 1e-3) / 1e12,
                          "fp64_issue_slots_per_interaction": FP64_SLOTS,
-                         "kernel": "sweep_kernel<OpGradVDGradV>", "kernel_ms": k_ms,
+                         "kernel": "sweep_kernel<OpGradVDGradV" + (", PEER>" if exchange == "peer" else ">"), "kernel_ms": k_ms,
                          "interactions_per_launch": k_inter},
         }
         if cpu_v is not None:
@@ -317,6 +351,8 @@ def run_ours(args):
                 "sample": f"symmetric i<j acc+jerk sweep over the first {args.cpu_sample} bodies of "
                           f"the same Plummer workload ({cpu_dt:.2f} s wall, OpenMP, all host threads)"}
         print_line(line)
+    if hasattr(sh, "close"):
+        sh.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -331,6 +367,8 @@ def main():
     ap.add_argument("--n", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=65536,
                     help="bodies of the workload the CPU arm sweeps per step (~20 core-seconds)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how a rank gets the other ranks' bodies (see run_ours)")
     ap.add_argument("--overlap", type=int, default=0,
                     help="1: sweep local sources while the all-gather is in flight")
     args = ap.parse_args()

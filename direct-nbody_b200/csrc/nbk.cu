@@ -105,13 +105,13 @@ int check_ranges(nbk_ctx *ctx, int n, int t0, int t1, int s0, int s1) {
 }
 
 // ---- sweep launcher --------------------------------------------------------------------------
-template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
+template <class Op, int NT, int IPT, int MINB, int UNROLL, bool PEER = false> struct Launcher {
   static int occupancy(nbk_ctx *ctx, int *occ) {
     // the shared-memory attribute is per device: cache per device ordinal
     static int cached[64] = {0};
     int &slot = cached[ctx->device & 63];
     if (slot <= 0) {
-      auto kern = sweep_kernel<Op, NT, IPT, MINB, UNROLL>;
+      auto kern = sweep_kernel<Op, NT, IPT, MINB, UNROLL, PEER>;
       constexpr size_t smem = sweep_smem_bytes(naux_of<Op>::value);
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int o = 0;
@@ -141,7 +141,7 @@ template <class Op, int NT, int IPT, int MINB, int UNROLL> struct Launcher {
     TRY(reserve(ctx, ctx->d_partial, (size_t)2 * G * Op::NACC * TI * sizeof(double)));
     P.partial = (double *)ctx->d_partial.p;
     if (time_it) CK(cudaEventRecord(ctx->ev0, st));
-    sweep_kernel<Op, NT, IPT, MINB, UNROLL>
+    sweep_kernel<Op, NT, IPT, MINB, UNROLL, PEER>
         <<<(unsigned)G, NT, sweep_smem_bytes(naux_of<Op>::value), st>>>(P);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -221,15 +221,26 @@ int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
   return run_op<OpGradVDGradVB<1>>(ctx, P, st, time_it);
 }
 
+// Sharded sources read from the owning GPUs (sweep_kernel<..., PEER = true>): i-parallel shapes
+// only - a rank of a sharded sweep has thousands of targets.
+template <class Op>
+int run_op_peer(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  switch (pick_shape(ctx, P.t1 - P.t0)) {
+    case SHAPE_LARGE: return Launcher<Op, 256, 4, 1, 4, true>::run(ctx, P, st, time_it);
+    case SHAPE_MEDIUM: return Launcher<Op, 128, 2, 4, 4, true>::run(ctx, P, st, time_it);
+    default: return Launcher<Op, 128, 1, 6, 4, true>::run(ctx, P, st, time_it);
+  }
+}
+
 // Tangent sweeps: aux tiles make the stage (1+KT) x 8 KB; one shape per KT.
-template <int KT, bool JERK>
+template <int KT, bool JERK, bool PEER = false>
 int run_tangent(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st) {
   const bool time_it = (st == ctx->stream);
   if constexpr (KT == 1) {
     if (P.t1 - P.t0 >= 256)
-      return Launcher<OpTangent<KT, JERK>, 128, 2, 2, 1>::run(ctx, P, st, time_it);
+      return Launcher<OpTangent<KT, JERK>, 128, 2, 2, 1, PEER>::run(ctx, P, st, time_it);
   }
-  return Launcher<OpTangent<KT, JERK>, 128, 1, 2, 1>::run(ctx, P, st, time_it);
+  return Launcher<OpTangent<KT, JERK>, 128, 1, 2, 1, PEER>::run(ctx, P, st, time_it);
 }
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
@@ -1575,6 +1586,169 @@ int nbk_dev_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, const double *d_packed, con
     P.out[1] = d_dgsum_tan + (size_t)k0 * 3 * nt;
     if (kt == 3) TRY((run_tangent<3, true>(ctx, P, (cudaStream_t)stream)));
     else TRY((run_tangent<1, true>(ctx, P, (cudaStream_t)stream)));
+    k0 += kt;
+  }
+  return NBK_OK;
+}
+
+// ---- peer-memory exchange ---------------------------------------------------------------------
+int nbk_peer_alloc(nbk_ctx *ctx, size_t bytes, void **d_ptr, unsigned char *handle) {
+  if (!ctx || !d_ptr || bytes == 0) return ctx ? fail(ctx, NBK_ERR_ARG, "nbk_peer_alloc: bad arguments") : NBK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess)
+    return fail(ctx, NBK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  CK(cudaMemset(p, 0, bytes));
+  if (handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == NBK_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      return fail(ctx, NBK_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof h);
+  }
+  *d_ptr = p;
+  return NBK_OK;
+}
+
+int nbk_peer_open(nbk_ctx *ctx, const unsigned char *handle, void **d_ptr) {
+  if (!ctx || !handle || !d_ptr) return ctx ? fail(ctx, NBK_ERR_ARG, "nbk_peer_open: bad arguments") : NBK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NBK_OK;
+}
+
+int nbk_peer_close(nbk_ctx *ctx, void *d_ptr) {
+  if (!ctx) return NBK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (d_ptr) CK(cudaIpcCloseMemHandle(d_ptr));
+  return NBK_OK;
+}
+
+int nbk_peer_free(nbk_ctx *ctx, void *d_ptr) {
+  if (!ctx) return NBK_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (d_ptr) CK(cudaFree(d_ptr));
+  return NBK_OK;
+}
+
+int nbk_dev_publish(nbk_ctx *ctx, int nranks, int self, uint64_t *const *d_ready_of_rank,
+                    uint64_t epoch, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (nranks < 1 || nranks > MAX_PEERS || self < 0 || self >= nranks || !d_ready_of_rank)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_publish: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  PublishParams F;
+  memset(&F, 0, sizeof F);
+  for (int r = 0; r < nranks; ++r) {
+    if (!d_ready_of_rank[r]) return fail(ctx, NBK_ERR_ARG, "nbk_dev_publish: null ready array");
+    F.ready_of[r] = (unsigned long long *)d_ready_of_rank[r];
+  }
+  publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(F, nranks, self, (unsigned long long)epoch);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+namespace {
+// Validates a shard table and turns it into sweep parameters (targets must be rows of `self`).
+int peer_params(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0, int t1,
+                int s0, int s1, bool need_aux, SweepParams &P) {
+  TRY(check_ranges(ctx, n_total, t0, t1, s0, s1));
+  if (!sh || sh->nranks < 1 || sh->nranks > MAX_PEERS || sh->self < 0 || sh->self >= sh->nranks ||
+      sh->shard_rows <= 0 || sh->shard_rows % TJ != 0 || s0 % TJ != 0)
+    return fail(ctx, NBK_ERR_ARG,
+                "bad shard table (1..%d ranks, shard_rows and s0 multiples of %d)", MAX_PEERS, TJ);
+  if ((long long)sh->shard_rows * sh->nranks < n_total)
+    return fail(ctx, NBK_ERR_ARG, "shards hold %lld rows < n_total = %d",
+                (long long)sh->shard_rows * sh->nranks, n_total);
+  const long long lo = (long long)sh->self * sh->shard_rows;
+  if (t1 > t0 && (t0 < lo || t1 > lo + sh->shard_rows))
+    return fail(ctx, NBK_ERR_ARG, "targets [%d,%d) are not rows of rank %d's shard", t0, t1,
+                sh->self);
+  P = base_params(nullptr, eps2, t0, t1, s0, s1);
+  for (int r = 0; r < sh->nranks; ++r) {
+    if (!sh->packed[r] || ((uintptr_t)sh->packed[r] & 15) ||
+        (need_aux && (!sh->aux[r] || ((uintptr_t)sh->aux[r] & 15))))
+      return fail(ctx, NBK_ERR_ARG, "shard %d: null or misaligned device pointer", r);
+    P.shard[r] = sh->packed[r];
+    P.aux_shard[r] = need_aux ? sh->aux[r] : nullptr;
+  }
+  P.shard_rows = sh->shard_rows;
+  P.self_rank = sh->self;
+  P.ready = (const unsigned long long *)sh->ready;
+  P.epoch = sh->epoch;
+  // this rank's own shard, biased so that packed + i*PK is target i (never dereferenced outside it)
+  P.packed = sh->packed[sh->self] - (size_t)lo * PK;
+  if (need_aux) P.aux = sh->aux[sh->self] - (size_t)lo * PK;
+  CK(cudaSetDevice(ctx->device));
+  return NBK_OK;
+}
+}  // namespace
+
+int nbk_dev_grad_v_dgrad_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
+                                    int t0, int t1, int s0, int s1, double *d_gsum,
+                                    double *d_dgsum, int accumulate, void *stream) {
+  SweepParams P;
+  TRY(peer_params(ctx, sh, n_total, eps2, t0, t1, s0, s1, false, P));
+  if (t1 == t0 || s1 == s0) return NBK_OK;
+  if (!d_gsum || !d_dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  P.out[0] = d_gsum;
+  P.out[1] = d_dgsum;
+  P.accumulate = accumulate;
+  return run_op_peer<OpGradVDGradVB<1>>(ctx, P, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_grad_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0,
+                            int t1, int s0, int s1, double *d_gsum, int accumulate,
+                            void *stream) {
+  SweepParams P;
+  TRY(peer_params(ctx, sh, n_total, eps2, t0, t1, s0, s1, false, P));
+  if (t1 == t0 || s1 == s0) return NBK_OK;
+  if (!d_gsum) return fail(ctx, NBK_ERR_ARG, "null output");
+  P.out[0] = d_gsum;
+  P.accumulate = accumulate;
+  return run_op_peer<OpGradV>(ctx, P, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0,
+                       int t1, int s0, int s1, double *d_phi, int accumulate, void *stream) {
+  SweepParams P;
+  TRY(peer_params(ctx, sh, n_total, eps2, t0, t1, s0, s1, false, P));
+  if (t1 == t0 || s1 == s0) return NBK_OK;
+  if (!d_phi) return fail(ctx, NBK_ERR_ARG, "null output");
+  P.out[0] = d_phi;
+  P.accumulate = accumulate;
+  return run_op_peer<OpV>(ctx, P, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, int K,
+                                            double eps2, int t0, int t1, int s0, int s1,
+                                            double *d_gsum_tan, double *d_dgsum_tan,
+                                            void *stream) {
+  SweepParams P0;
+  TRY(peer_params(ctx, sh, n_total, eps2, t0, t1, s0, s1, true, P0));
+  if (t1 == t0 || s1 == s0) return NBK_OK;
+  if (K <= 0 || !d_gsum_tan || !d_dgsum_tan)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_grad_v_dgrad_v_sum_tangent_peer: bad arguments");
+  const size_t nt = (size_t)(t1 - t0);
+  const size_t dir = (size_t)sh->shard_rows * PK;  // doubles per direction inside a shard
+  for (int k0 = 0; k0 < K;) {
+    const int kt = (K - k0 >= 3) ? 3 : 1;
+    SweepParams P = P0;
+    P.aux = P0.aux + (size_t)k0 * dir;
+    for (int r = 0; r < sh->nranks; ++r) P.aux_shard[r] = P0.aux_shard[r] + (size_t)k0 * dir;
+    P.aux_stride = (int)dir;
+    P.K = kt;
+    P.out[0] = d_gsum_tan + (size_t)k0 * 3 * nt;
+    P.out[1] = d_dgsum_tan + (size_t)k0 * 3 * nt;
+    if (kt == 3) TRY((run_tangent<3, true, true>(ctx, P, (cudaStream_t)stream)));
+    else TRY((run_tangent<1, true, true>(ctx, P, (cudaStream_t)stream)));
     k0 += kt;
   }
   return NBK_OK;

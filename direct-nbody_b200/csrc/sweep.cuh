@@ -24,6 +24,7 @@ namespace nbk {
 constexpr int PK = 8;            // doubles per packed body {x,y,z,m,vx,vy,vz,0}
 constexpr int TJ = 128;          // sources per tile (8 KB per stage)
 constexpr int STAGES = 3;
+constexpr int MAX_PEERS = 8;      // GPUs of one NVSwitch box
 
 // ---- PTX helpers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -67,6 +68,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
       : "memory");
 }
 
+// System-scope acquire load of a flag another GPU writes over NVLink.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Orders the generic-proxy acquire above before the async-proxy (TMA) reads that follow.
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 // 1/sqrt(x): MUFU.RSQ64H seed (~2^-22 relative) + one third-order step
 // y = y0 (1 + e/2 + 3 e^2/8), e = 1 - x y0^2: error ~ (5/16) e^3 < 2^-64, so the result is
 // the correctly rounded value to within the last two roundings.  2 DMUL + 3 DFMA.  No
@@ -108,6 +123,17 @@ struct SweepParams {
   double *partial;  // [2*G][NACC][TI]
   double *out[4];   // op-specific outputs (device)
   int accumulate;
+  // Sharded sources (sweep_kernel<..., PEER = true> only): body j lives in row j % shard_rows of
+  // shard[j / shard_rows], a peer-mapped array on the GPU that owns it (NVLink P2P).  `packed`
+  // is then this GPU's own shard, biased so that packed + i*PK is target i.  ready != NULL:
+  // rank r's rows may be read once ready[r] >= epoch (peers store their flag with release.sys
+  // after packing, nbk::publish_kernel).
+  const double *shard[MAX_PEERS];
+  const double *aux_shard[MAX_PEERS];
+  int shard_rows;
+  int self_rank;
+  const unsigned long long *ready;
+  unsigned long long epoch;
 };
 
 // ---- pair operations -----------------------------------------------------------------------
@@ -659,7 +685,10 @@ constexpr size_t sweep_smem_bytes(int naux) {
 
 // NT threads per CTA, IPT targets per thread (i-tile TI = NT*IPT), MINB resident CTAs per SM
 // asked of the register allocator, UNROLL = source-loop unroll of the off-diagonal path.
-template <class Op, int NT, int IPT, int MINB, int UNROLL>
+// PEER: source tiles are bulk-copied straight out of the owning GPU's memory over NVLink
+// (SweepParams::shard) - the exchange step of the target-sharded multi-GPU sweep fused into the
+// sweep itself, tile by tile behind the same TMA ring, instead of an all-gather in front of it.
+template <class Op, int NT, int IPT, int MINB, int UNROLL, bool PEER = false>
 __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
   constexpr int TI = NT * IPT;
   constexpr int NAUX = naux_of<Op>::value;
@@ -685,6 +714,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
   __syncthreads();
 
   // Producer side (thread 0): tile k of this CTA is unit u_begin+k -> source tile jt.
+  unsigned seen = 0;  // PEER: owners whose ready flag this CTA has already acquired
   auto issue = [&](int k) {
     long long u = u_begin + k;
     int jt = (int)(u % P.n_jt);
@@ -693,12 +723,26 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
     int st = k % STAGES;
     uint32_t bytes = (uint32_t)cnt * PK * 8;
     double *dst = tiles + (size_t)st * STAGE_DOUBLES;
+    const double *src = P.packed + (size_t)j0 * PK;
+    const double *asrc = P.aux + (size_t)j0 * PK;
+    if constexpr (PEER) {
+      // shard_rows and s0 are multiples of TJ: a tile never straddles two owners
+      const int owner = j0 / P.shard_rows;
+      const size_t row = (size_t)(j0 - owner * P.shard_rows);
+      src = P.shard[owner] + row * PK;
+      asrc = P.aux_shard[owner] + row * PK;
+      if (P.ready != nullptr && owner != P.self_rank && !((seen >> owner) & 1u)) {
+        while (ld_acquire_sys(P.ready + owner) < P.epoch) __nanosleep(64);
+        fence_proxy_async();
+        seen |= 1u << owner;
+      }
+    }
     mbar_arrive_expect_tx(&full[st], bytes * (1 + NAUX));
-    tma_bulk_g2s(dst, P.packed + (size_t)j0 * PK, bytes, &full[st]);
+    tma_bulk_g2s(dst, src, bytes, &full[st]);
 #pragma unroll
     for (int a = 0; a < NAUX; ++a)
-      tma_bulk_g2s(dst + (size_t)(1 + a) * TJ * PK,
-                   P.aux + (size_t)a * P.aux_stride + (size_t)j0 * PK, bytes, &full[st]);
+      tma_bulk_g2s(dst + (size_t)(1 + a) * TJ * PK, asrc + (size_t)a * P.aux_stride, bytes,
+                   &full[st]);
   };
   if (tid == 0) {
     for (int k = 0; k < STAGES - 1 && k < ntiles; ++k) issue(k);
@@ -804,6 +848,19 @@ __global__ void __launch_bounds__(TI) fixup_kernel(const SweepParams P) {
     Op::combine(acc, part);
   }
   Op::store(P, i, acc);
+}
+
+// Publishes "rank `self`'s rows of epoch `epoch` are in place" into every rank's ready array
+// (peer-mapped): launched on the stream after the kernel that wrote the rows.
+struct PublishParams {
+  unsigned long long *ready_of[MAX_PEERS];
+};
+__global__ void publish_kernel(PublishParams F, int nranks, int self, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r < nranks) {
+    __threadfence_system();
+    st_release_sys(F.ready_of[r] + self, epoch);
+  }
 }
 
 // ---- few targets: source-parallel kernel -----------------------------------------------------

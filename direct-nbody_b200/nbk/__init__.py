@@ -23,6 +23,19 @@ _d, _i, _f = C.c_double, C.c_int, C.c_float
 _pd = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class Shards(C.Structure):
+    """nbk_shards (include/nbk.h): where each rank's packed rows live, as seen from this GPU."""
+    _fields_ = [("nranks", _i), ("self", _i), ("shard_rows", _i),
+                ("packed", _vp * MAX_PEERS), ("aux", _vp * MAX_PEERS),
+                ("ready", _vp), ("epoch", C.c_uint64)]
+
+
+_psh = C.POINTER(Shards)
+
 # name -> (restype, argtypes): every symbol include/nbk.h declares.
 SYMBOLS = {
     "nbk_create": (_i, [C.POINTER(_vp), _i]),
@@ -79,6 +92,16 @@ SYMBOLS = {
     "nbk_dev_pack_aux": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _i, _i, _vp, _vp,
                                                 _vp]),
+    "nbk_peer_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "nbk_peer_open": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "nbk_peer_close": (_i, [_vp, _vp]),
+    "nbk_peer_free": (_i, [_vp, _vp]),
+    "nbk_dev_publish": (_i, [_vp, _i, _i, C.POINTER(_vp), C.c_uint64, _vp]),
+    "nbk_dev_grad_v_dgrad_v_sum_peer": (_i, [_vp, _psh, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "nbk_dev_grad_v_sum_peer": (_i, [_vp, _psh, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_dev_v_sum_peer": (_i, [_vp, _psh, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_dev_grad_v_dgrad_v_sum_tangent_peer": (_i, [_vp, _psh, _i, _i, _d, _i, _i, _i, _i, _vp,
+                                                     _vp, _vp]),
     "nbk_tune": (_i, [_vp, _i]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
@@ -429,3 +452,64 @@ class Context:
         (t0, t1), (s0, s1) = targets, sources
         self._ck(self._lib.nbk_dev_v_sum(self._h, d_packed, n_total, eps2, t0, t1, s0, s1, d_phi,
                                          int(accumulate), stream or None))
+
+    # -------------------------------------------------------------- peer-memory exchange
+    def peer_alloc(self, nbytes, want_handle=True):
+        """-> (device address, 64-byte IPC handle or None) of a zeroed region."""
+        ptr = _vp()
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES) if want_handle else None
+        self._ck(self._lib.nbk_peer_alloc(self._h, nbytes, C.byref(ptr), buf))
+        return ptr.value, (buf.raw if want_handle else None)
+
+    def peer_open(self, handle: bytes):
+        ptr = _vp()
+        self._ck(self._lib.nbk_peer_open(self._h, handle, C.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr):
+        self._ck(self._lib.nbk_peer_close(self._h, ptr))
+
+    def peer_free(self, ptr):
+        self._ck(self._lib.nbk_peer_free(self._h, ptr))
+
+    def dev_publish(self, self_rank, ready_of_rank, epoch, stream=0):
+        arr = (_vp * len(ready_of_rank))(*ready_of_rank)
+        self._ck(self._lib.nbk_dev_publish(self._h, len(ready_of_rank), self_rank, arr, epoch,
+                                           stream or None))
+
+    @staticmethod
+    def make_shards(self_rank, shard_rows, packed, ready=0, epoch=0, aux=None):
+        sh = Shards()
+        sh.nranks, sh.self, sh.shard_rows = len(packed), self_rank, shard_rows
+        for r, ptr in enumerate(packed):
+            sh.packed[r] = ptr
+            sh.aux[r] = aux[r] if aux is not None else None
+        sh.ready = ready or None
+        sh.epoch = epoch
+        return sh
+
+    def dev_grad_v_dgrad_v_sum_peer(self, shards, n_total, eps2, targets, sources, d_gsum, d_dgsum,
+                                    accumulate=False, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum_peer(
+            self._h, C.byref(shards), n_total, eps2, t0, t1, s0, s1, d_gsum, d_dgsum,
+            int(accumulate), stream or None))
+
+    def dev_grad_v_sum_peer(self, shards, n_total, eps2, targets, sources, d_gsum,
+                            accumulate=False, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_sum_peer(self._h, C.byref(shards), n_total, eps2, t0, t1,
+                                                   s0, s1, d_gsum, int(accumulate), stream or None))
+
+    def dev_v_sum_peer(self, shards, n_total, eps2, targets, sources, d_phi, accumulate=False,
+                       stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_v_sum_peer(self._h, C.byref(shards), n_total, eps2, t0, t1, s0,
+                                              s1, d_phi, int(accumulate), stream or None))
+
+    def dev_grad_v_dgrad_v_sum_tangent_peer(self, shards, n_total, K, eps2, targets, sources,
+                                            d_gsum_tan, d_dgsum_tan, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum_tangent_peer(
+            self._h, C.byref(shards), n_total, K, eps2, t0, t1, s0, s1, d_gsum_tan, d_dgsum_tan,
+            stream or None))

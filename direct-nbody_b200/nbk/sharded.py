@@ -35,10 +35,13 @@ class ShardPlan:
         return self.t1 - self.t0
 
 
-def make_plan(n: int, world: int, rank: int) -> ShardPlan:
-    if n < 0 or world < 1 or not 0 <= rank < world:
-        raise ValueError(f"bad shard plan n={n} world={world} rank={rank}")
+def make_plan(n: int, world: int, rank: int, align: int = 1) -> ShardPlan:
+    """Contiguous equal shards; `align` rounds the shard up to whole source tiles (128 for the
+    peer-memory exchange, whose tiles must not straddle two owners)."""
+    if n < 0 or world < 1 or not 0 <= rank < world or align < 1:
+        raise ValueError(f"bad shard plan n={n} world={world} rank={rank} align={align}")
     shard = (n + world - 1) // world if n else 0
+    shard = (shard + align - 1) // align * align
     t0, t1 = min(rank * shard, n), min((rank + 1) * shard, n)
     return ShardPlan(n, world, rank, shard, t0, t1)
 
@@ -179,3 +182,182 @@ class ShardedTangent:
                 self.packed_all.data_ptr(), self.aux_all.data_ptr(), pl.npad, self.K, eps2,
                 (pl.t0, pl.t1), (0, pl.n), self.gt.data_ptr(), self.dgt.data_ptr(), stream)
         return self.gt, self.dgt
+
+
+# ---------------------------------------------------------------------------------------------
+# Peer-memory exchange: the all-gather fused into the sweep (include/nbk.h, "peer-memory
+# exchange").  Every rank keeps its packed rows in a region the other ranks map over NVLink
+# (CUDA IPC); the sweep kernel bulk-copies each source tile straight out of its owner's memory
+# behind the TMA ring that stages local tiles, so there is no exchange step left in a sweep.
+# ---------------------------------------------------------------------------------------------
+PEER_TILE = 128        # sources per tile: shards are whole tiles
+PEER_FLAG_BYTES = 1024  # ready[8] flags, padded
+
+
+def peer_region_layout(shard_rows: int, K: int = 0, nbuf: int = 2):
+    """Byte offsets inside one rank's region: flags, then nbuf x {packed rows, K direction
+    arrays}.  Returns (total_bytes, [packed offset per buffer], [aux offset per buffer])."""
+    rows_bytes = shard_rows * PACKED * 8
+    buf_bytes = rows_bytes * (1 + K)
+    packed_off = [PEER_FLAG_BYTES + b * buf_bytes for b in range(nbuf)]
+    aux_off = [o + rows_bytes for o in packed_off]
+    return PEER_FLAG_BYTES + nbuf * buf_bytes, packed_off, aux_off
+
+
+class PeerRegions:
+    """This rank's region plus the mapped regions of every other rank."""
+
+    def __init__(self, plan: ShardPlan, ctx, K: int = 0, group=None, exchange=None):
+        if plan.shard % PEER_TILE:
+            raise ValueError("peer exchange needs make_plan(..., align=128)")
+        self.plan, self.ctx, self.K = plan, ctx, K
+        self.total, self.packed_off, self.aux_off = peer_region_layout(plan.shard, K)
+        self.base = [0] * plan.world
+        self.base[plan.rank], handle = ctx.peer_alloc(self.total, want_handle=plan.world > 1)
+        if exchange is None:
+            def exchange(obj):
+                import torch.distributed as dist
+                out = [None] * plan.world
+                dist.all_gather_object(out, obj, group=group)
+                return out
+        self._opened = []
+        if plan.world > 1:
+            handles = exchange(handle)
+            for r in range(plan.world):
+                if r != plan.rank:
+                    self.base[r] = ctx.peer_open(handles[r])
+                    self._opened.append(self.base[r])
+        self.group = group
+
+    def packed(self, buf):      # rank -> address of its packed rows in buffer `buf`
+        return [b + self.packed_off[buf] for b in self.base]
+
+    def aux(self, buf):
+        return [b + self.aux_off[buf] for b in self.base]
+
+    @property
+    def ready_local(self):
+        return self.base[self.plan.rank]
+
+    def close(self, barrier=None):
+        for ptr in self._opened:
+            self.ctx.peer_close(ptr)
+        self._opened = []
+        if barrier is not None:
+            barrier()  # nobody frees a region a peer still maps
+        if self.base[self.plan.rank]:
+            self.ctx.peer_free(self.base[self.plan.rank])
+            self.base[self.plan.rank] = 0
+
+
+class PeerShardedAccJerk:
+    """ShardedAccJerk without the all-gather: step() = publish this rank's rows + ONE sweep
+    kernel that reads remote source tiles over NVLink (nbk_dev_grad_v_dgrad_v_sum_peer)."""
+
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None):
+        import torch
+        self.torch, self.plan, self.device, self.ctx, self.group = torch, plan, device, ctx, group
+        self.regions = PeerRegions(plan, ctx, 0, group, exchange)
+        self.g = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.dg = torch.zeros_like(self.g)
+        self.epoch, self.cur = 0, 0
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def load_local(self, m, q, p):
+        """Pack this rank's bodies into the row buffer the NEXT step reads (the one no peer is
+        reading: buffers alternate, see include/nbk.h)."""
+        torch, pl = self.torch, self.plan
+        self.cur = (self.epoch + 1) % 2
+        if pl.count == 0:
+            return
+        sl = slice(pl.t0, pl.t1)
+        d_m = torch.as_tensor(m[sl], dtype=torch.float64).to(self.device).contiguous()
+        d_q = torch.as_tensor(q[sl], dtype=torch.float64).to(self.device).contiguous()
+        d_p = torch.as_tensor(p[sl], dtype=torch.float64).to(self.device).contiguous()
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+                          self.regions.packed(self.cur)[pl.rank], self._stream())
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self, eps2: float = 0.0):
+        pl, rg = self.plan, self.regions
+        self.epoch += 1
+        st = self._stream()
+        if pl.world > 1:
+            self.ctx.dev_publish(pl.rank, rg.base, self.epoch, st)  # flags sit at offset 0
+        if pl.count:
+            sh = self.ctx.make_shards(pl.rank, pl.shard, rg.packed(self.cur),
+                                      rg.ready_local if pl.world > 1 else 0, self.epoch)
+            self.ctx.dev_grad_v_dgrad_v_sum_peer(sh, pl.n, eps2, (pl.t0, pl.t1), (0, pl.n),
+                                                 self.g.data_ptr(), self.dg.data_ptr(), False, st)
+        return self.g, self.dg
+
+    def close(self):
+        self.torch.cuda.synchronize(self.device)
+        barrier = None
+        if self.plan.world > 1:
+            import torch.distributed as dist
+            barrier = lambda: dist.barrier(group=self.group)
+            barrier()  # every rank's last sweep has finished reading
+        self.regions.close(barrier)
+
+
+class PeerShardedTangent:
+    """ShardedTangent over the peer-memory exchange: bodies and the K direction arrays are read
+    from their owners by the tangent sweep itself."""
+
+    def __init__(self, plan: ShardPlan, K: int, device, ctx, group=None, exchange=None):
+        import torch
+        self.torch, self.plan, self.K, self.device, self.ctx = torch, plan, K, device, ctx
+        self.group = group
+        self.regions = PeerRegions(plan, ctx, K, group, exchange)
+        self.gt = torch.zeros(K, max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.dgt = torch.zeros_like(self.gt)
+        self.epoch, self.cur = 0, 0
+
+    def load_local(self, m, q, p, dq, dp):
+        torch, pl, rg = self.torch, self.plan, self.regions
+        self.cur = (self.epoch + 1) % 2
+        if pl.count == 0:
+            return
+        sl = slice(pl.t0, pl.t1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        d_m = torch.as_tensor(m[sl]).to(self.device).contiguous()
+        d_q = torch.as_tensor(q[sl]).to(self.device).contiguous()
+        d_p = torch.as_tensor(p[sl]).to(self.device).contiguous()
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+                          rg.packed(self.cur)[pl.rank], stream)
+        keep = [d_m, d_q, d_p]
+        dir_bytes = pl.shard * PACKED * 8
+        for k in range(self.K):
+            d_dq = torch.as_tensor(dq[k][sl]).to(self.device).contiguous()
+            d_dp = torch.as_tensor(dp[k][sl]).to(self.device).contiguous()
+            self.ctx.dev_pack_aux(pl.count, d_m.data_ptr(), d_dq.data_ptr(), d_dp.data_ptr(),
+                                  rg.aux(self.cur)[pl.rank] + k * dir_bytes, stream)
+            keep += [d_dq, d_dp]
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self, eps2: float = 0.0):
+        pl, rg = self.plan, self.regions
+        self.epoch += 1
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        if pl.world > 1:
+            self.ctx.dev_publish(pl.rank, rg.base, self.epoch, st)
+        if pl.count:
+            sh = self.ctx.make_shards(pl.rank, pl.shard, rg.packed(self.cur),
+                                      rg.ready_local if pl.world > 1 else 0, self.epoch,
+                                      aux=rg.aux(self.cur))
+            self.ctx.dev_grad_v_dgrad_v_sum_tangent_peer(
+                sh, pl.n, self.K, eps2, (pl.t0, pl.t1), (0, pl.n), self.gt.data_ptr(),
+                self.dgt.data_ptr(), st)
+        return self.gt, self.dgt
+
+    def close(self):
+        self.torch.cuda.synchronize(self.device)
+        barrier = None
+        if self.plan.world > 1:
+            import torch.distributed as dist
+            barrier = lambda: dist.barrier(group=self.group)
+            barrier()
+        self.regions.close(barrier)

@@ -282,6 +282,52 @@ int nbk_dev_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, const double *d_packed, con
                                        int s1, double *d_gsum_tan, double *d_dgsum_tan,
                                        void *stream);
 
+/* ---- peer-memory exchange: the all-gather fused into the sweep ------------------------------ */
+/* One rank of a target-sharded sweep needs every body as a source.  Instead of
+ * all-gathering the packed rows in front of the sweep, the *_peer sweeps read each source tile
+ * straight out of the owning GPU's memory over NVLink/NVSwitch, behind the same TMA ring that
+ * stages local tiles, so the exchange overlaps the arithmetic tile by tile and costs no step of
+ * its own.  Body j lives in row j % shard_rows of rank j / shard_rows.
+ *
+ * Regions: nbk_peer_alloc gives zeroed device memory plus (if handle != NULL) a 64-byte CUDA IPC
+ * handle another PROCESS passes to nbk_peer_open to map it (one process per GPU, the handles
+ * travel over torch.distributed); inside one process plain device pointers work once peer
+ * access is enabled (nbk_create_multi does that).
+ * Ordering: a rank packs its rows, then nbk_dev_publish stores `epoch` into slot `self` of every
+ * rank's ready[] array (release, system scope); a *_peer sweep given ready != NULL does not read
+ * rank r's rows before ready[r] >= epoch (acquire).  With two row buffers used alternately no
+ * further synchronisation is needed: a rank packs epoch e+1 only after its own sweep of epoch
+ * e, which has seen every peer publish e, i.e. finish reading epoch e-1. */
+#define NBK_MAX_PEERS 8
+#define NBK_IPC_HANDLE_BYTES 64
+typedef struct nbk_shards {
+  int nranks, self;
+  int shard_rows;                      /* rows per rank: a multiple of 128 */
+  const double *packed[NBK_MAX_PEERS]; /* rank r's packed rows [shard_rows][8], mapped on this device */
+  const double *aux[NBK_MAX_PEERS];    /* tangent sweeps: rank r's direction rows [K][shard_rows][8] */
+  const uint64_t *ready;               /* this rank's ready[NBK_MAX_PEERS], or NULL: caller ordered the streams */
+  uint64_t epoch;
+} nbk_shards;
+int nbk_peer_alloc(nbk_ctx *ctx, size_t bytes, void **d_ptr, unsigned char *handle);
+int nbk_peer_open(nbk_ctx *ctx, const unsigned char *handle, void **d_ptr);
+int nbk_peer_close(nbk_ctx *ctx, void *d_ptr);
+int nbk_peer_free(nbk_ctx *ctx, void *d_ptr);
+/* d_ready_of_rank[r] = rank r's ready[] array as mapped on this device. */
+int nbk_dev_publish(nbk_ctx *ctx, int nranks, int self, uint64_t *const *d_ready_of_rank,
+                    uint64_t epoch, void *stream);
+/* As nbk_dev_grad_v_dgrad_v_sum / _grad_v_sum / _v_sum / _tangent with the sources sharded;
+ * targets [t0,t1) must be rows of rank `self`, s0 a multiple of 128. */
+int nbk_dev_grad_v_dgrad_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
+                                    int t0, int t1, int s0, int s1, double *d_gsum,
+                                    double *d_dgsum, int accumulate, void *stream);
+int nbk_dev_grad_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0,
+                            int t1, int s0, int s1, double *d_gsum, int accumulate, void *stream);
+int nbk_dev_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0,
+                       int t1, int s0, int s1, double *d_phi, int accumulate, void *stream);
+int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, int K,
+                                            double eps2, int t0, int t1, int s0, int s1,
+                                            double *d_gsum_tan, double *d_dgsum_tan, void *stream);
+
 /* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
  * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).
  * Results do not depend on the shape beyond summation order.  A knob for profiles/ and

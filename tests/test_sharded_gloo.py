@@ -80,3 +80,81 @@ def test_two_rank_sharded_sweep_equals_single_process(tmp_path, oracle, n, overl
     a0, a1 = np.load(tmp_path / "all0.npy"), np.load(tmp_path / "all1.npy")
     assert np.array_equal(a0, a1)
     assert np.array_equal(a0[:n, 0:3], q) and np.array_equal(a0[:n, 3], m)
+
+
+# ---- peer-memory exchange: host-side plumbing (the CUDA side is tests/test_peer_gpu.py) ------
+def test_aligned_plan_keeps_tiles_inside_one_owner():
+    from nbk.sharded import make_plan
+    for n in (1, 127, 128, 129, 5000, 131072, 131073):
+        for world in (1, 2, 3, 8):
+            plans = [make_plan(n, world, r, align=128) for r in range(world)]
+            assert plans[0].shard % 128 == 0 and plans[0].npad >= n
+            assert plans[0].t0 == 0 and plans[-1].t1 == n
+            for a, b in zip(plans, plans[1:]):
+                assert a.t1 == b.t0
+            for j0 in range(0, n, 128):  # every source tile has exactly one owner
+                assert j0 // plans[0].shard == (min(j0 + 128, n) - 1) // plans[0].shard
+
+
+def test_peer_region_layout_is_disjoint_and_aligned():
+    from nbk.sharded import PEER_FLAG_BYTES, peer_region_layout
+    for rows, K in ((128, 0), (16384, 0), (4096, 6)):
+        total, poff, aoff = peer_region_layout(rows, K)
+        assert poff[0] == PEER_FLAG_BYTES and len(poff) == 2
+        row_bytes = rows * 64
+        assert poff[1] - poff[0] == row_bytes * (1 + K) and total == poff[1] + row_bytes * (1 + K)
+        assert all(o % 128 == 0 for o in poff + aoff)
+        assert aoff[0] == poff[0] + row_bytes
+
+
+class _FakeCtx:
+    """Stands in for nbk.Context: records the region calls PeerRegions makes."""
+
+    def __init__(self, rank):
+        self.rank, self.log = rank, []
+
+    def peer_alloc(self, nbytes, want_handle=True):
+        self.log.append(("alloc", nbytes))
+        return 0x1000 * (self.rank + 1), (bytes([self.rank]) * 64 if want_handle else None)
+
+    def peer_open(self, handle):
+        self.log.append(("open", handle[0]))
+        return 0x100000 * (handle[0] + 1)
+
+    def peer_close(self, ptr):
+        self.log.append(("close", ptr))
+
+    def peer_free(self, ptr):
+        self.log.append(("free", ptr))
+
+
+def _peer_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbk.sharded import PeerRegions, make_plan
+        ctx = _FakeCtx(rank)
+        rg = PeerRegions(make_plan(1000, world, rank, align=128), ctx)  # handles over gloo
+        bases = list(rg.base)
+        rg.close(barrier=dist.barrier)
+        np.save(os.path.join(out_dir, f"bases{rank}.npy"), np.array(bases))
+        with open(os.path.join(out_dir, f"log{rank}.txt"), "w") as f:
+            f.write(repr(ctx.log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_peer_region_handle_exchange(tmp_path):
+    world = 2
+    port = 29300 + os.getpid() % 300
+    mp.spawn(_peer_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        bases = np.load(tmp_path / f"bases{rank}.npy")
+        other = 1 - rank
+        assert bases[rank] == 0x1000 * (rank + 1)          # own allocation
+        assert bases[other] == 0x100000 * (other + 1)      # the peer's handle, opened
+        log = eval(open(tmp_path / f"log{rank}.txt").read())
+        kinds = [k for k, _ in log]
+        assert kinds == ["alloc", "open", "close", "free"]  # unmap peers before freeing
+        assert log[1] == ("open", other)

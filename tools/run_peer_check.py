@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""torchrun job: the peer-memory exchange (sweep reads remote source tiles over NVLink, CUDA IPC
+regions) against the NCCL all-gather path, same shards -> results must be bit-identical.
+Also times both (device events, max over ranks) and, with --tangent K, the tangent sweeps.
+
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 \
+      tools/run_peer_check.py --bodies 131072 --steps 10
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "direct-nbody_b200")):
+    sys.path.insert(0, _p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bodies", dest="n", type=int, default=131072)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--tangent", type=int, default=0)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import nbh
+    import nbk
+    from nbk.sharded import (PeerShardedAccJerk, PeerShardedTangent, ShardedAccJerk,
+                             ShardedTangent, make_plan)
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = nbk.Context(local)
+    n = args.n
+    m, q, p = nbh.make_plummer(n, 20243)
+    plan = make_plan(n, world, rank, align=128)
+    stream = torch.cuda.current_stream()
+
+    def timed(step):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ok = True
+    if args.tangent == 0:
+        a = ShardedAccJerk(plan, dev, ctx=ctx)
+        b = PeerShardedAccJerk(plan, dev, ctx)
+        a.load_local(m, q, p)
+        b.load_local(m, q, p)
+        ga, dga = a.step(1e-4)
+        gb, dgb = b.step(1e-4)
+        torch.cuda.synchronize()
+        ok = torch.equal(ga, gb) and torch.equal(dga, dgb)
+        # a second epoch with fresh rows in the other buffer
+        q2 = q * 1.001
+        a.load_local(m, q2, p)
+        b.load_local(m, q2, p)
+        ga, dga = a.step(0.0)
+        gb, dgb = b.step(0.0)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(ga, gb) and torch.equal(dga, dgb)
+        ms_nccl = timed(lambda: a.step(0.0))
+        ms_peer = timed(lambda: b.step(0.0))
+        inter = float(n) * (n - 1)
+    else:
+        K = args.tangent
+        rng = np.random.default_rng(20245)
+        dq = rng.standard_normal((K, n, 3))
+        dp = rng.standard_normal((K, n, 3)) * m[None, :, None]
+        a = ShardedTangent(plan, K, dev, ctx)
+        b = PeerShardedTangent(plan, K, dev, ctx)
+        a.load_local(m, q, p, dq, dp)
+        b.load_local(m, q, p, dq, dp)
+        ga, dga = a.step(1e-4)
+        gb, dgb = b.step(1e-4)
+        torch.cuda.synchronize()
+        ok = torch.equal(ga, gb) and torch.equal(dga, dgb)
+        ms_nccl = timed(lambda: a.step(1e-4))
+        ms_peer = timed(lambda: b.step(1e-4))
+        inter = float(K) * n * (n - 1)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    b.close()
+    if rank == 0:
+        what = "acc+jerk" if args.tangent == 0 else f"tangent K={args.tangent}"
+        print(f"{what} N={n} on {world} GPUs: NCCL all-gather + sweep {ms_nccl:.3f} ms/step "
+              f"({inter / ms_nccl / 1e6:.1f} G/s), peer-read sweep {ms_peer:.3f} ms/step "
+              f"({inter / ms_peer / 1e6:.1f} G/s); bit-identical: {bool(flag.item())}")
+        print("PEER CHECK OK" if flag.item() else "PEER CHECK FAILED")
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
