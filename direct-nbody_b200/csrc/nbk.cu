@@ -54,6 +54,9 @@ struct nbk_ctx {
   // single-process multi-GPU (nbk_create_multi): further contexts, one per extra device
   std::vector<nbk_ctx *> peers;
   cudaEvent_t ev_ready = nullptr;
+  bool p2p_all = false;      // every device of the multi context can map every other's memory
+  bool multi_sharded = false;  // the last multi_stage left the bodies sharded (peer-read sweeps)
+  int multi_shard_rows = 0;
 };
 
 namespace {
@@ -456,26 +459,78 @@ int run_kick(nbk_ctx *ctx, const double *packed, double eta, double dt, int t0, 
 struct Slice {
   nbk_ctx *c;
   int a, b;  // targets [a, b) of this device
+  int d;     // device index inside the multi context
 };
+
+nbk_ctx *multi_dev(nbk_ctx *ctx, int d) { return d == 0 ? ctx : ctx->peers[d - 1]; }
 
 int multi_plan(nbk_ctx *ctx, int t0, int t1, std::vector<Slice> &out) {
   const int ndev = 1 + (int)ctx->peers.size();
+  if (ctx->multi_sharded) {  // a device sweeps the targets among its own rows
+    const int rows = ctx->multi_shard_rows;
+    for (int d = 0; d < ndev; ++d) {
+      int a = std::max(t0, d * rows), b = std::min(t1, (d + 1) * rows);
+      if (b < a) b = a;
+      out.push_back({multi_dev(ctx, d), a, b, d});
+    }
+    return NBK_OK;
+  }
   const int nt = t1 - t0;
   int per = (nt + ndev - 1) / ndev;
   per = (per + 1023) / 1024 * 1024;  // whole large tiles per device
   for (int d = 0; d < ndev; ++d) {
-    nbk_ctx *c = d == 0 ? ctx : ctx->peers[d - 1];
     int a = t0 + d * per, b = t0 + (d + 1) * per;
     if (a > t1) a = t1;
     if (b > t1) b = t1;
-    out.push_back({c, a, b});
+    out.push_back({multi_dev(ctx, d), a, b, d});
   }
   return NBK_OK;
 }
 
-// Stage on device 0 and broadcast the packed array to the peers.
+// Stage the bodies for a multi-device sweep.
+// Peer mode (all devices map each other, sources start on a tile): every device uploads and
+// packs ITS OWN rows - ndev host->device copies in parallel, one per PCIe link - and the sweeps
+// read the other devices' rows over NVLink themselves (sweep_kernel<..., PEER>); streams are
+// ordered with events, so the kernels need no ready flags.
+// Otherwise: stage on device 0 and broadcast the packed array (cudaMemcpyPeerAsync).
 int multi_stage(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
-                int is_velocity) {
+                int is_velocity, int s0) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  ctx->multi_sharded = false;
+  if (ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ) {
+    if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
+    int rows = (n + ndev - 1) / ndev;
+    rows = (rows + 1023) / 1024 * 1024;  // whole large target tiles (and source tiles) per device
+    for (int d = 0; d < ndev; ++d) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
+      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
+      int rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
+      if (rc == NBK_OK && cnt > 0) {
+        rc = upload(c, c->d_m, m + a, cnt);
+        if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
+        if (rc == NBK_OK && vel) rc = upload(c, c->d_vel, vel + 3 * (size_t)a, 3 * (size_t)cnt);
+        if (rc == NBK_OK)
+          rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
+                    vel ? (const double *)c->d_vel.p : nullptr, is_velocity,
+                    (double *)c->d_packed.p, c->stream);
+      }
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
+      if (cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
+        return fail(ctx, NBK_ERR_CUDA, "cudaEventRecord");
+    }
+    for (int d = 0; d < ndev; ++d) {  // nobody sweeps before every shard is packed
+      nbk_ctx *c = multi_dev(ctx, d);
+      cudaSetDevice(c->device);
+      for (int e = 0; e < ndev; ++e)
+        if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
+          return fail(ctx, NBK_ERR_CUDA, "cudaStreamWaitEvent");
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->multi_sharded = true;
+    ctx->multi_shard_rows = rows;
+    return NBK_OK;
+  }
   CK(cudaSetDevice(ctx->device));
   TRY(stage_bodies(ctx, n, m, q, vel, is_velocity));
   CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
@@ -488,6 +543,24 @@ int multi_stage(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
                            peer->stream));
   }
   return NBK_OK;
+}
+
+// Sweep parameters of one device's slice after multi_stage.
+SweepParams multi_params(nbk_ctx *ctx, const Slice &s, double eps2, int s0, int s1) {
+  SweepParams P = base_params((const double *)s.c->d_packed.p, eps2, s.a, s.b, s0, s1);
+  if (ctx->multi_sharded) {
+    const int ndev = 1 + (int)ctx->peers.size();
+    for (int d = 0; d < ndev; ++d) P.shard[d] = (const double *)multi_dev(ctx, d)->d_packed.p;
+    P.shard_rows = ctx->multi_shard_rows;
+    P.self_rank = s.d;
+    P.packed = P.shard[s.d] - (size_t)s.d * P.shard_rows * PK;
+  }
+  return P;
+}
+
+template <class Op> int multi_run(nbk_ctx *ctx, nbk_ctx *c, const SweepParams &P) {
+  return ctx->multi_sharded ? run_op_peer<Op>(c, P, c->stream, true)
+                            : run_op<Op>(c, P, c->stream, true);
 }
 
 // =================================================================================================
@@ -551,17 +624,23 @@ int nbk_create_multi(nbk_ctx **out, int ndev, const int *devices) {
       return rc;
     }
     root->peers.push_back(peer);
-    // direct NVLink copies between the devices (ignore "already enabled")
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, peer->device, root->device);
-    if (can) {
-      cudaSetDevice(peer->device);
-      cudaDeviceEnablePeerAccess(root->device, 0);
-      cudaSetDevice(root->device);
-      cudaDeviceEnablePeerAccess(peer->device, 0);
-      cudaGetLastError();
-    }
   }
+  // direct NVLink access between every pair of devices (ignore "already enabled")
+  root->p2p_all = ndev > 1 && getenv("NBK_NO_PEER_READS") == nullptr;
+  for (int a = 0; a < ndev; ++a)
+    for (int b = 0; b < ndev; ++b) {
+      if (a == b) continue;
+      nbk_ctx *ca = multi_dev(root, a), *cb = multi_dev(root, b);
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, ca->device, cb->device);
+      if (can) {
+        cudaSetDevice(ca->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(cb->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        cudaGetLastError();
+      }
+      if (!can) root->p2p_all = false;
+    }
   CK(cudaSetDevice(root->device));
   *out = root;
   return NBK_OK;
@@ -611,7 +690,7 @@ int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double
   if (n == 0) return NBK_OK;
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
     if (!gsum) return fail(ctx, NBK_ERR_ARG, "null output");
-    TRY(multi_stage(ctx, n, m, q, nullptr, 1));
+    TRY(multi_stage(ctx, n, m, q, nullptr, 1, s0));
     std::vector<Slice> sl;
     TRY(multi_plan(ctx, t0, t1, sl));
     for (Slice &s : sl) {
@@ -619,9 +698,9 @@ int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double
       nbk_ctx *c = s.c;
       if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
       int rc = reserve(c, c->d_out[0], 3 * (size_t)(s.b - s.a) * sizeof(double));
-      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
       P.out[0] = (double *)c->d_out[0].p;
-      if (rc == NBK_OK) rc = K1::run(c, P, c->stream, true);
+      if (rc == NBK_OK) rc = multi_run<OpGradV>(ctx, c, P);
       if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
     }
     for (Slice &s : sl) {
@@ -648,7 +727,7 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
   if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
     if (!gsum || !dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
-    TRY(multi_stage(ctx, n, m, q, p, 0));
+    TRY(multi_stage(ctx, n, m, q, p, 0, s0));
     std::vector<Slice> sl;
     TRY(multi_plan(ctx, t0, t1, sl));
     for (Slice &s : sl) {
@@ -658,10 +737,10 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
       const size_t cnt = 3 * (size_t)(s.b - s.a) * sizeof(double);
       int rc = reserve(c, c->d_out[0], cnt);
       if (rc == NBK_OK) rc = reserve(c, c->d_out[1], cnt);
-      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
       P.out[0] = (double *)c->d_out[0].p;
       P.out[1] = (double *)c->d_out[1].p;
-      if (rc == NBK_OK) rc = run_k2(c, P, c->stream, true);
+      if (rc == NBK_OK) rc = multi_run<OpGradVDGradVB<1>>(ctx, c, P);
       if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
     }
     for (Slice &s : sl) {
@@ -691,7 +770,7 @@ int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2
     return NBK_OK;
   }
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
-    TRY(multi_stage(ctx, n, m, q, nullptr, 1));
+    TRY(multi_stage(ctx, n, m, q, nullptr, 1, s0));
     std::vector<Slice> sl;
     TRY(multi_plan(ctx, t0, t1, sl));
     for (Slice &s : sl) {  // launch everywhere first
@@ -700,9 +779,9 @@ int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2
       if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
       int rc = reserve(c, c->d_out[0], (size_t)(s.b - s.a) * sizeof(double));
       if (rc == NBK_OK) rc = reserve(c, c->d_scalar, 64);
-      SweepParams P = base_params((const double *)c->d_packed.p, eps2, s.a, s.b, s0, s1);
+      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
       P.out[0] = (double *)c->d_out[0].p;
-      if (rc == NBK_OK) rc = K3::run(c, P, c->stream, true);
+      if (rc == NBK_OK) rc = multi_run<OpV>(ctx, c, P);
       if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
       if (total) {
         sum_kernel<<<1, 1024, 0, c->stream>>>((const double *)c->d_out[0].p, s.b - s.a,
