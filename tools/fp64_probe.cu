@@ -15,6 +15,9 @@ template <int MODE> __global__ void __launch_bounds__(256) probe(int iters, doub
     c[i] = 1e-9 * (i + 1) + s * 1e-12;
   }
   const double kb = 1.0000001 + s * 1e-12, kc = 1e-9 + s * 1e-15;
+  float fa[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fa[i] = 0.f;
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -29,12 +32,31 @@ template <int MODE> __global__ void __launch_bounds__(256) probe(int iters, doub
         if (MODE == 5) a[i] = fma(b[i], b[i], a[i]);         // 2 distinct (one twice)
         if (MODE == 6) a[i] = fma(b[i], c[(i + u) & 7], a[i]);  // 3 distinct, rotating
         if (MODE == 7) a[i] = fma(kb, b[i], a[i]);           // shared in slot A
+        // modes 8-10: mode 0's DFMA stream plus a double->float conversion of the result
+        if (MODE == 8) {  // one F2F.F32.F64 (+ FADD) per DFMA
+          a[i] = fma(a[i], kb, kc);
+          fa[i] += __double2float_rn(a[i]);
+        }
+        if (MODE == 9) {  // one F2F per 4 DFMA
+          a[i] = fma(a[i], kb, kc);
+          if ((i & 3) == 0) fa[i] += __double2float_rn(a[i]);
+        }
+        if (MODE == 10) {  // conversion by integer ops on the high word (truncating, normal range)
+          a[i] = fma(a[i], kb, kc);
+          int hi = __double2hiint(a[i]);
+          int fb = (hi & 0x80000000) | (((hi & 0x7fffffff) - (896 << 20)) << 3);
+          fa[i] += __int_as_float(fb);
+        }
+        if (MODE == 11) {  // F2F only (a[] is refreshed by an integer xor): conversion throughput
+          a[i] = __hiloint2double(__double2hiint(a[i]) ^ (it & 1), __double2loint(a[i]));
+          fa[i] += __double2float_rn(a[i]);
+        }
       }
     }
   }
   double r = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r += a[i] + b[i] + c[i];
+  for (int i = 0; i < 8; ++i) r += a[i] + b[i] + c[i] + fa[i];
   if (r == 12345.678) sink[0] = r;
 }
 
@@ -70,5 +92,9 @@ int main() {
   run<5>(p.multiProcessorCount, sink);
   run<6>(p.multiProcessorCount, sink);
   run<7>(p.multiProcessorCount, sink);
+  run<8>(p.multiProcessorCount, sink);
+  run<9>(p.multiProcessorCount, sink);
+  run<10>(p.multiProcessorCount, sink);
+  run<11>(p.multiProcessorCount, sink);
   return 0;
 }
