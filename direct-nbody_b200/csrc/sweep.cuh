@@ -286,14 +286,32 @@ struct OpV {
 };
 
 // Leapfrog.kick summed (leapfrog.ml:70-104), pre-kick velocities.  The velocity half uses
-// the fast rsqrt (dv_i = dt * sum m_j d / r^3, unsoftened); the time-scale half repeats the
-// reference's IEEE operation sequence with correctly rounded sqrt/div and no contraction, so
-// each pair's tscale - and therefore the min - is bit-identical to the reference formula.
+// the fast rsqrt (dv_i = dt * sum m_j d / r^3, unsoftened).  The time-scale half must return,
+// bit for bit, the minimum over sources of the reference's pair time-scale, which costs 2 sqrt
+// + 5 div in IEEE arithmetic - far too much to run on every pair.  So every pair goes through a
+// FILTER on the FP32 pipe (which idles beside the FP64 pipe): a sufficient condition, free of
+// divisions and square roots, for "this pair's time-scale exceeds the running minimum by more
+// than 0.2 %".  Only pairs that fail it - about ln N per target, plus anything NaN/inf/out of
+// float range - run the reference's exact operation sequence (correctly rounded sqrt/div, no
+// contraction), so the minimum is bit-identical to the reference formula.
+//
+// Filter.  With y = 1/r, s = |d.u| y^2, T = 1.002 min-so-far, M = m_i + m_j (leapfrog.ml:94-101):
+//   tff = eta sqrt(r^3/M), tff_eff = tff / |1 - a|, a = 0.75 (d.u/r^2) tff
+//   tc  = eta r/|u|,       tc_eff  = tc  / |1 - b|, b = 0.5 (d.u/r^2) tc (1 + M/(|u|^2 r))
+// |1 - a| <= 1 + |a| gives  tff_eff > T  <=  g > 0 and tff^2 g^2 > T^2,  g = 1 - 0.75 T s, i.e.
+//   (eta^2 r2^2 y / T^2) g^2 > M;
+// likewise  tc_eff > T  <=  G > 0 and (eta^2 r2 / T^2) G^2 > |u|^6,  G = |u|^2 - 0.5 T s (|u|^2 + M y).
+// A pair costs 4 double->float conversions and ~30 FP32 operations.  (A looser test on r^2,
+// |u|^2 and M alone was tried, alone and as a first level: it lets ~1 % of the pairs through,
+// which with 32 lanes x 4 targets per warp makes most warps take the slow branch - slower.)
+// State per target (acc[4], two floats): Tf >= T and 1/Tf^2; Tf = +inf, 1/Tf^2 = 0 (never
+// "far") until a first exact value exists or whenever T leaves [1e-12, 1e12].
 template <bool WITH_TSCALE> struct OpKick {
-  static constexpr int NACC = WITH_TSCALE ? 4 : 3;
+  static constexpr int NACC = WITH_TSCALE ? 5 : 3;
   static constexpr int ND2 = WITH_TSCALE ? 4 : 2;
   struct Tgt {
     double x, y, z, vx, vy, vz, m;
+    float mf;
   };
   __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
@@ -303,70 +321,157 @@ template <bool WITH_TSCALE> struct OpKick {
     t.vx = pk[4];
     t.vy = pk[5];
     t.vz = pk[6];
+    t.mf = __double2float_rn(pk[3]);
+  }
+  __device__ __forceinline__ static double filter_state(double tmin) {
+    const double T = tmin * 1.002;
+    float Tf = __int_as_float(0x7f800000), inv = 0.0f;
+    if (T > 1e-12 && T < 1e12) {
+      Tf = __double2float_ru(T);
+      inv = __frcp_rd(__fmul_ru(Tf, Tf));
+    }
+    return __hiloint2double(__float_as_int(inv), __float_as_int(Tf));
   }
   __device__ __forceinline__ static void zero(double *acc) {
     acc[0] = acc[1] = acc[2] = 0.0;
-    if (WITH_TSCALE) acc[3] = __longlong_as_double(0x7ff0000000000000LL);
+    if (WITH_TSCALE) {
+      acc[3] = __longlong_as_double(0x7ff0000000000000LL);
+      acc[4] = __hiloint2double(0, 0x7f800000);
+    }
+  }
+  // The reference's exact pair time-scale (leapfrog.ml:80-104, unfused, correctly rounded).
+  __device__ __noinline__ static double exact_tscale(double dx, double dy, double dz, double ux,
+                                                     double uy, double uz, double mi, double mj,
+                                                     double eta) {
+    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double vsqe = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), __dmul_rn(uz, uz));
+    const double vdre = __dadd_rn(__dadd_rn(__dmul_rn(dx, ux), __dmul_rn(dy, uy)), __dmul_rn(dz, uz));
+    const double mtot = __dadd_rn(mi, mj);
+    double r = __dsqrt_rn(r2e);
+    double r3 = __dmul_rn(r2e, r);
+    double tff = __dmul_rn(eta, __dsqrt_rn(__ddiv_rn(r3, mtot)));
+    double tc = __dmul_rn(eta, __dsqrt_rn(__ddiv_rn(r2e, vsqe)));
+    double svdr = __ddiv_rn(vdre, r2e);
+    double dtff = __dmul_rn(__dmul_rn(1.5, svdr), tff);
+    double dtc = __dmul_rn(__dmul_rn(svdr, tc), __dadd_rn(1.0, __ddiv_rn(mtot, __dmul_rn(vsqe, r))));
+    tff = fabs(__ddiv_rn(tff, __dsub_rn(1.0, __dmul_rn(0.5, dtff))));
+    tc = fabs(__ddiv_rn(tc, __dsub_rn(1.0, __dmul_rn(0.5, dtc))));
+    return (tff < tc) ? tff : tc;
+  }
+  // FP32 filter: true = this pair's time-scale certainly exceeds 1.002 x the running minimum.
+  __device__ __forceinline__ static bool far_pair(double r2, double y, double vsq, double vdr,
+                                                        float M, double state, float eta2) {
+    const float X = __double2float_rn(r2), yf = __double2float_rn(y);
+    const float V = __double2float_rn(vsq), vdrf = __double2float_rn(vdr);
+    const float Tf = __int_as_float(__double2loint(state));
+    const float inv = __int_as_float(__double2hiint(state));
+    const float Ts = Tf * (fabsf(vdrf) * (yf * yf));
+    const float g = fmaf(-0.75f, Ts, 1.0f);
+    const float e2r = eta2 * X;
+    const float l1 = (((e2r * X) * yf) * inv) * (g * g);  // small factors first: an underflow
+    // reads "exact"; NaN, inf or anything beyond 1e30 fails a comparison -> exact path
+    const float G = fmaf(-0.5f * Ts, fmaf(M, yf, V), V);
+    const float l2 = (e2r * inv) * (G * G);
+    const float rh2 = (V * V) * V;
+    return (l1 > M) & (g > 0.0f) & (l2 > rh2) & (G > 0.0f) & (l1 < 1e30f) & (l2 < 1e30f);
   }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
                                               const double2 *, bool self, const SweepParams &P) {
     double2 a = sj[0], b = sj[1];
     double dx = a.x - t.x, dy = a.y - t.y, dz = b.x - t.z;
-    double r2e = __dmul_rn(dx, dx);
-    r2e = __dadd_rn(r2e, __dmul_rn(dy, dy));
-    r2e = __dadd_rn(r2e, __dmul_rn(dz, dz));  // leapfrog.ml:80 association
+    double r2 = dx * dx;
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
     double mj = b.y;
-    double r2 = r2e;
     if (CHECK) {
       r2 = self ? 1.0 : r2;
       mj = self ? 0.0 : mj;
     }
-    double y = rsqrt_nr(r2);
-    double w = (mj * y) * (y * y);
+    const double y = rsqrt_nr(r2);
+    const double w = (mj * y) * (y * y);
     acc[0] = fma(w, dx, acc[0]);
     acc[1] = fma(w, dy, acc[1]);
     acc[2] = fma(w, dz, acc[2]);
     if (WITH_TSCALE) {
       double2 c = sj[2], d = sj[3];
-      double ux = c.x - t.vx, uy = c.y - t.vy, uz = d.x - t.vz;
-      double vsq = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), __dmul_rn(uz, uz));
-      double vdr = __dadd_rn(__dadd_rn(__dmul_rn(dx, ux), __dmul_rn(dy, uy)), __dmul_rn(dz, uz));
-      const double mtot = __dadd_rn(t.m, b.y);
-      // Filter: a fast estimate of the pair time-scale (rsqrt/rcp seeds + Newton, ~1e-15
-      // relative).  Only a pair whose estimate comes within 0.1 % of the running minimum - or
-      // is NaN/inf - can change the result, and only then is the reference's exact IEEE
-      // sequence evaluated (~ln N times per target), so the minimum stays bit-exact.
-      // With y = 1/r: tff = eta rsqrt(mtot y^3), tc = eta rsqrt(vsq y^2), and
-      // |t / D| > T  <=>  |t| > T |D| needs no division.  Two MUFU + ~25 FP64 ops.
-      bool need_exact;
-      {
-        const double y2 = y * y;
-        const double za = mtot * (y2 * y);  // mtot / r^3
-        const double tffa = P.eta * rsqrt_nr(za);
-        const double qa = rsqrt_nr(vsq * y2);  // r / |u|
-        const double tca = P.eta * qa;
-        const double sva = vdr * y2;
-        const double d1 = fma(-0.75 * sva, tffa, 1.0);
-        const double d2 = fma(-0.5 * (sva * tca), fma(za, qa * qa, 1.0), 1.0);
-        const double T = acc[3] * 1.001;
-        // any NaN / inf makes a comparison false -> exact path
-        need_exact = !((fabs(tffa) > T * fabs(d1)) && (fabs(tca) > T * fabs(d2)));
-      }
+      const double ux = c.x - t.vx, uy = c.y - t.vy, uz = d.x - t.vz;
+      double vsq = ux * ux;
+      vsq = fma(uy, uy, vsq);
+      vsq = fma(uz, uz, vsq);
+      double vdr = dx * ux;
+      vdr = fma(dy, uy, vdr);
+      vdr = fma(dz, uz, vdr);
+      const float eta2 = __double2float_rn(P.eta * P.eta);
+      const bool far = far_pair(r2, y, vsq, vdr, t.mf + __double2float_rn(b.y), acc[4], eta2);
       const bool skip = CHECK ? self : false;
-      if (need_exact && !skip) {
-        double r = __dsqrt_rn(r2e);
-        double r3 = __dmul_rn(r2e, r);
-        double tff = __dmul_rn(P.eta, __dsqrt_rn(__ddiv_rn(r3, mtot)));
-        double tc = __dmul_rn(P.eta, __dsqrt_rn(__ddiv_rn(r2e, vsq)));
-        double svdr = __ddiv_rn(vdr, r2e);
-        double dtff = __dmul_rn(__dmul_rn(1.5, svdr), tff);
-        double dtc = __dmul_rn(__dmul_rn(svdr, tc),
-                               __dadd_rn(1.0, __ddiv_rn(mtot, __dmul_rn(vsq, r))));
-        tff = fabs(__ddiv_rn(tff, __dsub_rn(1.0, __dmul_rn(0.5, dtff))));
-        tc = fabs(__ddiv_rn(tc, __dsub_rn(1.0, __dmul_rn(0.5, dtc))));
-        double ts = (tff < tc) ? tff : tc;
-        if (acc[3] > ts) acc[3] = ts;  // NaN ts leaves acc[3] alone, leapfrog.ml:103
+      if (!far && !skip) {
+        const double ts = exact_tscale(dx, dy, dz, ux, uy, uz, t.m, b.y, P.eta);
+        if (acc[3] > ts) {  // NaN ts leaves acc[3] alone, leapfrog.ml:103
+          acc[3] = ts;
+          acc[4] = filter_state(ts);
+        }
+      }
+    }
+  }
+  // One source against the IPT targets of a thread, phase by phase: the IPT filters run as
+  // independent instruction streams and ONE branch guards the (rare) exact evaluations.
+  static constexpr int BATCHED = 1;
+  template <bool CHECK, int IPT>
+  __device__ __forceinline__ static void pairs(const Tgt (&t)[IPT], double (&acc)[IPT][NACC],
+                                               const double2 *sj, int jg, const int (&ig)[IPT],
+                                               const SweepParams &P) {
+    if constexpr (!WITH_TSCALE) {
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) pair<CHECK>(t[r], acc[r], sj, nullptr, jg == ig[r], P);
+    } else {
+      const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
+      const float eta2 = __double2float_rn(P.eta * P.eta);
+      const float mjf = __double2float_rn(b.y);
+      double dx[IPT], dy[IPT], dz[IPT], ux[IPT], uy[IPT], uz[IPT];
+      unsigned need = 0;
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        dx[r] = a.x - t[r].x;
+        dy[r] = a.y - t[r].y;
+        dz[r] = b.x - t[r].z;
+        double r2 = dx[r] * dx[r];
+        r2 = fma(dy[r], dy[r], r2);
+        r2 = fma(dz[r], dz[r], r2);
+        double mj = b.y;
+        const bool self = CHECK ? (jg == ig[r]) : false;
+        if (CHECK) {
+          r2 = self ? 1.0 : r2;
+          mj = self ? 0.0 : mj;
+        }
+        const double y = rsqrt_nr(r2);
+        const double w = (mj * y) * (y * y);
+        acc[r][0] = fma(w, dx[r], acc[r][0]);
+        acc[r][1] = fma(w, dy[r], acc[r][1]);
+        acc[r][2] = fma(w, dz[r], acc[r][2]);
+        ux[r] = c.x - t[r].vx;
+        uy[r] = c.y - t[r].vy;
+        uz[r] = d.x - t[r].vz;
+        double vsq = ux[r] * ux[r];
+        vsq = fma(uy[r], uy[r], vsq);
+        vsq = fma(uz[r], uz[r], vsq);
+        double vdr = dx[r] * ux[r];
+        vdr = fma(dy[r], uy[r], vdr);
+        vdr = fma(dz[r], uz[r], vdr);
+        const bool far = far_pair(r2, y, vsq, vdr, t[r].mf + mjf, acc[r][4], eta2);
+        if (!far && !self) need |= 1u << r;
+      }
+      if (need) {
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) {
+          if ((need >> r) & 1u) {
+            const double ts = exact_tscale(dx[r], dy[r], dz[r], ux[r], uy[r], uz[r], t[r].m, b.y, P.eta);
+            if (acc[r][3] > ts) {
+              acc[r][3] = ts;
+              acc[r][4] = filter_state(ts);
+            }
+          }
+        }
       }
     }
   }

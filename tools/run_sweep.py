@@ -12,6 +12,7 @@ import nbk  # noqa: E402
 op = sys.argv[1] if len(sys.argv) > 1 else "accjerk"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+shape = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # nbk_tune: 0 auto, 1 large, 2 medium, 3 small
 m, q, p = nbh.make_plummer(n, 20243)
 v = p / m[:, None]
 if op == "tangent":
@@ -20,6 +21,7 @@ if op == "tangent":
     dq = rng.standard_normal((6, n, 3))
     dp = rng.standard_normal((6, n, 3)) * m[None, :, None]
 with nbk.Context(0) as ctx:
+    ctx.tune(shape)
     for _ in range(reps):
         if op == "accjerk":
             ctx.grad_v_dgrad_v_sum(m, q, p, 0.0)
