@@ -103,6 +103,22 @@ int nbh_constant_sf_integrate(nbk_ctx *ctx, int n, int *id, double *state, doubl
                               double sf, double max_eg_err, double eps2, double *energy_errors,
                               int cap, int *nerr);
 
+/* ---- text snapshots: A.print / A.read (advancer.ml:88-96, 118-124), Leapfrog.print / read
+ * (leapfrog.ml:44-62) --------------------------------------------------------------------- */
+/* The reference's `--- !Particle` records, byte for byte (Printf "%g" is C's): id, t, r, v
+ * (= p/m for Advancer.A), m, and for Leapfrog t_max = t + dt_max.  append != 0 appends.  The
+ * readers take every record of the file (the reference reads one per call): *n = number found,
+ * an error if it exceeds cap or a record does not scan (Scanf.Scan_failure).  Read bodies carry
+ * p = v * m (advancer.ml:124) and dt_max = t_max - t (leapfrog.ml:62). */
+int nbh_advancer_print(const char *path, int append, int n, const int *id, const double *t,
+                       const double *m, const double *q, const double *p);
+int nbh_advancer_read(const char *path, int cap, int *n, int *id, double *t, double *m, double *q,
+                      double *p);
+int nbh_leapfrog_print(const char *path, int append, int n, const int *id, const double *t,
+                       const double *dt_max, const double *m, const double *q, const double *v);
+int nbh_leapfrog_read(const char *path, int cap, int *n, int *id, double *t, double *dt_max,
+                      double *m, double *q, double *v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,10 @@ SYMBOLS = {
     "nbh_advancer_advance": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _vp, _vp, _pl]),
     "nbh_extpot_plummer_test_energy": (_d, [_i, _pd, _pd]),
     "nbh_constant_sf_integrate": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _d, _d, _pd, _i, _pi]),
+    "nbh_advancer_print": (_i, [C.c_char_p, _i, _i, _pi, _pd, _pd, _pd, _pd]),
+    "nbh_advancer_read": (_i, [C.c_char_p, _i, _pi, _pi, _pd, _pd, _pd, _pd]),
+    "nbh_leapfrog_print": (_i, [C.c_char_p, _i, _i, _pi, _pd, _pd, _pd, _pd, _pd]),
+    "nbh_leapfrog_read": (_i, [C.c_char_p, _i, _pi, _pi, _pd, _pd, _pd, _pd, _pd]),
 }
 ADV_STRIDE = 35
 
@@ -300,3 +304,42 @@ def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0
         raise EgErr(o, e)
     _ck(rc)
     return o, e
+
+
+# ---- text snapshots (A.print / A.read, Leapfrog.print / read) ----------------------------------
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def advancer_print(path, ids, t, m, q, p, append=False):
+    ids, t, m, q, p = _i32(ids), _f(t), _f(m), _f(q), _f(p)
+    _ck(load_library().nbh_advancer_print(os.fsencode(path), int(append), len(m), _ip(ids), _p(t),
+                                          _p(m), _p(q), _p(p)))
+
+
+def advancer_read(path, cap=1 << 20):
+    n = C.c_int(0)
+    ids = np.zeros(cap, dtype=np.int32)
+    t, m = np.zeros(cap), np.zeros(cap)
+    q, p = np.zeros((cap, 3)), np.zeros((cap, 3))
+    _ck(load_library().nbh_advancer_read(os.fsencode(path), cap, C.byref(n), _ip(ids), _p(t), _p(m),
+                                         _p(q), _p(p)))
+    k = n.value
+    return ids[:k], t[:k], m[:k], q[:k], p[:k]
+
+
+def leapfrog_print(path, ids, t, dt_max, m, q, v, append=False):
+    ids, t, dt_max, m, q, v = _i32(ids), _f(t), _f(dt_max), _f(m), _f(q), _f(v)
+    _ck(load_library().nbh_leapfrog_print(os.fsencode(path), int(append), len(m), _ip(ids), _p(t),
+                                          _p(dt_max), _p(m), _p(q), _p(v)))
+
+
+def leapfrog_read(path, cap=1 << 20):
+    n = C.c_int(0)
+    ids = np.zeros(cap, dtype=np.int32)
+    t, dtm, m = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    q, v = np.zeros((cap, 3)), np.zeros((cap, 3))
+    _ck(load_library().nbh_leapfrog_read(os.fsencode(path), cap, C.byref(n), _ip(ids), _p(t),
+                                         _p(dtm), _p(m), _p(q), _p(v)))
+    k = n.value
+    return ids[:k], t[:k], dtm[:k], m[:k], q[:k], v[:k]

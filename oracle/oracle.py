@@ -411,3 +411,70 @@ def advancer_advance(s: AdvancerState, dt, sf, eps2=0.0, extpot=None) -> Advance
 def extpot_plummer_test_energy(m, q):
     m, q = _f(m), _f(q)
     return lib().oracle_extpot_plummer_test_energy(len(m), _p(m), _p(q))
+
+
+# ---- text snapshots: A.print / A.read (advancer.ml:88-96, 118-124), Leapfrog.print / read
+# (leapfrog.ml:44-62).  Pure-Python restatement: OCaml's Printf "%g" / "%d" are C's, and so is
+# Python's % operator; Scanf's " key: %g " (blanks match any white space) is a regular expression.
+def _particle_text(i, t, q, v, m):
+    return ("--- !Particle\n" + "id: %d\n" % i + "t: %g\n" % t + "r:\n" +
+            "  - %g\n  - %g\n  - %g\n" % (q[0], q[1], q[2]) + "v:\n" +
+            "  - %g\n  - %g\n  - %g\n" % (v[0], v[1], v[2]) + "m: %g\n" % m)
+
+
+def advancer_print_text(ids, t, m, q, p):
+    """A.print for every body (advancer.ml:88-96): v = p / m."""
+    return "".join(_particle_text(int(ids[i]), t[i], q[i], (p[i][0] / m[i], p[i][1] / m[i],
+                                                             p[i][2] / m[i]), m[i])
+                   for i in range(len(m)))
+
+
+def leapfrog_print_text(ids, t, dt_max, m, q, v):
+    """Leapfrog.print for every body (leapfrog.ml:44-53): t_max = t + dt_max."""
+    return "".join(_particle_text(int(ids[i]), t[i], q[i], v[i], m[i]) +
+                   "t_max: %g\n" % (t[i] + dt_max[i]) for i in range(len(m)))
+
+
+_FLT = r"([-+]?(?:nan|inf(?:inity)?|(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?))"
+_REC = (r"\s*---\s*!Particle\s*id:\s*([-+]?\d+)\s*t:\s*" + _FLT + r"\s*r:\s*-\s*" + _FLT +
+        r"\s*-\s*" + _FLT + r"\s*-\s*" + _FLT + r"\s*v:\s*-\s*" + _FLT + r"\s*-\s*" + _FLT +
+        r"\s*-\s*" + _FLT + r"\s*m:\s*" + _FLT + r"\s*")
+
+
+def advancer_read_text(text):
+    """A.read repeated to end of input (advancer.ml:118-124): p = v * m."""
+    import re
+    ids, t, m, q, p = [], [], [], [], []
+    pos = 0
+    pat = re.compile(_REC, re.I)
+    while text[pos:].strip():
+        mt = pat.match(text, pos)
+        if not mt:
+            raise ValueError(f"Scan_failure at byte {pos}")
+        g = mt.groups()
+        ids.append(int(g[0])); t.append(float(g[1])); m.append(float(g[8]))
+        q.append([float(x) for x in g[2:5]])
+        p.append([float(x) * float(g[8]) for x in g[5:8]])
+        pos = mt.end()
+    return (np.array(ids, dtype=np.int32), np.array(t), np.array(m), np.array(q).reshape(-1, 3),
+            np.array(p).reshape(-1, 3))
+
+
+def leapfrog_read_text(text):
+    """Leapfrog.read repeated to end of input (leapfrog.ml:55-62): dt_max = t_max - t."""
+    import re
+    ids, t, dtm, m, q, v = [], [], [], [], [], []
+    pos = 0
+    pat = re.compile(_REC + r"t_max:\s*" + _FLT + r"\s*", re.I)
+    while text[pos:].strip():
+        mt = pat.match(text, pos)
+        if not mt:
+            raise ValueError(f"Scan_failure at byte {pos}")
+        g = mt.groups()
+        ids.append(int(g[0])); t.append(float(g[1])); m.append(float(g[8]))
+        q.append([float(x) for x in g[2:5]])
+        v.append([float(x) for x in g[5:8]])
+        dtm.append(float(g[9]) - float(g[1]))
+        pos = mt.end()
+    return (np.array(ids, dtype=np.int32), np.array(t), np.array(dtm), np.array(m),
+            np.array(q).reshape(-1, 3), np.array(v).reshape(-1, 3))

@@ -50,8 +50,22 @@ def trajectories():
     return out
 
 
+def snapshot():
+    """particles_advancer.yaml: five bodies in the reference's `--- !Particle` text format
+    (A.print, advancer.ml:88-96), written by the oracle's restatement of it."""
+    m, q, p = O.rescale_to_standard_units(*O.make_plummer(5, 20246))
+    ids = np.arange(5, dtype=np.int32)
+    t = np.array([0.0, 0.25, 0.25, 1.0, 1e-3])
+    with open(os.path.join(HERE, "particles_advancer.yaml"), "w") as f:
+        f.write(O.advancer_print_text(ids, t, m, q, p))
+
+
 if __name__ == "__main__":
-    np.savez(os.path.join(HERE, "sweeps_n64_eps0.npz"), **sweeps(64, 20240, 0.0))
-    np.savez(os.path.join(HERE, "sweeps_n257_eps004.npz"), **sweeps(257, 20241, 0.04))
-    np.savez(os.path.join(HERE, "trajectories_n16.npz"), **trajectories())
-    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+    what = sys.argv[1:] or ["npz", "yaml"]
+    if "npz" in what:
+        np.savez(os.path.join(HERE, "sweeps_n64_eps0.npz"), **sweeps(64, 20240, 0.0))
+        np.savez(os.path.join(HERE, "sweeps_n257_eps004.npz"), **sweeps(257, 20241, 0.04))
+        np.savez(os.path.join(HERE, "trajectories_n16.npz"), **trajectories())
+    if "yaml" in what:
+        snapshot()
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith((".npz", ".yaml"))))
