@@ -43,6 +43,11 @@ struct nbk_ctx {
   // resident Advancer.A records
   int adv_n = 0;
   DevBuf d_adv, d_adv2;
+  // resident Omelyan_advancer.OA state: m, q, p, q*, gsum; g_valid = gsum belongs to the current q
+  int oa_n = 0;
+  bool oa_g_valid = false;
+  double oa_g_eps2 = 0.0;
+  DevBuf d_oa_m, d_oa_q, d_oa_p, d_oa_qs, d_oa_g, d_oa_phi, d_oa_el;
   // resident Hermite state
   int hermite_n = 0;
   int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size, -8 the cluster kernel (NBK_HERMITE_THREADS)
@@ -666,7 +671,8 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
-                    &c->d_adv,    &c->d_adv2};
+                    &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
+                    &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -1423,6 +1429,120 @@ int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe) {
     }
   }
   return nbk_energy(ctx, n, m, q, p, eps2, ke, pe);
+}
+
+// ---- device-resident Omelyan_advancer.OA ---------------------------------------------------------
+int nbk_oa_upload(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || (n && (!m || !q || !p))) return fail(ctx, NBK_ERR_ARG, "nbk_oa_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  TRY(upload(ctx, ctx->d_oa_m, m, n));
+  TRY(upload(ctx, ctx->d_oa_q, q, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_oa_p, p, 3 * (size_t)n));
+  TRY(reserve(ctx, ctx->d_oa_qs, 3 * (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_oa_g, 3 * (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  ctx->oa_n = n;
+  ctx->oa_g_valid = false;
+  return sync(ctx);
+}
+
+namespace {
+// gsum of the resident bodies at positions `pos` into d_oa_g
+int oa_sweep(nbk_ctx *ctx, const double *pos, double eps2) {
+  const int n = ctx->oa_n;
+  TRY(pack(ctx, n, (const double *)ctx->d_oa_m.p, pos, nullptr, 1, (double *)ctx->d_packed.p,
+           ctx->stream));
+  SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, 0, n, 0, n);
+  P.out[0] = (double *)ctx->d_oa_g.p;
+  return K1::run(ctx, P, ctx->stream, true);
+}
+}  // namespace
+
+int nbk_oa_steps(nbk_ctx *ctx, double h, double eps2, int nsteps) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (ctx->oa_n <= 0 || nsteps < 0) return fail(ctx, NBK_ERR_STATE, "nbk_oa_steps: no resident bodies");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->oa_n;
+  const size_t n3 = 3 * (size_t)n;
+  double *m = (double *)ctx->d_oa_m.p, *q = (double *)ctx->d_oa_q.p, *p = (double *)ctx->d_oa_p.p;
+  double *qs = (double *)ctx->d_oa_qs.p, *g = (double *)ctx->d_oa_g.p;
+  const unsigned b3 = (unsigned)((n3 + 255) / 256), b1 = (unsigned)((n + 255) / 256);
+  cudaStream_t st = ctx->stream;
+  for (int s = 0; s < nsteps; ++s) {
+    if (n < 2) {  // no pairs: only the two a_operate drifts act
+      oa_drift_kernel<<<b1, 256, 0, st>>>(n, m, q, p, h);
+      oa_drift_kernel<<<b1, 256, 0, st>>>(n, m, q, p, h);
+      ctx->launches += 2;
+      continue;
+    }
+    // B(h): the step's first b_operate sees the positions the previous step's last one saw
+    // (nothing moves q in between, omelyan_advancer.ml:96-104), so its sums are reused
+    if (!(ctx->oa_g_valid && ctx->oa_g_eps2 == eps2)) TRY(oa_sweep(ctx, q, eps2));
+    oa_axpy_kernel<<<b3, 256, 0, st>>>(p, g, n3, h / 6.0);
+    oa_drift_kernel<<<b1, 256, 0, st>>>(n, m, q, p, h);
+    // C(h)
+    TRY(oa_sweep(ctx, q, eps2));
+    oa_qstar_kernel<<<b1, 256, 0, st>>>(n, m, q, g, h, qs);
+    TRY(oa_sweep(ctx, qs, eps2));
+    oa_axpy_kernel<<<b3, 256, 0, st>>>(p, g, n3, 2.0 * h / 3.0);
+    oa_drift_kernel<<<b1, 256, 0, st>>>(n, m, q, p, h);
+    // B(h)
+    TRY(oa_sweep(ctx, q, eps2));
+    oa_axpy_kernel<<<b3, 256, 0, st>>>(p, g, n3, h / 6.0);
+    CK(cudaGetLastError());
+    ctx->launches += 6;
+    ctx->oa_g_valid = true;
+    ctx->oa_g_eps2 = eps2;
+  }
+  return NBK_OK;
+}
+
+int nbk_oa_download(nbk_ctx *ctx, double *q, double *p) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (ctx->oa_n <= 0) return fail(ctx, NBK_ERR_STATE, "nbk_oa_download: no resident bodies");
+  CK(cudaSetDevice(ctx->device));
+  if (q) TRY(download(ctx, q, ctx->d_oa_q, 3 * (size_t)ctx->oa_n));
+  if (p) TRY(download(ctx, p, ctx->d_oa_p, 3 * (size_t)ctx->oa_n));
+  return sync(ctx);
+}
+
+int nbk_oa_diagnostics(nbk_ctx *ctx, double eps2, double *ke, double *pe, double *el) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (ctx->oa_n <= 0) return fail(ctx, NBK_ERR_STATE, "nbk_oa_diagnostics: no resident bodies");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->oa_n;
+  double *m = (double *)ctx->d_oa_m.p, *q = (double *)ctx->d_oa_q.p, *p = (double *)ctx->d_oa_p.p;
+  TRY(reserve(ctx, ctx->d_oa_phi, (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_oa_el, 4 * (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[0], (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_scalar, 64));
+  double *phi = (double *)ctx->d_oa_phi.p, *sc = (double *)ctx->d_scalar.p;
+  cudaStream_t st = ctx->stream;
+  // one potential sweep serves Energy.total_potential_energy (0.5 sum phi) and every E_i
+  TRY(pack(ctx, n, m, q, nullptr, 1, (double *)ctx->d_packed.p, st));
+  if (n >= 2) {
+    SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, 0, n, 0, n);
+    P.out[0] = phi;
+    TRY(K3::run(ctx, P, st, true));
+  } else {
+    CK(cudaMemsetAsync(phi, 0, (size_t)n * sizeof(double), st));
+  }
+  sum_kernel<<<1, 1024, 0, st>>>(phi, n, sc);
+  kinetic_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, m, p, (double *)ctx->d_out[0].p);
+  sum_kernel<<<1, 1024, 0, st>>>((const double *)ctx->d_out[0].p, n, sc + 1);
+  ctx->launches += 3;
+  if (el) {
+    el_phase_space_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, m, q, p, phi, (double *)ctx->d_oa_el.p);
+    ctx->launches++;
+    TRY(download(ctx, el, ctx->d_oa_el, 4 * (size_t)n));
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_scalar, sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TRY(sync(ctx));
+  if (pe) *pe = 0.5 * ctx->h_scalar[0];
+  if (ke) *ke = ctx->h_scalar[1];
+  return NBK_OK;
 }
 
 // ---- device-resident Hermite state -------------------------------------------------------------

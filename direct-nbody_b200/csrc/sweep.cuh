@@ -1828,6 +1828,54 @@ __global__ void pack_kernel(int n, const double *__restrict__ m, const double *_
   o[3] = make_double2(vz, 0.0);
 }
 
+// ---- device-resident Omelyan_advancer.OA (omelyan_advancer.ml:44-104) ------------------------
+// O(N) halves of the operators; every formula repeats the host mirror's (= the reference's)
+// operation sequence without contraction, so a resident step is bit-identical to the
+// host-buffer one.  x[3n] -= f * g[3n]   (b_operate's p_i -= f gsum_i, :44-56; c_operate's
+// p_i -= pf gsum*_i, :83-90)
+__global__ void oa_axpy_kernel(double *__restrict__ x, const double *__restrict__ g, size_t n3,
+                               double f) {
+  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n3) x[a] = __dsub_rn(x[a], __dmul_rn(f, g[a]));
+}
+// a_operate (:58-65): q += p * (h / (2 m))
+__global__ void oa_drift_kernel(int n, const double *__restrict__ m, double *__restrict__ q,
+                                const double *__restrict__ p, double h) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = __ddiv_rn(h, __dmul_rn(2.0, m[i]));
+  for (int k = 0; k < 3; ++k) q[3 * i + k] = __dadd_rn(q[3 * i + k], __dmul_rn(p[3 * i + k], f));
+}
+// c_operate's q*_i = q_i - (h^2 / (24 m_i)) gsum_i (:70-78)
+__global__ void oa_qstar_kernel(int n, const double *__restrict__ m, const double *__restrict__ q,
+                                const double *__restrict__ g, double h, double *__restrict__ qs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = __ddiv_rn(__dmul_rn(h, h), __dmul_rn(24.0, m[i]));
+  for (int k = 0; k < 3; ++k) qs[3 * i + k] = __dsub_rn(q[3 * i + k], __dmul_rn(f, g[3 * i + k]));
+}
+// Analysis.bodies_to_el_phase_space (analysis.ml:904-919) from the per-body potential phi:
+// el[4i..] = {E_i, E_i/m, |L_i|, |L_i|/m}, E_i = |p|^2/(2m) + phi_i, L = q x p.
+__global__ void el_phase_space_kernel(int n, const double *__restrict__ m,
+                                      const double *__restrict__ q, const double *__restrict__ p,
+                                      const double *__restrict__ phi, double *__restrict__ el) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+  const double px = p[3 * i], py = p[3 * i + 1], pz = p[3 * i + 2];
+  const double lx = __dsub_rn(__dmul_rn(qy, pz), __dmul_rn(qz, py));
+  const double ly = __dsub_rn(__dmul_rn(qz, px), __dmul_rn(qx, pz));
+  const double lz = __dsub_rn(__dmul_rn(qx, py), __dmul_rn(qy, px));
+  const double lb = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(lx, lx), __dmul_rn(ly, ly)), __dmul_rn(lz, lz)));
+  const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz));
+  const double ke = __ddiv_rn(p2, __dmul_rn(2.0, m[i]));
+  const double e = __dadd_rn(ke, phi[i]);
+  el[4 * i + 0] = e;
+  el[4 * i + 1] = __ddiv_rn(e, m[i]);
+  el[4 * i + 2] = lb;
+  el[4 * i + 3] = __ddiv_rn(lb, m[i]);
+}
+
 // Tangent direction (dq, dp|dv) -> {dq, 0, dv, 0}, dv = dp / m.
 __global__ void pack_aux_kernel(int n, const double *__restrict__ m, const double *__restrict__ dq,
                                 const double *__restrict__ dvel, int is_velocity,

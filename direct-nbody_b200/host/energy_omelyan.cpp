@@ -79,4 +79,40 @@ int nbh_omelyan_advance(nbk_ctx *ctx, int n, const double *m, double *q, double 
   return 0;
 }
 
+// nsteps of OA.advance h with the bodies resident on the device (nbk_oa_*): one upload, all the
+// B A C A B operators and their four sweeps on the GPU, one download.  energies (may be NULL)
+// receives Energy.energy after every step - the per-step diagnostics of
+// bin/el_mass_segregation.ml's loop - and el (may be NULL) bodies_to_el_phase_space of the final
+// state, both from one potential sweep per step.  A multi-device context steps through the
+// host-buffer calls instead (its sweeps shard over the devices).
+int nbh_omelyan_advance_steps(nbk_ctx *ctx, int n, const double *m, double *q, double *p,
+                              double *t, double h, double eps2, int nsteps, double *energies,
+                              double *el) {
+  if (nsteps < 0) return fail(NBK_ERR_ARG, "nbh_omelyan_advance_steps: nsteps < 0");
+  if (nbk_device_count(ctx) > 1 || n == 0) {
+    for (int s = 0; s < nsteps; ++s) {
+      NBH_TRY(nbh_omelyan_advance(ctx, n, m, q, p, t, h, eps2));
+      if (energies) {
+        double ke = 0.0, pe = 0.0;
+        NBH_TRY(nbh_energy(ctx, n, m, q, p, eps2, &ke, &pe));
+        energies[s] = ke + pe;
+      }
+    }
+    if (el) NBH_TRY(nbh_bodies_to_el_phase_space(ctx, n, m, q, p, eps2, el));
+    return 0;
+  }
+  NBH_TRY(ck(ctx, nbk_oa_upload(ctx, n, m, q, p)));
+  for (int s = 0; s < nsteps; ++s) {
+    NBH_TRY(ck(ctx, nbk_oa_steps(ctx, h, eps2, 1)));
+    *t = *t + h;
+    if (energies || (el && s == nsteps - 1)) {
+      double ke = 0.0, pe = 0.0;
+      NBH_TRY(ck(ctx, nbk_oa_diagnostics(ctx, eps2, &ke, &pe, s == nsteps - 1 ? el : nullptr)));
+      if (energies) energies[s] = ke + pe;
+    }
+  }
+  if (el && nsteps == 0) NBH_TRY(ck(ctx, nbk_oa_diagnostics(ctx, eps2, nullptr, nullptr, el)));
+  return ck(ctx, nbk_oa_download(ctx, q, p));
+}
+
 }  // extern "C"

@@ -54,6 +54,13 @@ int nbh_bodies_to_el_phase_space(nbk_ctx *ctx, int n, const double *m, const dou
 int nbh_omelyan_advance(nbk_ctx *ctx, int n, const double *m, double *q, double *p, double *t,
                         double h, double eps2);
 
+/* nsteps of OA.advance h with the bodies resident on the device; energies[nsteps] (may be NULL)
+ * = Energy.energy after every step, el[4n] (may be NULL) = bodies_to_el_phase_space of the final
+ * state.  Bit-identical to nsteps calls of nbh_omelyan_advance. */
+int nbh_omelyan_advance_steps(nbk_ctx *ctx, int n, const double *m, double *q, double *p,
+                              double *t, double h, double eps2, int nsteps, double *energies,
+                              double *el);
+
 /* ---- Leapfrog (leapfrog.ml:113-165): flat image of Leapfrog.b array ------------------------ */
 /* advance bs dt eta: output order is the reference's (sorted by dt_max); id[] follows. */
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,

@@ -32,6 +32,7 @@ SYMBOLS = {
     "nbh_energy": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd, _pd]),
     "nbh_bodies_to_el_phase_space": (_i, [_vp, _i, _pd, _pd, _pd, _d, _pd]),
     "nbh_omelyan_advance": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _d, _d]),
+    "nbh_omelyan_advance_steps": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _d, _d, _i, _pd, _pd]),
     "nbh_leapfrog_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _d, _pl]),
     "nbh_leapfrog_advance_const_dt": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _i]),
     "nbh_hermite_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d, _d, _pl]),
@@ -76,6 +77,8 @@ def _ck(rc):
 
 
 def _p(a):
+    if a is None:
+        return None
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_pd)
 
@@ -157,6 +160,19 @@ def omelyan_advance(ctx, m, q, p, t, h, eps2=0.0):
     _ck(load_library().nbh_omelyan_advance(ctx._h, len(m), _p(m), _p(q), _p(p), C.byref(tt), h,
                                            eps2))
     return q, p, tt.value
+
+
+def omelyan_advance_steps(ctx, m, q, p, t, h, nsteps, eps2=0.0, want_energies=True, want_el=False):
+    """nsteps of OA.advance h with the bodies resident on the device; returns
+    (q, p, t, energies[nsteps] | None, el[n,4] | None)."""
+    m = _f(m)
+    q, p = _f(q).copy(), _f(p).copy()
+    tt = _d(t)
+    en = np.zeros(nsteps) if want_energies else None
+    el = np.zeros((len(m), 4)) if want_el else None
+    _ck(load_library().nbh_omelyan_advance_steps(ctx._h, len(m), _p(m), _p(q), _p(p), C.byref(tt),
+                                                 h, eps2, nsteps, _p(en), _p(el)))
+    return q, p, tt.value, en, el
 
 
 # ------------------------------------------------------------------ Leapfrog

@@ -80,6 +80,10 @@ SYMBOLS = {
     "nbk_adv_get_t": (_i, [_vp, _i, _pd]),
     "nbk_adv_init_first": (_i, [_vp, _d]),
     "nbk_adv_energy": (_i, [_vp, _d, _pd, _pd]),
+    "nbk_oa_upload": (_i, [_vp, _i, _pd, _pd, _pd]),
+    "nbk_oa_steps": (_i, [_vp, _d, _d, _i]),
+    "nbk_oa_download": (_i, [_vp, _pd, _pd]),
+    "nbk_oa_diagnostics": (_i, [_vp, _d, _pd, _pd, _pd]),
     "nbk_hermite_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd]),
     "nbk_hermite_resident_max": (_i, []),
     "nbk_hermite_advance_resident": (_i, [_vp, _d, _d, _d, C.c_long, C.POINTER(C.c_long)]),
@@ -452,6 +456,26 @@ class Context:
         (t0, t1), (s0, s1) = targets, sources
         self._ck(self._lib.nbk_dev_v_sum(self._h, d_packed, n_total, eps2, t0, t1, s0, s1, d_phi,
                                          int(accumulate), stream or None))
+
+    # -------------------------------------------------------------- resident Omelyan OA
+    def oa_upload(self, m, q, p):
+        m, q, p = _arr(m), _arr(q), _arr(p)
+        self._oa_n = len(m)
+        self._ck(self._lib.nbk_oa_upload(self._h, len(m), _p(m), _p(q), _p(p)))
+
+    def oa_steps(self, h, eps2=0.0, nsteps=1):
+        self._ck(self._lib.nbk_oa_steps(self._h, h, eps2, nsteps))
+
+    def oa_download(self):
+        q, p = np.empty((self._oa_n, 3)), np.empty((self._oa_n, 3))
+        self._ck(self._lib.nbk_oa_download(self._h, _p(q), _p(p)))
+        return q, p
+
+    def oa_diagnostics(self, eps2=0.0, want_el=True):
+        ke, pe = _d(), _d()
+        el = np.empty((self._oa_n, 4)) if want_el else None
+        self._ck(self._lib.nbk_oa_diagnostics(self._h, eps2, C.byref(ke), C.byref(pe), _p(el)))
+        return ke.value, pe.value, el
 
     # -------------------------------------------------------------- peer-memory exchange
     def peer_alloc(self, nbytes, want_handle=True):

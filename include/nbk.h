@@ -225,6 +225,21 @@ int nbk_adv_init_first(nbk_ctx *ctx, double eps2);
 /* Energy.energy of the resident bodies */
 int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
 
+/* ---- device-resident Omelyan_advancer.OA (omelyan_advancer.ml:44-104) ----------------------- */
+/* The bodies (m, q, p) stay on the device; nbk_oa_steps runs nsteps of OA.advance h
+ * (B A C A B: three grad_v sweeps at q, one at q*, omelyan_advancer.ml:96-104) without a host
+ * round trip.  Every O(N) formula repeats the reference's operation sequence, so the result
+ * is bit-identical to stepping through nbk_grad_v_sum from the host.  A step's first b_operate
+ * reuses the sums of the previous step's last one (q does not move in between): 3 sweeps per
+ * step in the steady state instead of 4, same bits. */
+int nbk_oa_upload(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p);
+int nbk_oa_steps(nbk_ctx *ctx, double h, double eps2, int nsteps);
+int nbk_oa_download(nbk_ctx *ctx, double *q, double *p);
+/* Energy.energy (energy.ml:57-78) and, if el != NULL, Analysis.bodies_to_el_phase_space
+ * (analysis.ml:904-919; el[4n] = {E_i, E_i/m, |L_i|, |L_i|/m}) of the resident bodies from ONE
+ * potential sweep: *ke + *pe is the total energy. */
+int nbk_oa_diagnostics(nbk_ctx *ctx, double eps2, double *ke, double *pe, double *el);
+
 /* ---- device-resident Hermite state: one body steps at a time (hermite.ml:95-130, 171-178) --- */
 
 /* Uploads the full Hermite.b array state (hermite.ml:20-29): t[n], m[n], q, p, f, df [3n] and

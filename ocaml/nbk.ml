@@ -41,6 +41,14 @@ external grad_v_dgrad_v_sum_tangent :
   ctx -> vec -> vec -> vec -> int -> vec -> vec -> float -> range -> vec -> vec -> unit
   = "nbk_ml_tangent_bc" "nbk_ml_tangent"
 
+(* Bodies resident on the device for Omelyan_advancer.OA (nbk_oa_*): upload once, run whole
+   steps of B A C A B on the GPU, read diagnostics / the state back when needed. *)
+external oa_upload : ctx -> vec -> vec -> vec -> unit = "nbk_ml_oa_upload"
+external oa_steps : ctx -> float -> float -> int -> unit = "nbk_ml_oa_steps"
+external oa_download : ctx -> vec -> vec -> unit = "nbk_ml_oa_download"
+(* [oa_diagnostics ctx eps2 el] = (ke, pe); fills el (4n: E_i, E_i/m, |L_i|, |L_i|/m) *)
+external oa_diagnostics : ctx -> float -> vec -> float * float = "nbk_ml_oa_diagnostics"
+
 (* One context per process, created on first use (the reference is single-threaded and keeps
    its configuration in globals such as Base.eps2, base.ml:20-34). *)
 let the_ctx = lazy (create 0)

@@ -181,3 +181,38 @@ CAMLprim value nbk_ml_tangent(value a0, value a1, value a2, value a3, value a4, 
   value a[11] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10};
   return nbk_ml_tangent_bc(a, 11);
 }
+
+/* ---- bodies resident on the device for Omelyan_advancer.OA (nbk_oa_*) ---------------------- */
+/* external oa_upload : ctx -> m -> q -> p -> unit */
+CAMLprim value nbk_ml_oa_upload(value ctx, value m, value q, value p) {
+  CAMLparam4(ctx, m, q, p);
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx), nbk_oa_upload(Ctx_val(ctx), n, D(m), D(q), D(p)));
+  CAMLreturn(Val_unit);
+}
+
+/* external oa_steps : ctx -> h:float -> eps2:float -> nsteps:int -> unit */
+CAMLprim value nbk_ml_oa_steps(value ctx, value h, value eps2, value nsteps) {
+  CAMLparam4(ctx, h, eps2, nsteps);
+  check(Ctx_val(ctx), nbk_oa_steps(Ctx_val(ctx), Double_val(h), Double_val(eps2), Int_val(nsteps)));
+  CAMLreturn(Val_unit);
+}
+
+/* external oa_download : ctx -> q -> p -> unit */
+CAMLprim value nbk_ml_oa_download(value ctx, value q, value p) {
+  CAMLparam3(ctx, q, p);
+  check(Ctx_val(ctx), nbk_oa_download(Ctx_val(ctx), D(q), D(p)));
+  CAMLreturn(Val_unit);
+}
+
+/* external oa_diagnostics : ctx -> eps2:float -> el -> float * float   (ke, pe) */
+CAMLprim value nbk_ml_oa_diagnostics(value ctx, value eps2, value el) {
+  CAMLparam3(ctx, eps2, el);
+  CAMLlocal1(res);
+  double ke = 0.0, pe = 0.0;
+  check(Ctx_val(ctx), nbk_oa_diagnostics(Ctx_val(ctx), Double_val(eps2), &ke, &pe, D(el)));
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, caml_copy_double(ke));
+  Store_field(res, 1, caml_copy_double(pe));
+  CAMLreturn(res);
+}

@@ -28,3 +28,25 @@ let c_operate h bs =
   let g = gsum_of (fun b -> b.q_star) bs in
   List.iteri (fun i { p = p } ->
       for k = 0 to 2 do p.(k) <- p.(k) -. pf *. g.{3 * i + k} done) bs
+
+(* [advance_steps h n bs]: n calls of OA.advance h (omelyan_advancer.ml:96-104) with the bodies
+   resident on the device - one upload, every operator and sweep on the GPU, one download.
+   Same bits as n times [advance h]; [f] (if given) sees the total energy after every step
+   without the state leaving the device (bin/el_mass_segregation.ml's per-step diagnostics). *)
+let advance_steps ?f h nsteps bs =
+  let bs = Array.map copy bs in
+  let n = Array.length bs and ctx = Nbk.ctx () in
+  let m = Nbk.pack1 (fun b -> b.m) bs and q = Nbk.pack3 (fun b -> b.q) bs
+  and p = Nbk.pack3 (fun b -> b.p) bs and el = Nbk.vec (4 * n) in
+  Nbk.oa_upload ctx m q p;
+  for _ = 1 to nsteps do
+    Nbk.oa_steps ctx h !Base.eps2 1;
+    (match f with
+     | Some f -> let ke, pe = Nbk.oa_diagnostics ctx !Base.eps2 el in f (ke +. pe) el
+     | None -> ())
+  done;
+  Nbk.oa_download ctx q p;
+  Array.iteri (fun i b ->
+      for k = 0 to 2 do b.q.(k) <- q.{3 * i + k}; b.p.(k) <- p.{3 * i + k} done;
+      b.t <- b.t +. float_of_int nsteps *. h) bs;
+  bs

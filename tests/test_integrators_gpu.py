@@ -83,6 +83,33 @@ def test_omelyan_two_mass_energy_diagnostics(ctx, oracle):
     assert abs((ea - e0) / e0) < 1e-5
 
 
+@pytest.mark.parametrize("n,eps", [(1, 0.0), (2, 0.0), (300, 0.0), (2500, 0.01)])
+def test_omelyan_resident_steps_bit_identical_to_host_buffer_steps(ctx, oracle, n, eps):
+    """nbk_oa_* (bodies, operators and sweeps resident on the device, a step's first b_operate
+    reusing the previous step's last sums) against stepping through nbk_grad_v_sum from the
+    host: identical bits, energies and per-body E_i from one potential sweep included."""
+    m, q, p = oracle.make_plummer(n, 20244)
+    eps2, h, nsteps = eps * eps, 1.0 / 128, 3
+    qa, pa, ta, en_ref = q, p, 0.0, []
+    for _ in range(nsteps):
+        qa, pa, ta = nbh.omelyan_advance(ctx, m, qa, pa, ta, h, eps2)
+        en_ref.append(sum(nbh.energy(ctx, m, qa, pa, eps2)))
+    el_ref = nbh.bodies_to_el_phase_space(ctx, m, qa, pa, eps2)
+    qb, pb, tb, en, el = nbh.omelyan_advance_steps(ctx, m, q, p, 0.0, h, nsteps, eps2, want_el=True)
+    assert tb == ta and np.array_equal(qb, qa) and np.array_equal(pb, pa)
+    assert np.array_equal(en, np.array(en_ref)) and np.array_equal(el, el_ref)
+    if n > 1:  # and the oracle, to rounding
+        qo, po, to = q, p, 0.0
+        for _ in range(nsteps):
+            qo, po, to = oracle.omelyan_advance(m, qo, po, to, h, eps2)
+        assert rel(qb, qo) <= 1e-12 and rel(pb, po) <= 1e-11
+        assert abs(en[-1] - oracle.energy(m, qo, po, eps2)) <= 1e-11 * abs(en[-1])
+    # a second call continues from a fresh upload: no stale sums survive
+    qc, pc, tc, _, _ = nbh.omelyan_advance_steps(ctx, m, qb, pb, tb, h, 1, eps2)
+    qd, pd, td = nbh.omelyan_advance(ctx, m, qa, pa, ta, h, eps2)
+    assert np.array_equal(qc, qd) and np.array_equal(pc, pd)
+
+
 def _hot100(oracle, seed):
     m, q, p = oracle.make_hot_spherical(100, seed)
     m, q, p = oracle.adjust_frame(m, q, p)
