@@ -100,6 +100,11 @@ with nbk.Context(0) as ctx:
     m, q, p = nbh.adjust_frame(m, q, p)
     m, q, p = nbh.rescale_to_standard_units(ctx, m, q, p)
     e0 = sum(nbh.energy(ctx, m, q, p))
+    # device-resident: bodies, operators, sweeps and diagnostics on the GPU (nbk_oa_*)
+    nbh.omelyan_advance_steps(ctx, m, q, p, 0.0, 1.0 / 256, 1)  # warm-up
+    t0 = time.perf_counter()
+    qr, pr, tr, en_r, el_r = nbh.omelyan_advance_steps(ctx, m, q, p, 0.0, 1.0 / 256, 4, want_el=True)
+    t_res = (time.perf_counter() - t0) / 4
     t, errs, t_step, t_diag = 0.0, [], 0.0, 0.0
     for _ in range(4):
         t0 = time.perf_counter()
@@ -113,6 +118,9 @@ with nbk.Context(0) as ctx:
     res.append({"config": 3, "what": f"OA.advance h=1/256 x 4, two-mass Plummer N={n}, energy + per-body E_i each step",
                 "dE_per_step": errs, "ms_per_step_gpu": 1e3 * t_step / 4,
                 "ms_diagnostics_per_step_gpu": 1e3 * t_diag / 4,
+                "ms_per_step_with_diagnostics_device_resident": 1e3 * t_res,
+                "device_resident_bit_identical": bool(np.array_equal(qr, q) and np.array_equal(pr, p)
+                                                      and np.array_equal(el_r, el) and en_r[-1] == e),
                 "sum_Ei_minus_KE_minus_2PE": float(abs(el[:, 0].sum() - (e + nbh.energy(ctx, m, q, p)[1])))})
     print(res[-1], flush=True)
 
