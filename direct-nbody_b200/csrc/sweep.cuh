@@ -815,11 +815,23 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
       mbar_init(&empty[s], NT / 32);
     }
     mbar_fence_init();
+    if constexpr (PEER) {
+      // Every owner's rows must be published before this CTA pulls its first tile.  Stream-K
+      // hands a CTA tiles of every owner from the start, so waiting owner by owner inside the
+      // loop would buy nothing - and keeping that state alive across the hot loop costs it
+      // registers (measured: +0.8 % kernel time).
+      if (P.ready != nullptr) {
+        const int r_lo = P.s0 / P.shard_rows, r_hi = (P.s1 - 1) / P.shard_rows;
+        for (int r = r_lo; r <= r_hi; ++r)  // the owners of sources [s0, s1)
+          if (r != P.self_rank)
+            while (ld_acquire_sys(P.ready + r) < P.epoch) __nanosleep(64);
+        fence_proxy_async();
+      }
+    }
   }
   __syncthreads();
 
   // Producer side (thread 0): tile k of this CTA is unit u_begin+k -> source tile jt.
-  unsigned seen = 0;  // PEER: owners whose ready flag this CTA has already acquired
   auto issue = [&](int k) {
     long long u = u_begin + k;
     int jt = (int)(u % P.n_jt);
@@ -836,11 +848,6 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
       const size_t row = (size_t)(j0 - owner * P.shard_rows);
       src = P.shard[owner] + row * PK;
       asrc = P.aux_shard[owner] + row * PK;
-      if (P.ready != nullptr && owner != P.self_rank && !((seen >> owner) & 1u)) {
-        while (ld_acquire_sys(P.ready + owner) < P.epoch) __nanosleep(64);
-        fence_proxy_async();
-        seen |= 1u << owner;
-      }
     }
     mbar_arrive_expect_tx(&full[st], bytes * (1 + NAUX));
     tma_bulk_g2s(dst, src, bytes, &full[st]);
