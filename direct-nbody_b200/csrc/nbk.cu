@@ -43,6 +43,12 @@ struct nbk_ctx {
   // resident Advancer.A records
   int adv_n = 0;
   DevBuf d_adv, d_adv2;
+  // resident Leapfrog.b array: packed rows {q, m, v} in array order + dt_max
+  int lf_n = 0;
+  DevBuf d_lf_packed, d_lf_packed2, d_lf_dtmax, d_lf_dtmax2;
+  double *h_lf_stage = nullptr;  // pinned staging: dt_max read-backs and sort permutations
+  size_t h_lf_cap = 0;
+  cudaEvent_t ev_lf = nullptr;   // the last permutation upload has left the staging buffer
   // resident Omelyan_advancer.OA state: m, q, p, q*, gsum; g_valid = gsum belongs to the current q
   int oa_n = 0;
   bool oa_g_valid = false;
@@ -672,11 +678,14 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
-                    &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el};
+                    &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el, &c->d_lf_packed,
+                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
   if (c->h_hres) cudaFreeHost(c->h_hres);
+  if (c->h_lf_stage) cudaFreeHost(c->h_lf_stage);
+  if (c->ev_lf) cudaEventDestroy(c->ev_lf);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1429,6 +1438,145 @@ int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe) {
     }
   }
   return nbk_energy(ctx, n, m, q, p, eps2, ke, pe);
+}
+
+// ---- device-resident Leapfrog.b array ------------------------------------------------------------
+#define NEED_LF()                                                                          \
+  do {                                                                                     \
+    if (!ctx) return NBK_ERR_ARG;                                                          \
+    if (ctx->lf_n == 0)                                                                    \
+      return fail(ctx, NBK_ERR_STATE, "no resident Leapfrog bodies: call nbk_lf_upload");   \
+    CK(cudaSetDevice(ctx->device));                                                        \
+  } while (0)
+
+int nbk_lf_upload(nbk_ctx *ctx, int n, const double *dt_max, const double *m, const double *q,
+                  const double *v) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n <= 0 || !dt_max || !m || !q || !v) return fail(ctx, NBK_ERR_ARG, "nbk_lf_upload: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  TRY(upload(ctx, ctx->d_m, m, n));
+  TRY(upload(ctx, ctx->d_q, q, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_vel, v, 3 * (size_t)n));
+  TRY(upload(ctx, ctx->d_lf_dtmax, dt_max, n));
+  TRY(reserve(ctx, ctx->d_lf_dtmax2, (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_lf_packed, (size_t)n * PK * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_lf_packed2, (size_t)n * PK * sizeof(double)));
+  TRY(pack(ctx, n, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
+           (const double *)ctx->d_vel.p, 1, (double *)ctx->d_lf_packed.p, ctx->stream));
+  if (ctx->h_lf_cap < (size_t)n) {  // pinned: n doubles for dt_max, then n ints for a permutation
+    if (ctx->h_lf_stage) CK(cudaFreeHost(ctx->h_lf_stage));
+    ctx->h_lf_stage = nullptr;
+    ctx->h_lf_cap = 0;
+    CK(cudaMallocHost((void **)&ctx->h_lf_stage, (size_t)n * (sizeof(double) + sizeof(int))));
+    ctx->h_lf_cap = (size_t)n;
+  }
+  if (!ctx->ev_lf) CK(cudaEventCreateWithFlags(&ctx->ev_lf, cudaEventDisableTiming));
+  CK(cudaEventRecord(ctx->ev_lf, ctx->stream));
+  ctx->lf_n = n;
+  return sync(ctx);
+}
+
+int nbk_lf_download(nbk_ctx *ctx, double *dt_max, double *q, double *v) {
+  NEED_LF();
+  const int n = ctx->lf_n;
+  if (q || v) {
+    TRY(reserve(ctx, ctx->d_q, 3 * (size_t)n * sizeof(double)));
+    TRY(reserve(ctx, ctx->d_vel, 3 * (size_t)n * sizeof(double)));
+    unpack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const double *)ctx->d_lf_packed.p, n,
+                                                           (double *)ctx->d_q.p, (double *)ctx->d_vel.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (q) TRY(download(ctx, q, ctx->d_q, 3 * (size_t)n));
+    if (v) TRY(download(ctx, v, ctx->d_vel, 3 * (size_t)n));
+  }
+  if (dt_max) TRY(download(ctx, dt_max, ctx->d_lf_dtmax, n));
+  return sync(ctx);
+}
+
+int nbk_lf_permute(nbk_ctx *ctx, int count, const int *perm) {
+  NEED_LF();
+  if (count < 0 || count > ctx->lf_n || (count > 0 && !perm))
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_permute: bad arguments");
+  if (count == 0) return NBK_OK;
+  TRY(reserve(ctx, ctx->d_aux_in, (size_t)count * sizeof(int)));
+  // stage the permutation in pinned memory so the call need not wait for the copy
+  int *stage = reinterpret_cast<int *>(ctx->h_lf_stage + ctx->h_lf_cap);
+  CK(cudaEventSynchronize(ctx->ev_lf));  // the previous permutation has left the buffer
+  memcpy(stage, perm, (size_t)count * sizeof(int));
+  CK(cudaMemcpyAsync(ctx->d_aux_in.p, stage, (size_t)count * sizeof(int), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaEventRecord(ctx->ev_lf, ctx->stream));
+  const size_t elems = (size_t)count * PK;
+  lf_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ctx->stream>>>(
+      (const double *)ctx->d_lf_packed.p, (double *)ctx->d_lf_packed2.p,
+      (const double *)ctx->d_lf_dtmax.p, (double *)ctx->d_lf_dtmax2.p, (const int *)ctx->d_aux_in.p,
+      count);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->d_lf_packed.p, ctx->d_lf_packed2.p, elems * sizeof(double),
+                     cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_lf_dtmax.p, ctx->d_lf_dtmax2.p, (size_t)count * sizeof(double),
+                     cudaMemcpyDeviceToDevice, ctx->stream));
+  return NBK_OK;
+}
+
+int nbk_lf_begin(nbk_ctx *ctx, int ibegin, int iend) {
+  NEED_LF();
+  if (ibegin < 0 || iend < ibegin || iend > ctx->lf_n)
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_begin: bad range [%d,%d)", ibegin, iend);
+  if (iend == ibegin) return NBK_OK;
+  const size_t cnt = (size_t)(iend - ibegin);
+  fill_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(
+      (double *)ctx->d_lf_dtmax.p + ibegin, cnt, __builtin_inf());
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_lf_drift(nbk_ctx *ctx, int i0, int i1, double dt) {
+  NEED_LF();
+  if (i0 < 0 || i1 < i0 || i1 > ctx->lf_n)
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_drift: bad range [%d,%d)", i0, i1);
+  if (i1 == i0) return NBK_OK;
+  lf_drift_kernel<<<(i1 - i0 + 255) / 256, 256, 0, ctx->stream>>>((double *)ctx->d_lf_packed.p, i0, i1, dt);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_lf_kick_block(nbk_ctx *ctx, int iend, int ibegin, double eta, double dt, int with_tscale,
+                      int with_drift, double drift_after, double *dt_max) {
+  NEED_LF();
+  if (iend < 0 || iend > ctx->lf_n || ibegin < 0 || ibegin > iend)
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_kick_block: bad arguments (ibegin=%d, iend=%d)", ibegin, iend);
+  if (iend == 0 || ibegin == iend) return NBK_OK;
+  const size_t n = (size_t)iend;
+  TRY(reserve(ctx, ctx->d_out[0], 3 * n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[1], n * sizeof(double)));
+  double *o0 = (double *)ctx->d_out[0].p, *o1 = (double *)ctx->d_out[1].p;
+  const double *packed = (const double *)ctx->d_lf_packed.p;
+  auto sweep = [&](int t0, int t1, int s0, int s1) -> int {
+    SweepParams P = base_params(packed, 0.0, t0, t1, s0, s1);
+    P.dt = dt;
+    P.eta = eta;
+    P.out[0] = o0 + 3 * (size_t)t0;
+    P.out[1] = o1 + t0;
+    return with_tscale ? K4T::run(ctx, P, ctx->stream, false) : K4::run(ctx, P, ctx->stream, false);
+  };
+  TRY(sweep(ibegin, iend, 0, iend));                    // active x everybody
+  if (ibegin > 0) TRY(sweep(0, ibegin, ibegin, iend));  // passive x active
+  lf_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      (double *)ctx->d_lf_packed.p, (double *)ctx->d_lf_dtmax.p, o0, with_tscale ? o1 : nullptr,
+      ibegin, iend, with_drift, drift_after);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (with_tscale && dt_max) {
+    CK(cudaMemcpyAsync(ctx->h_lf_stage, ctx->d_lf_dtmax.p, n * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync(ctx));
+    memcpy(dt_max, ctx->h_lf_stage, n * sizeof(double));
+  }
+  return NBK_OK;
 }
 
 // ---- device-resident Omelyan_advancer.OA ---------------------------------------------------------

@@ -1810,6 +1810,53 @@ __global__ void adv_gather_kernel(const double *__restrict__ src, double *__rest
   dst[e] = src[(size_t)perm[row] * AB + c];
 }
 
+// ---- device-resident Leapfrog.b array (leapfrog.ml:5-12): packed rows + dt_max ---------------
+// sort_sub (leapfrog.ml:106-111): rows [0,count) := old rows perm[0..count)
+__global__ void lf_gather_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                 const double *__restrict__ dsrc, double *__restrict__ ddst,
+                                 const int *__restrict__ perm, int count) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)count * PK) return;
+  const int row = (int)(e / PK), c = (int)(e % PK);
+  dst[e] = src[(size_t)perm[row] * PK + c];
+  if (c == 0) ddst[row] = dsrc[perm[row]];
+}
+// drift dt (leapfrog.ml:64-68) on rows [i0, i1)
+__global__ void lf_drift_kernel(double *__restrict__ packed, int i0, int i1, double dt) {
+  int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  double *b = packed + (size_t)i * PK;
+  b[0] = __dadd_rn(b[0], __dmul_rn(dt, b[4]));
+  b[1] = __dadd_rn(b[1], __dmul_rn(dt, b[5]));
+  b[2] = __dadd_rn(b[2], __dmul_rn(dt, b[6]));
+}
+// after a kick block (leapfrog.ml:125-137 for bodies [0, iend), active block [ibegin, iend)):
+// v += dv; dt_max = min(dt_max, tmin) as leapfrog.ml:103-104 writes it, where an active body
+// starts from infinity (the reset of :125-127, which nothing reads before this point); then the
+// second half drift of the active bodies.
+__global__ void lf_apply_kernel(double *__restrict__ packed, double *__restrict__ dt_max,
+                                const double *__restrict__ dv, const double *__restrict__ tmin,
+                                int ibegin, int iend, int with_drift, double drift_after) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= iend) return;
+  double *b = packed + (size_t)i * PK;
+  b[4] = __dadd_rn(b[4], dv[3 * i]);
+  b[5] = __dadd_rn(b[5], dv[3 * i + 1]);
+  b[6] = __dadd_rn(b[6], dv[3 * i + 2]);
+  if (tmin != nullptr) {
+    double d = i >= ibegin ? __longlong_as_double(0x7ff0000000000000LL) : dt_max[i];
+    if (d > tmin[i]) d = tmin[i];
+    dt_max[i] = d;
+  } else if (i >= ibegin) {
+    dt_max[i] = __longlong_as_double(0x7ff0000000000000LL);
+  }
+  if (with_drift && i >= ibegin) {
+    b[0] = __dadd_rn(b[0], __dmul_rn(drift_after, b[4]));
+    b[1] = __dadd_rn(b[1], __dmul_rn(drift_after, b[5]));
+    b[2] = __dadd_rn(b[2], __dmul_rn(drift_after, b[6]));
+  }
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

@@ -37,7 +37,46 @@ struct Leap {
   nbk_ctx *ctx;
   std::vector<LBody> bs;
   std::vector<double> m, q, v, dv, tm;
+  std::vector<int> perm;
   long nkicks = 0;
+  // resident: positions and velocities live on the device in bs order (nbk_lf_*); the host keeps
+  // what the recursion needs (id, t, dt_max, m) and bs[i].q / .v are stale until fetch().
+  bool resident = false;
+
+  int to_device() {
+    const int n = (int)bs.size();
+    pack(n);
+    tm.resize(n);
+    for (int i = 0; i < n; ++i) tm[i] = bs[i].dt_max;
+    NBH_TRY(ck(ctx, nbk_lf_upload(ctx, n, tm.data(), m.data(), q.data(), v.data())));
+    resident = true;
+    return 0;
+  }
+  int fetch() {
+    const int n = (int)bs.size();
+    q.resize(3 * (size_t)n);
+    v.resize(3 * (size_t)n);
+    NBH_TRY(ck(ctx, nbk_lf_download(ctx, nullptr, q.data(), v.data())));
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        bs[i].q[k] = q[3 * i + k];
+        bs[i].v[k] = v[3 * i + k];
+      }
+    resident = false;
+    return 0;
+  }
+  int begin_block(int ibegin, int iend) {  // leapfrog.ml:125-127
+    for (int i = ibegin; i < iend; ++i) bs[i].dt_max = INFINITY;
+    return 0;  // resident: nbk_lf_kick_block resets its active block itself
+  }
+  int drift_block(double dt, int ibegin, int iend) {  // leapfrog.ml:129-131, 137
+    if (resident) {
+      for (int i = ibegin; i < iend; ++i) bs[i].t = bs[i].t + dt;
+      return ck(ctx, nbk_lf_drift(ctx, ibegin, iend, dt));
+    }
+    for (int i = ibegin; i < iend; ++i) drift(dt, bs[i]);
+    return 0;
+  }
 
   void drift(double dt, LBody &b) {  // leapfrog.ml:64-68
     b.t = b.t + dt;
@@ -46,10 +85,24 @@ struct Leap {
     b.q[2] = b.q[2] + dt * b.v[2];
   }
 
-  void sort_sub(int iend) {  // leapfrog.ml:106-111 (Array.fast_sort is stable)
-    std::stable_sort(bs.begin(), bs.begin() + iend, [](const LBody &a, const LBody &b) {
-      return ocaml_compare(a.dt_max, b.dt_max) < 0;
+  int sort_sub(int iend) {  // leapfrog.ml:106-111 (Array.fast_sort is stable)
+    if (!resident) {
+      std::stable_sort(bs.begin(), bs.begin() + iend, [](const LBody &a, const LBody &b) {
+        return ocaml_compare(a.dt_max, b.dt_max) < 0;
+      });
+      return 0;
+    }
+    perm.resize(iend);
+    for (int i = 0; i < iend; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+      return ocaml_compare(bs[a].dt_max, bs[b].dt_max) < 0;
     });
+    bool identity = true;
+    for (int i = 0; i < iend && identity; ++i) identity = perm[i] == i;
+    if (identity) return 0;
+    std::vector<LBody> tmp(bs.begin(), bs.begin() + iend);
+    for (int i = 0; i < iend; ++i) bs[i] = tmp[perm[i]];
+    return ck(ctx, nbk_lf_permute(ctx, iend, perm.data()));
   }
 
   int find_can_advance_index(int iend, double dt) const {  // leapfrog.ml:113-117
@@ -79,12 +132,27 @@ struct Leap {
 
   // for i in [ibegin,iend) for j in [0,i): kick eta dt bs.(i) bs.(j)   (leapfrog.ml:132-136)
   // = targets [ibegin,iend) x sources [0,iend), and targets [0,ibegin) x sources [ibegin,iend).
-  int kick_block(double eta, double dt, int ibegin, int iend) {
+  // drift_after: the half drift that follows the kick (leapfrog.ml:137), fused into the
+  // resident call; the host path drifts in advance_subsystem.
+  int kick_block(double eta, double dt, int ibegin, int iend, bool with_drift = false,
+                 double drift_after = 0.0) {
     if (iend - ibegin <= 0) return 0;
-    pack(iend);
     // eta = infinity makes every pair time-scale inf/NaN, which never lowers dt_max
     // (leapfrog.ml:94-104): skip that half of the kernel.
     const bool ts = !(std::isinf(eta) && eta > 0);
+    if (resident) {
+      tm.resize(iend);
+      NBH_TRY(ck(ctx, nbk_lf_kick_block(ctx, iend, ibegin, eta, dt, ts ? 1 : 0, with_drift ? 1 : 0,
+                                        drift_after,
+                                        ts ? tm.data() : nullptr)));
+      if (ts)
+        for (int i = 0; i < iend; ++i) bs[i].dt_max = tm[i];
+      if (with_drift)
+        for (int i = ibegin; i < iend; ++i) bs[i].t = bs[i].t + drift_after;
+      nkicks += 1;
+      return 0;
+    }
+    pack(iend);
     dv.resize(3 * (size_t)iend);
     tm.resize(iend);
     NBH_TRY(ck(ctx, nbk_kick_block_sum(ctx, iend, ibegin, m.data(), q.data(), v.data(), eta, dt,
@@ -98,14 +166,17 @@ struct Leap {
     if (iend <= 0) return 0;
     const int ibegin = find_can_advance_index(iend, dt);
     const double dt2 = dt / 2.0;
-    for (int i = ibegin; i < iend; ++i) bs[i].dt_max = INFINITY;
+    NBH_TRY(begin_block(ibegin, iend));
     NBH_TRY(advance_subsystem(dt2, eta, ibegin));
-    for (int i = ibegin; i < iend; ++i) drift(dt2, bs[i]);
-    NBH_TRY(kick_block(eta, dt, ibegin, iend));
-    for (int i = ibegin; i < iend; ++i) drift(dt2, bs[i]);
+    NBH_TRY(drift_block(dt2, ibegin, iend));
+    if (resident) {
+      NBH_TRY(kick_block(eta, dt, ibegin, iend, true, dt2));  // kick + second half drift, one call
+    } else {
+      NBH_TRY(kick_block(eta, dt, ibegin, iend));
+      NBH_TRY(drift_block(dt2, ibegin, iend));
+    }
     NBH_TRY(advance_subsystem(dt2, eta, ibegin));
-    sort_sub(iend);
-    return 0;
+    return sort_sub(iend);
   }
 };
 
@@ -149,13 +220,15 @@ int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max
   L.ctx = ctx;
   load(L, n, id, t, dt_max, m, q, v);  // Array.map copy (leapfrog.ml:145)
   for (auto &b : L.bs) b.dt_max = INFINITY;
+  // the bodies stay on the device for the whole advance (nbk_lf_*); a multi-device context
+  // has no resident Leapfrog state and goes through the host-buffer calls
+  if (g_leapfrog_resident && n > 0 && nbk_device_count(ctx) == 1) NBH_TRY(L.to_device());
   // "Kick" the entire system with dt = 0.0 to set up the time-scales (leapfrog.ml:146-155):
   // all pairs i<j == every body against every other.
   NBH_TRY(L.kick_block(eta, 0.0, 0, n));
-  std::stable_sort(L.bs.begin(), L.bs.end(), [](const LBody &a, const LBody &b) {
-    return ocaml_compare(a.dt_max, b.dt_max) < 0;
-  });
+  NBH_TRY(L.sort_sub(n));  // leapfrog.ml:156
   NBH_TRY(L.advance_subsystem(dt, eta, n));
+  if (L.resident) NBH_TRY(L.fetch());
   store(L, id, t, dt_max, m, q, v);
   if (nkicks) *nkicks = L.nkicks;
   return 0;

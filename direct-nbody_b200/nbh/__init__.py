@@ -197,7 +197,10 @@ class LeapfrogState:
         return copy.deepcopy(self)
 
 
-def leapfrog_advance(ctx, s, dt, eta):
+def leapfrog_advance(ctx, s, dt, eta, resident=True):
+    """Leapfrog.advance bs dt eta; resident: bodies stay on the device (nbk_lf_*) for the whole
+    block recursion, else one nbk_kick_block_sum (upload + read-back) per kick block."""
+    load_library().nbh_set_leapfrog_resident(int(resident))
     o = s.copy()
     nk = C.c_long(0)
     _ck(load_library().nbh_leapfrog_advance(ctx._h, len(o.m), _ip(o.id), _p(o.t), _p(o.dt_max),

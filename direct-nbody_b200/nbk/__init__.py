@@ -80,6 +80,12 @@ SYMBOLS = {
     "nbk_adv_get_t": (_i, [_vp, _i, _pd]),
     "nbk_adv_init_first": (_i, [_vp, _d]),
     "nbk_adv_energy": (_i, [_vp, _d, _pd, _pd]),
+    "nbk_lf_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd]),
+    "nbk_lf_download": (_i, [_vp, _pd, _pd, _pd]),
+    "nbk_lf_permute": (_i, [_vp, _i, C.POINTER(_i)]),
+    "nbk_lf_begin": (_i, [_vp, _i, _i]),
+    "nbk_lf_drift": (_i, [_vp, _i, _i, _d]),
+    "nbk_lf_kick_block": (_i, [_vp, _i, _i, _d, _d, _i, _i, _d, _pd]),
     "nbk_oa_upload": (_i, [_vp, _i, _pd, _pd, _pd]),
     "nbk_oa_steps": (_i, [_vp, _d, _d, _i]),
     "nbk_oa_download": (_i, [_vp, _pd, _pd]),

@@ -225,6 +225,32 @@ int nbk_adv_init_first(nbk_ctx *ctx, double eps2);
 /* Energy.energy of the resident bodies */
 int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
 
+/* ---- device-resident Leapfrog.b array (leapfrog.ml:106-158) ---------------------------------- */
+/* The bodies of Leapfrog.advance / advance_subsystem stay on the device in the reference's array
+ * order; the host keeps the block recursion (leapfrog.ml:119-142) - which needs nothing but
+ * dt_max - and calls one function per phase.  Every formula repeats the reference's operation
+ * sequence, so results are bit-identical to the same phases on the host around
+ * nbk_kick_block_sum.  Calls are enqueued; only functions that return data synchronise. */
+int nbk_lf_upload(nbk_ctx *ctx, int n, const double *dt_max, const double *m, const double *q,
+                  const double *v);
+/* any pointer may be NULL */
+int nbk_lf_download(nbk_ctx *ctx, double *dt_max, double *q, double *v);
+/* sort_sub (leapfrog.ml:106-111): new rows [0,count) := old rows perm[0..count) */
+int nbk_lf_permute(nbk_ctx *ctx, int count, const int *perm);
+/* dt_max := infinity on [ibegin, iend)   (leapfrog.ml:125-127).  nbk_lf_kick_block performs
+ * this reset itself for its active block - nothing reads those values in between - so a caller
+ * following advance_subsystem need not call it. */
+int nbk_lf_begin(nbk_ctx *ctx, int ibegin, int iend);
+/* drift dt on bodies [i0, i1)   (leapfrog.ml:64-68; the host adds dt to its own copy of t) */
+int nbk_lf_drift(nbk_ctx *ctx, int i0, int i1, double dt);
+/* The kick loop of advance_subsystem (leapfrog.ml:132-136) as in nbk_kick_block_sum, applied in
+ * place: v += dv; dt_max = min(dt_max, tmin), an active body [ibegin, iend) starting from
+ * infinity (with_tscale = 0: velocities only, the eta = infinity case); then the drift that
+ * follows the kick (leapfrog.ml:137) if with_drift != 0: drift drift_after on the active bodies.
+ * dt_max (may be NULL) receives the updated dt_max[0..iend). */
+int nbk_lf_kick_block(nbk_ctx *ctx, int iend, int ibegin, double eta, double dt, int with_tscale,
+                      int with_drift, double drift_after, double *dt_max);
+
 /* ---- device-resident Omelyan_advancer.OA (omelyan_advancer.ml:44-104) ----------------------- */
 /* The bodies (m, q, p) stay on the device; nbk_oa_steps runs nsteps of OA.advance h
  * (B A C A B: three grad_v sweeps at q, one at q*, omelyan_advancer.ml:96-104) without a host

@@ -158,6 +158,23 @@ def test_leapfrog_initial_timescales_bit_exact(ctx, oracle):
     assert np.array_equal(a.id, b.id)
 
 
+@pytest.mark.parametrize("n,span,eta", [(100, 1.0 / 32, 1e-3), (1500, 1.0 / 64, 2e-3), (1, 0.1, 1e-3),
+                                        (64, 0.0, 1e-3)])
+def test_leapfrog_adaptive_device_resident_is_bit_identical_to_host_path(ctx, oracle, n, span, eta):
+    """Leapfrog.advance with the bodies resident on the device (nbk_lf_*: drifts, kick blocks,
+    dt_max updates and sort moves on the GPU, block recursion on the host) against the
+    host-buffer path (one nbk_kick_block_sum per block): same order, same bits."""
+    m, q, p = (oracle.rescale_to_standard_units(*oracle.make_hot_spherical(n, 5)) if n > 1
+               else oracle.make_hot_spherical(n, 5))
+    a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=True)
+    b = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=False)
+    assert a.nkicks == b.nkicks and np.array_equal(a.id, b.id)
+    assert np.array_equal(a.t, b.t) and np.array_equal(a.dt_max, b.dt_max)
+    assert np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v)
+    if n > 1:
+        assert a.nkicks > 1 or span == 0.0
+
+
 def test_leapfrog_adaptive_energy_error_beside_oracle(ctx, oracle):
     """Leapfrog.advance with block time steps (leapfrog.ml:119-158) on the GPU path beside the
     oracle's sequential-kick run of the same bodies: same elapsed time, energy errors of the same

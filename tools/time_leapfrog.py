@@ -30,3 +30,14 @@ with nbk.Context(0) as ctx:
         dt = time.perf_counter() - t0
         ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
         print(f"host mirror resident={resident}: {1e3 * dt / nst:.3f} ms/step, dE/E = {abs((ke + pe + 0.25) / 0.25):.3e}")
+    # adaptive block steps (Leapfrog.advance): bodies resident on the device vs one
+    # upload + read-back per kick block
+    na = min(n, 4096)
+    m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(na, 20241))
+    span, eta = 1.0 / 256, 5e-3
+    for resident in (True, False):
+        t0 = time.perf_counter()
+        a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=resident)
+        dt = time.perf_counter() - t0
+        print(f"Leapfrog.advance N={na}, span {span:g}, eta {eta:g}, resident={resident}: {a.nkicks} kick "
+              f"blocks in {dt:.3f} s = {1e6 * dt / max(a.nkicks, 1):.1f} us/block")
