@@ -1908,6 +1908,19 @@ int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2
   return K3::run(ctx, P, st, false);
 }
 
+int nbk_dev_kick_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eta, double dt,
+                     int t0, int t1, int s0, int s1, double *d_dv, double *d_tmin, void *stream) {
+  DEV_COMMON();
+  if (!d_dv) return fail(ctx, NBK_ERR_ARG, "null output");
+  SweepParams P = base_params(d_packed, 0.0, t0, t1, s0, s1);
+  P.dt = dt;
+  P.eta = eta;
+  P.out[0] = d_dv;
+  P.out[1] = d_tmin;
+  cudaStream_t st = (cudaStream_t)stream;
+  return d_tmin ? K4T::run(ctx, P, st, false) : K4::run(ctx, P, st, false);
+}
+
 int nbk_dev_pack_aux(nbk_ctx *ctx, int n, const double *d_m, const double *d_dq,
                      const double *d_dp, double *d_aux, void *stream) {
   if (!ctx) return NBK_ERR_ARG;
@@ -2078,6 +2091,21 @@ int nbk_dev_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double e
   P.out[0] = d_phi;
   P.accumulate = accumulate;
   return run_op_peer<OpV>(ctx, P, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_kick_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eta, double dt,
+                          int t0, int t1, int s0, int s1, double *d_dv, double *d_tmin,
+                          void *stream) {
+  SweepParams P;
+  TRY(peer_params(ctx, sh, n_total, 0.0, t0, t1, s0, s1, false, P));
+  if (t1 == t0 || s1 == s0) return NBK_OK;
+  if (!d_dv) return fail(ctx, NBK_ERR_ARG, "null output");
+  P.dt = dt;
+  P.eta = eta;
+  P.out[0] = d_dv;
+  P.out[1] = d_tmin;
+  return d_tmin ? run_op_peer<OpKick<true>>(ctx, P, (cudaStream_t)stream, false)
+                : run_op_peer<OpKick<false>>(ctx, P, (cudaStream_t)stream, false);
 }
 
 int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, int K,

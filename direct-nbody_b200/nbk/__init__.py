@@ -99,6 +99,8 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "nbk_dev_grad_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
     "nbk_dev_v_sum": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nbk_dev_kick_sum": (_i, [_vp, _vp, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nbk_dev_kick_sum_peer": (_i, [_vp, _psh, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nbk_dev_pack_aux": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _i, _i, _vp, _vp,
                                                 _vp]),
@@ -543,3 +545,14 @@ class Context:
         self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sum_tangent_peer(
             self._h, C.byref(shards), n_total, K, eps2, t0, t1, s0, s1, d_gsum_tan, d_dgsum_tan,
             stream or None))
+
+    def dev_kick_sum(self, d_packed, n_total, eta, dt, targets, sources, d_dv, d_tmin=0, stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_kick_sum(self._h, d_packed, n_total, eta, dt, t0, t1, s0, s1,
+                                            d_dv, d_tmin or None, stream or None))
+
+    def dev_kick_sum_peer(self, shards, n_total, eta, dt, targets, sources, d_dv, d_tmin=0,
+                          stream=0):
+        (t0, t1), (s0, s1) = targets, sources
+        self._ck(self._lib.nbk_dev_kick_sum_peer(self._h, C.byref(shards), n_total, eta, dt, t0, t1,
+                                                 s0, s1, d_dv, d_tmin or None, stream or None))

@@ -250,24 +250,22 @@ class PeerRegions:
             self.base[self.plan.rank] = 0
 
 
-class PeerShardedAccJerk:
-    """ShardedAccJerk without the all-gather: step() = publish this rank's rows + ONE sweep
-    kernel that reads remote source tiles over NVLink (nbk_dev_grad_v_dgrad_v_sum_peer)."""
+class _PeerSharded:
+    """Common part of the peer-exchange drivers: this rank's rows in the shared region, the
+    publish step and the shard table of the current row buffer."""
 
-    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None):
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None, K=0):
         import torch
         self.torch, self.plan, self.device, self.ctx, self.group = torch, plan, device, ctx, group
-        self.regions = PeerRegions(plan, ctx, 0, group, exchange)
-        self.g = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
-        self.dg = torch.zeros_like(self.g)
+        self.regions = PeerRegions(plan, ctx, K, group, exchange)
         self.epoch, self.cur = 0, 0
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
-    def load_local(self, m, q, p):
+    def load_local(self, m, q, vel, is_velocity=False):
         """Pack this rank's bodies into the row buffer the NEXT step reads (the one no peer is
-        reading: buffers alternate, see include/nbk.h)."""
+        reading: buffers alternate, see include/nbk.h).  vel = momenta, or velocities."""
         torch, pl = self.torch, self.plan
         self.cur = (self.epoch + 1) % 2
         if pl.count == 0:
@@ -275,23 +273,26 @@ class PeerShardedAccJerk:
         sl = slice(pl.t0, pl.t1)
         d_m = torch.as_tensor(m[sl], dtype=torch.float64).to(self.device).contiguous()
         d_q = torch.as_tensor(q[sl], dtype=torch.float64).to(self.device).contiguous()
-        d_p = torch.as_tensor(p[sl], dtype=torch.float64).to(self.device).contiguous()
-        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+        d_v = torch.as_tensor(vel[sl], dtype=torch.float64).to(self.device).contiguous()
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_v.data_ptr(), is_velocity,
                           self.regions.packed(self.cur)[pl.rank], self._stream())
+        self._local = (d_m, d_v) if not is_velocity else (d_m, d_v * d_m[:, None])  # m, p
         torch.cuda.current_stream(self.device).synchronize()
 
-    def step(self, eps2: float = 0.0):
+    def _publish(self):
+        """New epoch: tell the peers this rank's rows are in place; returns the shard table."""
         pl, rg = self.plan, self.regions
         self.epoch += 1
-        st = self._stream()
         if pl.world > 1:
-            self.ctx.dev_publish(pl.rank, rg.base, self.epoch, st)  # flags sit at offset 0
-        if pl.count:
-            sh = self.ctx.make_shards(pl.rank, pl.shard, rg.packed(self.cur),
-                                      rg.ready_local if pl.world > 1 else 0, self.epoch)
-            self.ctx.dev_grad_v_dgrad_v_sum_peer(sh, pl.n, eps2, (pl.t0, pl.t1), (0, pl.n),
-                                                 self.g.data_ptr(), self.dg.data_ptr(), False, st)
-        return self.g, self.dg
+            self.ctx.dev_publish(pl.rank, rg.base, self.epoch, self._stream())  # flags at offset 0
+        return self.ctx.make_shards(pl.rank, pl.shard, rg.packed(self.cur),
+                                    rg.ready_local if pl.world > 1 else 0, self.epoch)
+
+    def _all_reduce(self, t, op):
+        if self.plan.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=getattr(dist.ReduceOp, op), group=self.group)
+        return t
 
     def close(self):
         self.torch.cuda.synchronize(self.device)
@@ -301,6 +302,81 @@ class PeerShardedAccJerk:
             barrier = lambda: dist.barrier(group=self.group)
             barrier()  # every rank's last sweep has finished reading
         self.regions.close(barrier)
+
+
+class PeerShardedAccJerk(_PeerSharded):
+    """ShardedAccJerk without the all-gather: step() = publish this rank's rows + ONE sweep
+    kernel that reads remote source tiles over NVLink (nbk_dev_grad_v_dgrad_v_sum_peer)."""
+
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None):
+        super().__init__(plan, device, ctx, group, exchange)
+        torch = self.torch
+        self.g = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.dg = torch.zeros_like(self.g)
+
+    def step(self, eps2: float = 0.0):
+        pl = self.plan
+        sh = self._publish()
+        if pl.count:
+            self.ctx.dev_grad_v_dgrad_v_sum_peer(sh, pl.n, eps2, (pl.t0, pl.t1), (0, pl.n),
+                                                 self.g.data_ptr(), self.dg.data_ptr(), False,
+                                                 self._stream())
+        return self.g, self.dg
+
+
+class PeerShardedEnergy(_PeerSharded):
+    """Energy.energy (energy.ml:57-78) of the sharded system: every rank sweeps
+    the potential of its targets over all sources (peer reads), sums its phi and its kinetic
+    energies in a fixed order, and ONE all-reduce of two doubles gives (ke, pe) on every rank.
+    phi stays on the device for per-body diagnostics (analysis.ml:904-919)."""
+
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None):
+        super().__init__(plan, device, ctx, group, exchange)
+        self.phi = self.torch.zeros(max(plan.count, 1), dtype=self.torch.float64, device=device)
+
+    def step(self, eps2: float = 0.0):
+        torch, pl = self.torch, self.plan
+        sh = self._publish()
+        part = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if pl.count:
+            self.ctx.dev_v_sum_peer(sh, pl.n, eps2, (pl.t0, pl.t1), (0, pl.n), self.phi.data_ptr(),
+                                    False, self._stream())
+            d_m, d_p = self._local
+            part[0] = ((d_p * d_p).sum(dim=1) / (2.0 * d_m)).sum()
+            part[1] = 0.5 * self.phi[:pl.count].sum()
+        self._all_reduce(part, "SUM")
+        ke, pe = (float(x) for x in part.tolist())
+        return ke, pe
+
+
+class PeerShardedKick(_PeerSharded):
+    """The all-pairs Leapfrog.kick sweep (leapfrog.ml:151-155, pre-kick order) of the sharded
+    system: dv and the per-body min time-scale for this rank's targets; the global minimum
+    time-scale (the step a shared-step integrator would take) is one all-reduce(min)."""
+
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None):
+        super().__init__(plan, device, ctx, group, exchange)
+        torch = self.torch
+        self.dv = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.tmin = torch.full((max(plan.count, 1),), float("inf"), dtype=torch.float64, device=device)
+
+    def load_local(self, m, q, v):
+        super().load_local(m, q, v, is_velocity=True)
+
+    def step(self, eta: float, dt: float):
+        torch, pl = self.torch, self.plan
+        sh = self._publish()
+        if pl.count:
+            self.ctx.dev_kick_sum_peer(sh, pl.n, eta, dt, (pl.t0, pl.t1), (0, pl.n),
+                                       self.dv.data_ptr(), self.tmin.data_ptr(), self._stream())
+        gmin = torch.full((1,), float("inf"), dtype=torch.float64, device=self.device)
+        if pl.count:
+            ok = self.tmin[:pl.count]
+            ok = ok[~torch.isnan(ok)]
+            if ok.numel():
+                gmin[0] = ok.min()
+        self._all_reduce(gmin, "MIN")
+        return self.dv, self.tmin, float(gmin.item())
 
 
 class PeerShardedTangent:

@@ -313,6 +313,11 @@ int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double
 int nbk_dev_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0, int t1,
                   int s0, int s1, double *d_phi, int accumulate, void *stream);
 
+/* Leapfrog.kick sums on device pointers (packed with velocities): d_dv[3 (t1-t0)], and
+ * d_tmin[t1-t0] unless NULL (the eta = infinity fast path), as nbk_kick_sum. */
+int nbk_dev_kick_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eta, double dt,
+                     int t0, int t1, int s0, int s1, double *d_dv, double *d_tmin, void *stream);
+
 /* Tangent sweep on device pointers (one rank of a sharded DFloat_pushforward force evaluation,
  * BASELINE configs[4]).  d_aux is [K][n_total][8]: direction k's rows {dq, 0, dv, 0} built by
  * nbk_dev_pack_aux (dv = dp / m).  Outputs d_gsum_tan, d_dgsum_tan are [K][3 (t1-t0)]. */
@@ -365,6 +370,9 @@ int nbk_dev_grad_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, dou
                             int t1, int s0, int s1, double *d_gsum, int accumulate, void *stream);
 int nbk_dev_v_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, int t0,
                        int t1, int s0, int s1, double *d_phi, int accumulate, void *stream);
+int nbk_dev_kick_sum_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eta, double dt,
+                          int t0, int t1, int s0, int s1, double *d_dv, double *d_tmin,
+                          void *stream);
 int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, int K,
                                             double eps2, int t0, int t1, int s0, int s1,
                                             double *d_gsum_tan, double *d_dgsum_tan, void *stream);

@@ -125,6 +125,33 @@ def test_virtual_ranks_tangent(ctx, oracle, K):
             ctx.peer_free(b)
 
 
+def test_sharded_energy_and_kick_drivers_world1(ctx, oracle):
+    """PeerShardedEnergy / PeerShardedKick (nbk/sharded.py) on one rank: the peer sweeps, the
+    local reductions and the (trivial) all-reduce against the single-context calls."""
+    import torch
+    from nbk.sharded import PeerShardedEnergy, PeerShardedKick, make_plan
+    n = 3000
+    m, q, p = oracle.make_plummer(n, 20244)
+    dev = torch.device("cuda", 0)
+    plan = make_plan(n, 1, 0, align=128)
+    e = PeerShardedEnergy(plan, dev, ctx)
+    e.load_local(m, q, p)
+    ke, pe = e.step(1e-4)
+    ke_ref, pe_ref = ctx.energy(m, q, p, 1e-4)
+    assert abs(ke - ke_ref) <= 1e-13 * abs(ke_ref) and abs(pe - pe_ref) <= 1e-13 * abs(pe_ref)
+    phi_ref, _ = ctx.v_sum(m, q, 1e-4)
+    assert np.array_equal(e.phi.cpu().numpy(), phi_ref)
+    e.close()
+    v = p / m[:, None]
+    k = PeerShardedKick(plan, dev, ctx)
+    k.load_local(m, q, v)
+    dv, tmin, gmin = k.step(1e-3, 1e-4)
+    dv_ref, tmin_ref = ctx.kick_sum(m, q, v, 1e-3, 1e-4)
+    assert np.array_equal(dv.cpu().numpy(), dv_ref) and np.array_equal(tmin.cpu().numpy(), tmin_ref)
+    assert gmin == tmin_ref.min()
+    k.close()
+
+
 def test_peer_argument_errors(ctx):
     import nbk
     base, _ = ctx.peer_alloc(1 << 20, want_handle=False)

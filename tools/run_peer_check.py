@@ -92,6 +92,34 @@ def main():
         ms_nccl = timed(lambda: a.step(1e-4))
         ms_peer = timed(lambda: b.step(1e-4))
         inter = float(K) * n * (n - 1)
+    if args.tangent == 0:
+        # energy (one all-reduce of two doubles) and kick + global min time-scale over the same
+        # exchange, against this rank's own single-GPU evaluation of the whole system
+        from nbk.sharded import PeerShardedEnergy, PeerShardedKick
+        nn = min(n, 16384)
+        pl2 = make_plan(nn, world, rank, align=128)
+        mm, qq, pp = m[:nn], q[:nn], p[:nn]
+        e = PeerShardedEnergy(pl2, dev, ctx)
+        e.load_local(mm, qq, pp)
+        ke, pe = e.step(1e-4)
+        ke_ref, pe_ref = ctx.energy(mm, qq, pp, 1e-4)
+        ok = ok and abs(ke - ke_ref) <= 1e-12 * abs(ke_ref) and abs(pe - pe_ref) <= 1e-12 * abs(pe_ref)
+        e.close()
+        vv = pp / mm[:, None]
+        k = PeerShardedKick(pl2, dev, ctx)
+        k.load_local(mm, qq, vv)
+        dv, tmin, gmin = k.step(1e-3, 1e-4)
+        dv_ref, tmin_ref = ctx.kick_sum(mm, qq, vv, 1e-3, 1e-4)
+        torch.cuda.synchronize()
+        sl = slice(pl2.t0, pl2.t1)
+        dv_h = dv[:pl2.count].cpu().numpy()
+        rel = np.max(np.linalg.norm(dv_h - dv_ref[sl], axis=1) / np.linalg.norm(dv_ref[sl], axis=1)) if pl2.count else 0.0
+        ok = ok and rel <= 1e-12 and np.array_equal(tmin[:pl2.count].cpu().numpy(), tmin_ref[sl])
+        ok = ok and gmin == float(tmin_ref.min())
+        k.close()
+        if rank == 0:
+            print(f"sharded energy N={nn}: ke {ke:.15e} pe {pe:.15e} (single GPU {ke_ref:.15e} {pe_ref:.15e}); "
+                  f"kick: max rel dv diff {rel:.1e}, tmin bit-exact, global min {gmin:.6e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     b.close()
