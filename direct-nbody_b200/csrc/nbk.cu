@@ -1424,20 +1424,41 @@ int nbk_adv_init_first(nbk_ctx *ctx, double eps2) {
 int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe) {
   NEED_ADV();
   const int n = ctx->adv_n;
-  // Energy.energy needs only (m, q, p): read them back and reuse the host-buffer path
-  std::string buf((size_t)n * AB * sizeof(double), '\0');
-  double *r = reinterpret_cast<double *>(&buf[0]);
-  TRY(nbk_adv_download(ctx, 0, n, r));
-  std::string mb((size_t)n * 7 * sizeof(double), '\0');
-  double *m = reinterpret_cast<double *>(&mb[0]), *q = m + n, *p = q + 3 * (size_t)n;
-  for (int i = 0; i < n; ++i) {
-    m[i] = r[(size_t)i * AB + 1];
-    for (int k = 0; k < 3; ++k) {
-      q[3 * i + k] = r[(size_t)i * AB + 2 + k];
-      p[3 * i + k] = r[(size_t)i * AB + 5 + k];
+  // Energy.energy needs only (m, q, p): taken from the resident records, nothing leaves the
+  // device but the two sums.  Same kernels and summation trees as nbk_energy.
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_out[0], (size_t)n * sizeof(double)));
+  TRY(reserve(ctx, ctx->d_scalar, 64));
+  const double *rec = (const double *)ctx->d_adv.p;
+  double *o = (double *)ctx->d_out[0].p, *sc = (double *)ctx->d_scalar.p;
+  cudaStream_t st = ctx->stream;
+  ctx->h_scalar[0] = ctx->h_scalar[1] = 0.0;
+  if (pe) {
+    adv_pack_full_kernel<<<(n + 255) / 256, 256, 0, st>>>(rec, n, (double *)ctx->d_packed.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (n > 1) {
+      SweepParams P = base_params((const double *)ctx->d_packed.p, eps2, 0, n, 0, n);
+      P.out[0] = o;
+      TRY(K3::run(ctx, P, st, true));
+    } else {
+      CK(cudaMemsetAsync(o, 0, (size_t)n * sizeof(double), st));
     }
+    sum_kernel<<<1, 1024, 0, st>>>(o, n, sc);
+    CK(cudaGetLastError());
+    ctx->launches++;
   }
-  return nbk_energy(ctx, n, m, q, p, eps2, ke, pe);
+  if (ke) {
+    adv_kinetic_kernel<<<(n + 255) / 256, 256, 0, st>>>(rec, n, o);
+    sum_kernel<<<1, 1024, 0, st>>>(o, n, sc + 1);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  CK(cudaMemcpyAsync(ctx->h_scalar, sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TRY(sync(ctx));
+  if (pe) *pe = 0.5 * ctx->h_scalar[0];
+  if (ke) *ke = ctx->h_scalar[1];
+  return NBK_OK;
 }
 
 // ---- device-resident Leapfrog.b array ------------------------------------------------------------

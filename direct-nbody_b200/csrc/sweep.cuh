@@ -822,9 +822,18 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
       // registers (measured: +0.8 % kernel time).
       if (P.ready != nullptr) {
         const int r_lo = P.s0 / P.shard_rows, r_hi = (P.s1 - 1) / P.shard_rows;
+        // A peer that never publishes (it crashed) must not hang this GPU: after 20 s the kernel
+        // traps, which the host sees as a launch failure on its next CUDA call.
+        unsigned long long t_start;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         for (int r = r_lo; r <= r_hi; ++r)  // the owners of sources [s0, s1)
           if (r != P.self_rank)
-            while (ld_acquire_sys(P.ready + r) < P.epoch) __nanosleep(64);
+            while (ld_acquire_sys(P.ready + r) < P.epoch) {
+              __nanosleep(64);
+              unsigned long long t_now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+              if (t_now - t_start > 20000000000ULL) __trap();
+            }
         fence_proxy_async();
       }
     }
@@ -1799,6 +1808,16 @@ __global__ void adv_pack_full_kernel(const double *__restrict__ rec, int n,
   o[1] = make_double2(b[4], m);
   o[2] = make_double2(__ddiv_rn(b[5], m), __ddiv_rn(b[6], m));
   o[3] = make_double2(__ddiv_rn(b[7], m), 0.0);
+}
+
+// ke[i] = |p_i|^2 / (2 m_i) of every record (energy.ml:57-58), the host formula's sequence
+__global__ void adv_kinetic_kernel(const double *__restrict__ rec, int n, double *__restrict__ ke) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *b = rec + (size_t)i * AB;
+  const double x = b[5], y = b[6], z = b[7];
+  const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+  ke[i] = __ddiv_rn(n2, __dmul_rn(2.0, b[1]));
 }
 
 // rows [0, count) := old rows perm[0..count)  (sort_range, advancer.ml:290-297)

@@ -382,7 +382,9 @@ struct AdvResident {
     return sort_prefix(imax);
   }
 
-  int run(int n_, int *id_io, double *state, double dt, double sf) {
+  // energy_out (may be NULL): Energy.energy of the advanced bodies, computed from the resident
+  // records before they are read back (nbk_adv_energy: nothing but two sums leaves the device)
+  int run(int n_, int *id_io, double *state, double dt, double sf, double *energy_out = nullptr) {
     n = n_;
     id.assign(id_io, id_io + n);
     hmax.resize(n);
@@ -408,6 +410,11 @@ struct AdvResident {
     }
     NBH_TRY(sort_prefix(n));  // Array.fast_sort hmax_lt bs
     NBH_TRY(advance_range(n, dt, sf));
+    if (energy_out) {
+      double ke = 0.0, pe = 0.0;
+      NBH_TRY(ck(ctx, nbk_adv_energy(ctx, eps2, &ke, &pe)));
+      *energy_out = ke + pe;
+    }
     recs.resize((size_t)n * NBH_ADV_STRIDE);
     NBH_TRY(ck(ctx, nbk_adv_download(ctx, 0, n, recs.data())));
     for (int i = 0; i < n; ++i) {
@@ -480,6 +487,45 @@ int nbh_constant_sf_integrate(nbk_ctx *ctx, int n, int *id, double *state, doubl
                               double sf, double max_eg_err, double eps2, double *energy_errors,
                               int cap, int *nerr) {
   if (n <= 0) return fail(NBK_ERR_ARG, "constant_sf_integrate: empty body array");
+  if (g_advancer_resident) {
+    // Records resident on the device during each A.advance; the checkpoint energy is taken from
+    // them before they come back (same body order, same kernels and summation trees as the
+    // host-buffer path below, hence the same bits).
+    Adv A0;
+    A0.ctx = ctx;
+    A0.eps2 = eps2;
+    A0.extpot = nullptr;
+    A0.extpot_arg = nullptr;
+    A0.load(n, id, state);
+    double e = 0.0;
+    NBH_TRY(A0.energy(&e));
+    const double stop_t = dt + state[0];
+    std::vector<int> good_id(n);
+    std::vector<double> good((size_t)n * NBH_ADV_STRIDE);
+    int count = 0;
+    for (;;) {
+      std::copy(id, id + n, good_id.begin());
+      std::copy(state, state + (size_t)n * NBH_ADV_STRIDE, good.begin());
+      AdvResident R;
+      R.ctx = ctx;
+      R.eps2 = eps2;
+      double new_e = 0.0;
+      NBH_TRY(R.run(n, id, state, std::fmin(INFINITY, ci), sf, &new_e));
+      const double new_t = state[0];
+      const double eerr = std::fabs((new_e - e) / e);
+      if (energy_errors && count < cap) energy_errors[count] = eerr;
+      ++count;
+      if (eerr > max_eg_err) {  // raise (Eg_err bs): hand back the last good state
+        std::copy(good_id.begin(), good_id.end(), id);
+        std::copy(good.begin(), good.end(), state);
+        if (nerr) *nerr = count;
+        return fail(NBH_ERR_EG, "Integrator.Eg_err: energy error bound exceeded");
+      }
+      if (new_t >= stop_t) break;
+    }
+    if (nerr) *nerr = count;
+    return 0;
+  }
   Adv A;
   A.ctx = ctx;
   A.eps2 = eps2;

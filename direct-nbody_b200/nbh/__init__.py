@@ -308,9 +308,11 @@ class EgErr(RuntimeError):
         self.state, self.errors = state, errors
 
 
-def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0):
+def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0, resident=True):
     """Integrator.Make(B)(Advancer.A).constant_sf_integrate (integrator.ml:58-84).  Returns
-    (final state, energy errors after each step); raises EgErr like the reference."""
+    (final state, energy errors after each step); raises EgErr like the reference.
+    resident: records on the device during each advance, checkpoint energy taken from them."""
+    load_library().nbh_set_advancer_resident(int(resident))
     o = s.copy()
     cap = 4096
     errs = np.zeros(cap)

@@ -312,6 +312,15 @@ def test_integrator_checkpoints_and_eg_err(ctx, oracle):
     with pytest.raises(nbh.EgErr) as ei:
         nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01)
     assert np.all(ei.value.state.t == 0.0) and len(ei.value.errors) == 1
+    # records resident + energy from the resident records == host-buffer path, bit for bit
+    s2, errs2 = nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-2, eps2=0.01,
+                                          resident=False)
+    assert np.array_equal(errs, errs2) and np.array_equal(s1.id, s2.id)
+    assert np.array_equal(s1.state, s2.state, equal_nan=True)
+    with pytest.raises(nbh.EgErr) as ej:
+        nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01,
+                                  resident=False)
+    assert np.array_equal(ej.value.errors, ei.value.errors)
 
 
 def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
