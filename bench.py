@@ -192,17 +192,10 @@ def run_ours(args):
     exchange = args.exchange if world > 1 else "none"
     sh = None
     if exchange == "peer":
-        try:
+        try:  # raises on EVERY rank if any rank cannot allocate or map a region
             sh = PeerShardedAccJerk(plan, dev, ctx)
-            peer_ok = 1
-        except Exception as e:  # no IPC/P2P between these devices: every rank must agree
-            print(f"rank {rank}: peer exchange unavailable ({e})", file=sys.stderr)
-            peer_ok = 0
-        flag = torch.tensor([peer_ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if not flag.item():
-            if sh is not None:
-                sh.close()
+        except RuntimeError as e:
+            print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
             sh, exchange = None, "nccl (peer exchange unavailable)"
     if sh is None:
         sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))

@@ -213,21 +213,38 @@ class PeerRegions:
         self.plan, self.ctx, self.K = plan, ctx, K
         self.total, self.packed_off, self.aux_off = peer_region_layout(plan.shard, K)
         self.base = [0] * plan.world
-        self.base[plan.rank], handle = ctx.peer_alloc(self.total, want_handle=plan.world > 1)
+        self._opened = []
+        self.group = group
         if exchange is None:
             def exchange(obj):
                 import torch.distributed as dist
                 out = [None] * plan.world
                 dist.all_gather_object(out, obj, group=group)
                 return out
-        self._opened = []
+        # Every rank takes part in both exchanges whatever happened to it locally, so that a
+        # rank whose allocation or mapping failed cannot leave the others waiting; the outcome
+        # (all mapped / RuntimeError) is the same on every rank.
+        handle, err = None, None
+        try:
+            self.base[plan.rank], handle = ctx.peer_alloc(self.total, want_handle=plan.world > 1)
+        except Exception as e:  # noqa: BLE001 - reported to every rank below
+            err = f"rank {plan.rank}: {e}"
         if plan.world > 1:
             handles = exchange(handle)
-            for r in range(plan.world):
-                if r != plan.rank:
-                    self.base[r] = ctx.peer_open(handles[r])
-                    self._opened.append(self.base[r])
-        self.group = group
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r in range(plan.world):
+                        if r != plan.rank:
+                            self.base[r] = ctx.peer_open(handles[r])
+                            self._opened.append(self.base[r])
+                except Exception as e:  # noqa: BLE001
+                    err = f"rank {plan.rank}: {e}"
+            errs = [e for e in exchange(err) if e is not None]
+            if errs or any(h is None for h in handles):
+                self.close(barrier=lambda: exchange(None))
+                raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(errs or ["no handle"]))
+        elif err is not None:
+            raise RuntimeError(err)
 
     def packed(self, buf):      # rank -> address of its packed rows in buffer `buf`
         return [b + self.packed_off[buf] for b in self.base]

@@ -158,3 +158,43 @@ def test_two_rank_peer_region_handle_exchange(tmp_path):
         kinds = [k for k, _ in log]
         assert kinds == ["alloc", "open", "close", "free"]  # unmap peers before freeing
         assert log[1] == ("open", other)
+
+
+class _FailingCtx(_FakeCtx):
+    def peer_open(self, handle):
+        if self.rank == 1:
+            raise RuntimeError("cudaIpcOpenMemHandle failed (simulated)")
+        return super().peer_open(handle)
+
+
+def _peer_fail_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbk.sharded import PeerRegions, make_plan
+        ctx = _FailingCtx(rank)
+        try:
+            PeerRegions(make_plan(1000, world, rank, align=128), ctx)
+            outcome = "mapped"
+        except RuntimeError as e:
+            outcome = "error: " + str(e)
+        with open(os.path.join(out_dir, f"fail{rank}.txt"), "w") as f:
+            f.write(outcome + "\n" + repr([k for k, _ in ctx.log]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_region_failure_is_agreed_by_every_rank(tmp_path):
+    """One rank cannot map its peer: BOTH ranks get the RuntimeError (nobody is left waiting in
+    a collective), unmap what they mapped and free their own region - bench.py then falls back
+    to the NCCL all-gather on every rank."""
+    world = 2
+    port = 29350 + os.getpid() % 200
+    mp.spawn(_peer_fail_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        outcome, kinds = open(tmp_path / f"fail{rank}.txt").read().split("\n")
+        assert outcome.startswith("error: peer-memory exchange unavailable") and "rank 1" in outcome
+        kinds = eval(kinds)
+        assert kinds[0] == "alloc" and kinds[-1] == "free"
+        assert kinds.count("open") == kinds.count("close")
