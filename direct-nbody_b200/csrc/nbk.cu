@@ -43,6 +43,8 @@ struct nbk_ctx {
   // resident Advancer.A records
   int adv_n = 0;
   DevBuf d_adv, d_adv2;
+  DevBuf d_adt;  // workspace of the device-side advance_range (nbk_adv_advance_range)
+  bool adt_attr_set = false;
   // resident Leapfrog.b array: packed rows {q, m, v} in array order + dt_max
   int lf_n = 0;
   DevBuf d_lf_packed, d_lf_packed2, d_lf_dtmax, d_lf_dtmax2;
@@ -679,7 +681,7 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
                     &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el, &c->d_lf_packed,
-                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2};
+                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -1418,6 +1420,84 @@ int nbk_adv_init_first(nbk_ctx *ctx, double eps2) {
       (double *)ctx->d_adv.p, n, (const double *)ctx->d_out[0].p, (const double *)ctx->d_out[1].p);
   CK(cudaGetLastError());
   ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_adv_range_max(void) { return ADT_MAX; }
+
+int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double eps2, double *hmax,
+                          int *perm, long long *stats) {
+  NEED_ADV();
+  const int n = ctx->adv_n;
+  if (imax < 1 || imax > n || imax > ADT_MAX || !hmax || !perm || !(dt > 0.0))
+    return fail(ctx, NBK_ERR_ARG, "nbk_adv_advance_range: bad arguments (imax=%d of %d, limit %d, dt=%g)",
+                imax, n, ADT_MAX, dt);
+  // CTA size by n: one slot per thread wherever the chip is wide enough, few resident warps else
+  int T = n <= ctx->sm_count * 128 ? 128 : (n <= ctx->sm_count * 256 ? 256 : 512);
+  int G = std::min(ctx->sm_count, (n + T - 1) / T);
+  if (const char *e = getenv("NBK_ADT_SHAPE")) {  // "threads,ctas": a knob for tests and profiles
+    int t = 0, g = 0;
+    if (sscanf(e, "%d,%d", &t, &g) == 2 && (t == 128 || t == 256 || t == 512) && g >= 1 &&
+        g <= ctx->sm_count) {
+      T = t;
+      G = g;
+    }
+  }
+  // workspace: packed4 [n][4] | tact [ADT_MAX][6] | partial [G][ADT_MAX][3] | hmax, hmax_out
+  // [ADT_MAX] each | out [4] | barrier | map [ADT_MAX] ints
+  const size_t o_tact = (size_t)n * 4, o_part = o_tact + (size_t)ADT_MAX * 6,
+               o_hmax = o_part + (size_t)G * ADT_MAX * 3, o_hout = o_hmax + ADT_MAX,
+               o_out = o_hout + ADT_MAX, o_bar = o_out + 4, o_map = o_bar + 2,
+               total = o_map + ADT_MAX / 2;
+  TRY(reserve(ctx, ctx->d_adt, total * sizeof(double)));
+  double *w = (double *)ctx->d_adt.p;
+  cudaStream_t st = ctx->stream;
+  if (!ctx->adt_attr_set) {
+    CK(cudaFuncSetAttribute(adv_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)ADT_SMEM));
+    ctx->adt_attr_set = true;
+  }
+  CK(cudaMemcpyAsync(w + o_hmax, hmax, (size_t)imax * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(w + o_out, 0, 6 * sizeof(double), st));  // out[4] and the barrier counter
+  AdvTreeParams P;
+  P.rec = (double *)ctx->d_adv.p;
+  P.packed4 = w;
+  P.tact = w + o_tact;
+  P.partial = w + o_part;
+  P.hmax = w + o_hmax;
+  P.hmax_out = w + o_hout;
+  P.out = (long long *)(w + o_out);
+  P.bar = (unsigned long long *)(w + o_bar);
+  P.map = (int *)(w + o_map);
+  P.n = n;
+  P.imax = imax;
+  P.dt = dt;
+  P.sf = sf;
+  P.eps2 = eps2;
+  void *args[] = {&P};
+  CK(cudaLaunchCooperativeKernel((const void *)adv_tree_kernel, dim3(G), dim3(T), args, ADT_SMEM, st));
+  // sort_range's row moves, once: rows [0, imax) := old rows map[0..imax)
+  const size_t elems = (size_t)imax * AB;
+  adv_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(
+      (const double *)ctx->d_adv.p, (double *)ctx->d_adv2.p, P.map, imax);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->d_adv.p, ctx->d_adv2.p, elems * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  ctx->launches += 2;
+  long long out[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(hmax, P.hmax_out, (size_t)imax * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(perm, P.map, (size_t)imax * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out, P.out, sizeof out, cudaMemcpyDeviceToHost, st));
+  TRY(sync(ctx));
+  if (out[2] == -1)
+    return fail(ctx, NBK_ERR_STATE, "nbk_adv_advance_range: block recursion deeper than %d frames",
+                ADT_DEPTH);
+  if (out[2] != 0)
+    return fail(ctx, NBK_ERR_STATE,
+                "nbk_adv_advance_range: empty block at the end of the array (index out of bounds)");
+  if (stats) {
+    stats[0] += out[0];
+    stats[1] += out[1];
+  }
   return NBK_OK;
 }
 

@@ -1673,12 +1673,14 @@ __global__ void unpack_kernel(const double *__restrict__ packed, int n, double *
 // intrinsics (no contraction), so this path is bit-identical to the host mirror.
 constexpr int AB = 35;
 
-// predict_q012 + clear_before_step on rows [imin, imax)  (advancer.ml:143-171)
-__global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, double hnew) {
-  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= imax) return;
-  double *b = rec + (size_t)i * AB;
-  const double h = b[8], m = b[1];
+// Row operations, shared by the per-phase kernels below and by the device-side block recursion
+// (adv_tree_kernel).  Loads go through L2 (ld.global.cg): inside the persistent kernel a row is
+// written and read by different CTAs across grid barriers.
+#define ADV_LD(p) __ldcg(p)
+
+// predict_q012 b hnew; clear_before_step b  (advancer.ml:143-171)
+__device__ __forceinline__ void adv_begin_row(double *b, double hnew) {
+  const double h = ADV_LD(b + 8), m = ADV_LD(b + 1);
   const double hnew2 = __dmul_rn(hnew, hnew), h2 = __dmul_rn(h, h);
   const double hnew3 = __dmul_rn(hnew2, hnew), h3 = __dmul_rn(h2, h);
   const double a0 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(h, hnew)), __dmul_rn(__dmul_rn(8.0, h3), m));
@@ -1694,8 +1696,8 @@ __global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, d
       __dmul_rn(hnew2, __dadd_rn(__dadd_rn(__dmul_rn(3.0, h2), __dmul_rn(__dmul_rn(3.0, h), hnew)), hnew2)),
       __dmul_rn(h3, m));
   for (int k = 0; k < 3; ++k) {
-    const double p = b[5 + k], q = b[2 + k];
-    const double v0 = b[11 + k], v1 = b[14 + k], v2 = b[17 + k];
+    const double p = ADV_LD(b + 5 + k), q = ADV_LD(b + 2 + k);
+    const double v0 = ADV_LD(b + 11 + k), v1 = ADV_LD(b + 14 + k), v2 = ADV_LD(b + 17 + k);
     b[20 + k] = p;
     b[23 + k] = q;
     b[26 + k] = __dsub_rn(
@@ -1709,20 +1711,15 @@ __global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, d
         __dmul_rn(b2, v2));
   }
   b[8] = hnew;
-  b[10] = b[0];
+  b[10] = ADV_LD(b + 0);
   for (int k = 0; k < 3; ++k) b[11 + k] = b[14 + k] = b[17 + k] = b[32 + k] = 0.0;
   b[32] = 1.0;
 }
 
-// predict_position for rows [imin, n) to time t (advancer.ml:173-195), then pack {q, m} for the
-// grad_v sweeps, re-indexed from imin.
-__global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int n, double t,
-                                        double *__restrict__ packed) {
-  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double *b = rec + (size_t)i * AB;
-  if (b[0] != t) {
-    const double dt = __dsub_rn(t, b[10]), h = b[8];
+// predict_position b t (advancer.ml:173-195); returns {q, m} as the two double2 of a packed row
+__device__ __forceinline__ void adv_predict_row(double *b, double t, double2 &xy, double2 &zm) {
+  if (ADV_LD(b + 0) != t) {
+    const double dt = __dsub_rn(t, ADV_LD(b + 10)), h = ADV_LD(b + 8);
     const double h2 = __dmul_rn(h, h);
     const double c0 = __ddiv_rn(
         __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(2.0, dt), dt), __dmul_rn(__dmul_rn(3.0, dt), h)), h2), h2);
@@ -1731,47 +1728,112 @@ __global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int 
     b[32] = c0;
     b[33] = c1;
     b[34] = c2;
-    for (int k = 0; k < 3; ++k)
-      b[2 + k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, b[23 + k]), __dmul_rn(c1, b[26 + k])),
-                           __dmul_rn(c2, b[29 + k]));
+    double q[3];
+    for (int k = 0; k < 3; ++k) {
+      q[k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, ADV_LD(b + 23 + k)), __dmul_rn(c1, ADV_LD(b + 26 + k))),
+                       __dmul_rn(c2, ADV_LD(b + 29 + k)));
+      b[2 + k] = q[k];
+    }
     b[0] = t;
+    xy = make_double2(q[0], q[1]);
+    zm = make_double2(q[2], ADV_LD(b + 1));
+  } else {
+    xy = make_double2(ADV_LD(b + 2), ADV_LD(b + 3));
+    zm = make_double2(ADV_LD(b + 4), ADV_LD(b + 1));
   }
+}
+
+// dVdqK += cK S, cK = vC cs[K]  (advancer.ml:216-234 in per-target form)
+__device__ __forceinline__ void adv_accumulate_row(double *b, double c0, double c1, double c2,
+                                                   const double *s) {
+  for (int k = 0; k < 3; ++k) {
+    b[11 + k] = __dadd_rn(ADV_LD(b + 11 + k), __dmul_rn(c0, s[k]));
+    b[14 + k] = __dadd_rn(ADV_LD(b + 14 + k), __dmul_rn(c1, s[k]));
+    b[17 + k] = __dadd_rn(ADV_LD(b + 17 + k), __dmul_rn(c2, s[k]));
+  }
+}
+
+// finish_body b t (advancer.ml:238-252)
+__device__ __forceinline__ void adv_finish_row(double *b, double t) {
+  const double cp = __ddiv_rn(ADV_LD(b + 8), ADV_LD(b + 1));
+  const double cV0 = cp, cV1 = __dmul_rn(0.5, cp);
+  for (int k = 0; k < 3; ++k) {
+    const double v0 = ADV_LD(b + 11 + k), v1 = ADV_LD(b + 14 + k), v2 = ADV_LD(b + 17 + k),
+                 pi = ADV_LD(b + 20 + k);
+    b[2 + k] = __dsub_rn(__dsub_rn(__dadd_rn(ADV_LD(b + 23 + k), __dmul_rn(cp, pi)), __dmul_rn(cV0, v0)),
+                         __dmul_rn(cV1, v1));
+    b[5 + k] = __dsub_rn(__dsub_rn(__dsub_rn(pi, v0), v1), v2);
+  }
+  b[0] = t;
+}
+
+// h_adaptive sf b (advancer.ml:257-281) -> the body's new hmax.  The operation sequence is the
+// reference's; `**` is CUDA's pow (<= 2 ulp), where the host paths use libm's: hmax only steers
+// comparisons (block membership, sort order), so a last-bit difference changes nothing unless it
+// flips one of them.
+__device__ __forceinline__ double adv_h_adaptive_row(const double *b, double sf) {
+  const double h = ADV_LD(b + 8), m = ADV_LD(b + 1), t = ADV_LD(b + 0);
+  const double dx = __dsub_rn(ADV_LD(b + 2), ADV_LD(b + 29)), dy = __dsub_rn(ADV_LD(b + 3), ADV_LD(b + 30)),
+               dz = __dsub_rn(ADV_LD(b + 4), ADV_LD(b + 31));
+  const double dq =
+      __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+  double dt;
+  if (dq == 0.0) {
+    dt = __dmul_rn(h, 2.01);
+  } else {
+    const double vx = ADV_LD(b + 17), vy = ADV_LD(b + 18), vz = ADV_LD(b + 19);
+    const double nv =
+        __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+    const double a = __ddiv_rn(__ddiv_rn(__dmul_rn(nv, 6.0), h), m);
+    const double a_dq = __dmul_rn(__dmul_rn(__dmul_rn(0.5, h), h), a);
+    const double ratio = __ddiv_rn(a_dq, dq);
+    dt = __dmul_rn(h, pow(__dmul_rn(sf, ratio), 0.3333333));
+  }
+  const double e100 = 100.0 * 2.220446049250313e-16;
+  if (dt < __dadd_rn(__dmul_rn(e100, fabs(t)), e100)) return __dadd_rn(__dmul_rn(e100, t), e100);
+  return dt;
+}
+
+// predict_q012 + clear_before_step on rows [imin, imax)
+__global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, double hnew) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= imax) return;
+  adv_begin_row(rec + (size_t)i * AB, hnew);
+}
+
+// predict_position for rows [imin, n) to time t, then pack {q, m} for the grad_v sweeps,
+// re-indexed from imin.
+__global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int n, double t,
+                                        double *__restrict__ packed) {
+  const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 xy, zm;
+  adv_predict_row(rec + (size_t)i * AB, t, xy, zm);
   double2 *o = reinterpret_cast<double2 *>(packed + (size_t)(i - imin) * PK);
-  o[0] = make_double2(b[2], b[3]);
-  o[1] = make_double2(b[4], b[1]);
+  o[0] = xy;
+  o[1] = zm;
   o[2] = make_double2(0.0, 0.0);
   o[3] = make_double2(0.0, 0.0);
 }
 
-// dVdqK_x += (vC cs_x[K]) S_x for rows [imin, n)  (advancer.ml:216-234 in per-target form)
+// dVdqK_x += (vC cs_x[K]) S_x for rows [imin, n)
 __global__ void adv_accumulate_kernel(double *__restrict__ rec, int imin, int n, double vC,
                                       const double *__restrict__ S) {
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double *b = rec + (size_t)i * AB;
-  const double c0 = __dmul_rn(vC, b[32]), c1 = __dmul_rn(vC, b[33]), c2 = __dmul_rn(vC, b[34]);
-  for (int k = 0; k < 3; ++k) {
-    const double s = S[3 * (size_t)(i - imin) + k];
-    b[11 + k] = __dadd_rn(b[11 + k], __dmul_rn(c0, s));
-    b[14 + k] = __dadd_rn(b[14 + k], __dmul_rn(c1, s));
-    b[17 + k] = __dadd_rn(b[17 + k], __dmul_rn(c2, s));
-  }
+  const double c0 = __dmul_rn(vC, ADV_LD(b + 32)), c1 = __dmul_rn(vC, ADV_LD(b + 33)),
+               c2 = __dmul_rn(vC, ADV_LD(b + 34));
+  const double s[3] = {S[3 * (size_t)(i - imin)], S[3 * (size_t)(i - imin) + 1],
+                       S[3 * (size_t)(i - imin) + 2]};
+  adv_accumulate_row(b, c0, c1, c2, s);
 }
 
-// finish_body on rows [imin, imax)  (advancer.ml:238-252); h_adaptive stays on the host (libm pow)
+// finish_body on rows [imin, imax); on this path h_adaptive stays on the host (libm pow)
 __global__ void adv_finish_kernel(double *__restrict__ rec, int imin, int imax, double t) {
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= imax) return;
-  double *b = rec + (size_t)i * AB;
-  const double cp = __ddiv_rn(b[8], b[1]);
-  const double cV0 = cp, cV1 = __dmul_rn(0.5, cp);
-  for (int k = 0; k < 3; ++k) {
-    const double v0 = b[11 + k], v1 = b[14 + k], v2 = b[17 + k], pi = b[20 + k];
-    b[2 + k] = __dsub_rn(__dsub_rn(__dadd_rn(b[23 + k], __dmul_rn(cp, pi)), __dmul_rn(cV0, v0)),
-                         __dmul_rn(cV1, v1));
-    b[5 + k] = __dsub_rn(__dsub_rn(__dsub_rn(pi, v0), v1), v2);
-  }
-  b[0] = t;
+  adv_finish_row(rec + (size_t)i * AB, t);
 }
 
 // initialize_before_first_step (advancer.ml:357-393): clear, h := 1, then from the all-pairs
@@ -1827,6 +1889,382 @@ __global__ void adv_gather_kernel(const double *__restrict__ src, double *__rest
   if (e >= (size_t)count * AB) return;
   const int row = (int)(e / AB), c = (int)(e % AB);
   dst[e] = src[(size_t)perm[row] * AB + c];
+}
+
+// ---- Advancer.A.advance_range ENTIRELY on the device (advancer.ml:316-350) ---------------------
+// One persistent cooperative kernel runs the block recursion of `advance_range bs imax dt sf None`
+// for a prefix of imax <= ADT_MAX slots: warp 0 of every CTA walks the same explicit frame stack
+// (the decisions depend only on the prefix's hmax, which every CTA mirrors in shared memory), and
+// each interact_bodies is three grid-synchronous phases:
+//   P1  every slot j in [imin, n): predict_q012 + clear (active slots of a step's first
+//       interact), predict_position to t, publish {q, m}                          | grid barrier
+//   P2  A: thread-per-slot, T_j = sum over the ACTIVE slots a != j of the pair term (active
+//          positions broadcast from shared memory); a passive slot is complete and is folded
+//          into its dVdq0..2 at once;
+//       B: the passive slots are cut into one slice per CTA, staged through shared memory;
+//          thread (a, s) sums slice sources s, s+SPLIT, ... for active a, the SPLIT lanes of a
+//          target are combined by a fixed shuffle tree (+ a fixed pass over warps)   | grid barrier
+//   P3  one warp per active slot adds the CTAs' partial sums in a fixed order, folds T_a + R_a
+//       into dVdq0..2 and - after the step's third interact - runs finish_body and h_adaptive.
+// After a step: one more barrier, every CTA reloads the new hmax and sorts its mirror of
+// (hmax, slot -> row) with the stable rank of sort_range (advancer.ml:290-297).  Rows never move
+// inside the kernel; the host applies the final permutation once.  Sums are reproducible run to
+// run (fixed grid, fixed trees); their order differs from the tiled sweeps', so this path agrees
+// with the per-phase path to rounding (1e-13), not bit for bit.
+constexpr int ADT_MAX = 1024;    // largest prefix (and active block) the device recursion takes
+constexpr int ADT_DEPTH = 192;   // frames of the explicit recursion stack
+constexpr int ADT_TS = 512;      // passive sources per shared-memory tile
+
+struct AdvTreeParams {
+  double *rec;                 // [n][AB]
+  double *packed4;             // [n][4]  {q, m} of every slot at the current interact time
+  double *hmax;                // [imax]  in: the prefix's hmax (then the steps' new values in transit)
+  double *hmax_out;            // [imax]  out: hmax in the final slot order
+  int *map;                    // [imax]  out: slot -> row it started in
+  double *tact;                // [ADT_MAX][6]  T_a and the weights vC cs of the active slots
+  double *partial;             // [gridDim.x][ADT_MAX][3]
+  unsigned long long *bar;     // grid barrier counter (zeroed before the launch)
+  long long *out;              // interact_bodies calls, pair interactions, error
+  int n, imax;
+  double dt, sf, eps2;
+};
+struct AdvFrame {
+  int imax, imin, stage, pad;
+  double dt, t0;
+};
+struct AdvCtl {
+  int op, imin, imax, begin, last, pad;
+  double t, vC, hnew;
+};
+constexpr size_t ADT_SMEM = sizeof(double) * (ADT_MAX * 4 + ADT_TS * 4 + 2 * ADT_MAX + 64) +
+                            sizeof(AdvFrame) * ADT_DEPTH + sizeof(int) * 2 * ADT_MAX;
+
+__device__ __forceinline__ void adv_grid_barrier(unsigned long long *bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ULL);
+    unsigned long long v;
+    const long long c0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - c0 > (20LL << 30)) __trap();  // ~10 s: a CTA is missing, do not hang the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double adv_sort_key(double h) { return h != h ? __longlong_as_double(0x7ff0000000000000LL) : h; }
+
+// one pair: target at (x,y,z), source {sx,sy,sz,sm}; acc += sm d / s^3, d = source - target
+__device__ __forceinline__ void adv_pair(double x, double y, double z, double2 sxy, double2 szm,
+                                         double eps2, bool self, double &ax, double &ay, double &az) {
+  const double dx = sxy.x - x, dy = sxy.y - y, dz = szm.x - z;
+  double r2 = fma(dx, dx, eps2);
+  r2 = fma(dy, dy, r2);
+  r2 = fma(dz, dz, r2);
+  double mj = szm.y;
+  r2 = self ? 1.0 : r2;
+  mj = self ? 0.0 : mj;
+  const double yv = rsqrt_nr(r2);
+  const double w = (mj * yv) * (yv * yv);
+  ax = fma(w, dx, ax);
+  ay = fma(w, dy, ay);
+  az = fma(w, dz, az);
+}
+
+__global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P) {
+  extern __shared__ __align__(16) unsigned char adt_smem[];
+  double *xa = reinterpret_cast<double *>(adt_smem);  // active {q, m}
+  double *tile = xa + ADT_MAX * 4;                    // passive source tile
+  double *hs = tile + ADT_TS * 4;                     // hmax of the prefix, slot order
+  double *hs2 = hs + ADT_MAX;
+  double *red = hs2 + ADT_MAX;                        // [16 warps][3]
+  AdvFrame *stack = reinterpret_cast<AdvFrame *>(red + 64);
+  int *ms = reinterpret_cast<int *>(stack + ADT_DEPTH);  // slot -> row
+  int *ms2 = ms + ADT_MAX;
+  __shared__ AdvCtl ctl;
+  __shared__ int s_sp;
+
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, G = gridDim.x;
+  const int gt = blockIdx.x * T + tid, GT = G * T;
+  const int n = P.n, top = P.imax;
+  const double eps2 = P.eps2;
+  unsigned long long nbar = 0;
+  long long n_int = 0, n_pair = 0;
+
+  for (int i = tid; i < top; i += T) {
+    hs[i] = __ldcg(P.hmax + i);
+    ms[i] = i;
+  }
+  if (tid == 0) {
+    stack[0] = AdvFrame{top, 0, 0, 0, P.dt, 0.0};
+    s_sp = 1;
+  }
+  __syncthreads();
+
+  for (;;) {
+    // ---- control: warp 0 walks the frames until the next interact_bodies (lane 0 writes) -----
+    if (tid < 32) {
+      int sp = s_sp, op = 0;
+      while (sp > 0) {
+        __syncwarp();
+        const AdvFrame f = stack[sp - 1];
+        __syncwarp();
+        if (f.stage == 0) {
+          if (hs[f.imax - 1] < f.dt) {  // advancer.ml:317-319: two half steps
+            if (sp >= ADT_DEPTH) { op = -1; break; }
+            if (lane == 0) {
+              stack[sp - 1].stage = 10;
+              stack[sp] = AdvFrame{f.imax, 0, 0, 0, f.dt / 2.0, 0.0};
+            }
+            ++sp;
+            continue;
+          }
+          int imin = 0;  // advancer.ml:321-328, scanned 32 slots at a time from the top
+          for (int hi = f.imax; hi > 0; hi -= 32) {
+            const int i = hi - 1 - lane;
+            const bool stop = i >= 0 && !(f.dt < hs[i]);
+            const unsigned bal = __ballot_sync(0xffffffffu, stop);
+            if (bal) {
+              imin = hi - (__ffs(bal) - 1);
+              break;
+            }
+          }
+          if (imin >= n) { op = -2; break; }  // bs.(imin).t out of bounds (the reference raises)
+          const double t0 =
+              __ldcg(P.rec + (size_t)(imin < top ? ms[imin] : imin) * AB);  // let t0 = bs.(imin).t
+          if (imin > 0 && sp >= ADT_DEPTH) { op = -1; break; }
+          if (lane == 0) {
+            stack[sp - 1].imin = imin;
+            stack[sp - 1].t0 = t0;
+            stack[sp - 1].stage = 1;
+            ctl = AdvCtl{1, imin, f.imax, 1, 0, 0, t0, f.dt / 6.0, f.dt};
+            if (imin > 0) stack[sp] = AdvFrame{imin, 0, 0, 0, f.dt / 2.0, 0.0};
+          }
+          if (imin > 0) ++sp;
+          op = 1;
+          break;
+        } else if (f.stage == 1) {
+          if (f.imin > 0 && sp >= ADT_DEPTH) { op = -1; break; }
+          if (lane == 0) {
+            stack[sp - 1].stage = 2;
+            ctl = AdvCtl{1, f.imin, f.imax, 0, 0, 0, f.t0 + 0.5 * f.dt, 2.0 * f.dt / 3.0, f.dt};
+            if (f.imin > 0) stack[sp] = AdvFrame{f.imin, 0, 0, 0, f.dt / 2.0, 0.0};
+          }
+          if (f.imin > 0) ++sp;
+          op = 1;
+          break;
+        } else if (f.stage == 2) {
+          if (lane == 0) ctl = AdvCtl{1, f.imin, f.imax, 0, 1, 0, f.t0 + f.dt, f.dt / 6.0, f.dt};
+          --sp;
+          op = 1;
+          break;
+        } else if (f.stage == 10) {  // second half step
+          if (sp >= ADT_DEPTH) { op = -1; break; }
+          if (lane == 0) {
+            stack[sp - 1].stage = 11;
+            stack[sp] = AdvFrame{f.imax, 0, 0, 0, f.dt / 2.0, 0.0};
+          }
+          ++sp;
+        } else {
+          --sp;
+        }
+      }
+      if (lane == 0) {
+        s_sp = sp;
+        if (op != 1) ctl.op = op;
+      }
+    }
+    __syncthreads();
+    if (ctl.op != 1) break;
+    const int imin = ctl.imin, imax = ctl.imax, na = imax - imin, np = n - imax;
+    const bool begin = ctl.begin != 0, last = ctl.last != 0;
+    const double t = ctl.t, vC = ctl.vC, hnew = ctl.hnew;
+    n_int += 1;
+    n_pair += (long long)na * (n - imin - 1) - (long long)na * (na - 1) / 2;
+
+    // ---- P1: predictors ------------------------------------------------------------------
+    for (int j = imin + gt; j < n; j += GT) {
+      double *b = P.rec + (size_t)(j < top ? ms[j] : j) * AB;
+      if (begin && j < imax) adv_begin_row(b, hnew);
+      double2 xy, zm;
+      adv_predict_row(b, t, xy, zm);
+      double2 *o = reinterpret_cast<double2 *>(P.packed4 + (size_t)j * 4);
+      o[0] = xy;
+      o[1] = zm;
+    }
+    adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+
+    if (na == 0) continue;  // hmax = dt exactly: an empty block (advancer.ml:321-328), nothing to sum
+
+    // ---- P2 A: every slot against the active block -----------------------------------------
+    {
+      const double2 *src = reinterpret_cast<const double2 *>(P.packed4 + (size_t)imin * 4);
+      for (int e = tid; e < 2 * na; e += T) reinterpret_cast<double2 *>(xa)[e] = __ldcg(src + e);
+    }
+    __syncthreads();
+    for (int j = imin + gt; j < n; j += GT) {
+      const double2 *me = reinterpret_cast<const double2 *>(P.packed4 + (size_t)j * 4);
+      const double2 mxy = __ldcg(me), mzm = __ldcg(me + 1);
+      double ax = 0.0, ay = 0.0, az = 0.0;
+      const int aself = j - imin;  // >= na for a passive slot: never matches
+      const double2 *x2 = reinterpret_cast<const double2 *>(xa);
+#pragma unroll 4
+      for (int a = 0; a < na; ++a)
+        adv_pair(mxy.x, mxy.y, mzm.x, x2[2 * a], x2[2 * a + 1], eps2, a == aself, ax, ay, az);
+      double *b = P.rec + (size_t)(j < top ? ms[j] : j) * AB;
+      const double c0 = __dmul_rn(vC, ADV_LD(b + 32)), c1 = __dmul_rn(vC, ADV_LD(b + 33)),
+                   c2 = __dmul_rn(vC, ADV_LD(b + 34));
+      if (j >= imax) {
+        const double sm = -mzm.y;
+        const double s[3] = {sm * ax, sm * ay, sm * az};
+        adv_accumulate_row(b, c0, c1, c2, s);
+      } else {
+        double *o = P.tact + (size_t)aself * 6;
+        o[0] = ax;
+        o[1] = ay;
+        o[2] = az;
+        o[3] = c0;
+        o[4] = c1;
+        o[5] = c2;
+      }
+    }
+
+    // ---- P2 B: the active block against this CTA's slice of the passive slots --------------
+    const int L = np > 0 ? (np + G - 1) / G : 1;
+    const int Gc = np > 0 ? (np + L - 1) / L : 0;  // CTAs with a non-empty slice
+    if ((int)blockIdx.x < Gc) {
+      const int k0 = imax + blockIdx.x * L, k1 = min(n, k0 + L);
+      for (int a0 = 0; a0 < na; a0 += T) {
+        const int nac = min(T, na - a0);
+        int napad = 1;
+        while (napad < nac) napad <<= 1;
+        const int SPLIT = T / napad;
+        const int al = tid / SPLIT, s = tid - al * SPLIT;
+        const bool live = al < nac;
+        double x = 0.0, y = 0.0, z = 0.0;
+        if (live) {
+          x = xa[4 * (a0 + al)];
+          y = xa[4 * (a0 + al) + 1];
+          z = xa[4 * (a0 + al) + 2];
+        }
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        for (int kt = k0; kt < k1; kt += ADT_TS) {
+          const int cnt = min(ADT_TS, k1 - kt);
+          __syncthreads();
+          const double2 *src = reinterpret_cast<const double2 *>(P.packed4 + (size_t)kt * 4);
+          for (int e = tid; e < 2 * cnt; e += T) reinterpret_cast<double2 *>(tile)[e] = __ldcg(src + e);
+          __syncthreads();
+          if (live) {
+            const double2 *t2 = reinterpret_cast<const double2 *>(tile);
+            for (int k = s; k < cnt; k += SPLIT)
+              adv_pair(x, y, z, t2[2 * k], t2[2 * k + 1], eps2, false, r0, r1, r2);
+          }
+        }
+        const int width = SPLIT < 32 ? SPLIT : 32;
+        for (int off = width >> 1; off > 0; off >>= 1) {
+          r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+          r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+          r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+        }
+        double *po = P.partial + ((size_t)blockIdx.x * ADT_MAX + a0) * 3;
+        if (SPLIT > 32) {  // several warps per target: fixed pass over them
+          __syncthreads();
+          if (lane == 0) {
+            red[3 * (tid >> 5)] = r0;
+            red[3 * (tid >> 5) + 1] = r1;
+            red[3 * (tid >> 5) + 2] = r2;
+          }
+          __syncthreads();
+          if (tid < nac) {
+            const int wpt = SPLIT >> 5;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            for (int w = 0; w < wpt; ++w) {
+              q0 += red[3 * (tid * wpt + w)];
+              q1 += red[3 * (tid * wpt + w) + 1];
+              q2 += red[3 * (tid * wpt + w) + 2];
+            }
+            po[3 * tid] = q0;
+            po[3 * tid + 1] = q1;
+            po[3 * tid + 2] = q2;
+          }
+        } else if (live && s == 0) {
+          po[3 * al] = r0;
+          po[3 * al + 1] = r1;
+          po[3 * al + 2] = r2;
+        }
+      }
+    }
+    adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+
+    // ---- P3: one warp per active slot ------------------------------------------------------
+    for (int a = gt >> 5; a < na; a += GT >> 5) {
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+      for (int c = lane; c < Gc; c += 32) {
+        const double *pi = P.partial + ((size_t)c * ADT_MAX + a) * 3;
+        r0 += __ldcg(pi);
+        r1 += __ldcg(pi + 1);
+        r2 += __ldcg(pi + 2);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+      }
+      if (lane == 0) {
+        double *b = P.rec + (size_t)ms[imin + a] * AB;
+        const double *ta = P.tact + (size_t)a * 6;
+        const double sm = -ADV_LD(b + 1);
+        const double s[3] = {sm * (__ldcg(ta) + r0), sm * (__ldcg(ta + 1) + r1), sm * (__ldcg(ta + 2) + r2)};
+        adv_accumulate_row(b, __ldcg(ta + 3), __ldcg(ta + 4), __ldcg(ta + 5), s);
+        if (last) {  // advancer.ml:339-342
+          adv_finish_row(b, t);
+          P.hmax[imin + a] = adv_h_adaptive_row(b, P.sf);
+        }
+      }
+    }
+    if (last) {
+      adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+      for (int i = imin + tid; i < imax; i += T) hs[i] = __ldcg(P.hmax + i);
+      __syncthreads();
+      // sort_range bs hmax_lt 0 imax (advancer.ml:290-297, 349): stable rank, NaN keyed as +inf
+      int bad = 0;
+      for (int i = tid; i + 1 < imax; i += T) bad |= adv_sort_key(hs[i + 1]) < adv_sort_key(hs[i]);
+      if (__syncthreads_or(bad)) {
+        for (int i = tid; i < imax; i += T) {
+          const double ki = adv_sort_key(hs[i]);
+          int r = 0;
+          for (int k = 0; k < imax; ++k) {
+            const double kk = adv_sort_key(hs[k]);
+            r += (kk < ki || (kk == ki && k < i)) ? 1 : 0;
+          }
+          hs2[r] = hs[i];
+          ms2[r] = ms[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < imax; i += T) {
+          hs[i] = hs2[i];
+          ms[i] = ms2[i];
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < top; i += T) {
+      P.hmax_out[i] = hs[i];
+      P.map[i] = ms[i];
+    }
+    if (tid == 0) {
+      P.out[0] = n_int;
+      P.out[1] = n_pair;
+      P.out[2] = ctl.op;  // 0 done, -1 recursion deeper than ADT_DEPTH, -2 empty block at the array's end
+    }
+  }
 }
 
 // ---- device-resident Leapfrog.b array (leapfrog.ml:5-12): packed rows + dt_max ---------------

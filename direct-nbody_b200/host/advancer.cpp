@@ -303,6 +303,7 @@ struct AdvResident {
   double eps2;
   long n_interact = 0, n_pairs = 0;
   int n = 0;
+  int tree_max = 0;  // prefixes up to this many rows recurse on the device (0: host recursion)
   std::vector<double> hmax, recs;
   std::vector<int> id, perm;
 
@@ -353,7 +354,22 @@ struct AdvResident {
     return 0;
   }
 
+  // advance_range for a prefix that fits the device-side recursion (nbk_adv_advance_range): one
+  // launch runs every block step of the subtree; hmax and ids follow the returned permutation.
+  int advance_range_on_device(int imax, double dt, double sf) {
+    perm.resize(imax);
+    long long st[2] = {0, 0};
+    NBH_TRY(ck(ctx, nbk_adv_advance_range(ctx, imax, dt, sf, eps2, hmax.data(), perm.data(), st)));
+    std::vector<int> i2(imax);
+    for (int i = 0; i < imax; ++i) i2[i] = id[perm[i]];
+    std::copy(i2.begin(), i2.end(), id.begin());
+    n_interact += st[0];
+    n_pairs += st[1];
+    return 0;
+  }
+
   int advance_range(int imax, double dt, double sf) {  // advancer.ml:316-350
+    if (tree_max > 0 && imax <= tree_max) return advance_range_on_device(imax, dt, sf);
     if (hmax[imax - 1] < dt) {
       NBH_TRY(advance_range(imax, dt / 2.0, sf));
       NBH_TRY(advance_range(imax, dt / 2.0, sf));
@@ -428,13 +444,25 @@ struct AdvResident {
   }
 };
 
-int g_advancer_resident = 1;  // 0: host-buffer path (nbk_interact_sum per interact_bodies)
+// 0: host-buffer path (nbk_interact_sum per interact_bodies); 1: records resident, block recursion
+// on the host (bit-identical to 0); 2: records resident and every subtree of the recursion whose
+// prefix fits runs on the device (nbk_adv_advance_range; agrees with 1 to rounding)
+int g_advancer_resident = 2;
+int g_advancer_tree_max = 0;  // 0: automatic
+
+int tree_max_for(int n) {
+  if (g_advancer_resident < 2) return 0;
+  const int cap = nbk_adv_range_max();
+  if (g_advancer_tree_max > 0) return std::min(g_advancer_tree_max, cap);
+  return n <= 8192 ? cap : cap / 2;  // large systems: big blocks are faster through the tiled sweeps
+}
 
 }  // namespace
 
 extern "C" {
 
-void nbh_set_advancer_resident(int on) { g_advancer_resident = on; }
+void nbh_set_advancer_resident(int mode) { g_advancer_resident = mode; }
+void nbh_set_advancer_tree_max(int rows) { g_advancer_tree_max = rows; }
 
 int nbh_advancer_advance(nbk_ctx *ctx, int n, int *id, double *state, double dt, double sf,
                          double eps2, nbh_extpot_fn extpot, void *extpot_arg, long *stats) {
@@ -443,6 +471,7 @@ int nbh_advancer_advance(nbk_ctx *ctx, int n, int *id, double *state, double dt,
     AdvResident R;
     R.ctx = ctx;
     R.eps2 = eps2;
+    R.tree_max = tree_max_for(n);
     NBH_TRY(R.run(n, id, state, dt, sf));
     if (stats) {
       stats[0] = R.n_interact;
@@ -509,6 +538,7 @@ int nbh_constant_sf_integrate(nbk_ctx *ctx, int n, int *id, double *state, doubl
       AdvResident R;
       R.ctx = ctx;
       R.eps2 = eps2;
+      R.tree_max = tree_max_for(n);
       double new_e = 0.0;
       NBH_TRY(R.run(n, id, state, std::fmin(INFINITY, ci), sf, &new_e));
       const double new_t = state[0];

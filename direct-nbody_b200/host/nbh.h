@@ -91,9 +91,14 @@ int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, doub
  * stats (may be NULL) receives {interact_bodies calls, pair interactions evaluated}. */
 #define NBH_ADV_STRIDE 35
 typedef void (*nbh_extpot_fn)(void *arg, double m, const double *q, const double *p, double *gv);
-/* 1 (default): the body records stay resident on the device for the whole advance (nbk_adv_*;
- * used when extpot == NULL); 0: host-buffer path, one nbk_interact_sum per interact_bodies. */
-void nbh_set_advancer_resident(int on);
+/* 2 (default): the body records stay resident on the device for the whole advance (nbk_adv_*;
+ * used when extpot == NULL) and every subtree of advance_range whose prefix fits
+ * (nbk_adv_range_max rows; half of that above 8192 bodies, nbh_set_advancer_tree_max to force)
+ * runs its whole block recursion on the device (nbk_adv_advance_range);
+ * 1: resident records, block recursion on the host - bit-identical to 0;
+ * 0: host-buffer path, one nbk_interact_sum per interact_bodies. */
+void nbh_set_advancer_resident(int mode);
+void nbh_set_advancer_tree_max(int rows); /* 0: automatic */
 int nbh_advancer_advance(nbk_ctx *ctx, int n, int *id, double *state, double dt, double sf,
                          double eps2, nbh_extpot_fn extpot, void *extpot_arg, long *stats);
 /* The field of test/advance_test.ml:39-46 (Plummer, M = 1, eps = 0.1) and its potential energy. */

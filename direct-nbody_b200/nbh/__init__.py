@@ -277,11 +277,14 @@ class AdvancerState:
         return o
 
 
-def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None, resident=True):
+def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None, resident=2, tree_max=0):
     """Advancer.A.advance ?extpot bs dt sf; extpot is None or "plummer_test"
-    (the field of test/advance_test.ml:39-46).  resident: keep the records on the device for
-    the whole advance (default) or ship the bodies per interact_bodies."""
+    (the field of test/advance_test.ml:39-46).  resident: 2 (default) records on the device and
+    the block recursion of every subtree that fits on the device too (nbk_adv_advance_range;
+    tree_max rows, 0 = automatic); 1/True records on the device, recursion on the host; 0/False
+    ship the bodies per interact_bodies (1 and 0 are bit-identical)."""
     load_library().nbh_set_advancer_resident(int(resident))
+    load_library().nbh_set_advancer_tree_max(int(tree_max))
     o = s.copy()
     stats = (C.c_long * 2)(0, 0)
     fn = None
@@ -308,11 +311,13 @@ class EgErr(RuntimeError):
         self.state, self.errors = state, errors
 
 
-def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0, resident=True):
+def constant_sf_integrate(ctx, s, dt, ci=1.0, sf=2e-3, max_eg_err=1e-2, eps2=0.0, resident=2):
     """Integrator.Make(B)(Advancer.A).constant_sf_integrate (integrator.ml:58-84).  Returns
     (final state, energy errors after each step); raises EgErr like the reference.
-    resident: records on the device during each advance, checkpoint energy taken from them."""
+    resident: as in advancer_advance; with 1 or 2 the checkpoint energy is taken from the
+    resident records."""
     load_library().nbh_set_advancer_resident(int(resident))
+    load_library().nbh_set_advancer_tree_max(0)
     o = s.copy()
     cap = 4096
     errs = np.zeros(cap)

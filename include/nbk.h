@@ -224,6 +224,21 @@ int nbk_adv_get_t(nbk_ctx *ctx, int i, double *t);
 int nbk_adv_init_first(nbk_ctx *ctx, double eps2);
 /* Energy.energy of the resident bodies */
 int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
+/* `advance_range bs imax dt sf None` (advancer.ml:316-350) ENTIRELY on the device, for a prefix
+ * of imax <= nbk_adv_range_max() rows of the resident records: one persistent cooperative kernel
+ * runs the block recursion (frame stack, block search, predict_q012, the three interact_bodies
+ * of every block step against ALL rows [imin, n), finish_body, h_adaptive, sort_range) with grid
+ * barriers between the phases - no host round trip per block step.  hmax[imax]: in, the
+ * prefix's hmax (the host's mirror); out, the new hmax in the new row order.  perm[imax]: out,
+ * new row s = old row perm[s] (the device rows have already been moved; the caller applies it to
+ * whatever it keeps per row, e.g. ids).  stats (may be NULL): += {interact_bodies calls, pair
+ * interactions}.  The sums are reproducible run to run but ordered differently from
+ * nbk_adv_interact's, and h_adaptive uses the device's pow (<= 2 ulp) instead of libm's; hmax
+ * only steers comparisons, so the block schedule is the reference's unless such a comparison
+ * is decided in the last bit.  Agreement with the per-phase path: rounding (1e-13), not bits. */
+int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double eps2, double *hmax,
+                          int *perm, long long *stats);
+int nbk_adv_range_max(void);
 
 /* ---- device-resident Leapfrog.b array (leapfrog.ml:106-158) ---------------------------------- */
 /* The bodies of Leapfrog.advance / advance_subsystem stay on the device in the reference's array

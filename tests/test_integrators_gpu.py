@@ -307,10 +307,12 @@ def test_integrator_checkpoints_and_eg_err(ctx, oracle):
     each, Eg_err with the last good state when the bound is exceeded."""
     m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(32, 9))
     s0 = nbh.AdvancerState(m, q, p)
-    s1, errs = nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-2, eps2=0.01)
+    s1, errs = nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-2, eps2=0.01,
+                                         resident=1)
     assert len(errs) == 4 and np.all(s1.t == 0.5) and errs.max() < 1e-4
     with pytest.raises(nbh.EgErr) as ei:
-        nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01)
+        nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01,
+                                  resident=1)
     assert np.all(ei.value.state.t == 0.0) and len(ei.value.errors) == 1
     # records resident + energy from the resident records == host-buffer path, bit for bit
     s2, errs2 = nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-2, eps2=0.01,
@@ -321,6 +323,11 @@ def test_integrator_checkpoints_and_eg_err(ctx, oracle):
         nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-16, eps2=0.01,
                                   resident=False)
     assert np.array_equal(ej.value.errors, ei.value.errors)
+    # default: the block recursion on the device too - same checkpoints, to rounding
+    s3, errs3 = nbh.constant_sf_integrate(ctx, s0, 0.5, ci=0.125, sf=1e-3, max_eg_err=1e-2, eps2=0.01)
+    assert len(errs3) == 4 and np.all(s3.t == 0.5) and np.array_equal(s3.id, s1.id)
+    assert np.allclose(errs3, errs, rtol=1e-4, atol=1e-15)
+    assert rel(s3.q, s1.q) <= 1e-9 and rel(s3.p, s1.p) <= 1e-9
 
 
 def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
@@ -346,8 +353,8 @@ def test_advancer_device_resident_is_bit_identical_to_host_path(ctx, oracle, n, 
     oracle."""
     m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 5))
     eps2 = eps * eps
-    a = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=True)
-    b = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=False)
+    a = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=1)
+    b = nbh.advancer_advance(ctx, nbh.AdvancerState(m, q, p), span, 1e-4, eps2, resident=0)
     c = oracle.advancer_advance(oracle.AdvancerState(m, q, p), span, 1e-4, eps2)
     assert a.stats == b.stats == c.stats
     assert np.array_equal(a.id, b.id) and np.array_equal(a.id, c.id)
@@ -355,6 +362,79 @@ def test_advancer_device_resident_is_bit_identical_to_host_path(ctx, oracle, n, 
     assert np.all(a.t == span)
     assert rel(a.q, c.q) <= 1e-9 and rel(a.p, c.p) <= 1e-9
     # a second advance continues from the carried state (h, hmax, dVdq* all live)
-    a2 = nbh.advancer_advance(ctx, a, span, 1e-4, eps2, resident=True)
-    b2 = nbh.advancer_advance(ctx, b, span, 1e-4, eps2, resident=False)
+    a2 = nbh.advancer_advance(ctx, a, span, 1e-4, eps2, resident=1)
+    b2 = nbh.advancer_advance(ctx, b, span, 1e-4, eps2, resident=0)
     assert np.array_equal(a2.state, b2.state, equal_nan=True) and a2.stats == b2.stats
+
+
+def assert_records_close(a, b, tol=1e-9):
+    """Two Advancer.A record arrays that followed the same block schedule with differently
+    ordered sums: times and step sizes equal, vectors to rounding amplified by the flow; hmax
+    comes out of |q - q2| (a cancellation, advancer.ml:273) and is only compared loosely."""
+    assert np.array_equal(a.id, b.id)
+    sa, sb = a.state, b.state
+    for col in (0, 1, 8, 10):  # t, m, h, t0
+        assert np.array_equal(sa[:, col], sb[:, col]), col
+    assert np.allclose(sa[:, 9], sb[:, 9], rtol=1e-3, atol=0)  # hmax
+    for c0 in range(2, 8, 3):  # q, p
+        assert rel(sa[:, c0:c0 + 3], sb[:, c0:c0 + 3]) <= tol, c0
+    for c0 in list(range(11, 35, 3)):  # dVdq0-2, p0, q0, q1, q2, cs
+        d = np.max(np.abs(sa[:, c0:c0 + 3] - sb[:, c0:c0 + 3]))
+        assert d <= 100 * tol * np.max(np.abs(sb[:, c0:c0 + 3])), (c0, d)
+
+
+@pytest.mark.parametrize("n,span,eps,tree_max", [(10, 1.0, 0.4, 0), (100, 0.25, 0.04, 0),
+                                                 (1024, 1.0 / 64, 0.01, 0), (700, 1.0 / 32, 0.01, 96),
+                                                 (3000, 2.0 ** -16, 0.01, 512)])
+def test_advancer_block_recursion_on_device(ctx, oracle, n, span, eps, tree_max):
+    """nbk_adv_advance_range: advance_range (advancer.ml:316-350) as ONE persistent cooperative
+    kernel for every subtree whose prefix fits (all of it when n <= 1024; below a host-side top
+    of the recursion otherwise / when tree_max forces it).  Same block schedule and order as the
+    host recursion and the oracle, states to rounding, reproducible run to run; a second
+    advance continues from the carried records."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 5))
+    eps2 = eps * eps
+    s0 = nbh.AdvancerState(m, q, p)
+    a = nbh.advancer_advance(ctx, s0, span, 1e-4, eps2, resident=2, tree_max=tree_max)
+    b = nbh.advancer_advance(ctx, s0, span, 1e-4, eps2, resident=1)
+    assert a.stats == b.stats and np.all(a.t == span)
+    assert_records_close(a, b)
+    if n <= 1024:
+        c = oracle.advancer_advance(oracle.AdvancerState(m, q, p), span, 1e-4, eps2)
+        assert a.stats == c.stats and np.array_equal(a.id, c.id)
+        assert rel(a.q, c.q) <= 1e-9 and rel(a.p, c.p) <= 1e-9
+    a_again = nbh.advancer_advance(ctx, s0, span, 1e-4, eps2, resident=2, tree_max=tree_max)
+    assert np.array_equal(a.state, a_again.state, equal_nan=True) and np.array_equal(a.id, a_again.id)
+    a2 = nbh.advancer_advance(ctx, a, span, 1e-4, eps2, resident=2, tree_max=tree_max)
+    b2 = nbh.advancer_advance(ctx, b, span, 1e-4, eps2, resident=1)
+    assert a2.stats == b2.stats and np.all(a2.t == 2 * span)
+    assert_records_close(a2, b2, tol=1e-8)
+
+
+@pytest.mark.parametrize("n,span,tree_max,shape", [(700, 1.0 / 32, 0, "128,2"), (700, 1.0 / 32, 96, "512,1"),
+                                                   (700, 1.0 / 32, 0, "256,3"),
+                                                   (3000, 2.0 ** -16, 512, "256,2")])
+def test_advancer_block_recursion_on_device_forced_grids(ctx, oracle, monkeypatch, n, span, tree_max, shape):
+    """NBK_ADT_SHAPE = "threads,ctas" forces small grids, so that the kernel's multi-pass loops
+    (more slots than threads, active blocks wider than a CTA, passive slices of several
+    shared-memory tiles, several warps per active slot) run at sizes a test can afford."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 5))
+    s0 = nbh.AdvancerState(m, q, p)
+    b = nbh.advancer_advance(ctx, s0, span, 1e-4, 1e-4, resident=1)
+    monkeypatch.setenv("NBK_ADT_SHAPE", shape)
+    a = nbh.advancer_advance(ctx, s0, span, 1e-4, 1e-4, resident=2, tree_max=tree_max)
+    assert a.stats == b.stats and np.all(a.t == span)
+    assert_records_close(a, b)
+
+
+@pytest.mark.parametrize("n", [148 * 128 + 40, 148 * 256 + 40])
+def test_advancer_block_recursion_on_device_wide_grids(ctx, oracle, n):
+    """The 256- and 512-thread shapes of the device recursion (one slot per thread up to
+    148 x 512 rows); subtrees of up to 512 rows under the host's top of the recursion."""
+    m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(n, 20244))
+    s0 = nbh.AdvancerState(m, q, p)
+    span = 2.0 ** -20
+    a = nbh.advancer_advance(ctx, s0, span, 1e-4, 1e-6, resident=2)
+    b = nbh.advancer_advance(ctx, s0, span, 1e-4, 1e-6, resident=1)
+    assert a.stats == b.stats and np.all(a.t == span) and a.stats[0] > 500
+    assert_records_close(a, b)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times Advancer.A.advance (the integrator bin/nbody.ml and bin/el_mass_segregation.ml run) with
 the records resident on the device against the host-buffer path.
-usage: tools/time_advancer.py N span [eps] [two_mass]"""
+usage: [ADV_MODES=2,1,0] [ADV_TREE_MAX=rows] tools/time_advancer.py N span [eps] [two_mass]"""
 import os
 import sys
 import time
@@ -25,9 +25,11 @@ with nbk.Context(0) as ctx:
     e0 = sum(nbh.energy(ctx, m, q, p, eps * eps))
     s0 = nbh.AdvancerState(m, q, p)
     nbh.advancer_advance(ctx, s0, span / 64, 1e-4, eps * eps)  # warm-up
-    for resident in (True, False):
+    modes = [int(x) for x in os.environ.get("ADV_MODES", "2,1,0").split(",")]
+    tree_max = int(os.environ.get("ADV_TREE_MAX", "0"))
+    for resident in modes:  # 2: block recursion on the device, 1: resident records, 0: host buffers
         t0 = time.perf_counter()
-        a = nbh.advancer_advance(ctx, s0, span, 1e-4, eps * eps, resident=resident)
+        a = nbh.advancer_advance(ctx, s0, span, 1e-4, eps * eps, resident=resident, tree_max=tree_max)
         dt = time.perf_counter() - t0
         de = abs((sum(nbh.energy(ctx, a.m, a.q, a.p, eps * eps)) - e0) / e0)
         print(f"N={n} span={span} resident={resident}: {a.stats[0]} interact_bodies calls, "
