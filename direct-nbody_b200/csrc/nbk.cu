@@ -45,6 +45,7 @@ struct nbk_ctx {
   DevBuf d_adv, d_adv2;
   DevBuf d_adt;  // workspace of the device-side advance_range (nbk_adv_advance_range)
   bool adt_attr_set = false;
+  long long adt_prof[11] = {0};  // block steps, 9 per-phase cycle counts of CTA 0, kernel launches
   // resident Leapfrog.b array: packed rows {q, m, v} in array order + dt_max
   int lf_n = 0;
   DevBuf d_lf_packed, d_lf_packed2, d_lf_dtmax, d_lf_dtmax2;
@@ -1443,25 +1444,30 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
       G = g;
     }
   }
-  // workspace: packed4 [n][4] | tact [ADT_MAX][6] | partial [G][ADT_MAX][3] | hmax, hmax_out
-  // [ADT_MAX] each | out [4] | barrier | map [ADT_MAX] ints
-  const size_t o_tact = (size_t)n * 4, o_part = o_tact + (size_t)ADT_MAX * 6,
+  // workspace: column-major records [AB][ld] | packed4 [n][4] | tact [ADT_MAX][6] | partial
+  // [G][ADT_MAX][3] | hmax, hmax_out [ADT_MAX] each | out [16] | barrier | map [ADT_MAX] ints
+  const size_t ld = ((size_t)n + 31) & ~(size_t)31;
+  const size_t o_p4 = (size_t)AB * ld, o_tact = o_p4 + (size_t)n * 4, o_part = o_tact + (size_t)ADT_MAX * 6,
                o_hmax = o_part + (size_t)G * ADT_MAX * 3, o_hout = o_hmax + ADT_MAX,
-               o_out = o_hout + ADT_MAX, o_bar = o_out + 4, o_map = o_bar + 2,
+               o_out = o_hout + ADT_MAX, o_bar = o_out + 16, o_map = o_bar + 2,
                total = o_map + ADT_MAX / 2;
   TRY(reserve(ctx, ctx->d_adt, total * sizeof(double)));
   double *w = (double *)ctx->d_adt.p;
   cudaStream_t st = ctx->stream;
   if (!ctx->adt_attr_set) {
-    CK(cudaFuncSetAttribute(adv_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(adv_tree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)ADT_SMEM));
+    CK(cudaFuncSetAttribute(adv_tree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)ADT_SMEM));
     ctx->adt_attr_set = true;
   }
   CK(cudaMemcpyAsync(w + o_hmax, hmax, (size_t)imax * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(w + o_out, 0, 6 * sizeof(double), st));  // out[4] and the barrier counter
+  CK(cudaMemsetAsync(w + o_out, 0, 18 * sizeof(double), st));  // out[16] and the barrier counter
   AdvTreeParams P;
   P.rec = (double *)ctx->d_adv.p;
-  P.packed4 = w;
+  P.soa = w;
+  P.ld = ld;
+  P.packed4 = w + o_p4;
   P.tact = w + o_tact;
   P.partial = w + o_part;
   P.hmax = w + o_hmax;
@@ -1475,15 +1481,10 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
   P.sf = sf;
   P.eps2 = eps2;
   void *args[] = {&P};
-  CK(cudaLaunchCooperativeKernel((const void *)adv_tree_kernel, dim3(G), dim3(T), args, ADT_SMEM, st));
-  // sort_range's row moves, once: rows [0, imax) := old rows map[0..imax)
-  const size_t elems = (size_t)imax * AB;
-  adv_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(
-      (const double *)ctx->d_adv.p, (double *)ctx->d_adv2.p, P.map, imax);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->d_adv.p, ctx->d_adv2.p, elems * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  ctx->launches += 2;
-  long long out[4] = {0, 0, 0, 0};
+  const void *kern = T <= 256 ? (const void *)adv_tree_kernel<256> : (const void *)adv_tree_kernel<512>;
+  CK(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(T), args, ADT_SMEM, st));
+  ctx->launches++;  // the kernel also writes the rows back in their new order (sort_range's moves)
+  long long out[16] = {0};
   CK(cudaMemcpyAsync(hmax, P.hmax_out, (size_t)imax * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(perm, P.map, (size_t)imax * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(out, P.out, sizeof out, cudaMemcpyDeviceToHost, st));
@@ -1498,6 +1499,15 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
     stats[0] += out[0];
     stats[1] += out[1];
   }
+  for (int k = 0; k < 10; ++k) ctx->adt_prof[k] += out[3 + k];
+  ctx->adt_prof[10] += 1;
+  return NBK_OK;
+}
+
+int nbk_adv_range_profile(nbk_ctx *ctx, long long *prof, int reset) {
+  if (!ctx || !prof) return NBK_ERR_ARG;
+  for (int k = 0; k < 11; ++k) prof[k] = ctx->adt_prof[k];
+  if (reset) for (int k = 0; k < 11; ++k) ctx->adt_prof[k] = 0;
   return NBK_OK;
 }
 

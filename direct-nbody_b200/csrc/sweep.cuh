@@ -1676,11 +1676,25 @@ constexpr int AB = 35;
 // Row operations, shared by the per-phase kernels below and by the device-side block recursion
 // (adv_tree_kernel).  Loads go through L2 (ld.global.cg): inside the persistent kernel a row is
 // written and read by different CTAs across grid barriers.
-#define ADV_LD(p) __ldcg(p)
+// A row is reached through an accessor: AdvRowAoS = record i of the [n][35] array (the layout of
+// the ABI and of the per-phase kernels); AdvRowSoA = column-major copy the persistent kernel
+// works on (field k of row i at base[k*ld + i]: a warp's loads of one field coalesce).
+struct AdvRowAoS {
+  double *b;
+  __device__ __forceinline__ double ld(int k) const { return __ldcg(b + k); }
+  __device__ __forceinline__ void st(int k, double v) const { b[k] = v; }
+};
+struct AdvRowSoA {
+  double *b;
+  size_t fs;
+  __device__ __forceinline__ double ld(int k) const { return __ldcg(b + (size_t)k * fs); }
+  __device__ __forceinline__ void st(int k, double v) const { b[(size_t)k * fs] = v; }
+};
 
 // predict_q012 b hnew; clear_before_step b  (advancer.ml:143-171)
-__device__ __forceinline__ void adv_begin_row(double *b, double hnew) {
-  const double h = ADV_LD(b + 8), m = ADV_LD(b + 1);
+template <class Row>
+__device__ __forceinline__ void adv_begin_row(const Row b, double hnew) {
+  const double h = b.ld(8), m = b.ld(1);
   const double hnew2 = __dmul_rn(hnew, hnew), h2 = __dmul_rn(h, h);
   const double hnew3 = __dmul_rn(hnew2, hnew), h3 = __dmul_rn(h2, h);
   const double a0 = __ddiv_rn(__dmul_rn(hnew3, __dadd_rn(h, hnew)), __dmul_rn(__dmul_rn(8.0, h3), m));
@@ -1696,92 +1710,133 @@ __device__ __forceinline__ void adv_begin_row(double *b, double hnew) {
       __dmul_rn(hnew2, __dadd_rn(__dadd_rn(__dmul_rn(3.0, h2), __dmul_rn(__dmul_rn(3.0, h), hnew)), hnew2)),
       __dmul_rn(h3, m));
   for (int k = 0; k < 3; ++k) {
-    const double p = ADV_LD(b + 5 + k), q = ADV_LD(b + 2 + k);
-    const double v0 = ADV_LD(b + 11 + k), v1 = ADV_LD(b + 14 + k), v2 = ADV_LD(b + 17 + k);
-    b[20 + k] = p;
-    b[23 + k] = q;
-    b[26 + k] = __dsub_rn(
+    const double p = b.ld(5 + k), q = b.ld(2 + k);
+    const double v0 = b.ld(11 + k), v1 = b.ld(14 + k), v2 = b.ld(17 + k);
+    b.st(20 + k, p);
+    b.st(23 + k, q);
+    b.st(26 + k, __dsub_rn(
         __dadd_rn(__dsub_rn(__dadd_rn(q, __ddiv_rn(__dmul_rn(hnew, p), __dmul_rn(2.0, m))),
                             __dmul_rn(a0, v0)),
                   __dmul_rn(a1, v1)),
-        __dmul_rn(a2, v2));
-    b[29 + k] = __dsub_rn(
+        __dmul_rn(a2, v2)));
+    b.st(29 + k, __dsub_rn(
         __dadd_rn(__dsub_rn(__dadd_rn(q, __ddiv_rn(__dmul_rn(hnew, p), m)), __dmul_rn(b0, v0)),
                   __dmul_rn(b1, v1)),
-        __dmul_rn(b2, v2));
+        __dmul_rn(b2, v2)));
   }
-  b[8] = hnew;
-  b[10] = ADV_LD(b + 0);
-  for (int k = 0; k < 3; ++k) b[11 + k] = b[14 + k] = b[17 + k] = b[32 + k] = 0.0;
-  b[32] = 1.0;
+  b.st(8, hnew);
+  b.st(10, b.ld(0));
+  for (int k = 0; k < 3; ++k) {
+    b.st(11 + k, 0.0);
+    b.st(14 + k, 0.0);
+    b.st(17 + k, 0.0);
+    b.st(32 + k, 0.0);
+  }
+  b.st(32, 1.0);
 }
 
 // predict_position b t (advancer.ml:173-195); returns {q, m} as the two double2 of a packed row
-__device__ __forceinline__ void adv_predict_row(double *b, double t, double2 &xy, double2 &zm) {
-  if (ADV_LD(b + 0) != t) {
-    const double dt = __dsub_rn(t, ADV_LD(b + 10)), h = ADV_LD(b + 8);
+template <class Row>
+__device__ __forceinline__ void adv_predict_row(const Row b, double t, double2 &xy, double2 &zm) {
+  // every load the usual branch needs is issued up front: one trip to L2 instead of three
+  const double told = b.ld(0), t0 = b.ld(10), h = b.ld(8), m = b.ld(1);
+  double q0[3], q1[3], q2[3];
+  for (int k = 0; k < 3; ++k) {
+    q0[k] = b.ld(23 + k);
+    q1[k] = b.ld(26 + k);
+    q2[k] = b.ld(29 + k);
+  }
+  if (told != t) {
+    const double dt = __dsub_rn(t, t0);
     const double h2 = __dmul_rn(h, h);
     const double c0 = __ddiv_rn(
         __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(2.0, dt), dt), __dmul_rn(__dmul_rn(3.0, dt), h)), h2), h2);
     const double c1 = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, dt), __dsub_rn(h, dt)), h2);
     const double c2 = __ddiv_rn(__dmul_rn(dt, __dsub_rn(__dmul_rn(2.0, dt), h)), h2);
-    b[32] = c0;
-    b[33] = c1;
-    b[34] = c2;
+    b.st(32, c0);
+    b.st(33, c1);
+    b.st(34, c2);
     double q[3];
     for (int k = 0; k < 3; ++k) {
-      q[k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, ADV_LD(b + 23 + k)), __dmul_rn(c1, ADV_LD(b + 26 + k))),
-                       __dmul_rn(c2, ADV_LD(b + 29 + k)));
-      b[2 + k] = q[k];
+      q[k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, q0[k]), __dmul_rn(c1, q1[k])), __dmul_rn(c2, q2[k]));
+      b.st(2 + k, q[k]);
     }
-    b[0] = t;
+    b.st(0, t);
     xy = make_double2(q[0], q[1]);
-    zm = make_double2(q[2], ADV_LD(b + 1));
+    zm = make_double2(q[2], m);
   } else {
-    xy = make_double2(ADV_LD(b + 2), ADV_LD(b + 3));
-    zm = make_double2(ADV_LD(b + 4), ADV_LD(b + 1));
+    xy = make_double2(b.ld(2), b.ld(3));
+    zm = make_double2(b.ld(4), m);
   }
 }
 
 // dVdqK += cK S, cK = vC cs[K]  (advancer.ml:216-234 in per-target form)
-__device__ __forceinline__ void adv_accumulate_row(double *b, double c0, double c1, double c2,
+template <class Row>
+__device__ __forceinline__ void adv_accumulate_row(const Row b, double c0, double c1, double c2,
                                                    const double *s) {
   for (int k = 0; k < 3; ++k) {
-    b[11 + k] = __dadd_rn(ADV_LD(b + 11 + k), __dmul_rn(c0, s[k]));
-    b[14 + k] = __dadd_rn(ADV_LD(b + 14 + k), __dmul_rn(c1, s[k]));
-    b[17 + k] = __dadd_rn(ADV_LD(b + 17 + k), __dmul_rn(c2, s[k]));
+    b.st(11 + k, __dadd_rn(b.ld(11 + k), __dmul_rn(c0, s[k])));
+    b.st(14 + k, __dadd_rn(b.ld(14 + k), __dmul_rn(c1, s[k])));
+    b.st(17 + k, __dadd_rn(b.ld(17 + k), __dmul_rn(c2, s[k])));
   }
 }
 
-// finish_body b t (advancer.ml:238-252)
-__device__ __forceinline__ void adv_finish_row(double *b, double t) {
-  const double cp = __ddiv_rn(ADV_LD(b + 8), ADV_LD(b + 1));
+// the same with the nine accumulators already in registers (loaded ahead of the pair loop)
+template <class Row>
+__device__ __forceinline__ void adv_accumulate_row_pre(const Row b, const double *v, double c0,
+                                                       double c1, double c2, const double *s) {
+  for (int k = 0; k < 3; ++k) {
+    b.st(11 + k, __dadd_rn(v[k], __dmul_rn(c0, s[k])));
+    b.st(14 + k, __dadd_rn(v[3 + k], __dmul_rn(c1, s[k])));
+    b.st(17 + k, __dadd_rn(v[6 + k], __dmul_rn(c2, s[k])));
+  }
+}
+
+// finish_body (advancer.ml:238-252) on values: v = dVdq0..2 (9), p0, q0 -> q, p
+__device__ __forceinline__ void adv_finish_vals(double h, double m, const double *v, const double *p0,
+                                                const double *q0, double *q, double *p) {
+  const double cp = __ddiv_rn(h, m);
   const double cV0 = cp, cV1 = __dmul_rn(0.5, cp);
   for (int k = 0; k < 3; ++k) {
-    const double v0 = ADV_LD(b + 11 + k), v1 = ADV_LD(b + 14 + k), v2 = ADV_LD(b + 17 + k),
-                 pi = ADV_LD(b + 20 + k);
-    b[2 + k] = __dsub_rn(__dsub_rn(__dadd_rn(ADV_LD(b + 23 + k), __dmul_rn(cp, pi)), __dmul_rn(cV0, v0)),
-                         __dmul_rn(cV1, v1));
-    b[5 + k] = __dsub_rn(__dsub_rn(__dsub_rn(pi, v0), v1), v2);
+    const double v0 = v[k], v1 = v[3 + k], v2 = v[6 + k], pi = p0[k];
+    q[k] = __dsub_rn(__dsub_rn(__dadd_rn(q0[k], __dmul_rn(cp, pi)), __dmul_rn(cV0, v0)),
+                     __dmul_rn(cV1, v1));
+    p[k] = __dsub_rn(__dsub_rn(__dsub_rn(pi, v0), v1), v2);
   }
-  b[0] = t;
 }
 
-// h_adaptive sf b (advancer.ml:257-281) -> the body's new hmax.  The operation sequence is the
-// reference's; `**` is CUDA's pow (<= 2 ulp), where the host paths use libm's: hmax only steers
-// comparisons (block membership, sort order), so a last-bit difference changes nothing unless it
-// flips one of them.
-__device__ __forceinline__ double adv_h_adaptive_row(const double *b, double sf) {
-  const double h = ADV_LD(b + 8), m = ADV_LD(b + 1), t = ADV_LD(b + 0);
-  const double dx = __dsub_rn(ADV_LD(b + 2), ADV_LD(b + 29)), dy = __dsub_rn(ADV_LD(b + 3), ADV_LD(b + 30)),
-               dz = __dsub_rn(ADV_LD(b + 4), ADV_LD(b + 31));
+// finish_body b t
+template <class Row>
+__device__ __forceinline__ void adv_finish_row(const Row b, double t) {
+  const double h = b.ld(8), m = b.ld(1);
+  double v[9], p0[3], q0[3], q[3], p[3];
+  for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
+  for (int k = 0; k < 3; ++k) {
+    p0[k] = b.ld(20 + k);
+    q0[k] = b.ld(23 + k);
+  }
+  adv_finish_vals(h, m, v, p0, q0, q, p);
+  for (int k = 0; k < 3; ++k) {
+    b.st(2 + k, q[k]);
+    b.st(5 + k, p[k]);
+  }
+  b.st(0, t);
+}
+
+// h_adaptive sf b (advancer.ml:257-281) -> the body's new hmax, on values (v2 = dVdq2).  The
+// operation sequence is the reference's; `**` is CUDA's pow (<= 2 ulp), where the host paths use
+// libm's: hmax only steers comparisons (block membership, sort order), so a last-bit difference
+// changes nothing unless it flips one of them.
+__device__ __forceinline__ double adv_h_adaptive_vals(double h, double m, double t, const double *q,
+                                                      const double *q2, const double *v2, double sf) {
+  const double dx = __dsub_rn(q[0], q2[0]), dy = __dsub_rn(q[1], q2[1]), dz = __dsub_rn(q[2], q2[2]);
   const double dq =
       __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
   double dt;
   if (dq == 0.0) {
     dt = __dmul_rn(h, 2.01);
   } else {
-    const double vx = ADV_LD(b + 17), vy = ADV_LD(b + 18), vz = ADV_LD(b + 19);
+    const double vx = v2[0], vy = v2[1], vz = v2[2];
     const double nv =
         __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
     const double a = __ddiv_rn(__ddiv_rn(__dmul_rn(nv, 6.0), h), m);
@@ -1798,7 +1853,7 @@ __device__ __forceinline__ double adv_h_adaptive_row(const double *b, double sf)
 __global__ void adv_begin_kernel(double *__restrict__ rec, int imin, int imax, double hnew) {
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= imax) return;
-  adv_begin_row(rec + (size_t)i * AB, hnew);
+  adv_begin_row(AdvRowAoS{rec + (size_t)i * AB}, hnew);
 }
 
 // predict_position for rows [imin, n) to time t, then pack {q, m} for the grad_v sweeps,
@@ -1808,7 +1863,7 @@ __global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int 
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 xy, zm;
-  adv_predict_row(rec + (size_t)i * AB, t, xy, zm);
+  adv_predict_row(AdvRowAoS{rec + (size_t)i * AB}, t, xy, zm);
   double2 *o = reinterpret_cast<double2 *>(packed + (size_t)(i - imin) * PK);
   o[0] = xy;
   o[1] = zm;
@@ -1821,9 +1876,8 @@ __global__ void adv_accumulate_kernel(double *__restrict__ rec, int imin, int n,
                                       const double *__restrict__ S) {
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double *b = rec + (size_t)i * AB;
-  const double c0 = __dmul_rn(vC, ADV_LD(b + 32)), c1 = __dmul_rn(vC, ADV_LD(b + 33)),
-               c2 = __dmul_rn(vC, ADV_LD(b + 34));
+  const AdvRowAoS b{rec + (size_t)i * AB};
+  const double c0 = __dmul_rn(vC, b.ld(32)), c1 = __dmul_rn(vC, b.ld(33)), c2 = __dmul_rn(vC, b.ld(34));
   const double s[3] = {S[3 * (size_t)(i - imin)], S[3 * (size_t)(i - imin) + 1],
                        S[3 * (size_t)(i - imin) + 2]};
   adv_accumulate_row(b, c0, c1, c2, s);
@@ -1833,7 +1887,7 @@ __global__ void adv_accumulate_kernel(double *__restrict__ rec, int imin, int n,
 __global__ void adv_finish_kernel(double *__restrict__ rec, int imin, int imax, double t) {
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= imax) return;
-  adv_finish_row(rec + (size_t)i * AB, t);
+  adv_finish_row(AdvRowAoS{rec + (size_t)i * AB}, t);
 }
 
 // initialize_before_first_step (advancer.ml:357-393): clear, h := 1, then from the all-pairs
@@ -1916,7 +1970,9 @@ constexpr int ADT_DEPTH = 192;   // frames of the explicit recursion stack
 constexpr int ADT_TS = 512;      // passive sources per shared-memory tile
 
 struct AdvTreeParams {
-  double *rec;                 // [n][AB]
+  double *rec;                 // [n][AB]  the records (ABI layout): read at entry, rewritten at exit
+  double *soa;                 // [AB][ld] column-major working copy, rows where they started
+  size_t ld;
   double *packed4;             // [n][4]  {q, m} of every slot at the current interact time
   double *hmax;                // [imax]  in: the prefix's hmax (then the steps' new values in transit)
   double *hmax_out;            // [imax]  out: hmax in the final slot order
@@ -1924,7 +1980,9 @@ struct AdvTreeParams {
   double *tact;                // [ADT_MAX][6]  T_a and the weights vC cs of the active slots
   double *partial;             // [gridDim.x][ADT_MAX][3]
   unsigned long long *bar;     // grid barrier counter (zeroed before the launch)
-  long long *out;              // interact_bodies calls, pair interactions, error
+  long long *out;              // [16] interact_bodies calls, pair interactions, error, block steps,
+                               // then CTA 0's clock cycles per phase: control, P1, barrier, P2 A,
+                               // P2 B, barrier, P3, barrier, sort
   int n, imax;
   double dt, sf, eps2;
 };
@@ -1975,7 +2033,8 @@ __device__ __forceinline__ void adv_pair(double x, double y, double z, double2 s
   az = fma(w, dz, az);
 }
 
-__global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P) {
+template <int NTMAX>  // register budget: 255 per thread up to 256 threads, 128 at 512
+__global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams P) {
   extern __shared__ __align__(16) unsigned char adt_smem[];
   double *xa = reinterpret_cast<double *>(adt_smem);  // active {q, m}
   double *tile = xa + ADT_MAX * 4;                    // passive source tile
@@ -1993,7 +2052,14 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
   const int n = P.n, top = P.imax;
   const double eps2 = P.eps2;
   unsigned long long nbar = 0;
-  long long n_int = 0, n_pair = 0;
+  long long n_int = 0, n_pair = 0, n_step = 0;
+  long long cyc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, c_prev = clock64();
+#define ADT_TICK(k)                     \
+  do {                                  \
+    const long long c_now = clock64();  \
+    cyc[k] += c_now - c_prev;           \
+    c_prev = c_now;                     \
+  } while (0)
 
   for (int i = tid; i < top; i += T) {
     hs[i] = __ldcg(P.hmax + i);
@@ -2003,7 +2069,12 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
     stack[0] = AdvFrame{top, 0, 0, 0, P.dt, 0.0};
     s_sp = 1;
   }
-  __syncthreads();
+  const size_t LD = P.ld;
+  for (size_t e = gt; e < (size_t)n * AB; e += GT) {  // records -> column-major working copy
+    const size_t row = e / AB;
+    P.soa[(e - row * AB) * LD + row] = __ldcg(P.rec + e);
+  }
+  adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
 
   for (;;) {
     // ---- control: warp 0 walks the frames until the next interact_bodies (lane 0 writes) -----
@@ -2034,8 +2105,7 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
             }
           }
           if (imin >= n) { op = -2; break; }  // bs.(imin).t out of bounds (the reference raises)
-          const double t0 =
-              __ldcg(P.rec + (size_t)(imin < top ? ms[imin] : imin) * AB);  // let t0 = bs.(imin).t
+          const double t0 = __ldcg(P.soa + (imin < top ? ms[imin] : imin));  // let t0 = bs.(imin).t
           if (imin > 0 && sp >= ADT_DEPTH) { op = -1; break; }
           if (lane == 0) {
             stack[sp - 1].imin = imin;
@@ -2079,16 +2149,18 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
       }
     }
     __syncthreads();
+    ADT_TICK(0);
     if (ctl.op != 1) break;
     const int imin = ctl.imin, imax = ctl.imax, na = imax - imin, np = n - imax;
     const bool begin = ctl.begin != 0, last = ctl.last != 0;
     const double t = ctl.t, vC = ctl.vC, hnew = ctl.hnew;
     n_int += 1;
+    n_step += last ? 1 : 0;
     n_pair += (long long)na * (n - imin - 1) - (long long)na * (na - 1) / 2;
 
     // ---- P1: predictors ------------------------------------------------------------------
     for (int j = imin + gt; j < n; j += GT) {
-      double *b = P.rec + (size_t)(j < top ? ms[j] : j) * AB;
+      const AdvRowSoA b{P.soa + (j < top ? ms[j] : j), LD};
       if (begin && j < imax) adv_begin_row(b, hnew);
       double2 xy, zm;
       adv_predict_row(b, t, xy, zm);
@@ -2096,7 +2168,9 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
       o[0] = xy;
       o[1] = zm;
     }
+    ADT_TICK(1);
     adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+    ADT_TICK(2);
 
     if (na == 0) continue;  // hmax = dt exactly: an empty block (advancer.ml:321-328), nothing to sum
 
@@ -2109,19 +2183,22 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
     for (int j = imin + gt; j < n; j += GT) {
       const double2 *me = reinterpret_cast<const double2 *>(P.packed4 + (size_t)j * 4);
       const double2 mxy = __ldcg(me), mzm = __ldcg(me + 1);
+      const AdvRowSoA b{P.soa + (j < top ? ms[j] : j), LD};
+      const double cs0 = b.ld(32), cs1 = b.ld(33), cs2 = b.ld(34);
+      double v[9];
+      if (j >= imax)
+        for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
       double ax = 0.0, ay = 0.0, az = 0.0;
       const int aself = j - imin;  // >= na for a passive slot: never matches
       const double2 *x2 = reinterpret_cast<const double2 *>(xa);
 #pragma unroll 4
       for (int a = 0; a < na; ++a)
         adv_pair(mxy.x, mxy.y, mzm.x, x2[2 * a], x2[2 * a + 1], eps2, a == aself, ax, ay, az);
-      double *b = P.rec + (size_t)(j < top ? ms[j] : j) * AB;
-      const double c0 = __dmul_rn(vC, ADV_LD(b + 32)), c1 = __dmul_rn(vC, ADV_LD(b + 33)),
-                   c2 = __dmul_rn(vC, ADV_LD(b + 34));
+      const double c0 = __dmul_rn(vC, cs0), c1 = __dmul_rn(vC, cs1), c2 = __dmul_rn(vC, cs2);
       if (j >= imax) {
         const double sm = -mzm.y;
         const double s[3] = {sm * ax, sm * ay, sm * az};
-        adv_accumulate_row(b, c0, c1, c2, s);
+        adv_accumulate_row_pre(b, v, c0, c1, c2, s);
       } else {
         double *o = P.tact + (size_t)aself * 6;
         o[0] = ax;
@@ -2133,6 +2210,7 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
       }
     }
 
+    ADT_TICK(3);
     // ---- P2 B: the active block against this CTA's slice of the passive slots --------------
     const int L = np > 0 ? (np + G - 1) / G : 1;
     const int Gc = np > 0 ? (np + L - 1) / L : 0;  // CTAs with a non-empty slice
@@ -2198,10 +2276,29 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
         }
       }
     }
+    ADT_TICK(4);
     adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+    ADT_TICK(5);
 
     // ---- P3: one warp per active slot ------------------------------------------------------
     for (int a = gt >> 5; a < na; a += GT >> 5) {
+      // lane 0 owns the row: everything it will need is requested before the partial sums, so
+      // the whole fix-up is one trip to L2
+      const AdvRowSoA b{P.soa + ms[imin + a], LD};
+      double ta[6], v[9], p0[3], q0[3], q2[3], m = 0.0, h = 0.0;
+      if (lane == 0) {
+        for (int k = 0; k < 6; ++k) ta[k] = __ldcg(P.tact + (size_t)a * 6 + k);
+        for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
+        m = b.ld(1);
+        if (last) {
+          h = b.ld(8);
+          for (int k = 0; k < 3; ++k) {
+            p0[k] = b.ld(20 + k);
+            q0[k] = b.ld(23 + k);
+            q2[k] = b.ld(29 + k);
+          }
+        }
+      }
       double r0 = 0.0, r1 = 0.0, r2 = 0.0;
       for (int c = lane; c < Gc; c += 32) {
         const double *pi = P.partial + ((size_t)c * ADT_MAX + a) * 3;
@@ -2215,31 +2312,68 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
         r2 += __shfl_xor_sync(0xffffffffu, r2, off);
       }
       if (lane == 0) {
-        double *b = P.rec + (size_t)ms[imin + a] * AB;
-        const double *ta = P.tact + (size_t)a * 6;
-        const double sm = -ADV_LD(b + 1);
-        const double s[3] = {sm * (__ldcg(ta) + r0), sm * (__ldcg(ta + 1) + r1), sm * (__ldcg(ta + 2) + r2)};
-        adv_accumulate_row(b, __ldcg(ta + 3), __ldcg(ta + 4), __ldcg(ta + 5), s);
-        if (last) {  // advancer.ml:339-342
-          adv_finish_row(b, t);
-          P.hmax[imin + a] = adv_h_adaptive_row(b, P.sf);
+        const double sm = -m;
+        const double s[3] = {sm * (ta[0] + r0), sm * (ta[1] + r1), sm * (ta[2] + r2)};
+        for (int k = 0; k < 3; ++k) {  // adv_accumulate_row on the values
+          v[k] = __dadd_rn(v[k], __dmul_rn(ta[3], s[k]));
+          v[3 + k] = __dadd_rn(v[3 + k], __dmul_rn(ta[4], s[k]));
+          v[6 + k] = __dadd_rn(v[6 + k], __dmul_rn(ta[5], s[k]));
+        }
+        for (int k = 0; k < 9; ++k) b.st(11 + k, v[k]);
+        if (last) {  // advancer.ml:339-342: finish_body, h_adaptive
+          double q[3], p[3];
+          adv_finish_vals(h, m, v, p0, q0, q, p);
+          for (int k = 0; k < 3; ++k) {
+            b.st(2 + k, q[k]);
+            b.st(5 + k, p[k]);
+          }
+          b.st(0, t);
+          P.hmax[imin + a] = adv_h_adaptive_vals(h, m, t, q, q2, v + 6, P.sf);
         }
       }
     }
+    ADT_TICK(6);
     if (last) {
       adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+      ADT_TICK(7);
       for (int i = imin + tid; i < imax; i += T) hs[i] = __ldcg(P.hmax + i);
       __syncthreads();
-      // sort_range bs hmax_lt 0 imax (advancer.ml:290-297, 349): stable rank, NaN keyed as +inf
-      int bad = 0;
-      for (int i = tid; i + 1 < imax; i += T) bad |= adv_sort_key(hs[i + 1]) < adv_sort_key(hs[i]);
-      if (__syncthreads_or(bad)) {
+      // sort_range bs hmax_lt 0 imax (advancer.ml:290-297, 349): stable rank, NaN keyed as +inf.
+      // Only the block [imin, imax) has new keys; when the rest of the prefix is still in order
+      // (it is, unless NaNs got in) a slot's rank needs the block's keys and one binary search.
+      int bad = 0, badlow = 0;
+      for (int i = tid; i + 1 < imax; i += T) {
+        const int b1 = adv_sort_key(hs[i + 1]) < adv_sort_key(hs[i]);
+        bad |= b1;
+        badlow |= (i + 1 < imin) ? b1 : 0;
+      }
+      const int flags = __syncthreads_or(bad | (badlow << 1));
+      if (flags & 1) {
         for (int i = tid; i < imax; i += T) {
           const double ki = adv_sort_key(hs[i]);
           int r = 0;
-          for (int k = 0; k < imax; ++k) {
-            const double kk = adv_sort_key(hs[k]);
-            r += (kk < ki || (kk == ki && k < i)) ? 1 : 0;
+          if (!(flags & 2)) {
+            if (i < imin) {  // ties: a slot below the block stays ahead of the block's slots
+              r = i;
+              for (int k = imin; k < imax; ++k) r += adv_sort_key(hs[k]) < ki ? 1 : 0;
+            } else {
+              int lo = 0, hi = imin;  // slots below the block with key <= ki
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (adv_sort_key(hs[mid]) <= ki) lo = mid + 1;
+                else hi = mid;
+              }
+              r = lo;
+              for (int k = imin; k < imax; ++k) {
+                const double kk = adv_sort_key(hs[k]);
+                r += (kk < ki || (kk == ki && k < i)) ? 1 : 0;
+              }
+            }
+          } else {
+            for (int k = 0; k < imax; ++k) {
+              const double kk = adv_sort_key(hs[k]);
+              r += (kk < ki || (kk == ki && k < i)) ? 1 : 0;
+            }
           }
           hs2[r] = hs[i];
           ms2[r] = ms[i];
@@ -2251,9 +2385,17 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
         }
         __syncthreads();
       }
+      ADT_TICK(8);
     }
   }
 
+  // working copy -> records, each row to the slot the sorts gave it (every write above is behind
+  // a grid barrier by now)
+  for (size_t e = gt; e < (size_t)n * AB; e += GT) {
+    const size_t row = e / AB;
+    const size_t src = row < (size_t)top ? (size_t)ms[row] : row;
+    P.rec[e] = __ldcg(P.soa + (e - row * AB) * LD + src);
+  }
   if (blockIdx.x == 0) {
     for (int i = tid; i < top; i += T) {
       P.hmax_out[i] = hs[i];
@@ -2263,6 +2405,8 @@ __global__ void __launch_bounds__(512, 1) adv_tree_kernel(const AdvTreeParams P)
       P.out[0] = n_int;
       P.out[1] = n_pair;
       P.out[2] = ctl.op;  // 0 done, -1 recursion deeper than ADT_DEPTH, -2 empty block at the array's end
+      P.out[3] = n_step;
+      for (int k = 0; k < 9; ++k) P.out[4 + k] = cyc[k];
     }
   }
 }

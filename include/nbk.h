@@ -239,6 +239,10 @@ int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
 int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double eps2, double *hmax,
                           int *perm, long long *stats);
 int nbk_adv_range_max(void);
+/* Diagnostics of nbk_adv_advance_range since the last reset: prof[0] block steps, prof[1..9]
+ * clock cycles CTA 0 spent in {control, predictors, barrier, slot x active sums, active x
+ * passive-slice sums, barrier, fix-up + finish, barrier, sort}, prof[10] kernel launches. */
+int nbk_adv_range_profile(nbk_ctx *ctx, long long *prof, int reset);
 
 /* ---- device-resident Leapfrog.b array (leapfrog.ml:106-158) ---------------------------------- */
 /* The bodies of Leapfrog.advance / advance_subsystem stay on the device in the reference's array

@@ -32,6 +32,15 @@ with nbk.Context(0) as ctx:
         a = nbh.advancer_advance(ctx, s0, span, 1e-4, eps * eps, resident=resident, tree_max=tree_max)
         dt = time.perf_counter() - t0
         de = abs((sum(nbh.energy(ctx, a.m, a.q, a.p, eps * eps)) - e0) / e0)
+        if resident == 2:
+            import ctypes
+            prof = (ctypes.c_longlong * 11)()
+            nbk.load_library().nbk_adv_range_profile(ctx._h, prof, 1)
+            names = ("control", "P1", "bar", "P2A", "P2B", "bar", "P3", "bar", "sort")
+            tot = sum(prof[1:10]) or 1
+            print(f"  device recursion: {prof[10]} launches, {prof[0]} block steps, CTA 0 cycles "
+                  f"{tot / 1.965e3:.0f} us: " +
+                  ", ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof[1:10])))
         print(f"N={n} span={span} resident={resident}: {a.stats[0]} interact_bodies calls, "
               f"{a.stats[1]:.3e} pair interactions in {dt:.3f} s = {1e6 * dt / a.stats[0]:.1f} us/call, "
               f"dE/E = {de:.3e}")
