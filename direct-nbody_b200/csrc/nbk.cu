@@ -1434,7 +1434,8 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
     return fail(ctx, NBK_ERR_ARG, "nbk_adv_advance_range: bad arguments (imax=%d of %d, limit %d, dt=%g)",
                 imax, n, ADT_MAX, dt);
   // CTA size by n: one slot per thread wherever the chip is wide enough, few resident warps else
-  int T = n <= ctx->sm_count * 128 ? 128 : (n <= ctx->sm_count * 256 ? 256 : 512);
+  // (512 threads leave 128 registers per thread and spill; two slots per thread at 256 measured faster)
+  int T = n <= ctx->sm_count * 128 ? 128 : 256;
   int G = std::min(ctx->sm_count, (n + T - 1) / T);
   if (const char *e = getenv("NBK_ADT_SHAPE")) {  // "threads,ctas": a knob for tests and profiles
     int t = 0, g = 0;
@@ -1444,11 +1445,11 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
       G = g;
     }
   }
-  // workspace: column-major records [AB][ld] | packed4 [n][4] | tact [ADT_MAX][6] | partial
-  // [G][ADT_MAX][3] | hmax, hmax_out [ADT_MAX] each | out [16] | barrier | map [ADT_MAX] ints
+  // workspace: column-major records [AB][ld] | tact [2][ADT_MAX][6] | partial [2][G][ADT_MAX][3]
+  // | hmax, hmax_out [ADT_MAX] each | out [16] | barrier | map [ADT_MAX] ints
   const size_t ld = ((size_t)n + 31) & ~(size_t)31;
-  const size_t o_p4 = (size_t)AB * ld, o_tact = o_p4 + (size_t)n * 4, o_part = o_tact + (size_t)ADT_MAX * 6,
-               o_hmax = o_part + (size_t)G * ADT_MAX * 3, o_hout = o_hmax + ADT_MAX,
+  const size_t o_tact = (size_t)AB * ld, o_part = o_tact + 2 * (size_t)ADT_MAX * 6,
+               o_hmax = o_part + 2 * (size_t)G * ADT_MAX * 3, o_hout = o_hmax + ADT_MAX,
                o_out = o_hout + ADT_MAX, o_bar = o_out + 16, o_map = o_bar + 2,
                total = o_map + ADT_MAX / 2;
   TRY(reserve(ctx, ctx->d_adt, total * sizeof(double)));
@@ -1467,7 +1468,6 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
   P.rec = (double *)ctx->d_adv.p;
   P.soa = w;
   P.ld = ld;
-  P.packed4 = w + o_p4;
   P.tact = w + o_tact;
   P.partial = w + o_part;
   P.hmax = w + o_hmax;

@@ -1735,9 +1735,24 @@ __device__ __forceinline__ void adv_begin_row(const Row b, double hnew) {
   b.st(32, 1.0);
 }
 
-// predict_position b t (advancer.ml:173-195); returns {q, m} as the two double2 of a packed row
+// predict_position (advancer.ml:173-195) on values: weights c[3] and q = c0 q0 + c1 q1 + c2 q2
+__device__ __forceinline__ void adv_predict_vals(double t, double t0, double h, const double *q0,
+                                                 const double *q1, const double *q2, double *c,
+                                                 double *q) {
+  const double dt = __dsub_rn(t, t0);
+  const double h2 = __dmul_rn(h, h);
+  c[0] = __ddiv_rn(
+      __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(2.0, dt), dt), __dmul_rn(__dmul_rn(3.0, dt), h)), h2), h2);
+  c[1] = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, dt), __dsub_rn(h, dt)), h2);
+  c[2] = __ddiv_rn(__dmul_rn(dt, __dsub_rn(__dmul_rn(2.0, dt), h)), h2);
+  for (int k = 0; k < 3; ++k)
+    q[k] = __dadd_rn(__dadd_rn(__dmul_rn(c[0], q0[k]), __dmul_rn(c[1], q1[k])), __dmul_rn(c[2], q2[k]));
+}
+
+// predict_position b t; returns {q, m} as the two double2 of a packed row and the row's cs
 template <class Row>
-__device__ __forceinline__ void adv_predict_row(const Row b, double t, double2 &xy, double2 &zm) {
+__device__ __forceinline__ void adv_predict_row(const Row b, double t, double2 &xy, double2 &zm,
+                                                double *cs) {
   // every load the usual branch needs is issued up front: one trip to L2 instead of three
   const double told = b.ld(0), t0 = b.ld(10), h = b.ld(8), m = b.ld(1);
   double q0[3], q1[3], q2[3];
@@ -1747,24 +1762,17 @@ __device__ __forceinline__ void adv_predict_row(const Row b, double t, double2 &
     q2[k] = b.ld(29 + k);
   }
   if (told != t) {
-    const double dt = __dsub_rn(t, t0);
-    const double h2 = __dmul_rn(h, h);
-    const double c0 = __ddiv_rn(
-        __dadd_rn(__dsub_rn(__dmul_rn(__dmul_rn(2.0, dt), dt), __dmul_rn(__dmul_rn(3.0, dt), h)), h2), h2);
-    const double c1 = __ddiv_rn(__dmul_rn(__dmul_rn(4.0, dt), __dsub_rn(h, dt)), h2);
-    const double c2 = __ddiv_rn(__dmul_rn(dt, __dsub_rn(__dmul_rn(2.0, dt), h)), h2);
-    b.st(32, c0);
-    b.st(33, c1);
-    b.st(34, c2);
     double q[3];
+    adv_predict_vals(t, t0, h, q0, q1, q2, cs, q);
     for (int k = 0; k < 3; ++k) {
-      q[k] = __dadd_rn(__dadd_rn(__dmul_rn(c0, q0[k]), __dmul_rn(c1, q1[k])), __dmul_rn(c2, q2[k]));
+      b.st(32 + k, cs[k]);
       b.st(2 + k, q[k]);
     }
     b.st(0, t);
     xy = make_double2(q[0], q[1]);
     zm = make_double2(q[2], m);
   } else {
+    for (int k = 0; k < 3; ++k) cs[k] = b.ld(32 + k);
     xy = make_double2(b.ld(2), b.ld(3));
     zm = make_double2(b.ld(4), m);
   }
@@ -1863,7 +1871,8 @@ __global__ void adv_predict_pack_kernel(double *__restrict__ rec, int imin, int 
   const int i = imin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 xy, zm;
-  adv_predict_row(AdvRowAoS{rec + (size_t)i * AB}, t, xy, zm);
+  double cs[3];
+  adv_predict_row(AdvRowAoS{rec + (size_t)i * AB}, t, xy, zm, cs);
   double2 *o = reinterpret_cast<double2 *>(packed + (size_t)(i - imin) * PK);
   o[0] = xy;
   o[1] = zm;
@@ -1949,17 +1958,20 @@ __global__ void adv_gather_kernel(const double *__restrict__ src, double *__rest
 // One persistent cooperative kernel runs the block recursion of `advance_range bs imax dt sf None`
 // for a prefix of imax <= ADT_MAX slots: warp 0 of every CTA walks the same explicit frame stack
 // (the decisions depend only on the prefix's hmax, which every CTA mirrors in shared memory), and
-// each interact_bodies is three grid-synchronous phases:
-//   P1  every slot j in [imin, n): predict_q012 + clear (active slots of a step's first
-//       interact), predict_position to t, publish {q, m}                          | grid barrier
-//   P2  A: thread-per-slot, T_j = sum over the ACTIVE slots a != j of the pair term (active
-//          positions broadcast from shared memory); a passive slot is complete and is folded
-//          into its dVdq0..2 at once;
-//       B: the passive slots are cut into one slice per CTA, staged through shared memory;
-//          thread (a, s) sums slice sources s, s+SPLIT, ... for active a, the SPLIT lanes of a
-//          target are combined by a fixed shuffle tree (+ a fixed pass over warps)   | grid barrier
-//   P3  one warp per active slot adds the CTAs' partial sums in a fixed order, folds T_a + R_a
+// each interact_bodies is two grid-synchronous phases:
+//   A   every CTA first predicts the ACTIVE block for itself into shared memory (from fields that
+//       are stable during the phase: q at a step's first interact, q0..q2/h/t0 afterwards - the
+//       same formula on the same inputs as the owner's, hence the same bits).  Then thread-per-
+//       slot j in [imin, n): predict_q012 + clear (active slots of a step's first interact),
+//       predict_position to t; T_j = sum over the active slots a != j of the pair term; a
+//       passive slot is complete and is folded into its dVdq0..2 at once.  The passive slots a
+//       CTA owns are also its SOURCE tile (straight from registers to shared memory): thread
+//       (a, s) sums tile sources s, s+SPLIT, ... for active a, the SPLIT lanes of a target are
+//       combined by a fixed shuffle tree (+ a fixed pass over warps)                | grid barrier
+//   B   one warp per active slot adds the CTAs' partial sums in a fixed order, folds T_a + R_a
 //       into dVdq0..2 and - after the step's third interact - runs finish_body and h_adaptive.
+//       No barrier before the next interact's phase A: it touches other fields of these rows,
+//       and the T_a / partial-sum buffers alternate between interacts.
 // After a step: one more barrier, every CTA reloads the new hmax and sorts its mirror of
 // (hmax, slot -> row) with the stable rank of sort_range (advancer.ml:290-297).  Rows never move
 // inside the kernel; the host applies the final permutation once.  Sums are reproducible run to
@@ -1967,18 +1979,17 @@ __global__ void adv_gather_kernel(const double *__restrict__ src, double *__rest
 // with the per-phase path to rounding (1e-13), not bit for bit.
 constexpr int ADT_MAX = 1024;    // largest prefix (and active block) the device recursion takes
 constexpr int ADT_DEPTH = 192;   // frames of the explicit recursion stack
-constexpr int ADT_TS = 512;      // passive sources per shared-memory tile
+constexpr int ADT_TS = 512;      // source tile = one slot per thread of the CTA
 
 struct AdvTreeParams {
   double *rec;                 // [n][AB]  the records (ABI layout): read at entry, rewritten at exit
   double *soa;                 // [AB][ld] column-major working copy, rows where they started
   size_t ld;
-  double *packed4;             // [n][4]  {q, m} of every slot at the current interact time
   double *hmax;                // [imax]  in: the prefix's hmax (then the steps' new values in transit)
   double *hmax_out;            // [imax]  out: hmax in the final slot order
   int *map;                    // [imax]  out: slot -> row it started in
-  double *tact;                // [ADT_MAX][6]  T_a and the weights vC cs of the active slots
-  double *partial;             // [gridDim.x][ADT_MAX][3]
+  double *tact;                // [2][ADT_MAX][6]  T_a and the weights vC cs of the active slots
+  double *partial;             // [2][gridDim.x][ADT_MAX][3]   (buffers alternate between interacts)
   unsigned long long *bar;     // grid barrier counter (zeroed before the launch)
   long long *out;              // [16] interact_bodies calls, pair interactions, error, block steps,
                                // then CTA 0's clock cycles per phase: control, P1, barrier, P2 A,
@@ -1994,7 +2005,7 @@ struct AdvCtl {
   int op, imin, imax, begin, last, pad;
   double t, vC, hnew;
 };
-constexpr size_t ADT_SMEM = sizeof(double) * (ADT_MAX * 4 + ADT_TS * 4 + 2 * ADT_MAX + 64) +
+constexpr size_t ADT_SMEM = sizeof(double) * (ADT_MAX * 4 + ADT_TS * 4 + 2 * ADT_MAX + 64 + ADT_MAX * 3) +
                             sizeof(AdvFrame) * ADT_DEPTH + sizeof(int) * 2 * ADT_MAX;
 
 __device__ __forceinline__ void adv_grid_barrier(unsigned long long *bar, unsigned long long target) {
@@ -2033,6 +2044,62 @@ __device__ __forceinline__ void adv_pair(double x, double y, double z, double2 s
   az = fma(w, dz, az);
 }
 
+// Folds an active slot's sums into its dVdq0..2: T_a (+ weights vC cs) from `ta`, the CTAs'
+// partial sums R_a from part[c * ADT_MAX * 3 + 0..2], c < gc, added in a fixed order by the warp.
+// Lane 0 owns the row: everything it needs is requested before the partial sums, so the fold is
+// one trip to L2.  last: finish_body and h_adaptive follow on the values (advancer.ml:339-342).
+template <class Row>
+__device__ __forceinline__ void adv_fold_row(const Row b, const double *ta_g, const double *part,
+                                             int gc, int lane, bool last, double t, double sf,
+                                             double *hmax_out) {
+  double ta[6], v[9], p0[3], q0[3], q2[3], m = 0.0, h = 0.0;
+  if (lane == 0) {
+    for (int k = 0; k < 6; ++k) ta[k] = __ldcg(ta_g + k);
+    for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
+    m = b.ld(1);
+    if (last) {
+      h = b.ld(8);
+      for (int k = 0; k < 3; ++k) {
+        p0[k] = b.ld(20 + k);
+        q0[k] = b.ld(23 + k);
+        q2[k] = b.ld(29 + k);
+      }
+    }
+  }
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  for (int c = lane; c < gc; c += 32) {
+    const double *pi = part + (size_t)c * ADT_MAX * 3;
+    r0 += __ldcg(pi);
+    r1 += __ldcg(pi + 1);
+    r2 += __ldcg(pi + 2);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+    r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+  }
+  if (lane == 0) {
+    const double sm = -m;
+    const double s[3] = {sm * (ta[0] + r0), sm * (ta[1] + r1), sm * (ta[2] + r2)};
+    for (int k = 0; k < 3; ++k) {  // adv_accumulate_row on the values
+      v[k] = __dadd_rn(v[k], __dmul_rn(ta[3], s[k]));
+      v[3 + k] = __dadd_rn(v[3 + k], __dmul_rn(ta[4], s[k]));
+      v[6 + k] = __dadd_rn(v[6 + k], __dmul_rn(ta[5], s[k]));
+    }
+    for (int k = 0; k < 9; ++k) b.st(11 + k, v[k]);
+    if (last) {
+      double q[3], p[3];
+      adv_finish_vals(h, m, v, p0, q0, q, p);
+      for (int k = 0; k < 3; ++k) {
+        b.st(2 + k, q[k]);
+        b.st(5 + k, p[k]);
+      }
+      b.st(0, t);
+      *hmax_out = adv_h_adaptive_vals(h, m, t, q, q2, v + 6, sf);
+    }
+  }
+}
+
 template <int NTMAX>  // register budget: 255 per thread up to 256 threads, 128 at 512
 __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams P) {
   extern __shared__ __align__(16) unsigned char adt_smem[];
@@ -2041,7 +2108,8 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
   double *hs = tile + ADT_TS * 4;                     // hmax of the prefix, slot order
   double *hs2 = hs + ADT_MAX;
   double *red = hs2 + ADT_MAX;                        // [16 warps][3]
-  AdvFrame *stack = reinterpret_cast<AdvFrame *>(red + 64);
+  double *racc = red + 64;                            // [ADT_MAX][3] this CTA's sums for the active slots
+  AdvFrame *stack = reinterpret_cast<AdvFrame *>(racc + ADT_MAX * 3);
   int *ms = reinterpret_cast<int *>(stack + ADT_DEPTH);  // slot -> row
   int *ms2 = ms + ADT_MAX;
   __shared__ AdvCtl ctl;
@@ -2053,6 +2121,8 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
   const double eps2 = P.eps2;
   unsigned long long nbar = 0;
   long long n_int = 0, n_pair = 0, n_step = 0;
+  int pend_imin = 0, pend_na = 0, pend_gc = 0;  // the previous interact's fold, still to be done
+  const double *pend_tact = nullptr, *pend_part = nullptr;
   long long cyc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, c_prev = clock64();
 #define ADT_TICK(k)                     \
   do {                                  \
@@ -2151,187 +2221,183 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     __syncthreads();
     ADT_TICK(0);
     if (ctl.op != 1) break;
-    const int imin = ctl.imin, imax = ctl.imax, na = imax - imin, np = n - imax;
+    const int imin = ctl.imin, imax = ctl.imax, na = imax - imin;
     const bool begin = ctl.begin != 0, last = ctl.last != 0;
     const double t = ctl.t, vC = ctl.vC, hnew = ctl.hnew;
     n_int += 1;
     n_step += last ? 1 : 0;
     n_pair += (long long)na * (n - imin - 1) - (long long)na * (na - 1) / 2;
 
-    // ---- P1: predictors ------------------------------------------------------------------
-    for (int j = imin + gt; j < n; j += GT) {
-      const AdvRowSoA b{P.soa + (j < top ? ms[j] : j), LD};
-      if (begin && j < imax) adv_begin_row(b, hnew);
-      double2 xy, zm;
-      adv_predict_row(b, t, xy, zm);
-      double2 *o = reinterpret_cast<double2 *>(P.packed4 + (size_t)j * 4);
-      o[0] = xy;
-      o[1] = zm;
+    double *tactb = P.tact + (size_t)(n_int & 1) * ADT_MAX * 6;
+    double *partb = P.partial + (size_t)(n_int & 1) * G * ADT_MAX * 3;
+    const int Gc = min(G, (n - imin + T - 1) / T);  // CTAs that own a slot
+
+    // ---- A.0: the previous interact's fold, by the CTA that owns the slot in THIS phase (so it
+    // is ordered before that slot's passive update below by the CTA's own barrier) -------------
+    if (pend_na > 0) {
+      for (int a = tid >> 5; a < pend_na; a += T >> 5) {
+        const int slot = pend_imin + a;
+        if (((slot - imin) / T) % G != (int)blockIdx.x) continue;
+        adv_fold_row(AdvRowSoA{P.soa + ms[slot], LD}, pend_tact + (size_t)a * 6,
+                     pend_part + (size_t)a * 3, pend_gc, lane, false, 0.0, 0.0, nullptr);
+      }
+      pend_na = 0;
+    }
+
+    // ---- A.1: the active block, predicted by every CTA for itself ----------------------------
+    for (int a = tid; a < na; a += T) {
+      const AdvRowSoA b{P.soa + ms[imin + a], LD};
+      double x[3];
+      const double m = b.ld(1);
+      if (begin) {  // bs.(a).t = t0 here: predict_position leaves q alone (advancer.ml:174-175)
+        for (int k = 0; k < 3; ++k) x[k] = b.ld(2 + k);
+      } else {
+        const double t0 = b.ld(10), h = b.ld(8);
+        double q0[3], q1[3], q2[3], c[3];
+        for (int k = 0; k < 3; ++k) {
+          q0[k] = b.ld(23 + k);
+          q1[k] = b.ld(26 + k);
+          q2[k] = b.ld(29 + k);
+        }
+        adv_predict_vals(t, t0, h, q0, q1, q2, c, x);
+      }
+      xa[4 * a] = x[0];
+      xa[4 * a + 1] = x[1];
+      xa[4 * a + 2] = x[2];
+      xa[4 * a + 3] = m;
+      racc[3 * a] = racc[3 * a + 1] = racc[3 * a + 2] = 0.0;
     }
     ADT_TICK(1);
-    adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
-    ADT_TICK(2);
 
-    if (na == 0) continue;  // hmax = dt exactly: an empty block (advancer.ml:321-328), nothing to sum
-
-    // ---- P2 A: every slot against the active block -----------------------------------------
-    {
-      const double2 *src = reinterpret_cast<const double2 *>(P.packed4 + (size_t)imin * 4);
-      for (int e = tid; e < 2 * na; e += T) reinterpret_cast<double2 *>(xa)[e] = __ldcg(src + e);
-    }
-    __syncthreads();
-    for (int j = imin + gt; j < n; j += GT) {
-      const double2 *me = reinterpret_cast<const double2 *>(P.packed4 + (size_t)j * 4);
-      const double2 mxy = __ldcg(me), mzm = __ldcg(me + 1);
-      const AdvRowSoA b{P.soa + (j < top ? ms[j] : j), LD};
-      const double cs0 = b.ld(32), cs1 = b.ld(33), cs2 = b.ld(34);
-      double v[9];
-      if (j >= imax)
-        for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
-      double ax = 0.0, ay = 0.0, az = 0.0;
-      const int aself = j - imin;  // >= na for a passive slot: never matches
-      const double2 *x2 = reinterpret_cast<const double2 *>(xa);
-#pragma unroll 4
-      for (int a = 0; a < na; ++a)
-        adv_pair(mxy.x, mxy.y, mzm.x, x2[2 * a], x2[2 * a + 1], eps2, a == aself, ax, ay, az);
-      const double c0 = __dmul_rn(vC, cs0), c1 = __dmul_rn(vC, cs1), c2 = __dmul_rn(vC, cs2);
-      if (j >= imax) {
-        const double sm = -mzm.y;
-        const double s[3] = {sm * ax, sm * ay, sm * az};
-        adv_accumulate_row_pre(b, v, c0, c1, c2, s);
-      } else {
-        double *o = P.tact + (size_t)aself * 6;
-        o[0] = ax;
-        o[1] = ay;
-        o[2] = az;
-        o[3] = c0;
-        o[4] = c1;
-        o[5] = c2;
+    // ---- A.2: passes of one slot per thread ---------------------------------------------------
+    for (int r = 0;; ++r) {
+      const long long j0l = (long long)imin + (long long)blockIdx.x * T + (long long)r * GT;
+      if (j0l >= n) break;
+      const int j0 = (int)j0l, j = j0 + tid;
+      const bool valid = j < n;
+      const AdvRowSoA b{P.soa + (valid ? (j < top ? ms[j] : j) : 0), LD};
+      double2 mxy = make_double2(0.0, 0.0), mzm = mxy;
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0, v[9];
+      __syncthreads();  // xa / racc are set; the previous pass is done with the tile
+      if (valid) {
+        if (j >= imax)
+          for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
+        if (begin && j < imax) adv_begin_row(b, hnew);
+        double cs[3];
+        adv_predict_row(b, t, mxy, mzm, cs);
+        c0 = __dmul_rn(vC, cs[0]);
+        c1 = __dmul_rn(vC, cs[1]);
+        c2 = __dmul_rn(vC, cs[2]);
+        reinterpret_cast<double2 *>(tile)[2 * tid] = mxy;
+        reinterpret_cast<double2 *>(tile)[2 * tid + 1] = mzm;
       }
-    }
-
-    ADT_TICK(3);
-    // ---- P2 B: the active block against this CTA's slice of the passive slots --------------
-    const int L = np > 0 ? (np + G - 1) / G : 1;
-    const int Gc = np > 0 ? (np + L - 1) / L : 0;  // CTAs with a non-empty slice
-    if ((int)blockIdx.x < Gc) {
-      const int k0 = imax + blockIdx.x * L, k1 = min(n, k0 + L);
-      for (int a0 = 0; a0 < na; a0 += T) {
-        const int nac = min(T, na - a0);
-        int napad = 1;
-        while (napad < nac) napad <<= 1;
-        const int SPLIT = T / napad;
-        const int al = tid / SPLIT, s = tid - al * SPLIT;
-        const bool live = al < nac;
-        double x = 0.0, y = 0.0, z = 0.0;
-        if (live) {
-          x = xa[4 * (a0 + al)];
-          y = xa[4 * (a0 + al) + 1];
-          z = xa[4 * (a0 + al) + 2];
+      __syncthreads();
+      ADT_TICK(2);
+      if (valid && na > 0) {  // this slot against the active block
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        const int aself = j - imin;  // >= na for a passive slot: never matches
+        const double2 *x2 = reinterpret_cast<const double2 *>(xa);
+#pragma unroll 4
+        for (int a = 0; a < na; ++a)
+          adv_pair(mxy.x, mxy.y, mzm.x, x2[2 * a], x2[2 * a + 1], eps2, a == aself, ax, ay, az);
+        if (j >= imax) {
+          const double sm = -mzm.y;
+          const double s[3] = {sm * ax, sm * ay, sm * az};
+          adv_accumulate_row_pre(b, v, c0, c1, c2, s);
+        } else {
+          double *o = tactb + (size_t)aself * 6;
+          o[0] = ax;
+          o[1] = ay;
+          o[2] = az;
+          o[3] = c0;
+          o[4] = c1;
+          o[5] = c2;
         }
-        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-        for (int kt = k0; kt < k1; kt += ADT_TS) {
-          const int cnt = min(ADT_TS, k1 - kt);
-          __syncthreads();
-          const double2 *src = reinterpret_cast<const double2 *>(P.packed4 + (size_t)kt * 4);
-          for (int e = tid; e < 2 * cnt; e += T) reinterpret_cast<double2 *>(tile)[e] = __ldcg(src + e);
-          __syncthreads();
+      }
+      ADT_TICK(3);
+      // the active block against the passive slots of this pass (tile entries [klo, khi))
+      const int klo = max(0, imax - j0), khi = min(T, n - j0);
+      if (klo < khi) {
+        for (int a0 = 0; a0 < na; a0 += T) {
+          const int nac = min(T, na - a0);
+          int napad = 1;
+          while (napad < nac) napad <<= 1;
+          const int SPLIT = T / napad;
+          const int al = tid / SPLIT, s = tid - al * SPLIT;
+          const bool live = al < nac;
+          double r0 = 0.0, r1 = 0.0, r2 = 0.0;
           if (live) {
+            const double x = xa[4 * (a0 + al)], y = xa[4 * (a0 + al) + 1], z = xa[4 * (a0 + al) + 2];
             const double2 *t2 = reinterpret_cast<const double2 *>(tile);
-            for (int k = s; k < cnt; k += SPLIT)
+            for (int k = klo + s; k < khi; k += SPLIT)
               adv_pair(x, y, z, t2[2 * k], t2[2 * k + 1], eps2, false, r0, r1, r2);
           }
-        }
-        const int width = SPLIT < 32 ? SPLIT : 32;
-        for (int off = width >> 1; off > 0; off >>= 1) {
-          r0 += __shfl_xor_sync(0xffffffffu, r0, off);
-          r1 += __shfl_xor_sync(0xffffffffu, r1, off);
-          r2 += __shfl_xor_sync(0xffffffffu, r2, off);
-        }
-        double *po = P.partial + ((size_t)blockIdx.x * ADT_MAX + a0) * 3;
-        if (SPLIT > 32) {  // several warps per target: fixed pass over them
-          __syncthreads();
-          if (lane == 0) {
-            red[3 * (tid >> 5)] = r0;
-            red[3 * (tid >> 5) + 1] = r1;
-            red[3 * (tid >> 5) + 2] = r2;
+          const int width = SPLIT < 32 ? SPLIT : 32;
+          for (int off = width >> 1; off > 0; off >>= 1) {
+            r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, off);
           }
-          __syncthreads();
-          if (tid < nac) {
-            const int wpt = SPLIT >> 5;
-            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-            for (int w = 0; w < wpt; ++w) {
-              q0 += red[3 * (tid * wpt + w)];
-              q1 += red[3 * (tid * wpt + w) + 1];
-              q2 += red[3 * (tid * wpt + w) + 2];
+          if (SPLIT > 32) {  // several warps per target: fixed pass over them
+            __syncthreads();
+            if (lane == 0) {
+              red[3 * (tid >> 5)] = r0;
+              red[3 * (tid >> 5) + 1] = r1;
+              red[3 * (tid >> 5) + 2] = r2;
             }
-            po[3 * tid] = q0;
-            po[3 * tid + 1] = q1;
-            po[3 * tid + 2] = q2;
+            __syncthreads();
+            if (tid < nac) {
+              const int wpt = SPLIT >> 5;
+              double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+              for (int w = 0; w < wpt; ++w) {
+                q0 += red[3 * (tid * wpt + w)];
+                q1 += red[3 * (tid * wpt + w) + 1];
+                q2 += red[3 * (tid * wpt + w) + 2];
+              }
+              racc[3 * (a0 + tid)] += q0;
+              racc[3 * (a0 + tid) + 1] += q1;
+              racc[3 * (a0 + tid) + 2] += q2;
+            }
+          } else if (live && s == 0) {
+            racc[3 * (a0 + al)] += r0;
+            racc[3 * (a0 + al) + 1] += r1;
+            racc[3 * (a0 + al) + 2] += r2;
           }
-        } else if (live && s == 0) {
-          po[3 * al] = r0;
-          po[3 * al + 1] = r1;
-          po[3 * al + 2] = r2;
         }
       }
     }
+    __syncthreads();
+    if ((int)blockIdx.x < Gc)
+      for (int e = tid; e < 3 * na; e += T) partb[(size_t)blockIdx.x * ADT_MAX * 3 + e] = racc[e];
     ADT_TICK(4);
     adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
     ADT_TICK(5);
+    if (na == 0) continue;  // hmax = dt exactly: an empty block (advancer.ml:321-328), nothing to fold
 
-    // ---- P3: one warp per active slot ------------------------------------------------------
-    for (int a = gt >> 5; a < na; a += GT >> 5) {
-      // lane 0 owns the row: everything it will need is requested before the partial sums, so
-      // the whole fix-up is one trip to L2
-      const AdvRowSoA b{P.soa + ms[imin + a], LD};
-      double ta[6], v[9], p0[3], q0[3], q2[3], m = 0.0, h = 0.0;
-      if (lane == 0) {
-        for (int k = 0; k < 6; ++k) ta[k] = __ldcg(P.tact + (size_t)a * 6 + k);
-        for (int k = 0; k < 9; ++k) v[k] = b.ld(11 + k);
-        m = b.ld(1);
-        if (last) {
-          h = b.ld(8);
-          for (int k = 0; k < 3; ++k) {
-            p0[k] = b.ld(20 + k);
-            q0[k] = b.ld(23 + k);
-            q2[k] = b.ld(29 + k);
-          }
-        }
-      }
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-      for (int c = lane; c < Gc; c += 32) {
-        const double *pi = P.partial + ((size_t)c * ADT_MAX + a) * 3;
-        r0 += __ldcg(pi);
-        r1 += __ldcg(pi + 1);
-        r2 += __ldcg(pi + 2);
-      }
-      for (int off = 16; off > 0; off >>= 1) {
-        r0 += __shfl_xor_sync(0xffffffffu, r0, off);
-        r1 += __shfl_xor_sync(0xffffffffu, r1, off);
-        r2 += __shfl_xor_sync(0xffffffffu, r2, off);
-      }
-      if (lane == 0) {
-        const double sm = -m;
-        const double s[3] = {sm * (ta[0] + r0), sm * (ta[1] + r1), sm * (ta[2] + r2)};
-        for (int k = 0; k < 3; ++k) {  // adv_accumulate_row on the values
-          v[k] = __dadd_rn(v[k], __dmul_rn(ta[3], s[k]));
-          v[3 + k] = __dadd_rn(v[3 + k], __dmul_rn(ta[4], s[k]));
-          v[6 + k] = __dadd_rn(v[6 + k], __dmul_rn(ta[5], s[k]));
-        }
-        for (int k = 0; k < 9; ++k) b.st(11 + k, v[k]);
-        if (last) {  // advancer.ml:339-342: finish_body, h_adaptive
-          double q[3], p[3];
-          adv_finish_vals(h, m, v, p0, q0, q, p);
-          for (int k = 0; k < 3; ++k) {
-            b.st(2 + k, q[k]);
-            b.st(5 + k, p[k]);
-          }
-          b.st(0, t);
-          P.hmax[imin + a] = adv_h_adaptive_vals(h, m, t, q, q2, v + 6, P.sf);
-        }
-      }
+    // ---- B: after a step's third interact, one warp per active slot: fold, finish_body,
+    // h_adaptive (advancer.ml:339-342).  Other interacts leave the fold to the next phase A.
+    if (!last && na <= (T >> 4)) {  // a few slots: their owners' CTAs fold them in the next phase A
+      pend_imin = imin;
+      pend_na = na;
+      pend_gc = Gc;
+      pend_tact = tactb;
+      pend_part = partb;
+      continue;
     }
+    if (!last) {  // a wide block: every warp of the grid takes slots, then a barrier orders the
+                  // folds before the next interact's passive updates of the same rows
+      for (int a = gt >> 5; a < na; a += GT >> 5)
+        adv_fold_row(AdvRowSoA{P.soa + ms[imin + a], LD}, tactb + (size_t)a * 6,
+                     partb + (size_t)a * 3, Gc, lane, false, 0.0, 0.0, nullptr);
+      ADT_TICK(6);
+      adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+      ADT_TICK(7);
+      continue;
+    }
+    for (int a = gt >> 5; a < na; a += GT >> 5)
+      adv_fold_row(AdvRowSoA{P.soa + ms[imin + a], LD}, tactb + (size_t)a * 6,
+                   partb + (size_t)a * 3, Gc, lane, true, t, P.sf, P.hmax + imin + a);
+    pend_na = 0;
     ADT_TICK(6);
     if (last) {
       adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);

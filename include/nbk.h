@@ -227,8 +227,8 @@ int nbk_adv_energy(nbk_ctx *ctx, double eps2, double *ke, double *pe);
 /* `advance_range bs imax dt sf None` (advancer.ml:316-350) ENTIRELY on the device, for a prefix
  * of imax <= nbk_adv_range_max() rows of the resident records: one persistent cooperative kernel
  * runs the block recursion (frame stack, block search, predict_q012, the three interact_bodies
- * of every block step against ALL rows [imin, n), finish_body, h_adaptive, sort_range) with grid
- * barriers between the phases - no host round trip per block step.  hmax[imax]: in, the
+ * of every block step against ALL rows [imin, n), finish_body, h_adaptive, sort_range) with one
+ * grid barrier per interact_bodies and one per sort - no host round trip per block step.  hmax[imax]: in, the
  * prefix's hmax (the host's mirror); out, the new hmax in the new row order.  perm[imax]: out,
  * new row s = old row perm[s] (the device rows have already been moved; the caller applies it to
  * whatever it keeps per row, e.g. ids).  stats (may be NULL): += {interact_bodies calls, pair
@@ -240,8 +240,9 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
                           int *perm, long long *stats);
 int nbk_adv_range_max(void);
 /* Diagnostics of nbk_adv_advance_range since the last reset: prof[0] block steps, prof[1..9]
- * clock cycles CTA 0 spent in {control, predictors, barrier, slot x active sums, active x
- * passive-slice sums, barrier, fix-up + finish, barrier, sort}, prof[10] kernel launches. */
+ * clock cycles CTA 0 spent in {control, deferred folds + active-block prediction, predictors,
+ * slot x active sums, active x own-tile sums, barrier, fold + finish_body + h_adaptive, barrier,
+ * sort}, prof[10] kernel launches. */
 int nbk_adv_range_profile(nbk_ctx *ctx, long long *prof, int reset);
 
 /* ---- device-resident Leapfrog.b array (leapfrog.ml:106-158) ---------------------------------- */

@@ -36,7 +36,8 @@ with nbk.Context(0) as ctx:
             import ctypes
             prof = (ctypes.c_longlong * 11)()
             nbk.load_library().nbk_adv_range_profile(ctx._h, prof, 1)
-            names = ("control", "P1", "bar", "P2A", "P2B", "bar", "P3", "bar", "sort")
+            names = ("control", "fold+actives", "predict", "slot x active", "active x tile", "barrier",
+                     "finish", "barrier", "sort")
             tot = sum(prof[1:10]) or 1
             print(f"  device recursion: {prof[10]} launches, {prof[0]} block steps, CTA 0 cycles "
                   f"{tot / 1.965e3:.0f} us: " +
