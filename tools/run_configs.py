@@ -53,7 +53,7 @@ with nbk.Context(0) as ctx:
     b = O.advancer_advance(O.AdvancerState(m, q, p), span, 1e-4, eps2a)
     tc = time.perf_counter() - t0
     e0 = sum(nbh.energy(ctx, m, q, p, eps2a))
-    res.append({"config": "0b", "what": f"Advancer.A.advance, Plummer N={na}, eps=0.01, {span} time units, sf=1e-4 (block steps, host recursion + GPU sweeps)",
+    res.append({"config": "0b", "what": f"Advancer.A.advance, Plummer N={na}, eps=0.01, {span} time units, sf=1e-4 (block recursion on the device, nbk_adv_advance_range)",
                 "interact_bodies_calls": a.stats[0], "pair_interactions": a.stats[1],
                 "same_schedule_as_oracle": a.stats == b.stats,
                 "dE_gpu": abs((sum(nbh.energy(ctx, a.m, a.q, a.p, eps2a)) - e0) / e0),

@@ -54,4 +54,17 @@ with nbk.Context(0) as ctx:
     nbh.load_library().nbh_set_step_cap(2_000_000)
     nbh.hermite_advance(ctx, s, 1e-3, 1e-4, mode=1)
     nbh.hermite_advance(ctx, s, 1e-3, 1e-4, mode=2)
+    # resident integrators: Advancer.A (per-phase kernels, then the device-side block recursion
+    # in its default and in forced grid shapes), Leapfrog block steps, Omelyan steps
+    mm, qq, pp = nbh.rescale_to_standard_units(ctx, m[:300] * (n / 300), q[:300], p[:300] * (n / 300))
+    a0 = nbh.AdvancerState(mm, qq, pp)
+    nbh.advancer_advance(ctx, a0, 2.0 ** -9, 1e-4, 1e-4, resident=1)
+    a1 = nbh.advancer_advance(ctx, a0, 2.0 ** -9, 1e-4, 1e-4, resident=2)
+    nbh.advancer_advance(ctx, a1, 2.0 ** -9, 1e-4, 1e-4, resident=2, tree_max=40)
+    for shape in ("128,2", "256,1", "512,1"):
+        os.environ["NBK_ADT_SHAPE"] = shape
+        nbh.advancer_advance(ctx, a1, 2.0 ** -10, 1e-4, 1e-4, resident=2)
+    del os.environ["NBK_ADT_SHAPE"]
+    nbh.leapfrog_advance(ctx, nbh.LeapfrogState(mm, qq, pp), 2.0 ** -9, 5e-3)
+    nbh.omelyan_advance_steps(ctx, mm, qq, pp, 0.0, 2.0 ** -9, 2, 1e-4, want_el=True)
     print("sanitize tour done:", ctx.launch_count, "launches")
