@@ -4,6 +4,7 @@
 #include "sweep.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +45,8 @@ struct nbk_ctx {
   int adv_n = 0;
   DevBuf d_adv, d_adv2;
   DevBuf d_adt;  // workspace of the device-side advance_range (nbk_adv_advance_range)
+  DevBuf d_lft;  // workspace of the device-side advance_subsystem (nbk_lf_advance_subsystem)
+  bool lft_attr_set = false;
   bool adt_attr_set = false;
   long long adt_prof[11] = {0};  // block steps, 9 per-phase cycle counts of CTA 0, kernel launches
   // resident Leapfrog.b array: packed rows {q, m, v} in array order + dt_max
@@ -682,7 +685,7 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
                     &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el, &c->d_lf_packed,
-                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt};
+                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt, &c->d_lft};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -1687,6 +1690,52 @@ int nbk_lf_kick_block(nbk_ctx *ctx, int iend, int ibegin, double eta, double dt,
     TRY(sync(ctx));
     memcpy(dt_max, ctx->h_lf_stage, n * sizeof(double));
   }
+  return NBK_OK;
+}
+
+int nbk_lf_subsystem_max(void) { return LFT_MAX; }
+
+int nbk_lf_advance_subsystem(nbk_ctx *ctx, int iend, double dt, double eta, double *t, double *dt_max,
+                             int *perm, long long *nkicks) {
+  NEED_LF();
+  if (iend < 1 || iend > ctx->lf_n || iend > LFT_MAX || !t || !dt_max || !perm || !(dt >= 0.0))
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_advance_subsystem: bad arguments (iend=%d of %d, limit %d, dt=%g)",
+                iend, ctx->lf_n, LFT_MAX, dt);
+  // workspace: t [LFT_MAX] | out [2] | map [LFT_MAX] ints
+  TRY(reserve(ctx, ctx->d_lft, (size_t)(LFT_MAX + 2 + LFT_MAX / 2) * sizeof(double)));
+  double *w = (double *)ctx->d_lft.p;
+  cudaStream_t st = ctx->stream;
+  const bool ts = !(std::isinf(eta) && eta > 0);
+  if (!ctx->lft_attr_set) {
+    CK(cudaFuncSetAttribute(lf_tree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
+    CK(cudaFuncSetAttribute(lf_tree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
+    ctx->lft_attr_set = true;
+  }
+  CK(cudaMemcpyAsync(w, t, (size_t)iend * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(w + LFT_MAX, 0, 2 * sizeof(double), st));
+  LfTreeParams P;
+  P.packed = (double *)ctx->d_lf_packed.p;
+  P.dt_max = (double *)ctx->d_lf_dtmax.p;
+  P.t = w;
+  P.out = (long long *)(w + LFT_MAX);
+  P.map = (int *)(w + LFT_MAX + 2);
+  P.iend = iend;
+  P.dt = dt;
+  P.eta = eta;
+  if (ts) lf_tree_kernel<true><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
+  else lf_tree_kernel<false><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  long long out[2] = {0, 0};
+  CK(cudaMemcpyAsync(t, P.t, (size_t)iend * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(dt_max, P.dt_max, (size_t)iend * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(perm, P.map, (size_t)iend * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out, P.out, sizeof out, cudaMemcpyDeviceToHost, st));
+  TRY(sync(ctx));
+  if (out[1] != 0)
+    return fail(ctx, NBK_ERR_STATE, "nbk_lf_advance_subsystem: block recursion deeper than %d frames",
+                LFT_DEPTH);
+  if (nkicks) *nkicks += out[0];
   return NBK_OK;
 }
 

@@ -2524,6 +2524,271 @@ __global__ void lf_apply_kernel(double *__restrict__ packed, double *__restrict_
   }
 }
 
+// ---- Leapfrog.advance_subsystem ENTIRELY on the device (leapfrog.ml:113-142) -------------------
+// `advance_subsystem dt eta bs iend` touches nothing but bodies [0, iend): a subtree of the
+// block recursion with iend <= LFT_MAX is self-contained, and one CTA runs all of it with the
+// bodies in shared memory - explicit frame stack, find_can_advance_index, drifts, the kick block
+// of every step (same pair function and FP32 filter as the tiled kick sweep: velocity kicks from
+// the pre-kick state, bit-exact pair time-scales), dt_max updates, stable sort_sub.  Rows stay
+// where they are; the sorts permute a slot -> row map (and dt_max, t), applied when the rows are
+// written back.  Kick block, targets [0, iend) with active block [ibegin, iend):
+//   B: active slot a against the passive slots [0, ibegin): SPLIT lanes per target take sources
+//      s, s+SPLIT, ..., fixed shuffle tree (sum of dv, min of the time-scale);
+//   A: every slot against the active block, one thread per slot; an active slot then adds B.
+constexpr int LFT_MAX = 1024;
+constexpr int LFT_THREADS = 512;
+constexpr int LFT_DEPTH = 160;
+
+struct LfTreeParams {
+  double *packed;   // [iend][PK] in/out, array order
+  double *dt_max;   // [iend] in/out
+  double *t;        // [iend] in/out (the bodies' times, drifted like leapfrog.ml:65)
+  int *map;         // [iend] out: new row s = old row map[s]
+  long long *out;   // kick blocks, error
+  int iend;
+  double dt, eta;
+};
+struct LfFrame {
+  int iend, ibegin, stage, pad;
+  double dt;
+};
+constexpr size_t LFT_SMEM = sizeof(double) * ((size_t)LFT_MAX * PK + 4 * LFT_MAX + 4 * LFT_MAX + 64) +
+                            sizeof(LfFrame) * LFT_DEPTH + sizeof(int) * 2 * LFT_MAX;
+
+// OCaml's compare on floats puts nan below everything (leapfrog.ml:108)
+__device__ __forceinline__ double lf_sort_key(double d) {
+  return d != d ? __longlong_as_double(0xfff0000000000000LL) : d;
+}
+
+template <bool TS>
+__global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreeParams P) {
+  using Op = OpKick<TS>;
+  extern __shared__ __align__(16) unsigned char lft_smem[];
+  double *rows = reinterpret_cast<double *>(lft_smem);  // [LFT_MAX][PK]
+  double *dtm = rows + (size_t)LFT_MAX * PK;           // dt_max, slot order
+  double *tt = dtm + LFT_MAX;                          // t, slot order
+  double *dtm2 = tt + LFT_MAX;
+  double *tt2 = dtm2 + LFT_MAX;
+  double *res = tt2 + LFT_MAX;                         // [LFT_MAX][4] dv (unscaled), tmin per slot
+  double *red = res + 4 * LFT_MAX;                     // [16 warps][4]
+  LfFrame *stack = reinterpret_cast<LfFrame *>(red + 64);
+  int *ms = reinterpret_cast<int *>(stack + LFT_DEPTH);  // slot -> row
+  int *ms2 = ms + LFT_MAX;
+
+  const int T = LFT_THREADS, tid = threadIdx.x, lane = tid & 31;
+  const int top = P.iend;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  SweepParams SP;
+  SP.eta = P.eta;
+  long long nk = 0;
+  int sp = 0, err = 0;
+
+  for (int e = tid; e < top * PK; e += T) rows[e] = P.packed[e];
+  for (int i = tid; i < top; i += T) {
+    dtm[i] = P.dt_max[i];
+    tt[i] = P.t[i];
+    ms[i] = i;
+  }
+  if (tid == 0) stack[0] = LfFrame{top, 0, 0, 0, P.dt};
+  sp = 1;
+  __syncthreads();
+
+  // every thread walks the same frames (the data it looks at is shared and only changes between
+  // barriers); thread 0 alone writes the stack
+  while (sp > 0 && !err) {
+    const LfFrame f = stack[sp - 1];
+    __syncthreads();
+    if (f.stage == 0) {
+      if (f.iend <= 0) {  // leapfrog.ml:120-121
+        --sp;
+        continue;
+      }
+      int ibegin = f.iend;  // find_can_advance_index (leapfrog.ml:113-117)
+      while (!(ibegin == 0 || dtm[ibegin - 1] < f.dt)) --ibegin;
+      __syncthreads();
+      for (int i = ibegin + tid; i < f.iend; i += T) dtm[i] = INF;  // leapfrog.ml:125-127
+      if (sp >= LFT_DEPTH) {
+        err = 1;
+        break;
+      }
+      if (tid == 0) {
+        stack[sp - 1].ibegin = ibegin;
+        stack[sp - 1].stage = 1;
+        stack[sp] = LfFrame{ibegin, 0, 0, 0, f.dt / 2.0};
+      }
+      ++sp;
+      __syncthreads();
+      continue;
+    }
+    if (f.stage == 2) {  // sort_sub bs iend (leapfrog.ml:106-111, 141): stable rank
+      const int iend = f.iend;
+      int bad = 0;
+      for (int i = tid; i + 1 < iend; i += T) bad |= lf_sort_key(dtm[i + 1]) < lf_sort_key(dtm[i]);
+      if (__syncthreads_or(bad)) {
+        for (int i = tid; i < iend; i += T) {
+          const double ki = lf_sort_key(dtm[i]);
+          int r = 0;
+          for (int k = 0; k < iend; ++k) {
+            const double kk = lf_sort_key(dtm[k]);
+            r += (kk < ki || (kk == ki && k < i)) ? 1 : 0;
+          }
+          dtm2[r] = dtm[i];
+          tt2[r] = tt[i];
+          ms2[r] = ms[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < iend; i += T) {
+          dtm[i] = dtm2[i];
+          tt[i] = tt2[i];
+          ms[i] = ms2[i];
+        }
+      }
+      --sp;
+      __syncthreads();
+      continue;
+    }
+    // stage 1: drift, kick block, drift (leapfrog.ml:129-139), then the second half recursion
+    const int ibegin = f.ibegin, iend = f.iend, na = iend - ibegin;
+    const double dt = f.dt, dt2 = f.dt / 2.0;
+    if (na > 0) {
+      for (int i = ibegin + tid; i < iend; i += T) {
+        double *b = rows + (size_t)ms[i] * PK;
+        tt[i] = __dadd_rn(tt[i], dt2);
+        b[0] = __dadd_rn(b[0], __dmul_rn(dt2, b[4]));
+        b[1] = __dadd_rn(b[1], __dmul_rn(dt2, b[5]));
+        b[2] = __dadd_rn(b[2], __dmul_rn(dt2, b[6]));
+      }
+      __syncthreads();
+      // B: active slots against the passive slots
+      for (int a0 = 0; a0 < na; a0 += T) {
+        const int nac = min(T, na - a0);
+        int napad = 1;
+        while (napad < nac) napad <<= 1;
+        const int SPLIT = T / napad;
+        const int al = tid / SPLIT, s = tid - al * SPLIT;
+        const bool live = al < nac;
+        double acc[5];
+        Op::zero(acc);
+        if (live && ibegin > 0) {
+          typename Op::Tgt tg;
+          Op::load(tg, rows + (size_t)ms[ibegin + a0 + al] * PK, SP, 0);
+          for (int k = s; k < ibegin; k += SPLIT)
+            Op::template pair<false>(tg, acc, reinterpret_cast<const double2 *>(rows + (size_t)ms[k] * PK),
+                                     nullptr, false, SP);
+        }
+        const int width = SPLIT < 32 ? SPLIT : 32;
+        for (int off = width >> 1; off > 0; off >>= 1) {
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
+          acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], off);
+          acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], off);
+          if (TS) {
+            const double o = __shfl_xor_sync(0xffffffffu, acc[3], off);
+            if (acc[3] > o) acc[3] = o;
+          }
+        }
+        const double tmin = TS ? acc[3] : INF;
+        if (SPLIT > 32) {
+          __syncthreads();
+          if (lane == 0) {
+            red[4 * (tid >> 5)] = acc[0];
+            red[4 * (tid >> 5) + 1] = acc[1];
+            red[4 * (tid >> 5) + 2] = acc[2];
+            red[4 * (tid >> 5) + 3] = tmin;
+          }
+          __syncthreads();
+          if (tid < nac) {
+            const int wpt = SPLIT >> 5;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = INF;
+            for (int w = 0; w < wpt; ++w) {
+              q0 += red[4 * (tid * wpt + w)];
+              q1 += red[4 * (tid * wpt + w) + 1];
+              q2 += red[4 * (tid * wpt + w) + 2];
+              const double o = red[4 * (tid * wpt + w) + 3];
+              if (q3 > o) q3 = o;
+            }
+            double *r = res + 4 * (size_t)(ibegin + a0 + tid);
+            r[0] = q0;
+            r[1] = q1;
+            r[2] = q2;
+            r[3] = q3;
+          }
+        } else if (live && s == 0) {
+          double *r = res + 4 * (size_t)(ibegin + a0 + al);
+          r[0] = acc[0];
+          r[1] = acc[1];
+          r[2] = acc[2];
+          r[3] = tmin;
+        }
+      }
+      __syncthreads();
+      // A: every slot against the active block
+      for (int x = tid; x < iend; x += T) {
+        typename Op::Tgt tg;
+        Op::load(tg, rows + (size_t)ms[x] * PK, SP, 0);
+        double acc[5];
+        Op::zero(acc);
+        for (int y = ibegin; y < iend; ++y)
+          Op::template pair<true>(tg, acc, reinterpret_cast<const double2 *>(rows + (size_t)ms[y] * PK),
+                                  nullptr, y == x, SP);
+        double *r = res + 4 * (size_t)x;
+        double tmin = TS ? acc[3] : INF;
+        if (x >= ibegin) {  // passive part first, then the active part
+          acc[0] = r[0] + acc[0];
+          acc[1] = r[1] + acc[1];
+          acc[2] = r[2] + acc[2];
+          if (tmin > r[3]) tmin = r[3];
+        }
+        r[0] = acc[0];
+        r[1] = acc[1];
+        r[2] = acc[2];
+        r[3] = tmin;
+      }
+      __syncthreads();
+      // v += dv; dt_max = min(dt_max, tmin) (leapfrog.ml:103-104); second half drift of the block
+      for (int i = tid; i < iend; i += T) {
+        double *b = rows + (size_t)ms[i] * PK;
+        const double *r = res + 4 * (size_t)i;
+        b[4] = __dadd_rn(b[4], dt * r[0]);
+        b[5] = __dadd_rn(b[5], dt * r[1]);
+        b[6] = __dadd_rn(b[6], dt * r[2]);
+        if (TS) {
+          double d = dtm[i];  // an active slot holds infinity since stage 0
+          if (d > r[3]) d = r[3];
+          dtm[i] = d;
+        }
+        if (i >= ibegin) {
+          tt[i] = __dadd_rn(tt[i], dt2);
+          b[0] = __dadd_rn(b[0], __dmul_rn(dt2, b[4]));
+          b[1] = __dadd_rn(b[1], __dmul_rn(dt2, b[5]));
+          b[2] = __dadd_rn(b[2], __dmul_rn(dt2, b[6]));
+        }
+      }
+      nk += 1;
+    }
+    if (sp >= LFT_DEPTH) {
+      err = 1;
+      break;
+    }
+    if (tid == 0) {
+      stack[sp - 1].stage = 2;
+      stack[sp] = LfFrame{ibegin, 0, 0, 0, dt2};
+    }
+    ++sp;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int e = tid; e < top * PK; e += T) P.packed[e] = rows[(size_t)ms[e / PK] * PK + (e % PK)];
+  for (int i = tid; i < top; i += T) {
+    P.dt_max[i] = dtm[i];
+    P.t[i] = tt[i];
+    P.map[i] = ms[i];
+  }
+  if (tid == 0) {
+    P.out[0] = nk;
+    P.out[1] = err;
+  }
+}
+
 // ---- O(N) helpers ----------------------------------------------------------------------------
 // Pack (m, q, p|v) into the 64-byte source layout; v = p / m is the IEEE division the
 // reference performs per pair (base.ml:93-97), done once per body.

@@ -16,7 +16,20 @@ namespace {
 
 using namespace nbh;
 
-int g_leapfrog_resident = 1;  // const-dt steady state on the device (0: host loop, one sweep per step)
+// 0: host-buffer path (one nbk_kick_block_sum per kick block, host loop for const-dt steps);
+// 1: bodies resident on the device, block recursion on the host (one launch group + one dt_max
+//    read-back per kick block), const-dt steady state on the device;
+// 2: as 1, and every subtree of advance_subsystem whose prefix fits runs on the device in one
+//    launch (nbk_lf_advance_subsystem; agrees with 1 to rounding)
+int g_leapfrog_resident = 2;
+int g_leapfrog_tree_max = 0;  // 0: automatic
+
+int lf_tree_max() {
+  if (g_leapfrog_resident < 2) return 0;
+  const int cap = nbk_lf_subsystem_max();
+  if (g_leapfrog_tree_max > 0) return std::min(g_leapfrog_tree_max, cap);
+  return cap / 2;  // one CTA: wider blocks are faster through the tiled sweeps
+}
 
 struct LBody {
   int id;
@@ -42,6 +55,7 @@ struct Leap {
   // resident: positions and velocities live on the device in bs order (nbk_lf_*); the host keeps
   // what the recursion needs (id, t, dt_max, m) and bs[i].q / .v are stale until fetch().
   bool resident = false;
+  int tree_max = 0;  // resident only: prefixes up to this many bodies recurse on the device
 
   int to_device() {
     const int n = (int)bs.size();
@@ -162,8 +176,28 @@ struct Leap {
     return 0;
   }
 
+  // advance_subsystem for a prefix that fits the device-side recursion: one launch; the host's
+  // records (id, m, t, dt_max) follow the returned permutation.
+  int advance_subsystem_on_device(double dt, double eta, int iend) {
+    tm.resize(iend);
+    perm.resize(iend);
+    std::vector<double> tt(iend);
+    for (int i = 0; i < iend; ++i) tt[i] = bs[i].t;
+    long long nk = 0;
+    NBH_TRY(ck(ctx, nbk_lf_advance_subsystem(ctx, iend, dt, eta, tt.data(), tm.data(), perm.data(), &nk)));
+    std::vector<LBody> tmp(bs.begin(), bs.begin() + iend);
+    for (int i = 0; i < iend; ++i) {
+      bs[i] = tmp[perm[i]];
+      bs[i].t = tt[i];
+      bs[i].dt_max = tm[i];
+    }
+    nkicks += (long)nk;
+    return 0;
+  }
+
   int advance_subsystem(double dt, double eta, int iend) {  // leapfrog.ml:119-142
     if (iend <= 0) return 0;
+    if (resident && tree_max > 0 && iend <= tree_max) return advance_subsystem_on_device(dt, eta, iend);
     const int ibegin = find_can_advance_index(iend, dt);
     const double dt2 = dt / 2.0;
     NBH_TRY(begin_block(ibegin, iend));
@@ -212,7 +246,8 @@ void store(const Leap &L, int *id, double *t, double *dt_max, double *m, double 
 
 extern "C" {
 
-void nbh_set_leapfrog_resident(int on) { g_leapfrog_resident = on; }
+void nbh_set_leapfrog_resident(int mode) { g_leapfrog_resident = mode; }
+void nbh_set_leapfrog_tree_max(int bodies) { g_leapfrog_tree_max = bodies; }
 
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks) {
@@ -222,7 +257,10 @@ int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max
   for (auto &b : L.bs) b.dt_max = INFINITY;
   // the bodies stay on the device for the whole advance (nbk_lf_*); a multi-device context
   // has no resident Leapfrog state and goes through the host-buffer calls
-  if (g_leapfrog_resident && n > 0 && nbk_device_count(ctx) == 1) NBH_TRY(L.to_device());
+  if (g_leapfrog_resident && n > 0 && nbk_device_count(ctx) == 1) {
+    NBH_TRY(L.to_device());
+    L.tree_max = lf_tree_max();
+  }
   // "Kick" the entire system with dt = 0.0 to set up the time-scales (leapfrog.ml:146-155):
   // all pairs i<j == every body against every other.
   NBH_TRY(L.kick_block(eta, 0.0, 0, n));

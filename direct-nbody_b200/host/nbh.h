@@ -65,9 +65,14 @@ int nbh_omelyan_advance_steps(nbk_ctx *ctx, int n, const double *m, double *q, d
 /* advance bs dt eta: output order is the reference's (sorted by dt_max); id[] follows. */
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks);
-/* 1 (default): once every body has dt_max >= dt the remaining const-dt steps run on the device
- * (nbk_resident_leapfrog_steps); 0: every step goes through the host recursion. */
-void nbh_set_leapfrog_resident(int on);
+/* 2 (default): the bodies stay on the device (nbk_lf_*) and every subtree of advance_subsystem
+ * whose prefix fits (half of nbk_lf_subsystem_max bodies; nbh_set_leapfrog_tree_max to force)
+ * runs in ONE launch (nbk_lf_advance_subsystem); advance_const_dt: once every body has
+ * dt_max >= dt the remaining steps run on the device (nbk_resident_leapfrog_steps);
+ * 1: resident bodies, block recursion on the host - bit-identical to 0;
+ * 0: host-buffer path, every step through the host recursion. */
+void nbh_set_leapfrog_resident(int mode);
+void nbh_set_leapfrog_tree_max(int bodies); /* 0: automatic */
 int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max,
                                   double *m, double *q, double *v, double dt, int nsteps);
 

@@ -197,10 +197,13 @@ class LeapfrogState:
         return copy.deepcopy(self)
 
 
-def leapfrog_advance(ctx, s, dt, eta, resident=True):
-    """Leapfrog.advance bs dt eta; resident: bodies stay on the device (nbk_lf_*) for the whole
-    block recursion, else one nbk_kick_block_sum (upload + read-back) per kick block."""
+def leapfrog_advance(ctx, s, dt, eta, resident=2, tree_max=0):
+    """Leapfrog.advance bs dt eta; resident: 2 (default) bodies on the device and every subtree
+    of advance_subsystem that fits in one launch (nbk_lf_advance_subsystem; tree_max bodies,
+    0 = automatic); 1/True bodies on the device (nbk_lf_*), block recursion on the host; 0/False
+    one nbk_kick_block_sum (upload + read-back) per kick block (1 and 0 are bit-identical)."""
     load_library().nbh_set_leapfrog_resident(int(resident))
+    load_library().nbh_set_leapfrog_tree_max(int(tree_max))
     o = s.copy()
     nk = C.c_long(0)
     _ck(load_library().nbh_leapfrog_advance(ctx._h, len(o.m), _ip(o.id), _p(o.t), _p(o.dt_max),

@@ -83,6 +83,8 @@ SYMBOLS = {
     "nbk_adv_advance_range": (_i, [_vp, _i, _d, _d, _d, _pd, C.POINTER(_i), C.POINTER(C.c_longlong)]),
     "nbk_adv_range_max": (_i, []),
     "nbk_adv_range_profile": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
+    "nbk_lf_advance_subsystem": (_i, [_vp, _i, _d, _d, _pd, _pd, C.POINTER(_i), C.POINTER(C.c_longlong)]),
+    "nbk_lf_subsystem_max": (_i, []),
     "nbk_lf_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd]),
     "nbk_lf_download": (_i, [_vp, _pd, _pd, _pd]),
     "nbk_lf_permute": (_i, [_vp, _i, C.POINTER(_i)]),

@@ -271,6 +271,19 @@ int nbk_lf_drift(nbk_ctx *ctx, int i0, int i1, double dt);
 int nbk_lf_kick_block(nbk_ctx *ctx, int iend, int ibegin, double eta, double dt, int with_tscale,
                       int with_drift, double drift_after, double *dt_max);
 
+/* `advance_subsystem dt eta bs iend` (leapfrog.ml:119-142) ENTIRELY on the device, for a prefix of
+ * iend <= nbk_lf_subsystem_max() resident bodies: the call touches no body beyond iend, so one
+ * CTA keeps them in shared memory and runs the whole block recursion (find_can_advance_index,
+ * the dt_max resets, drifts, every kick block with its dt_max updates, sort_sub) - one launch
+ * instead of one launch group and one read-back per kick block.  t[iend]: in/out, the bodies'
+ * times (the device keeps no t).  dt_max[iend]: out, in the new array order.  perm[iend]: out,
+ * new row s = old row perm[s] (the device rows have been moved).  *nkicks += kick blocks.
+ * Pair time-scales are bit-exact as in nbk_lf_kick_block; the velocity sums are ordered
+ * differently from the tiled sweeps' (agreement to rounding). */
+int nbk_lf_advance_subsystem(nbk_ctx *ctx, int iend, double dt, double eta, double *t, double *dt_max,
+                             int *perm, long long *nkicks);
+int nbk_lf_subsystem_max(void);
+
 /* ---- device-resident Omelyan_advancer.OA (omelyan_advancer.ml:44-104) ----------------------- */
 /* The bodies (m, q, p) stay on the device; nbk_oa_steps runs nsteps of OA.advance h
  * (B A C A B: three grad_v sweeps at q, one at q*, omelyan_advancer.ml:96-104) without a host

@@ -166,13 +166,34 @@ def test_leapfrog_adaptive_device_resident_is_bit_identical_to_host_path(ctx, or
     host-buffer path (one nbk_kick_block_sum per block): same order, same bits."""
     m, q, p = (oracle.rescale_to_standard_units(*oracle.make_hot_spherical(n, 5)) if n > 1
                else oracle.make_hot_spherical(n, 5))
-    a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=True)
-    b = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=False)
+    a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=1)
+    b = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=0)
     assert a.nkicks == b.nkicks and np.array_equal(a.id, b.id)
     assert np.array_equal(a.t, b.t) and np.array_equal(a.dt_max, b.dt_max)
     assert np.array_equal(a.q, b.q) and np.array_equal(a.v, b.v)
     if n > 1:
         assert a.nkicks > 1 or span == 0.0
+
+
+@pytest.mark.parametrize("n,span,eta,tree_max", [(100, 1.0 / 32, 1e-3, 0), (512, 1.0 / 64, 2e-3, 0),
+                                                 (1024, 1.0 / 128, 2e-3, 1024), (1500, 1.0 / 64, 2e-3, 0),
+                                                 (1500, 1.0 / 64, 2e-3, 100), (1, 0.1, 1e-3, 0),
+                                                 (64, 0.0, 1e-3, 0), (700, 1.0 / 256, float("inf"), 1024)])
+def test_leapfrog_block_recursion_on_device(ctx, oracle, n, span, eta, tree_max):
+    """nbk_lf_advance_subsystem: advance_subsystem (leapfrog.ml:119-142) in ONE launch for every
+    subtree whose prefix fits (one CTA, bodies in shared memory).  Same kick blocks, same order
+    and times as the host recursion; dt_max and states to rounding (the velocity sums are
+    ordered differently; the pair time-scales themselves are bit-exact); reproducible."""
+    m, q, p = (oracle.rescale_to_standard_units(*oracle.make_hot_spherical(n, 5)) if n > 1
+               else oracle.make_hot_spherical(n, 5))
+    a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=2, tree_max=tree_max)
+    b = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=1)
+    assert a.nkicks == b.nkicks and np.array_equal(a.id, b.id)
+    assert np.array_equal(a.t, b.t)
+    assert np.allclose(a.dt_max, b.dt_max, rtol=1e-9, atol=0)
+    assert np.allclose(a.q, b.q, rtol=0, atol=1e-11) and np.allclose(a.v, b.v, rtol=0, atol=1e-10)
+    a2 = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=2, tree_max=tree_max)
+    assert np.array_equal(a.q, a2.q) and np.array_equal(a.v, a2.v) and np.array_equal(a.dt_max, a2.dt_max)
 
 
 def test_leapfrog_adaptive_energy_error_beside_oracle(ctx, oracle):

@@ -35,7 +35,7 @@ with nbk.Context(0) as ctx:
     na = min(n, 4096)
     m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(na, 20241))
     span, eta = 1.0 / 256, 5e-3
-    for resident in (True, False):
+    for resident in (2, 1, 0):  # 2: block recursion of the small subtrees on the device too
         t0 = time.perf_counter()
         a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta, resident=resident)
         dt = time.perf_counter() - t0
