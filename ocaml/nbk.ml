@@ -49,6 +49,39 @@ external oa_download : ctx -> vec -> vec -> unit = "nbk_ml_oa_download"
 (* [oa_diagnostics ctx eps2 el] = (ke, pe); fills el (4n: E_i, E_i/m, |L_i|, |L_i|/m) *)
 external oa_diagnostics : ctx -> float -> vec -> float * float = "nbk_ml_oa_diagnostics"
 
+(* Advancer.A (advancer.ml:207-428).  [interact_sum ctx m q na eps2 s]: bodies [imin, n)
+   re-indexed from 0, the first na active; s (3 per body) receives the grad_v sums of
+   interact_bodies' pair loop (advancer.ml:213-235). *)
+external interact_sum : ctx -> vec -> vec -> int -> float -> vec -> unit
+  = "nbk_ml_interact_sum_bc" "nbk_ml_interact_sum"
+
+(* The body records resident on the device, 35 doubles per body in the field order of
+   include/nbk.h: t m q(3) p(3) h hmax t0 dVdq0(3) dVdq1(3) dVdq2(3) p0(3) q0(3) q1(3) q2(3) cs(3) *)
+type perm = (int32, int32_elt, c_layout) Array1.t
+external adv_upload : ctx -> vec -> unit = "nbk_ml_adv_upload"
+external adv_download : ctx -> int -> int -> vec -> unit = "nbk_ml_adv_download"
+external adv_permute : ctx -> perm -> unit = "nbk_ml_adv_permute"
+external adv_begin_step : ctx -> int -> int -> float -> unit = "nbk_ml_adv_begin_step"
+external adv_interact : ctx -> int -> int -> float -> float -> float -> unit
+  = "nbk_ml_adv_interact_bc" "nbk_ml_adv_interact"
+external adv_finish : ctx -> int -> int -> float -> vec -> unit = "nbk_ml_adv_finish"
+external adv_get_t : ctx -> int -> float = "nbk_ml_adv_get_t"
+external adv_init_first : ctx -> float -> unit = "nbk_ml_adv_init_first"
+external adv_range_max : unit -> int = "nbk_ml_adv_range_max"
+(* [adv_advance_range ctx dt sf eps2 hmax perm]: advance_range bs imax dt sf None
+   (advancer.ml:316-350) ENTIRELY on the device for the prefix of imax = dim hmax rows; hmax: in,
+   the prefix's hmax, out, the new hmax in the new order; perm: out, new row s = old row perm.{s} *)
+external adv_advance_range : ctx -> float -> float -> float -> vec -> perm -> unit
+  = "nbk_ml_adv_advance_range_bc" "nbk_ml_adv_advance_range"
+
+(* Leapfrog with the bodies resident on the device (leapfrog.ml:106-158) *)
+external lf_upload : ctx -> vec -> vec -> vec -> vec -> unit = "nbk_ml_lf_upload"
+external lf_download : ctx -> vec -> vec -> vec -> unit = "nbk_ml_lf_download"
+(* [lf_advance_subsystem ctx dt eta t dt_max perm]: advance_subsystem dt eta bs iend
+   (leapfrog.ml:119-142) ENTIRELY on the device for iend = dim t <= nbk_lf_subsystem_max bodies *)
+external lf_advance_subsystem : ctx -> float -> float -> vec -> vec -> perm -> unit
+  = "nbk_ml_lf_advance_subsystem_bc" "nbk_ml_lf_advance_subsystem"
+
 (* One context per process, created on first use (the reference is single-threaded and keeps
    its configuration in globals such as Base.eps2, base.ml:20-34). *)
 let the_ctx = lazy (create 0)

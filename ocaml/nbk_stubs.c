@@ -216,3 +216,130 @@ CAMLprim value nbk_ml_oa_diagnostics(value ctx, value eps2, value el) {
   Store_field(res, 1, caml_copy_double(pe));
   CAMLreturn(res);
 }
+
+/* ---- Advancer.A (advancer.ml:207-428) --------------------------------------------------------- */
+/* external interact_sum : ctx -> m -> q -> na:int -> eps2:float -> s -> unit
+ * bodies [imin, n) re-indexed from 0, the first na of them active (advancer.ml:213-235) */
+CAMLprim value nbk_ml_interact_sum(value ctx, value m, value q, value na, value eps2, value s) {
+  CAMLparam5(ctx, m, q, na, eps2);
+  CAMLxparam1(s);
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx), nbk_interact_sum(Ctx_val(ctx), n, Int_val(na), D(m), D(q), Double_val(eps2), D(s)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_interact_sum_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_interact_sum(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
+/* Records resident on the device: records = Bigarray of n*35 doubles in the field order of
+ * include/nbk.h (t, m, q, p, h, hmax, t0, dVdq0-2, p0, q0, q1, q2, cs). */
+/* external adv_upload : ctx -> records -> unit */
+CAMLprim value nbk_ml_adv_upload(value ctx, value rec) {
+  CAMLparam2(ctx, rec);
+  int n = (int)(Caml_ba_array_val(rec)->dim[0] / 35);
+  check(Ctx_val(ctx), nbk_adv_upload(Ctx_val(ctx), n, D(rec)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_download : ctx -> i0:int -> i1:int -> records -> unit */
+CAMLprim value nbk_ml_adv_download(value ctx, value i0, value i1, value rec) {
+  CAMLparam4(ctx, i0, i1, rec);
+  check(Ctx_val(ctx), nbk_adv_download(Ctx_val(ctx), Int_val(i0), Int_val(i1), D(rec)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_permute : ctx -> (int32, c_layout) Array1 -> unit */
+CAMLprim value nbk_ml_adv_permute(value ctx, value perm) {
+  CAMLparam2(ctx, perm);
+  int n = (int)Caml_ba_array_val(perm)->dim[0];
+  check(Ctx_val(ctx), nbk_adv_permute(Ctx_val(ctx), n, (const int *)Caml_ba_data_val(perm)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_begin_step : ctx -> imin:int -> imax:int -> hnew:float -> unit */
+CAMLprim value nbk_ml_adv_begin_step(value ctx, value imin, value imax, value hnew) {
+  CAMLparam4(ctx, imin, imax, hnew);
+  check(Ctx_val(ctx), nbk_adv_begin_step(Ctx_val(ctx), Int_val(imin), Int_val(imax), Double_val(hnew)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_interact : ctx -> imin:int -> imax:int -> t:float -> vC:float -> eps2:float -> unit */
+CAMLprim value nbk_ml_adv_interact(value ctx, value imin, value imax, value t, value vC, value eps2) {
+  CAMLparam5(ctx, imin, imax, t, vC);
+  CAMLxparam1(eps2);
+  check(Ctx_val(ctx), nbk_adv_interact(Ctx_val(ctx), Int_val(imin), Int_val(imax), Double_val(t),
+                                       Double_val(vC), Double_val(eps2)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_adv_interact_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_adv_interact(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+/* external adv_finish : ctx -> imin:int -> imax:int -> t:float -> records -> unit
+ * (records receives the (imax-imin)*35 finished doubles) */
+CAMLprim value nbk_ml_adv_finish(value ctx, value imin, value imax, value t, value rec) {
+  CAMLparam5(ctx, imin, imax, t, rec);
+  check(Ctx_val(ctx), nbk_adv_finish(Ctx_val(ctx), Int_val(imin), Int_val(imax), Double_val(t), D(rec)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_get_t : ctx -> int -> float */
+CAMLprim value nbk_ml_adv_get_t(value ctx, value i) {
+  CAMLparam2(ctx, i);
+  double t = 0.0;
+  check(Ctx_val(ctx), nbk_adv_get_t(Ctx_val(ctx), Int_val(i), &t));
+  CAMLreturn(caml_copy_double(t));
+}
+/* external adv_init_first : ctx -> eps2:float -> unit */
+CAMLprim value nbk_ml_adv_init_first(value ctx, value eps2) {
+  CAMLparam2(ctx, eps2);
+  check(Ctx_val(ctx), nbk_adv_init_first(Ctx_val(ctx), Double_val(eps2)));
+  CAMLreturn(Val_unit);
+}
+/* external adv_range_max : unit -> int */
+CAMLprim value nbk_ml_adv_range_max(value unit) {
+  (void)unit;
+  return Val_int(nbk_adv_range_max());
+}
+/* external adv_advance_range : ctx -> dt:float -> sf:float -> eps2:float -> hmax -> perm -> unit
+ * advance_range bs imax dt sf None on the device, imax = dim hmax = dim perm (int32) */
+CAMLprim value nbk_ml_adv_advance_range(value ctx, value dt, value sf, value eps2, value hmax,
+                                        value perm) {
+  CAMLparam5(ctx, dt, sf, eps2, hmax);
+  CAMLxparam1(perm);
+  int imax = (int)Caml_ba_array_val(hmax)->dim[0];
+  check(Ctx_val(ctx), nbk_adv_advance_range(Ctx_val(ctx), imax, Double_val(dt), Double_val(sf),
+                                            Double_val(eps2), D(hmax), (int *)Caml_ba_data_val(perm),
+                                            NULL));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_adv_advance_range_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_adv_advance_range(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
+/* ---- Leapfrog with the bodies resident on the device (leapfrog.ml:106-158) --------------------- */
+/* external lf_upload : ctx -> dt_max -> m -> q -> v -> unit */
+CAMLprim value nbk_ml_lf_upload(value ctx, value dtm, value m, value q, value v) {
+  CAMLparam5(ctx, dtm, m, q, v);
+  int n = (int)Caml_ba_array_val(m)->dim[0];
+  check(Ctx_val(ctx), nbk_lf_upload(Ctx_val(ctx), n, D(dtm), D(m), D(q), D(v)));
+  CAMLreturn(Val_unit);
+}
+/* external lf_download : ctx -> dt_max -> q -> v -> unit */
+CAMLprim value nbk_ml_lf_download(value ctx, value dtm, value q, value v) {
+  CAMLparam4(ctx, dtm, q, v);
+  check(Ctx_val(ctx), nbk_lf_download(Ctx_val(ctx), D(dtm), D(q), D(v)));
+  CAMLreturn(Val_unit);
+}
+/* external lf_advance_subsystem : ctx -> dt:float -> eta:float -> t -> dt_max -> perm -> unit
+ * advance_subsystem dt eta bs iend on the device, iend = dim t = dim dt_max = dim perm (int32) */
+CAMLprim value nbk_ml_lf_advance_subsystem(value ctx, value dt, value eta, value t, value dtm,
+                                           value perm) {
+  CAMLparam5(ctx, dt, eta, t, dtm);
+  CAMLxparam1(perm);
+  int iend = (int)Caml_ba_array_val(t)->dim[0];
+  check(Ctx_val(ctx), nbk_lf_advance_subsystem(Ctx_val(ctx), iend, Double_val(dt), Double_val(eta),
+                                               D(t), D(dtm), (int *)Caml_ba_data_val(perm), NULL));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nbk_ml_lf_advance_subsystem_bc(value *a, int n) {
+  (void)n;
+  return nbk_ml_lf_advance_subsystem(a[0], a[1], a[2], a[3], a[4], a[5]);
+}

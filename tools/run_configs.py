@@ -93,6 +93,29 @@ with nbk.Context(0) as ctx:
                 "ms_per_step_oracle_1core_n4096": 1e3 * tc / nst})
     print(res[-1], flush=True)
 
+    # ---- configs[1], adaptive: Leapfrog.advance with block time steps, coarse eta; the oracle's
+    # sequential-kick run beside it on the first 1024 bodies (statistical agreement: dt_max sees
+    # pre-kick velocities on the GPU path)
+    span, eta = (1.0 / 1024, 2e-2) if quick else (1.0 / 256, 2e-2)
+    t0 = time.perf_counter()
+    a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), span, eta)
+    tg = time.perf_counter() - t0
+    ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
+    n_o = 1024
+    mo, qo, po = O.rescale_to_standard_units(m[:n_o], q[:n_o], p[:n_o])
+    t0 = time.perf_counter()
+    bo = O.leapfrog_advance(O.LeapfrogState(mo, qo, po), span, eta)
+    tc = time.perf_counter() - t0
+    bg = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(mo, qo, po), span, eta)
+    res.append({"config": "1b", "what": f"Leapfrog.advance (block steps) span={span:g}, eta={eta:g}, Plummer N=16384",
+                "kick_blocks_n16384": a.nkicks, "wall_gpu_s_n16384": tg,
+                "dE_gpu_n16384": abs((ke + pe + 0.25) / 0.25),
+                "n_oracle": n_o, "kick_blocks_gpu_n1024": bg.nkicks,
+                "dE_gpu_n1024": abs((sum(nbh.energy(ctx, bg.m, bg.q, bg.p)) + 0.25) / 0.25),
+                "dE_oracle_n1024": abs((O.energy(bo.m, bo.q, bo.p) + 0.25) / 0.25),
+                "wall_oracle_1core_s_n1024": tc})
+    print(res[-1], flush=True)
+
     # ---- configs[3]: two-mass Plummer N=65536, Omelyan advancer, per-step energy diagnostics
     n = 16384 if quick else 65536
     m, q, p = nbh.make_plummer(n, 20243 + 1)
