@@ -51,7 +51,7 @@ let to_records bs =
 
 let of_record r o b hmax =
   let get3 o = Array.init 3 (fun k -> r.{o + k}) in
-  { b with t = r.{o}; q = get3 (o + 2); p = get3 (o + 5); h = r.{o + 8}; hmax = hmax;
+  { b with t = r.{o}; m = r.{o + 1}; q = get3 (o + 2); p = get3 (o + 5); h = r.{o + 8}; hmax = hmax;
            t0 = r.{o + 10}; dVdq0 = get3 (o + 11); dVdq1 = get3 (o + 14); dVdq2 = get3 (o + 17);
            p0 = get3 (o + 20); q0 = get3 (o + 23); q1 = get3 (o + 26); q2 = get3 (o + 29);
            cs = get3 (o + 32) }
@@ -65,6 +65,8 @@ let apply_perm st count perm =
     st.hmax.(s) <- h.(perm s); st.who.(s) <- w.(perm s)
   done
 
+let compare_hmax h1 h2 = if h1 < h2 then -1 else if h1 > h2 then 1 else 0
+
 (* sort_range bs hmax_lt 0 imax: stable; the device rows follow *)
 let sort_prefix st imax =
   let idx = Array.init imax (fun i -> i) in
@@ -75,7 +77,6 @@ let sort_prefix st imax =
     Nbk.adv_permute st.c p;
     apply_perm st imax (fun s -> idx.(s))
   end
-and compare_hmax h1 h2 = if h1 < h2 then -1 else if h1 > h2 then 1 else 0
 
 (* h_adaptive (advancer.ml:272-281) from a finished record *)
 let h_adaptive_of_record sf r o =
