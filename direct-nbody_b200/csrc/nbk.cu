@@ -1483,9 +1483,26 @@ int nbk_adv_advance_range(nbk_ctx *ctx, int imax, double dt, double sf, double e
   P.dt = dt;
   P.sf = sf;
   P.eps2 = eps2;
+  P.cluster = (G <= 8 && !getenv("NBK_ADT_NOCLUSTER")) ? 1 : 0;
   void *args[] = {&P};
   const void *kern = T <= 256 ? (const void *)adv_tree_kernel<256> : (const void *)adv_tree_kernel<512>;
-  CK(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(T), args, ADT_SMEM, st));
+  if (P.cluster) {  // the whole grid as one thread-block cluster: hardware barrier between the phases
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = ADT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelExC(&cfg, kern, args));
+  } else {
+    CK(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(T), args, ADT_SMEM, st));
+  }
   ctx->launches++;  // the kernel also writes the rows back in their new order (sort_range's moves)
   long long out[16] = {0};
   CK(cudaMemcpyAsync(hmax, P.hmax_out, (size_t)imax * sizeof(double), cudaMemcpyDeviceToHost, st));

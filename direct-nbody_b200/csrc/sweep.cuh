@@ -1995,6 +1995,7 @@ struct AdvTreeParams {
                                // then CTA 0's clock cycles per phase: control, P1, barrier, P2 A,
                                // P2 B, barrier, P3, barrier, sort
   int n, imax;
+  int cluster;  // the grid is one thread-block cluster (<= 8 CTAs)
   double dt, sf, eps2;
 };
 struct AdvFrame {
@@ -2023,6 +2024,10 @@ __device__ __forceinline__ void adv_grid_barrier(unsigned long long *bar, unsign
     __threadfence();
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void adv_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ double adv_sort_key(double h) { return h != h ? __longlong_as_double(0x7ff0000000000000LL) : h; }
@@ -2120,15 +2125,30 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
   const int n = P.n, top = P.imax;
   const double eps2 = P.eps2;
   unsigned long long nbar = 0;
-  long long n_int = 0, n_pair = 0, n_step = 0;
+  // up to 8 CTAs are launched as ONE thread-block cluster: the hardware cluster barrier (release /
+  // acquire at cluster scope) replaces the atomic counter in L2
+#define ADT_SYNC()                                                       \
+  do {                                                                   \
+    if (P.cluster) adv_cluster_barrier();                                \
+    else adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);        \
+  } while (0)
+  int n_int = 0;  // interacts so far (its parity picks the T_a / partial-sum buffers)
+  __shared__ long long s_cnt[2];  // thread 0's counters: pair interactions, block steps
   int pend_imin = 0, pend_na = 0, pend_gc = 0;  // the previous interact's fold, still to be done
   const double *pend_tact = nullptr, *pend_part = nullptr;
-  long long cyc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, c_prev = clock64();
-#define ADT_TICK(k)                     \
-  do {                                  \
-    const long long c_now = clock64();  \
-    cyc[k] += c_now - c_prev;           \
-    c_prev = c_now;                     \
+  __shared__ long long s_cyc[10];  // thread 0's cycle counters per phase, [9] = the last reading
+  if (tid == 0) {
+    for (int k = 0; k < 9; ++k) s_cyc[k] = 0;
+    s_cyc[9] = clock64();
+    s_cnt[0] = s_cnt[1] = 0;
+  }
+#define ADT_TICK(k)                       \
+  do {                                    \
+    if (tid == 0) {                       \
+      const long long c_now = clock64();  \
+      s_cyc[k] += c_now - s_cyc[9];       \
+      s_cyc[9] = c_now;                   \
+    }                                     \
   } while (0)
 
   for (int i = tid; i < top; i += T) {
@@ -2144,7 +2164,7 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     const size_t row = e / AB;
     P.soa[(e - row * AB) * LD + row] = __ldcg(P.rec + e);
   }
-  adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+  ADT_SYNC();
 
   for (;;) {
     // ---- control: warp 0 walks the frames until the next interact_bodies (lane 0 writes) -----
@@ -2225,8 +2245,10 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     const bool begin = ctl.begin != 0, last = ctl.last != 0;
     const double t = ctl.t, vC = ctl.vC, hnew = ctl.hnew;
     n_int += 1;
-    n_step += last ? 1 : 0;
-    n_pair += (long long)na * (n - imin - 1) - (long long)na * (na - 1) / 2;
+    if (tid == 0) {
+      s_cnt[0] += (long long)na * (n - imin - 1) - (long long)na * (na - 1) / 2;
+      s_cnt[1] += last ? 1 : 0;
+    }
 
     double *tactb = P.tact + (size_t)(n_int & 1) * ADT_MAX * 6;
     double *partb = P.partial + (size_t)(n_int & 1) * G * ADT_MAX * 3;
@@ -2370,7 +2392,7 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     if ((int)blockIdx.x < Gc)
       for (int e = tid; e < 3 * na; e += T) partb[(size_t)blockIdx.x * ADT_MAX * 3 + e] = racc[e];
     ADT_TICK(4);
-    adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+    ADT_SYNC();
     ADT_TICK(5);
     if (na == 0) continue;  // hmax = dt exactly: an empty block (advancer.ml:321-328), nothing to fold
 
@@ -2390,7 +2412,7 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
         adv_fold_row(AdvRowSoA{P.soa + ms[imin + a], LD}, tactb + (size_t)a * 6,
                      partb + (size_t)a * 3, Gc, lane, false, 0.0, 0.0, nullptr);
       ADT_TICK(6);
-      adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+      ADT_SYNC();
       ADT_TICK(7);
       continue;
     }
@@ -2400,7 +2422,7 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     pend_na = 0;
     ADT_TICK(6);
     if (last) {
-      adv_grid_barrier(P.bar, (unsigned long long)G * ++nbar);
+      ADT_SYNC();
       ADT_TICK(7);
       for (int i = imin + tid; i < imax; i += T) hs[i] = __ldcg(P.hmax + i);
       __syncthreads();
@@ -2469,10 +2491,10 @@ __global__ void __launch_bounds__(NTMAX, 1) adv_tree_kernel(const AdvTreeParams 
     }
     if (tid == 0) {
       P.out[0] = n_int;
-      P.out[1] = n_pair;
+      P.out[1] = s_cnt[0];
       P.out[2] = ctl.op;  // 0 done, -1 recursion deeper than ADT_DEPTH, -2 empty block at the array's end
-      P.out[3] = n_step;
-      for (int k = 0; k < 9; ++k) P.out[4 + k] = cyc[k];
+      P.out[3] = s_cnt[1];
+      for (int k = 0; k < 9; ++k) P.out[4 + k] = s_cyc[k];
     }
   }
 }
