@@ -459,3 +459,24 @@ def test_advancer_block_recursion_on_device_wide_grids(ctx, oracle, n):
     b = nbh.advancer_advance(ctx, s0, span, 1e-4, 1e-6, resident=1)
     assert a.stats == b.stats and np.all(a.t == span) and a.stats[0] > 500
     assert_records_close(a, b)
+
+
+def test_device_recursion_argument_and_state_errors():
+    """nbk_adv_advance_range / nbk_lf_advance_subsystem on a context with nothing uploaded, and
+    with prefixes beyond their limits: an error code and a message, never a launch."""
+    import ctypes as C
+    import nbk
+    lib = nbk.load_library()
+    with nbk.Context(0) as c:
+        h = (C.c_double * 4)(1.0, 1.0, 1.0, 1.0)
+        perm = (C.c_int * 4)()
+        assert lib.nbk_adv_advance_range(c._h, 4, 0.5, 1e-4, 0.0, h, perm, None) == -4  # NBK_ERR_STATE
+        assert b"nbk_adv_upload" in lib.nbk_last_error(c._h)
+        assert lib.nbk_lf_advance_subsystem(c._h, 4, 0.5, 1e-3, h, h, perm, None) == -4
+        rec = np.zeros((8, nbh.ADV_STRIDE))
+        rec[:, 1] = 1.0
+        assert lib.nbk_adv_upload(c._h, 8, rec.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert lib.nbk_adv_advance_range(c._h, 9, 0.5, 1e-4, 0.0, h, perm, None) == -1  # imax > n
+        assert lib.nbk_adv_advance_range(c._h, 4, -1.0, 1e-4, 0.0, h, perm, None) == -1
+        assert lib.nbk_adv_advance_range(c._h, 4, 0.5, 1e-4, 0.0, None, perm, None) == -1
+        assert lib.nbk_adv_range_max() == 1024 and lib.nbk_lf_subsystem_max() == 1024
