@@ -547,3 +547,77 @@ def advancer_advance(m, q, p, dt, sf, eps2, t=0.0):  # A.make then A.advance (ad
     bs = _stable_sort(bs, _hmax_lt)
     _advance_range(bs, len(bs), dt, sf, eps2, stats)
     return bs, stats
+
+
+# ---- analysis.ml ------------------------------------------------------------------------------------
+def binary_energy(m1, q1, p1, m2, q2, p2, eps2):  # analysis.ml:809-822
+    vrel = [0.0] * 3
+    for i in range(3):
+        vrel[i] = p2[i] / m2 - p1[i] / m1
+    mu = m1 * m2 / (m1 + m2)
+    ke = 0.5 * mu * dot(vrel, vrel)
+    pe = v(m1, q1, m2, q2, eps2)
+    return ke + pe
+
+
+def binaries_threshold(m, q, p, eps2, eg):  # analysis.ml:849-861, pairs in loop order
+    out = []
+    n = len(m)
+    for i in range(n):
+        for j in range(i + 1, n):
+            e = binary_energy(m[i], q[i], p[i], m[j], q[j], p[j], eps2)
+            if e < -abs(eg):
+                out.append((i, j, e))
+    return out
+
+
+def bodies_to_el_phase_space(m, q, p, eps2):  # analysis.ml:904-919 (+ :539-543, energy.ml:57-58)
+    n = len(m)
+    out = []
+    for i in range(n):
+        qi, pi = q[i], p[i]
+        lvec = [qi[1] * pi[2] - qi[2] * pi[1], qi[2] * pi[0] - qi[0] * pi[2], qi[0] * pi[1] - qi[1] * pi[0]]
+        lb = norm(lvec)
+        ke = norm_squared(pi) / (2.0 * m[i])
+        pe = 0.0
+        for j in range(i):
+            pe = pe + v(m[i], qi, m[j], q[j], eps2)
+        for j in range(i + 1, n):
+            pe = pe + v(m[i], qi, m[j], q[j], eps2)
+        etot = ke + pe
+        out.append([etot, etot / m[i], lb, lb / m[i]])
+    return out
+
+
+# ---- ics.ml -------------------------------------------------------------------------------------------
+def adjust_frame(m, q, p):  # ics.ml:161-175 over analysis.ml:508-537
+    n = len(m)
+    p_tot = [0.0] * 3
+    for b in range(n):
+        for i in range(3):
+            p_tot[i] = p_tot[i] + p[b][i]
+    m_tot = 0.0
+    for b in range(n):
+        m_tot = m_tot + m[b]
+    com = [0.0] * 3
+    for b in range(n):
+        for i in range(3):
+            com[i] = com[i] + q[b][i] * (m[b] / m_tot)
+    qn = [[q[b][i] - com[i] for i in range(3)] for b in range(n)]
+    pn = [[p[b][i] - p_tot[i] * m[b] / m_tot for i in range(3)] for b in range(n)]
+    return list(m), qn, pn
+
+
+def rescale_to_standard_units(m, q, p, eps2):  # ics.ml:304-331
+    n = len(m)
+    mtot = 0.0
+    for b in range(n):
+        mtot = mtot + m[b]
+    mn = [m[b] / mtot for b in range(n)]
+    pn = [[p[b][i] * mn[b] / m[b] for i in range(3)] for b in range(n)]
+    e = total_kinetic_energy(mn, pn) + total_potential_energy(mn, q, eps2)
+    assert e < 0.0
+    efactor = (-0.25) / e
+    q2 = [[q[b][i] / efactor for i in range(3)] for b in range(n)]
+    p2 = [[pn[b][i] * math.sqrt(efactor) for i in range(3)] for b in range(n)]
+    return mn, q2, p2

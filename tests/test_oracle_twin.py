@@ -74,3 +74,27 @@ def test_advancer_advance_bitwise(oracle, bodies):
             "q2": 29, "cs": 32}
     for k, c in vecs.items():
         assert np.array_equal(a.state[:, c:c + 3], np.array([b[k] for b in bs])), k
+
+
+def test_analysis_bitwise(oracle, bodies):
+    """Analysis.binary_energy / binaries_threshold / bodies_to_el_phase_space (analysis.ml:809-919)."""
+    m, q, p, eps2 = bodies
+    el = oracle.bodies_to_el_phase_space(m, q, p, eps2)
+    assert np.array_equal(el, np.array(twin.bodies_to_el_phase_space(list(m), lists(q), lists(p), eps2)))
+    pi, pj, e = oracle.binaries(m, q, p, eps2, 0.0)
+    ref = twin.binaries_threshold(list(m), lists(q), lists(p), eps2, 0.0)
+    assert list(zip(pi.tolist(), pj.tolist())) == [(i, j) for i, j, _ in ref]
+    assert np.array_equal(e, np.array([x for _, _, x in ref]))
+
+
+def test_ics_frame_and_units_bitwise(oracle):
+    """Ics.adjust_frame and rescale_to_standard_units (ics.ml:161-175, 304-331) on raw draws."""
+    m, q, p = oracle.make_plummer(9, 77)
+    a = oracle.adjust_frame(m, q, p)
+    t = twin.adjust_frame(list(m), lists(q), lists(p))
+    for x, y in zip(a, t):
+        assert np.array_equal(np.asarray(x), np.array(y))
+    b = oracle.rescale_to_standard_units(*a, eps2=0.0025)
+    u = twin.rescale_to_standard_units(*t, 0.0025)
+    for x, y in zip(b, u):
+        assert np.array_equal(np.asarray(x), np.array(y))
