@@ -1724,8 +1724,12 @@ int nbk_lf_advance_subsystem(nbk_ctx *ctx, int iend, double dt, double eta, doub
   cudaStream_t st = ctx->stream;
   const bool ts = !(std::isinf(eta) && eta > 0);
   if (!ctx->lft_attr_set) {
-    CK(cudaFuncSetAttribute(lf_tree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
-    CK(cudaFuncSetAttribute(lf_tree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
+    CK(cudaFuncSetAttribute(lf_tree_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
+    CK(cudaFuncSetAttribute(lf_tree_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LFT_SMEM));
+    CK(cudaFuncSetAttribute(lf_tree_kernel<true, LFT_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)LFT_SMEM));
+    CK(cudaFuncSetAttribute(lf_tree_kernel<false, LFT_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)LFT_SMEM));
     ctx->lft_attr_set = true;
   }
   CK(cudaMemcpyAsync(w, t, (size_t)iend * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1739,8 +1743,32 @@ int nbk_lf_advance_subsystem(nbk_ctx *ctx, int iend, double dt, double eta, doub
   P.iend = iend;
   P.dt = dt;
   P.eta = eta;
-  if (ts) lf_tree_kernel<true><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
-  else lf_tree_kernel<false><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
+  // narrow prefixes: one CTA; wider ones: a cluster of LFT_CLUSTER CTAs that share out the targets
+  // of every kick block (NBK_LFT_CLUSTER=0/1 forces either - a knob for tests and profiles)
+  bool use_cluster = iend > 96;
+  if (const char *e = getenv("NBK_LFT_CLUSTER")) use_cluster = atoi(e) != 0;
+  if (use_cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(LFT_CLUSTER);
+    cfg.blockDim = dim3(LFT_THREADS);
+    cfg.dynamicSmemBytes = LFT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = LFT_CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void *args[] = {&P};
+    const void *kern = ts ? (const void *)lf_tree_kernel<true, LFT_CLUSTER>
+                          : (const void *)lf_tree_kernel<false, LFT_CLUSTER>;
+    CK(cudaLaunchKernelExC(&cfg, kern, args));
+  } else if (ts) {
+    lf_tree_kernel<true, 1><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
+  } else {
+    lf_tree_kernel<false, 1><<<1, LFT_THREADS, LFT_SMEM, st>>>(P);
+  }
   CK(cudaGetLastError());
   ctx->launches++;
   long long out[2] = {0, 0};

@@ -2554,12 +2554,13 @@ __global__ void lf_apply_kernel(double *__restrict__ packed, double *__restrict_
 // the pre-kick state, bit-exact pair time-scales), dt_max updates, stable sort_sub.  Rows stay
 // where they are; the sorts permute a slot -> row map (and dt_max, t), applied when the rows are
 // written back.  Kick block, targets [0, iend) with active block [ibegin, iend):
-//   B: active slot a against the passive slots [0, ibegin): SPLIT lanes per target take sources
-//      s, s+SPLIT, ..., fixed shuffle tree (sum of dv, min of the time-scale);
-//   A: every slot against the active block, one thread per slot; an active slot then adds B.
+// an active slot sums every other slot of [0, iend), a passive one the active block; SPLIT lanes
+// share a target and take sources s, s+SPLIT, ..., combined by a fixed shuffle tree (sum of dv,
+// min of the time-scale).
 constexpr int LFT_MAX = 1024;
 constexpr int LFT_THREADS = 512;
 constexpr int LFT_DEPTH = 160;
+constexpr int LFT_CLUSTER = 8;  // CTAs of the cluster variant (wide subtrees)
 
 struct LfTreeParams {
   double *packed;   // [iend][PK] in/out, array order
@@ -2582,9 +2583,18 @@ __device__ __forceinline__ double lf_sort_key(double d) {
   return d != d ? __longlong_as_double(0xfff0000000000000LL) : d;
 }
 
-template <bool TS>
+// NC = 1: one CTA.  NC = LFT_CLUSTER: the grid is ONE thread-block cluster; every CTA keeps a full
+// replica of the state and runs the same control flow, but a kick block's targets are dealt out
+// (slot x belongs to CTA x mod NC): a CTA sums, applies and drifts its own slots, then - behind a
+// cluster barrier, once nobody reads the old rows any more - stores the updated rows, dt_max and
+// t into the other replicas through distributed shared memory, and a second cluster barrier
+// publishes them.  Wide blocks run NC times faster; the sums per slot are the same in both.
+template <bool TS, int NC>
 __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreeParams P) {
   using Op = OpKick<TS>;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = NC > 1 ? (int)cluster.block_rank() : 0;
   extern __shared__ __align__(16) unsigned char lft_smem[];
   double *rows = reinterpret_cast<double *>(lft_smem);  // [LFT_MAX][PK]
   double *dtm = rows + (size_t)LFT_MAX * PK;           // dt_max, slot order
@@ -2681,22 +2691,34 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
         b[2] = __dadd_rn(b[2], __dmul_rn(dt2, b[6]));
       }
       __syncthreads();
-      // B: active slots against the passive slots
-      for (int a0 = 0; a0 < na; a0 += T) {
-        const int nac = min(T, na - a0);
+      // the kick sums of this CTA's slots x = rank, rank + NC, ...: an active slot against every
+      // other slot of [0, iend), a passive one against the active block.  SPLIT lanes share a
+      // target (sources lo + s, lo + s + SPLIT, ...), combined by a fixed shuffle tree (sum of
+      // dv, min of the time-scale) and, beyond a warp, a fixed pass over the warps.  The running
+      // minimum starts from the slot's current dt_max - nothing above it matters (:103-104) - so
+      // the FP32 filter rejects most pairs of a passive slot at once.
+      const int nslots = rank < iend ? (iend - rank + NC - 1) / NC : 0;
+      for (int u0 = 0; u0 < nslots; u0 += T) {
+        const int nac = min(T, nslots - u0);
         int napad = 1;
         while (napad < nac) napad <<= 1;
         const int SPLIT = T / napad;
-        const int al = tid / SPLIT, s = tid - al * SPLIT;
-        const bool live = al < nac;
+        const int ul = tid / SPLIT, sl = tid - ul * SPLIT;
+        const bool live = ul < nac;
+        const int x = rank + NC * (u0 + ul);
         double acc[5];
         Op::zero(acc);
-        if (live && ibegin > 0) {
+        if (live) {
           typename Op::Tgt tg;
-          Op::load(tg, rows + (size_t)ms[ibegin + a0 + al] * PK, SP, 0);
-          for (int k = s; k < ibegin; k += SPLIT)
-            Op::template pair<false>(tg, acc, reinterpret_cast<const double2 *>(rows + (size_t)ms[k] * PK),
-                                     nullptr, false, SP);
+          Op::load(tg, rows + (size_t)ms[x] * PK, SP, 0);
+          if (TS) {
+            acc[3] = dtm[x];  // infinity for an active slot (reset in stage 0)
+            acc[4] = Op::filter_state(acc[3]);
+          }
+          const int lo = x >= ibegin ? 0 : ibegin;
+          for (int k = lo + sl; k < iend; k += SPLIT)
+            Op::template pair<true>(tg, acc, reinterpret_cast<const double2 *>(rows + (size_t)ms[k] * PK),
+                                    nullptr, k == x, SP);
         }
         const int width = SPLIT < 32 ? SPLIT : 32;
         for (int off = width >> 1; off > 0; off >>= 1) {
@@ -2728,14 +2750,14 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
               const double o = red[4 * (tid * wpt + w) + 3];
               if (q3 > o) q3 = o;
             }
-            double *r = res + 4 * (size_t)(ibegin + a0 + tid);
+            double *r = res + 4 * (size_t)(rank + NC * (u0 + tid));
             r[0] = q0;
             r[1] = q1;
             r[2] = q2;
             r[3] = q3;
           }
-        } else if (live && s == 0) {
-          double *r = res + 4 * (size_t)(ibegin + a0 + al);
+        } else if (live && sl == 0) {
+          double *r = res + 4 * (size_t)x;
           r[0] = acc[0];
           r[1] = acc[1];
           r[2] = acc[2];
@@ -2743,31 +2765,8 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
         }
       }
       __syncthreads();
-      // A: every slot against the active block
-      for (int x = tid; x < iend; x += T) {
-        typename Op::Tgt tg;
-        Op::load(tg, rows + (size_t)ms[x] * PK, SP, 0);
-        double acc[5];
-        Op::zero(acc);
-        for (int y = ibegin; y < iend; ++y)
-          Op::template pair<true>(tg, acc, reinterpret_cast<const double2 *>(rows + (size_t)ms[y] * PK),
-                                  nullptr, y == x, SP);
-        double *r = res + 4 * (size_t)x;
-        double tmin = TS ? acc[3] : INF;
-        if (x >= ibegin) {  // passive part first, then the active part
-          acc[0] = r[0] + acc[0];
-          acc[1] = r[1] + acc[1];
-          acc[2] = r[2] + acc[2];
-          if (tmin > r[3]) tmin = r[3];
-        }
-        r[0] = acc[0];
-        r[1] = acc[1];
-        r[2] = acc[2];
-        r[3] = tmin;
-      }
-      __syncthreads();
       // v += dv; dt_max = min(dt_max, tmin) (leapfrog.ml:103-104); second half drift of the block
-      for (int i = tid; i < iend; i += T) {
+      for (int i = rank + NC * tid; i < iend; i += NC * T) {
         double *b = rows + (size_t)ms[i] * PK;
         const double *r = res + 4 * (size_t)i;
         b[4] = __dadd_rn(b[4], dt * r[0]);
@@ -2785,6 +2784,17 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
           b[2] = __dadd_rn(b[2], __dmul_rn(dt2, b[6]));
         }
       }
+      if constexpr (NC > 1) {
+        cluster.sync();  // every CTA is done reading the old rows
+        // own slots -> the other replicas: {q, m, v} row, dt_max, t  (10 doubles per slot)
+        for (int e = tid; e < nslots * 10 * (NC - 1); e += T) {
+          const int peer0 = e % (NC - 1), w = (e / (NC - 1)) % 10, i = rank + NC * (e / (10 * (NC - 1)));
+          const int peer = peer0 + (peer0 >= rank ? 1 : 0);
+          double *src = w < 8 ? rows + (size_t)ms[i] * PK + w : (w == 8 ? dtm + i : tt + i);
+          *cluster.map_shared_rank(src, peer) = *src;
+        }
+        cluster.sync();  // the replicas agree again
+      }
       nk += 1;
     }
     if (sp >= LFT_DEPTH) {
@@ -2799,15 +2809,18 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
     __syncthreads();
   }
   __syncthreads();
-  for (int e = tid; e < top * PK; e += T) P.packed[e] = rows[(size_t)ms[e / PK] * PK + (e % PK)];
-  for (int i = tid; i < top; i += T) {
-    P.dt_max[i] = dtm[i];
-    P.t[i] = tt[i];
-    P.map[i] = ms[i];
-  }
-  if (tid == 0) {
-    P.out[0] = nk;
-    P.out[1] = err;
+  if constexpr (NC > 1) cluster.sync();  // nobody leaves while a peer may still store into its shared memory
+  if (rank == 0) {
+    for (int e = tid; e < top * PK; e += T) P.packed[e] = rows[(size_t)ms[e / PK] * PK + (e % PK)];
+    for (int i = tid; i < top; i += T) {
+      P.dt_max[i] = dtm[i];
+      P.t[i] = tt[i];
+      P.map[i] = ms[i];
+    }
+    if (tid == 0) {
+      P.out[0] = nk;
+      P.out[1] = err;
+    }
   }
 }
 

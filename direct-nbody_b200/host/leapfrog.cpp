@@ -28,7 +28,7 @@ int lf_tree_max() {
   if (g_leapfrog_resident < 2) return 0;
   const int cap = nbk_lf_subsystem_max();
   if (g_leapfrog_tree_max > 0) return std::min(g_leapfrog_tree_max, cap);
-  return cap / 2;  // one CTA: wider blocks are faster through the tiled sweeps
+  return cap;
 }
 
 struct LBody {
