@@ -66,7 +66,7 @@ int nbh_omelyan_advance_steps(nbk_ctx *ctx, int n, const double *m, double *q, d
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks);
 /* 2 (default): the bodies stay on the device (nbk_lf_*) and every subtree of advance_subsystem
- * whose prefix fits (half of nbk_lf_subsystem_max bodies; nbh_set_leapfrog_tree_max to force)
+ * whose prefix fits (nbk_lf_subsystem_max bodies; nbh_set_leapfrog_tree_max to lower)
  * runs in ONE launch (nbk_lf_advance_subsystem); advance_const_dt: once every body has
  * dt_max >= dt the remaining steps run on the device (nbk_resident_leapfrog_steps);
  * 1: resident bodies, block recursion on the host - bit-identical to 0;

@@ -273,9 +273,10 @@ int nbk_lf_kick_block(nbk_ctx *ctx, int iend, int ibegin, double eta, double dt,
 
 /* `advance_subsystem dt eta bs iend` (leapfrog.ml:119-142) ENTIRELY on the device, for a prefix of
  * iend <= nbk_lf_subsystem_max() resident bodies: the call touches no body beyond iend, so one
- * CTA keeps them in shared memory and runs the whole block recursion (find_can_advance_index,
- * the dt_max resets, drifts, every kick block with its dt_max updates, sort_sub) - one launch
- * instead of one launch group and one read-back per kick block.  t[iend]: in/out, the bodies'
+ * CTA - or, beyond 96 bodies, an 8-CTA thread-block cluster with a replica per CTA and the
+ * targets of every kick block dealt out - keeps them in shared memory and runs the whole block
+ * recursion (find_can_advance_index, the dt_max resets, drifts, every kick block with its dt_max
+ * updates, sort_sub): one launch instead of one launch group and one read-back per kick block.  t[iend]: in/out, the bodies'
  * times (the device keeps no t).  dt_max[iend]: out, in the new array order.  perm[iend]: out,
  * new row s = old row perm[s] (the device rows have been moved).  *nkicks += kick blocks.
  * Pair time-scales are bit-exact as in nbk_lf_kick_block; the velocity sums are ordered

@@ -40,7 +40,7 @@ let kick_block eta dt bs ibegin iend =
    The wide top of the recursion is left to the per-block path above (kick_block); the host
    mirror shows the same top with nbk_lf_drift / nbk_lf_kick_block / nbk_lf_permute, for which
    stubs are added the same way. *)
-let lf_subsystem_max = 512
+let lf_subsystem_max = 1024  (* nbk_lf_subsystem_max () *)
 
 (* advance_subsystem dt eta bs iend for iend <= lf_subsystem_max, bodies already uploaded in
    array order.  Updates t, dt_max and the order of bs.(0..iend-1) in place; q and v stay on the
