@@ -98,3 +98,57 @@ def test_ics_frame_and_units_bitwise(oracle):
     u = twin.rescale_to_standard_units(*t, 0.0025)
     for x, y in zip(b, u):
         assert np.array_equal(np.asarray(x), np.array(y))
+
+
+def _closed_form_tangent(m, q, p, dq, dp, eps2):
+    """SURVEY.md §8 a14, in extended precision: per target i the sums over j != i of
+    g = mu r/s^3, dg = mu [w/s^3 - 3 (r.w) r/s^5] and of their first-order variations
+      dg_t  = mu [dr/s^3 - 3 (r.dr) r/s^5]
+      ddg_t = mu [dw/s^3 - 3 (r.dr) w/s^5 - 3 ((dr.w + r.dw) r + (r.w) dr)/s^5 + 15 (r.w)(r.dr) r/s^7]
+    with r = q_i - q_j, w = p_i/m_i - p_j/m_j, dr, dw their variations, s^2 = |r|^2 + eps2."""
+    L = np.longdouble
+    m, q, p, dq, dp = (np.asarray(a, dtype=L) for a in (m, q, p, dq, dp))
+    n = len(m)
+    out = [np.zeros((n, 3), dtype=L) for _ in range(4)]
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                continue
+            mu = m[i] * m[j]
+            r, w = q[i] - q[j], p[i] / m[i] - p[j] / m[j]
+            dr, dw = dq[i] - dq[j], dp[i] / m[i] - dp[j] / m[j]
+            s2 = r @ r + L(eps2)
+            s = np.sqrt(s2)
+            s3, s5, s7 = s * s2, s * s2 * s2, s * s2 * s2 * s2
+            rw, rdr = r @ w, r @ dr
+            out[0][i] += mu * r / s3
+            out[1][i] += mu * (w / s3 - 3 * rw * r / s5)
+            out[2][i] += mu * (dr / s3 - 3 * rdr * r / s5)
+            out[3][i] += mu * (dw / s3 - 3 * rdr * w / s5 - 3 * ((dr @ w + r @ dw) * r + rw * dr) / s5
+                               + 15 * rw * rdr * r / s7)
+    return [np.asarray(o, dtype=np.float64) for o in out]
+
+
+@pytest.mark.parametrize("eps2", [0.0, 1e-3])
+def test_dual_number_tangents_match_closed_forms(oracle, eps2):
+    """The oracle's stand-in for Diff.DFloat (oracle/num.hh: value + one tangent, textbook rules)
+    pushed through DFloatBase.grad_v_dgrad_v (dFloat_advancer.ml:66-81) against the closed-form
+    variations evaluated in extended precision - an independent derivation, so neither the dual
+    arithmetic nor the formula is taken on trust.  And against central differences of the value
+    sums."""
+    rng = np.random.default_rng(5)
+    n = 24
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 11))
+    dq = rng.standard_normal((n, 3))
+    dp = rng.standard_normal((n, 3)) * m[:, None]
+    g, dg, gt, dgt = oracle.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, eps2)
+    cg, cdg, cgt, cdgt = _closed_form_tangent(m, q, p, dq, dp, eps2)
+    for a, b in ((g, cg), (dg, cdg), (gt, cgt), (dgt, cdgt)):
+        assert np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)) <= 1e-13
+    g1, gt1 = oracle.grad_v_sum_tangent(m, q, dq, eps2)
+    assert np.array_equal(g1, g) and np.max(np.abs(gt1 - gt)) <= 1e-13 * np.max(np.abs(gt))
+    h = 1e-6  # central differences of the value sums along (dq, dp)
+    gp, dgp = oracle.grad_v_dgrad_v_sum(m, q + h * dq, p + h * dp, eps2)
+    gm, dgm = oracle.grad_v_dgrad_v_sum(m, q - h * dq, p - h * dp, eps2)
+    assert np.max(np.abs((gp - gm) / (2 * h) - gt)) <= 1e-6 * np.max(np.abs(gt))
+    assert np.max(np.abs((dgp - dgm) / (2 * h) - dgt)) <= 1e-6 * np.max(np.abs(dgt))
