@@ -15,6 +15,7 @@ import nbh  # noqa: E402
 import nbk  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
+assert n >= 1500, "the tour's fixed ranges need n >= 1500"
 m, q, p = nbh.make_plummer(n, 5)
 v = p / m[:, None]
 rng = np.random.default_rng(1)
