@@ -1968,15 +1968,21 @@ __global__ void adv_gather_kernel(const double *__restrict__ src, double *__rest
 //       CTA owns are also its SOURCE tile (straight from registers to shared memory): thread
 //       (a, s) sums tile sources s, s+SPLIT, ... for active a, the SPLIT lanes of a target are
 //       combined by a fixed shuffle tree (+ a fixed pass over warps)                | grid barrier
-//   B   one warp per active slot adds the CTAs' partial sums in a fixed order, folds T_a + R_a
-//       into dVdq0..2 and - after the step's third interact - runs finish_body and h_adaptive.
-//       No barrier before the next interact's phase A: it touches other fields of these rows,
-//       and the T_a / partial-sum buffers alternate between interacts.
+//   B   one warp per active slot adds the CTAs' partial sums in a fixed order and folds T_a + R_a
+//       into dVdq0..2.  For a block of a few slots this is left to phase A of the NEXT interact,
+//       done by the CTA that owns the slot there (its own barrier then orders the fold before
+//       that slot's passive update) - no grid barrier.  A wide block is folded at once by every
+//       warp of the grid, followed by a barrier.  After a step's third interact the fold is
+//       followed by finish_body and h_adaptive on the same registers.  The T_a / partial-sum
+//       buffers alternate between interacts.
 // After a step: one more barrier, every CTA reloads the new hmax and sorts its mirror of
-// (hmax, slot -> row) with the stable rank of sort_range (advancer.ml:290-297).  Rows never move
-// inside the kernel; the host applies the final permutation once.  Sums are reproducible run to
-// run (fixed grid, fixed trees); their order differs from the tiled sweeps', so this path agrees
-// with the per-phase path to rounding (1e-13), not bit for bit.
+// (hmax, slot -> row) with the stable rank of sort_range (advancer.ml:290-297).  The records are
+// transposed into a column-major working copy at entry (a warp's loads of one field coalesce)
+// and rows never move inside the kernel; at exit they are written back in their sorted order.
+// Grids of up to 8 CTAs are launched as one thread-block cluster and use the hardware cluster
+// barrier, wider ones are cooperative launches with an atomic counter in L2.  Sums are
+// reproducible run to run (fixed grid, fixed trees); their order differs from the tiled sweeps',
+// so this path agrees with the per-phase path to rounding (1e-13), not bit for bit.
 constexpr int ADT_MAX = 1024;    // largest prefix (and active block) the device recursion takes
 constexpr int ADT_DEPTH = 192;   // frames of the explicit recursion stack
 constexpr int ADT_TS = 512;      // source tile = one slot per thread of the CTA
