@@ -621,3 +621,18 @@ def rescale_to_standard_units(m, q, p, eps2):  # ics.ml:304-331
     q2 = [[q[b][i] / efactor for i in range(3)] for b in range(n)]
     p2 = [[pn[b][i] * math.sqrt(efactor) for i in range(3)] for b in range(n)]
     return mn, q2, p2
+
+
+def leapfrog_advance_const_dt(m, q, p, dt, nsteps):  # Leapfrog.make then advance_const_dt (:160-165)
+    bs = [dict(id=i + 1, t=0.0, dt_max=0.0, m=m[i], q=list(q[i]), v=[x / m[i] for x in p[i]])
+          for i in range(len(m))]
+    count = [0]
+    import sys
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old, 6000))  # dt_max = 0 halves dt down to the last subnormal: ~1100 levels
+    try:
+        for _ in range(nsteps):
+            _lf_advance_subsystem(dt, INF, bs, len(bs), count)
+    finally:
+        sys.setrecursionlimit(old)
+    return bs

@@ -9,6 +9,10 @@ import pytest
 from oracle import twin
 
 
+def fl(a):  # plain Python floats: the twin's arithmetic must not go through numpy scalars
+    return [float(x) for x in a]
+
+
 def lists(a):
     return [[float(x) for x in row] for row in np.asarray(a)]
 
@@ -22,21 +26,21 @@ def bodies(request, oracle):
 
 def test_energies_bitwise(oracle, bodies):
     m, q, p, eps2 = bodies
-    assert oracle.total_potential_energy(m, q, eps2) == twin.total_potential_energy(list(m), lists(q), eps2)
-    assert oracle.total_kinetic_energy(m, p) == twin.total_kinetic_energy(list(m), lists(p))
+    assert oracle.total_potential_energy(m, q, eps2) == twin.total_potential_energy(fl(m), lists(q), eps2)
+    assert oracle.total_kinetic_energy(m, p) == twin.total_kinetic_energy(fl(m), lists(p))
 
 
 def test_hermite_start_bs_bitwise(oracle, bodies):
     m, q, p, eps2 = bodies
     f, df = oracle.start_bs_sweep(m, q, p, eps2)
-    tf, tdf, _ = twin.hermite_start_bs(1e-3, list(m), lists(q), lists(p), eps2)
+    tf, tdf, _ = twin.hermite_start_bs(1e-3, fl(m), lists(q), lists(p), eps2)
     assert np.array_equal(f, np.array(tf)) and np.array_equal(df, np.array(tdf))
 
 
 def test_hermite_advance_bitwise(oracle, bodies):
     m, q, p, eps2 = bodies
     a = oracle.hermite_advance(oracle.HermiteState(m, q, p), 1.0 / 32, 1e-3, eps2)
-    bs, nsteps = twin.hermite_advance(list(m), lists(q), lists(p), 1.0 / 32, 1e-3, eps2)
+    bs, nsteps = twin.hermite_advance(fl(m), lists(q), lists(p), 1.0 / 32, 1e-3, eps2)
     assert a.nsteps == nsteps and [b["id"] for b in bs] == list(a.id)
     for k in ("q", "p", "f", "df"):
         assert np.array_equal(getattr(a, k), np.array([b[k] for b in bs])), k
@@ -47,7 +51,7 @@ def test_hermite_advance_bitwise(oracle, bodies):
 def test_leapfrog_advance_bitwise(oracle, bodies):
     m, q, p, _ = bodies
     a = oracle.leapfrog_advance(oracle.LeapfrogState(m, q, p), 1.0 / 64, 1e-2)
-    bs, nk = twin.leapfrog_advance(list(m), lists(q), lists(p), 1.0 / 64, 1e-2)
+    bs, nk = twin.leapfrog_advance(fl(m), lists(q), lists(p), 1.0 / 64, 1e-2)
     assert [b["id"] for b in bs] == list(a.id) and a.nkicks == nk
     assert np.array_equal(a.q, np.array([b["q"] for b in bs]))
     assert np.array_equal(a.v, np.array([b["v"] for b in bs]))
@@ -58,14 +62,14 @@ def test_leapfrog_advance_bitwise(oracle, bodies):
 def test_omelyan_advance_bitwise(oracle, bodies):
     m, q, p, eps2 = bodies
     oq, op, ot = oracle.omelyan_advance(m, q, p, 0.0, 1.0 / 64, eps2)
-    tq, tp, tt = twin.omelyan_advance(list(m), lists(q), lists(p), 0.0, 1.0 / 64, eps2)
+    tq, tp, tt = twin.omelyan_advance(fl(m), lists(q), lists(p), 0.0, 1.0 / 64, eps2)
     assert ot == tt and np.array_equal(oq, np.array(tq)) and np.array_equal(op, np.array(tp))
 
 
 def test_advancer_advance_bitwise(oracle, bodies):
     m, q, p, eps2 = bodies
     a = oracle.advancer_advance(oracle.AdvancerState(m, q, p), 1.0 / 16, 1e-3, eps2)
-    bs, stats = twin.advancer_advance(list(m), lists(q), lists(p), 1.0 / 16, 1e-3, eps2)
+    bs, stats = twin.advancer_advance(fl(m), lists(q), lists(p), 1.0 / 16, 1e-3, eps2)
     assert tuple(stats) == tuple(a.stats) and [b["id"] for b in bs] == list(a.id)
     cols = {"t": 0, "m": 1, "h": 8, "hmax": 9, "t0": 10}
     for k, c in cols.items():
@@ -80,9 +84,9 @@ def test_analysis_bitwise(oracle, bodies):
     """Analysis.binary_energy / binaries_threshold / bodies_to_el_phase_space (analysis.ml:809-919)."""
     m, q, p, eps2 = bodies
     el = oracle.bodies_to_el_phase_space(m, q, p, eps2)
-    assert np.array_equal(el, np.array(twin.bodies_to_el_phase_space(list(m), lists(q), lists(p), eps2)))
+    assert np.array_equal(el, np.array(twin.bodies_to_el_phase_space(fl(m), lists(q), lists(p), eps2)))
     pi, pj, e = oracle.binaries(m, q, p, eps2, 0.0)
-    ref = twin.binaries_threshold(list(m), lists(q), lists(p), eps2, 0.0)
+    ref = twin.binaries_threshold(fl(m), lists(q), lists(p), eps2, 0.0)
     assert list(zip(pi.tolist(), pj.tolist())) == [(i, j) for i, j, _ in ref]
     assert np.array_equal(e, np.array([x for _, _, x in ref]))
 
@@ -91,7 +95,7 @@ def test_ics_frame_and_units_bitwise(oracle):
     """Ics.adjust_frame and rescale_to_standard_units (ics.ml:161-175, 304-331) on raw draws."""
     m, q, p = oracle.make_plummer(9, 77)
     a = oracle.adjust_frame(m, q, p)
-    t = twin.adjust_frame(list(m), lists(q), lists(p))
+    t = twin.adjust_frame(fl(m), lists(q), lists(p))
     for x, y in zip(a, t):
         assert np.array_equal(np.asarray(x), np.array(y))
     b = oracle.rescale_to_standard_units(*a, eps2=0.0025)
@@ -152,3 +156,15 @@ def test_dual_number_tangents_match_closed_forms(oracle, eps2):
     gm, dgm = oracle.grad_v_dgrad_v_sum(m, q - h * dq, p - h * dp, eps2)
     assert np.max(np.abs((gp - gm) / (2 * h) - gt)) <= 1e-6 * np.max(np.abs(gt))
     assert np.max(np.abs((dgp - dgm) / (2 * h) - dgt)) <= 1e-6 * np.max(np.abs(dgt))
+
+
+def test_leapfrog_const_dt_bitwise(oracle, bodies):
+    """advance_const_dt on FRESH bodies (dt_max = 0): the geometric ladder of sub-steps the
+    reference actually performs (leapfrog.ml:113-142) - both restatements follow it."""
+    m, q, p, _ = bodies
+    a = oracle.leapfrog_advance_const_dt(oracle.LeapfrogState(m, q, p), 1.0 / 128, 3)
+    bs = twin.leapfrog_advance_const_dt(fl(m), lists(q), lists(p), 1.0 / 128, 3)
+    assert [b["id"] for b in bs] == list(a.id)
+    assert np.array_equal(a.q, np.array([b["q"] for b in bs]))
+    assert np.array_equal(a.v, np.array([b["v"] for b in bs]))
+    assert np.array_equal(a.t, np.array([b["t"] for b in bs]))
