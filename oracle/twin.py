@@ -636,3 +636,76 @@ def leapfrog_advance_const_dt(m, q, p, dt, nsteps):  # Leapfrog.make then advanc
     finally:
         sys.setrecursionlimit(old)
     return bs
+
+
+# ---- ics.ml recipes over the fixed generator of SURVEY.md §8d ------------------------------------------
+class Rng:
+    """splitmix64; Random.float x = (next >> 11) * 2^-53 * x; one draw per Random.float call, draws
+    in the textual order of each recipe (the reference's own stream is self-seeded and cannot be
+    reproduced)."""
+    M = (1 << 64) - 1
+
+    def __init__(self, seed):
+        self.s = seed & self.M
+
+    def float(self, x):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & self.M
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & self.M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & self.M
+        z = z ^ (z >> 31)
+        return float(z >> 11) * 2.0 ** -53 * x
+
+
+def _random_between(rng, a, b):  # ics.ml:177-179
+    dx = b - a
+    return a + rng.float(dx)
+
+
+def _random_from_dist(rng, dist, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0):  # ics.ml:181-187
+    x = _random_between(rng, xmin, xmax)
+    y = _random_between(rng, ymin, ymax)
+    while not (y < dist(x)):
+        x = _random_between(rng, xmin, xmax)
+        y = _random_between(rng, ymin, ymax)
+    return x
+
+
+def _random_vector(rng, r):  # ics.ml:189-197
+    pi = 4.0 * math.atan(1.0)
+    cos_theta = _random_between(rng, -1.0, 1.0)
+    phi = _random_between(rng, 0.0, 2.0 * pi)
+    theta = math.acos(cos_theta)
+    sin_theta = math.sin(theta)
+    return [r * math.cos(phi) * sin_theta, r * math.sin(phi) * sin_theta, r * cos_theta]
+
+
+def make_plummer(n, seed):  # ics.ml:211-227
+    rng = Rng(seed)
+    m = 1.0 / float(n)
+    pi = 4.0 * math.atan(1.0)
+    sf = 16.0 / (3.0 * pi)
+    ms, qs, ps = [], [], []
+    for _ in range(n):
+        r = 1.0 / math.sqrt(_random_between(rng, 0.0, 1.0) ** (-2.0 / 3.0) - 1.0)
+        x = _random_from_dist(rng, lambda x: square(x) * (1.0 - square(x)) ** 3.5, ymax=0.1)
+        q = _random_vector(rng, r / sf)
+        p = _random_vector(rng, math.sqrt(sf) * m * x * math.sqrt(2.0) * (1.0 + square(r)) ** (-0.25))
+        ms.append(m)
+        qs.append(q)
+        ps.append(p)
+    return adjust_frame(ms, qs, ps)
+
+
+def make_hot_spherical(n, seed):  # ics.ml:229-239
+    rng = Rng(seed)
+    v0 = math.sqrt(21.0 / 10.0)
+    m = 1.0 / float(n)
+    ms, qs, ps = [], [], []
+    for _ in range(n):
+        r = _random_from_dist(rng, square)
+        vv = _random_between(rng, 0.0, v0)
+        qs.append(_random_vector(rng, r))
+        ps.append(_random_vector(rng, m * vv))
+        ms.append(m)
+    return adjust_frame(ms, qs, ps)

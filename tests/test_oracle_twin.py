@@ -168,3 +168,15 @@ def test_leapfrog_const_dt_bitwise(oracle, bodies):
     assert np.array_equal(a.q, np.array([b["q"] for b in bs]))
     assert np.array_equal(a.v, np.array([b["v"] for b in bs]))
     assert np.array_equal(a.t, np.array([b["t"] for b in bs]))
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (33, 20243), (200, 7)])
+def test_ic_recipes_bitwise(oracle, n, seed):
+    """make_plummer / make_hot_spherical (ics.ml:211-239, with random_vector, random_from_dist and
+    adjust_frame) over the fixed splitmix64 stream of SURVEY.md §8d: the inputs of every BASELINE
+    config, draw for draw."""
+    for mk_o, mk_t in ((oracle.make_plummer, twin.make_plummer),
+                       (oracle.make_hot_spherical, twin.make_hot_spherical)):
+        a, b = mk_o(n, seed), mk_t(n, seed)
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.array(y))
