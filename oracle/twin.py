@@ -19,6 +19,83 @@ NAN = float("nan")
 EPS = 2.220446049250313e-16  # epsilon_float
 
 
+class Dual:
+    """First-order forward-mode dual number, the stand-in for Diff.DFloat.diff (dFloat.ml:20; the
+    library is not vendored and pinned nowhere): value + one tangent with the
+    textbook sum / product / quotient rules, d sqrt x = dx / (2 sqrt x), d x^c = c x^(c-1) dx,
+    comparisons on the value.  A float operand is the constant `C x` (zero tangent).  With it the
+    Hermite functions below ARE dFloat_hermite.ml, as that file is hermite.ml over `diff`."""
+    __slots__ = ("v", "d")
+
+    def __init__(self, v, d=0.0):
+        self.v, self.d = v, d
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Dual) else Dual(x, 0.0)
+
+    def __add__(a, b):
+        b = Dual.of(b)
+        return Dual(a.v + b.v, a.d + b.d)
+
+    def __radd__(b, a):
+        return Dual.of(a) + b
+
+    def __sub__(a, b):
+        b = Dual.of(b)
+        return Dual(a.v - b.v, a.d - b.d)
+
+    def __rsub__(b, a):
+        return Dual.of(a) - b
+
+    def __neg__(a):
+        return Dual(-a.v, -a.d)
+
+    def __mul__(a, b):
+        b = Dual.of(b)
+        return Dual(a.v * b.v, a.d * b.v + a.v * b.d)
+
+    def __rmul__(b, a):
+        return Dual.of(a) * b
+
+    def __truediv__(a, b):
+        b = Dual.of(b)
+        q = a.v / b.v
+        return Dual(q, (a.d - q * b.d) / b.v)
+
+    def __rtruediv__(b, a):
+        return Dual.of(a) / b
+
+    def __pow__(a, c):
+        return Dual(a.v ** c, c * a.v ** (c - 1.0) * a.d)
+
+    def sqrt(a):
+        r = math.sqrt(a.v)
+        return Dual(r, a.d / (2.0 * r))
+
+    def __lt__(a, b):
+        return a.v < Dual.of(b).v
+
+    def __gt__(a, b):
+        return a.v > Dual.of(b).v
+
+    def __le__(a, b):
+        return a.v <= Dual.of(b).v
+
+    def __ge__(a, b):
+        return a.v >= Dual.of(b).v
+
+    def __eq__(a, b):
+        return a.v == Dual.of(b).v
+
+    def __hash__(a):
+        return hash(a.v)
+
+
+def gsqrt(x):  # sqrt on a float or a Dual
+    return x.sqrt() if isinstance(x, Dual) else math.sqrt(x)
+
+
 # ---- base.ml -------------------------------------------------------------------------------------
 def norm_squared(v):  # base.ml:36-40
     x, y, z = v[0], v[1], v[2]
@@ -26,7 +103,7 @@ def norm_squared(v):  # base.ml:36-40
 
 
 def norm(v):  # base.ml:43
-    return math.sqrt(norm_squared(v))
+    return gsqrt(norm_squared(v))
 
 
 def distance_squared(x, y):  # base.ml:46-50
@@ -37,7 +114,7 @@ def distance_squared(x, y):  # base.ml:46-50
 
 
 def distance(x, y):  # base.ml:53
-    return math.sqrt(distance_squared(x, y))
+    return gsqrt(distance_squared(x, y))
 
 
 def dot(x, y):  # base.ml:56-57
@@ -74,7 +151,7 @@ def grad_v_dgrad_v(m1, q1, p1, m2, q2, p2, gv, dgv, eps2):  # base.ml:91-110
     r2 = norm_squared(gv)
     rdv = dot(gv, dgv)
     re = r2 + eps2
-    r3 = math.sqrt(re) * re
+    r3 = gsqrt(re) * re
     r5 = r3 * re
     factorg = m1 * m2 / r3
     factord = 3.0 * rdv * m1 * m2 / r5
@@ -709,3 +786,27 @@ def make_hot_spherical(n, seed):  # ics.ml:229-239
         ps.append(_random_vector(rng, m * vv))
         ms.append(m)
     return adjust_frame(ms, qs, ps)
+
+
+# ---- dFloat_pushforward.ml:39-76 over dFloat_hermite.ml ----------------------------------------------
+def hermite_jacobian_advance(m, q, p, dt, sf, eps2):
+    """jacobian_advance dt sf bs on fresh bodies: one forward pass of Hermite.advance over Dual per
+    input direction; state packed as [q(3n); p(3n)].  Returns (jac[6n][6n] with
+    jac[r][c] = d out[r] / d in[c], the advanced packed state)."""
+    n = len(m)
+    d6 = 6 * n
+    jac = [[0.0] * d6 for _ in range(d6)]
+    out = [0.0] * d6
+    for c in range(d6):
+        qd = [[Dual(q[i][k], 1.0 if c == 3 * i + k else 0.0) for k in range(3)] for i in range(n)]
+        pd = [[Dual(p[i][k], 1.0 if c == 3 * n + 3 * i + k else 0.0) for k in range(3)] for i in range(n)]
+        md = [Dual(x) for x in m]
+        bs, _ = hermite_advance(md, qd, pd, Dual(dt), Dual(sf), Dual(eps2), t0=Dual(0.0))
+        for i in range(n):
+            for k in range(3):
+                jac[3 * i + k][c] = bs[i]["q"][k].d
+                jac[3 * n + 3 * i + k][c] = bs[i]["p"][k].d
+                if c == 0:
+                    out[3 * i + k] = bs[i]["q"][k].v
+                    out[3 * n + 3 * i + k] = bs[i]["p"][k].v
+    return jac, out

@@ -180,3 +180,16 @@ def test_ic_recipes_bitwise(oracle, n, seed):
         a, b = mk_o(n, seed), mk_t(n, seed)
         for x, y in zip(a, b):
             assert np.array_equal(np.asarray(x), np.array(y))
+
+
+def test_dual_number_hermite_jacobian_bitwise(oracle):
+    """DFloat_pushforward.jacobian_advance over DFloat_hermite (dFloat_pushforward.ml:39-76,
+    dFloat_hermite.ml:53-209 = hermite.ml over `diff`): the compiled template instantiated with
+    the dual number against the Python Hermite functions run on twin.Dual - same rules, so the
+    whole 6n x 6n Jacobian must agree bit for bit; and the map is symplectic to rounding."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(3, 4))
+    jac, out = oracle.hermite_jacobian_advance(m, q, p, 1.0 / 16, 1e-3, 0.01)
+    tj, to = twin.hermite_jacobian_advance(fl(m), lists(q), lists(p), 1.0 / 16, 1e-3, 0.01)
+    assert np.array_equal(out, np.array(to))
+    assert np.array_equal(jac, np.array(tj))
+    assert abs(oracle.omega_pushforward(jac) - 1.0) < 1e-3
