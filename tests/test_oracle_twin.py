@@ -193,3 +193,31 @@ def test_dual_number_hermite_jacobian_bitwise(oracle):
     assert np.array_equal(out, np.array(to))
     assert np.array_equal(jac, np.array(tj))
     assert abs(oracle.omega_pushforward(jac) - 1.0) < 1e-3
+
+
+def test_golden_trajectories_reproduced_by_the_twin():
+    """tests/golden/trajectories_n16.npz was written by the compiled oracle; the Python twin,
+    started from the stored inputs, lands on the same bits - so the committed fixtures the GPU
+    parity tests read are vouched for by both restatements."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectories_n16.npz"))
+    m, q, p = fl(g["m"]), lists(g["q"]), lists(g["p"])
+    bs, nsteps = twin.hermite_advance(m, q, p, 0.125, 1e-4, 0.0)
+    assert nsteps == int(g["hermite_nsteps"])
+    assert np.array_equal(g["hermite_q"], np.array([b["q"] for b in bs]))
+    assert np.array_equal(g["hermite_p"], np.array([b["p"] for b in bs]))
+    assert np.array_equal(g["hermite_h"], np.array([b["h"] for b in bs]))
+    la, _ = twin.leapfrog_advance(m, q, p, 1.0 / 64, 1e-2)
+    assert [b["id"] for b in la] == list(g["leapfrog_adapt_id"])
+    assert np.array_equal(g["leapfrog_adapt_q"], np.array([b["q"] for b in la]))
+    assert np.array_equal(g["leapfrog_adapt_v"], np.array([b["v"] for b in la]))
+    assert np.array_equal(g["leapfrog_adapt_dtmax"], np.array([b["dt_max"] for b in la]))
+    oq, op, ot = twin.omelyan_advance(m, q, p, 0.0, 1.0 / 64, 0.0)
+    assert ot == float(g["omelyan_t"])
+    assert np.array_equal(g["omelyan_q"], np.array(oq)) and np.array_equal(g["omelyan_p"], np.array(op))
+    ab, stats = twin.advancer_advance(m, q, p, 0.125, 1e-3, 0.0)
+    assert list(g["advancer_stats"]) == stats and [b["id"] for b in ab] == list(g["advancer_id"])
+    st = g["advancer_state"]
+    assert np.array_equal(st[:, 2:5], np.array([b["q"] for b in ab]))
+    assert np.array_equal(st[:, 5:8], np.array([b["p"] for b in ab]))
+    assert np.array_equal(st[:, 9], np.array([b["hmax"] for b in ab]))
