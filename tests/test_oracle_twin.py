@@ -221,3 +221,16 @@ def test_golden_trajectories_reproduced_by_the_twin():
     assert np.array_equal(st[:, 2:5], np.array([b["q"] for b in ab]))
     assert np.array_equal(st[:, 5:8], np.array([b["p"] for b in ab]))
     assert np.array_equal(st[:, 9], np.array([b["hmax"] for b in ab]))
+
+
+@pytest.mark.parametrize("name", ["sweeps_n64_eps0.npz", "sweeps_n257_eps004.npz"])
+def test_golden_sweeps_reproduced_by_the_twin(name):
+    """The sweep fixtures (acc+jerk in start_bs order, potential, kinetic energy, E-L phase space)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    m, q, p, eps2 = fl(g["m"]), lists(g["q"]), lists(g["p"]), float(g["eps2"])
+    f, df, _ = twin.hermite_start_bs(1e-3, m, q, p, eps2)
+    assert np.array_equal(g["f"], np.array(f)) and np.array_equal(g["df"], np.array(df))
+    assert float(g["pe"]) == twin.total_potential_energy(m, q, eps2)
+    assert float(g["ke"]) == twin.total_kinetic_energy(m, p)
+    assert np.array_equal(g["el"], np.array(twin.bodies_to_el_phase_space(m, q, p, eps2)))
