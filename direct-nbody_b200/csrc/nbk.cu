@@ -34,6 +34,7 @@ struct nbk_ctx {
   bool ev_valid = false;
   int64_t launches = 0;
   int shape = 0;
+  unsigned long long peer_wait_ns = 20000000000ULL;  // nbk_set_peer_timeout / NBK_PEER_TIMEOUT_S
   std::string err;
   // device workspaces
   DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_out[4],
@@ -619,6 +620,10 @@ int nbk_create(nbk_ctx **out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("NBK_HERMITE_THREADS")) c->hermite_threads = atoi(e);
+  if (const char *e = getenv("NBK_PEER_TIMEOUT_S")) {
+    const double s = atof(e);
+    c->peer_wait_ns = s > 0.0 ? (unsigned long long)(s * 1e9) : 0ULL;
+  }
   cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   cudaError_t e2 = cudaEventCreate(&c->ev0);
   cudaError_t e3 = cudaEventCreate(&c->ev1);
@@ -1940,6 +1945,7 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
   if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state: call nbk_hermite_upload");
   if (i < 0 || i >= n || upd >= n || (upd >= 0 && !upd_state) || !gsum || !dgsum)
     return fail(ctx, NBK_ERR_ARG, "nbk_hermite_body_sum: bad arguments (i=%d upd=%d n=%d)", i, upd, n);
+  CK(cudaSetDevice(ctx->device));
   HermiteUpd u;
   memset(&u, 0, sizeof u);
   if (upd >= 0) memcpy(u.s, upd_state, sizeof u.s);
@@ -2254,6 +2260,7 @@ int peer_params(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2, in
   P.self_rank = sh->self;
   P.ready = (const unsigned long long *)sh->ready;
   P.epoch = sh->epoch;
+  P.wait_ns = ctx->peer_wait_ns;
   // this rank's own shard, biased so that packed + i*PK is target i (never dereferenced outside it)
   P.packed = sh->packed[sh->self] - (size_t)lo * PK;
   if (need_aux) P.aux = sh->aux[sh->self] - (size_t)lo * PK;
@@ -2337,6 +2344,14 @@ int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, 
     else TRY((run_tangent<1, true, true>(ctx, P, (cudaStream_t)stream)));
     k0 += kt;
   }
+  return NBK_OK;
+}
+
+int nbk_set_peer_timeout(nbk_ctx *ctx, double seconds) {
+  if (!ctx || !(seconds >= 0.0) || seconds > 1e9)
+    return ctx ? fail(ctx, NBK_ERR_ARG, "nbk_set_peer_timeout: seconds must be in [0, 1e9]") : NBK_ERR_ARG;
+  ctx->peer_wait_ns = (unsigned long long)(seconds * 1e9);
+  for (nbk_ctx *peer : ctx->peers) peer->peer_wait_ns = ctx->peer_wait_ns;
   return NBK_OK;
 }
 

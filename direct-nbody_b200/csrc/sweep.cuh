@@ -134,6 +134,7 @@ struct SweepParams {
   int self_rank;
   const unsigned long long *ready;
   unsigned long long epoch;
+  unsigned long long wait_ns;  // how long a CTA waits for a peer's flag before trapping; 0 = forever
 };
 
 // ---- pair operations -----------------------------------------------------------------------
@@ -289,29 +290,35 @@ struct OpV {
 // the fast rsqrt (dv_i = dt * sum m_j d / r^3, unsoftened).  The time-scale half must return,
 // bit for bit, the minimum over sources of the reference's pair time-scale, which costs 2 sqrt
 // + 5 div in IEEE arithmetic - far too much to run on every pair.  So every pair goes through a
-// FILTER on the FP32 pipe (which idles beside the FP64 pipe): a sufficient condition, free of
-// divisions and square roots, for "this pair's time-scale exceeds the running minimum by more
-// than 0.2 %".  Only pairs that fail it - about ln N per target, plus anything NaN/inf/out of
-// float range - run the reference's exact operation sequence (correctly rounded sqrt/div, no
-// contraction), so the minimum is bit-identical to the reference formula.
+// FILTER: a sufficient condition, free of divisions, square roots and d.u, for "this pair's
+// time-scale exceeds the running minimum by more than 0.2 %".  Only pairs that fail it - about
+// ln N per target, plus anything NaN - run the reference's exact operation sequence (correctly
+// rounded sqrt/div, no contraction), so the minimum is bit-identical to the reference formula.
 //
-// Filter.  With y = 1/r, s = |d.u| y^2, T = 1.002 min-so-far, M = m_i + m_j (leapfrog.ml:94-101):
-//   tff = eta sqrt(r^3/M), tff_eff = tff / |1 - a|, a = 0.75 (d.u/r^2) tff
-//   tc  = eta r/|u|,       tc_eff  = tc  / |1 - b|, b = 0.5 (d.u/r^2) tc (1 + M/(|u|^2 r))
-// |1 - a| <= 1 + |a| gives  tff_eff > T  <=  g > 0 and tff^2 g^2 > T^2,  g = 1 - 0.75 T s, i.e.
-//   (eta^2 r2^2 y / T^2) g^2 > M;
-// likewise  tc_eff > T  <=  G > 0 and (eta^2 r2 / T^2) G^2 > |u|^6,  G = |u|^2 - 0.5 T s (|u|^2 + M y).
-// A pair costs 4 double->float conversions and ~30 FP32 operations.  (A looser test on r^2,
-// |u|^2 and M alone was tried, alone and as a first level: it lets ~1 % of the pairs through,
-// which with 32 lanes x 4 targets per warp makes most warps take the slow branch - slower.)
-// State per target (acc[4], two floats): Tf >= T and 1/Tf^2; Tf = +inf, 1/Tf^2 = 0 (never
-// "far") until a first exact value exists or whenever T leaves [1e-12, 1e12].
+// Filter (FP64, on values the velocity half has already: r2, y = 1/r; plus |u|^2).  With
+// M = m_i + m_j, s = d.u / r^2 (leapfrog.ml:94-101):
+//   tff0 = eta sqrt(r^3/M),  tff = tff0 / |1 - a|,  a = 0.75 s tff0
+//   tc0  = eta r/|u|,        tc  = tc0  / |1 - b|,  b = 0.5 s tc0 (1 + z),  z = M/(|u|^2 r)
+// Cauchy-Schwarz gives |s| <= |u|/r = eta/tc0, hence |b| <= 0.5 eta (1 + z) and
+// |a| <= 0.75 eta tff0/tc0, and tff0/tc0 = 1/sqrt(z).  If z <= 1 (the pair moves faster than its
+// mutual orbital speed - all but bound pairs) then tff0 >= tc0, tc >= tc0/(1 + eta) and
+// tff >= tff0/(1 + 0.75 eta tff0/tc0) >= tc0/(1 + 0.75 eta): the pair's time-scale is at least
+// tc0/(1 + eta).  So the pair is "far" when
+//   |M| y <= |u|^2            (z <= 1)                                 and
+//   c r^2  >  |u|^2           (tc0 > T (1 + eta)),  c = (eta / (T (1 + eta)))^2, T = 1.002 min-so-far
+// 1 DADD + 2 DMUL + 2 DSETP on top of |u|^2, no conversions, no FP32 work (the earlier FP32-pipe
+// filter cost 4 F2F.F32.F64 on the XU pipe and ~30 FP32 issue slots per pair: 50 ms at
+// N = 131072; an FP64 instruction holds the dispatch port for >= 2 cycles, so every non-FP64
+// instruction adds to the FP64 time instead of hiding under it).  NaN anywhere fails a
+// comparison and takes the exact path; a zero or negative total mass leaves tff NaN or
+// infinite in the reference too, where the time-scale is tc, and the bound on tc holds for
+// |z| <= 1.  State per target (acc[4]) = c; 0 (never "far") until a first exact value exists,
+// for eta <= 0 or NaN, or whenever T leaves [1e-100, 1e100].
 template <bool WITH_TSCALE> struct OpKick {
   static constexpr int NACC = WITH_TSCALE ? 5 : 3;
   static constexpr int ND2 = WITH_TSCALE ? 4 : 2;
   struct Tgt {
     double x, y, z, vx, vy, vz, m;
-    float mf;
   };
   __device__ __forceinline__ static void load(Tgt &t, const double *pk, const SweepParams &, int) {
     t.x = pk[0];
@@ -321,22 +328,21 @@ template <bool WITH_TSCALE> struct OpKick {
     t.vx = pk[4];
     t.vy = pk[5];
     t.vz = pk[6];
-    t.mf = __double2float_rn(pk[3]);
   }
-  __device__ __forceinline__ static double filter_state(double tmin) {
+  __device__ __forceinline__ static double filter_state(double tmin, double eta) {
     const double T = tmin * 1.002;
-    float Tf = __int_as_float(0x7f800000), inv = 0.0f;
-    if (T > 1e-12 && T < 1e12) {
-      Tf = __double2float_ru(T);
-      inv = __frcp_rd(__fmul_ru(Tf, Tf));
+    double c = 0.0;
+    if (T > 1e-100 && T < 1e100 && eta > 0.0 && eta < 1e100) {
+      const double k = eta / (T * (1.0 + eta));
+      c = (k * k) * 0.999999;
     }
-    return __hiloint2double(__float_as_int(inv), __float_as_int(Tf));
+    return c;
   }
   __device__ __forceinline__ static void zero(double *acc) {
     acc[0] = acc[1] = acc[2] = 0.0;
     if (WITH_TSCALE) {
       acc[3] = __longlong_as_double(0x7ff0000000000000LL);
-      acc[4] = __hiloint2double(0, 0x7f800000);
+      acc[4] = 0.0;
     }
   }
   // The reference's exact pair time-scale (leapfrog.ml:80-104, unfused, correctly rounded).
@@ -358,22 +364,10 @@ template <bool WITH_TSCALE> struct OpKick {
     tc = fabs(__ddiv_rn(tc, __dsub_rn(1.0, __dmul_rn(0.5, dtc))));
     return (tff < tc) ? tff : tc;
   }
-  // FP32 filter: true = this pair's time-scale certainly exceeds 1.002 x the running minimum.
-  __device__ __forceinline__ static bool far_pair(double r2, double y, double vsq, double vdr,
-                                                        float M, double state, float eta2) {
-    const float X = __double2float_rn(r2), yf = __double2float_rn(y);
-    const float V = __double2float_rn(vsq), vdrf = __double2float_rn(vdr);
-    const float Tf = __int_as_float(__double2loint(state));
-    const float inv = __int_as_float(__double2hiint(state));
-    const float Ts = Tf * (fabsf(vdrf) * (yf * yf));
-    const float g = fmaf(-0.75f, Ts, 1.0f);
-    const float e2r = eta2 * X;
-    const float l1 = (((e2r * X) * yf) * inv) * (g * g);  // small factors first: an underflow
-    // reads "exact"; NaN, inf or anything beyond 1e30 fails a comparison -> exact path
-    const float G = fmaf(-0.5f * Ts, fmaf(M, yf, V), V);
-    const float l2 = (e2r * inv) * (G * G);
-    const float rh2 = (V * V) * V;
-    return (l1 > M) & (g > 0.0f) & (l2 > rh2) & (G > 0.0f) & (l1 < 1e30f) & (l2 < 1e30f);
+  // true = this pair's time-scale certainly exceeds 1.002 x the running minimum.
+  __device__ __forceinline__ static bool far_pair(double r2, double y, double vsq, double M,
+                                                  double c) {
+    return (fabs(M) * y <= vsq) & (c * r2 > vsq);
   }
   template <bool CHECK>
   __device__ __forceinline__ static void pair(const Tgt &t, double *acc, const double2 *sj,
@@ -399,17 +393,13 @@ template <bool WITH_TSCALE> struct OpKick {
       double vsq = ux * ux;
       vsq = fma(uy, uy, vsq);
       vsq = fma(uz, uz, vsq);
-      double vdr = dx * ux;
-      vdr = fma(dy, uy, vdr);
-      vdr = fma(dz, uz, vdr);
-      const float eta2 = __double2float_rn(P.eta * P.eta);
-      const bool far = far_pair(r2, y, vsq, vdr, t.mf + __double2float_rn(b.y), acc[4], eta2);
+      const bool far = far_pair(r2, y, vsq, t.m + b.y, acc[4]);
       const bool skip = CHECK ? self : false;
       if (!far && !skip) {
         const double ts = exact_tscale(dx, dy, dz, ux, uy, uz, t.m, b.y, P.eta);
         if (acc[3] > ts) {  // NaN ts leaves acc[3] alone, leapfrog.ml:103
           acc[3] = ts;
-          acc[4] = filter_state(ts);
+          acc[4] = filter_state(ts, P.eta);
         }
       }
     }
@@ -426,49 +416,76 @@ template <bool WITH_TSCALE> struct OpKick {
       for (int r = 0; r < IPT; ++r) pair<CHECK>(t[r], acc[r], sj, nullptr, jg == ig[r], P);
     } else {
       const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
-      const float eta2 = __double2float_rn(P.eta * P.eta);
-      const float mjf = __double2float_rn(b.y);
-      double dx[IPT], dy[IPT], dz[IPT], ux[IPT], uy[IPT], uz[IPT];
-      unsigned need = 0;
+      double dx[IPT], dy[IPT], dz[IPT], ux[IPT], uy[IPT], uz[IPT], r2[IPT], mj[IPT], y0[IPT];
+      double y[IPT], vsq[IPT];
 #pragma unroll
       for (int r = 0; r < IPT; ++r) {
         dx[r] = a.x - t[r].x;
         dy[r] = a.y - t[r].y;
         dz[r] = b.x - t[r].z;
-        double r2 = dx[r] * dx[r];
-        r2 = fma(dy[r], dy[r], r2);
-        r2 = fma(dz[r], dz[r], r2);
-        double mj = b.y;
-        const bool self = CHECK ? (jg == ig[r]) : false;
+      }
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        r2[r] = dx[r] * dx[r];
+        r2[r] = fma(dy[r], dy[r], r2[r]);
+        r2[r] = fma(dz[r], dz[r], r2[r]);
+        mj[r] = b.y;
         if (CHECK) {
-          r2 = self ? 1.0 : r2;
-          mj = self ? 0.0 : mj;
+          const bool self = jg == ig[r];
+          r2[r] = self ? 1.0 : r2[r];
+          mj[r] = self ? 0.0 : mj[r];
         }
-        const double y = rsqrt_nr(r2);
-        const double w = (mj * y) * (y * y);
-        acc[r][0] = fma(w, dx[r], acc[r][0]);
-        acc[r][1] = fma(w, dy[r], acc[r][1]);
-        acc[r][2] = fma(w, dz[r], acc[r][2]);
+      }
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[r]) : "d"(r2[r]));
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
         ux[r] = c.x - t[r].vx;
         uy[r] = c.y - t[r].vy;
         uz[r] = d.x - t[r].vz;
-        double vsq = ux[r] * ux[r];
-        vsq = fma(uy[r], uy[r], vsq);
-        vsq = fma(uz[r], uz[r], vsq);
-        double vdr = dx[r] * ux[r];
-        vdr = fma(dy[r], uy[r], vdr);
-        vdr = fma(dz[r], uz[r], vdr);
-        const bool far = far_pair(r2, y, vsq, vdr, t[r].mf + mjf, acc[r][4], eta2);
-        if (!far && !self) need |= 1u << r;
       }
-      if (need) {
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        vsq[r] = ux[r] * ux[r];
+        vsq[r] = fma(uy[r], uy[r], vsq[r]);
+        vsq[r] = fma(uz[r], uz[r], vsq[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        double tt = r2[r] * y0[r];
+        double e = fma(-tt, y0[r], 1.0);
+        double pp = fma(0.375, e, 0.5);
+        double q = e * pp;
+        y[r] = fma(y0[r], q, y0[r]);
+      }
+      // hot path: ONE predicate "every target's pair is far" (2 DSETP per target, chained); the
+      // cold path re-derives which targets need the exact sequence
+      double My[IPT], cr2[IPT];
+      bool allfar = true;
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        My[r] = fabs(t[r].m + b.y) * y[r];
+        cr2[r] = acc[r][4] * r2[r];
+        const bool self = CHECK ? (jg == ig[r]) : false;
+        allfar = allfar && (((My[r] <= vsq[r]) && (cr2[r] > vsq[r])) || self);
+      }
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        const double w = (mj[r] * y[r]) * (y[r] * y[r]);
+        acc[r][0] = fma(w, dx[r], acc[r][0]);
+        acc[r][1] = fma(w, dy[r], acc[r][1]);
+        acc[r][2] = fma(w, dz[r], acc[r][2]);
+      }
+      if (!allfar) {
 #pragma unroll
         for (int r = 0; r < IPT; ++r) {
-          if ((need >> r) & 1u) {
+          const bool self = CHECK ? (jg == ig[r]) : false;
+          const bool far = (My[r] <= vsq[r]) && (cr2[r] > vsq[r]);
+          if (!far && !self) {
             const double ts = exact_tscale(dx[r], dy[r], dz[r], ux[r], uy[r], uz[r], t[r].m, b.y, P.eta);
             if (acc[r][3] > ts) {
               acc[r][3] = ts;
-              acc[r][4] = filter_state(ts);
+              acc[r][4] = filter_state(ts, P.eta);
             }
           }
         }
@@ -822,8 +839,10 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
       // registers (measured: +0.8 % kernel time).
       if (P.ready != nullptr) {
         const int r_lo = P.s0 / P.shard_rows, r_hi = (P.s1 - 1) / P.shard_rows;
-        // A peer that never publishes (it crashed) must not hang this GPU: after 20 s the kernel
-        // traps, which the host sees as a launch failure on its next CUDA call.
+        // A peer that never publishes (it crashed) must not hang this GPU: after P.wait_ns
+        // (nbk_set_peer_timeout, default 20 s; 0 = wait forever, e.g. under a debugger) the
+        // kernel traps, which the host sees as a launch failure on its next CUDA call.  All
+        // ranks must call their sweeps in lockstep (same number of epochs).
         unsigned long long t_start;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         for (int r = r_lo; r <= r_hi; ++r)  // the owners of sources [s0, s1)
@@ -832,7 +851,7 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
               __nanosleep(64);
               unsigned long long t_now;
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-              if (t_now - t_start > 20000000000ULL) __trap();
+              if (P.wait_ns != 0 && t_now - t_start > P.wait_ns) __trap();
             }
         fence_proxy_async();
       }
@@ -2719,7 +2738,7 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
           Op::load(tg, rows + (size_t)ms[x] * PK, SP, 0);
           if (TS) {
             acc[3] = dtm[x];  // infinity for an active slot (reset in stage 0)
-            acc[4] = Op::filter_state(acc[3]);
+            acc[4] = Op::filter_state(acc[3], SP.eta);
           }
           const int lo = x >= ibegin ? 0 : ibegin;
           for (int k = lo + sl; k < iend; k += SPLIT)

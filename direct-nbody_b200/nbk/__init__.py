@@ -119,6 +119,7 @@ SYMBOLS = {
     "nbk_dev_v_sum_peer": (_i, [_vp, _psh, _i, _d, _i, _i, _i, _i, _vp, _i, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum_tangent_peer": (_i, [_vp, _psh, _i, _i, _d, _i, _i, _i, _i, _vp,
                                                      _vp, _vp]),
+    "nbk_set_peer_timeout": (_i, [_vp, _d]),
     "nbk_tune": (_i, [_vp, _i]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
@@ -219,6 +220,10 @@ class Context:
         ms = _f()
         self._ck(self._lib.nbk_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def set_peer_timeout(self, seconds):
+        """How long a *_peer sweep waits for a peer's ready flag before trapping; 0 = forever."""
+        self._ck(self._lib.nbk_set_peer_timeout(self._h, float(seconds)))
 
     def tune(self, variant):
         self._ck(self._lib.nbk_tune(self._h, variant))

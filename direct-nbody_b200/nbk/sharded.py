@@ -97,6 +97,15 @@ class ShardedAccJerk:
             rows[:, 4:7] = d_p / d_m[:, None]
             rows[:, 7] = 0.0
 
+    def load_local_device(self, d_m, d_q, d_p):
+        """As load_local for device tensors of this rank's slice; enqueued, not waited for."""
+        pl = self.plan
+        if pl.count == 0:
+            return
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+                          self.packed_loc.data_ptr(), stream)
+
     def step(self, eps2: float = 0.0):
         """All-gather, then sweep this rank's targets over all sources.  Returns the device
         tensors (gsum, dgsum) for targets [t0, t1)."""
@@ -204,6 +213,17 @@ def peer_region_layout(shard_rows: int, K: int = 0, nbuf: int = 2):
     return PEER_FLAG_BYTES + nbuf * buf_bytes, packed_off, aux_off
 
 
+def next_row_buffer(cur: int, stepped_since_load: bool) -> int:
+    """Which of the two row buffers a load may overwrite.  The buffer in use (`cur`) may be read
+    by a peer's sweep of the latest epoch for as long as this rank has not completed a LATER
+    sweep, so it is never the target once a step has published it; the other buffer was last
+    read in sweeps that ended before the peers published the epoch this rank's last sweep
+    acquired, so it is free - however many steps ran since the last load (the toggle follows
+    the loads, not the epoch parity: load, step, step, load must not reuse the live buffer).
+    Two loads without a step in between re-pack the same, still unpublished, buffer."""
+    return 1 - cur if stepped_since_load else cur
+
+
 class PeerRegions:
     """This rank's region plus the mapped regions of every other rank."""
 
@@ -276,6 +296,7 @@ class _PeerSharded:
         self.torch, self.plan, self.device, self.ctx, self.group = torch, plan, device, ctx, group
         self.regions = PeerRegions(plan, ctx, K, group, exchange)
         self.epoch, self.cur = 0, 0
+        self._stepped_since_load = True  # the first load_local takes the other buffer
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -284,7 +305,8 @@ class _PeerSharded:
         """Pack this rank's bodies into the row buffer the NEXT step reads (the one no peer is
         reading: buffers alternate, see include/nbk.h).  vel = momenta, or velocities."""
         torch, pl = self.torch, self.plan
-        self.cur = (self.epoch + 1) % 2
+        self.cur = next_row_buffer(self.cur, self._stepped_since_load)
+        self._stepped_since_load = False
         if pl.count == 0:
             return
         sl = slice(pl.t0, pl.t1)
@@ -296,10 +318,24 @@ class _PeerSharded:
         self._local = (d_m, d_v) if not is_velocity else (d_m, d_v * d_m[:, None])  # m, p
         torch.cuda.current_stream(self.device).synchronize()
 
+    def load_local_device(self, d_m, d_q, d_vel, is_velocity=False):
+        """load_local for a caller whose bodies already live on this device (an integrator that
+        moved its slice since the last sweep): d_m [count], d_q, d_vel [count][3] device tensors
+        of THIS RANK'S slice.  Enqueues the pack on the current stream - no copy, no
+        synchronisation - into the row buffer no peer is reading."""
+        pl = self.plan
+        self.cur = next_row_buffer(self.cur, self._stepped_since_load)
+        self._stepped_since_load = False
+        if pl.count == 0:
+            return
+        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_vel.data_ptr(), is_velocity,
+                          self.regions.packed(self.cur)[pl.rank], self._stream())
+
     def _publish(self):
         """New epoch: tell the peers this rank's rows are in place; returns the shard table."""
         pl, rg = self.plan, self.regions
         self.epoch += 1
+        self._stepped_since_load = True
         if pl.world > 1:
             self.ctx.dev_publish(pl.rank, rg.base, self.epoch, self._stream())  # flags at offset 0
         return self.ctx.make_shards(pl.rank, pl.shard, rg.packed(self.cur),
@@ -408,10 +444,12 @@ class PeerShardedTangent:
         self.gt = torch.zeros(K, max(plan.count, 1), 3, dtype=torch.float64, device=device)
         self.dgt = torch.zeros_like(self.gt)
         self.epoch, self.cur = 0, 0
+        self._stepped_since_load = True
 
     def load_local(self, m, q, p, dq, dp):
         torch, pl, rg = self.torch, self.plan, self.regions
-        self.cur = (self.epoch + 1) % 2
+        self.cur = next_row_buffer(self.cur, self._stepped_since_load)
+        self._stepped_since_load = False
         if pl.count == 0:
             return
         sl = slice(pl.t0, pl.t1)
@@ -434,6 +472,7 @@ class PeerShardedTangent:
     def step(self, eps2: float = 0.0):
         pl, rg = self.plan, self.regions
         self.epoch += 1
+        self._stepped_since_load = True
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         if pl.world > 1:
             self.ctx.dev_publish(pl.rank, rg.base, self.epoch, st)

@@ -56,10 +56,13 @@ int nbk_create(nbk_ctx **ctx, int device);
 /* Single-process multi-GPU context over ndev devices (devices[] = their ordinals, or NULL for
  * 0..ndev-1) - what a single OCaml process uses to drive the GPUs of one box.  It behaves like
  * a context on the first device, except that the host-buffer sweeps nbk_grad_v_dgrad_v_sum,
- * nbk_grad_v_sum, nbk_v_sum and nbk_energy shard their TARGETS over all the devices: bodies are
- * uploaded and packed once, broadcast to the other devices over NVLink, every device sweeps its
- * slice over all sources, and the slices are read back into place.  Results depend on ndev
- * only at rounding level (where a target's source range is cut into runs). */
+ * nbk_grad_v_sum, nbk_v_sum and nbk_energy shard their TARGETS over all the devices: every
+ * device uploads and packs ITS OWN rows (the host->device copies go out over all PCIe links
+ * side by side), sweeps its slice over all sources - reading the other devices' rows in place
+ * over NVLink (peer access, the PEER sweep kernels; no broadcast) - and the slices are read
+ * back into place.  Devices that cannot map each other fall back to staging on the first device
+ * and a cudaMemcpyPeerAsync broadcast.  Results depend on ndev only at rounding level (where a
+ * target's source range is cut into runs). */
 int nbk_create_multi(nbk_ctx **ctx, int ndev, const int *devices);
 int nbk_device_count(const nbk_ctx *ctx);
 void nbk_destroy(nbk_ctx *ctx);
@@ -392,6 +395,12 @@ int nbk_peer_alloc(nbk_ctx *ctx, size_t bytes, void **d_ptr, unsigned char *hand
 int nbk_peer_open(nbk_ctx *ctx, const unsigned char *handle, void **d_ptr);
 int nbk_peer_close(nbk_ctx *ctx, void *d_ptr);
 int nbk_peer_free(nbk_ctx *ctx, void *d_ptr);
+/* How long a *_peer sweep waits for a peer's ready flag before the kernel traps (the host then
+ * sees a launch failure on its next call instead of a hung GPU): default 20 s, or the
+ * environment variable NBK_PEER_TIMEOUT_S at nbk_create; 0 = wait forever (debugger, profiler,
+ * ranks with long host-side work between steps).  All ranks must call their sweeps in lockstep:
+ * a rank that steps fewer epochs than its peers leaves them waiting. */
+int nbk_set_peer_timeout(nbk_ctx *ctx, double seconds);
 /* d_ready_of_rank[r] = rank r's ready[] array as mapped on this device. */
 int nbk_dev_publish(nbk_ctx *ctx, int nranks, int self, uint64_t *const *d_ready_of_rank,
                     uint64_t epoch, void *stream);

@@ -107,6 +107,26 @@ def test_peer_region_layout_is_disjoint_and_aligned():
         assert aoff[0] == poff[0] + row_bytes
 
 
+def test_row_buffer_toggle_follows_loads_not_epoch_parity():
+    """load, step, step, load must not pack into the buffer the peers' sweeps of the
+    latest epoch read.  The toggle is relative to the buffer in use; two loads in a row re-pack
+    the same (unpublished) buffer."""
+    from nbk.sharded import next_row_buffer
+    cur, stepped, live = 0, True, []
+    for op in "LSSLSLLSSSLS":
+        if op == "L":
+            new = next_row_buffer(cur, stepped)
+            if stepped:          # `cur` has been published: a peer may be reading it
+                assert new != cur
+            else:                # nobody has seen `cur` yet
+                assert new == cur
+            cur, stepped = new, False
+        else:
+            stepped = True
+        live.append(cur)
+    assert live == [1, 1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 0]
+
+
 class _FakeCtx:
     """Stands in for nbk.Context: records the region calls PeerRegions makes."""
 

@@ -73,6 +73,25 @@ def main():
         gb, dgb = b.step(0.0)
         torch.cuda.synchronize()
         ok = ok and torch.equal(ga, gb) and torch.equal(dga, dgb)
+        # load, step, step, load, step with ranks deliberately skewed: the second load must not
+        # touch the row buffer a slower peer's sweep of the latest epoch is still reading
+        for rep in range(4):
+            if rank == rep % world:
+                torch.cuda._sleep(int(3e7))  # this rank's stream lags ~15 ms
+            qa, qb = q * (1.0 + 1e-3 * (rep + 1)), q * (1.0 - 1e-3 * (rep + 1))
+            b.load_local(m, qa, p)
+            b.step(0.0)
+            gb, dgb = b.step(0.0)
+            gb1, dgb1 = gb.clone(), dgb.clone()
+            b.load_local(m, qb, p)
+            gb, dgb = b.step(0.0)
+            a.load_local(m, qa, p)
+            ga, dga = a.step(0.0)
+            ok = ok and torch.equal(ga, gb1) and torch.equal(dga, dgb1)
+            a.load_local(m, qb, p)
+            ga, dga = a.step(0.0)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(ga, gb) and torch.equal(dga, dgb)
         ms_nccl = timed(lambda: a.step(0.0))
         ms_peer = timed(lambda: b.step(0.0))
         inter = float(n) * (n - 1)
