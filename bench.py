@@ -7,11 +7,16 @@ on 1/2/4/8 B200.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...                          (CPU arm, oracle port)
 
-A step = one full acc+jerk sweep: every rank owns a contiguous shard of the targets, all-gathers
-the packed (q, v, m) of all bodies with NCCL, and sweeps its targets over all N sources
-(strong scaling: N is fixed).  `value` = N(N-1) interactions / step, device-timed with the
-bodies resident in HBM; `e2e` = the same sweep through the reference-facing C-ABI call on
-pinned HOST buffers (H2D + pack + sweep + D2H inside the timed region).
+A step = one full acc+jerk sweep of bodies that MOVED since the last one: every rank owns a
+contiguous shard of the targets, re-packs its (drifted) rows into the row buffer no peer is
+reading, publishes them, and sweeps its targets over all N sources - reading the other ranks'
+rows out of their HBM over NVLink inside the sweep kernel (--exchange nccl: an all-gather in
+front of it).  Strong scaling: N is fixed.  `value` = N(N-1) interactions / step, device-timed
+with the bodies resident in HBM; `e2e` = the same sweep through the reference-facing C-ABI call
+on pinned HOST buffers (H2D + pack + sweep + D2H inside the timed region), one call per rank for
+its shard; `e2e_single_process` = ONE process driving all the GPUs through nbk_create_multi.
+`parity` = the last timed step's results against the oracle, per body, on >= 256 targets per
+rank; the run exits 3 above 1e-12.
 """
 import argparse
 import json
@@ -98,70 +103,144 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic_bytes():
     """dram__bytes_read + dram__bytes_write of the acc+jerk sweep kernel per launch, from the
-    committed ncu --set full summary (profiles/); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_k2_large_shape_summary.txt")
-    try:
-        tot = 0.0
-        for line in open(path):
-            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                if line.startswith(key + " "):
-                    unit = line.split("[")[1].split("]")[0]
-                    val = float(line.split("=")[1])
-                    tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-        return tot or None
-    except Exception:
-        return None
+    committed `ncu --set full` summary (profiles/; a profiler cannot run inside a bench);
+    returns (bytes or None, file name)."""
+    for name in ("r2_ncu_k2_large_shape_summary.txt", "r1_ncu_k2_large_shape_summary.txt"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            tot = 0.0
+            for line in open(path):
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    if line.startswith(key + " "):
+                        unit = line.split("[")[1].split("]")[0]
+                        val = float(line.split("=")[1])
+                        tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            if tot:
+                return tot, "profiles/" + name
+        except Exception:
+            pass
+    return None, None
 
 
-def cpu_sample(n_sample, threads_all=True, n_total=131072):
-    """The reference's CPU path (oracle port of Hermite.start_bs' symmetric pair loop) timed on
-    a bounded sample: the first n_sample bodies of the same Plummer workload."""
-    from oracle import oracle as O
-    m, q, p = O.make_plummer(n_total, SEED)
-    m, q, p = m[:n_sample].copy(), q[:n_sample].copy(), p[:n_sample].copy()
+def make_config(n, world, exchange="peer", overlap=0):
+    """The workload both arms state (the reference arm runs it on the host cores): identical
+    for `--impl ours` and `--impl reference` at the same --gpus."""
+    if world == 1:
+        sharding = "single GPU"
+    elif exchange == "peer":
+        sharding = (f"targets/{world}, sweep kernel reads remote source tiles from the owning GPU "
+                    "over NVLink (peer memory, CUDA IPC); no all-gather step")
+    else:
+        sharding = (f"targets/{world}, NCCL all-gather of packed (q,v,m) per step [{exchange}]"
+                    + (", overlapped with the local-source sweep" if overlap else ""))
+    return {"workload": f"Plummer sphere N={n}, Hermite acc+jerk sweep (BASELINE.json configs[2])",
+            "n": n, "eps": 0.0, "seed": SEED, "sharding": sharding,
+            "bodies": "move every step: each rank re-packs its (drifted) rows into the other row "
+                      "buffer, publishes, sweeps",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def workload(n):
+    """Seeded Plummer bodies and the two position sets the steps alternate between (q and a
+    drift of 1e-3 time units): what a start_bs-per-step caller hands the sweep."""
+    import nbh
+    m, q, p = nbh.make_plummer(n, SEED)
+    q2 = q + 1e-3 * (p / m[:, None])
+    return m, (q, q2), p
+
+
+def parity_ranges(t0, t1, groups=8, width=32):
+    """>= 256 targets of [t0, t1): `groups` runs of `width` spread over the shard, the first
+    starting at t0 (first tile) and the last ending at t1 (last tile)."""
+    cnt = t1 - t0
+    if cnt <= groups * width:
+        return [(t0, t1)] if cnt > 0 else []
+    out = []
+    for g in range(groups):
+        a = t0 + (cnt - width) * g // (groups - 1)
+        out.append((a, a + width))
+    return out
+
+
+def cpu_rate(O, m, q, p, n_sample, threads):
+    """interactions/s of the oracle's symmetric start_bs pair loop over the first n_sample
+    bodies on `threads` host threads (1 = the plain single-thread loop the reference is)."""
+    ms, qs, ps = m[:n_sample].copy(), q[:n_sample].copy(), p[:n_sample].copy()
+    O.set_num_threads(threads)
     t = time.perf_counter()
-    O.start_bs_sweep(m, q, p, 0.0, omp=threads_all)
+    O.start_bs_sweep(ms, qs, ps, 0.0, omp=threads > 1)
     dt = time.perf_counter() - t
-    cores = O.num_threads() if threads_all else 1
-    return n_sample * (n_sample - 1) / dt, cores, dt
+    return n_sample * (n_sample - 1) / dt, dt
+
+
+def cpu_baseline_object(n, n_sample, with_single=True):
+    """The reference's CPU path beside the GPU number: all host threads on a bounded sample,
+    plus the single-thread rate (the reference itself is single-threaded OCaml)."""
+    from oracle import oracle as O
+    m, q, p = O.make_plummer(n, SEED)
+    cores = O.host_cores()
+    v_all, dt_all = cpu_rate(O, m, q, p, n_sample, cores)
+    out = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"symmetric i<j acc+jerk sweep over the first {n_sample} bodies of the same "
+                     f"Plummer workload ({dt_all:.2f} s wall, OpenMP, {cores} threads set "
+                     "explicitly - OMP_NUM_THREADS ignored)"}
+    if with_single:
+        n1 = min(n_sample, 12288)
+        v1, dt1 = cpu_rate(O, m, q, p, n1, 1)
+        out["single_thread"] = {"value": v1, "cores": 1, "sample": f"first {n1} bodies, {dt1:.2f} s"}
+    return out
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The OCaml
     reference cannot be compiled in this image (no OCaml toolchain), so this is the oracle
-    port (kind "port"), all host threads, each step a bounded sample of the workload."""
+    port (kind "port").  Thread count is set here (all host cores), never inherited from
+    OMP_NUM_THREADS - torchrun exports 1.  The full N is swept at least once; the timed steps
+    are the full N when K+W of them fit in ~100 s, else a half-size sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = args.cpu_sample
+    from oracle import oracle as O
+    n = args.n
+    m, q, p = O.make_plummer(n, SEED)  # bit-identical to the product's generator (tests/)
+    cores = O.host_cores()
+    v_full, dt_full = cpu_rate(O, m, q, p, n, cores)  # the stated config, measured once
+    full_steps = dt_full * (args.steps + args.warmup) <= 100.0
+    n_sample = n if full_steps else min(n, args.cpu_sample)
     vals = []
     for k in range(args.warmup + args.steps):
-        v, cores, dt = cpu_sample(n_sample, True, args.n)
+        v, dt = cpu_rate(O, m, q, p, n_sample, cores)
         if k >= args.warmup:
             vals.append((v, dt))
     value = statistics.mean(v for v, _ in vals)
     ms = 1e3 * statistics.mean(d for _, d in vals)
-    sample = (f"symmetric i<j acc+jerk sweep over the first {n_sample} bodies of the N={args.n} "
-              f"Plummer workload, OpenMP over {cores} threads")
+    n1 = min(n, 12288)
+    v1, dt1 = cpu_rate(O, m, q, p, n1, 1)
+    sample = (f"symmetric i<j acc+jerk sweep over {'all' if full_steps else 'the first'} "
+              f"{n_sample} bodies of the N={n} Plummer workload per step, OpenMP over {cores} "
+              "threads (set explicitly, OMP_NUM_THREADS ignored)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": f"Plummer sphere N={args.n}, Hermite acc+jerk sweep "
-                                   "(BASELINE.json configs[2])", "n": args.n, "eps": 0.0,
-                       "seed": SEED},
+            "config": make_config(n, args.gpus, args.exchange, args.overlap),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample},
+                             "sample": sample,
+                             "full_n": {"value": v_full, "seconds": dt_full, "n": n,
+                                        "cores": cores, "measured": True},
+                             "single_thread": {"value": v1, "cores": 1,
+                                               "sample": f"first {n1} bodies, {dt1:.2f} s; the "
+                                                         "reference itself is single-threaded"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print_line(line)
 
 
 def run_ours(args):
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
-    import nbh
     import nbk
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,10 +259,11 @@ def run_ours(args):
     from nbk.sharded import PeerShardedAccJerk, ShardedAccJerk, make_plan
     plan = make_plan(n, world, rank, align=128)
     t0, t1 = plan.t0, plan.t1
+    nt = t1 - t0
     ctx = nbk.Context(local)
-    m, q, p = nbh.make_plummer(n, SEED)  # same seeded bodies on every rank
+    m, qs, p = workload(n)  # same seeded bodies on every rank
 
-    # ---- device-resident state: this rank's shard of packed (q, v, m).
+    # ---- device-resident state: this rank's slice (m, q, p) and its packed rows.
     # exchange "peer" (default for N > 1): the rows stay in a region the other ranks map over
     # NVLink (CUDA IPC) and the sweep kernel reads remote source tiles itself - no all-gather;
     # "nccl": in-place all-gather of the packed rows in front of the sweep.
@@ -199,12 +279,22 @@ def run_ours(args):
             sh, exchange = None, "nccl (peer exchange unavailable)"
     if sh is None:
         sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))
-    sh.load_local(m, q, p)
+    sl = slice(t0, t1)
+    d_m = torch.as_tensor(m[sl]).to(dev).contiguous()
+    d_p = torch.as_tensor(p[sl]).to(dev).contiguous()
+    d_q = [torch.as_tensor(q[sl]).to(dev).contiguous() for q in qs]
     g, dg = sh.g, sh.dg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    counter = [0]
 
     def step():
+        # the bodies moved since the last sweep: re-pack this rank's rows (into the row buffer
+        # no peer is reading), publish, sweep
+        k = counter[0]
+        counter[0] += 1
+        sh.load_local_device(d_m, d_q[k % 2], d_p)
         sh.step(0.0)
+        return k % 2
 
     def barrier():
         if world > 1:
@@ -221,10 +311,11 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    which = 0
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations, outside the per-step events
         ev[k][0].record(stream)
-        step()
+        which = step()
         ev[k][1].record(stream)
     barrier()
     sampler.stop_flag.set()
@@ -236,6 +327,43 @@ def run_ours(args):
     ms_per_step = float(tot_ms.item()) / args.steps
     inter = float(n) * float(n - 1)
     value = inter / (ms_per_step * 1e-3)
+
+    # ---- parity of the LAST timed step against the oracle (the checker, never the path):
+    # >= 256 of this rank's targets, spread over its shard incl. first and last tile, over all
+    # N sources, per body; the run fails above 1e-12.
+    par = torch.zeros(3, dtype=torch.float64, device=dev)
+    parity_note = None
+    if args.parity:
+        try:
+            from oracle import oracle as O
+            O.set_num_threads(max(1, O.host_cores() // world))
+            g_h, dg_h = g.cpu().numpy(), dg.cpu().numpy()
+            ea = ej = 0.0
+            checked = 0
+            for a, b in parity_ranges(t0, t1):
+                g_ref, dg_ref = O.grad_v_dgrad_v_sum(m, qs[which], p, 0.0, targets=(a, b))
+                ea = max(ea, float(np.max(np.linalg.norm(g_h[a - t0:b - t0] - g_ref, axis=1)
+                                          / np.linalg.norm(g_ref, axis=1))))
+                ej = max(ej, float(np.max(np.linalg.norm(dg_h[a - t0:b - t0] - dg_ref, axis=1)
+                                          / np.linalg.norm(dg_ref, axis=1))))
+                checked += b - a
+            par = torch.tensor([ea, ej, float(checked)], dtype=torch.float64, device=dev)
+        except ImportError as e:  # the oracle is test infrastructure; say so instead of passing
+            parity_note = f"oracle unavailable: {e}"
+    if world > 1:
+        cnt = par[2:].clone()
+        dist.all_reduce(par, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        par[2] = cnt[0]
+    parity = {"max_rel_acc": float(par[0]), "max_rel_jerk": float(par[1]),
+              "targets_checked": int(par[2]), "tolerance": 1e-12,
+              "against": "oracle grad_v_dgrad_v_sum over all N sources, last timed step's bodies, "
+                         "per body |d|2/|ref|2, max over ranks"}
+    if parity_note:
+        parity["note"] = parity_note
+    parity_ok = (not args.parity) or (parity_note is None and parity["targets_checked"] > 0
+                                      and parity["max_rel_acc"] <= 1e-12
+                                      and parity["max_rel_jerk"] <= 1e-12)
 
     # ---- dominant kernel alone (this rank's share), live CUDA events, for the roofline
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -260,32 +388,30 @@ def run_ours(args):
         kev[k][1].record(stream)
     torch.cuda.synchronize()
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
-    k_inter = float(t1 - t0) * float(n - 1)
+    k_inter = float(nt) * float(n - 1)
 
-    # ---- e2e: the reference-facing C-ABI call on pinned host buffers
+    # ---- e2e: the reference-facing C-ABI call on pinned host buffers, inputs alternating
     hm = torch.from_numpy(m).pin_memory()
-    hq = torch.from_numpy(q).pin_memory()
+    hq = [torch.from_numpy(np.ascontiguousarray(q)).pin_memory() for q in qs]
     hp = torch.from_numpy(p).pin_memory()
-    nt = t1 - t0
     hg = torch.empty(max(nt, 1), 3, dtype=torch.float64).pin_memory()
     hdg = torch.empty(max(nt, 1), 3, dtype=torch.float64).pin_memory()
-    import ctypes as C
     pd = C.POINTER(C.c_double)
 
     def cptr(t):
         return C.cast(t.data_ptr(), pd)
 
-    def e2e_step():
-        rc = ctx._lib.nbk_grad_v_dgrad_v_sum(ctx._h, n, cptr(hm), cptr(hq), cptr(hp), 0.0, t0, t1,
-                                             0, n, cptr(hg), cptr(hdg))
-        ctx._ck(rc)
+    def e2e_step(c, k, a, b, og, odg):
+        rc = c._lib.nbk_grad_v_dgrad_v_sum(c._h, n, cptr(hm), cptr(hq[k % 2]), cptr(hp), 0.0, a, b,
+                                           0, n, cptr(og), cptr(odg))
+        c._ck(rc)
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_step()
+    e2e_step(ctx, 0, t0, t1, hg, hdg)
     barrier()
     tw = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns with results in host memory
+    for k in range(e2e_steps):
+        e2e_step(ctx, k, t0, t1, hg, hdg)  # synchronous: returns with results in host memory
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - tw) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
@@ -294,40 +420,70 @@ def run_ours(args):
     h2d = 7 * 8 * n
     d2h = 6 * 8 * nt
 
+    # ---- e2e through ONE process driving all the GPUs (nbk_create_multi): what a single
+    # OCaml host does.  Rank 0 works, the other ranks wait at the barrier.
+    e2e_single = None
+    if world > 1 and args.single_process:
+        barrier()
+        if rank == 0:
+            try:
+                cm = nbk.Context(devices=list(range(world)))
+                fg = torch.empty(n, 3, dtype=torch.float64).pin_memory()
+                fdg = torch.empty(n, 3, dtype=torch.float64).pin_memory()
+                for k in range(2):
+                    e2e_step(cm, k, 0, n, fg, fdg)
+                tw = time.perf_counter()
+                for k in range(e2e_steps):
+                    e2e_step(cm, k, 0, n, fg, fdg)
+                sp_s = (time.perf_counter() - tw) / e2e_steps
+                e2e_single = {"value": inter / sp_s, "unit": UNIT, "ms_per_call": sp_s * 1e3,
+                              "devices": world, "h2d_bytes_per_step": 7 * 8 * n,
+                              "d2h_bytes_per_step": 6 * 8 * n,
+                              "what": "nbk_grad_v_dgrad_v_sum on host buffers through "
+                                      "nbk_create_multi, one process, all targets"}
+                cm.close()
+                torch.cuda.set_device(local)
+            except Exception as e:  # noqa: BLE001
+                e2e_single = {"unavailable": str(e)}
+        barrier()
+
+    if hasattr(sh, "close"):
+        sh.close()
+    ctx_sm_count = ctx.sm_count
     if rank == 0:
         peak_tf, _ = ctx.fp64_peak(20000)
         peak_tf, _ = ctx.fp64_peak(20000)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+    if rank == 0:
         achieved_tf = FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12
         clocks = sampler.summary()
-        nominal = ctx.sm_count * 64 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+        nominal = ctx_sm_count * 64 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         try:
-            cpu_v, cpu_cores, cpu_dt = cpu_sample(args.cpu_sample, True, n) if world == 1 else (None, None, None)
+            cpu = cpu_baseline_object(n, args.cpu_sample)
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
-            cpu_v, cpu_cores, cpu_dt = None, None, None
+            cpu = None
             print(f"cpu_baseline unavailable: {e}", file=sys.stderr)
+        traffic, traffic_file = ncu_traffic_bytes() if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Plummer sphere N={n}, Hermite acc+jerk sweep "
-                                   "(BASELINE.json configs[2])", "n": n, "eps": 0.0, "seed": SEED,
-                       "sharding": (
-                           "single GPU" if world == 1 else
-                           f"targets/{world}, sweep kernel reads remote source tiles from the owning "
-                           "GPU over NVLink (peer memory, CUDA IPC); no all-gather step"
-                           if exchange == "peer" else
-                           f"targets/{world}, NCCL all-gather of packed (q,v,m) per step [{exchange}]"
-                           + (", overlapped with the local-source sweep" if args.overlap else "")),
-                       "l2": "flushed between timed iterations (256 MiB write)"},
+            "config": make_config(n, world, "peer" if exchange == "peer" else exchange,
+                                  args.overlap),
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": ncu_traffic_bytes() if world == 1 else None,
-                         "traffic_note": "ncu dram bytes per launch (profiles/); algorithmic = "
-                                         "64 B x N read once + 48 B x N written",
+                         "traffic": traffic,
+                         "traffic_note": "ncu dram bytes per launch"
+                                         + (f" ({traffic_file})" if traffic_file else "")
+                                         + "; algorithmic = 64 B x N read once + 48 B x N written",
                          "peak_source": "on-box DFMA microbenchmark (nbk_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": nominal, "frac_of_nominal": achieved_tf / nominal,
@@ -338,17 +494,14 @@ def run_ours(args):
                          "kernel": "sweep_kernel<OpGradVDGradV" + (", PEER>" if exchange == "peer" else ">"), "kernel_ms": k_ms,
                          "interactions_per_launch": k_inter},
         }
-        if cpu_v is not None:
-            line["cpu_baseline"] = {
-                "value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port",
-                "sample": f"symmetric i<j acc+jerk sweep over the first {args.cpu_sample} bodies of "
-                          f"the same Plummer workload ({cpu_dt:.2f} s wall, OpenMP, all host threads)"}
+        if e2e_single is not None:
+            line["e2e_single_process"] = e2e_single
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print_line(line)
-    if hasattr(sh, "close"):
-        sh.close()
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if not parity_ok:
+        print(f"rank {rank}: PARITY FAILED {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -364,6 +517,10 @@ def main():
                     help="N > 1: how a rank gets the other ranks' bodies (see run_ours)")
     ap.add_argument("--overlap", type=int, default=0,
                     help="1: sweep local sources while the all-gather is in flight")
+    ap.add_argument("--parity", type=int, default=1,
+                    help="0: skip the oracle check of the last timed step (exit 3 if it fails)")
+    ap.add_argument("--single-process", type=int, default=1,
+                    help="N > 1: also time one process driving all GPUs (nbk_create_multi)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout must carry exactly ONE JSON line: route everything libraries print there (NCCL's

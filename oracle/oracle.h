@@ -17,6 +17,7 @@ extern "C" {
 #endif
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 /* test-run guard: step loops stop early past this many steps (default 2e8) */
 void oracle_set_step_cap(long cap);
 

@@ -53,6 +53,7 @@ def _declare(L):
         f.argtypes = list(args)
 
     sig("oracle_num_threads", _i)
+    sig("oracle_set_num_threads", None, _i)
     sig("oracle_set_step_cap", None, C.c_long)
     sig("oracle_start_bs_sweep", None, _i, _pd, _pd, _pd, _d, _pd, _pd)
     sig("oracle_start_bs_sweep_omp", None, _i, _pd, _pd, _pd, _d, _pd, _pd)
@@ -109,6 +110,19 @@ def set_step_cap(cap: int) -> None:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """Thread count of the OpenMP sweeps from here on (ignores OMP_NUM_THREADS)."""
+    lib().oracle_set_num_threads(int(n))
+
+
+def host_cores() -> int:
+    """Cores this process may run on (the GPU box's host cores)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------ initial conditions

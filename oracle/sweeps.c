@@ -36,6 +36,16 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* Thread count of the OpenMP loops, set explicitly (bench.py's CPU arm must not inherit the
+ * OMP_NUM_THREADS=1 that torchrun exports); n <= 0 leaves it alone. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* hermite.ml:148-167: bodies get zeroed f, df; for each head b, for each later b2:
  *   f -= gv; f2 += gv; df -= dgv; df2 += dgv. */
 void oracle_start_bs_sweep(int n, const double *m, const double *q, const double *p,

@@ -31,6 +31,35 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # hygiene: thread count set by the arm itself, single-thread rate beside it,
+    # the stated N measured at least once, config identical to the GPU arm's
+    assert d["cpu_baseline"]["full_n"]["measured"] is True and d["cpu_baseline"]["full_n"]["n"] == 8192
+    assert d["cpu_baseline"]["single_thread"]["cores"] == 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.make_config(8192, 1)
+
+
+def test_reference_arm_ignores_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core."""
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "2048",
+             "--n", "4096", env={"OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_parity_ranges_cover_first_and_last_tile():
+    sys.path.insert(0, ROOT)
+    import bench
+    for t0, t1 in ((0, 131072), (16384, 32768), (114688, 131072), (0, 300), (5, 100), (7, 7)):
+        rs = bench.parity_ranges(t0, t1)
+        tot = sum(b - a for a, b in rs)
+        assert tot == min(256, t1 - t0)
+        if rs:
+            assert rs[0][0] == t0 and rs[-1][1] == t1
+            assert all(t0 <= a < b <= t1 for a, b in rs)
+            assert all(x[1] <= y[0] for x, y in zip(rs, rs[1:]))
 
 
 def test_reference_arm_other_ranks_print_nothing():

@@ -15,6 +15,36 @@ def rel_err(a, b):
     return float(np.max(num / den))
 
 
+def abs_sums(m, q, p, eps2, tg, sr):
+    """Per target: A_i = sum_j |grad_v(i,j)|, B_i = sum_j |dgrad_v(i,j)| (numpy, test-side only) -
+    the scale a sum's rounding error is proportional to.  |sum| << A means the reference sum is
+    itself a cancellation, and only there may a per-body check fall back from |ref_i| to it."""
+    (t0, t1), (s0, s1) = tg, sr
+    v = p / m[:, None]
+    A, B = np.zeros(t1 - t0), np.zeros(t1 - t0)
+    js = np.arange(s0, s1)
+    for i in range(t0, t1):
+        keep = js != i
+        d = q[s0:s1][keep] - q[i]
+        u = v[s0:s1][keep] - v[i]
+        r2 = (d * d).sum(1) + eps2
+        mu = m[i] * m[s0:s1][keep]
+        A[i - t0] = (mu * np.sqrt((d * d).sum(1)) / r2 ** 1.5).sum()
+        rv = (d * u).sum(1)
+        B[i - t0] = (mu * np.linalg.norm(u - 3.0 * (rv / r2)[:, None] * d, axis=1) / r2 ** 1.5).sum()
+    return A, B
+
+
+def assert_per_body(x, ref, scale, what=""):
+    """north_star's criterion PER BODY: |x_i - ref_i|_2 <= 1e-12 |ref_i|_2.  Only where the
+    reference sum cancels by more than 1000x (|ref_i| < 1e-3 sum_j |term_ij|) is the bound
+    1e-15 sum_j |term_ij| instead - never a maximum over other targets."""
+    err = np.linalg.norm(x - ref, axis=-1)
+    bound = TOL * np.maximum(np.linalg.norm(ref, axis=-1), 1e-3 * scale)
+    bad = np.nonzero(~(err <= bound))[0]
+    assert bad.size == 0, (what, bad[:5], err[bad[:5]], bound[bad[:5]])
+
+
 @pytest.mark.parametrize("n", [2, 3, 257, 1024, 4096])
 @pytest.mark.parametrize("eps", [0.0, 0.04, 0.4])
 def test_grad_v_dgrad_v_sum_matches_oracle(ctx, oracle, n, eps):
@@ -78,10 +108,9 @@ def test_rectangular_ranges(ctx, oracle, ranges):
     g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
     assert g.shape == g_ref.shape
     if g.size and sr[1] > sr[0]:
-        scale = np.linalg.norm(g_ref, axis=1).max()
-        assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * scale
-        scale = np.linalg.norm(dg_ref, axis=1).max()
-        assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * scale
+        A, B = abs_sums(m, q, p, 0.0, tg, sr)
+        assert_per_body(g, g_ref, A, "acc")
+        assert_per_body(dg, dg_ref, B, "jerk")
     else:
         assert not g.any() and not dg.any()
     phi_ref = oracle.v_sum(m, q, 0.0, targets=tg, sources=sr)
@@ -143,6 +172,28 @@ def test_baseline_size_sampled_against_oracle(ctx, oracle):
     assert np.array_equal(g, g2) and np.array_equal(dg, dg2)
 
 
+@pytest.mark.parametrize("eps2", [0.0, 1e-8])
+def test_baseline_size_all_bodies_per_body(ctx, oracle, eps2):
+    """SURVEY.md section 8d, cfg 3: ALL 131072 targets of the metric sweep against the oracle's
+    rows (hermite.ml:148-169 restated, OpenMP over targets, ascending-j sums = the reference's
+    per-body order), eps = 0 and eps = 1e-4: <= 1e-12 relative for EVERY body, acceleration and
+    jerk.  Prints the five worst bodies."""
+    import os
+    import nbh
+    n = 131072
+    m, q, p = nbh.make_plummer(n, 20243)
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, eps2)
+    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps2)
+    eg = np.linalg.norm(g - g_ref, axis=1) / np.linalg.norm(g_ref, axis=1)
+    edg = np.linalg.norm(dg - dg_ref, axis=1) / np.linalg.norm(dg_ref, axis=1)
+    for name, e in (("acc", eg), ("jerk", edg)):
+        worst = np.argsort(e)[-5:][::-1]
+        print(f"N={n} eps2={eps2:g} {name}: worst 5 bodies "
+              + ", ".join(f"{i}:{e[i]:.2e}" for i in worst) + f"; median {np.median(e):.2e}")
+    assert eg.max() <= TOL and edg.max() <= TOL, (eg.max(), edg.max())
+
+
 def test_resident_bodies_and_update(ctx, oracle):
     m, q, p = oracle.make_plummer(2000, 13)
     ctx.bodies_upload(m, q, p)
@@ -199,10 +250,9 @@ def test_few_targets_source_parallel_path(ctx, oracle, nt):
     for sr in [(0, n), (100, 2999), (1230, 1240)]:
         g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
         g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=tg, sources=sr)
-        sc_g = np.linalg.norm(g_ref, axis=1).max() + 1e-300
-        sc_dg = np.linalg.norm(dg_ref, axis=1).max() + 1e-300
-        assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * sc_g
-        assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * sc_dg
+        A, B = abs_sums(m, q, p, 0.0, tg, sr)
+        assert_per_body(g, g_ref, A, ("acc", sr))
+        assert_per_body(dg, dg_ref, B, ("jerk", sr))
     v = p / m[:, None]
     dv_ref, tmin_ref = oracle.kick_sum(m, q, v, 1e-3, 1e-4, targets=tg)
     dv, tmin = ctx.kick_sum(m, q, v, 1e-3, 1e-4, targets=tg)
@@ -386,10 +436,9 @@ def test_fuzz_rectangles_all_shapes(ctx, oracle):
             ctx.tune(int(rng.integers(0, 4)))
             g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, eps2, targets=(t0, t1), sources=(s0, s1))
             g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps2, targets=(t0, t1), sources=(s0, s1))
-            sg = np.linalg.norm(g_ref, axis=1).max() + 1e-300
-            sdg = np.linalg.norm(dg_ref, axis=1).max() + 1e-300
-            assert np.max(np.linalg.norm(g - g_ref, axis=1)) <= TOL * sg, (case, n, t0, t1, s0, s1)
-            assert np.max(np.linalg.norm(dg - dg_ref, axis=1)) <= TOL * sdg, (case, n, t0, t1, s0, s1)
+            A, B = abs_sums(m, q, p, eps2, (t0, t1), (s0, s1))
+            assert_per_body(g, g_ref, A, ("acc", case, n, t0, t1, s0, s1))
+            assert_per_body(dg, dg_ref, B, ("jerk", case, n, t0, t1, s0, s1))
             phi_ref = oracle.v_sum(m, q, eps2, targets=(t0, t1), sources=(s0, s1))
             phi, tot = ctx.v_sum(m, q, eps2, targets=(t0, t1), sources=(s0, s1))
             assert np.allclose(phi, phi_ref, rtol=TOL, atol=1e-300), (case, n, t0, t1, s0, s1)
@@ -397,8 +446,9 @@ def test_fuzz_rectangles_all_shapes(ctx, oracle):
             v = p / m[:, None]
             dv_ref, tm_ref = oracle.kick_sum(m, q, v, 1e-2, 1e-3, targets=(t0, t1), sources=(s0, s1))
             dv, tm = ctx.kick_sum(m, q, v, 1e-2, 1e-3, targets=(t0, t1), sources=(s0, s1))
-            sdv = np.linalg.norm(dv_ref, axis=1).max() + 1e-300
-            assert np.max(np.linalg.norm(dv - dv_ref, axis=1)) <= TOL * sdv, (case, n, t0, t1, s0, s1)
+            # kick: dv_i = dt sum_j m_j d / r^3 = dt A_i / m_i at eps = 0
+            A0 = A if eps2 == 0.0 else abs_sums(m, q, p, 0.0, (t0, t1), (s0, s1))[0]
+            assert_per_body(dv, dv_ref, 1e-3 * A0 / m[t0:t1], ("kick", case, n, t0, t1, s0, s1))
             assert np.array_equal(tm, tm_ref), (case, n, t0, t1, s0, s1)
     finally:
         ctx.tune(0)
