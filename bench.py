@@ -252,8 +252,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host-only barrier for the single-process leg: an NCCL barrier is a kernel spinning on
+        # every waiting rank's GPU, which would share the SMs with the sweeps rank 0 launches there
+        cpu_group = dist.new_group(backend="gloo")
 
     n = args.n
     from nbk.sharded import PeerShardedAccJerk, ShardedAccJerk, make_plan
@@ -425,6 +429,7 @@ def run_ours(args):
     e2e_single = None
     if world > 1 and args.single_process:
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 cm = nbk.Context(devices=list(range(world)))
@@ -445,7 +450,7 @@ def run_ours(args):
                 torch.cuda.set_device(local)
             except Exception as e:  # noqa: BLE001
                 e2e_single = {"unavailable": str(e)}
-        barrier()
+        dist.barrier(group=cpu_group)  # the other ranks wait on the host, GPUs idle
 
     if hasattr(sh, "close"):
         sh.close()

@@ -1085,18 +1085,11 @@ int nbk_grad_v_dgrad_v_sum_predicted(nbk_ctx *ctx, int n, const double *t, const
 }
 
 namespace {
-// Shared body of the two tangent entry points.
-int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p, int K,
-                   const double *dq, const double *dp, double eps2, int t0, int t1, int s0,
-                   int s1, double *gsum, double *dgsum, double *gsum_tan, double *dgsum_tan,
-                   bool jerk) {
-  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
-  CK(cudaSetDevice(ctx->device));
-  if (K < 0 || (K > 0 && (!dq || !gsum_tan || (jerk && (!dp || !dgsum_tan)))))
-    return fail(ctx, NBK_ERR_ARG, "tangent sweep: bad direction arguments");
-  if (n == 0 || t1 == t0) return NBK_OK;
-  const size_t nt = (size_t)(t1 - t0), n3 = 3 * (size_t)n;
-  TRY(stage_bodies(ctx, n, m, q, jerk ? p : nullptr, 0));
+// Value and tangent sums over bodies already packed in ctx->d_packed and directions already
+// packed in ctx->d_aux ([K][n][8]); results to the host.
+int tangent_sweeps(nbk_ctx *ctx, int n, int K, double eps2, int t0, int t1, int s0, int s1,
+                   double *gsum, double *dgsum, double *gsum_tan, double *dgsum_tan, bool jerk) {
+  const size_t nt = (size_t)(t1 - t0);
   if (gsum || dgsum) {  // value sums from the plain kernels
     if (jerk) {
       TRY(reserve(ctx, ctx->d_out[2], 3 * nt * sizeof(double)));
@@ -1125,18 +1118,6 @@ int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const 
     }
   }
   if (K == 0) return sync(ctx);
-  // directions: upload, pack into aux[K][n][8]
-  TRY(reserve(ctx, ctx->d_aux, (size_t)K * n * PK * sizeof(double)));
-  TRY(upload(ctx, ctx->d_aux_in, dq, (size_t)K * n3));
-  if (jerk) TRY(upload(ctx, ctx->d_aux_in2, dp, (size_t)K * n3));
-  for (int k = 0; k < K; ++k) {
-    pack_aux_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
-        n, (const double *)ctx->d_m.p, (const double *)ctx->d_aux_in.p + (size_t)k * n3,
-        jerk ? (const double *)ctx->d_aux_in2.p + (size_t)k * n3 : nullptr, 0,
-        (double *)ctx->d_aux.p + (size_t)k * n * PK);
-    ctx->launches++;
-  }
-  CK(cudaGetLastError());
   TRY(reserve(ctx, ctx->d_out[0], (size_t)K * 3 * nt * sizeof(double)));
   TRY(reserve(ctx, ctx->d_out[1], (size_t)K * 3 * nt * sizeof(double)));
   if (s1 == s0) {
@@ -1165,7 +1146,95 @@ int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const 
   if (jerk) TRY(download(ctx, dgsum_tan, ctx->d_out[1], (size_t)K * 3 * nt));
   return sync(ctx);
 }
+
+// Shared body of the two tangent entry points.
+int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p, int K,
+                   const double *dq, const double *dp, double eps2, int t0, int t1, int s0,
+                   int s1, double *gsum, double *dgsum, double *gsum_tan, double *dgsum_tan,
+                   bool jerk) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (K < 0 || (K > 0 && (!dq || !gsum_tan || (jerk && (!dp || !dgsum_tan)))))
+    return fail(ctx, NBK_ERR_ARG, "tangent sweep: bad direction arguments");
+  if (n == 0 || t1 == t0) return NBK_OK;
+  const size_t n3 = 3 * (size_t)n;
+  TRY(stage_bodies(ctx, n, m, q, jerk ? p : nullptr, 0));
+  if (K > 0) {  // directions: upload, pack into aux[K][n][8]
+    TRY(reserve(ctx, ctx->d_aux, (size_t)K * n * PK * sizeof(double)));
+    TRY(upload(ctx, ctx->d_aux_in, dq, (size_t)K * n3));
+    if (jerk) TRY(upload(ctx, ctx->d_aux_in2, dp, (size_t)K * n3));
+    for (int k = 0; k < K; ++k) {
+      pack_aux_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+          n, (const double *)ctx->d_m.p, (const double *)ctx->d_aux_in.p + (size_t)k * n3,
+          jerk ? (const double *)ctx->d_aux_in2.p + (size_t)k * n3 : nullptr, 0,
+          (double *)ctx->d_aux.p + (size_t)k * n * PK);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  return tangent_sweeps(ctx, n, K, eps2, t0, t1, s0, s1, gsum, dgsum, gsum_tan, dgsum_tan, jerk);
+}
 }  // namespace
+
+// DFloat_hermite.advance_body's loop (dFloat_hermite.ml:115-135): predict every body to the dual
+// time nt from its own dual state, then the tangent acc+jerk sums over the predicted bodies.
+int nbk_grad_v_dgrad_v_sum_predicted_tangent(
+    nbk_ctx *ctx, int n, const double *t, const double *m, const double *q, const double *p,
+    const double *f, const double *df, int K, const double *t_tan, const double *q_tan,
+    const double *p_tan, const double *f_tan, const double *df_tan, double nt,
+    const double *nt_tan, double eps2, int t0, int t1, int s0, int s1, double *gsum,
+    double *dgsum, double *gsum_tan, double *dgsum_tan) {
+  TRY(check_ranges(ctx, n, t0, t1, s0, s1));
+  CK(cudaSetDevice(ctx->device));
+  if (!t || !m || !q || !p || !f || !df) return fail(ctx, NBK_ERR_ARG, "null body array");
+  if (K < 0 || (K > 0 && (!q_tan || !p_tan || !f_tan || !df_tan || !gsum_tan || !dgsum_tan)))
+    return fail(ctx, NBK_ERR_ARG, "predicted tangent sweep: bad direction arguments");
+  if (n == 0 || t1 == t0) return NBK_OK;
+  const size_t n3 = 3 * (size_t)n, Kn3 = (size_t)K * n3;
+  TRY(upload(ctx, ctx->d_m, m, n));
+  TRY(upload(ctx, ctx->d_q, q, n3));
+  TRY(upload(ctx, ctx->d_vel, p, n3));
+  TRY(upload(ctx, ctx->d_t, t, n));
+  TRY(upload(ctx, ctx->d_f, f, n3));
+  TRY(upload(ctx, ctx->d_df, df, n3));
+  TRY(reserve(ctx, ctx->d_packed, (size_t)n * PK * sizeof(double)));
+  predict_pack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+      n, (const double *)ctx->d_t.p, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
+      (const double *)ctx->d_vel.p, (const double *)ctx->d_f.p, (const double *)ctx->d_df.p, nt,
+      (double *)ctx->d_packed.p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (K > 0) {
+    // tangent inputs in one buffer: [q_tan | p_tan | f_tan | df_tan] (each [K][3n]), then
+    // t_tan [K][n] (zeros if NULL) and nt_tan [K] (zeros if NULL)
+    TRY(reserve(ctx, ctx->d_aux_in, (4 * Kn3 + (size_t)K * n + K) * sizeof(double)));
+    double *base = (double *)ctx->d_aux_in.p;
+    double *d_tt = base + 4 * Kn3, *d_ntt = d_tt + (size_t)K * n;
+    const double *src[4] = {q_tan, p_tan, f_tan, df_tan};
+    for (int a = 0; a < 4; ++a)
+      CK(cudaMemcpyAsync(base + a * Kn3, src[a], Kn3 * sizeof(double), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    if (t_tan)
+      CK(cudaMemcpyAsync(d_tt, t_tan, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    else
+      CK(cudaMemsetAsync(d_tt, 0, (size_t)K * n * sizeof(double), ctx->stream));
+    if (nt_tan)
+      CK(cudaMemcpyAsync(d_ntt, nt_tan, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    else
+      CK(cudaMemsetAsync(d_ntt, 0, (size_t)K * sizeof(double), ctx->stream));
+    TRY(reserve(ctx, ctx->d_aux, (size_t)K * n * PK * sizeof(double)));
+    dim3 grid((n + 255) / 256, K);
+    predict_pack_tangent_kernel<<<grid, 256, 0, ctx->stream>>>(
+        n, (const double *)ctx->d_t.p, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
+        (const double *)ctx->d_vel.p, (const double *)ctx->d_f.p, (const double *)ctx->d_df.p, nt,
+        d_tt, base, base + Kn3, base + 2 * Kn3, base + 3 * Kn3, d_ntt, (double *)ctx->d_aux.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  return tangent_sweeps(ctx, n, K, eps2, t0, t1, s0, s1, gsum, dgsum, gsum_tan, dgsum_tan, true);
+}
 
 int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q,
                                    const double *p, int K, const double *dq, const double *dp,

@@ -2979,4 +2979,45 @@ __global__ void predict_pack_kernel(int n, const double *__restrict__ t,
   o[3] = make_double2(vp[2], 0.0);
 }
 
+// The same predictor over dual numbers (dFloat_hermite.ml:60-79): direction k of body i carries
+// tangents of t, q, p, f, df (the mass is a constant, dFloat_hermite.ml:36-46) and the target
+// time nt carries nt_tan[k].  Values follow predict_pack_kernel; the tangents are the product /
+// quotient rules applied to the same expression tree:
+//   ddt = dnt - dt_i, dpc = ddt/m, dfc = (dpc dt + pc ddt) 0.5, ddfc = (dfc dt + fc ddt)/3
+//   dqp = dq + dpc p + pc dp + dfc f + fc df_ + ddfc df + dfc_ ddf      (df_ = f's tangent)
+//   dpp = dp + ddt f + dt df_ + (dt ddt) df + (dt dt 0.5) ddf
+// stored as the tangent sweep's direction rows {dqp, 0, dpp/m, 0}.  grid = (bodies, K).
+__global__ void predict_pack_tangent_kernel(
+    int n, const double *__restrict__ t, const double *__restrict__ m, const double *__restrict__ q,
+    const double *__restrict__ p, const double *__restrict__ f, const double *__restrict__ df,
+    double nt, const double *__restrict__ t_tan, const double *__restrict__ q_tan,
+    const double *__restrict__ p_tan, const double *__restrict__ f_tan,
+    const double *__restrict__ df_tan, const double *__restrict__ nt_tan,
+    double *__restrict__ aux) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (i >= n) return;
+  const size_t o3 = (size_t)k * 3 * n + 3 * (size_t)i;
+  const double mi = m[i];
+  const double dt = __dsub_rn(nt, t[i]);
+  const double ddt = nt_tan[k] - t_tan[(size_t)k * n + i];
+  const double pc = __ddiv_rn(dt, mi), dpc = ddt / mi;
+  const double fc = __dmul_rn(__dmul_rn(pc, dt), 0.5), dfc = (dpc * dt + pc * ddt) * 0.5;
+  const double dfc3 = __ddiv_rn(__dmul_rn(fc, dt), 3.0), ddfc3 = (dfc * dt + fc * ddt) / 3.0;
+  const double pdfc = __dmul_rn(__dmul_rn(dt, dt), 0.5), dpdfc = dt * ddt;
+  double dqp[3], dvp[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double pk = p[3 * i + c], fk = f[3 * i + c], dfk = df[3 * i + c];
+    const double dq = q_tan[o3 + c], dp = p_tan[o3 + c], dff = f_tan[o3 + c], ddf = df_tan[o3 + c];
+    dqp[c] = dq + (dpc * pk + pc * dp) + (dfc * fk + fc * dff) + (ddfc3 * dfk + dfc3 * ddf);
+    const double dpp = dp + (ddt * fk + dt * dff) + (dpdfc * dfk + pdfc * ddf);
+    dvp[c] = dpp / mi;
+  }
+  double2 *o = reinterpret_cast<double2 *>(aux + ((size_t)k * n + i) * PK);
+  o[0] = make_double2(dqp[0], dqp[1]);
+  o[1] = make_double2(dqp[2], 0.0);
+  o[2] = make_double2(dvp[0], dvp[1]);
+  o[3] = make_double2(dvp[2], 0.0);
+}
+
 }  // namespace nbk

@@ -88,6 +88,29 @@ int nbh_hermite_advance(nbk_ctx *ctx, int n, int *id, double *t, double *m, doub
                         double *h, double *f, double *df, double dt, double sf, double eps2,
                         long *nsteps);
 
+/* ---- DFloat_hermite.advance (dFloat_hermite.ml:199-209) and DFloat_pushforward.Make(DFloat_hermite)
+ * (dFloat_pushforward.ml:39-76, 141-150) ----------------------------------------------------- */
+/* Hermite over dual numbers carrying K tangents at once: every field of a body (t, q, p, h, f,
+ * df) is a dual; masses, sf, dt, eps are constants.  Values as in nbh_hermite_advance; tangents
+ * direction major: t_tan, h_tan [K][n], q_tan, p_tan, f_tan, df_tan [K][3n] (any may be NULL =
+ * zero on input, not returned).  The scheduler compares values (the reference's comparisons on
+ * diff); both pair loops run on the GPU (nbk_grad_v_dgrad_v_sum_tangent for start_bs,
+ * nbk_grad_v_dgrad_v_sum_predicted_tangent for advance_body).  Output rows in id order. */
+int nbh_dfloat_hermite_advance(nbk_ctx *ctx, int n, int K, const int *id, double *t, const double *m,
+                               double *q, double *p, double *h, double *f, double *df,
+                               double *t_tan, double *q_tan, double *p_tan, double *h_tan,
+                               double *f_tan, double *df_tan, double dt, double sf, double eps2,
+                               long *nsteps);
+/* jacobian_advance dt sf bs: fresh Hermite bodies, state packed [q(3n); p(3n)], jac 6n x 6n
+ * row-major (jac[r*6n + c] = d out[r] / d in[c]), out6n (may be NULL) the advanced state; one
+ * pass over the 6n unit directions.  *nsteps (may be NULL) += advance_body calls. */
+int nbh_dfloat_jacobian_advance(nbk_ctx *ctx, int n, const double *m, const double *q,
+                                const double *p, double dt, double sf, double eps2, double *jac,
+                                double *out6n, long *nsteps);
+/* omega_pushforward's scalar from a Jacobian (dFloat_pushforward.ml:141-150): 1 if symplectic. */
+double nbh_omega_pushforward(int n, const double *jac);
+void nbh_set_dfloat_step_cap(long cap);
+
 /* ---- Advancer.A.advance ?extpot bs dt sf (advancer.ml:422-428) ------------------------------ */
 /* state[i*35..] = {t, m, q[3], p[3], h, hmax, t0, dVdq0[3], dVdq1[3], dVdq2[3], p0[3], q0[3],
  * q1[3], q2[3], cs[3]}: the Advancer.A.body record (advancer.ml:27-45); fresh bodies carry NaN

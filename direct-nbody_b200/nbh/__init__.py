@@ -36,6 +36,10 @@ SYMBOLS = {
     "nbh_leapfrog_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _d, _pl]),
     "nbh_leapfrog_advance_const_dt": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _d, _i]),
     "nbh_hermite_advance": (_i, [_vp, _i, _pi, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d, _d, _pl]),
+    "nbh_dfloat_hermite_advance": (_i, [_vp, _i, _i, _pi, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd,
+                                        _pd, _pd, _pd, _pd, _d, _d, _d, _pl]),
+    "nbh_dfloat_jacobian_advance": (_i, [_vp, _i, _pd, _pd, _pd, _d, _d, _d, _pd, _pd, _pl]),
+    "nbh_omega_pushforward": (_d, [_i, _pd]),
     "nbh_advancer_advance": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _vp, _vp, _pl]),
     "nbh_extpot_plummer_test_energy": (_d, [_i, _pd, _pd]),
     "nbh_constant_sf_integrate": (_i, [_vp, _i, _pi, _pd, _d, _d, _d, _d, _d, _pd, _i, _pi]),
@@ -304,6 +308,44 @@ def advancer_advance(ctx, s, dt, sf, eps2=0.0, extpot=None, resident=2, tree_max
 def extpot_plummer_test_energy(m, q):
     m, q = _f(m), _f(q)
     return load_library().nbh_extpot_plummer_test_energy(len(m), _p(m), _p(q))
+
+
+def dfloat_jacobian_advance(ctx, m, q, p, dt, sf, eps2=0.0):
+    """DFloat_pushforward.Make(DFloat_hermite).jacobian_advance dt sf bs
+    (dFloat_pushforward.ml:61-76) -> (jac [6n][6n], advanced [q; p] state [6n], advance_body calls)."""
+    m, q, p = (np.ascontiguousarray(a, dtype=np.float64) for a in (m, q, p))
+    n = len(m)
+    jac, out = np.zeros((6 * n, 6 * n)), np.zeros(6 * n)
+    ns = C.c_long(0)
+    _ck(load_library().nbh_dfloat_jacobian_advance(ctx._h, n, _p(m), _p(q), _p(p), dt, sf, eps2,
+                                                   _p(jac), _p(out), C.byref(ns)))
+    return jac, out, ns.value
+
+
+def omega_pushforward(jac):
+    jac = np.ascontiguousarray(jac, dtype=np.float64)
+    return load_library().nbh_omega_pushforward(jac.shape[0] // 6, _p(jac))
+
+
+def dfloat_hermite_advance(ctx, m, q, p, dq, dp, dt, sf, eps2=0.0):
+    """DFloat_hermite.advance on fresh bodies (t = 0, h = -1) carrying the K tangent directions
+    (dq, dp) [K][n][3] -> dict of advanced values and tangents (id order)."""
+    m, q, p = (np.array(a, dtype=np.float64, order="C") for a in (m, q, p))
+    n = len(m)
+    q_tan = np.array(dq, dtype=np.float64, order="C").reshape(-1, n, 3)
+    p_tan = np.array(dp, dtype=np.float64, order="C").reshape(-1, n, 3)
+    K = q_tan.shape[0]
+    ids = np.arange(1, n + 1, dtype=np.int32)
+    t, h = np.zeros(n), np.full(n, -1.0)
+    f, df = np.zeros((n, 3)), np.zeros((n, 3))
+    t_tan, h_tan = np.zeros((K, n)), np.zeros((K, n))
+    f_tan, df_tan = np.zeros((K, n, 3)), np.zeros((K, n, 3))
+    ns = C.c_long(0)
+    _ck(load_library().nbh_dfloat_hermite_advance(
+        ctx._h, n, K, _ip(ids), _p(t), _p(m), _p(q), _p(p), _p(h), _p(f), _p(df), _p(t_tan),
+        _p(q_tan), _p(p_tan), _p(h_tan), _p(f_tan), _p(df_tan), dt, sf, eps2, C.byref(ns)))
+    return dict(t=t, q=q, p=p, h=h, f=f, df=df, t_tan=t_tan, q_tan=q_tan, p_tan=p_tan,
+                h_tan=h_tan, f_tan=f_tan, df_tan=df_tan, nsteps=ns.value)
 
 
 class EgErr(RuntimeError):

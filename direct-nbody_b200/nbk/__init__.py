@@ -62,6 +62,9 @@ SYMBOLS = {
                                               _i, _i, _i, _i, _pd, _pd]),
     "nbk_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _i, _pd, _pd, _pd, _i, _pd, _pd, _d,
                                             _i, _i, _i, _i, _pd, _pd, _pd, _pd]),
+    "nbk_grad_v_dgrad_v_sum_predicted_tangent": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, _pd, _i, _pd,
+                                                      _pd, _pd, _pd, _pd, _d, _pd, _d, _i, _i, _i,
+                                                      _i, _pd, _pd, _pd, _pd]),
     "nbk_grad_v_sum_tangent": (_i, [_vp, _i, _pd, _pd, _i, _pd, _d, _i, _i, _i, _i, _pd, _pd]),
     "nbk_bodies_upload": (_i, [_vp, _i, _pd, _pd, _pd, _i]),
     "nbk_bodies_update": (_i, [_vp, _i, _i, _pd, _pd, _i]),
@@ -347,6 +350,27 @@ class Context:
         gt, dgt = np.empty((K, nt, 3)), np.empty((K, nt, 3))
         self._ck(self._lib.nbk_grad_v_dgrad_v_sum_tangent(
             self._h, n, _p(m), _p(q), _p(p), K, _p(dq), _p(dp), eps2, t0, t1, s0, s1, _p(g),
+            _p(dg), _p(gt), _p(dgt)))
+        return g, dg, gt, dgt
+
+    def grad_v_dgrad_v_sum_predicted_tangent(self, t, m, q, p, f, df, t_tan, q_tan, p_tan, f_tan,
+                                             df_tan, nt, nt_tan=None, eps2=0.0, targets=None,
+                                             sources=None):
+        """DFloat_hermite.advance_body's loop: *_tan are [K][n][3] ([K][n] for t_tan, [K] for
+        nt_tan; either of those may be None = zeros)."""
+        t, m, q, p, f, df = (_arr(a) for a in (t, m, q, p, f, df))
+        n = len(m)
+        q_tan, p_tan, f_tan, df_tan = (_arr(a).reshape(-1, n, 3) for a in (q_tan, p_tan, f_tan, df_tan))
+        K = q_tan.shape[0]
+        t_tan = None if t_tan is None else _arr(t_tan).reshape(K, n)
+        nt_tan = None if nt_tan is None else _arr(nt_tan).reshape(K)
+        t0, t1, s0, s1 = self._rng(n, targets, sources)
+        ntg = max(t1 - t0, 0)
+        g, dg = np.empty((ntg, 3)), np.empty((ntg, 3))
+        gt, dgt = np.empty((K, ntg, 3)), np.empty((K, ntg, 3))
+        self._ck(self._lib.nbk_grad_v_dgrad_v_sum_predicted_tangent(
+            self._h, n, _p(t), _p(m), _p(q), _p(p), _p(f), _p(df), K, _p(t_tan), _p(q_tan),
+            _p(p_tan), _p(f_tan), _p(df_tan), float(nt), _p(nt_tan), eps2, t0, t1, s0, s1, _p(g),
             _p(dg), _p(gt), _p(dgt)))
         return g, dg, gt, dgt
 

@@ -169,6 +169,25 @@ int nbk_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const d
                                    double eps2, int t0, int t1, int s0, int s1, double *gsum,
                                    double *dgsum, double *gsum_tan, double *dgsum_tan);
 
+/* DFloat_hermite.advance_body's loop (dFloat_hermite.ml:115-135): the dual-number copy of
+ * nbk_grad_v_dgrad_v_sum_predicted.  Every body carries K tangents of its whole Hermite state -
+ * t_tan [K][n] (may be NULL: zeros), q_tan, p_tan, f_tan, df_tan [K][3n], direction major; masses,
+ * eps2 and eta carry none (dFloat_hermite.ml:36-46, dFloat_pushforward.ml:51) - and the target
+ * time is the dual nt + nt_tan[K] (may be NULL: zeros; next_time of the stepping body,
+ * dFloat_hermite.ml:81-82).  Each body is predicted to nt over duals (predict_position_into /
+ * predict_momentum_into, dFloat_hermite.ml:60-79: values by the reference's operation sequence,
+ * tangents by the product and quotient rules on the same expression tree), then
+ * DFloatBase.grad_v_dgrad_v (dFloat_advancer.ml:66-81) is summed over the predicted sources:
+ * value sums gsum, dgsum [3 nt] (either may be NULL; fp = -gsum, dfp = -dgsum) and their
+ * tangents gsum_tan, dgsum_tan [K][3 nt].  With K = 6n unit directions this is one
+ * advance_body of DFloat_pushforward.jacobian_advance (dFloat_pushforward.ml:39-76). */
+int nbk_grad_v_dgrad_v_sum_predicted_tangent(
+    nbk_ctx *ctx, int n, const double *t, const double *m, const double *q, const double *p,
+    const double *f, const double *df, int K, const double *t_tan, const double *q_tan,
+    const double *p_tan, const double *f_tan, const double *df_tan, double nt,
+    const double *nt_tan, double eps2, int t0, int t1, int s0, int s1, double *gsum,
+    double *dgsum, double *gsum_tan, double *dgsum_tan);
+
 /* Tangent of nbk_grad_v_sum (DFloatBase.grad_v, dFloat_advancer.ml:57-64). */
 int nbk_grad_v_sum_tangent(nbk_ctx *ctx, int n, const double *m, const double *q, int K,
                            const double *dq, double eps2, int t0, int t1, int s0, int s1,

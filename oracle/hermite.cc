@@ -236,6 +236,46 @@ void oracle_hermite_advance_body(int n, const double *t, const double *m, const 
   }
 }
 
+// DFloat_hermite.advance_body eta b bs (dFloat_hermite.ml:115-150) for body `ib` against all
+// others in array order, ONE tangent direction: every field of every body is a dual (value
+// arrays as in oracle_hermite_advance_body, tangent arrays *_d of the same shapes); masses and
+// eta are constants.  out / out_d[0..13] = {t, h, q[3], p[3], f[3], df[3]} of the new body:
+// values and tangents.
+void oracle_dfloat_hermite_advance_body(int n, const double *t, const double *m, const double *q,
+                                        const double *p, const double *h, const double *f,
+                                        const double *df, const double *t_d, const double *q_d,
+                                        const double *p_d, const double *h_d, const double *f_d,
+                                        const double *df_d, int ib, double eta, double eps2,
+                                        double *out, double *out_d) {
+  std::vector<HBody<Dual>> bs(n);
+  for (int i = 0; i < n; ++i) {
+    bs[i].id = i;
+    bs[i].t = Dual(t[i], t_d[i]);
+    bs[i].m = Dual(m[i]);
+    bs[i].h = Dual(h[i], h_d[i]);
+    for (int k = 0; k < 3; ++k) {
+      bs[i].q[k] = Dual(q[3 * i + k], q_d[3 * i + k]);
+      bs[i].p[k] = Dual(p[3 * i + k], p_d[3 * i + k]);
+      bs[i].f[k] = Dual(f[3 * i + k], f_d[3 * i + k]);
+      bs[i].df[k] = Dual(df[3 * i + k], df_d[3 * i + k]);
+    }
+  }
+  std::vector<const HBody<Dual> *> others;
+  for (int i = 0; i < n; ++i)
+    if (i != ib) others.push_back(&bs[i]);
+  long ns = 0;
+  HBody<Dual> nb =
+      advance_body<Dual>(Dual(eps2), Dual(eta), bs[ib], others.data(), others.size(), &ns);
+  out[0] = nb.t.v, out_d[0] = nb.t.d;
+  out[1] = nb.h.v, out_d[1] = nb.h.d;
+  for (int k = 0; k < 3; ++k) {
+    out[2 + k] = nb.q[k].v, out_d[2 + k] = nb.q[k].d;
+    out[5 + k] = nb.p[k].v, out_d[5 + k] = nb.p[k].d;
+    out[8 + k] = nb.f[k].v, out_d[8 + k] = nb.f[k].d;
+    out[11 + k] = nb.df[k].v, out_d[11 + k] = nb.df[k].d;
+  }
+}
+
 // Tangent of the rectangular acc+jerk sum (DFloatBase.grad_v_dgrad_v, dFloat_advancer.ml:66-81,
 // accumulated like dFloat_hermite.ml:177-186) for ONE tangent direction (dq, dp); masses and
 // eps2 are constants (dFloat_hermite.ml:36-46).  Outputs the value sums and their tangents.

@@ -74,6 +74,12 @@ void oracle_hermite_advance_body(int n, const double *t, const double *m, const 
                                  const double *p, const double *h, const double *f,
                                  const double *df, int ib, double eta, double eps2,
                                  double *out14);
+void oracle_dfloat_hermite_advance_body(int n, const double *t, const double *m, const double *q,
+                                        const double *p, const double *h, const double *f,
+                                        const double *df, const double *t_d, const double *q_d,
+                                        const double *p_d, const double *h_d, const double *f_d,
+                                        const double *df_d, int ib, double eta, double eps2,
+                                        double *out14, double *out14_d);
 void oracle_grad_v_dgrad_v_sum_tangent(int n, const double *m, const double *q, const double *p,
                                        const double *dq, const double *dp, double eps2, int t0,
                                        int t1, int s0, int s1, double *gsum, double *dgsum,

@@ -78,6 +78,8 @@ def _declare(L):
     sig("oracle_rescale_to_standard_units", _i, _i, _pd, _pd, _pd, _d)
     sig("oracle_hermite_advance", None, _i, _pi, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _d, _d, _d, _pl)
     sig("oracle_hermite_advance_body", None, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _i, _d, _d, _pd)
+    sig("oracle_dfloat_hermite_advance_body", None, _i, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd, _pd,
+        _pd, _pd, _pd, _pd, _i, _d, _d, _pd, _pd)
     sig("oracle_grad_v_dgrad_v_sum_tangent", None, _i, _pd, _pd, _pd, _pd, _pd, _d, _i, _i, _i, _i,
         _pd, _pd, _pd, _pd)
     sig("oracle_grad_v_sum_tangent", None, _i, _pd, _pd, _pd, _d, _i, _i, _i, _i, _pd, _pd)
@@ -318,6 +320,20 @@ def hermite_advance_body(t, m, q, p, h, f, df, ib, eta, eps2=0.0):
     out = np.empty(14)
     lib().oracle_hermite_advance_body(len(arrs[1]), *[_p(a) for a in arrs], ib, eta, eps2, _p(out))
     return dict(t=out[0], h=out[1], q=out[2:5], p=out[5:8], f=out[8:11], df=out[11:14])
+
+
+def dfloat_hermite_advance_body(t, m, q, p, h, f, df, t_d, q_d, p_d, h_d, f_d, df_d, ib, eta,
+                                eps2=0.0):
+    """DFloat_hermite.advance_body (dFloat_hermite.ml:115-150), one tangent direction:
+    returns (values, tangents) dicts of the new body."""
+    vals = [_f(a) for a in (t, m, q, p, h, f, df)]
+    tans = [_f(a) for a in (t_d, q_d, p_d, h_d, f_d, df_d)]
+    out, out_d = np.empty(14), np.empty(14)
+    lib().oracle_dfloat_hermite_advance_body(len(vals[1]), *[_p(a) for a in vals],
+                                             *[_p(a) for a in tans], ib, eta, eps2, _p(out),
+                                             _p(out_d))
+    unpack = lambda o: dict(t=o[0], h=o[1], q=o[2:5], p=o[5:8], f=o[8:11], df=o[11:14])
+    return unpack(out), unpack(out_d)
 
 
 def hermite_jacobian_advance(m, q, p, dt, sf, eps2=0.0):
