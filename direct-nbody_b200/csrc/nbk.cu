@@ -1229,7 +1229,8 @@ int nbk_grad_v_dgrad_v_sum_predicted_tangent(
     predict_pack_tangent_kernel<<<grid, 256, 0, ctx->stream>>>(
         n, (const double *)ctx->d_t.p, (const double *)ctx->d_m.p, (const double *)ctx->d_q.p,
         (const double *)ctx->d_vel.p, (const double *)ctx->d_f.p, (const double *)ctx->d_df.p, nt,
-        d_tt, base, base + Kn3, base + 2 * Kn3, base + 3 * Kn3, d_ntt, (double *)ctx->d_aux.p);
+        d_tt, base, base + Kn3, base + 2 * Kn3, base + 3 * Kn3, d_ntt, (double *)ctx->d_aux.p,
+        (size_t)n * PK);
     CK(cudaGetLastError());
     ctx->launches++;
   }
@@ -2209,6 +2210,45 @@ int nbk_dev_pack_aux(nbk_ctx *ctx, int n, const double *d_m, const double *d_dq,
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return NBK_OK;
   pack_aux_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_m, d_dq, d_dp, 0, d_aux);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_dev_predict_pack(nbk_ctx *ctx, int n, const double *d_t, const double *d_m,
+                         const double *d_q, const double *d_p, const double *d_f,
+                         const double *d_df, double nt, double *d_packed, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || (n > 0 && (!d_t || !d_m || !d_q || !d_p || !d_f || !d_df || !d_packed)))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_predict_pack: bad arguments");
+  if (n == 0) return NBK_OK;
+  CK(cudaSetDevice(ctx->device));
+  predict_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_t, d_m, d_q, d_p, d_f,
+                                                                        d_df, nt, d_packed);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
+int nbk_dev_predict_pack_tangent(nbk_ctx *ctx, int n, int K, const double *d_t, const double *d_m,
+                                 const double *d_q, const double *d_p, const double *d_f,
+                                 const double *d_df, double nt, const double *d_t_tan,
+                                 const double *d_q_tan, const double *d_p_tan,
+                                 const double *d_f_tan, const double *d_df_tan,
+                                 const double *d_nt_tan, double *d_aux, size_t aux_stride,
+                                 void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || K < 0 ||
+      (n > 0 && K > 0 &&
+       (!d_t || !d_m || !d_q || !d_p || !d_f || !d_df || !d_q_tan || !d_p_tan || !d_f_tan ||
+        !d_df_tan || !d_aux || aux_stride < (size_t)n * PK)))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_predict_pack_tangent: bad arguments");
+  if (n == 0 || K == 0) return NBK_OK;
+  CK(cudaSetDevice(ctx->device));
+  dim3 grid((n + 255) / 256, K);
+  predict_pack_tangent_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      n, d_t, d_m, d_q, d_p, d_f, d_df, nt, d_t_tan, d_q_tan, d_p_tan, d_f_tan, d_df_tan, d_nt_tan,
+      d_aux, aux_stride);
   CK(cudaGetLastError());
   ctx->launches++;
   return NBK_OK;

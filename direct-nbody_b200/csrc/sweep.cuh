@@ -2986,20 +2986,21 @@ __global__ void predict_pack_kernel(int n, const double *__restrict__ t,
 //   ddt = dnt - dt_i, dpc = ddt/m, dfc = (dpc dt + pc ddt) 0.5, ddfc = (dfc dt + fc ddt)/3
 //   dqp = dq + dpc p + pc dp + dfc f + fc df_ + ddfc df + dfc_ ddf      (df_ = f's tangent)
 //   dpp = dp + ddt f + dt df_ + (dt ddt) df + (dt dt 0.5) ddf
-// stored as the tangent sweep's direction rows {dqp, 0, dpp/m, 0}.  grid = (bodies, K).
+// stored as the tangent sweep's direction rows {dqp, 0, dpp/m, 0}, direction k at
+// aux + k * aux_stride.  grid = (bodies, K).  t_tan / nt_tan may be NULL (zeros).
 __global__ void predict_pack_tangent_kernel(
     int n, const double *__restrict__ t, const double *__restrict__ m, const double *__restrict__ q,
     const double *__restrict__ p, const double *__restrict__ f, const double *__restrict__ df,
     double nt, const double *__restrict__ t_tan, const double *__restrict__ q_tan,
     const double *__restrict__ p_tan, const double *__restrict__ f_tan,
     const double *__restrict__ df_tan, const double *__restrict__ nt_tan,
-    double *__restrict__ aux) {
+    double *__restrict__ aux, size_t aux_stride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (i >= n) return;
   const size_t o3 = (size_t)k * 3 * n + 3 * (size_t)i;
   const double mi = m[i];
   const double dt = __dsub_rn(nt, t[i]);
-  const double ddt = nt_tan[k] - t_tan[(size_t)k * n + i];
+  const double ddt = (nt_tan ? nt_tan[k] : 0.0) - (t_tan ? t_tan[(size_t)k * n + i] : 0.0);
   const double pc = __ddiv_rn(dt, mi), dpc = ddt / mi;
   const double fc = __dmul_rn(__dmul_rn(pc, dt), 0.5), dfc = (dpc * dt + pc * ddt) * 0.5;
   const double dfc3 = __ddiv_rn(__dmul_rn(fc, dt), 3.0), ddfc3 = (dfc * dt + fc * ddt) / 3.0;
@@ -3013,7 +3014,7 @@ __global__ void predict_pack_tangent_kernel(
     const double dpp = dp + (ddt * fk + dt * dff) + (dpdfc * dfk + pdfc * ddf);
     dvp[c] = dpp / mi;
   }
-  double2 *o = reinterpret_cast<double2 *>(aux + ((size_t)k * n + i) * PK);
+  double2 *o = reinterpret_cast<double2 *>(aux + (size_t)k * aux_stride + (size_t)i * PK);
   o[0] = make_double2(dqp[0], dqp[1]);
   o[1] = make_double2(dqp[2], 0.0);
   o[2] = make_double2(dvp[0], dvp[1]);

@@ -110,6 +110,9 @@ SYMBOLS = {
     "nbk_dev_kick_sum": (_i, [_vp, _vp, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nbk_dev_kick_sum_peer": (_i, [_vp, _psh, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nbk_dev_pack_aux": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nbk_dev_predict_pack": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]),
+    "nbk_dev_predict_pack_tangent": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp,
+                                          _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "nbk_dev_grad_v_dgrad_v_sum_tangent": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, _i, _i, _i, _vp, _vp,
                                                 _vp]),
     "nbk_peer_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp), C.c_char_p]),
@@ -479,6 +482,16 @@ class Context:
     def dev_pack_aux(self, n, d_m, d_dq, d_dp, d_aux, stream=0):
         self._ck(self._lib.nbk_dev_pack_aux(self._h, n, d_m, d_dq, d_dp or None, d_aux,
                                             stream or None))
+
+    def dev_predict_pack(self, n, d_t, d_m, d_q, d_p, d_f, d_df, nt, d_packed, stream=0):
+        self._ck(self._lib.nbk_dev_predict_pack(self._h, n, d_t, d_m, d_q, d_p, d_f, d_df,
+                                                float(nt), d_packed, stream or None))
+
+    def dev_predict_pack_tangent(self, n, K, d_t, d_m, d_q, d_p, d_f, d_df, nt, d_t_tan, d_q_tan,
+                                 d_p_tan, d_f_tan, d_df_tan, d_nt_tan, d_aux, aux_stride, stream=0):
+        self._ck(self._lib.nbk_dev_predict_pack_tangent(
+            self._h, n, K, d_t, d_m, d_q, d_p, d_f, d_df, float(nt), d_t_tan or None, d_q_tan,
+            d_p_tan, d_f_tan, d_df_tan, d_nt_tan or None, d_aux, aux_stride, stream or None))
 
     def dev_grad_v_dgrad_v_sum_tangent(self, d_packed, d_aux, n_total, K, eps2, targets, sources,
                                        d_gsum_tan, d_dgsum_tan, stream=0):

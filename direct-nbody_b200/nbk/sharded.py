@@ -469,6 +469,37 @@ class PeerShardedTangent:
             keep += [d_dq, d_dp]
         torch.cuda.current_stream(self.device).synchronize()
 
+    def load_local_predicted(self, t, m, q, p, f, df, t_tan, q_tan, p_tan, f_tan, df_tan, nt,
+                             nt_tan=None):
+        """The dual-number Hermite step's exchange (DFloat_hermite.advance_body,
+        dFloat_hermite.ml:115-135, all bodies as targets): this rank PREDICTS its own slice to
+        the dual time nt - values and the K tangents of (t, q, p, f, df) - straight into its
+        region (nbk_dev_predict_pack / _tangent); step() then sweeps as usual.  Host arrays of
+        the FULL system: t, m [n]; q, p, f, df [n][3]; t_tan [K][n] or None; *_tan [K][n][3];
+        nt_tan [K] or None."""
+        torch, pl, rg = self.torch, self.plan, self.regions
+        self.cur = next_row_buffer(self.cur, self._stepped_since_load)
+        self._stepped_since_load = False
+        if pl.count == 0:
+            return
+        sl = slice(pl.t0, pl.t1)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+
+        def up(a):
+            return torch.as_tensor(a, dtype=torch.float64).to(self.device).contiguous()
+        d = [up(a[sl]) for a in (t, m, q, p, f, df)]
+        self.ctx.dev_predict_pack(pl.count, *[x.data_ptr() for x in d], nt,
+                                  rg.packed(self.cur)[pl.rank], stream)
+        d_tt = up(t_tan[:, sl]) if t_tan is not None else None
+        d_tan = [up(a[:, sl]) for a in (q_tan, p_tan, f_tan, df_tan)]
+        d_ntt = up(nt_tan) if nt_tan is not None else None
+        self.ctx.dev_predict_pack_tangent(
+            pl.count, self.K, *[x.data_ptr() for x in d], nt,
+            d_tt.data_ptr() if d_tt is not None else 0, *[x.data_ptr() for x in d_tan],
+            d_ntt.data_ptr() if d_ntt is not None else 0, rg.aux(self.cur)[pl.rank],
+            pl.shard * PACKED, stream)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def step(self, eps2: float = 0.0):
         pl, rg = self.plan, self.regions
         self.epoch += 1

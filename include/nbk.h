@@ -379,6 +379,21 @@ int nbk_dev_kick_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double e
  * nbk_dev_pack_aux (dv = dp / m).  Outputs d_gsum_tan, d_dgsum_tan are [K][3 (t1-t0)]. */
 int nbk_dev_pack_aux(nbk_ctx *ctx, int n, const double *d_m, const double *d_dq,
                      const double *d_dp, double *d_aux, void *stream);
+/* The Hermite predictor fused with the pack, on device pointers (one rank predicts its own
+ * slice before a sharded sweep): rows {qp, m, pp/m} of nbk_grad_v_dgrad_v_sum_predicted, and
+ * the direction rows {dqp, 0, dpp/m, 0} of nbk_grad_v_dgrad_v_sum_predicted_tangent (direction k
+ * at d_aux + k * aux_stride doubles; tangent arrays [K][n] / [K][3n]; d_t_tan and d_nt_tan may be
+ * NULL). */
+int nbk_dev_predict_pack(nbk_ctx *ctx, int n, const double *d_t, const double *d_m,
+                         const double *d_q, const double *d_p, const double *d_f,
+                         const double *d_df, double nt, double *d_packed, void *stream);
+int nbk_dev_predict_pack_tangent(nbk_ctx *ctx, int n, int K, const double *d_t, const double *d_m,
+                                 const double *d_q, const double *d_p, const double *d_f,
+                                 const double *d_df, double nt, const double *d_t_tan,
+                                 const double *d_q_tan, const double *d_p_tan,
+                                 const double *d_f_tan, const double *d_df_tan,
+                                 const double *d_nt_tan, double *d_aux, size_t aux_stride,
+                                 void *stream);
 int nbk_dev_grad_v_dgrad_v_sum_tangent(nbk_ctx *ctx, const double *d_packed, const double *d_aux,
                                        int n_total, int K, double eps2, int t0, int t1, int s0,
                                        int s1, double *d_gsum_tan, double *d_dgsum_tan,

@@ -121,3 +121,25 @@ def test_dfloat_hermite_advance_k_directions_equal_single_passes(ctx, oracle):
         for key in ("q_tan", "p_tan", "t_tan", "h_tan", "f_tan", "df_tan"):
             a, b = one[key][0], allk[key][k]
             assert np.allclose(a, b, rtol=1e-12, atol=1e-14 * np.abs(b).max()), key
+
+
+def test_sharded_predicted_tangent_driver_single_rank(ctx, oracle):
+    """PeerShardedTangent.load_local_predicted (device-side dual predictor into the peer region)
+    + step() against the host-buffer entry point, one rank."""
+    import torch
+    from nbk.sharded import PeerShardedTangent, make_plan
+    n, K = 3000, 4
+    m, q, p, t, h, f, df, tan = _dual_state(oracle, n, K, 21)
+    nt, nt_tan = 0.03, np.linspace(-1e-3, 1e-3, K)
+    sh = PeerShardedTangent(make_plan(n, 1, 0, align=128), K, torch.device("cuda", 0), ctx)
+    try:
+        sh.load_local_predicted(t, m, q, p, f, df, tan["t"], tan["q"], tan["p"], tan["f"],
+                                tan["df"], nt, nt_tan)
+        gt, dgt = sh.step(1e-6)
+        torch.cuda.synchronize()
+        _, _, gt_ref, dgt_ref = ctx.grad_v_dgrad_v_sum_predicted_tangent(
+            t, m, q, p, f, df, tan["t"], tan["q"], tan["p"], tan["f"], tan["df"], nt, nt_tan, 1e-6)
+        for a, b in ((gt.cpu().numpy(), gt_ref), (dgt.cpu().numpy(), dgt_ref)):
+            assert np.max(np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)) <= 1e-13
+    finally:
+        sh.close()
