@@ -4,7 +4,12 @@
 #include "sweep.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +27,33 @@ thread_local std::string g_create_error;
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+};
+
+// One host thread per extra device of a multi context (nbk_create_multi): the per-device halves
+// of a sharded sweep (upload + pack, then waits + launch + read-back) are enqueued side by side
+// instead of from one serial host loop - the sweeps cannot start before EVERY device has staged
+// its rows, so that loop's length was on the critical path.  Threads are internal: they never
+// call back into the host program and are parked on a condition variable between calls.
+struct MultiPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  unsigned long long generation = 0;
+  int pending = 0;
+  bool stop = false;
+  std::function<void(int)> job;
+  // sense-reversing barrier between the phases of a job (all ndev participants)
+  std::atomic<int> arrived{0}, sense{0};
+  int nparticipants = 1;
+  void barrier() {
+    const int s = sense.load(std::memory_order_acquire);
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nparticipants) {
+      arrived.store(0, std::memory_order_relaxed);
+      sense.store(s ^ 1, std::memory_order_release);
+    } else {
+      while (sense.load(std::memory_order_acquire) == s) std::this_thread::yield();
+    }
+  }
 };
 
 }  // namespace
@@ -75,6 +107,7 @@ struct nbk_ctx {
   bool p2p_all = false;      // every device of the multi context can map every other's memory
   bool multi_sharded = false;  // the last multi_stage left the bodies sharded (peer-read sweeps)
   int multi_shard_rows = 0;
+  MultiPool *pool = nullptr;   // worker threads of a multi context (NULL: serial host loop)
 };
 
 namespace {
@@ -475,11 +508,12 @@ int run_kick(nbk_ctx *ctx, const double *packed, double eta, double dt, int t0, 
 }  // namespace
 
 // ---- single-process multi-GPU: targets sharded over the devices of a multi context ----------
-// The host has all bodies, so the exchange step is a broadcast: bodies are uploaded and packed
-// once on the first device and copied to the others over NVLink (cudaMemcpyPeerAsync), every
-// device sweeps its slice of the targets over all sources, and each slice is read back into
-// its place in the caller's arrays.  All launches are issued before any read-back so the
-// devices run concurrently.
+// The host has all bodies.  Sharded mode (every device maps every other's memory, sources start
+// on a tile): every device uploads and packs ITS OWN rows - one host->device copy per PCIe link,
+// side by side - and the sweeps read the other devices' rows over NVLink themselves
+// (sweep_kernel<..., PEER>); streams are ordered with events, so the kernels need no ready flags.
+// One host thread per device enqueues its half (MultiPool).  Otherwise: stage on device 0 and
+// broadcast the packed array (cudaMemcpyPeerAsync), serial host loop.
 struct Slice {
   nbk_ctx *c;
   int a, b;  // targets [a, b) of this device
@@ -511,65 +545,7 @@ int multi_plan(nbk_ctx *ctx, int t0, int t1, std::vector<Slice> &out) {
   return NBK_OK;
 }
 
-// Stage the bodies for a multi-device sweep.
-// Peer mode (all devices map each other, sources start on a tile): every device uploads and
-// packs ITS OWN rows - ndev host->device copies in parallel, one per PCIe link - and the sweeps
-// read the other devices' rows over NVLink themselves (sweep_kernel<..., PEER>); streams are
-// ordered with events, so the kernels need no ready flags.
-// Otherwise: stage on device 0 and broadcast the packed array (cudaMemcpyPeerAsync).
-int multi_stage(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
-                int is_velocity, int s0) {
-  const int ndev = 1 + (int)ctx->peers.size();
-  ctx->multi_sharded = false;
-  if (ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ) {
-    if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
-    int rows = (n + ndev - 1) / ndev;
-    rows = (rows + 1023) / 1024 * 1024;  // whole large target tiles (and source tiles) per device
-    for (int d = 0; d < ndev; ++d) {
-      nbk_ctx *c = multi_dev(ctx, d);
-      const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
-      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
-      int rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
-      if (rc == NBK_OK && cnt > 0) {
-        rc = upload(c, c->d_m, m + a, cnt);
-        if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
-        if (rc == NBK_OK && vel) rc = upload(c, c->d_vel, vel + 3 * (size_t)a, 3 * (size_t)cnt);
-        if (rc == NBK_OK)
-          rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
-                    vel ? (const double *)c->d_vel.p : nullptr, is_velocity,
-                    (double *)c->d_packed.p, c->stream);
-      }
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-      if (cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
-        return fail(ctx, NBK_ERR_CUDA, "cudaEventRecord");
-    }
-    for (int d = 0; d < ndev; ++d) {  // nobody sweeps before every shard is packed
-      nbk_ctx *c = multi_dev(ctx, d);
-      cudaSetDevice(c->device);
-      for (int e = 0; e < ndev; ++e)
-        if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
-          return fail(ctx, NBK_ERR_CUDA, "cudaStreamWaitEvent");
-    }
-    CK(cudaSetDevice(ctx->device));
-    ctx->multi_sharded = true;
-    ctx->multi_shard_rows = rows;
-    return NBK_OK;
-  }
-  CK(cudaSetDevice(ctx->device));
-  TRY(stage_bodies(ctx, n, m, q, vel, is_velocity));
-  CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
-  const size_t bytes = (size_t)n * PK * sizeof(double);
-  for (nbk_ctx *peer : ctx->peers) {
-    CK(cudaSetDevice(peer->device));
-    TRY(reserve(peer, peer->d_packed, bytes));
-    CK(cudaStreamWaitEvent(peer->stream, ctx->ev_ready, 0));
-    CK(cudaMemcpyPeerAsync(peer->d_packed.p, peer->device, ctx->d_packed.p, ctx->device, bytes,
-                           peer->stream));
-  }
-  return NBK_OK;
-}
-
-// Sweep parameters of one device's slice after multi_stage.
+// Sweep parameters of one device's slice once the bodies are staged.
 SweepParams multi_params(nbk_ctx *ctx, const Slice &s, double eps2, int s0, int s1) {
   SweepParams P = base_params((const double *)s.c->d_packed.p, eps2, s.a, s.b, s0, s1);
   if (ctx->multi_sharded) {
@@ -585,6 +561,177 @@ SweepParams multi_params(nbk_ctx *ctx, const Slice &s, double eps2, int s0, int 
 template <class Op> int multi_run(nbk_ctx *ctx, nbk_ctx *c, const SweepParams &P) {
   return ctx->multi_sharded ? run_op_peer<Op>(c, P, c->stream, true)
                             : run_op<Op>(c, P, c->stream, true);
+}
+
+// Runs fn(d) for every device of the multi context, device d on its own host thread (d = 0 on
+// the caller's), and returns when all are done.  Without a pool: a serial loop.
+void multi_for(nbk_ctx *ctx, const std::function<void(int)> &fn) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  MultiPool *pool = ctx->pool;
+  if (!pool) {
+    for (int d = 0; d < ndev; ++d) fn(d);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(pool->mu);
+    pool->job = fn;
+    pool->pending = ndev - 1;
+    pool->generation++;
+  }
+  pool->cv_go.notify_all();
+  fn(0);
+  std::unique_lock<std::mutex> lk(pool->mu);
+  pool->cv_done.wait(lk, [&] { return pool->pending == 0; });
+}
+
+void multi_worker(MultiPool *pool, int d) {
+  unsigned long long seen = 0;
+  for (;;) {
+    std::function<void(int)> job;
+    {
+      std::unique_lock<std::mutex> lk(pool->mu);
+      pool->cv_go.wait(lk, [&] { return pool->stop || pool->generation != seen; });
+      if (pool->stop) return;
+      seen = pool->generation;
+      job = pool->job;
+    }
+    job(d);
+    {
+      std::lock_guard<std::mutex> lk(pool->mu);
+      if (--pool->pending == 0) pool->cv_done.notify_all();
+    }
+  }
+}
+
+// One sharded sweep of a multi context from host buffers.  `work(c, slice, P)` enqueues the
+// sweep of the device's slice and its read-backs on c->stream (called with the device current,
+// possibly on a worker thread; it must touch only c).  Returns after every device has finished.
+int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
+                int is_velocity, double eps2, int t0, int t1, int s0, int s1,
+                const std::function<int(nbk_ctx *, const Slice &, SweepParams)> &work) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
+  ctx->multi_sharded = ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ;
+  if (!ctx->multi_sharded) {
+    // fallback: stage on device 0, broadcast, serial host loop
+    CK(cudaSetDevice(ctx->device));
+    TRY(stage_bodies(ctx, n, m, q, vel, is_velocity));
+    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    const size_t bytes = (size_t)n * PK * sizeof(double);
+    for (nbk_ctx *peer : ctx->peers) {
+      CK(cudaSetDevice(peer->device));
+      TRY(reserve(peer, peer->d_packed, bytes));
+      CK(cudaStreamWaitEvent(peer->stream, ctx->ev_ready, 0));
+      CK(cudaMemcpyPeerAsync(peer->d_packed.p, peer->device, ctx->d_packed.p, ctx->device, bytes,
+                             peer->stream));
+    }
+    std::vector<Slice> sl;
+    TRY(multi_plan(ctx, t0, t1, sl));
+    for (Slice &s : sl) {  // launch everywhere first
+      if (s.b == s.a) continue;
+      if (cudaSetDevice(s.c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
+      int rc = work(s.c, s, multi_params(ctx, s, eps2, s0, s1));
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(s.c));
+    }
+    for (Slice &s : sl) {
+      cudaSetDevice(s.c->device);
+      int rc = sync(s.c);
+      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(s.c));
+    }
+    CK(cudaSetDevice(ctx->device));
+    return NBK_OK;
+  }
+  int rows = (n + ndev - 1) / ndev;
+  rows = (rows + 1023) / 1024 * 1024;  // whole large target tiles (and source tiles) per device
+  ctx->multi_shard_rows = rows;
+  std::vector<Slice> sl;
+  TRY(multi_plan(ctx, t0, t1, sl));
+  std::vector<int> rcs(ndev, NBK_OK);
+  if (ctx->pool) ctx->pool->nparticipants = ndev;
+  auto per_device = [&](int d) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    int rc = NBK_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
+    // phase 1: this device's rows
+    const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
+    if (rc == NBK_OK) rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
+    if (rc == NBK_OK && cnt > 0) {
+      rc = upload(c, c->d_m, m + a, cnt);
+      if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
+      if (rc == NBK_OK && vel) rc = upload(c, c->d_vel, vel + 3 * (size_t)a, 3 * (size_t)cnt);
+      if (rc == NBK_OK)
+        rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
+                  vel ? (const double *)c->d_vel.p : nullptr, is_velocity, (double *)c->d_packed.p,
+                  c->stream);
+    }
+    if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
+      rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
+    rcs[d] = rc;
+    // every device's "rows packed" event is recorded (or failed) past this point
+    if (ctx->pool) ctx->pool->barrier();
+    bool all_ok = true;
+    for (int e = 0; e < ndev; ++e) all_ok = all_ok && rcs[e] == NBK_OK;
+    if (!all_ok) return;
+    // phase 2: nobody sweeps before every shard is packed
+    for (int e = 0; e < ndev && rc == NBK_OK; ++e)
+      if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
+        rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
+    const Slice &s = sl[d];
+    if (rc == NBK_OK && s.b > s.a) rc = work(c, s, multi_params(ctx, s, eps2, s0, s1));
+    int rc2 = sync(c);
+    rcs[d] = rc != NBK_OK ? rc : rc2;
+  };
+  if (ctx->pool) {
+    multi_for(ctx, per_device);
+  } else {
+    // serial host loop: phase 1 everywhere, then phase 2 (two passes stand in for the barrier)
+    std::vector<int> keep(ndev, NBK_OK);
+    for (int d = 0; d < ndev; ++d) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      int rc = NBK_OK;
+      if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
+      const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
+      if (rc == NBK_OK) rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
+      if (rc == NBK_OK && cnt > 0) {
+        rc = upload(c, c->d_m, m + a, cnt);
+        if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
+        if (rc == NBK_OK && vel) rc = upload(c, c->d_vel, vel + 3 * (size_t)a, 3 * (size_t)cnt);
+        if (rc == NBK_OK)
+          rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
+                    vel ? (const double *)c->d_vel.p : nullptr, is_velocity,
+                    (double *)c->d_packed.p, c->stream);
+      }
+      if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
+        rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
+      rcs[d] = rc;
+    }
+    bool all_ok = true;
+    for (int e = 0; e < ndev; ++e) all_ok = all_ok && rcs[e] == NBK_OK;
+    for (int d = 0; d < ndev && all_ok; ++d) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      int rc = NBK_OK;
+      cudaSetDevice(c->device);
+      for (int e = 0; e < ndev && rc == NBK_OK; ++e)
+        if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
+          rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
+      const Slice &s = sl[d];
+      if (rc == NBK_OK && s.b > s.a) rc = work(c, s, multi_params(ctx, s, eps2, s0, s1));
+      rcs[d] = rc;
+    }
+    for (int d = 0; d < ndev; ++d) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      cudaSetDevice(c->device);
+      int rc2 = sync(c);
+      if (rcs[d] == NBK_OK) rcs[d] = rc2;
+    }
+  }
+  cudaSetDevice(ctx->device);
+  for (int d = 0; d < ndev; ++d)
+    if (rcs[d] != NBK_OK) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      return c == ctx ? rcs[d] : fail(ctx, rcs[d], "device %d: %s", c->device, nbk_last_error(c));
+    }
+  return NBK_OK;
 }
 
 // =================================================================================================
@@ -659,6 +806,7 @@ int nbk_create_multi(nbk_ctx **out, int ndev, const int *devices) {
     for (int b = 0; b < ndev; ++b) {
       if (a == b) continue;
       nbk_ctx *ca = multi_dev(root, a), *cb = multi_dev(root, b);
+      if (ca->device == cb->device) continue;  // same GPU listed twice (tests): trivially mapped
       int can = 0;
       cudaDeviceCanAccessPeer(&can, ca->device, cb->device);
       if (can) {
@@ -670,6 +818,15 @@ int nbk_create_multi(nbk_ctx **out, int ndev, const int *devices) {
       if (!can) root->p2p_all = false;
     }
   CK(cudaSetDevice(root->device));
+  // one host thread per extra device (NBK_MULTI_THREADS=0: serial host loop)
+  const char *mt = getenv("NBK_MULTI_THREADS");
+  if (ndev > 1 && !(mt && atoi(mt) == 0)) {
+    root->pool = new (std::nothrow) MultiPool();
+    if (root->pool) {
+      root->pool->nparticipants = ndev;
+      for (int d = 1; d < ndev; ++d) root->pool->threads.emplace_back(multi_worker, root->pool, d);
+    }
+  }
   *out = root;
   return NBK_OK;
 }
@@ -678,6 +835,16 @@ int nbk_device_count(const nbk_ctx *ctx) { return ctx ? 1 + (int)ctx->peers.size
 
 void nbk_destroy(nbk_ctx *c) {
   if (!c) return;
+  if (c->pool) {
+    {
+      std::lock_guard<std::mutex> lk(c->pool->mu);
+      c->pool->stop = true;
+    }
+    c->pool->cv_go.notify_all();
+    for (std::thread &t : c->pool->threads) t.join();
+    delete c->pool;
+    c->pool = nullptr;
+  }
   for (nbk_ctx *peer : c->peers) nbk_destroy(peer);
   c->peers.clear();
   cudaSetDevice(c->device);
@@ -704,7 +871,12 @@ void nbk_destroy(nbk_ctx *c) {
 }
 
 int nbk_sm_count(const nbk_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
-int64_t nbk_launch_count(const nbk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t nbk_launch_count(const nbk_ctx *ctx) {
+  if (!ctx) return 0;
+  int64_t tot = ctx->launches;
+  for (const nbk_ctx *peer : ctx->peers) tot += peer->launches;
+  return tot;
+}
 
 int nbk_last_kernel_ms(nbk_ctx *ctx, float *ms) {
   if (!ctx || !ms) return NBK_ERR_ARG;
@@ -722,29 +894,16 @@ int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double
   if (n == 0) return NBK_OK;
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
     if (!gsum) return fail(ctx, NBK_ERR_ARG, "null output");
-    TRY(multi_stage(ctx, n, m, q, nullptr, 1, s0));
-    std::vector<Slice> sl;
-    TRY(multi_plan(ctx, t0, t1, sl));
-    for (Slice &s : sl) {
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
-      int rc = reserve(c, c->d_out[0], 3 * (size_t)(s.b - s.a) * sizeof(double));
-      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
-      P.out[0] = (double *)c->d_out[0].p;
-      if (rc == NBK_OK) rc = multi_run<OpGradV>(ctx, c, P);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-    }
-    for (Slice &s : sl) {
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      cudaSetDevice(c->device);
-      int rc = download(c, gsum + 3 * (size_t)(s.a - t0), c->d_out[0], 3 * (size_t)(s.b - s.a));
-      if (rc == NBK_OK) rc = sync(c);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-    }
-    CK(cudaSetDevice(ctx->device));
-    return NBK_OK;
+    return multi_sweep(ctx, n, m, q, nullptr, 1, eps2, t0, t1, s0, s1,
+                       [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
+                         const size_t cnt = 3 * (size_t)(sl.b - sl.a);
+                         int rc = reserve(c, c->d_out[0], cnt * sizeof(double));
+                         if (rc != NBK_OK) return rc;
+                         P.out[0] = (double *)c->d_out[0].p;
+                         rc = multi_run<OpGradV>(ctx, c, P);
+                         if (rc != NBK_OK) return rc;
+                         return download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0], cnt);
+                       });
   }
   TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
   return run_grad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum);
@@ -759,34 +918,21 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
   if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
     if (!gsum || !dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
-    TRY(multi_stage(ctx, n, m, q, p, 0, s0));
-    std::vector<Slice> sl;
-    TRY(multi_plan(ctx, t0, t1, sl));
-    for (Slice &s : sl) {
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
-      const size_t cnt = 3 * (size_t)(s.b - s.a) * sizeof(double);
-      int rc = reserve(c, c->d_out[0], cnt);
-      if (rc == NBK_OK) rc = reserve(c, c->d_out[1], cnt);
-      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
-      P.out[0] = (double *)c->d_out[0].p;
-      P.out[1] = (double *)c->d_out[1].p;
-      if (rc == NBK_OK) rc = multi_run<OpGradVDGradVB<1>>(ctx, c, P);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-    }
-    for (Slice &s : sl) {
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      cudaSetDevice(c->device);
-      const size_t cnt = 3 * (size_t)(s.b - s.a);
-      int rc = download(c, gsum + 3 * (size_t)(s.a - t0), c->d_out[0], cnt);
-      if (rc == NBK_OK) rc = download(c, dgsum + 3 * (size_t)(s.a - t0), c->d_out[1], cnt);
-      if (rc == NBK_OK) rc = sync(c);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-    }
-    CK(cudaSetDevice(ctx->device));
-    return NBK_OK;
+    return multi_sweep(ctx, n, m, q, p, 0, eps2, t0, t1, s0, s1,
+                       [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
+                         const size_t cnt = 3 * (size_t)(sl.b - sl.a);
+                         int rc = reserve(c, c->d_out[0], cnt * sizeof(double));
+                         if (rc == NBK_OK) rc = reserve(c, c->d_out[1], cnt * sizeof(double));
+                         if (rc != NBK_OK) return rc;
+                         P.out[0] = (double *)c->d_out[0].p;
+                         P.out[1] = (double *)c->d_out[1].p;
+                         rc = multi_run<OpGradVDGradVB<1>>(ctx, c, P);
+                         if (rc != NBK_OK) return rc;
+                         // each slice goes home as soon as its own fix-up ends
+                         rc = download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0], cnt);
+                         if (rc != NBK_OK) return rc;
+                         return download(c, dgsum + 3 * (size_t)(sl.a - t0), c->d_out[1], cnt);
+                       });
   }
   TRY(stage_bodies(ctx, n, m, q, p, 0));
   return run_grad_v_dgrad_v(ctx, (const double *)ctx->d_packed.p, eps2, t0, t1, s0, s1, gsum,
@@ -802,40 +948,36 @@ int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2
     return NBK_OK;
   }
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
-    TRY(multi_stage(ctx, n, m, q, nullptr, 1, s0));
-    std::vector<Slice> sl;
-    TRY(multi_plan(ctx, t0, t1, sl));
-    for (Slice &s : sl) {  // launch everywhere first
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
-      int rc = reserve(c, c->d_out[0], (size_t)(s.b - s.a) * sizeof(double));
-      if (rc == NBK_OK) rc = reserve(c, c->d_scalar, 64);
-      SweepParams P = multi_params(ctx, s, eps2, s0, s1);
-      P.out[0] = (double *)c->d_out[0].p;
-      if (rc == NBK_OK) rc = multi_run<OpV>(ctx, c, P);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-      if (total) {
-        sum_kernel<<<1, 1024, 0, c->stream>>>((const double *)c->d_out[0].p, s.b - s.a,
-                                              (double *)c->d_scalar.p);
-        c->launches++;
-        cudaMemcpyAsync(c->h_scalar, c->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost,
-                        c->stream);
-      }
+    const int ndev = 1 + (int)ctx->peers.size();
+    std::vector<char> has(ndev, 0);
+    char *hasp = has.data();
+    TRY(multi_sweep(ctx, n, m, q, nullptr, 1, eps2, t0, t1, s0, s1,
+                    [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
+                      const size_t cnt = (size_t)(sl.b - sl.a);
+                      int rc = reserve(c, c->d_out[0], cnt * sizeof(double));
+                      if (rc == NBK_OK) rc = reserve(c, c->d_scalar, 64);
+                      if (rc != NBK_OK) return rc;
+                      P.out[0] = (double *)c->d_out[0].p;
+                      rc = multi_run<OpV>(ctx, c, P);
+                      if (rc != NBK_OK) return rc;
+                      if (total) {
+                        sum_kernel<<<1, 1024, 0, c->stream>>>((const double *)c->d_out[0].p,
+                                                              (int)cnt, (double *)c->d_scalar.p);
+                        c->launches++;
+                        if (cudaMemcpyAsync(c->h_scalar, c->d_scalar.p, sizeof(double),
+                                            cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+                          return fail(c, NBK_ERR_CUDA, "cudaMemcpyAsync failed");
+                        hasp[sl.d] = 1;
+                      }
+                      if (phi) return download(c, phi + (size_t)(sl.a - t0), c->d_out[0], cnt);
+                      return NBK_OK;
+                    }));
+    if (total) {  // per-device partial sums, combined in device order (fixed summation order)
+      double tot = 0.0;
+      for (int d = 0; d < ndev; ++d)
+        if (has[d]) tot += multi_dev(ctx, d)->h_scalar[0];
+      *total = tot;
     }
-    double tot = 0.0;
-    for (Slice &s : sl) {  // then collect, in device order (fixed summation order)
-      if (s.b == s.a) continue;
-      nbk_ctx *c = s.c;
-      cudaSetDevice(c->device);
-      int rc = NBK_OK;
-      if (phi) rc = download(c, phi + (size_t)(s.a - t0), c->d_out[0], (size_t)(s.b - s.a));
-      if (rc == NBK_OK) rc = sync(c);
-      if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(c));
-      if (total) tot += c->h_scalar[0];
-    }
-    if (total) *total = tot;
-    CK(cudaSetDevice(ctx->device));
     return NBK_OK;
   }
   TRY(stage_bodies(ctx, n, m, q, nullptr, 1));

@@ -418,6 +418,42 @@ def test_single_process_multi_gpu_context(oracle):
         assert abs(pe - oracle.total_potential_energy(m, q)) <= 1e-12 * abs(pe)
 
 
+@pytest.mark.parametrize("ndev,threads", [(2, "1"), (3, "1"), (3, "0")])
+def test_virtual_multi_device_context_on_one_gpu(oracle, monkeypatch, ndev, threads):
+    """nbk_create_multi over the SAME GPU listed ndev times: every "device" is its own context
+    with its own stream, host thread (NBK_MULTI_THREADS=1) and shard of the rows, and the PEER
+    sweeps read the other shards in place - everything but the NVLink hop, on a 1-GPU box.
+    Repeated calls with changing bodies exercise the per-call staging and the thread hand-off."""
+    import nbk
+    monkeypatch.setenv("NBK_MULTI_THREADS", threads)
+    n = 9000
+    m, q, p = oracle.make_plummer(n, 31)
+    with nbk.Context(0) as one, nbk.Context(devices=[0] * ndev) as multi:
+        assert multi.device_count == ndev
+        for rep in range(4):
+            qq = q * (1.0 + 0.01 * rep)
+            a = one.grad_v_dgrad_v_sum(m, qq, p, 1e-4)
+            b = multi.grad_v_dgrad_v_sum(m, qq, p, 1e-4)
+            assert rel_err(b[0], a[0]) <= 1e-13 and rel_err(b[1], a[1]) <= 1e-13
+        g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q * 1.03, p, 1e-4)
+        assert rel_err(b[0], g_ref) <= TOL and rel_err(b[1], dg_ref) <= TOL
+        assert rel_err(multi.grad_v_sum(m, q, 0.0), one.grad_v_sum(m, q, 0.0)) <= 1e-13
+        pa, ta = one.v_sum(m, q, 0.0)
+        pb, tb = multi.v_sum(m, q, 0.0)
+        assert np.allclose(pa, pb, rtol=1e-13, atol=0) and abs(ta - tb) <= 1e-13 * abs(ta)
+        sub = multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 8100), sources=(128, 8950))
+        ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 8100), sources=(128, 8950))
+        assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
+        # sources not starting on a tile: the broadcast fallback, serial host loop
+        sub = multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
+        ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(100, 4100), sources=(50, 4950))
+        assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
+        ke, pe = multi.energy(m, q, p, 0.0)
+        assert abs(pe - oracle.total_potential_energy(m, q)) <= 1e-12 * abs(pe)
+        with pytest.raises(nbk.NbkError):
+            multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(0, n + 1))
+
+
 def test_fuzz_rectangles_all_shapes(ctx, oracle):
     """Random sizes, target/source rectangles, softenings and tile shapes: exercises the stream-K
     split points and the fix-up's slot rule at many (n_it, n_jt, units_per_cta) combinations."""
