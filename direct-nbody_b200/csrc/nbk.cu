@@ -603,12 +603,16 @@ void multi_worker(MultiPool *pool, int d) {
   }
 }
 
-// One sharded sweep of a multi context from host buffers.  `work(c, slice, P)` enqueues the
-// sweep of the device's slice and its read-backs on c->stream (called with the device current,
-// possibly on a worker thread; it must touch only c).  Returns after every device has finished.
+// One sharded sweep of a multi context from host buffers.  `launch(c, slice, P)` enqueues the
+// sweep of the device's slice on c->stream, `collect(c, slice)` its read-backs (both called with
+// the device current, possibly on a worker thread; they must touch only c).  The serial paths
+// launch everywhere before collecting anywhere - a read-back into pageable memory blocks the
+// host.  Returns after every device has finished.
+using MultiLaunch = std::function<int(nbk_ctx *, const Slice &, SweepParams)>;
+using MultiCollect = std::function<int(nbk_ctx *, const Slice &)>;
 int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
                 int is_velocity, double eps2, int t0, int t1, int s0, int s1,
-                const std::function<int(nbk_ctx *, const Slice &, SweepParams)> &work) {
+                const MultiLaunch &launch, const MultiCollect &collect) {
   const int ndev = 1 + (int)ctx->peers.size();
   if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
   ctx->multi_sharded = ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ;
@@ -630,12 +634,13 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
     for (Slice &s : sl) {  // launch everywhere first
       if (s.b == s.a) continue;
       if (cudaSetDevice(s.c->device) != cudaSuccess) return fail(ctx, NBK_ERR_CUDA, "cudaSetDevice");
-      int rc = work(s.c, s, multi_params(ctx, s, eps2, s0, s1));
+      int rc = launch(s.c, s, multi_params(ctx, s, eps2, s0, s1));
       if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(s.c));
     }
     for (Slice &s : sl) {
       cudaSetDevice(s.c->device);
-      int rc = sync(s.c);
+      int rc = s.b > s.a ? collect(s.c, s) : NBK_OK;
+      if (rc == NBK_OK) rc = sync(s.c);
       if (rc != NBK_OK) return fail(ctx, rc, "%s", nbk_last_error(s.c));
     }
     CK(cudaSetDevice(ctx->device));
@@ -677,7 +682,8 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
       if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
         rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
     const Slice &s = sl[d];
-    if (rc == NBK_OK && s.b > s.a) rc = work(c, s, multi_params(ctx, s, eps2, s0, s1));
+    if (rc == NBK_OK && s.b > s.a) rc = launch(c, s, multi_params(ctx, s, eps2, s0, s1));
+    if (rc == NBK_OK && s.b > s.a) rc = collect(c, s);  // the slice goes home as soon as it is done
     int rc2 = sync(c);
     rcs[d] = rc != NBK_OK ? rc : rc2;
   };
@@ -715,12 +721,14 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
         if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
           rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
       const Slice &s = sl[d];
-      if (rc == NBK_OK && s.b > s.a) rc = work(c, s, multi_params(ctx, s, eps2, s0, s1));
+      if (rc == NBK_OK && s.b > s.a) rc = launch(c, s, multi_params(ctx, s, eps2, s0, s1));
       rcs[d] = rc;
     }
     for (int d = 0; d < ndev; ++d) {
       nbk_ctx *c = multi_dev(ctx, d);
       cudaSetDevice(c->device);
+      const Slice &s = sl[d];
+      if (all_ok && rcs[d] == NBK_OK && s.b > s.a) rcs[d] = collect(c, s);
       int rc2 = sync(c);
       if (rcs[d] == NBK_OK) rcs[d] = rc2;
     }
@@ -900,9 +908,11 @@ int nbk_grad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double
                          int rc = reserve(c, c->d_out[0], cnt * sizeof(double));
                          if (rc != NBK_OK) return rc;
                          P.out[0] = (double *)c->d_out[0].p;
-                         rc = multi_run<OpGradV>(ctx, c, P);
-                         if (rc != NBK_OK) return rc;
-                         return download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0], cnt);
+                         return multi_run<OpGradV>(ctx, c, P);
+                       },
+                       [=](nbk_ctx *c, const Slice &sl) -> int {
+                         return download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0],
+                                         3 * (size_t)(sl.b - sl.a));
                        });
   }
   TRY(stage_bodies(ctx, n, m, q, nullptr, 1));
@@ -926,10 +936,11 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
                          if (rc != NBK_OK) return rc;
                          P.out[0] = (double *)c->d_out[0].p;
                          P.out[1] = (double *)c->d_out[1].p;
-                         rc = multi_run<OpGradVDGradVB<1>>(ctx, c, P);
-                         if (rc != NBK_OK) return rc;
-                         // each slice goes home as soon as its own fix-up ends
-                         rc = download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0], cnt);
+                         return multi_run<OpGradVDGradVB<1>>(ctx, c, P);
+                       },
+                       [=](nbk_ctx *c, const Slice &sl) -> int {
+                         const size_t cnt = 3 * (size_t)(sl.b - sl.a);
+                         int rc = download(c, gsum + 3 * (size_t)(sl.a - t0), c->d_out[0], cnt);
                          if (rc != NBK_OK) return rc;
                          return download(c, dgsum + 3 * (size_t)(sl.a - t0), c->d_out[1], cnt);
                        });
@@ -969,7 +980,12 @@ int nbk_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q, double eps2
                           return fail(c, NBK_ERR_CUDA, "cudaMemcpyAsync failed");
                         hasp[sl.d] = 1;
                       }
-                      if (phi) return download(c, phi + (size_t)(sl.a - t0), c->d_out[0], cnt);
+                      return NBK_OK;
+                    },
+                    [=](nbk_ctx *c, const Slice &sl) -> int {
+                      if (phi)
+                        return download(c, phi + (size_t)(sl.a - t0), c->d_out[0],
+                                        (size_t)(sl.b - sl.a));
                       return NBK_OK;
                     }));
     if (total) {  // per-device partial sums, combined in device order (fixed summation order)
