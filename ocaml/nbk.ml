@@ -82,6 +82,84 @@ external lf_download : ctx -> vec -> vec -> vec -> unit = "nbk_ml_lf_download"
 external lf_advance_subsystem : ctx -> float -> float -> vec -> vec -> perm -> unit
   = "nbk_ml_lf_advance_subsystem_bc" "nbk_ml_lf_advance_subsystem"
 
+(* ---- round 2: the remaining integrator-facing entry points ------------------------------------ *)
+type ivec = (int32, int32_elt, c_layout) Array1.t
+
+external device_count : ctx -> int = "nbk_ml_device_count"
+
+(* Energy.total_kinetic_energy alone: no potential sweep runs (pe = NULL in nbk_energy) *)
+external kinetic_energy : ctx -> vec -> vec -> float = "nbk_ml_kinetic_energy"
+external potential_energy : ctx -> vec -> vec -> float -> float = "nbk_ml_potential_energy"
+
+(* Leapfrog.kick loops.  [kick_dv_sum ctx m q dt range dv]: velocities only (eta = infinity);
+   [kick_block_sum ctx m q v ibegin eta dt dv tmin]: the whole loop of advance_subsystem
+   (leapfrog.ml:132-136) for bodies [0, dim m) with the active block [ibegin, dim m) *)
+external kick_dv_sum : ctx -> vec -> vec -> float -> range -> vec -> unit
+  = "nbk_ml_kick_dv_sum_bc" "nbk_ml_kick_dv_sum"
+external kick_block_sum : ctx -> vec -> vec -> vec -> int -> float -> float -> vec -> vec -> unit
+  = "nbk_ml_kick_block_sum_bc" "nbk_ml_kick_block_sum"
+
+(* DFloatBase.grad_v tangents (dFloat_advancer.ml:57-64), k directions, dq direction major *)
+external grad_v_sum_tangent : ctx -> vec -> vec -> int -> vec -> float -> range -> vec -> unit
+  = "nbk_ml_grad_v_sum_tangent_bc" "nbk_ml_grad_v_sum_tangent"
+
+(* DFloat_hermite.advance_body's loop (dFloat_hermite.ml:115-135):
+   [grad_v_dgrad_v_sum_predicted_tangent ctx (t, m, q, p, f, df) k (t_tan, q_tan, p_tan, f_tan, df_tan)
+      nt nt_tan eps2 range (gsum, dgsum, gsum_tan, dgsum_tan)] *)
+external grad_v_dgrad_v_sum_predicted_tangent :
+  ctx -> vec * vec * vec * vec * vec * vec -> int -> vec * vec * vec * vec * vec -> float -> vec ->
+  float -> range -> vec * vec * vec * vec -> unit
+  = "nbk_ml_predicted_tangent_bc" "nbk_ml_predicted_tangent"
+
+(* Analysis.binaries / binaries_threshold / tightest_binary (analysis.ml:836-876) *)
+external binary_scan :
+  ctx -> vec -> vec -> vec -> float -> float -> range -> vec -> ivec -> ivec -> unit
+  = "nbk_ml_binary_scan_bc" "nbk_ml_binary_scan"
+external binary_list : ctx -> vec -> vec -> vec -> float -> float -> ivec -> ivec -> vec -> int
+  = "nbk_ml_binary_list_bc" "nbk_ml_binary_list"
+
+(* packed bodies resident on the device: small-active-set callers *)
+external bodies_upload : ctx -> vec -> vec -> vec -> bool -> unit = "nbk_ml_bodies_upload"
+external bodies_update : ctx -> int -> int -> vec -> vec -> bool -> unit
+  = "nbk_ml_bodies_update_bc" "nbk_ml_bodies_update"
+external resident_count : ctx -> int = "nbk_ml_resident_count"
+external resident_grad_v_sum : ctx -> float -> range -> vec -> unit = "nbk_ml_resident_grad_v_sum"
+external resident_grad_v_dgrad_v_sum : ctx -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_resident_grad_v_dgrad_v_sum"
+external resident_v_sum : ctx -> float -> range -> vec -> float = "nbk_ml_resident_v_sum"
+external resident_kick_sum : ctx -> float -> float -> range -> vec -> vec -> unit
+  = "nbk_ml_resident_kick_sum_bc" "nbk_ml_resident_kick_sum"
+(* [resident_leapfrog_steps ctx dt nsteps q v]: nsteps DKD steps on the device (leapfrog.ml:160-165) *)
+external resident_leapfrog_steps : ctx -> float -> int -> vec -> vec -> unit
+  = "nbk_ml_resident_leapfrog_steps"
+
+(* Leapfrog per-phase calls on the resident array: the recursion above lf_subsystem_max bodies *)
+external lf_permute : ctx -> ivec -> unit = "nbk_ml_lf_permute"
+external lf_begin : ctx -> int -> int -> unit = "nbk_ml_lf_begin"
+external lf_drift : ctx -> int -> int -> float -> unit = "nbk_ml_lf_drift"
+(* [lf_kick_block ctx iend ibegin eta dt with_tscale drift_after dt_max] *)
+external lf_kick_block : ctx -> int -> int -> float -> float -> bool -> float -> vec -> unit
+  = "nbk_ml_lf_kick_block_bc" "nbk_ml_lf_kick_block"
+external lf_subsystem_max : unit -> int = "nbk_ml_lf_subsystem_max"
+
+(* Hermite.b array resident on the device (hermite.ml:95-130, 171-178) *)
+external hermite_upload : ctx -> vec -> vec -> vec -> vec -> vec -> vec -> vec -> unit
+  = "nbk_ml_hermite_upload_bc" "nbk_ml_hermite_upload"
+external hermite_resident_max : unit -> int = "nbk_ml_hermite_resident_max"
+(* [hermite_advance_resident ctx stop_time eta eps2 max_steps] = advance_body calls made *)
+external hermite_advance_resident : ctx -> float -> float -> float -> int -> int
+  = "nbk_ml_hermite_advance_resident"
+external hermite_download : ctx -> vec -> vec -> vec -> vec -> vec -> vec -> unit
+  = "nbk_ml_hermite_download_bc" "nbk_ml_hermite_download"
+(* [hermite_body_sum ctx i nt eps2 upd upd_state gsum dgsum] *)
+external hermite_body_sum : ctx -> int -> float -> float -> int -> vec -> vec -> vec -> unit
+  = "nbk_ml_hermite_body_sum_bc" "nbk_ml_hermite_body_sum"
+
+external adv_energy : ctx -> float -> float * float = "nbk_ml_adv_energy"
+external set_peer_timeout : ctx -> float -> unit = "nbk_ml_set_peer_timeout"
+
+let ivec n = Array1.create int32 c_layout n
+
 (* One context per process, created on first use (the reference is single-threaded and keeps
    its configuration in globals such as Base.eps2, base.ml:20-34). *)
 let the_ctx = lazy (create 0)
