@@ -219,6 +219,42 @@ def test_leapfrog_adaptive_energy_error_beside_oracle(ctx, oracle):
     assert 2.0 < out[0] / out[1] < 8.0
 
 
+def test_leapfrog_unit_time_energy_error_trajectory_beside_oracle(ctx, oracle):
+    """north_star: leapfrog energy-error trajectories agree over ONE N-body time unit.
+    test/leapfrog_test.ml:17-25 at its own length - hot sphere N = 100, Leapfrog.advance bs 1.0 eta,
+    eta in {1e-3, 5e-4} - on the GPU path (device-side advance_subsystem recursion) beside the
+    oracle's sequential-kick run of the same bodies: both stop at t = 1, the GPU path's energy
+    errors sit within 2x of the oracle's, its eta-scaling ratio falls in the reference test's
+    band (sqrt 8, sqrt 32), and the error trajectory sampled every quarter time unit
+    (four successive advances of 1/4) stays within 2x of the oracle's at every checkpoint."""
+    m, q, p = _hot100(oracle, 2)
+    de_gpu, de_ref = [], []
+    for eta in (1e-3, 5e-4):
+        a = nbh.leapfrog_advance(ctx, nbh.LeapfrogState(m, q, p), 1.0, eta)
+        b = oracle.leapfrog_advance(oracle.LeapfrogState(m, q, p), 1.0, eta)
+        assert np.allclose(a.t, 1.0, rtol=0, atol=1e-12) and np.allclose(b.t, 1.0, rtol=0, atol=1e-12)
+        ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
+        de_gpu.append(abs((ke + pe + 0.25) / 0.25))
+        de_ref.append(abs((oracle.energy(b.m, b.q, b.p) + 0.25) / 0.25))
+        print(f"leapfrog N=100 t=1 eta={eta:g}: dE gpu {de_gpu[-1]:.3e} oracle {de_ref[-1]:.3e} "
+              f"kick blocks {a.nkicks} / {b.nkicks}")
+        assert 0.5 < de_gpu[-1] / de_ref[-1] < 2.0, (eta, de_gpu, de_ref)
+    r_gpu, r_ref = de_gpu[0] / de_gpu[1], de_ref[0] / de_ref[1]
+    assert np.sqrt(8.0) < r_ref < np.sqrt(32.0), r_ref
+    assert np.sqrt(8.0) < r_gpu < np.sqrt(32.0), r_gpu
+    # the trajectory: |E(t) + 1/4| / (1/4) at t = 1/4, 1/2, 3/4, 1 from successive advances
+    sa, sb = nbh.LeapfrogState(m, q, p), oracle.LeapfrogState(m, q, p)
+    for k in range(4):
+        sa = nbh.leapfrog_advance(ctx, sa, 0.25, 1e-3)
+        sb = oracle.leapfrog_advance(sb, 0.25, 1e-3)
+        ke, pe = nbh.energy(ctx, sa.m, sa.q, sa.p)
+        da = abs((ke + pe + 0.25) / 0.25)
+        db = abs((oracle.energy(sb.m, sb.q, sb.p) + 0.25) / 0.25)
+        print(f"  t = {0.25 * (k + 1):.2f}: dE gpu {da:.3e} oracle {db:.3e}")
+        assert np.allclose(sa.t, 0.25 * (k + 1), rtol=0, atol=1e-12)
+        assert 0.5 < da / db < 2.0, (k, da, db)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_hermite_short_run_matches_oracle(ctx, oracle, plummer64, mode):
     """mode 1: host scheduler + one launch per advance_body; mode 2: the whole loop in one

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[1], [3], [4] (and [0]) at their stated sizes on one B200, each beside a
 bounded run of the oracle: timings and energy errors, one JSON object per config
-(-> profiles/r1_configs.json).  configs[2] is bench.py.
+(-> profiles/r2_configs.json).  configs[2] is bench.py.
 
 usage: tools/run_configs.py [out.json] [--quick]
 """
@@ -72,36 +72,38 @@ with nbk.Context(0) as ctx:
                     "us_per_interact_call_gpu": 1e6 * tg / max(a.stats[0], 1)})
         print(res[-1], flush=True)
 
-    # ---- configs[1]: Plummer N=16384, leapfrog (const dt DKD), energy error vs reference
+    # ---- configs[1]: Plummer N=16384, leapfrog (const dt DKD), 1024 steps of 1/1024 = one N-body
+    # time unit on the GPU; the oracle (the reference's sequential symmetric kick loop, one core)
+    # beside it AT THE SAME N for the first 64 steps: positions and energy error at that point
     if want("1"):
         n = 16384
         m, q, p = nbh.rescale_to_standard_units(ctx, *nbh.make_plummer(n, 20241))
         s = nbh.LeapfrogState(m, q, p)
         s.dt_max[:] = np.inf  # skip the reference's sub-step ladder on fresh bodies
-        nst = 16 if quick else 64
+        nst_o, nst = (8, 64) if quick else (64, 1024)
         nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 1024, 2)  # warm-up (first use of the kernels)
         t0 = time.perf_counter()
-        a = nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 1024, nst)
+        a64 = nbh.leapfrog_advance_const_dt(ctx, s, 1.0 / 1024, nst_o)
+        a = nbh.leapfrog_advance_const_dt(ctx, a64, 1.0 / 1024, nst - nst_o)
         tg = time.perf_counter() - t0
+        e64 = sum(nbh.energy(ctx, a64.m, a64.q, a64.p))
         ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
-        # oracle on the first 4096 bodies of the same system, same dt and steps
-        n_o = 4096
-        mo, qo, po = O.rescale_to_standard_units(m[:n_o], q[:n_o], p[:n_o])
-        so = O.LeapfrogState(mo, qo, po)
+        so = O.LeapfrogState(m, q, p)
         so.dt_max[:] = np.inf
-        sg = nbh.LeapfrogState(mo, qo, po)
-        sg.dt_max[:] = np.inf
         t0 = time.perf_counter()
-        bo = O.leapfrog_advance_const_dt(so, 1.0 / 1024, nst)
+        bo = O.leapfrog_advance_const_dt(so, 1.0 / 1024, nst_o)
         tc = time.perf_counter() - t0
-        bg = nbh.leapfrog_advance_const_dt(ctx, sg, 1.0 / 1024, nst)
         res.append({"config": 1, "what": f"Leapfrog.advance_const_dt dt=1/1024 x {nst}, Plummer N=16384",
-                    "dE_gpu_n16384": abs((ke + pe + 0.25) / 0.25), "ms_per_step_gpu": 1e3 * tg / nst,
-                    "n_oracle": n_o, "dE_gpu_n4096": abs((sum(nbh.energy(ctx, bg.m, bg.q, bg.p)) + 0.25) / 0.25),
-                    "dE_oracle_n4096": abs((O.energy(bo.m, bo.q, bo.p) + 0.25) / 0.25),
-                    "max_rel_pos_diff_n4096": float(np.max(np.linalg.norm(bg.q - bo.q, axis=1) /
-                                                           np.linalg.norm(bo.q, axis=1))),
-                    "ms_per_step_oracle_1core_n4096": 1e3 * tc / nst})
+                    "t_end": float(a.t[0]), "dE_gpu_t_end": abs((ke + pe + 0.25) / 0.25),
+                    "ms_per_step_gpu": 1e3 * tg / nst,
+                    "oracle_steps_same_n": nst_o,
+                    f"dE_gpu_after_{nst_o}": abs((e64 + 0.25) / 0.25),
+                    f"dE_oracle_after_{nst_o}": abs((O.energy(bo.m, bo.q, bo.p) + 0.25) / 0.25),
+                    f"max_rel_pos_diff_after_{nst_o}": float(np.max(np.linalg.norm(a64.q - bo.q, axis=1) /
+                                                                   np.linalg.norm(bo.q, axis=1))),
+                    f"max_rel_vel_diff_after_{nst_o}": float(np.max(np.linalg.norm(a64.v - bo.v, axis=1) /
+                                                                   np.linalg.norm(bo.v, axis=1))),
+                    "ms_per_step_oracle_1core": 1e3 * tc / nst_o})
         print(res[-1], flush=True)
 
     # ---- configs[1], adaptive: Leapfrog.advance with block time steps, coarse eta; the oracle's
