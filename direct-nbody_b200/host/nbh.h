@@ -159,6 +159,21 @@ int nbh_leapfrog_print(const char *path, int append, int n, const int *id, const
 int nbh_leapfrog_read(const char *path, int cap, int *n, int *id, double *t, double *dt_max,
                       double *m, double *q, double *v);
 
+/* ---- binary state streams: Marshal.to_channel chan (bs : B.b array) [] (bin/nbody.ml:80,
+ * bin/el_mass_segregation.ml:96-108) and Analysis.load_states / load_state (analysis.ml:556-575) -- */
+/* Array.length (load_states file): complete values in the stream (a truncated tail is ignored,
+ * as the reference's `with _ ->` does). */
+int nbh_marshal_count_states(const char *path, int *nstates);
+/* load_state index file: *n bodies (<= cap), id[], state[n][35] in Advancer.A.body field order
+ * (output_counter dropped).  *kind = 17 for Advancer.A.body, 6 for Leapfrog.b (row = {t, m, q[3],
+ * v[3], dt_max}, rest NaN).  Physical sharing in the stream (CODE_SHARED) is resolved. */
+int nbh_marshal_read_state(const char *path, int index, int cap, int *n, int *kind, int *id,
+                           double *state);
+/* Marshal.to_channel of an Advancer.A.body array: appends (append != 0) one value to the stream.
+ * No sharing is emitted; doubles little-endian, small header - what ocamlopt writes on x86-64 /
+ * arm64 up to sharing. */
+int nbh_marshal_write_state(const char *path, int append, int n, const int *id, const double *state);
+
 #ifdef __cplusplus
 }
 #endif

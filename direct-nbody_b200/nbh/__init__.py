@@ -46,6 +46,9 @@ SYMBOLS = {
     "nbh_advancer_print": (_i, [C.c_char_p, _i, _i, _pi, _pd, _pd, _pd, _pd]),
     "nbh_advancer_read": (_i, [C.c_char_p, _i, _pi, _pi, _pd, _pd, _pd, _pd]),
     "nbh_leapfrog_print": (_i, [C.c_char_p, _i, _i, _pi, _pd, _pd, _pd, _pd, _pd]),
+    "nbh_marshal_count_states": (_i, [C.c_char_p, _pi]),
+    "nbh_marshal_read_state": (_i, [C.c_char_p, _i, _i, _pi, _pi, _pi, _pd]),
+    "nbh_marshal_write_state": (_i, [C.c_char_p, _i, _i, _pi, _pd]),
     "nbh_leapfrog_read": (_i, [C.c_char_p, _i, _pi, _pi, _pd, _pd, _pd, _pd, _pd]),
 }
 ADV_STRIDE = 35
@@ -414,3 +417,34 @@ def leapfrog_read(path, cap=1 << 20):
                                          _p(dtm), _p(m), _p(q), _p(v)))
     k = n.value
     return ids[:k], t[:k], dtm[:k], m[:k], q[:k], v[:k]
+
+
+# ---- binary state streams (Marshal.to_channel / Analysis.load_states, analysis.ml:556-575) -------
+def marshal_count_states(path):
+    n = C.c_int(0)
+    _ck(load_library().nbh_marshal_count_states(os.fsencode(path), C.byref(n)))
+    return n.value
+
+
+def marshal_read_state(path, index, cap=1 << 20):
+    """Analysis.load_state index file -> (kind, ids, state[n][35]); kind 17 = Advancer.A.body,
+    6 = Leapfrog.b ({t, m, q, v, dt_max} in the first 9 columns)."""
+    n, kind = C.c_int(0), C.c_int(0)
+    ids = np.zeros(cap, dtype=np.int32)
+    state = np.zeros((cap, ADV_STRIDE))
+    _ck(load_library().nbh_marshal_read_state(os.fsencode(path), index, cap, C.byref(n),
+                                              C.byref(kind), _ip(ids), _p(state)))
+    return kind.value, ids[:n.value].copy(), state[:n.value].copy()
+
+
+def marshal_load_states(path, cap=1 << 20):
+    """Analysis.load_states file: every state of the stream, in order."""
+    return [marshal_read_state(path, k, cap) for k in range(marshal_count_states(path))]
+
+
+def marshal_write_state(path, ids, state, append=True):
+    """Marshal.to_channel out (bs : Advancer.A.body array) [] (bin/el_mass_segregation.ml:104-108)."""
+    ids = _i32(ids)
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    _ck(load_library().nbh_marshal_write_state(os.fsencode(path), int(append), len(ids), _ip(ids),
+                                               _p(state)))

@@ -11,6 +11,7 @@
      ref/traj.hex     Hermite.advance (hermite.ml:180-189), Leapfrog.advance_const_dt / advance
                       (leapfrog.ml:144-165), OA.advance (omelyan_advancer.ml:96-104),
                       Advancer.A.advance (advancer.ml:422-428)
+     ref/states_adv.bin   Marshal.to_channel of the fresh and the advanced Advancer.A.body arrays
 
    The repository cannot run this (its build image has no OCaml toolchain); the first machine that
    has one pins the oracle:   make -C oracle/ref_fixtures REF=/path/to/direct-nbody
@@ -138,6 +139,12 @@ let traj bodies =
   let ab = Array.map (fun (m, q, p) -> Advancer.A.make 0.0 m q p) bodies in
   let ida = Advancer.A.id ab.(0) in
   let out = Advancer.A.advance ab 0.125 1e-3 in
+  (* the drivers' binary state stream (bin/nbody.ml:80, bin/el_mass_segregation.ml:104-108):
+     two values back to back, read here by host/marshal.cpp (tests/test_marshal.py) *)
+  let st = open_out_bin "ref/states_adv.bin" in
+  Marshal.to_channel st ab [];
+  Marshal.to_channel st out [];
+  close_out st;
   Array.iteri (fun s b ->
       emit oc "adv_id" s 0 0 (float_of_int (Advancer.A.id b - ida));
       emit oc "adv_t" s 0 0 b.Advancer.A.t;
@@ -153,4 +160,4 @@ let () =
   pairs (read_bodies "inputs/plummer_n64_seed20240.txt");
   sums (read_bodies "inputs/plummer_n64_seed20240.txt");
   traj (read_bodies "inputs/plummer_n16_std_seed20241.txt");
-  print_endline "wrote ref/pairs.hex ref/sums.hex ref/traj.hex"
+  print_endline "wrote ref/pairs.hex ref/sums.hex ref/traj.hex ref/states_adv.bin"
