@@ -23,8 +23,8 @@
 // the object table.  The writer emits no sharing (legal: sharing is an optimisation of the
 // encoding; the value read back is structurally equal) and little-endian doubles, like ocamlopt
 // on x86-64 / arm64.  PARITY UNPINNED against a real OCaml runtime: checked here by round trips
-// and by hand-assembled streams (tests/test_marshal.py); oracle/ref_fixtures/gen.ml writes a
-// stream from the real Marshal module for the day a toolchain is at hand.
+// and by hand-assembled streams (tests/test_marshal.py), which also reads a stream written by the
+// real Marshal module whenever one has been generated on a machine with an OCaml toolchain.
 #include <cerrno>
 #include <cmath>
 #include <cstdint>
