@@ -12,9 +12,12 @@ contiguous shard of the targets, re-packs its (drifted) rows into the row buffer
 reading, publishes them, and sweeps its targets over all N sources - reading the other ranks'
 rows out of their HBM over NVLink inside the sweep kernel (--exchange nccl: an all-gather in
 front of it).  Strong scaling: N is fixed.  `value` = N(N-1) interactions / step, device-timed
-with the bodies resident in HBM; `e2e` = the same sweep through the reference-facing C-ABI call
-on pinned HOST buffers (H2D + pack + sweep + D2H inside the timed region), one call per rank for
-its shard; `e2e_single_process` = ONE process driving all the GPUs through nbk_create_multi.
+with the bodies resident in HBM; `e2e` = the same sweep from pinned HOST buffers with H2D + pack
++ sweep + D2H inside the timed region: on one GPU the reference-facing C-ABI call
+nbk_grad_v_dgrad_v_sum; on N > 1 the sharded host-buffer step (each rank uploads its own slice,
+peer-read sweep, reads its slice of the results back; the per-rank C-ABI call that uploads the
+whole system everywhere is kept as `e2e.e2e_cabi_full_upload`); `e2e_single_process` = ONE process
+driving all the GPUs through nbk_create_multi (what a single OCaml host does).
 `parity` = the last timed step's results against the oracle, per body, on >= 256 targets per
 rank; the run exits 3 above 1e-12.
 """
@@ -411,18 +414,56 @@ def run_ours(args):
         c._ck(rc)
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_step(ctx, 0, t0, t1, hg, hdg)
-    barrier()
-    tw = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(ctx, k, t0, t1, hg, hdg)  # synchronous: returns with results in host memory
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - tw) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = inter / float(e2e_s.item())
-    h2d = 7 * 8 * n
-    d2h = 6 * 8 * nt
+
+    def timed_host_steps(fn):
+        fn(0)
+        barrier()
+        tw = time.perf_counter()
+        for k in range(e2e_steps):
+            fn(k)  # synchronous: returns with results in host memory
+        barrier()
+        sec = torch.tensor([(time.perf_counter() - tw) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec.item())
+
+    cabi_s = timed_host_steps(lambda k: e2e_step(ctx, k, t0, t1, hg, hdg))
+    e2e = {"value": inter / cabi_s, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * n,
+           "d2h_bytes_per_step": 6 * 8 * nt,
+           "path": "nbk_grad_v_dgrad_v_sum (C ABI) on pinned host buffers"}
+    if world > 1 and exchange == "peer":
+        # The sharded host-buffer step: every rank uploads ITS OWN slice from pinned host memory,
+        # packs it into the row buffer no peer is reading, publishes, sweeps (remote source tiles
+        # read over NVLink by the kernel) and reads its slice of the results back - no rank
+        # uploads the whole system (the per-rank C-ABI call above does: `e2e_cabi_full_upload`).
+        hs_m = torch.from_numpy(m[sl].copy()).pin_memory()
+        hs_p = torch.from_numpy(p[sl].copy()).pin_memory()
+        hs_q = [torch.from_numpy(q[sl].copy()).pin_memory() for q in qs]
+        e_m, e_p, e_q = torch.empty_like(d_m), torch.empty_like(d_p), torch.empty_like(d_q[0])
+
+        def sharded_step(k):
+            e_m.copy_(hs_m, non_blocking=True)
+            e_q.copy_(hs_q[k % 2], non_blocking=True)
+            e_p.copy_(hs_p, non_blocking=True)
+            sh.load_local_device(e_m, e_q, e_p)
+            sh.step(0.0)
+            hg.copy_(g[:max(nt, 1)], non_blocking=True)
+            hdg.copy_(dg[:max(nt, 1)], non_blocking=True)
+            stream.synchronize()
+
+        sh_s = timed_host_steps(sharded_step)
+        e2e = {"value": inter / sh_s, "unit": UNIT, "h2d_bytes_per_step": 7 * 8 * nt,
+               "d2h_bytes_per_step": 6 * 8 * nt, "bytes_are": "per rank (each rank moves its slice)",
+               "path": "PeerShardedAccJerk on pinned host buffers: H2D of the rank's slice, pack, "
+                       "publish, peer-read sweep, D2H of the rank's results",
+               "e2e_cabi_full_upload": {"value": inter / cabi_s, "h2d_bytes_per_step": 7 * 8 * n,
+                                        "what": "every rank calls nbk_grad_v_dgrad_v_sum with the "
+                                                "whole system on host buffers for its targets"}}
+        # the last sharded step's results must be the same sums the device-resident step gave
+        chk = torch.tensor([float(torch.equal(hg[:nt], g[:nt].cpu())
+                                  and torch.equal(hdg[:nt], dg[:nt].cpu()))], device=dev)
+        dist.all_reduce(chk, op=dist.ReduceOp.MIN)
+        e2e["results_read_back_intact"] = bool(chk.item())
 
     # ---- e2e through ONE process driving all the GPUs (nbk_create_multi): what a single
     # OCaml host does.  Rank 0 works, the other ranks wait at the barrier.
@@ -481,8 +522,7 @@ def run_ours(args):
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "parity": parity,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+            "e2e": e2e,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "traffic": traffic,
