@@ -96,7 +96,7 @@ struct nbk_ctx {
   // resident Hermite state
   int hermite_n = 0;
   int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size, -8 the cluster kernel (NBK_HERMITE_THREADS)
-  DevBuf d_hstate, d_hpartial, d_hticket, d_hout;
+  DevBuf d_hstate, d_hpartial, d_hticket, d_hout, d_hgrid;
   double *h_hres = nullptr, *d_hres = nullptr;  // mapped pinned result slot of the per-step kernel
   double hseq = 0.0;
   // pinned host staging for scalar read-back
@@ -862,7 +862,7 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
                     &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
-                    &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout,
+                    &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout, &c->d_hgrid,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
                     &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el, &c->d_lf_packed,
                     &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt, &c->d_lft};
@@ -2207,17 +2207,58 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
   return NBK_OK;
 }
 
-int nbk_hermite_resident_max(void) { return HCL_MAX_N; }
+int nbk_hermite_resident_max(void) { return HGR_MAX_N; }
 
 int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, double eps2,
                                  long max_steps, long *nsteps) {
   if (!ctx) return NBK_ERR_ARG;
   const int n = ctx->hermite_n;
   if (n == 0) return fail(ctx, NBK_ERR_STATE, "no resident Hermite state: call nbk_hermite_upload");
-  if (n > HCL_MAX_N)
-    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n, HCL_MAX_N);
+  if (n > HGR_MAX_N || n > ctx->sm_count * HGR_PER_CTA)
+    return fail(ctx, NBK_ERR_ARG, "nbk_hermite_advance_resident: n=%d exceeds %d", n,
+                std::min(HGR_MAX_N, ctx->sm_count * HGR_PER_CTA));
   CK(cudaSetDevice(ctx->device));
   TRY(reserve(ctx, ctx->d_scalar, 64));
+  if (n > HCL_MAX_N || ctx->hermite_threads == -148) {
+    // the whole grid, one CTA per SM, state split over their shared memories, candidates and
+    // partial sums through L2, two grid barriers per step (cooperative launch)
+    int G = std::min(ctx->sm_count, HGR_MAX_CTAS);
+    G = std::min(G, std::max((n + HGR_THREADS - 1) / HGR_THREADS, (n + HGR_PER_CTA - 1) / HGR_PER_CTA));
+    if (const char *e = getenv("NBK_HERMITE_GRID_CTAS")) G = std::max(1, std::min(G, atoi(e)));
+    G = std::max(G, (n + HGR_PER_CTA - 1) / HGR_PER_CTA);
+    const int per = (n + G - 1) / G;
+    const size_t gsmem = (size_t)per * HRES_STRIDE * sizeof(double);
+    const size_t words = (size_t)2 * G * HCL_CAND + (size_t)2 * G * 8 + 8;
+    TRY(reserve(ctx, ctx->d_hgrid, words * sizeof(double)));
+    double *w = (double *)ctx->d_hgrid.p;
+    HermiteGridParams Q;
+    Q.state = (double *)ctx->d_hstate.p;
+    Q.cand = w;
+    Q.part = w + (size_t)2 * G * HCL_CAND;
+    Q.bar = (unsigned long long *)(Q.part + (size_t)2 * G * 8);
+    Q.nsteps_out = (long long *)ctx->d_scalar.p;
+    Q.n = n;
+    Q.stop_time = stop_time;
+    Q.eta = eta;
+    Q.eps2 = eps2;
+    Q.max_steps = (long long)max_steps;
+    CK(cudaMemsetAsync(Q.bar, 0, 8 * sizeof(double), ctx->stream));
+    CK(cudaFuncSetAttribute(hermite_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)gsmem));
+    void *args[] = {&Q};
+    CK(cudaLaunchCooperativeKernel((const void *)hermite_grid_kernel, dim3(G), dim3(HGR_THREADS),
+                                   args, gsmem, ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    TRY(sync(ctx));
+    long long gsteps;
+    memcpy(&gsteps, ctx->h_scalar, sizeof gsteps);
+    if (nsteps) *nsteps = (long)gsteps;
+    if (gsteps >= (long long)max_steps && max_steps > 0)
+      return fail(ctx, NBK_ERR_STATE, "Hermite step cap (%ld) reached before stop_time", max_steps);
+    return NBK_OK;
+  }
   if (n > HRES_MAX_N || ctx->hermite_threads == -8) {
     // thread-block cluster of 8 CTAs, state split over their shared memories (DSMEM exchange)
     const int per = (n + HCL_CTAS - 1) / HCL_CTAS;

@@ -109,6 +109,25 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return fma(y0, e, y0);
 }
 
+// Grid-wide barrier of a cooperative launch: every CTA adds 1 to a counter in L2 and waits for
+// it to reach `target` (G x the number of barriers so far).
+__device__ __forceinline__ void adv_grid_barrier(unsigned long long *bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ULL);
+    unsigned long long v;
+    const long long c0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - c0 > (20LL << 30)) __trap();  // ~10 s: a CTA is missing, do not hang the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 // ---- sweep parameters ----------------------------------------------------------------------
 struct SweepParams {
   const double *packed;  // [n_total][PK]
@@ -1614,6 +1633,269 @@ __global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 
   if (rank == 0 && tid == 0) *nsteps_out = steps;
 }
 
+// ---- the same stepping loop on the WHOLE GRID (12288 < N <= HGR_MAX_N) --------------------------
+// One CTA per SM (cooperative launch), each keeping n / G bodies in its shared memory; what the
+// cluster variant passes through distributed shared memory goes through L2 here, with two grid
+// barriers per step (an atomic counter, as in adv_tree_kernel):
+//   post:  every CTA writes its earliest unfinished body - key and whole record - into row
+//          [rank] of the candidate table in global memory
+//   barrier A
+//   pick:  every CTA reduces the G keys to the same winner, fetches the winner's record,
+//          predicts its own bodies, sums its part of the 1 x (N-1) acc+jerk and writes six
+//          partial sums into row [rank] of the partial table
+//   barrier B
+//   owner: adds the G partials in rank order (fixed tree), corrector + new time step.
+// Both tables alternate with the step parity, so a fast CTA's post of step s+2 cannot overwrite
+// what a slow one still reads in step s (it would have to pass barrier B of step s+1 first).
+// Replaces one launch + a mapped-memory round trip per step from the host scheduler (17 us).
+constexpr int HGR_THREADS = 256;
+constexpr int HGR_PER_CTA = 1600;          // 1600 x 17 doubles = 217.6 KB of the 227 KB
+constexpr int HGR_MAX_CTAS = 148;
+constexpr int HGR_MAX_N = HGR_MAX_CTAS * HGR_PER_CTA;
+
+struct HermiteGridParams {
+  double *state;            // [n][HB]
+  double *cand;             // [2][G][HCL_CAND]
+  double *part;             // [2][G][8]
+  unsigned long long *bar;  // grid barrier counter, zero at launch
+  long long *nsteps_out;
+  int n;
+  double stop_time, eta, eps2;
+  long long max_steps;
+};
+
+__global__ void __launch_bounds__(HGR_THREADS, 1) hermite_grid_kernel(const HermiteGridParams Q) {
+  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slot 16 = done flag
+  __shared__ double win[HCL_CAND];
+  __shared__ double red[HGR_THREADS / 32][6];
+  __shared__ double key_nt[HGR_THREADS / 32], key_st[HGR_THREADS / 32];
+  __shared__ int key_idx[HGR_THREADS / 32], key_own[HGR_THREADS / 32];
+  __shared__ int s_it, s_owner;
+  __shared__ double s_nt;
+  constexpr int NW = HGR_THREADS / 32;
+  constexpr int NONE = 0x7fffffff;
+  const int G = (int)gridDim.x, rank = (int)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = Q.n;
+  const int per = (n + G - 1) / G;
+  const int j_lo = min(rank * per, n), j_hi = min(j_lo + per, n), nloc = j_hi - j_lo;
+  SweepParams P;
+  P.eps2 = Q.eps2;
+  for (int l = tid; l < nloc; l += HGR_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rec[l * HRES_STRIDE + c] = Q.state[(size_t)(j_lo + l) * HB + c];
+    rec[l * HRES_STRIDE + 16] = 0.0;
+  }
+  __syncthreads();
+  long long steps = 0, stamp = 0;
+  unsigned long long nbar = 0;
+  bool finishing = false;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  auto better = [](double ont, double ost, int oidx, double knt, double kst, int kidx) {
+    return oidx != NONE &&
+           (kidx == NONE || (ont < knt) ||
+            (ont == knt && (ost > kst || (ost == kst && oidx < kidx))));
+  };
+  for (;;) {
+    const int par = (int)(steps & 1);
+    double *cand = Q.cand + (size_t)par * G * HCL_CAND;
+    double *part = Q.part + (size_t)par * G * 8;
+    // ---- post: local arg-min (next time asc, stamp desc, global index asc)
+    double knt = INF, kst = -INF;
+    int kidx = NONE;
+    for (int l = tid; l < nloc; l += HGR_THREADS) {
+      const double *r = rec + l * HRES_STRIDE;
+      if (r[16] != 0.0) continue;
+      const double nt = r[0] + r[14];
+      if (better(nt, r[15], j_lo + l, knt, kst, kidx)) {
+        knt = nt;
+        kst = r[15];
+        kidx = j_lo + l;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ont = __shfl_down_sync(0xffffffffu, knt, off);
+      const double ost = __shfl_down_sync(0xffffffffu, kst, off);
+      const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
+      if (better(ont, ost, oidx, knt, kst, kidx)) {
+        knt = ont;
+        kst = ost;
+        kidx = oidx;
+      }
+    }
+    if (lane == 0) {
+      key_nt[warp] = knt;
+      key_st[warp] = kst;
+      key_idx[warp] = kidx;
+    }
+    __syncthreads();
+    knt = key_nt[0];
+    kst = key_st[0];
+    kidx = key_idx[0];
+    for (int w = 1; w < NW; ++w)
+      if (better(key_nt[w], key_st[w], key_idx[w], knt, kst, kidx)) {
+        knt = key_nt[w];
+        kst = key_st[w];
+        kidx = key_idx[w];
+      }
+    if (tid < HCL_CAND) {
+      double v = 0.0;
+      if (tid == 0) v = knt;
+      else if (tid == 1) v = kst;
+      else if (tid == 2) v = (kidx == NONE) ? -1.0 : (double)kidx;
+      else if (tid < 19 && kidx != NONE) v = rec[(kidx - j_lo) * HRES_STRIDE + (tid - 3)];
+      __stcg(cand + (size_t)rank * HCL_CAND + tid, v);
+    }
+    adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);  // A
+    // ---- pick: the same winner everywhere (thread r reads CTA r's key; G <= HGR_THREADS)
+    {
+      double bnt = INF, bst = -INF;
+      int bidx = NONE, bown = 0;
+      if (tid < G) {
+        const double *c = cand + (size_t)tid * HCL_CAND;
+        const double c2 = __ldcg(c + 2);
+        bidx = c2 < 0.0 ? NONE : (int)c2;
+        bnt = __ldcg(c);
+        bst = __ldcg(c + 1);
+        bown = tid;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ont = __shfl_down_sync(0xffffffffu, bnt, off);
+        const double ost = __shfl_down_sync(0xffffffffu, bst, off);
+        const int oidx = __shfl_down_sync(0xffffffffu, bidx, off);
+        const int oown = __shfl_down_sync(0xffffffffu, bown, off);
+        if (better(ont, ost, oidx, bnt, bst, bidx)) {
+          bnt = ont;
+          bst = ost;
+          bidx = oidx;
+          bown = oown;
+        }
+      }
+      if (lane == 0) {
+        key_nt[warp] = bnt;
+        key_st[warp] = bst;
+        key_idx[warp] = bidx;
+        key_own[warp] = bown;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < NW; ++w)
+          if (better(key_nt[w], key_st[w], key_idx[w], bnt, bst, bidx)) {
+            bnt = key_nt[w];
+            bst = key_st[w];
+            bidx = key_idx[w];
+            bown = key_own[w];
+          }
+        s_it = bidx;
+        s_owner = bown;
+        s_nt = bnt;
+      }
+      __syncthreads();
+    }
+    const int it = s_it, owner = s_owner;
+    if (it == NONE) break;  // every body finished (uniform over the grid)
+    if (!finishing) {
+      if (steps >= Q.max_steps) break;
+      if (s_nt > Q.stop_time) finishing = true;
+    }
+    if (tid < HCL_CAND) win[tid] = __ldcg(cand + (size_t)owner * HCL_CAND + tid);
+    __syncthreads();
+    const double *tr = &win[3];
+    const double h = finishing ? __dsub_rn(Q.stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    double mt, qt[3], vt[3];
+    hermite_predict_fast(tr, nt, mt, qt, vt);
+    const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = tid; l < nloc; l += HGR_THREADS) {
+      double mj, qj[3], vj[3];
+      hermite_predict_fast(rec + l * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, (j_lo + l) == it, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+    __syncthreads();
+    if (tid < 6) {
+      double a = red[0][tid];
+      for (int w = 1; w < NW; ++w) a += red[w][tid];
+      __stcg(part + (size_t)rank * 8 + tid, a);
+    }
+    adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);  // B
+    ++steps;
+    ++stamp;
+    // ---- owner: the G partials in rank order, corrector (hermite.ml:116-123), new time step
+    if (rank == owner) {
+      if (warp < 6) {  // warp c sums component c: lanes take ranks lane, lane+32, ..., fixed tree
+        double a = 0.0;
+        for (int r = lane; r < G; r += 32) a += __ldcg(part + (size_t)r * 8 + warp);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+        if (lane == 0) red[0][warp] = a;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double fp[3], dfp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          fp[c] = mt * red[0][c];
+          dfp[c] = mt * red[0][3 + c];
+        }
+        double *wr = rec + (it - j_lo) * HRES_STRIDE;
+        const double m = mt, eta = Q.eta;
+        double qn[3], pn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+          pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+          qn[c] = __dadd_rn(
+              __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+              __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+        }
+        const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+        const double rr = __dsqrt_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        const double fn = __dsqrt_rn(__dadd_rn(
+            __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+        double hn;
+        if (rr == 0.0) {
+          hn = __dmul_rn(h, 1.189207115002721);
+        } else {
+          const double x =
+              __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+          hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));
+        }
+        wr[0] = nt;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wr[2 + c] = qn[c];
+          wr[5 + c] = pn[c];
+          wr[8 + c] = fp[c];
+          wr[11 + c] = dfp[c];
+        }
+        wr[14] = hn;
+        wr[15] = (double)stamp;
+        if (finishing) wr[16] = 1.0;
+      }
+    }
+    __syncthreads();  // the owner's next arg-min must see the update; uniform in every CTA
+  }
+  __syncthreads();
+  for (int l = tid; l < nloc; l += HGR_THREADS)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) Q.state[(size_t)(j_lo + l) * HB + c] = rec[l * HRES_STRIDE + c];
+  if (rank == 0 && tid == 0) *Q.nsteps_out = steps;
+}
+
 // ---- Analysis.binaries support ------------------------------------------------------------------
 // Slot 7 of a packed body := its global index (OpBinary reports partners by index).
 __global__ void index_kernel(double *__restrict__ packed, int n) {
@@ -2033,23 +2315,6 @@ struct AdvCtl {
 };
 constexpr size_t ADT_SMEM = sizeof(double) * (ADT_MAX * 4 + ADT_TS * 4 + 2 * ADT_MAX + 64 + ADT_MAX * 3) +
                             sizeof(AdvFrame) * ADT_DEPTH + sizeof(int) * 2 * ADT_MAX;
-
-__device__ __forceinline__ void adv_grid_barrier(unsigned long long *bar, unsigned long long target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1ULL);
-    unsigned long long v;
-    const long long c0 = clock64();
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-      if (v >= target) break;
-      if (clock64() - c0 > (20LL << 30)) __trap();  // ~10 s: a CTA is missing, do not hang the GPU
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 __device__ __forceinline__ void adv_cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -7,7 +7,10 @@
 // §3.3), so velocity kicks agree with the reference's sequential loop to rounding and dt_max
 // to O(dt); with dt = 0 (the initial sweep) or eta = infinity (const-dt) they agree exactly.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.hpp"
@@ -46,8 +49,32 @@ int ocaml_compare(double x, double y) {
   return xn ? -1 : 1;
 }
 
+// NBH_LF_PROFILE=1: wall-clock per phase of the host recursion, printed at the end of an advance
+struct Prof {
+  bool on = std::getenv("NBH_LF_PROFILE") != nullptr;
+  double t[4] = {0, 0, 0, 0};  // kick blocks from the host, sorts, device subtrees, drifts
+  long n[4] = {0, 0, 0, 0};
+  std::chrono::steady_clock::time_point t0;
+  void start() {
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void stop(int k) {
+    if (!on) return;
+    t[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    n[k]++;
+  }
+  void report() const {
+    if (!on) return;
+    const char *name[4] = {"kick blocks (host recursion)", "sort_sub", "device subtrees", "drifts"};
+    for (int k = 0; k < 4; ++k)
+      std::fprintf(stderr, "  leapfrog %-30s %8ld calls %10.3f ms  %8.1f us/call\n", name[k], n[k],
+                   1e3 * t[k], n[k] ? 1e6 * t[k] / n[k] : 0.0);
+  }
+};
+
 struct Leap {
   nbk_ctx *ctx;
+  Prof prof;
   std::vector<LBody> bs;
   std::vector<double> m, q, v, dv, tm;
   std::vector<int> perm;
@@ -197,20 +224,32 @@ struct Leap {
 
   int advance_subsystem(double dt, double eta, int iend) {  // leapfrog.ml:119-142
     if (iend <= 0) return 0;
-    if (resident && tree_max > 0 && iend <= tree_max) return advance_subsystem_on_device(dt, eta, iend);
+    if (resident && tree_max > 0 && iend <= tree_max) {
+      prof.start();
+      int rc = advance_subsystem_on_device(dt, eta, iend);
+      prof.stop(2);
+      return rc;
+    }
     const int ibegin = find_can_advance_index(iend, dt);
     const double dt2 = dt / 2.0;
     NBH_TRY(begin_block(ibegin, iend));
     NBH_TRY(advance_subsystem(dt2, eta, ibegin));
+    prof.start();
     NBH_TRY(drift_block(dt2, ibegin, iend));
+    prof.stop(3);
+    prof.start();
     if (resident) {
       NBH_TRY(kick_block(eta, dt, ibegin, iend, true, dt2));  // kick + second half drift, one call
     } else {
       NBH_TRY(kick_block(eta, dt, ibegin, iend));
       NBH_TRY(drift_block(dt2, ibegin, iend));
     }
+    prof.stop(0);
     NBH_TRY(advance_subsystem(dt2, eta, ibegin));
-    return sort_sub(iend);
+    prof.start();
+    int rc = sort_sub(iend);
+    prof.stop(1);
+    return rc;
   }
 };
 
@@ -269,6 +308,7 @@ int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max
   if (L.resident) NBH_TRY(L.fetch());
   store(L, id, t, dt_max, m, q, v);
   if (nkicks) *nkicks = L.nkicks;
+  L.prof.report();
   return 0;
 }
 

@@ -336,7 +336,9 @@ int nbk_hermite_upload(nbk_ctx *ctx, int n, const double *t, const double *m, co
 int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
                          const double *upd_state, double *gsum, double *dgsum);
 /* Hermite.advance_bodies + finish_bs (hermite.ml:132-143, 171-178) run ENTIRELY on the device
- * by one persistent kernel over the resident state (n <= nbk_hermite_resident_max()): steps
+ * by one persistent kernel over the resident state (n <= nbk_hermite_resident_max(): one CTA
+ * up to 1536 bodies, an 8-CTA cluster up to 12288, the whole grid - cooperative launch, two grid
+ * barriers per step - up to 1600 bodies per SM): steps
  * single bodies in the reference's list order until every next time exceeds stop_time, then
  * steps every body to stop_time.  *nsteps = advance_body calls made (Base.nsteps,
  * hermite.ml:124).  Stops early, returning NBK_ERR_STATE, after max_steps steps of the first

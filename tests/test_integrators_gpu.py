@@ -402,6 +402,45 @@ def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
     assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8
 
 
+@pytest.mark.parametrize("n,ctas", [(2000, "0"), (2000, "3"), (300, "0"), (7, "0")])
+def test_hermite_grid_kernel_matches_cluster_kernel_and_oracle(oracle, monkeypatch, n, ctas):
+    """N > 12288 steps on the whole grid (cooperative launch: state split over the SMs' shared
+    memories, candidates and partial sums through L2, two grid barriers per step).  Forced here at
+    small N (NBK_HERMITE_THREADS=-148) so that the oracle and the other device loops can run
+    beside it: same steps, same state."""
+    import nbk
+    monkeypatch.setenv("NBK_HERMITE_THREADS", "-148")
+    if ctas != "0":
+        monkeypatch.setenv("NBK_HERMITE_GRID_CTAS", ctas)
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 20246))
+    span = 0.004 if n > 100 else 0.05
+    with nbk.Context(0) as grid_ctx:
+        a = nbh.hermite_advance(grid_ctx, nbh.HermiteState(m, q, p), span, 1e-4, mode=2)
+    monkeypatch.delenv("NBK_HERMITE_THREADS")
+    with nbk.Context(0) as plain_ctx:
+        b = nbh.hermite_advance(plain_ctx, nbh.HermiteState(m, q, p), span, 1e-4, mode=2)
+    c = oracle.hermite_advance(oracle.HermiteState(m, q, p), span, 1e-4)
+    assert np.all(a.t == span) and np.array_equal(a.id, c.id)
+    assert abs(a.nsteps - c.nsteps) <= 2 and a.nsteps == b.nsteps
+    assert rel(a.q, c.q) <= 1e-10 and rel(a.p, c.p) <= 1e-8
+    assert rel(a.q, b.q) <= 1e-11 and rel(a.p, b.p) <= 1e-9
+
+
+def test_hermite_grid_kernel_large_system_beside_host_scheduler(ctx, oracle):
+    """N = 20000 (> 12288: the grid kernel is the automatic choice) against the host scheduler's
+    one-launch-per-step path over the same short span, and the oracle's step count."""
+    n = 20000
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 20247))
+    span = 2.0 ** -12
+    a = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), span, 1e-3, mode=0)   # grid kernel
+    b = nbh.hermite_advance(ctx, nbh.HermiteState(m, q, p), span, 1e-3, mode=1)   # host scheduler
+    assert np.all(a.t == span) and np.all(b.t == span)
+    assert a.nsteps >= n and abs(a.nsteps - b.nsteps) <= 2
+    assert rel(a.q, b.q) <= 1e-11 and rel(a.p, b.p) <= 1e-9
+    ke, pe = nbh.energy(ctx, a.m, a.q, a.p)
+    assert abs((ke + pe + 0.25) / 0.25) < 1e-6
+
+
 @pytest.mark.parametrize("n,span,eps", [(10, 1.0, 0.4), (100, 0.25, 0.04), (1024, 1.0 / 64, 0.01)])
 def test_advancer_device_resident_is_bit_identical_to_host_path(ctx, oracle, n, span, eps):
     """Advancer.A with the body records resident on the device (nbk_adv_*: predictors,
