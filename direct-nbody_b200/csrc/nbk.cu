@@ -610,13 +610,26 @@ void multi_worker(MultiPool *pool, int d) {
 // host.  Returns after every device has finished.
 using MultiLaunch = std::function<int(nbk_ctx *, const Slice &, SweepParams)>;
 using MultiCollect = std::function<int(nbk_ctx *, const Slice &)>;
+// optional: stage more per-row data of rows [a, b) on device c (sharded mode only; `rows` = rows
+// per device), e.g. the tangent directions
+using MultiStage = std::function<int(nbk_ctx *, int a, int b, int rows)>;
+
+// Sharded mode needs every device to map every other's memory, sources starting on a tile, and
+// at least one tile per device.
+bool multi_can_shard(const nbk_ctx *ctx, int n, int s0) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  return ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ;
+}
+
 int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const double *vel,
                 int is_velocity, double eps2, int t0, int t1, int s0, int s1,
-                const MultiLaunch &launch, const MultiCollect &collect) {
+                const MultiLaunch &launch, const MultiCollect &collect,
+                const MultiStage &stage = nullptr) {
   const int ndev = 1 + (int)ctx->peers.size();
   if (!m || !q) return fail(ctx, NBK_ERR_ARG, "null body array");
-  ctx->multi_sharded = ctx->p2p_all && s0 % TJ == 0 && n >= ndev * TJ;
+  ctx->multi_sharded = multi_can_shard(ctx, n, s0);
   if (!ctx->multi_sharded) {
+    if (stage) return fail(ctx, NBK_ERR_STATE, "multi_sweep: extra row data needs the sharded mode");
     // fallback: stage on device 0, broadcast, serial host loop
     CK(cudaSetDevice(ctx->device));
     TRY(stage_bodies(ctx, n, m, q, vel, is_velocity));
@@ -669,6 +682,7 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
                   vel ? (const double *)c->d_vel.p : nullptr, is_velocity, (double *)c->d_packed.p,
                   c->stream);
     }
+    if (rc == NBK_OK && stage) rc = stage(c, a, b, rows);
     if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
       rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
     rcs[d] = rc;
@@ -707,6 +721,7 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
                     vel ? (const double *)c->d_vel.p : nullptr, is_velocity,
                     (double *)c->d_packed.p, c->stream);
       }
+      if (rc == NBK_OK && stage) rc = stage(c, a, b, rows);
       if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
         rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
       rcs[d] = rc;
@@ -1041,6 +1056,29 @@ int nbk_kick_sum(nbk_ctx *ctx, int n, const double *m, const double *q, const do
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return NBK_OK;
   if (tmin && !v) return fail(ctx, NBK_ERR_ARG, "time-scale needs velocities");
+  if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {  // targets sharded over the devices
+    if (!dv) return fail(ctx, NBK_ERR_ARG, "null output");
+    return multi_sweep(ctx, n, m, q, v, 1, 0.0, t0, t1, s0, s1,
+                       [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
+                         const size_t cnt = (size_t)(sl.b - sl.a);
+                         int rc = reserve(c, c->d_out[0], 3 * cnt * sizeof(double));
+                         if (rc == NBK_OK) rc = reserve(c, c->d_out[1], cnt * sizeof(double));
+                         if (rc != NBK_OK) return rc;
+                         P.dt = dt;
+                         P.eta = eta;
+                         P.out[0] = (double *)c->d_out[0].p;
+                         P.out[1] = (double *)c->d_out[1].p;
+                         return tmin ? multi_run<OpKick<true>>(ctx, c, P)
+                                     : multi_run<OpKick<false>>(ctx, c, P);
+                       },
+                       [=](nbk_ctx *c, const Slice &sl) -> int {
+                         const size_t cnt = (size_t)(sl.b - sl.a);
+                         int rc = download(c, dv + 3 * (size_t)(sl.a - t0), c->d_out[0], 3 * cnt);
+                         if (rc == NBK_OK && tmin)
+                           rc = download(c, tmin + (size_t)(sl.a - t0), c->d_out[1], cnt);
+                         return rc;
+                       });
+  }
   TRY(stage_bodies(ctx, n, m, q, v, 1));
   return run_kick(ctx, (const double *)ctx->d_packed.p, eta, dt, t0, t1, s0, s1, dv, tmin);
 }
@@ -1316,6 +1354,90 @@ int tangent_common(nbk_ctx *ctx, int n, const double *m, const double *q, const 
     return fail(ctx, NBK_ERR_ARG, "tangent sweep: bad direction arguments");
   if (n == 0 || t1 == t0) return NBK_OK;
   const size_t n3 = 3 * (size_t)n;
+  if (!ctx->peers.empty() && s1 > s0 && K > 0 && multi_can_shard(ctx, n, s0)) {
+    // one process, several GPUs: targets sharded, every device stages its own rows of the bodies
+    // AND of the K direction arrays, the tangent sweeps read the other devices' rows in place
+    const size_t ntg = (size_t)(t1 - t0);
+    return multi_sweep(
+        ctx, n, m, q, jerk ? p : nullptr, 0, eps2, t0, t1, s0, s1,
+        [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
+          const size_t cnt = (size_t)(sl.b - sl.a);
+          const int ndev = 1 + (int)ctx->peers.size();
+          const size_t dir = (size_t)ctx->multi_shard_rows * PK;  // doubles per direction in a shard
+          int rc = reserve(c, c->d_out[0], (size_t)K * 3 * cnt * sizeof(double));
+          if (rc == NBK_OK) rc = reserve(c, c->d_out[1], (size_t)K * 3 * cnt * sizeof(double));
+          if (rc == NBK_OK && (gsum || dgsum)) {
+            rc = reserve(c, c->d_out[2], 3 * cnt * sizeof(double));
+            if (rc == NBK_OK) rc = reserve(c, c->d_out[3], 3 * cnt * sizeof(double));
+            if (rc != NBK_OK) return rc;
+            SweepParams V = P;
+            V.out[0] = (double *)c->d_out[2].p;
+            V.out[1] = (double *)c->d_out[3].p;
+            rc = jerk ? run_op_peer<OpGradVDGradVB<1>>(c, V, c->stream, false)
+                      : run_op_peer<OpGradV>(c, V, c->stream, false);
+          }
+          if (rc != NBK_OK) return rc;
+          for (int k0 = 0; k0 < K && rc == NBK_OK;) {
+            const int kt = (K - k0 >= 3) ? 3 : 1;
+            SweepParams T = P;
+            for (int e = 0; e < ndev; ++e)
+              T.aux_shard[e] = (const double *)multi_dev(ctx, e)->d_aux.p + (size_t)k0 * dir;
+            T.aux = T.aux_shard[sl.d] - (size_t)sl.d * ctx->multi_shard_rows * PK;
+            T.aux_stride = (int)dir;
+            T.K = kt;
+            T.out[0] = (double *)c->d_out[0].p + (size_t)k0 * 3 * cnt;
+            T.out[1] = (double *)c->d_out[1].p + (size_t)k0 * 3 * cnt;
+            if (jerk) rc = kt == 3 ? run_tangent<3, true, true>(c, T, c->stream)
+                                   : run_tangent<1, true, true>(c, T, c->stream);
+            else rc = kt == 3 ? run_tangent<3, false, true>(c, T, c->stream)
+                              : run_tangent<1, false, true>(c, T, c->stream);
+            k0 += kt;
+          }
+          return rc;
+        },
+        [=](nbk_ctx *c, const Slice &sl) -> int {
+          const size_t cnt = (size_t)(sl.b - sl.a), off = 3 * (size_t)(sl.a - t0);
+          int rc = NBK_OK;
+          if (gsum) rc = download(c, gsum + off, c->d_out[2], 3 * cnt);
+          if (rc == NBK_OK && dgsum) rc = download(c, dgsum + off, c->d_out[3], 3 * cnt);
+          for (int k = 0; k < K && rc == NBK_OK; ++k) {  // caller's arrays are [K][3 ntg]
+            if (cudaMemcpyAsync(gsum_tan + (size_t)k * 3 * ntg + off,
+                                (const double *)c->d_out[0].p + (size_t)k * 3 * cnt,
+                                3 * cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+              rc = fail(c, NBK_ERR_CUDA, "cudaMemcpyAsync failed");
+            if (rc == NBK_OK && jerk &&
+                cudaMemcpyAsync(dgsum_tan + (size_t)k * 3 * ntg + off,
+                                (const double *)c->d_out[1].p + (size_t)k * 3 * cnt,
+                                3 * cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+              rc = fail(c, NBK_ERR_CUDA, "cudaMemcpyAsync failed");
+          }
+          return rc;
+        },
+        [=](nbk_ctx *c, int a, int b, int rows) -> int {
+          const int cnt = b - a;
+          int rc = reserve(c, c->d_aux, (size_t)K * rows * PK * sizeof(double));
+          if (rc == NBK_OK) rc = reserve(c, c->d_aux_in, (size_t)K * 3 * std::max(cnt, 1) * sizeof(double));
+          if (rc == NBK_OK && jerk)
+            rc = reserve(c, c->d_aux_in2, (size_t)K * 3 * std::max(cnt, 1) * sizeof(double));
+          for (int k = 0; k < K && rc == NBK_OK && cnt > 0; ++k) {
+            double *din = (double *)c->d_aux_in.p + (size_t)k * 3 * cnt;
+            double *din2 = jerk ? (double *)c->d_aux_in2.p + (size_t)k * 3 * cnt : nullptr;
+            if (cudaMemcpyAsync(din, dq + (size_t)k * n3 + 3 * (size_t)a, 3 * (size_t)cnt * sizeof(double),
+                                cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                (jerk && cudaMemcpyAsync(din2, dp + (size_t)k * n3 + 3 * (size_t)a,
+                                         3 * (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice,
+                                         c->stream) != cudaSuccess))
+              rc = fail(c, NBK_ERR_CUDA, "cudaMemcpyAsync failed");
+            if (rc == NBK_OK) {
+              pack_aux_kernel<<<(cnt + 255) / 256, 256, 0, c->stream>>>(
+                  cnt, (const double *)c->d_m.p, din, din2, 0,
+                  (double *)c->d_aux.p + (size_t)k * rows * PK);
+              c->launches++;
+            }
+          }
+          return rc;
+        });
+  }
   TRY(stage_bodies(ctx, n, m, q, jerk ? p : nullptr, 0));
   if (K > 0) {  // directions: upload, pack into aux[K][n][8]
     TRY(reserve(ctx, ctx->d_aux, (size_t)K * n * PK * sizeof(double)));

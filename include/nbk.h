@@ -56,7 +56,9 @@ int nbk_create(nbk_ctx **ctx, int device);
 /* Single-process multi-GPU context over ndev devices (devices[] = their ordinals, or NULL for
  * 0..ndev-1) - what a single OCaml process uses to drive the GPUs of one box.  It behaves like
  * a context on the first device, except that the host-buffer sweeps nbk_grad_v_dgrad_v_sum,
- * nbk_grad_v_sum, nbk_v_sum and nbk_energy shard their TARGETS over all the devices: every
+ * nbk_grad_v_sum, nbk_v_sum, nbk_energy, nbk_kick_sum and the tangent sums
+ * nbk_grad_v_dgrad_v_sum_tangent / nbk_grad_v_sum_tangent (BASELINE configs[4] from one process)
+ * shard their TARGETS over all the devices: every
  * device uploads and packs ITS OWN rows (the host->device copies go out over all PCIe links
  * side by side), sweeps its slice over all sources - reading the other devices' rows in place
  * over NVLink (peer access, the PEER sweep kernels; no broadcast) - and the slices are read

@@ -450,6 +450,24 @@ def test_virtual_multi_device_context_on_one_gpu(oracle, monkeypatch, ndev, thre
         assert rel_err(sub[0], ref[0]) <= TOL and rel_err(sub[1], ref[1]) <= TOL
         ke, pe = multi.energy(m, q, p, 0.0)
         assert abs(pe - oracle.total_potential_energy(m, q)) <= 1e-12 * abs(pe)
+        # the kick (bit-exact time-scale) and the tangent sums shard the same way
+        v = p / m[:, None]
+        dv1, tm1 = one.kick_sum(m, q, v, 1e-3, 1e-4)
+        dv2, tm2 = multi.kick_sum(m, q, v, 1e-3, 1e-4)
+        assert rel_err(dv2, dv1) <= 1e-13 and np.array_equal(tm1, tm2)
+        dv3, none = multi.kick_sum(m, q, v, 1e-3, 1e-4, want_tmin=False, targets=(500, 8000))
+        assert none is None and rel_err(dv3, dv1[500:8000]) <= 1e-13
+        rng = np.random.default_rng(7)
+        dq = rng.standard_normal((4, n, 3))
+        dp = rng.standard_normal((4, n, 3)) * m[None, :, None]
+        a4 = one.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, 1e-4)
+        b4 = multi.grad_v_dgrad_v_sum_tangent(m, q, p, dq, dp, 1e-4)
+        for x, y in zip(a4, b4):
+            assert rel_err(y, x) <= 1e-12
+        a1 = one.grad_v_sum_tangent(m, q, dq[:1], 1e-4, targets=(128, 8200), sources=(256, 9000))
+        b1 = multi.grad_v_sum_tangent(m, q, dq[:1], 1e-4, targets=(128, 8200), sources=(256, 9000))
+        for x, y in zip(a1, b1):
+            assert rel_err(y, x) <= 1e-12
         with pytest.raises(nbk.NbkError):
             multi.grad_v_dgrad_v_sum(m, q, p, 0.0, targets=(0, n + 1))
 
