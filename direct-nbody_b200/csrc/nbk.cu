@@ -69,8 +69,8 @@ struct nbk_ctx {
   unsigned long long peer_wait_ns = 20000000000ULL;  // nbk_set_peer_timeout / NBK_PEER_TIMEOUT_S
   std::string err;
   // device workspaces
-  DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_out[4],
-      d_scalar;
+  DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_tbest,
+      d_out[4], d_scalar;
   // resident bodies
   int resident_n = 0;
   DevBuf d_res_m, d_res_packed;
@@ -158,6 +158,11 @@ int check_ranges(nbk_ctx *ctx, int n, int t0, int t1, int s0, int s1) {
   return NBK_OK;
 }
 
+__global__ void fill_kernel(double *p, size_t n, double v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // ---- sweep launcher --------------------------------------------------------------------------
 template <class Op, int NT, int IPT, int MINB, int UNROLL, bool PEER = false> struct Launcher {
   static int occupancy(nbk_ctx *ctx, int *occ) {
@@ -194,6 +199,19 @@ template <class Op, int NT, int IPT, int MINB, int UNROLL, bool PEER = false> st
     G = (P.units + P.units_per_cta - 1) / P.units_per_cta;  // drop empty trailing CTAs
     TRY(reserve(ctx, ctx->d_partial, (size_t)2 * G * Op::NACC * TI * sizeof(double)));
     P.partial = (double *)ctx->d_partial.p;
+    if constexpr (has_tile_hook<Op>::value) {
+      // the runs of a target share their time-scale bound (OpKick::tile_end) unless every
+      // target's sources fit one run
+      P.tbest = nullptr;
+      if (P.units_per_cta < 4LL * P.n_jt && !getenv("NBK_KICK_NO_SHARED_BOUND")) {
+        TRY(reserve(ctx, ctx->d_tbest, (size_t)nt * sizeof(double)));
+        fill_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>((double *)ctx->d_tbest.p, (size_t)nt,
+                                                                  __builtin_inf());
+        CK(cudaGetLastError());
+        ctx->launches++;
+        P.tbest = (unsigned long long *)ctx->d_tbest.p;
+      }
+    }
     if (time_it) CK(cudaEventRecord(ctx->ev0, st));
     sweep_kernel<Op, NT, IPT, MINB, UNROLL, PEER>
         <<<(unsigned)G, NT, sweep_smem_bytes(naux_of<Op>::value), st>>>(P);
@@ -304,10 +322,6 @@ int run_tangent(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st) {
 }
 
 // ---- O(N) device helpers ---------------------------------------------------------------------
-__global__ void fill_kernel(double *p, size_t n, double v) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
 
 // Deterministic single-CTA sum of x[0..n) (fixed tree shape): Energy's final scalar.
 __global__ void __launch_bounds__(1024) sum_kernel(const double *__restrict__ x, int n,
@@ -875,7 +889,7 @@ void nbk_destroy(nbk_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->d_t,     &c->d_f,      &c->d_df,     &c->d_aux_in2,
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
-                    &c->d_aux,   &c->d_partial, &c->d_out[0], &c->d_out[1], &c->d_out[2],
+                    &c->d_aux,   &c->d_partial, &c->d_tbest, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                     &c->d_out[3], &c->d_scalar, &c->d_res_m,  &c->d_res_packed,
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout, &c->d_hgrid,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,

@@ -154,6 +154,10 @@ struct SweepParams {
   const unsigned long long *ready;
   unsigned long long epoch;
   unsigned long long wait_ns;  // how long a CTA waits for a peer's flag before trapping; 0 = forever
+  // OpKick<true>: per target (index i - t0), the smallest exact pair time-scale any CTA has found
+  // so far, as the bits of a non-negative double (integer order = numeric order); +inf at launch.
+  // NULL = not shared (each run of sources warms its filter up on its own).
+  unsigned long long *tbest;
 };
 
 // ---- pair operations -----------------------------------------------------------------------
@@ -334,7 +338,10 @@ struct OpV {
 // |z| <= 1.  State per target (acc[4]) = c; 0 (never "far") until a first exact value exists,
 // for eta <= 0 or NaN, or whenever T leaves [1e-100, 1e100].
 template <bool WITH_TSCALE> struct OpKick {
-  static constexpr int NACC = WITH_TSCALE ? 5 : 3;
+  // acc: [0..2] velocity sums; [3] the minimum exact time-scale this run has evaluated; [4] the
+  // filter constant c and [5] the bound T it was derived from: min([3], what other runs of the
+  // same target have published, SweepParams::tbest)
+  static constexpr int NACC = WITH_TSCALE ? 6 : 3;
   static constexpr int ND2 = WITH_TSCALE ? 4 : 2;
   struct Tgt {
     double x, y, z, vx, vy, vz, m;
@@ -362,6 +369,46 @@ template <bool WITH_TSCALE> struct OpKick {
     if (WITH_TSCALE) {
       acc[3] = __longlong_as_double(0x7ff0000000000000LL);
       acc[4] = 0.0;
+      acc[5] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+  }
+  // A new exact value for this target: the minimum, and the filter if it is the tightest bound.
+  __device__ __forceinline__ static void record(double *acc, double ts, double eta) {
+    if (acc[3] > ts) {  // NaN ts leaves acc[3] alone, leapfrog.ml:103
+      acc[3] = ts;
+      if (ts < acc[5]) {
+        acc[5] = ts;
+        acc[4] = filter_state(ts, eta);
+      }
+    }
+  }
+  // Between source tiles: the sources of a target are split into RUNS over several CTAs (stream-K,
+  // and one process per GPU shards them further), and every run would warm its filter up from
+  // +infinity on its own - with 128 (lane, target) pairs per warp the first ~128 (1 + ln(K / 128))
+  // of a run's K iterations take the exact branch: 0.4 ms per run, 25 % of an 8-GPU kick sweep.
+  // So the runs of a target SHARE their bound: each publishes its minimum (atomicMin on the bits)
+  // and adopts a smaller one.  Any published value is the exact time-scale of a real pair of this
+  // target, hence an upper bound of its final minimum: the filter stays a sufficient condition,
+  // and the run that holds the true minimum pair still evaluates it - the combined result is
+  // bit-identical, whatever the timing.
+  static constexpr int TILE_HOOK = 1;
+  template <int IPT>
+  __device__ __forceinline__ static void tile_end(double (&acc)[IPT][NACC], const int (&ig)[IPT],
+                                                  const SweepParams &P) {
+    if constexpr (WITH_TSCALE) {
+      if (P.tbest == nullptr) return;
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        if (ig[r] >= P.t1) continue;
+        unsigned long long *slot = P.tbest + (ig[r] - P.t0);
+        const double g = __longlong_as_double((long long)__ldcg(slot));
+        if (acc[r][3] < g) {
+          atomicMin(slot, (unsigned long long)__double_as_longlong(acc[r][3]));
+        } else if (g < acc[r][5]) {
+          acc[r][5] = g;
+          acc[r][4] = filter_state(g, P.eta);
+        }
+      }
     }
   }
   // The reference's exact pair time-scale (leapfrog.ml:80-104, unfused, correctly rounded).
@@ -415,11 +462,7 @@ template <bool WITH_TSCALE> struct OpKick {
       const bool far = far_pair(r2, y, vsq, t.m + b.y, acc[4]);
       const bool skip = CHECK ? self : false;
       if (!far && !skip) {
-        const double ts = exact_tscale(dx, dy, dz, ux, uy, uz, t.m, b.y, P.eta);
-        if (acc[3] > ts) {  // NaN ts leaves acc[3] alone, leapfrog.ml:103
-          acc[3] = ts;
-          acc[4] = filter_state(ts, P.eta);
-        }
+        record(acc, exact_tscale(dx, dy, dz, ux, uy, uz, t.m, b.y, P.eta), P.eta);
       }
     }
   }
@@ -501,11 +544,8 @@ template <bool WITH_TSCALE> struct OpKick {
           const bool self = CHECK ? (jg == ig[r]) : false;
           const bool far = (My[r] <= vsq[r]) && (cr2[r] > vsq[r]);
           if (!far && !self) {
-            const double ts = exact_tscale(dx[r], dy[r], dz[r], ux[r], uy[r], uz[r], t[r].m, b.y, P.eta);
-            if (acc[r][3] > ts) {
-              acc[r][3] = ts;
-              acc[r][4] = filter_state(ts, P.eta);
-            }
+            record(acc[r], exact_tscale(dx[r], dy[r], dz[r], ux[r], uy[r], uz[r], t[r].m, b.y, P.eta),
+                   P.eta);
           }
         }
       }
@@ -595,6 +635,11 @@ struct OpBinary {
 // share a register operand adjacent ("operand bandwidth").
 template <class Op, class = void> struct has_batched { static constexpr bool value = false; };
 template <class Op> struct has_batched<Op, decltype((void)Op::BATCHED)> {
+  static constexpr bool value = true;
+};
+
+template <class Op, class = void> struct has_tile_hook { static constexpr bool value = false; };
+template <class Op> struct has_tile_hook<Op, decltype((void)Op::TILE_HOOK)> {
   static constexpr bool value = true;
 };
 
@@ -947,6 +992,8 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
         Op::load(tg[r], P.packed + (size_t)ic * PK, P, ic);
         Op::zero(acc[r]);
       }
+      // a run that starts late adopts what the earlier runs of its targets already know
+      if constexpr (has_tile_hook<Op>::value) Op::template tile_end<IPT>(acc, ig, P);
     }
     // keep STAGES-1 tiles in flight: refill the stage tile k-1 just vacated
     if (tid == 0) {
@@ -973,6 +1020,12 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
 #pragma unroll UNROLL
       for (int jj = 0; jj < cnt; ++jj)
         pairs<Op, false, IPT>(tg, acc, sj + jj * (PK / 2), sa + jj * (PK / 2), j0 + jj, ig, P);
+    }
+    // exchange with the other runs of these targets: at every tile while a run is young (that is
+    // when its own bound is still loose), then every eighth tile (the loads cost a stall)
+    if constexpr (has_tile_hook<Op>::value) {
+      const int kseg = jt - seg_jt0;
+      if (kseg < 4 || (kseg & 7) == 7) Op::template tile_end<IPT>(acc, ig, P);
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[st]);
@@ -2996,7 +3049,7 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
         const int ul = tid / SPLIT, sl = tid - ul * SPLIT;
         const bool live = ul < nac;
         const int x = rank + NC * (u0 + ul);
-        double acc[5];
+        double acc[Op::NACC < 5 ? 5 : Op::NACC];
         Op::zero(acc);
         if (live) {
           typename Op::Tgt tg;
@@ -3004,6 +3057,7 @@ __global__ void __launch_bounds__(LFT_THREADS, 1) lf_tree_kernel(const LfTreePar
           if (TS) {
             acc[3] = dtm[x];  // infinity for an active slot (reset in stage 0)
             acc[4] = Op::filter_state(acc[3], SP.eta);
+            acc[5] = acc[3];
           }
           const int lo = x >= ibegin ? 0 : ibegin;
           for (int k = lo + sl; k < iend; k += SPLIT)

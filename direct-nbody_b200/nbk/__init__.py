@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libnbk.so")
+# NBK_LIBRARY: another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("NBK_LIBRARY") or os.path.join(os.path.dirname(_PKG), "lib", "libnbk.so")
 PACKED_DOUBLES = 8
 
 _d, _i, _f = C.c_double, C.c_int, C.c_float
