@@ -1016,6 +1016,15 @@ __global__ void __launch_bounds__(NT, MINB) sweep_kernel(const SweepParams P) {
 #pragma unroll 2
       for (int jj = 0; jj < cnt; ++jj)
         pairs<Op, true, IPT>(tg, acc, sj + jj * (PK / 2), sa + jj * (PK / 2), j0 + jj, ig, P);
+    } else if (has_tile_hook<Op>::value && jt == seg_jt0) {
+      // the first tile of a run: exchange every 16 sources (see Op::tile_end)
+#pragma unroll 1
+      for (int jj = 0; jj < cnt; ++jj) {
+        pairs<Op, false, IPT>(tg, acc, sj + jj * (PK / 2), sa + jj * (PK / 2), j0 + jj, ig, P);
+        if constexpr (has_tile_hook<Op>::value) {
+          if ((jj & 15) == 15) Op::template tile_end<IPT>(acc, ig, P);
+        }
+      }
     } else {
 #pragma unroll UNROLL
       for (int jj = 0; jj < cnt; ++jj)
