@@ -2020,6 +2020,36 @@ int nbk_lf_permute(nbk_ctx *ctx, int count, const int *perm) {
   return NBK_OK;
 }
 
+int nbk_lf_sort_sub(nbk_ctx *ctx, int iend, int *perm) {
+  NEED_LF();
+  if (iend < 0 || iend > ctx->lf_n || (iend > 0 && !perm))
+    return fail(ctx, NBK_ERR_ARG, "nbk_lf_sort_sub: bad arguments");
+  if (iend == 0) return NBK_OK;
+  TRY(reserve(ctx, ctx->d_aux_in, (size_t)iend * sizeof(int)));
+  lf_rank_kernel<<<(iend + 255) / 256, 256, 0, ctx->stream>>>((const double *)ctx->d_lf_dtmax.p, iend,
+                                                             (int *)ctx->d_aux_in.p);
+  CK(cudaGetLastError());
+  const size_t elems = (size_t)iend * PK;
+  lf_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ctx->stream>>>(
+      (const double *)ctx->d_lf_packed.p, (double *)ctx->d_lf_packed2.p,
+      (const double *)ctx->d_lf_dtmax.p, (double *)ctx->d_lf_dtmax2.p, (const int *)ctx->d_aux_in.p,
+      iend);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ctx->d_lf_packed.p, ctx->d_lf_packed2.p, elems * sizeof(double),
+                     cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_lf_dtmax.p, ctx->d_lf_dtmax2.p, (size_t)iend * sizeof(double),
+                     cudaMemcpyDeviceToDevice, ctx->stream));
+  // the permutation goes home through the pinned staging buffer (shared with nbk_lf_permute)
+  int *stage = reinterpret_cast<int *>(ctx->h_lf_stage + ctx->h_lf_cap);
+  CK(cudaEventSynchronize(ctx->ev_lf));
+  CK(cudaMemcpyAsync(stage, ctx->d_aux_in.p, (size_t)iend * sizeof(int), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  TRY(sync(ctx));
+  memcpy(perm, stage, (size_t)iend * sizeof(int));
+  return NBK_OK;
+}
+
 int nbk_lf_begin(nbk_ctx *ctx, int ibegin, int iend) {
   NEED_LF();
   if (ibegin < 0 || iend < ibegin || iend > ctx->lf_n)

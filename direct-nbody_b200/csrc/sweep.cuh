@@ -2862,6 +2862,44 @@ __global__ void lf_gather_kernel(const double *__restrict__ src, double *__restr
   dst[e] = src[(size_t)perm[row] * PK + c];
   if (c == 0) ddst[row] = dsrc[perm[row]];
 }
+// sort_sub (leapfrog.ml:106-111) on the device: Array.fast_sort (stable) of the prefix by
+// `compare b1.dt_max b2.dt_max` - OCaml's polymorphic compare on floats: nan equals nan and sorts
+// below everything else, -0.0 equals 0.0.  Rank by counting: new position of row i =
+// #{j : key_j < key_i} + #{j < i : key_j = key_i}; iend^2 comparisons, one thread per row, keys
+// staged through shared memory.  perm[rank] = i (new row s = old row perm[s]).
+__device__ __forceinline__ bool lf_key_lt(double a, double b) {
+  if (a < b) return true;
+  if (a >= b) return false;        // a > b or a == b
+  return (a != a) && (b == b);     // a comparison with nan: nan < anything that is not nan
+}
+__device__ __forceinline__ bool lf_key_eq(double a, double b) {
+  return a == b || ((a != a) && (b != b));
+}
+__global__ void __launch_bounds__(256) lf_rank_kernel(const double *__restrict__ key, int iend,
+                                                      int *__restrict__ perm) {
+  __shared__ double tile[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const double ki = i < iend ? key[i] : 0.0;
+  int rank = 0;
+  for (int j0 = 0; j0 < iend; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < iend ? key[j] : 0.0;
+    __syncthreads();
+    const int cnt = min(256, iend - j0);
+    if (i < iend) {
+      if (j0 + cnt <= i) {          // every j of this tile precedes i: ties count
+        for (int t = 0; t < cnt; ++t) rank += (lf_key_lt(tile[t], ki) || lf_key_eq(tile[t], ki)) ? 1 : 0;
+      } else if (j0 > i) {          // every j follows i: strictly smaller keys only
+        for (int t = 0; t < cnt; ++t) rank += lf_key_lt(tile[t], ki) ? 1 : 0;
+      } else {
+        for (int t = 0; t < cnt; ++t)
+          rank += (lf_key_lt(tile[t], ki) || (j0 + t < i && lf_key_eq(tile[t], ki))) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+  if (i < iend) perm[rank] = i;
+}
 // drift dt (leapfrog.ml:64-68) on rows [i0, i1)
 __global__ void lf_drift_kernel(double *__restrict__ packed, int i0, int i1, double dt) {
   int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;

@@ -26,6 +26,7 @@ using namespace nbh;
 //    launch (nbk_lf_advance_subsystem; agrees with 1 to rounding)
 int g_leapfrog_resident = 2;
 int g_leapfrog_tree_max = 0;  // 0: automatic
+int g_leapfrog_device_sort_min = 512;  // resident sort_sub of at least this many rows: on the device
 
 int lf_tree_max() {
   if (g_leapfrog_resident < 2) return 0;
@@ -134,6 +135,17 @@ struct Leap {
       return 0;
     }
     perm.resize(iend);
+    if (iend >= g_leapfrog_device_sort_min) {
+      // wide prefixes: the device ranks its own dt_max (the host's copy is the same values) and
+      // moves the rows; only the permutation comes back
+      NBH_TRY(ck(ctx, nbk_lf_sort_sub(ctx, iend, perm.data())));
+      bool identity = true;
+      for (int i = 0; i < iend && identity; ++i) identity = perm[i] == i;
+      if (identity) return 0;
+      std::vector<LBody> tmp(bs.begin(), bs.begin() + iend);
+      for (int i = 0; i < iend; ++i) bs[i] = tmp[perm[i]];
+      return 0;
+    }
     for (int i = 0; i < iend; ++i) perm[i] = i;
     std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
       return ocaml_compare(bs[a].dt_max, bs[b].dt_max) < 0;
@@ -287,6 +299,7 @@ extern "C" {
 
 void nbh_set_leapfrog_resident(int mode) { g_leapfrog_resident = mode; }
 void nbh_set_leapfrog_tree_max(int bodies) { g_leapfrog_tree_max = bodies; }
+void nbh_set_leapfrog_device_sort_min(int rows) { g_leapfrog_device_sort_min = rows; }
 
 int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max, double *m,
                          double *q, double *v, double dt, double eta, long *nkicks) {

@@ -73,6 +73,9 @@ int nbh_leapfrog_advance(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max
  * 0: host-buffer path, every step through the host recursion. */
 void nbh_set_leapfrog_resident(int mode);
 void nbh_set_leapfrog_tree_max(int bodies); /* 0: automatic */
+/* resident modes: sort_sub of at least this many rows runs on the device (nbk_lf_sort_sub);
+ * default 512; a huge value keeps every sort on the host */
+void nbh_set_leapfrog_device_sort_min(int rows);
 int nbh_leapfrog_advance_const_dt(nbk_ctx *ctx, int n, int *id, double *t, double *dt_max,
                                   double *m, double *q, double *v, double dt, int nsteps);
 

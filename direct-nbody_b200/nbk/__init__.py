@@ -92,6 +92,7 @@ SYMBOLS = {
     "nbk_lf_upload": (_i, [_vp, _i, _pd, _pd, _pd, _pd]),
     "nbk_lf_download": (_i, [_vp, _pd, _pd, _pd]),
     "nbk_lf_permute": (_i, [_vp, _i, C.POINTER(_i)]),
+    "nbk_lf_sort_sub": (_i, [_vp, _i, C.POINTER(_i)]),
     "nbk_lf_begin": (_i, [_vp, _i, _i]),
     "nbk_lf_drift": (_i, [_vp, _i, _i, _d]),
     "nbk_lf_kick_block": (_i, [_vp, _i, _i, _d, _d, _i, _i, _d, _pd]),

@@ -281,6 +281,11 @@ int nbk_lf_upload(nbk_ctx *ctx, int n, const double *dt_max, const double *m, co
 int nbk_lf_download(nbk_ctx *ctx, double *dt_max, double *q, double *v);
 /* sort_sub (leapfrog.ml:106-111): new rows [0,count) := old rows perm[0..count) */
 int nbk_lf_permute(nbk_ctx *ctx, int count, const int *perm);
+/* sort_sub bs iend (leapfrog.ml:106-111) computed ON THE DEVICE from the resident dt_max: the
+ * stable sort of rows [0, iend) by OCaml's `compare` on dt_max (nan lowest, nan = nan), rows and
+ * dt_max moved accordingly; perm[iend]: out, new row s = old row perm[s] (for what the caller
+ * keeps per row).  Replaces a host sort of up to n keys plus nbk_lf_permute. */
+int nbk_lf_sort_sub(nbk_ctx *ctx, int iend, int *perm);
 /* dt_max := infinity on [ibegin, iend)   (leapfrog.ml:125-127).  nbk_lf_kick_block performs
  * this reset itself for its active block - nothing reads those values in between - so a caller
  * following advance_subsystem need not call it. */

@@ -90,14 +90,12 @@ let rec advance_subsystem_resident dt eta bs iend =
     for i = ibegin to iend - 1 do bs.(i).t <- bs.(i).t +. dt2 done;
     for i = 0 to iend - 1 do bs.(i).dt_max <- dtm.{i} done;
     advance_subsystem_resident dt2 eta bs ibegin;
-    (* sort_sub (leapfrog.ml:106-111): stable sort of the prefix by dt_max, same moves on the device *)
-    let idx = Array.init iend (fun i -> i) in
-    let keyed = Array.map (fun i -> (bs.(i).dt_max, i)) idx in
-    Array.stable_sort (fun (a, _) (b, _) -> compare a b) keyed;
+    (* sort_sub (leapfrog.ml:106-111): the device ranks its own dt_max (stable, OCaml's compare)
+       and moves the rows; the records here follow the permutation it returns *)
     let perm = Nbk.ivec iend in
+    Nbk.lf_sort_sub c perm;
     let old = Array.sub bs 0 iend in
-    Array.iteri (fun s (_, i) -> perm.{s} <- Int32.of_int i; bs.(s) <- old.(i)) keyed;
-    Nbk.lf_permute c perm
+    for s = 0 to iend - 1 do bs.(s) <- old.(Int32.to_int perm.{s}) done
   end
 
 (* Leapfrog.advance (leapfrog.ml:144-158) with resident bodies *)

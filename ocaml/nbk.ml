@@ -135,6 +135,8 @@ external resident_leapfrog_steps : ctx -> float -> int -> vec -> vec -> unit
 
 (* Leapfrog per-phase calls on the resident array: the recursion above lf_subsystem_max bodies *)
 external lf_permute : ctx -> ivec -> unit = "nbk_ml_lf_permute"
+(* [lf_sort_sub ctx perm]: sort_sub bs (dim perm) on the device; perm: out, new row s = old row perm.{s} *)
+external lf_sort_sub : ctx -> ivec -> unit = "nbk_ml_lf_sort_sub"
 external lf_begin : ctx -> int -> int -> unit = "nbk_ml_lf_begin"
 external lf_drift : ctx -> int -> int -> float -> unit = "nbk_ml_lf_drift"
 (* [lf_kick_block ctx iend ibegin eta dt with_tscale drift_after dt_max] *)

@@ -556,6 +556,13 @@ CAMLprim value nbk_ml_lf_permute(value ctx, value perm) {
   check(Ctx_val(ctx), nbk_lf_permute(Ctx_val(ctx), DIM0(perm), I32(perm)));
   CAMLreturn(Val_unit);
 }
+/* external lf_sort_sub : ctx -> perm:(int32) -> unit   sort_sub bs iend on the device, iend = dim perm;
+ * perm receives new row s = old row perm.{s} */
+CAMLprim value nbk_ml_lf_sort_sub(value ctx, value perm) {
+  CAMLparam2(ctx, perm);
+  check(Ctx_val(ctx), nbk_lf_sort_sub(Ctx_val(ctx), DIM0(perm), I32(perm)));
+  CAMLreturn(Val_unit);
+}
 /* external lf_begin : ctx -> ibegin:int -> iend:int -> unit   leapfrog.ml:125-127 */
 CAMLprim value nbk_ml_lf_begin(value ctx, value ibegin, value iend) {
   CAMLparam3(ctx, ibegin, iend);
