@@ -2026,9 +2026,17 @@ int nbk_lf_sort_sub(nbk_ctx *ctx, int iend, int *perm) {
     return fail(ctx, NBK_ERR_ARG, "nbk_lf_sort_sub: bad arguments");
   if (iend == 0) return NBK_OK;
   TRY(reserve(ctx, ctx->d_aux_in, (size_t)iend * sizeof(int)));
-  lf_rank_kernel<<<(iend + 255) / 256, 256, 0, ctx->stream>>>((const double *)ctx->d_lf_dtmax.p, iend,
-                                                             (int *)ctx->d_aux_in.p);
+  TRY(reserve(ctx, ctx->d_aux_in2, (size_t)iend * (sizeof(unsigned long long) + sizeof(int))));
+  unsigned long long *ukey = (unsigned long long *)ctx->d_aux_in2.p;
+  int *rank = (int *)(ukey + iend);
+  lf_sort_key_kernel<<<(iend + 255) / 256, 256, 0, ctx->stream>>>((const double *)ctx->d_lf_dtmax.p,
+                                                                 iend, ukey, rank);
+  dim3 rgrid((iend + 255) / 256, (iend + LFS_CHUNK - 1) / LFS_CHUNK);
+  lf_rank_kernel<<<rgrid, 256, 0, ctx->stream>>>(ukey, iend, rank);
+  lf_scatter_perm_kernel<<<(iend + 255) / 256, 256, 0, ctx->stream>>>(rank, iend,
+                                                                     (int *)ctx->d_aux_in.p);
   CK(cudaGetLastError());
+  ctx->launches += 2;
   const size_t elems = (size_t)iend * PK;
   lf_gather_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, ctx->stream>>>(
       (const double *)ctx->d_lf_packed.p, (double *)ctx->d_lf_packed2.p,

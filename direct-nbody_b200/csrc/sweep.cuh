@@ -2864,41 +2864,51 @@ __global__ void lf_gather_kernel(const double *__restrict__ src, double *__restr
 }
 // sort_sub (leapfrog.ml:106-111) on the device: Array.fast_sort (stable) of the prefix by
 // `compare b1.dt_max b2.dt_max` - OCaml's polymorphic compare on floats: nan equals nan and sorts
-// below everything else, -0.0 equals 0.0.  Rank by counting: new position of row i =
-// #{j : key_j < key_i} + #{j < i : key_j = key_i}; iend^2 comparisons, one thread per row, keys
-// staged through shared memory.  perm[rank] = i (new row s = old row perm[s]).
-__device__ __forceinline__ bool lf_key_lt(double a, double b) {
-  if (a < b) return true;
-  if (a >= b) return false;        // a > b or a == b
-  return (a != a) && (b == b);     // a comparison with nan: nan < anything that is not nan
-}
-__device__ __forceinline__ bool lf_key_eq(double a, double b) {
-  return a == b || ((a != a) && (b != b));
-}
-__global__ void __launch_bounds__(256) lf_rank_kernel(const double *__restrict__ key, int iend,
-                                                      int *__restrict__ perm) {
-  __shared__ double tile[256];
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  const double ki = i < iend ? key[i] : 0.0;
-  int rank = 0;
-  for (int j0 = 0; j0 < iend; j0 += 256) {
-    const int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = j < iend ? key[j] : 0.0;
-    __syncthreads();
-    const int cnt = min(256, iend - j0);
-    if (i < iend) {
-      if (j0 + cnt <= i) {          // every j of this tile precedes i: ties count
-        for (int t = 0; t < cnt; ++t) rank += (lf_key_lt(tile[t], ki) || lf_key_eq(tile[t], ki)) ? 1 : 0;
-      } else if (j0 > i) {          // every j follows i: strictly smaller keys only
-        for (int t = 0; t < cnt; ++t) rank += lf_key_lt(tile[t], ki) ? 1 : 0;
-      } else {
-        for (int t = 0; t < cnt; ++t)
-          rank += (lf_key_lt(tile[t], ki) || (j0 + t < i && lf_key_eq(tile[t], ki))) ? 1 : 0;
-      }
-    }
-    __syncthreads();
+// below everything else, -0.0 equals 0.0.  Keys are first mapped to unsigned integers in that
+// order (lf_sort_key_kernel); then rank by counting: new position of row i =
+// #{j < i : key_j <= key_i} + #{j > i : key_j < key_i} - iend^2 integer comparisons spread over a
+// 2-D grid (256 rows x a chunk of the keys per CTA, chunk staged in shared memory, partial counts
+// added atomically: integers, so the result does not depend on the order); lf_scatter_perm_kernel
+// then writes perm[rank] = i (new row s = old row perm[s]).
+__global__ void lf_sort_key_kernel(const double *__restrict__ key, int iend,
+                                   unsigned long long *__restrict__ ukey, int *__restrict__ rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= iend) return;
+  const double k = key[i];
+  unsigned long long u;
+  if (k != k) u = 0ULL;                                    // nan: below everything, all equal
+  else if (k == 0.0) u = 0x8000000000000000ULL;            // -0.0 = 0.0
+  else {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(k);
+    u = (b >> 63) ? ~b : (b | 0x8000000000000000ULL);     // negatives reversed, positives above
+    if (u == 0ULL) u = 1ULL;                               // (unreachable: ~b = 0 needs b = all ones = nan)
   }
-  if (i < iend) perm[rank] = i;
+  ukey[i] = u;
+  rank[i] = 0;
+}
+constexpr int LFS_CHUNK = 2048;  // keys per CTA in the j direction (16 KB of shared memory)
+__global__ void __launch_bounds__(256) lf_rank_kernel(const unsigned long long *__restrict__ ukey,
+                                                      int iend, int *__restrict__ rank) {
+  __shared__ unsigned long long tile[LFS_CHUNK];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int j0 = blockIdx.y * LFS_CHUNK, cnt = min(LFS_CHUNK, iend - j0);
+  for (int t = threadIdx.x; t < cnt; t += 256) tile[t] = ukey[j0 + t];
+  __syncthreads();
+  if (i >= iend) return;
+  const unsigned long long ki = ukey[i];
+  int r = 0;
+  // j < i: ties count (stable); j > i: strictly smaller only; j == i contributes nothing
+  const int before = min(max(i - j0, 0), cnt);       // tile entries with j < i
+  const int after0 = min(max(i + 1 - j0, 0), cnt);   // first tile entry with j > i
+#pragma unroll 4
+  for (int t = 0; t < before; ++t) r += tile[t] <= ki ? 1 : 0;
+#pragma unroll 4
+  for (int t = after0; t < cnt; ++t) r += tile[t] < ki ? 1 : 0;
+  if (r) atomicAdd(rank + i, r);
+}
+__global__ void lf_scatter_perm_kernel(const int *__restrict__ rank, int iend, int *__restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < iend) perm[rank[i]] = i;
 }
 // drift dt (leapfrog.ml:64-68) on rows [i0, i1)
 __global__ void lf_drift_kernel(double *__restrict__ packed, int i0, int i1, double dt) {

@@ -79,6 +79,7 @@ struct Leap {
   std::vector<LBody> bs;
   std::vector<double> m, q, v, dv, tm;
   std::vector<int> perm;
+  std::vector<char> small;
   long nkicks = 0;
   // resident: positions and velocities live on the device in bs order (nbk_lf_*); the host keeps
   // what the recursion needs (id, t, dt_max, m) and bs[i].q / .v are stale until fetch().
@@ -142,8 +143,22 @@ struct Leap {
       bool identity = true;
       for (int i = 0; i < iend && identity; ++i) identity = perm[i] == i;
       if (identity) return 0;
-      std::vector<LBody> tmp(bs.begin(), bs.begin() + iend);
-      for (int i = 0; i < iend; ++i) bs[i] = tmp[perm[i]];
+      // resident: q and v of the host records are stale until fetch(); move what the recursion
+      // keeps per row (id, t, dt_max, m) only
+      struct Small {
+        int id;
+        double t, dt_max, m;
+      };
+      small.resize(iend * sizeof(Small));
+      Small *sm = reinterpret_cast<Small *>(small.data());
+      for (int i = 0; i < iend; ++i) sm[i] = {bs[i].id, bs[i].t, bs[i].dt_max, bs[i].m};
+      for (int i = 0; i < iend; ++i) {
+        const Small &o = sm[perm[i]];
+        bs[i].id = o.id;
+        bs[i].t = o.t;
+        bs[i].dt_max = o.dt_max;
+        bs[i].m = o.m;
+      }
       return 0;
     }
     for (int i = 0; i < iend; ++i) perm[i] = i;
