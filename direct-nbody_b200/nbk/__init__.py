@@ -443,6 +443,22 @@ class Context:
         return q, v
 
     # -------------------------------------------------------------- resident Hermite state
+    # -------------------------------------------------------------- resident Leapfrog.b array
+    def lf_upload(self, dt_max, m, q, v):
+        dt_max, m, q, v = _arr(dt_max), _arr(m), _arr(q), _arr(v)
+        self._ck(self._lib.nbk_lf_upload(self._h, len(m), _p(dt_max), _p(m), _p(q), _p(v)))
+
+    def lf_download(self, n):
+        dt_max, q, v = np.empty(n), np.empty((n, 3)), np.empty((n, 3))
+        self._ck(self._lib.nbk_lf_download(self._h, _p(dt_max), _p(q), _p(v)))
+        return dt_max, q, v
+
+    def lf_sort_sub(self, iend):
+        """sort_sub bs iend (leapfrog.ml:106-111) on the device -> perm (new row s = old row perm[s])."""
+        perm = np.empty(max(iend, 1), dtype=np.int32)
+        self._ck(self._lib.nbk_lf_sort_sub(self._h, iend, perm.ctypes.data_as(C.POINTER(_i))))
+        return perm[:iend]
+
     def hermite_upload(self, t, m, q, p, f, df, h=None):
         t, m, q, p, f, df = (_arr(a) for a in (t, m, q, p, f, df))
         h = None if h is None else _arr(h)

@@ -196,6 +196,40 @@ def test_leapfrog_block_recursion_on_device(ctx, oracle, n, span, eta, tree_max)
     assert np.array_equal(a.q, a2.q) and np.array_equal(a.v, a2.v) and np.array_equal(a.dt_max, a2.dt_max)
 
 
+@pytest.mark.parametrize("n,iend", [(1, 1), (300, 300), (5000, 4097), (20000, 20000)])
+def test_leapfrog_sort_sub_on_device_is_ocamls_stable_sort(ctx, n, iend):
+    """nbk_lf_sort_sub against Array.fast_sort (stable) with OCaml's polymorphic compare on floats
+    (leapfrog.ml:106-111): nan below everything and equal to itself, -0.0 = 0.0, +inf on top, many
+    ties (dt_max = infinity is what a freshly reset block holds)."""
+    rng = np.random.default_rng(n + iend)
+    key = rng.choice([np.inf, -np.inf, np.nan, 0.0, -0.0, 1.0, 2.0 ** -30, -3.5], size=n)
+    rnd = rng.random(n) < 0.5
+    key[rnd] = 10.0 ** rng.uniform(-12, 3, int(rnd.sum()))
+    m = rng.uniform(0.5, 2.0, n)
+    q, v = rng.standard_normal((n, 3)), rng.standard_normal((n, 3))
+    ctx.lf_upload(key, m, q, v)
+    perm = ctx.lf_sort_sub(iend)
+    # the reference order: stable sort with cmp(x, y) = nan-lowest total order
+    import functools
+
+    def ocaml_compare(i, j):
+        x, y = key[i], key[j]
+        if x < y:
+            return -1
+        if x > y:
+            return 1
+        if x == y:
+            return 0
+        xn, yn = np.isnan(x), np.isnan(y)
+        return 0 if (xn and yn) else (-1 if xn else 1)
+    want = sorted(range(iend), key=functools.cmp_to_key(ocaml_compare))  # sorted() is stable
+    assert list(perm) == want
+    dt2, q2, v2 = ctx.lf_download(n)
+    full = np.concatenate([perm, np.arange(iend, n)])
+    assert np.array_equal(dt2.view(np.uint64), key[full].view(np.uint64))   # rows beyond iend untouched
+    assert np.array_equal(q2, q[full]) and np.array_equal(v2, v[full])
+
+
 def test_leapfrog_adaptive_energy_error_beside_oracle(ctx, oracle):
     """Leapfrog.advance with block time steps (leapfrog.ml:119-158) on the GPU path beside the
     oracle's sequential-kick run of the same bodies: same elapsed time, energy errors of the same
