@@ -539,14 +539,32 @@ template <bool WITH_TSCALE> struct OpKick {
         acc[r][2] = fma(w, dz[r], acc[r][2]);
       }
       if (!allfar) {
+        // Which of this lane's targets need the exact sequence; then one exact evaluation per
+        // trip of a lane-local loop, each lane working on ITS next target.  The warp makes as
+        // many trips as its busiest lane has needs - usually one - where a loop over r in
+        // lockstep made one trip for every r that ANY lane needed (four, while a run is young).
+        unsigned need = 0;
 #pragma unroll
         for (int r = 0; r < IPT; ++r) {
           const bool self = CHECK ? (jg == ig[r]) : false;
           const bool far = (My[r] <= vsq[r]) && (cr2[r] > vsq[r]);
-          if (!far && !self) {
-            record(acc[r], exact_tscale(dx[r], dy[r], dz[r], ux[r], uy[r], uz[r], t[r].m, b.y, P.eta),
-                   P.eta);
-          }
+          if (!far && !self) need |= 1u << r;
+        }
+        while (need) {
+          const int r = __ffs(need) - 1;
+          need &= need - 1;
+          double ex = dx[0], ey = dy[0], ez = dz[0], fx = ux[0], fy = uy[0], fz = uz[0], mi = t[0].m;
+#pragma unroll
+          for (int rr = 1; rr < IPT; ++rr)
+            if (rr == r) {
+              ex = dx[rr], ey = dy[rr], ez = dz[rr];
+              fx = ux[rr], fy = uy[rr], fz = uz[rr];
+              mi = t[rr].m;
+            }
+          const double ts = exact_tscale(ex, ey, ez, fx, fy, fz, mi, b.y, P.eta);
+#pragma unroll
+          for (int rr = 0; rr < IPT; ++rr)
+            if (rr == r) record(acc[rr], ts, P.eta);
         }
       }
     }
