@@ -633,6 +633,75 @@ struct OpBinary {
     }
     if (e < P.dt) acc[2] += 1.0;
   }
+  // One source against the IPT targets of a thread, with a FILTER in front of the exact sequence
+  // (2 IEEE divisions + 1 square root per pair, which made the scan 4x slower than the acc+jerk
+  // sweep).  A pair matters only if e < thr (it is counted) or e <= the running minimum (it may
+  // become the partner); with T = max(thr, emin), M = m_i + m_j > 0, y = 1/sqrt(r^2 + eps2):
+  //   e > T  <=>  m_i m_j (v^2/2 - M y) > T M,
+  // evaluated by fast arithmetic (FMA, rsqrt with one third-order step) with a margin of
+  // 1e-13 x the sum of the magnitudes of the three terms - 100x their rounding error - so a pair
+  // that is dismissed is certainly above T, and ties, NaN and non-positive masses take the exact
+  // path.  Counts, minima and partners stay bit-exact.  One branch per source for the thread's
+  // targets; inside it every lane loops over its own needs (as OpKick).
+  static constexpr int BATCHED = 1;
+  template <bool CHECK, int IPT>
+  __device__ __forceinline__ static void pairs(const Tgt (&t)[IPT], double (&acc)[IPT][NACC],
+                                               const double2 *sj, int jg, const int (&ig)[IPT],
+                                               const SweepParams &P) {
+    const double2 a = sj[0], b = sj[1], c = sj[2], d = sj[3];
+    const double mj = b.y;
+    double y[IPT], v2[IPT];
+    unsigned need = 0;
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const double dx = a.x - t[r].x, dy = a.y - t[r].y, dz = b.x - t[r].z;
+      double r2 = fma(dx, dx, P.eps2);
+      r2 = fma(dy, dy, r2);
+      r2 = fma(dz, dz, r2);
+      const bool self = CHECK ? (jg == ig[r]) : false;
+      if (CHECK) r2 = self ? 1.0 : r2;
+      y[r] = rsqrt_nr(r2);
+      const double ux = c.x - t[r].vx, uy = c.y - t[r].vy, uz = d.x - t[r].vz;
+      v2[r] = fma(uz, uz, fma(uy, uy, ux * ux));
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const bool self = CHECK ? (jg == ig[r]) : false;
+      const double M = t[r].m + mj, mm = t[r].m * mj;
+      const double T = fmax(P.dt, acc[r][0]);  // thr or the running minimum, whichever is larger
+      const double A = (0.5 * mm) * v2[r], B = mm * (M * y[r]), C = T * M;
+      const double lhs = (A - B) - C, mag = (A + B) + fabs(C);
+      const bool far = (fma(-1e-13, mag, lhs) > 0.0) & (mj > 0.0) & (t[r].m > 0.0);
+      if (!far && !self) need |= 1u << r;
+    }
+    while (need) {
+      const int r = __ffs(need) - 1;
+      need &= need - 1;
+      Tgt tt = t[0];
+#pragma unroll
+      for (int rr = 1; rr < IPT; ++rr)
+        if (rr == r) tt = t[rr];
+      double one[NACC] = {__longlong_as_double(0x7ff0000000000000LL), -1.0, 0.0};
+      exact_pair(tt, one, sj, P);
+#pragma unroll
+      for (int rr = 0; rr < IPT; ++rr)
+        if (rr == r) {
+          if (one[0] < acc[rr][0] || (one[0] == acc[rr][0] && one[1] < acc[rr][1])) {
+            acc[rr][0] = one[0];
+            acc[rr][1] = one[1];
+          }
+          acc[rr][2] += one[2];
+        }
+    }
+  }
+  // the exact pair of pair<>() out of line: acc = {e, source index, e < thr ? 1 : 0}
+  __device__ __noinline__ static void exact_pair(const Tgt &t, double *one, const double2 *sj,
+                                                 const SweepParams &P) {
+    one[0] = __longlong_as_double(0x7ff0000000000000LL);
+    one[1] = -1.0;
+    one[2] = 0.0;
+    pair<false>(t, one, sj, nullptr, false, P);
+  }
   __device__ __forceinline__ static void combine(double *a, const double *b) {
     if (b[0] < a[0] || (b[0] == a[0] && b[1] >= 0.0 && (a[1] < 0.0 || b[1] < a[1]))) {
       a[0] = b[0];

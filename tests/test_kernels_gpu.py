@@ -425,6 +425,48 @@ def test_binaries_scan_and_list_bit_exact(ctx, oracle, n, thr):
     assert np.all((p2 >= 0) & (p2 < 200)) and np.all(p2 != np.arange(10, 13))
 
 
+@pytest.mark.parametrize("case", ["plummer", "ties", "odd_masses", "softened"])
+@pytest.mark.parametrize("thr", [0.0, -2e-4, float("inf")])
+def test_binary_scan_every_target_bit_exact(ctx, oracle, case, thr):
+    """The filter in front of the exact binary energy must change nothing: per target the minimum
+    energy, its partner (lowest index on ties) and the count below the threshold, bit for bit
+    against ALL pair energies from the oracle's loop - with exact ties (mirrored bodies), zero and
+    negative masses (no filter there) and softening."""
+    n = 700
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 31))
+    eps2 = 0.0
+    if case == "ties":      # the second half mirrors the first: e(i, j) = e(i', j') exactly
+        h = n // 2
+        q[h:2 * h] = -q[:h]
+        p[h:2 * h] = -p[:h]
+        m[h:2 * h] = m[:h]
+    elif case == "odd_masses":
+        m[5] = 0.0
+        m[17] = -m[17]
+        p[17] = -p[17]
+        m[40:60] *= 1e6
+        p[40:60] *= 1e6
+    elif case == "softened":
+        eps2 = 1e-4
+    oi, oj, oe = oracle.binaries(m, q, p, eps2, float("inf"), max_pairs=n * n)  # every finite pair energy
+    emin_ref = np.full(n, np.inf)
+    part_ref = np.full(n, -1.0)
+    cnt_ref = np.zeros(n)
+    for a, b in ((oi, oj), (oj, oi)):           # each pair seen from both ends
+        order = np.lexsort((b, oe))             # by energy, then partner index
+        first = {}
+        for k in order:
+            first.setdefault(int(a[k]), k)
+        for i, k in first.items():
+            if oe[k] < emin_ref[i] or (oe[k] == emin_ref[i] and b[k] < part_ref[i]):
+                emin_ref[i], part_ref[i] = oe[k], b[k]
+        np.add.at(cnt_ref, a[oe < thr], 1.0)
+    emin, partner, count = ctx.binary_scan(m, q, p, eps2, thr)
+    assert np.array_equal(emin.view(np.uint64), emin_ref.view(np.uint64))
+    assert np.array_equal(partner, part_ref.astype(partner.dtype))
+    assert np.array_equal(count, cnt_ref.astype(count.dtype))
+
+
 def test_single_process_multi_gpu_context(oracle):
     """nbk_create_multi: one process, several GPUs, targets sharded by the library.  Results
     agree with the single-GPU context to rounding (a target's sources are cut into runs at
