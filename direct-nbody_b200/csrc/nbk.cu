@@ -680,11 +680,11 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
   TRY(multi_plan(ctx, t0, t1, sl));
   std::vector<int> rcs(ndev, NBK_OK);
   if (ctx->pool) ctx->pool->nparticipants = ndev;
-  auto per_device = [&](int d) {
+  // phase 1: device d uploads and packs its own rows, then records "rows packed"
+  auto pack_rows = [&](int d) {
     nbk_ctx *c = multi_dev(ctx, d);
     int rc = NBK_OK;
     if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
-    // phase 1: this device's rows
     const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
     if (rc == NBK_OK) rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
     if (rc == NBK_OK && cnt > 0) {
@@ -700,67 +700,49 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
     if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
       rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
     rcs[d] = rc;
-    // every device's "rows packed" event is recorded (or failed) past this point
-    if (ctx->pool) ctx->pool->barrier();
-    bool all_ok = true;
-    for (int e = 0; e < ndev; ++e) all_ok = all_ok && rcs[e] == NBK_OK;
-    if (!all_ok) return;
-    // phase 2: nobody sweeps before every shard is packed
+  };
+  auto all_packed = [&]() {
+    for (int e = 0; e < ndev; ++e)
+      if (rcs[e] != NBK_OK) return false;
+    return true;
+  };
+  // phase 2: nobody sweeps before every shard is packed
+  auto sweep_slice = [&](int d) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    int rc = NBK_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
     for (int e = 0; e < ndev && rc == NBK_OK; ++e)
       if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
         rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
     const Slice &s = sl[d];
     if (rc == NBK_OK && s.b > s.a) rc = launch(c, s, multi_params(ctx, s, eps2, s0, s1));
-    if (rc == NBK_OK && s.b > s.a) rc = collect(c, s);  // the slice goes home as soon as it is done
-    int rc2 = sync(c);
-    rcs[d] = rc != NBK_OK ? rc : rc2;
+    rcs[d] = rc;
+  };
+  // phase 3: the slice goes home as soon as it is done
+  auto collect_slice = [&](int d, bool swept) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    cudaSetDevice(c->device);
+    const Slice &s = sl[d];
+    if (swept && rcs[d] == NBK_OK && s.b > s.a) rcs[d] = collect(c, s);
+    const int rc2 = sync(c);
+    if (rcs[d] == NBK_OK) rcs[d] = rc2;
   };
   if (ctx->pool) {
-    multi_for(ctx, per_device);
+    // one host thread per device; the pool barrier separates phase 1 from phase 2
+    multi_for(ctx, [&](int d) {
+      pack_rows(d);
+      ctx->pool->barrier();  // every device's "rows packed" event is recorded (or failed) past here
+      const bool ok = all_packed();
+      if (ok) sweep_slice(d);
+      collect_slice(d, ok);
+    });
   } else {
-    // serial host loop: phase 1 everywhere, then phase 2 (two passes stand in for the barrier)
-    std::vector<int> keep(ndev, NBK_OK);
-    for (int d = 0; d < ndev; ++d) {
-      nbk_ctx *c = multi_dev(ctx, d);
-      int rc = NBK_OK;
-      if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
-      const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
-      if (rc == NBK_OK) rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
-      if (rc == NBK_OK && cnt > 0) {
-        rc = upload(c, c->d_m, m + a, cnt);
-        if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
-        if (rc == NBK_OK && vel) rc = upload(c, c->d_vel, vel + 3 * (size_t)a, 3 * (size_t)cnt);
-        if (rc == NBK_OK)
-          rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
-                    vel ? (const double *)c->d_vel.p : nullptr, is_velocity,
-                    (double *)c->d_packed.p, c->stream);
-      }
-      if (rc == NBK_OK && stage) rc = stage(c, a, b, rows);
-      if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
-        rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
-      rcs[d] = rc;
-    }
-    bool all_ok = true;
-    for (int e = 0; e < ndev; ++e) all_ok = all_ok && rcs[e] == NBK_OK;
-    for (int d = 0; d < ndev && all_ok; ++d) {
-      nbk_ctx *c = multi_dev(ctx, d);
-      int rc = NBK_OK;
-      cudaSetDevice(c->device);
-      for (int e = 0; e < ndev && rc == NBK_OK; ++e)
-        if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
-          rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
-      const Slice &s = sl[d];
-      if (rc == NBK_OK && s.b > s.a) rc = launch(c, s, multi_params(ctx, s, eps2, s0, s1));
-      rcs[d] = rc;
-    }
-    for (int d = 0; d < ndev; ++d) {
-      nbk_ctx *c = multi_dev(ctx, d);
-      cudaSetDevice(c->device);
-      const Slice &s = sl[d];
-      if (all_ok && rcs[d] == NBK_OK && s.b > s.a) rcs[d] = collect(c, s);
-      int rc2 = sync(c);
-      if (rcs[d] == NBK_OK) rcs[d] = rc2;
-    }
+    // serial host loop: one pass per phase stands in for the barrier, and every device's sweep is
+    // in flight before the first blocking download
+    for (int d = 0; d < ndev; ++d) pack_rows(d);
+    const bool ok = all_packed();
+    for (int d = 0; d < ndev && ok; ++d) sweep_slice(d);
+    for (int d = 0; d < ndev; ++d) collect_slice(d, ok);
   }
   cudaSetDevice(ctx->device);
   for (int d = 0; d < ndev; ++d)
