@@ -375,11 +375,12 @@ double nbh_omega_pushforward(int n, const double *jac) {
   double sum = 0.0;
   for (int i = 0; i < no2; ++i) {
     const int a = i + no2, b = i;
+    // (J^T *|| S) first (dFloat_pushforward.ml:147, *|| associates to the left): its row a is
+    // J[no2+j][a] for j < no2 and -J[j-no2][a] beyond, exactly (one non-zero term per sum); then
+    // the product with J accumulates over j = 0 .. 6n-1 in order (:81-95)
     double e = 0.0;
-    for (int r = 0; r < no2; ++r) {
-      e += jac[(size_t)r * d6 + a] * (-1.0) * jac[(size_t)(no2 + r) * d6 + b];
-      e += jac[(size_t)(no2 + r) * d6 + a] * (1.0) * jac[(size_t)r * d6 + b];
-    }
+    for (int j = 0; j < no2; ++j) e += jac[(size_t)(no2 + j) * d6 + a] * jac[(size_t)j * d6 + b];
+    for (int j = no2; j < d6; ++j) e += -jac[(size_t)(j - no2) * d6 + a] * jac[(size_t)j * d6 + b];
     sum += e;
   }
   return sum / (double)no2;

@@ -22,9 +22,10 @@
 // advancer.ml:98-116, are ONE boxed float referenced from every fresh body), so the reader keeps
 // the object table.  The writer emits no sharing (legal: sharing is an optimisation of the
 // encoding; the value read back is structurally equal) and little-endian doubles, like ocamlopt
-// on x86-64 / arm64.  PARITY UNPINNED against a real OCaml runtime: checked here by round trips
-// and by hand-assembled streams (tests/test_marshal.py), which also reads a stream written by the
-// real Marshal module whenever one has been generated on a machine with an OCaml toolchain.
+// on x86-64 / arm64.  Not checked against a real OCaml runtime (none exists in the build image):
+// checked by round trips, by hand-assembled streams and by a stream of the reference's own body
+// records written by an independent encoder (tests/test_marshal.py), which also reads a stream
+// written by the real Marshal module whenever one has been generated with an OCaml toolchain.
 #include <cerrno>
 #include <cmath>
 #include <cstdint>

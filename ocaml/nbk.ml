@@ -41,7 +41,7 @@ external grad_v_dgrad_v_sum_tangent :
   ctx -> vec -> vec -> vec -> int -> vec -> vec -> float -> range -> vec -> vec -> unit
   = "nbk_ml_tangent_bc" "nbk_ml_tangent"
 
-(* Bodies resident on the device for Omelyan_advancer.OA (nbk_oa_*): upload once, run whole
+(* Bodies resident on the device for Omelyan_advancer.OA (the nbk_oa_ entry points): upload once, run whole
    steps of B A C A B on the GPU, read diagnostics / the state back when needed. *)
 external oa_upload : ctx -> vec -> vec -> vec -> unit = "nbk_ml_oa_upload"
 external oa_steps : ctx -> float -> float -> int -> unit = "nbk_ml_oa_steps"

@@ -15,12 +15,18 @@
  *
  * PARITY STATUS: the reference repository holds no golden vector, fixed seed or fixture for
  * this path (test/run_tests.ml:10 self-seeds; the only fixture is listed in
- * .MISSING_LARGE_BLOBS) and no OCaml toolchain exists in the build image, so this
- * restatement cannot be checked bit-for-bit against a run of the reference.  It is pinned
- * by (i) the reference's own test invariants restated in tests/test_oracle_invariants.py
- * (test/ic_test.ml:9-23,47-61, test/advance_test.ml:9-52, test/leapfrog_test.ml:7-25),
- * (ii) analytic two-body values, and (iii) a __float128 evaluation of the same sums.
- * "parity unpinned" in the strict (golden-vector) sense.
+ * .MISSING_LARGE_BLOBS) and no OCaml toolchain exists in the build image.  The restatement is
+ * pinned against the reference's OWN SOURCE TEXT instead: oracle/miniml interprets the unmodified
+ * .ml files under /root/reference, oracle/ref_fixtures/gen*.ml drive them over committed seeded
+ * inputs, and this oracle reproduces all 6955 values they write BIT FOR BIT
+ * (oracle/ref_fixtures/ref_miniml/, tests/test_ref_fixtures.py).  That is a pin through an
+ * interpreter written for this repository (oracle/miniml/README.md says what it guarantees),
+ * not through an ocamlopt binary: oracle/ref_fixtures/Makefile prepares that run for the first
+ * machine with ocamlfind.  Also pinned by (i) the reference's own test invariants restated in
+ * tests/test_oracle_invariants.py (test/ic_test.ml:9-23,47-61, test/advance_test.ml:9-52,
+ * test/leapfrog_test.ml:7-25), (ii) analytic two-body values, (iii) a __float128 evaluation of
+ * the same sums, (iv) an independent Python twin (oracle/twin.py).  Third-party Diff.DFloat
+ * arithmetic stays unpinned (oracle/num.hh).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may use anything under oracle/.

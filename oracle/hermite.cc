@@ -376,15 +376,16 @@ void oracle_hermite_jacobian_advance(int n, const double *m, const double *q, co
 // `symplectic` (:132-139).  1.0 for a symplectic map.
 double oracle_omega_pushforward(int n, const double *jac) {
   const int d6 = 6 * n, no2 = 3 * n;
-  // (J^T S J)[a][b] = sum_{r,c} J[r][a] S[r][c] J[c][b];  S[i][no2+i] = -1, S[no2+i][i] = 1.
+  // S[i][no2+i] = -1, S[no2+i][i] = 1.
   double sum = 0.0;
   for (int i = 0; i < no2; ++i) {
     int a = i + no2, b = i;
+    // (J^T *|| S) first (dFloat_pushforward.ml:147, *|| associates to the left): its row a is
+    // J[no2+j][a] for j < no2 and -J[j-no2][a] beyond, exactly (one non-zero term per sum); then
+    // the product with J accumulates over j = 0 .. 6n-1 in order (:81-95)
     double e = 0.0;
-    for (int r = 0; r < no2; ++r) {
-      e += jac[(size_t)r * d6 + a] * (-1.0) * jac[(size_t)(no2 + r) * d6 + b];
-      e += jac[(size_t)(no2 + r) * d6 + a] * (1.0) * jac[(size_t)r * d6 + b];
-    }
+    for (int j = 0; j < no2; ++j) e += jac[(size_t)(no2 + j) * d6 + a] * jac[(size_t)j * d6 + b];
+    for (int j = no2; j < d6; ++j) e += -jac[(size_t)(j - no2) * d6 + a] * jac[(size_t)j * d6 + b];
     sum += e;
   }
   return sum / (double)no2;

@@ -1,8 +1,9 @@
 """oracle/oracle.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 ctypes loader for oracle/_build/liboracle.so, the CPU restatement of the reference's
-pairwise-gravity path (arithmetic and citations: oracle/base.h; parity status: "unpinned" in
-the golden-vector sense, pinned by the reference's test invariants — see base.h).
+pairwise-gravity path (arithmetic and citations: oracle/base.h; parity status: reproduces bit for
+bit what the reference's unmodified sources compute when interpreted by oracle/miniml — see base.h
+and oracle/ref_fixtures/README.md; no ocamlopt run exists).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this module.  Nothing under direct-nbody_b200/ does.

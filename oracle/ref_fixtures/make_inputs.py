@@ -120,12 +120,131 @@ def traj(m, q, p):
     return o.text()
 
 
+def _norm3(v):
+    return np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+
+def _emit_advancer(o, key, a):
+    for r in range(len(a.id)):
+        o.emit(f"{key}_id", r, 0, 0, float(a.id[r]))
+        o.emit(f"{key}_t", r, 0, 0, a.t[r])
+        o.emit(f"{key}_h", r, 0, 0, a.h[r])
+        o.emit(f"{key}_hmax", r, 0, 0, a.hmax[r])
+        o.emit3(f"{key}_q", r, 0, a.q[r])
+        o.emit3(f"{key}_p", r, 0, a.p[r])
+
+
+def wide(big, small):
+    """The oracle's answers to gen_wide.ml's calls, in its order."""
+    o = Out()
+    m, q, p = big
+    sm, sq, sp = small
+    eps2 = 0.2 * 0.2  # Base.set_eps 0.2 = square 0.2 (base.ml:30-31)
+    # -- softened()
+    f, df = O.start_bs_sweep(m, q, p, eps2)
+    for i in range(len(m)):
+        o.emit3("eps_start_f", i, 0, f[i])
+        o.emit3("eps_start_df", i, 0, df[i])
+        o.emit("eps_start_h", i, 0, 0, 6.0 * 1e-2 * _norm3(f[i]) / (m[i] * _norm3(df[i])))
+    ke, pe = O.total_kinetic_energy(m, p), O.total_potential_energy(m, q, eps2)
+    o.emit("eps_ke", 0, 0, 0, ke)
+    o.emit("eps_pe", 0, 0, 0, pe)
+    o.emit("eps_energy", 0, 0, 0, ke + pe)
+    # Leapfrog bodies keep v = p / m and B.p hands back v * m (leapfrog.ml:31-43)
+    plf = (p / m[:, None]) * m[:, None]
+    kelf = O.total_kinetic_energy(m, plf)
+    o.emit("eps_lf_ke", 0, 0, 0, kelf)
+    o.emit("eps_lf_energy", 0, 0, 0, kelf + pe)
+    h = O.hermite_advance(O.HermiteState(sm, sq, sp), 0.0625, 1e-3, eps2)
+    h = O.hermite_advance(h, 0.0625, 1e-3, eps2)
+    for i in range(len(sm)):
+        o.emit("h2_t", i, 0, 0, h.t[i])
+        o.emit("h2_h", i, 0, 0, h.h[i])
+        for key, arr in (("h2_q", h.q), ("h2_p", h.p), ("h2_f", h.f), ("h2_df", h.df)):
+            o.emit3(key, i, 0, arr[i])
+    o.emit("h2_nsteps", 0, 0, 0, float(h.nsteps))
+    a = O.advancer_advance(O.AdvancerState(sm, sq, sp), 0.0625, 1e-3, eps2)
+    a = O.advancer_advance(a, 0.0625, 1e-3, eps2)
+    _emit_advancer(o, "a2", a)
+    o.emit("a2_energy", 0, 0, 0, O.energy(a.m, a.q, a.p, eps2))
+    oq, op, ot = sq, sp, 0.0
+    for _ in range(4):
+        oq, op, ot = O.omelyan_advance(sm, oq, op, ot, 1.0 / 128.0, eps2)
+    for i in range(len(sm)):
+        o.emit("oa4_t", i, 0, 0, ot)
+        o.emit3("oa4_q", i, 0, oq[i])
+        o.emit3("oa4_p", i, 0, op[i])
+    # -- unsoftened()
+    s = O.leapfrog_advance(O.LeapfrogState(sm, sq, sp), 1.0 / 32.0, 1e-3)
+    for r in range(len(sm)):
+        o.emit("lf3_id", r, 0, 0, float(s.id[r] - 1))
+        o.emit("lf3_t", r, 0, 0, s.t[r])
+        o.emit("lf3_dtmax", r, 0, 0, s.dt_max[r])
+        o.emit3("lf3_q", r, 0, s.q[r])
+        o.emit3("lf3_v", r, 0, s.v[r])
+    o.emit("lf3_energy", 0, 0, 0, O.energy(s.m, s.q, s.v * s.m[:, None], 0.0))
+    a = O.advancer_advance(O.AdvancerState(sm, sq, sp), 0.0625, 1e-2, 0.0, extpot="plummer_test")
+    _emit_advancer(o, "ax", a)
+    bi, bj, be = O.binaries(m, q, p, 0.0, 0.0)
+    # Analysis.binaries conses as it scans: the list is the scan reversed (analysis.ml:836-847)
+    for k, (i, j, e) in enumerate(zip(bi[::-1], bj[::-1], be[::-1])):
+        o.emit("bin_i", k, 0, 0, float(i))
+        o.emit("bin_j", k, 0, 0, float(j))
+        o.emit("bin_e", k, 0, 0, e)
+    ti, tj, te = O.binaries(m, q, p, 0.0, -abs(0.01))
+    for k, (i, j, e) in enumerate(zip(ti[::-1], tj[::-1], te[::-1])):
+        o.emit("thr_i", k, 0, 0, float(i))
+        o.emit("thr_j", k, 0, 0, float(j))
+        o.emit("thr_e", k, 0, 0, e)
+    # tightest_binary folds from the head and replaces on a strictly larger |e| (analysis.ml:863-876)
+    best = 0
+    rev = list(zip(bi[::-1], bj[::-1], be[::-1]))
+    for k in range(1, len(rev)):
+        if abs(rev[k][2]) > abs(rev[best][2]):
+            best = k
+    o.emit("tight_i", 0, 0, 0, float(rev[best][0]))
+    o.emit("tight_j", 0, 0, 0, float(rev[best][1]))
+    el = O.bodies_to_el_phase_space(m, q, p, 0.0)
+    for i in range(len(m)):
+        for k in range(4):
+            o.emit("el", i, 0, k, el[i, k])
+    a = O.advancer_advance(O.AdvancerState(sm, sq, sp), 0.03125, 1e-3, 0.0)
+    a = O.advancer_advance(a, 0.03125, 1e-3, 0.0)
+    _emit_advancer(o, "int", a)
+    return o.text()
+
+
+def ics(big):
+    o = Out()
+    fm, fq, fp = O.adjust_frame(*big)
+    sm, sq, sp = O.rescale_to_standard_units(fm, fq, fp)
+    for key, (m, q, p) in (("frame", (fm, fq, fp)), ("std", (sm, sq, sp))):
+        for i in range(len(m)):
+            o.emit(f"{key}_m", i, 0, 0, m[i])
+            o.emit3(f"{key}_q", i, 0, q[i])
+            o.emit3(f"{key}_p", i, 0, p[i])
+    return o.text()
+
+
+def dfloat(small):
+    o = Out()
+    m, q, p = small
+    for key, n, dt, sf in (("n3", 3, 0.03125, 1e-2), ("n5", 5, 0.015625, 1e-2)):
+        jac, _ = O.hermite_jacobian_advance(m[:n], q[:n], p[:n], dt, sf)
+        for i in range(6 * n):
+            for j in range(6 * n):
+                o.emit(f"{key}_jac", i, j, 0, jac[i, j])
+        o.emit(f"{key}_omega", 0, 0, 0, O.omega_pushforward(jac))
+    return o.text()
+
+
 def expected(inputs_dir=None):
     """{file name: text} of the oracle's outputs for the committed inputs."""
     d = inputs_dir or os.path.join(HERE, "inputs")
     big = read_bodies(os.path.join(d, "plummer_n64_seed20240.txt"))
     small = read_bodies(os.path.join(d, "plummer_n16_std_seed20241.txt"))
-    return {"pairs.hex": pairs(*big), "sums.hex": sums(*big), "traj.hex": traj(*small)}
+    return {"pairs.hex": pairs(*big), "sums.hex": sums(*big), "traj.hex": traj(*small),
+            "wide.hex": wide(big, small), "ics.hex": ics(big), "dfloat.hex": dfloat(small)}
 
 
 if __name__ == "__main__":

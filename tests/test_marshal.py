@@ -5,8 +5,10 @@ the reader is checked against streams ASSEMBLED BY HAND from the runtime's publi
 (runtime/caml/intext.h) - including what a real writer produces and ours does not: physical
 sharing (the one boxed `nan` of A.make_body_id, advancer.ml:98-116, referenced from every fresh
 body), big-endian doubles, every integer width, the 64-bit "big" header - and the writer by
-round trips plus an independent re-derivation of its header words.  PARITY UNPINNED against a real
-runtime; oracle/ref_fixtures/gen.ml writes ref/states_adv.bin for that day."""
+round trips plus an independent re-derivation of its header words.  Not pinned against a real
+runtime; oracle/ref_fixtures/gen.ml writes ref/states_adv.bin for that day, and the same gen.ml run
+by the interpreter oracle/miniml gives ref_miniml/states_adv.bin (the reference's records through
+an independent encoder that DOES share boxed floats), read below."""
 import os
 import struct
 
@@ -173,13 +175,17 @@ def test_reader_accepts_leapfrog_records_and_rejects_garbage(tmp_path):
         nbh.marshal_read_state(bad, 0)
 
 
-def test_reference_written_stream_if_present():
-    """ref/states_adv.bin comes from the REAL Marshal module (oracle/ref_fixtures/gen.ml)."""
+@pytest.mark.parametrize("where", ["ref", "ref_miniml"])
+def test_reference_written_stream_if_present(where):
+    """ref/states_adv.bin comes from the REAL Marshal module (oracle/ref_fixtures/gen.ml compiled
+    with ocamlfind; absent until someone does that).  ref_miniml/states_adv.bin is the same
+    gen.ml interpreted by oracle/miniml over the unmodified Advancer.A: the body records are the
+    reference's, the encoder is miniml's (it shares boxed floats by identity, so the stream is
+    full of SHARED back-references - a different byte string from ocamlopt's, the same value)."""
     kit = os.path.join(ROOT, "oracle", "ref_fixtures")
-    path = os.path.join(kit, "ref", "states_adv.bin")
+    path = os.path.join(kit, where, "states_adv.bin")
     if not os.path.exists(path):
-        pytest.skip("PARITY UNPINNED: no stream written by a real OCaml runtime "
-                    "(oracle/ref_fixtures/ref/states_adv.bin)")
+        pytest.skip("no stream written by a real OCaml runtime (oracle/ref_fixtures/ref/states_adv.bin)")
     import sys
     sys.path.insert(0, kit)
     import make_inputs
@@ -190,7 +196,7 @@ def test_reference_written_stream_if_present():
     assert np.array_equal(st[:, 5:8], p) and np.isnan(st[:, 8:]).all()
     kind, ids, st = nbh.marshal_read_state(path, 1)   # after A.advance bs 0.125 1e-3
     ref = {}
-    for ln in open(os.path.join(kit, "ref", "traj.hex")):
+    for ln in open(os.path.join(kit, where, "traj.hex")):
         key, i, j, k, bits = ln.split()
         ref[(key, int(i), int(k))] = struct.unpack("<d", struct.pack("<Q", int(bits, 16)))[0]
     for r in range(len(ids)):

@@ -2,7 +2,7 @@
 the same OCaml functions written independently in plain Python (IEEE binary64, no FMA, libm pow
 and sqrt - the arithmetic of an ocamlopt build).  Bit-for-bit agreement on small systems: a
 transcription slip in either text, or a compiler that fuses or reorders the C one, shows up as a
-differing bit.  (Neither is the OCaml binary: DESIGN.md §6, "parity unpinned".)"""
+differing bit.  (Neither is the OCaml text itself: that comparison is tests/test_ref_fixtures.py)"""
 import numpy as np
 import pytest
 

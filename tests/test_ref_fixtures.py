@@ -1,13 +1,23 @@
-"""CPU: pinning the oracle against the REAL reference.
+"""CPU: pinning the oracle against the reference's own text.
 
-The reference is OCaml and this image has no OCaml toolchain, so nothing here can run it.
-oracle/ref_fixtures/ is the kit for the first machine that can: gen.ml links the unmodified
-reference modules and writes what Base / Hermite / Leapfrog / OA / Advancer.A / Energy return for
-the committed seeded inputs (bit patterns); `make -C oracle/ref_fixtures REF=...` produces
-ref/*.hex.  When those files exist, test_oracle_reproduces_reference_outputs asserts the oracle
-reproduces every value BIT FOR BIT; until then it skips with PARITY UNPINNED, and the other tests
-keep the kit honest: inputs and expected/ are exactly what the oracle produces today, gen.ml
-emits the same keys, and the seeded inputs are the golden fixtures' own bodies."""
+The reference is OCaml and this image has no OCaml toolchain.  oracle/ref_fixtures/ holds small
+OCaml programs (gen.ml, gen_wide.ml, gen_ics.ml, gen_dfloat.ml) that link the UNMODIFIED
+reference modules and write what Base / Hermite / Leapfrog / OA / Advancer.A / Energy / Analysis /
+Integrator / Ics / DFloat_hermite + DFloat_pushforward return for committed seeded inputs, as IEEE
+bit patterns.  Two ways of running them:
+
+  * oracle/miniml - an interpreter for the OCaml subset those sources use - executes them in this
+    container straight from /root/reference (run_miniml.py); its outputs are committed under
+    ref_miniml/ and the oracle must reproduce EVERY value BIT FOR BIT
+    (test_oracle_reproduces_reference_outputs[ref_miniml]); with the reference tree present the
+    interpreter is re-run and must reproduce the committed files
+    (test_committed_ref_miniml_is_what_the_interpreter_produces).
+  * `make -C oracle/ref_fixtures REF=...` on a machine with ocamlfind writes ref/*.hex from an
+    ocamlopt build; [ref] compares against that once it exists and is skipped until then.
+
+The other tests keep the kit honest: inputs and expected/ are exactly what the oracle produces
+today, the generators emit the same keys, and the seeded inputs are the golden fixtures' own
+bodies."""
 import os
 import re
 import sys
@@ -81,15 +91,56 @@ def test_gen_ml_emits_exactly_the_expected_keys_and_calls_the_reference():
     assert keys == want, (sorted(keys - want), sorted(want - keys))
 
 
-def test_oracle_reproduces_reference_outputs():
-    ref_dir = os.path.join(KIT, "ref")
-    names = ("pairs.hex", "sums.hex", "traj.hex")
-    if not all(os.path.exists(os.path.join(ref_dir, n)) for n in names):
-        pytest.skip("PARITY UNPINNED: oracle/ref_fixtures/ref/*.hex absent - no OCaml toolchain in "
-                    "this image has ever run oracle/ref_fixtures/gen.ml against the reference")
+SHEETS = ("pairs.hex", "sums.hex", "traj.hex", "wide.hex", "ics.hex", "dfloat.hex")
+
+
+@pytest.mark.parametrize("where", ["ref_miniml", "ref"])
+def test_oracle_reproduces_reference_outputs(where):
+    ref_dir = os.path.join(KIT, where)
+    names = [n for n in SHEETS if os.path.exists(os.path.join(ref_dir, n))]
+    if where == "ref" and not names:
+        pytest.skip("oracle/ref_fixtures/ref/*.hex absent: no ocamlopt build of the generators has "
+                    "been run (the interpreter-run pin is the [ref_miniml] case)")
+    assert where == "ref" or names == list(SHEETS), "ref_miniml/ must hold every sheet"
     exp = _kit().expected()
+    total = 0
     for n in names:
         ref, mine = _parse(open(os.path.join(ref_dir, n)).read()), _parse(exp[n])
         assert set(ref) == set(mine), n
         bad = [(k, ref[k], mine[k]) for k in sorted(ref) if ref[k] != mine[k]]
         assert not bad, f"{n}: {len(bad)} values differ from the reference, first: {bad[:5]}"
+        total += len(ref)
+    assert where == "ref" or total > 6000  # 6955 values at the time of writing
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree")
+def test_committed_ref_miniml_is_what_the_interpreter_produces():
+    """Re-run every generator over /root/reference with oracle/miniml (about 12 s) and compare with
+    the committed ref_miniml/ byte for byte: the committed pin is reproducible, not hand-made."""
+    import run_miniml
+    for gen, files in run_miniml.GENERATORS.items():
+        out = run_miniml.run_generator(gen, "/root/reference")
+        for f in files:
+            if f.endswith(".hex"):
+                assert out[f] == open(os.path.join(KIT, "ref_miniml", f), "rb").read(), (gen, f)
+
+
+def test_wide_generators_call_the_reference_and_cover_the_expected_keys():
+    for gen, sheet, fns in (
+            ("gen_wide.ml", "wide.hex",
+             ("Base.set_eps ", "Hermite.start_bs ", "Hermite.advance ", "Advancer.A.advance ",
+              "Advancer.A.advance ~extpot", "Omelyan_advancer.OA.advance ", "Leapfrog.advance ",
+              "An.binaries ", "An.binaries_threshold ", "An.tightest_binary ",
+              "An.bodies_to_el_phase_space ", "In.constant_sf_integrate ",
+              "Analysis.Make (Advancer.A)", "Integrator.Make (Advancer.A) (Advancer.A)")),
+            ("gen_ics.ml", "ics.hex", ("Ic.adjust_frame ", "Ic.rescale_to_standard_units ",
+                                       "Ics.Make (Advancer.A)")),
+            ("gen_dfloat.ml", "dfloat.hex", ("J.jacobian_advance ", "J.omega_pushforward ",
+                                             "DFloat_pushforward.Make (DFloat_hermite)"))):
+        code = re.sub(r"\(\*.*?\*\)", " ", open(os.path.join(KIT, gen)).read(), flags=re.S)
+        for fn in fns:
+            assert fn in code, (gen, fn)
+        keys = {k[0] for k in _parse(open(os.path.join(KIT, "expected", sheet)).read())}
+        stems = set(re.findall(r'"([a-z0-9_]+)"', code))
+        for k in keys:  # every expected key is a literal of the generator, or stem ^ "_suffix"
+            assert k in stems or any(k.startswith(st + "_") for st in stems), (gen, k)
