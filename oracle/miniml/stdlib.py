@@ -906,6 +906,40 @@ def install(interp):
     Sy.vals["word_size"] = [64]
     root.define_mod("Sys", Sy)
 
+    # -- Hashtbl (keys: ints, floats, strings and tuples of them; one binding per key is kept
+    #    visible - `add` shadows like the stdlib's, `remove` pops the newest)
+    H = Module("Hashtbl")
+
+    def hkey(k):
+        try:
+            hash(k)
+        except TypeError:
+            raise MLError("Hashtbl: only immediate / string / tuple keys are modelled")
+        return k
+
+    def h_find(t, k):
+        b = t.get(hkey(k))
+        if not b:
+            raise MLExn(Ctor("Not_found"))
+        return b[-1]
+
+    def h_remove(t, k):
+        b = t.get(hkey(k))
+        if b:
+            b.pop()
+            if not b:
+                del t[k]
+        return UNIT
+    fn("create", 1, lambda n: {}, H)
+    fn("add", 3, unit(lambda t, k, v: t.setdefault(hkey(k), []).append(v)), H)
+    fn("replace", 3, unit(lambda t, k, v: t.__setitem__(hkey(k), t.get(k, [None])[:-1] + [v])), H)
+    fn("find", 2, h_find, H)
+    fn("find_opt", 2, lambda t, k: Ctor("Some", t[k][-1]) if t.get(hkey(k)) else Ctor("None"), H)
+    fn("mem", 2, lambda t, k: bool(t.get(hkey(k))), H)
+    fn("remove", 2, h_remove, H)
+    fn("length", 1, lambda t: sum(len(b) for b in t.values()), H)
+    root.define_mod("Hashtbl", H)
+
     # -- Lazy, Int32, Bigarray.Array1 (as plain arrays: enough to LOAD code that uses them)
     Lz = Module("Lazy")
     fn("force", 1, lambda l: l.force(), Lz)
