@@ -117,7 +117,7 @@ let unsoftened oc big small =
   Array.iteri (fun k (b1, b2, e) ->
       emiti oc "thr_i" k 0 0 (Advancer.A.id b1 - ida);
       emiti oc "thr_j" k 0 0 (Advancer.A.id b2 - ida);
-      emit oc "thr_e" k 0 0 e) (An.binaries_threshold 0.01 ab);
+      emit oc "thr_e" k 0 0 e) (An.binaries_threshold 1e-4 ab);
   let (t1, t2) = An.tightest_binary ab in
   emiti oc "tight_i" 0 0 0 (Advancer.A.id t1 - ida);
   emiti oc "tight_j" 0 0 0 (Advancer.A.id t2 - ida);

@@ -191,7 +191,7 @@ def wide(big, small):
         o.emit("bin_i", k, 0, 0, float(i))
         o.emit("bin_j", k, 0, 0, float(j))
         o.emit("bin_e", k, 0, 0, e)
-    ti, tj, te = O.binaries(m, q, p, 0.0, -abs(0.01))
+    ti, tj, te = O.binaries(m, q, p, 0.0, -abs(1e-4))
     for k, (i, j, e) in enumerate(zip(ti[::-1], tj[::-1], te[::-1])):
         o.emit("thr_i", k, 0, 0, float(i))
         o.emit("thr_j", k, 0, 0, float(j))

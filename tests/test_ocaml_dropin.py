@@ -588,8 +588,9 @@ module AG = Analysis_gpu.Make (Advancer.A)
     gb = to_list(call(mods["AG"].vals["binaries"][0], ab))
     assert len(rb) == len(gb) > 10
     assert [(ident(a), ident(b), e) for (a, b), e in rb] == [(ident(a), ident(b), e) for (a, b), e in gb]
-    rt = call(mods["AR"].vals["binaries_threshold"][0], 0.01, ab)
-    gt = call(mods["AG"].vals["binaries_threshold"][0], 0.01, ab)
+    rt = call(mods["AR"].vals["binaries_threshold"][0], 1e-4, ab)
+    gt = call(mods["AG"].vals["binaries_threshold"][0], 1e-4, ab)
+    assert 2 < len(rt) < len(rb)
     assert [(ident(a), ident(b), e) for a, b, e in rt] == [(ident(a), ident(b), e) for a, b, e in gt]
     r1, r2 = call(mods["AR"].vals["tightest_binary"][0], ab)
     g1, g2 = call(mods["AG"].vals["tightest_binary"][0], ab)
