@@ -96,6 +96,7 @@ struct nbk_ctx {
   // resident Hermite state
   int hermite_n = 0;
   int hermite_threads = 0;  // 0 auto; 128/256/512/1024 force the stepping CTA size, -8 the cluster kernel (NBK_HERMITE_THREADS)
+  bool hermite_spec = true; // single-CTA loop: software-pipelined (default) or plain (NBK_HERMITE_SPEC=0)
   DevBuf d_hstate, d_hpartial, d_hticket, d_hout, d_hgrid;
   double *h_hres = nullptr, *d_hres = nullptr;  // mapped pinned result slot of the per-step kernel
   double hseq = 0.0;
@@ -786,6 +787,7 @@ int nbk_create(nbk_ctx **out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("NBK_HERMITE_THREADS")) c->hermite_threads = atoi(e);
+  if (const char *e = getenv("NBK_HERMITE_SPEC")) c->hermite_spec = atoi(e) != 0;
   if (const char *e = getenv("NBK_PEER_TIMEOUT_S")) {
     const double s = atof(e);
     c->peer_wait_ns = s > 0.0 ? (unsigned long long)(s * 1e9) : 0ULL;
@@ -2439,18 +2441,61 @@ int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, dou
   const size_t smem = (size_t)n * HRES_STRIDE * sizeof(double);
   // Threads of the single stepping CTA: the per-step cost is dominated by barriers and the two
   // block reductions, so fewer, busier warps win (measured on B200: profiles/).
-  int nth = ctx->hermite_threads ? ctx->hermite_threads : (n <= 128 ? 128 : 256);
+  // the pipelined loop wants ten warps at N = 1024 (two summing warps per scheduler): measured
+  // 2.02 us per step with 320 threads, 2.12 with 256, 2.15 with 384; N = 512: 1.70 with 192;
+  // N = 256: 1.45 - 1.49 with 128 or 256; N = 1536: 2.44 with 384
+  int nth = ctx->hermite_threads;
+  if (nth <= 0)
+    nth = ctx->hermite_spec && n >= 64 ? (n <= 256 ? 128 : n <= 640 ? 192 : n <= 1152 ? 320 : 384)
+                                      : (n <= 128 ? 128 : 256);
   auto launch = [&](auto kern, int threads) -> int {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<1, threads, smem, ctx->stream>>>((double *)ctx->d_hstate.p, n, stop_time, eta, eps2,
                                             (long long)max_steps, (long long *)ctx->d_scalar.p);
     return NBK_OK;
   };
-  switch (nth) {
-    case 128: TRY(launch(hermite_resident_kernel<128>, 128)); break;
-    case 512: TRY(launch(hermite_resident_kernel<512>, 512)); break;
-    case 1024: TRY(launch(hermite_resident_kernel<1024>, 1024)); break;
-    default: TRY(launch(hermite_resident_kernel<256>, 256)); break;
+  // NBK_HERMITE_SPEC=0: the plain loop; default: the software-pipelined one (corrector of step k
+  // overlapped with the search and the force sum of step k+1)
+  const bool spec = ctx->hermite_spec;
+  if (spec && n >= 64) {
+    static const bool want_prof = getenv("NBK_HERMITE_PROF") != nullptr;
+    long long *d_prof = nullptr;
+    if (want_prof) {
+      TRY(reserve(ctx, ctx->d_hgrid, 8 * sizeof(long long)));
+      d_prof = (long long *)ctx->d_hgrid.p;
+      CK(cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), ctx->stream));
+    }
+    auto launch_spec = [&](auto kern, int threads) -> int {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<1, threads, smem, ctx->stream>>>((double *)ctx->d_hstate.p, n, stop_time, eta, eps2,
+                                              (long long)max_steps, (long long *)ctx->d_scalar.p,
+                                              d_prof);
+      return NBK_OK;
+    };
+    switch (nth) {
+      case 128: TRY(launch_spec(hermite_resident_spec_kernel<128>, 128)); break;
+      case 192: TRY(launch_spec(hermite_resident_spec_kernel<192>, 192)); break;
+      case 320: TRY(launch_spec(hermite_resident_spec_kernel<320>, 320)); break;
+      case 384: TRY(launch_spec(hermite_resident_spec_kernel<384>, 384)); break;
+      case 512: TRY(launch_spec(hermite_resident_spec_kernel<512>, 512)); break;
+      case 1024: TRY(launch_spec(hermite_resident_spec_kernel<1024>, 1024)); break;
+      default: TRY(launch_spec(hermite_resident_spec_kernel<256>, 256)); break;
+    }
+    if (want_prof) {
+      long long hp[8];
+      CK(cudaMemcpyAsync(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost, ctx->stream));
+      TRY(sync(ctx));
+      fprintf(stderr, "hermite spec prof (cycles): t0 plain-sum %lld corrector %lld barrier %lld | "
+                      "t32 select %lld spec-sum %lld barrier %lld | plain steps %lld\n",
+              hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+    }
+  } else {
+    switch (nth) {
+      case 128: TRY(launch(hermite_resident_kernel<128>, 128)); break;
+      case 512: TRY(launch(hermite_resident_kernel<512>, 512)); break;
+      case 1024: TRY(launch(hermite_resident_kernel<1024>, 1024)); break;
+      default: TRY(launch(hermite_resident_kernel<256>, 256)); break;
+    }
   }
   CK(cudaGetLastError());
   ctx->launches++;

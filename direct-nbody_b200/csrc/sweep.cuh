@@ -1388,12 +1388,46 @@ __global__ void __launch_bounds__(256) hermite_body_kernel(double *__restrict__ 
 // re-insert.  A kernel launch per step costs ~10 us; this persistent single-CTA kernel keeps
 // the whole Hermite.b array in SHARED MEMORY (136 B per body, N <= HRES_MAX_N) and runs the loop
 // on the device: per step two block reductions (arg-min of next time, 6 force sums), one
-// thread doing the corrector - about 1.5 us per step.
+// thread doing the corrector - 3.6 us per step at N = 1024 (hermite_resident_spec_kernel below is
+// the pipelined version, 2.0 us).
 // Scheduling follows the reference's list semantics: earliest next time first, and among equal
 // next times the most recently re-inserted first (List.merge puts the new body before equal
 // elements, hermite.ml:178), initial ties by array order (stable sort, :187); finish_bs
 // (hermite.ml:132-143) then steps every body to stop_time in that same order.
 // Record slots: 0 t, 1 m, 2-4 q, 5-7 p, 8-10 f, 11-13 df, 14 h, 15 re-insertion stamp.
+// The scheduler's arg-min as integer reductions.  A body's rank in the reference's list is
+// (next time ascending, re-insertion stamp DESCENDING, index ascending); with the order-preserving
+// map of a double onto an unsigned integer below that is the lexicographic minimum of two 64-bit
+// keys, and a 64-bit minimum over a warp is two redux.sync (high word, then the low word among the
+// lanes that hold the minimal high word) instead of five shuffle-compare-select rounds on three
+// values.  Measured in hermite_resident_spec_kernel: 3900 -> ~500 cycles per selection.
+__device__ __forceinline__ unsigned long long hkey_of_double(double x) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double hkey_to_double(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+constexpr unsigned long long HKEY_NONE = ~0ull;
+constexpr int HKEY_IDX_BITS = 20;
+__device__ __forceinline__ unsigned long long hkey_tie(double stamp, int idx) {
+  // stamps are step counts (< 2^43) kept as doubles; newer (larger) first, then the lower index
+  return ((0x7ffffffffffull - (unsigned long long)stamp) << HKEY_IDX_BITS) | (unsigned)idx;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32);
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned lo = (hi == mh) ? (unsigned)v : 0xffffffffu;
+  const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+  return ((unsigned long long)mh << 32) | ml;
+}
+// lexicographic minimum of (k1, k2) over the warp
+__device__ __forceinline__ void warp_min_pair(unsigned long long &k1, unsigned long long &k2) {
+  const unsigned long long m1 = warp_min_u64(k1);
+  k2 = warp_min_u64(k1 == m1 ? k2 : HKEY_NONE);
+  k1 = m1;
+}
+
 constexpr int HRES_STRIDE = 17;   // odd stride: conflict-free per-thread rows
 constexpr int HRES_MAX_N = 1536;
 
@@ -1567,6 +1601,342 @@ __global__ void __launch_bounds__(HRES_THREADS, 1)
 #pragma unroll
     for (int c = 0; c < 16; ++c) state[(size_t)j * HB + c] = rec[j * HRES_STRIDE + c];
   if (tid == 0) *nsteps_out = steps;
+}
+
+// ---- the same loop, software-pipelined -------------------------------------------------------------
+// In hermite_resident_kernel everything serialises behind one thread: select, sum, correct,
+// select...  Here three things run side by side in every step k, on bodies whose records are not
+// being written:
+//   thread 0     the corrector and new time step of body i_k (a chain of dependent FP64 operations
+//                with three divisions and four square roots, ~1800 cycles)
+//   other warps  the force sum of step k+1: its target r (the earliest unfinished body other than
+//                i_k) is known when the step starts - see below - so everybody else is predicted
+//                to r's time and the 1 x (N-2) interactions that do not involve i_k are summed
+//   one warp     the two earliest unfinished bodies other than i_k, b1 (= r) and b2
+// After the step's single barrier the schedule's rule decides who is next: i_k again only if its
+// new next time is <= r's (ties go to the most recently re-inserted body, hermite.ml:178) - then
+// the speculative sums are dropped and the step is done the plain way (10 of 181 843 steps at
+// N = 1024); otherwise r, for which thread 0 only has to add the one missing interaction (r
+// against the NEW i_k) before its corrector.  The target after next needs no search either:
+// excluding r, the earliest body is b2 or the re-inserted i_k, whichever comes first.
+// Keys: a body's rank (next time asc, re-insertion stamp desc, index asc) is kept in its record as
+// two 64-bit integers (slot 16: next time through hkey_of_double, all ones once finished; slot 15:
+// hkey_tie), so the search is integer compares and redux.sync.  Same schedule and records as the
+// plain kernel up to the order of the six sums.  Needs at least 3 warps.
+template <int T>
+__global__ void __launch_bounds__(T, 1)
+    hermite_resident_spec_kernel(double *__restrict__ state, int n, double stop_time, double eta,
+                                 double eps2, long long max_steps,
+                                 long long *__restrict__ nsteps_out,
+                                 long long *__restrict__ prof) {
+  extern __shared__ double rec[];  // [n][HRES_STRIDE]
+  constexpr int NW = T / 32;
+  constexpr int NONE = 0x7fffffff;
+  static_assert(NW >= 3, "thread 0, a selection warp and at least one summing warp");
+  // Roles by warp: 0 = thread 0's corrector, 1 = the search, 2.. = the sums, their sources dealt
+  // round robin in chunks of 32.  Warps go to the SM's four schedulers by (warp & 3); with 10 warps
+  // every scheduler carries two summing warps, which measured best at N = 1024 (2.04 us per step;
+  // keeping thread 0's scheduler free of FP64 work: 2.16, dealing the chunks by scheduler capacity:
+  // 2.23, handing them out through a shared counter: 2.5 - the atomic's round trip serialises a
+  // warp's chunks).
+  constexpr int SELW = 1;
+  constexpr int NF = NW - 2;   // summing warps
+  __shared__ double red[2][NW][6];
+  __shared__ double tgt[2][8];  // summing warps -> thread 0: the next target's predicted state
+  // double-buffered by step parity, so that one barrier per step is enough
+  __shared__ unsigned long long top[2][2][2];  // warp 1 -> all: (k1, k2) of b1 and of b2
+  __shared__ unsigned long long newkey[2][2];  // thread 0 -> all: the stepped body's new (k1, k2)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_force = warp >= 2;
+  const int frank = warp - 2;  // rank among the summing warps
+  SweepParams P;
+  P.eps2 = eps2;
+  // prof (NBK_HERMITE_PROF=1, a debugging aid): cycles thread 0 spends [0] in the plain force sum,
+  // [1] in the corrector, [2] at the barrier after it; [3] warp 1 searching, [4] warp 2 summing,
+  // [5] warp 2 at the barrier; [6] steps taken the plain way
+  long long pc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long c0 = 0;
+  auto K1 = [&](int j) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + j * HRES_STRIDE + 16);
+  };
+  auto K2 = [&](int j) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + j * HRES_STRIDE + 15);
+  };
+  for (int j = tid; j < n; j += T) {
+    double *r = rec + j * HRES_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r[c] = state[(size_t)j * HB + c];
+    const double st = r[15];
+    K1(j) = hkey_of_double(r[0] + r[14]);
+    K2(j) = hkey_tie(st, j);
+  }
+  __syncthreads();
+  auto less = [](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                 unsigned long long b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+  // The search belongs to warp 1.  Lane g keeps, in registers, the two smallest keys of "its"
+  // bodies j = g, g + 32, g + 64, ... (ca = smallest, cb = second).  A step changes one key (the
+  // stepped body's) and hides one body (the one being stepped), so only their two groups are
+  // looked at again - cooperatively, one body per lane - and the rest is a reduction over the 32
+  // cached pairs: ~1000 cycles instead of a walk over all n keys.
+  unsigned long long ca1 = HKEY_NONE, ca2 = HKEY_NONE, cb1 = HKEY_NONE, cb2 = HKEY_NONE;
+  auto keep2 = [&](unsigned long long k1, unsigned long long k2, unsigned long long &a1,
+                   unsigned long long &a2, unsigned long long &b1, unsigned long long &b2) {
+    const bool lt_a = less(k1, k2, a1, a2), lt_b = less(k1, k2, b1, b2);
+    b1 = lt_a ? a1 : (lt_b ? k1 : b1);
+    b2 = lt_a ? a2 : (lt_b ? k2 : b2);
+    a1 = lt_a ? k1 : a1;
+    a2 = lt_a ? k2 : a2;
+  };
+  // warp-wide: the two smallest of the lanes' (a, b) pairs; every lane gets the result
+  auto combine2 = [&](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                      unsigned long long b2, unsigned long long (&o)[2][2]) {
+    unsigned long long g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    // the runner-up: a lane's best if it is not the winner (the tie key holds the index, so
+    // keys are unique), else that lane's second
+    const bool mine = (a1 == g1 && a2 == g2);
+    unsigned long long s1 = mine ? b1 : a1, s2 = mine ? b2 : a2;
+    warp_min_pair(s1, s2);
+    o[0][0] = g1, o[0][1] = g2, o[1][0] = s1, o[1][1] = s2;
+  };
+  auto scan_own = [&]() {  // every lane walks its own group (start-up only)
+    ca1 = ca2 = cb1 = cb2 = HKEY_NONE;
+#pragma unroll 4
+    for (int j = lane; j < n; j += 32) keep2(K1(j), K2(j), ca1, ca2, cb1, cb2);
+  };
+  auto rescan_group = [&](int g, int skip) {  // all lanes look at group g, lane g keeps the result
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    for (int j = g + 32 * lane; j < n; j += 32 * 32)
+      keep2(j == skip ? HKEY_NONE : K1(j), K2(j), a1, a2, b1, b2);
+    unsigned long long o[2][2];
+    combine2(a1, a2, b1, b2, o);
+    if (lane == g) ca1 = o[0][0], ca2 = o[0][1], cb1 = o[1][0], cb2 = o[1][1];
+  };
+  auto idx_of = [](unsigned long long k1, unsigned long long k2) {
+    return k1 == HKEY_NONE ? NONE : (int)(k2 & ((1u << HKEY_IDX_BITS) - 1));
+  };
+  // the six sums for target (tg, itarget) over sources != skip, by `nwarps` warps of which this
+  // one is number `rank`, into red[buf][rank]
+  auto force = [&](int rank, int nwarps, int skip, int itarget, const OpGradVDGradV::Tgt &tg,
+                   double nt, int buf) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = rank * 32 + lane; j < n; j += nwarps * 32) {
+      if (j == skip) continue;
+      double mj, qj[3], vj[3];
+      hermite_predict_fast(rec + j * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, j == itarget, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[buf][rank][c] = acc[c];
+  };
+
+  long long steps = 0, stamp = 0;
+  bool finishing = false;
+  int buf = 0;        // red[buf] holds the sums of the current step
+  bool have = false;  // ... speculatively: warps 2.., everything but the interaction with `prev`
+  int prev = NONE;    // the body stepped just before
+  // the first two bodies of the schedule (warp 1 searches, everybody reads)
+  unsigned long long t2[2][2];
+  if (warp == SELW) {
+    scan_own();
+    combine2(ca1, ca2, cb1, cb2, t2);
+    if (lane == 0)
+      top[1][0][0] = t2[0][0], top[1][0][1] = t2[0][1], top[1][1][0] = t2[1][0], top[1][1][1] = t2[1][1];
+  }
+  __syncthreads();
+  int it = idx_of(top[1][0][0], top[1][0][1]);
+  unsigned long long itk1 = top[1][0][0];
+  int r = idx_of(top[1][1][0], top[1][1][1]);  // the target after this one, unless `it` repeats
+  unsigned long long rk1 = top[1][1][0];
+  int par = 0;
+  for (;;) {
+    if (it == NONE) break;  // every body finished
+    const double knt = hkey_to_double(itk1);
+    if (!finishing) {
+      if (steps >= max_steps) break;
+      if (knt > stop_time) finishing = true;  // advance_bodies -> finish_bs (:172-173)
+    }
+    double *tr = rec + it * HRES_STRIDE;
+    const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    double mt = 0.0, qt[3] = {0, 0, 0}, vt[3] = {0, 0, 0};
+    // the target's predicted state: thread 0 needs it for the corrector (the summing warps left
+    // it in tgt[] when they prepared this step), everybody when the step is done the plain way
+    if (!have) {
+      hermite_predict_fast(tr, nt, mt, qt, vt);
+    } else if (tid == 0) {
+      mt = tgt[buf][0];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) qt[c] = tgt[buf][1 + c], vt[c] = tgt[buf][4 + c];
+    }
+    const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+    if (prof) c0 = clock64();
+    if (!have) {
+      force(warp, NW, NONE, it, tg, nt, buf);
+      __syncthreads();
+      ++pc[6];
+    }
+    if (prof) {
+      const long long c1 = clock64();
+      pc[0] += c1 - c0;
+      c0 = c1;
+    }
+    ++steps;
+    ++stamp;
+    if (tid == 0) {
+      // ---- corrector (hermite.ml:116-123), new time step (hermite.ml:87-93)
+      double extra[6] = {0, 0, 0, 0, 0, 0};
+      if (have) {  // the one interaction the speculative sums left out: the body stepped last
+        double mj, qj[3], vj[3];
+        hermite_predict_fast(rec + prev * HRES_STRIDE, nt, mj, qj, vj);
+        const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                                make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+        OpGradVDGradV::pair<false>(tg, extra, src, src, false, P);
+      }
+      double fp[3], dfp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double a = extra[c], d = extra[3 + c];
+        for (int w = 0; w < (have ? NF : NW); ++w) {
+          a += red[buf][w][c];
+          d += red[buf][w][3 + c];
+        }
+        fp[c] = mt * a;  // f = -gsum = m_i * acc
+        dfp[c] = mt * d;
+      }
+      const double m = mt;
+      double qn[3], pn[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+        pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                          __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+        qn[c] = __dadd_rn(
+            __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+      }
+      const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+      const double rr = __dsqrt_rn(
+          __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      const double fn = __dsqrt_rn(__dadd_rn(
+          __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+      double hn;
+      if (rr == 0.0) {
+        hn = __dmul_rn(h, 1.189207115002721);  // 2 ** 0.25
+      } else {
+        const double x =
+            __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+        hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));  // x ** 0.25
+      }
+      tr[0] = nt;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tr[2 + c] = qn[c];
+        tr[5 + c] = pn[c];
+        tr[8 + c] = fp[c];
+        tr[11 + c] = dfp[c];
+      }
+      tr[14] = hn;
+      const unsigned long long nk1 = finishing ? HKEY_NONE : hkey_of_double(nt + hn);
+      const unsigned long long nk2 = hkey_tie((double)stamp, it);
+      K1(it) = nk1;
+      K2(it) = nk2;
+      newkey[par][0] = nk1;
+      newkey[par][1] = nk2;
+      if (prof) {
+        const long long c1 = clock64();
+        pc[1] += c1 - c0;
+        c0 = c1;
+      }
+    } else if (warp == SELW) {
+      // ---- meanwhile: the two earliest bodies other than `it` (whose record is in flux)
+      if (prev != NONE && (prev & 31) != (it & 31)) rescan_group(prev & 31, it);
+      rescan_group(it & 31, it);
+      combine2(ca1, ca2, cb1, cb2, t2);
+      if (lane == 0)
+        top[par][0][0] = t2[0][0], top[par][0][1] = t2[0][1], top[par][1][0] = t2[1][0],
+        top[par][1][1] = t2[1][1];
+      if (prof) {
+        const long long c1 = clock64();
+        pc[3] += c1 - c0;
+        c0 = c1;
+      }
+    } else if (is_force && r != NONE) {
+      // ---- meanwhile: the sums of the next step's target r, without `it`
+      const bool fin_r = finishing || hkey_to_double(rk1) > stop_time;
+      const double *rr_ = rec + r * HRES_STRIDE;
+      const double hr = fin_r ? __dsub_rn(stop_time, rr_[0]) : rr_[14];
+      const double ntr = __dadd_rn(rr_[0], hr);
+      double mr, qr[3], vr[3];
+      hermite_predict_fast(rr_, ntr, mr, qr, vr);
+      const OpGradVDGradV::Tgt tgr = {qr[0], qr[1], qr[2], vr[0], vr[1], vr[2]};
+      if (frank == 0 && lane == 0) {
+        tgt[buf ^ 1][0] = mr;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tgt[buf ^ 1][1 + c] = qr[c], tgt[buf ^ 1][4 + c] = vr[c];
+      }
+      force(frank, NF, it, r, tgr, ntr, buf ^ 1);
+      if (prof) {
+        const long long c1 = clock64();
+        pc[4] += c1 - c0;
+        c0 = c1;
+      }
+    }
+    __syncthreads();
+    if (prof) {
+      const long long c1 = clock64();
+      pc[tid == 0 ? 2 : 5] += c1 - c0;
+    }
+    // ---- who is next, and who after that.  b1 (== r) and b2 are the earliest bodies other than
+    // `it`; `it` re-enters with its new key unless it is finished.
+    const unsigned long long b1k1 = top[par][0][0], b1k2 = top[par][0][1], b2k1 = top[par][1][0],
+                             b2k2 = top[par][1][1];
+    const unsigned long long nk1 = newkey[par][0], nk2 = newkey[par][1];
+    par ^= 1;
+    const bool again = nk1 != HKEY_NONE && (b1k1 == HKEY_NONE || less(nk1, nk2, b1k1, b1k2));
+    prev = it;
+    if (again) {
+      // `it` stays; the body after it is b1
+      itk1 = nk1;
+      have = false;
+      r = idx_of(b1k1, b1k2);
+      rk1 = b1k1;
+    } else {
+      it = idx_of(b1k1, b1k2);
+      itk1 = b1k1;
+      have = (it != NONE);
+      buf ^= 1;
+      // excluding b1, the earliest is b2 or the re-inserted body
+      if (nk1 != HKEY_NONE && less(nk1, nk2, b2k1, b2k2)) {
+        r = prev;
+        rk1 = nk1;
+      } else {
+        r = idx_of(b2k1, b2k2);
+        rk1 = b2k1;
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += T) {
+    double *rj = rec + j * HRES_STRIDE;
+    // slot 15 back to the re-insertion stamp the plain kernel keeps there
+    rj[15] = (double)(0x7ffffffffffull - (K2(j) >> HKEY_IDX_BITS));
+#pragma unroll
+    for (int c = 0; c < 16; ++c) state[(size_t)j * HB + c] = rj[c];
+  }
+  if (tid == 0) *nsteps_out = steps;
+  if (prof) {
+    if (tid == 0) prof[0] = pc[0], prof[1] = pc[1], prof[2] = pc[2], prof[6] = pc[6];
+    if (tid == 32 * SELW) prof[3] = pc[3];
+    if (is_force && frank == 0 && lane == 0) prof[4] = pc[4], prof[5] = pc[5];
+  }
 }
 
 // ---- the same stepping loop on a thread-block CLUSTER (1536 < N <= 12288) ----------------------

@@ -436,6 +436,60 @@ def test_hermite_cluster_kernel_matches_host_scheduler_and_oracle(ctx, oracle):
     assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8
 
 
+def _mirrored(oracle, half, seed):
+    """A point-symmetric system: body i + half is body i reflected through the origin, so the two
+    always have the same next time and the schedule is decided by the tie rule alone."""
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(half, seed))
+    return np.concatenate([m, m]) * 0.5, np.concatenate([q, -q]), np.concatenate([p, -p]) * 0.5
+
+
+@pytest.mark.parametrize("n,threads", [(64, "0"), (100, "128"), (333, "0"), (777, "192"), (1024, "0"),
+                                       (1024, "512"), (1536, "0"), (1300, "1024")])
+def test_hermite_pipelined_loop_matches_plain_loop_and_oracle(oracle, monkeypatch, n, threads):
+    """The single-CTA stepping loop is software-pipelined (corrector of step k beside the search
+    and the force sum of step k+1, integer-key arg-min); NBK_HERMITE_SPEC=0 is the plain loop.
+    Same schedule - same step count as each other and as the oracle - and the same state."""
+    import nbk
+    m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 20250 + n))
+    span = 0.01 if n > 512 else 0.03
+    if threads != "0":
+        monkeypatch.setenv("NBK_HERMITE_THREADS", threads)
+    with nbk.Context(0) as c1:
+        a = nbh.hermite_advance(c1, nbh.HermiteState(m, q, p), span, 1e-4, mode=2)
+        a2 = nbh.hermite_advance(c1, a, span, 1e-4, mode=2)          # resumed
+    monkeypatch.setenv("NBK_HERMITE_SPEC", "0")
+    with nbk.Context(0) as c0:
+        b = nbh.hermite_advance(c0, nbh.HermiteState(m, q, p), span, 1e-4, mode=2)
+        b2 = nbh.hermite_advance(c0, b, span, 1e-4, mode=2)
+    c = oracle.hermite_advance(oracle.HermiteState(m, q, p), span, 1e-4)
+    assert np.all(a.t == span) and np.array_equal(a.id, c.id)
+    assert abs(a.nsteps - b.nsteps) <= 2 and abs(a.nsteps - c.nsteps) <= 2 and a.nsteps > n
+    # the six sums are added in another order: rounding differences, amplified by close encounters
+    assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8 and rel(a.f, b.f) <= 1e-7
+    assert rel(a.q, c.q) <= 1e-10 and rel(a.p, c.p) <= 1e-8
+    assert abs(a2.nsteps - b2.nsteps) <= 2 and rel(a2.q, b2.q) <= 1e-9 and np.all(a2.t == 2 * span)
+
+
+@pytest.mark.parametrize("spec", ["1", "0"])
+def test_hermite_device_loops_break_ties_like_the_reference(oracle, monkeypatch, spec):
+    """Every body starts with a twin that has exactly the same next time; which one steps first is
+    the reference's list order (stable sort, List.merge puts the re-inserted body first,
+    hermite.ml:178,187).  The exact ties last only until rounding separates the twins (the sums
+    run over differently ordered lists), after which their order is decided at the 1e-16 level and
+    costs ~1e-10 in the positions - so: identical step counts on every path, states to 1e-8."""
+    import nbk
+    m, q, p = _mirrored(oracle, 96, 20251)
+    monkeypatch.setenv("NBK_HERMITE_SPEC", spec)
+    with nbk.Context(0) as cx:
+        a = nbh.hermite_advance(cx, nbh.HermiteState(m, q, p), 0.05, 1e-4, mode=2)
+        h = nbh.hermite_advance(cx, nbh.HermiteState(m, q, p), 0.05, 1e-4, mode=1)  # host scheduler
+    c = oracle.hermite_advance(oracle.HermiteState(m, q, p), 0.05, 1e-4)
+    assert a.nsteps == c.nsteps == h.nsteps and a.nsteps > 400
+    assert rel(a.q, c.q) <= 1e-8 and rel(a.p, c.p) <= 1e-7
+    assert rel(h.q, c.q) <= 1e-8 and rel(a.q, h.q) <= 1e-8
+    assert np.abs(a.q[:96] + a.q[96:]).max() <= 1e-7 * np.abs(a.q).max()   # still twins
+
+
 @pytest.mark.parametrize("n,ctas", [(2000, "0"), (2000, "3"), (300, "0"), (7, "0")])
 def test_hermite_grid_kernel_matches_cluster_kernel_and_oracle(oracle, monkeypatch, n, ctas):
     """N > 12288 steps on the whole grid (cooperative launch: state split over the SMs' shared
