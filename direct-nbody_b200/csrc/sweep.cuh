@@ -1963,12 +1963,13 @@ __global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slot 16 = done flag
-  __shared__ double cand[HCL_CTAS][HCL_CAND];
+  // [nloc][HRES_STRIDE]; slots 15 / 16 hold the body's rank as two integer keys (hkey_tie of
+  // stamp and global index; hkey_of_double of the next time, all ones once finished)
+  extern __shared__ double rec[];
+  __shared__ double cand[HCL_CTAS][HCL_CAND];  // key1, key2 (bit patterns), -, then the record
   __shared__ double part[HCL_CTAS][6];
   __shared__ double red[HCL_THREADS / 32][6];
-  __shared__ double key_nt[HCL_THREADS / 32], key_st[HCL_THREADS / 32];
-  __shared__ int key_idx[HCL_THREADS / 32];
+  __shared__ unsigned long long loc_key[2];  // warp 0 -> CTA: this CTA's earliest body
   constexpr int NW = HCL_THREADS / 32;
   constexpr int NONE = 0x7fffffff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1979,87 +1980,86 @@ __global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 
   for (int l = tid; l < nloc; l += HCL_THREADS) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) rec[l * HRES_STRIDE + c] = state[(size_t)(j_lo + l) * HB + c];
-    rec[l * HRES_STRIDE + 16] = 0.0;
+  }
+  auto K1 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 16);
+  };
+  auto K2 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 15);
+  };
+  for (int l = tid; l < nloc; l += HCL_THREADS) {
+    const double *r = rec + l * HRES_STRIDE;
+    const double st = r[15];
+    K1(l) = hkey_of_double(r[0] + r[14]);
+    K2(l) = hkey_tie(st, j_lo + l);
   }
   __syncthreads();
   long long steps = 0, stamp = 0;
   bool finishing = false;
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  auto better = [](double ont, double ost, int oidx, double knt, double kst, int kidx) {
-    return oidx != NONE &&
-           (kidx == NONE || (ont < knt) ||
-            (ont == knt && (ost > kst || (ost == kst && oidx < kidx))));
-  };
+  auto less = [](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                 unsigned long long b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+  // The CTA's earliest body (as in hermite_resident_spec_kernel): lane g of warp 0 keeps the
+  // smallest key of the local bodies l = g, g + 32, ...; a step changes one key in one CTA, whose
+  // warp 0 re-examines that one class, and the candidate is a redux.sync reduction of the 32
+  // cached keys - instead of every thread walking the records and two rounds of shuffles.
+  unsigned long long c1 = HKEY_NONE, c2 = HKEY_NONE;
+  if (warp == 0)
+    for (int l = lane; l < nloc; l += 32) {
+      const unsigned long long k1 = K1(l), k2 = K2(l);
+      if (less(k1, k2, c1, c2)) c1 = k1, c2 = k2;
+    }
+  int changed = -1;  // local index of the body whose key changed in the last step (owner only)
   for (;;) {
-    // ---- post: local arg-min (next time asc, stamp desc, global index asc)
-    double knt = INF, kst = -INF;
-    int kidx = NONE;
-    for (int l = tid; l < nloc; l += HCL_THREADS) {
-      const double *r = rec + l * HRES_STRIDE;
-      if (r[16] != 0.0) continue;
-      const double nt = r[0] + r[14];
-      if (better(nt, r[15], j_lo + l, knt, kst, kidx)) {
-        knt = nt;
-        kst = r[15];
-        kidx = j_lo + l;
+    // ---- post: this CTA's earliest body (next time asc, stamp desc, global index asc)
+    if (warp == 0) {
+      if (changed >= 0) {  // all lanes look at the class of the body that was stepped
+        const int g = changed & 31;
+        unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE;
+        for (int l = g + 32 * lane; l < nloc; l += 32 * 32) {
+          const unsigned long long k1 = K1(l), k2 = K2(l);
+          if (less(k1, k2, a1, a2)) a1 = k1, a2 = k2;
+        }
+        warp_min_pair(a1, a2);
+        if (lane == g) c1 = a1, c2 = a2;
       }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ont = __shfl_down_sync(0xffffffffu, knt, off);
-      const double ost = __shfl_down_sync(0xffffffffu, kst, off);
-      const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
-      if (better(ont, ost, oidx, knt, kst, kidx)) {
-        knt = ont;
-        kst = ost;
-        kidx = oidx;
-      }
-    }
-    if (lane == 0) {
-      key_nt[warp] = knt;
-      key_st[warp] = kst;
-      key_idx[warp] = kidx;
+      unsigned long long b1 = c1, b2 = c2;
+      warp_min_pair(b1, b2);
+      if (lane == 0) loc_key[0] = b1, loc_key[1] = b2;
     }
     __syncthreads();
-    {  // every thread reduces the NW warp keys (cheap) so all know the CTA's candidate
-      knt = key_nt[0];
-      kst = key_st[0];
-      kidx = key_idx[0];
-      for (int w = 1; w < NW; ++w)
-        if (better(key_nt[w], key_st[w], key_idx[w], knt, kst, kidx)) {
-          knt = key_nt[w];
-          kst = key_st[w];
-          kidx = key_idx[w];
-        }
-    }
-    if (tid < HCL_CTAS * HCL_CAND) {
-      const int dst = tid / HCL_CAND, slot = tid % HCL_CAND;
-      double v = 0.0;
-      if (slot == 0) v = knt;
-      else if (slot == 1) v = kst;
-      else if (slot == 2) v = (kidx == NONE) ? -1.0 : (double)kidx;
-      else if (slot < 19 && kidx != NONE) v = rec[(kidx - j_lo) * HRES_STRIDE + (slot - 3)];
-      double *remote = cluster.map_shared_rank(&cand[0][0], dst);
-      remote[rank * HCL_CAND + slot] = v;
+    {
+      const unsigned long long k1 = loc_key[0], k2 = loc_key[1];
+      const int kidx = k1 == HKEY_NONE ? NONE : (int)(k2 & ((1u << HKEY_IDX_BITS) - 1));
+      if (tid < HCL_CTAS * HCL_CAND) {
+        const int dst = tid / HCL_CAND, slot = tid % HCL_CAND;
+        double v = 0.0;
+        if (slot == 0) v = __longlong_as_double((long long)k1);
+        else if (slot == 1) v = __longlong_as_double((long long)k2);
+        else if (slot >= 3 && slot < 19 && kidx != NONE)
+          v = rec[(kidx - j_lo) * HRES_STRIDE + (slot - 3)];
+        double *remote = cluster.map_shared_rank(&cand[0][0], dst);
+        remote[rank * HCL_CAND + slot] = v;
+      }
     }
     cluster.sync();  // A
     // ---- pick: the same winner everywhere
     int it = NONE, owner = 0;
     {
-      double bnt = INF, bst = -INF;
+      unsigned long long b1 = HKEY_NONE, b2 = HKEY_NONE;
       for (int r = 0; r < HCL_CTAS; ++r) {
-        const int idx = cand[r][2] < 0.0 ? NONE : (int)cand[r][2];
-        if (better(cand[r][0], cand[r][1], idx, bnt, bst, it)) {
-          bnt = cand[r][0];
-          bst = cand[r][1];
-          it = idx;
+        const unsigned long long k1 = (unsigned long long)__double_as_longlong(cand[r][0]),
+                                 k2 = (unsigned long long)__double_as_longlong(cand[r][1]);
+        if (less(k1, k2, b1, b2)) {
+          b1 = k1;
+          b2 = k2;
           owner = r;
         }
       }
-      if (it == NONE) break;  // every body finished (uniform over the cluster)
+      if (b1 == HKEY_NONE) break;  // every body finished (uniform over the cluster)
+      it = (int)(b2 & ((1u << HKEY_IDX_BITS) - 1));
       if (!finishing) {
         if (steps >= max_steps) break;
-        if (bnt > stop_time) finishing = true;
+        if (hkey_to_double(b1) > stop_time) finishing = true;
       }
     }
     const double *tr = &cand[owner][3];
@@ -2140,15 +2140,19 @@ __global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 
         wr[11 + c] = dfp[c];
       }
       wr[14] = hn;
-      wr[15] = (double)stamp;
-      if (finishing) wr[16] = 1.0;
+      K1(it - j_lo) = finishing ? HKEY_NONE : hkey_of_double(nt + hn);
+      K2(it - j_lo) = hkey_tie((double)stamp, it);
     }
-    __syncthreads();  // the owner's next arg-min must see the update; uniform in every CTA
+    changed = rank == owner ? it - j_lo : -1;
+    __syncthreads();  // the owner's next search must see the update; uniform in every CTA
   }
   cluster.sync();  // nobody leaves while a peer may still write into its shared memory
-  for (int l = tid; l < nloc; l += HCL_THREADS)
+  for (int l = tid; l < nloc; l += HCL_THREADS) {
+    double *rl = rec + l * HRES_STRIDE;
+    rl[15] = (double)(0x7ffffffffffull - (K2(l) >> HKEY_IDX_BITS));  // back to the stamp
 #pragma unroll
-    for (int c = 0; c < 16; ++c) state[(size_t)(j_lo + l) * HB + c] = rec[l * HRES_STRIDE + c];
+    for (int c = 0; c < 16; ++c) state[(size_t)(j_lo + l) * HB + c] = rl[c];
+  }
   if (rank == 0 && tid == 0) *nsteps_out = steps;
 }
 
@@ -2184,13 +2188,13 @@ struct HermiteGridParams {
 };
 
 __global__ void __launch_bounds__(HGR_THREADS, 1) hermite_grid_kernel(const HermiteGridParams Q) {
-  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slot 16 = done flag
+  // [nloc][HRES_STRIDE]; slots 15 / 16 hold the body's rank as two integer keys (hkey_tie of
+  // stamp and global index; hkey_of_double of the next time, all ones once finished)
+  extern __shared__ double rec[];
   __shared__ double win[HCL_CAND];
   __shared__ double red[HGR_THREADS / 32][6];
-  __shared__ double key_nt[HGR_THREADS / 32], key_st[HGR_THREADS / 32];
-  __shared__ int key_idx[HGR_THREADS / 32], key_own[HGR_THREADS / 32];
-  __shared__ int s_it, s_owner;
-  __shared__ double s_nt;
+  __shared__ unsigned long long loc_key[2];               // warp 0 -> CTA: its earliest body
+  __shared__ unsigned long long wkey[HGR_THREADS / 32][2];  // per-warp minima of the G candidates
   constexpr int NW = HGR_THREADS / 32;
   constexpr int NONE = 0x7fffffff;
   const int G = (int)gridDim.x, rank = (int)blockIdx.x;
@@ -2203,121 +2207,84 @@ __global__ void __launch_bounds__(HGR_THREADS, 1) hermite_grid_kernel(const Herm
   for (int l = tid; l < nloc; l += HGR_THREADS) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) rec[l * HRES_STRIDE + c] = Q.state[(size_t)(j_lo + l) * HB + c];
-    rec[l * HRES_STRIDE + 16] = 0.0;
+  }
+  auto K1 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 16);
+  };
+  auto K2 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 15);
+  };
+  for (int l = tid; l < nloc; l += HGR_THREADS) {
+    const double *r = rec + l * HRES_STRIDE;
+    const double st = r[15];
+    K1(l) = hkey_of_double(r[0] + r[14]);
+    K2(l) = hkey_tie(st, j_lo + l);
   }
   __syncthreads();
   long long steps = 0, stamp = 0;
   unsigned long long nbar = 0;
   bool finishing = false;
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  auto better = [](double ont, double ost, int oidx, double knt, double kst, int kidx) {
-    return oidx != NONE &&
-           (kidx == NONE || (ont < knt) ||
-            (ont == knt && (ost > kst || (ost == kst && oidx < kidx))));
-  };
+  auto less = [](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                 unsigned long long b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+  // the CTA's earliest body: cached class minima in warp 0, as in hermite_cluster_kernel
+  unsigned long long c1 = HKEY_NONE, c2 = HKEY_NONE;
+  if (warp == 0)
+    for (int l = lane; l < nloc; l += 32) {
+      const unsigned long long k1 = K1(l), k2 = K2(l);
+      if (less(k1, k2, c1, c2)) c1 = k1, c2 = k2;
+    }
+  int changed = -1;  // local index of the body whose key changed in the last step (owner only)
   for (;;) {
     const int par = (int)(steps & 1);
     double *cand = Q.cand + (size_t)par * G * HCL_CAND;
     double *part = Q.part + (size_t)par * G * 8;
-    // ---- post: local arg-min (next time asc, stamp desc, global index asc)
-    double knt = INF, kst = -INF;
-    int kidx = NONE;
-    for (int l = tid; l < nloc; l += HGR_THREADS) {
-      const double *r = rec + l * HRES_STRIDE;
-      if (r[16] != 0.0) continue;
-      const double nt = r[0] + r[14];
-      if (better(nt, r[15], j_lo + l, knt, kst, kidx)) {
-        knt = nt;
-        kst = r[15];
-        kidx = j_lo + l;
+    // ---- post: this CTA's earliest body (next time asc, stamp desc, global index asc)
+    if (warp == 0) {
+      if (changed >= 0) {  // all lanes look at the class of the body that was stepped
+        const int g = changed & 31;
+        unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE;
+        for (int l = g + 32 * lane; l < nloc; l += 32 * 32) {
+          const unsigned long long k1 = K1(l), k2 = K2(l);
+          if (less(k1, k2, a1, a2)) a1 = k1, a2 = k2;
+        }
+        warp_min_pair(a1, a2);
+        if (lane == g) c1 = a1, c2 = a2;
       }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ont = __shfl_down_sync(0xffffffffu, knt, off);
-      const double ost = __shfl_down_sync(0xffffffffu, kst, off);
-      const int oidx = __shfl_down_sync(0xffffffffu, kidx, off);
-      if (better(ont, ost, oidx, knt, kst, kidx)) {
-        knt = ont;
-        kst = ost;
-        kidx = oidx;
-      }
-    }
-    if (lane == 0) {
-      key_nt[warp] = knt;
-      key_st[warp] = kst;
-      key_idx[warp] = kidx;
+      unsigned long long b1 = c1, b2 = c2;
+      warp_min_pair(b1, b2);
+      if (lane == 0) loc_key[0] = b1, loc_key[1] = b2;
     }
     __syncthreads();
-    knt = key_nt[0];
-    kst = key_st[0];
-    kidx = key_idx[0];
-    for (int w = 1; w < NW; ++w)
-      if (better(key_nt[w], key_st[w], key_idx[w], knt, kst, kidx)) {
-        knt = key_nt[w];
-        kst = key_st[w];
-        kidx = key_idx[w];
+    {
+      const unsigned long long k1 = loc_key[0], k2 = loc_key[1];
+      const int kidx = k1 == HKEY_NONE ? NONE : (int)(k2 & ((1u << HKEY_IDX_BITS) - 1));
+      if (tid < HCL_CAND) {
+        double v = 0.0;
+        if (tid == 0) v = __longlong_as_double((long long)k1);
+        else if (tid == 1) v = __longlong_as_double((long long)k2);
+        else if (tid >= 3 && tid < 19 && kidx != NONE) v = rec[(kidx - j_lo) * HRES_STRIDE + (tid - 3)];
+        __stcg(cand + (size_t)rank * HCL_CAND + tid, v);
       }
-    if (tid < HCL_CAND) {
-      double v = 0.0;
-      if (tid == 0) v = knt;
-      else if (tid == 1) v = kst;
-      else if (tid == 2) v = (kidx == NONE) ? -1.0 : (double)kidx;
-      else if (tid < 19 && kidx != NONE) v = rec[(kidx - j_lo) * HRES_STRIDE + (tid - 3)];
-      __stcg(cand + (size_t)rank * HCL_CAND + tid, v);
     }
     adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);  // A
     // ---- pick: the same winner everywhere (thread r reads CTA r's key; G <= HGR_THREADS)
-    {
-      double bnt = INF, bst = -INF;
-      int bidx = NONE, bown = 0;
-      if (tid < G) {
-        const double *c = cand + (size_t)tid * HCL_CAND;
-        const double c2 = __ldcg(c + 2);
-        bidx = c2 < 0.0 ? NONE : (int)c2;
-        bnt = __ldcg(c);
-        bst = __ldcg(c + 1);
-        bown = tid;
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ont = __shfl_down_sync(0xffffffffu, bnt, off);
-        const double ost = __shfl_down_sync(0xffffffffu, bst, off);
-        const int oidx = __shfl_down_sync(0xffffffffu, bidx, off);
-        const int oown = __shfl_down_sync(0xffffffffu, bown, off);
-        if (better(ont, ost, oidx, bnt, bst, bidx)) {
-          bnt = ont;
-          bst = ost;
-          bidx = oidx;
-          bown = oown;
-        }
-      }
-      if (lane == 0) {
-        key_nt[warp] = bnt;
-        key_st[warp] = bst;
-        key_idx[warp] = bidx;
-        key_own[warp] = bown;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < NW; ++w)
-          if (better(key_nt[w], key_st[w], key_idx[w], bnt, bst, bidx)) {
-            bnt = key_nt[w];
-            bst = key_st[w];
-            bidx = key_idx[w];
-            bown = key_own[w];
-          }
-        s_it = bidx;
-        s_owner = bown;
-        s_nt = bnt;
-      }
-      __syncthreads();
+    unsigned long long w1 = HKEY_NONE, w2 = HKEY_NONE;
+    if (tid < G) {
+      const double *c = cand + (size_t)tid * HCL_CAND;
+      w1 = (unsigned long long)__double_as_longlong(__ldcg(c));
+      w2 = (unsigned long long)__double_as_longlong(__ldcg(c + 1));
     }
-    const int it = s_it, owner = s_owner;
-    if (it == NONE) break;  // every body finished (uniform over the grid)
+    warp_min_pair(w1, w2);
+    if (lane == 0) wkey[warp][0] = w1, wkey[warp][1] = w2;
+    __syncthreads();
+    w1 = lane < NW ? wkey[lane][0] : HKEY_NONE;
+    w2 = lane < NW ? wkey[lane][1] : HKEY_NONE;
+    warp_min_pair(w1, w2);  // every warp ends up with the winner
+    if (w1 == HKEY_NONE) break;  // every body finished (uniform over the grid)
+    const int it = (int)(w2 & ((1u << HKEY_IDX_BITS) - 1)), owner = it / per;
     if (!finishing) {
       if (steps >= Q.max_steps) break;
-      if (s_nt > Q.stop_time) finishing = true;
+      if (hkey_to_double(w1) > Q.stop_time) finishing = true;
     }
     if (tid < HCL_CAND) win[tid] = __ldcg(cand + (size_t)owner * HCL_CAND + tid);
     __syncthreads();
@@ -2402,16 +2369,20 @@ __global__ void __launch_bounds__(HGR_THREADS, 1) hermite_grid_kernel(const Herm
           wr[11 + c] = dfp[c];
         }
         wr[14] = hn;
-        wr[15] = (double)stamp;
-        if (finishing) wr[16] = 1.0;
+        K1(it - j_lo) = finishing ? HKEY_NONE : hkey_of_double(nt + hn);
+        K2(it - j_lo) = hkey_tie((double)stamp, it);
       }
     }
-    __syncthreads();  // the owner's next arg-min must see the update; uniform in every CTA
+    changed = rank == owner ? it - j_lo : -1;
+    __syncthreads();  // the owner's next search must see the update; uniform in every CTA
   }
   __syncthreads();
-  for (int l = tid; l < nloc; l += HGR_THREADS)
+  for (int l = tid; l < nloc; l += HGR_THREADS) {
+    double *rl = rec + l * HRES_STRIDE;
+    rl[15] = (double)(0x7ffffffffffull - (K2(l) >> HKEY_IDX_BITS));  // back to the stamp
 #pragma unroll
-    for (int c = 0; c < 16; ++c) Q.state[(size_t)(j_lo + l) * HB + c] = rec[l * HRES_STRIDE + c];
+    for (int c = 0; c < 16; ++c) Q.state[(size_t)(j_lo + l) * HB + c] = rl[c];
+  }
   if (rank == 0 && tid == 0) *Q.nsteps_out = steps;
 }
 
