@@ -1,5 +1,6 @@
 import os, sys, time
-sys.path[:0] = ['/root/repo', '/root/repo/direct-nbody_b200']
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'direct-nbody_b200')]
 import numpy as np, nbh, nbk
 with nbk.Context(0) as ctx:
     for n in (16384, 65536, 131072):
