@@ -949,10 +949,8 @@ class Interp:
                 return lambda fr: -a(fr)
         f = self.compile(fe, fs, scope)
         cargs = []
-        labelled = False
         for x in args:
             if x[0] == "labarg":
-                labelled = True
                 c = self.compile(x[2], fs, scope)
                 cargs.append((lambda c, n, o: (lambda fr: Lab(n, c(fr), o)))(c, x[1], x[3]))
             else:
@@ -967,7 +965,6 @@ class Interp:
         if n == 3:
             a0, a1, a2 = cargs
             return lambda fr: apply(f(fr), [a0(fr), a1(fr), a2(fr)])
-        del labelled
         return lambda fr: apply(f(fr), [c(fr) for c in cargs])
 
     def c_if(self, e, fs, scope):
@@ -1025,7 +1022,7 @@ class Interp:
         cs = [self.compile(x, fs, scope, name=pat[1] if pat[0] == "pvar" else None) for pat, x in binds]
         pms = [self.compile_pat(pat, fs) for pat, _ in binds]
         cbody = self.compile(body, fs, scope)
-        fs.names = saved_restore(fs.names, saved)
+        fs.names = dict(saved)  # names the construct introduced go out of scope (slots stay theirs)
         if len(binds) == 1 and type(pms[0]) is int:
             i, c = pms[0], cs[0]
 
@@ -1088,7 +1085,7 @@ class Interp:
             pm = self.compile_pat_fn(pat, fs)
             g = self.compile(guard, fs, scope) if guard is not None else None
             b = self.compile(body, fs, scope)
-            fs.names = saved_restore(fs.names, saved)
+            fs.names = dict(saved)  # names the construct introduced go out of scope (slots stay theirs)
             out.append((pm, g, b))
         return out
 
@@ -1126,7 +1123,7 @@ class Interp:
         saved = dict(fs.names)
         i = fs.new_slot(var)
         cbody = self.compile(body, fs, scope)
-        fs.names = saved_restore(fs.names, saved)
+        fs.names = dict(saved)  # names the construct introduced go out of scope (slots stay theirs)
         if up:
             def for_up(fr):
                 lo, hi = ca(fr), cb(fr)
@@ -1238,6 +1235,3 @@ class Interp:
         return assert_
 
 
-def saved_restore(current, saved):
-    """Leave a binding construct: names it introduced go out of scope (their slots stay theirs)."""
-    return dict(saved)

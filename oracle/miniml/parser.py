@@ -718,7 +718,7 @@ class Parser:
             self.expect("in")
             return ("let", rec, binds, self.parse_seq())
         if self.accept("if"):
-            c = self.parse_seq_noif()
+            c = self.parse_seq()
             self.expect("then")
             a = self.parse_expr()
             b = self.parse_expr() if self.accept("else") else None
@@ -740,9 +740,6 @@ class Parser:
             self.expect("->")
             return ("fun", params, self.parse_seq())
         self.err("expression expected (%s)" % t.val)
-
-    def parse_seq_noif(self):
-        return self.parse_seq()
 
     def parse_arms(self):
         self.accept("|")

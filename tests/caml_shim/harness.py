@@ -26,13 +26,10 @@ def build():
 
 def externals():
     """{ocaml name: (arity, native primitive, bytecode primitive or None)} from ocaml/nbk.ml."""
-    sys.path.insert(0, ROOT)
-    from oracle.miniml.parser import Parser
-    src = open(os.path.join(ROOT, "ocaml", "nbk.ml")).read()
-    p = Parser(src, "nbk.ml")
-    out = {}
-    # the parser skips types; count the arrows of each `external` by hand
     import re
+    src = open(os.path.join(ROOT, "ocaml", "nbk.ml")).read()
+    out = {}
+    # arity = the arrows of the declared type outside parentheses
     code = re.sub(r"\(\*.*?\*\)", " ", src, flags=re.S)
     for m in re.finditer(r"external\s+(\w+)\s*:\s*(.*?)=\s*((?:\"\w+\"\s*)+)", code, flags=re.S):
         name, ty, prims = m.group(1), m.group(2), re.findall(r'"(\w+)"', m.group(3))
@@ -43,7 +40,6 @@ def externals():
             if ch == "-" and ty[k:k + 2] == "->" and depth == 0:
                 arrows += 1
         out[name] = (arrows, prims[-1], prims[0] if len(prims) == 2 else None)
-    del p
     return out
 
 
