@@ -2,7 +2,7 @@
 
 Nothing here can compile OCaml, and the reference tree does not travel to the GPU box, so the
 maintainer-side modules (Hermite_gpu, Omelyan_gpu, Leapfrog_gpu, Advancer_gpu, Energy_gpu,
-Analysis_gpu) are run the only way this image allows: by the interpreter oracle/miniml, next to
+Analysis_gpu, Dfloat_hermite_gpu) are run the only way this image allows: by the interpreter oracle/miniml, next to
 the UNMODIFIED reference modules they replace, with every `external` of ocaml/nbk.ml bound to a
 Python stand-in that does what include/nbk.h says the C entry point does.  The stand-ins are
 built from the reference's own functions (Base.grad_v, Leapfrog.kick, A.interact_bodies,
@@ -45,19 +45,22 @@ class World:
     """An interpreter with the reference, ocaml/ and the stand-ins for ocaml/nbk.ml's externals."""
 
     def __init__(self, hermite_resident_max=0, adv_range_max=0, lf_subsystem_max=0):
-        it = self.it = Interp(search_path=[REF, os.path.join(ROOT, "ocaml")],
+        it = self.it = Interp(search_path=[REF, os.path.join(ROOT, "ocaml"),
+                                           os.path.join(ROOT, "oracle", "ref_fixtures", "diff_restated")],
                               stdout=open(os.devnull, "w"), stderr=open(os.devnull, "w"))
         self.limits = dict(hermite_resident_max=hermite_resident_max, adv_range_max=adv_range_max,
                            lf_subsystem_max=lf_subsystem_max)
         self.calls = {}
-        for f in ("base", "hermite", "leapfrog", "advancer", "omelyan_advancer", "energy", "analysis"):
+        for f in ("base", "hermite", "leapfrog", "advancer", "omelyan_advancer", "energy", "analysis",
+                  "dFloat", "dFloat_advancer", "dFloat_hermite"):
             it.load_file(os.path.join(REF, f + ".ml"))
         self.An = it.load_source("module An = Analysis.Make(Advancer.A)", "AnHolder").mods["An"]
         self.register()
         for f in ("nbk", "hermite_gpu", "omelyan_gpu", "leapfrog_gpu", "advancer_gpu", "energy_gpu",
-                  "analysis_gpu"):
+                  "analysis_gpu", "dfloat_hermite_gpu"):
             it.load_file(os.path.join(ROOT, "ocaml", f + ".ml"))
-        assert it.missing <= {"input_value"}, it.missing   # Analysis.load_state(s): not used here
+        # Analysis.load_state(s) and the stale half of dFloat_advancer.ml: not used here
+        assert it.missing <= {"input_value", "zero"}, it.missing
 
     # -- access to interpreted values
     def fn(self, path):
@@ -371,6 +374,81 @@ class World:
                 dv[3 * (i - t0):3 * (i - t0) + 3] = acc
             return UNIT
 
+        # ---- dual-number sums (nbk_grad_v_dgrad_v_sum_tangent / _predicted_tangent): K directions
+        # through the reference's DFloatBase / DFloat_hermite, one direction at a time
+        def D(v, d):
+            return Ctor("D", (v, d))
+
+        def dual3(vals, tans, i):
+            return [D(vals[3 * i + c], tans[3 * i + c]) for c in range(3)]
+
+        def parts(x):
+            return (x.arg, 0.0) if x.name == "C" else x.arg
+
+        @ext(["nbk_ml_tangent", "nbk_ml_tangent_bc"], 11)
+        def _tangent(ctx, m, q, p, K, q_tan, p_tan, eps2, rng, gt, dgt):
+            t0, t1, s0, s1 = rng
+            n, nt_ = len(m), t1 - t0
+            gvd = self.fn("DFloat_advancer.DFloatBase.grad_v_dgrad_v")
+            for k in range(K):
+                qt, pt = q_tan[3 * n * k:3 * n * (k + 1)], p_tan[3 * n * k:3 * n * (k + 1)]
+                for i in range(t0, t1):
+                    a, b = [0.0] * 3, [0.0] * 3
+                    for j in range(s0, s1):
+                        if j == i:
+                            continue
+                        gv, dgv = [Ctor("C", 0.0)] * 3, [Ctor("C", 0.0)] * 3
+                        call(gvd, Ctor("C", m[i]), dual3(q, qt, i), dual3(p, pt, i),
+                             Ctor("C", m[j]), dual3(q, qt, j), dual3(p, pt, j), gv, dgv)
+                        for c in range(3):
+                            a[c] += parts(gv[c])[1]
+                            b[c] += parts(dgv[c])[1]
+                    o = 3 * nt_ * k + 3 * (i - t0)
+                    gt[o:o + 3], dgt[o:o + 3] = a, b
+            return UNIT
+
+        @ext(["nbk_ml_predicted_tangent", "nbk_ml_predicted_tangent_bc"], 9)
+        def _predicted_tangent(ctx, st_, K, tans, nt, nt_tan, eps2, rng, out):
+            t, m, q, p, f, df = st_
+            t_tan, q_tan, p_tan, f_tan, df_tan = tans
+            g, dg, gt, dgt = out
+            t0, t1, s0, s1 = rng
+            n = len(m)
+            predq = self.fn("DFloat_hermite.predict_position_into")
+            predp = self.fn("DFloat_hermite.predict_momentum_into")
+            gvd = self.fn("DFloat_advancer.DFloatBase.grad_v_dgrad_v")
+            C0 = Ctor("C", 0.0)
+            for k in range(K):
+                def body(i):
+                    sl3 = slice(3 * n * k, 3 * n * (k + 1))
+                    return Record(dict(id=i, t=D(t[i], t_tan[n * k + i]), m=Ctor("C", m[i]),
+                                       q=dual3(q, q_tan[sl3], i), p=dual3(p, p_tan[sl3], i), h=C0,
+                                       f=dual3(f, f_tan[sl3], i), df=dual3(df, df_tan[sl3], i)))
+                ntd = D(nt, nt_tan[k])
+                for i in range(t0, t1):
+                    bi = body(i)
+                    qp, pp = call(predq, [C0] * 3, bi, ntd), call(predp, [C0] * 3, bi, ntd)
+                    av, bv, at, bt = [0.0] * 3, [0.0] * 3, [0.0] * 3, [0.0] * 3
+                    for j in range(s0, s1):
+                        if j == i:
+                            continue
+                        bj = body(j)
+                        gv, dgv = [C0] * 3, [C0] * 3
+                        call(gvd, bi.f["m"], qp, pp, bj.f["m"], call(predq, [C0] * 3, bj, ntd),
+                             call(predp, [C0] * 3, bj, ntd), gv, dgv)
+                        for c in range(3):
+                            av[c] += parts(gv[c])[0]
+                            bv[c] += parts(dgv[c])[0]
+                            at[c] += parts(gv[c])[1]
+                            bt[c] += parts(dgv[c])[1]
+                    nt_ = t1 - t0
+                    o = 3 * nt_ * k + 3 * (i - t0)
+                    gt[o:o + 3], dgt[o:o + 3] = at, bt
+                    if k == 0:
+                        g[3 * (i - t0):3 * (i - t0) + 3] = av
+                        dg[3 * (i - t0):3 * (i - t0) + 3] = bv
+            return UNIT
+
         # ---- Analysis: binaries scan / list and the E-L diagnostics of the resident OA rows
         def abody(m, q, p, i):
             return call(A("make_body_id"), i, 0.0, m[i], q[3 * i:3 * i + 3], p[3 * i:3 * i + 3])
@@ -597,3 +675,65 @@ module AG = Analysis_gpu.Make (Advancer.A)
     assert (ident(r1), ident(r2)) == (ident(g1), ident(g2))
     assert call(mods["AG"].vals["bodies_to_el_phase_space"][0], ab) == \
         call(mods["AR"].vals["bodies_to_el_phase_space"][0], ab)
+
+
+def test_dual_number_hermite_loops(world):
+    """Dfloat_hermite_gpu: the two pair loops of dFloat_hermite.ml for K directions at once, beside
+    the reference's own DFloat_hermite.start_bs / advance_body run one direction at a time over
+    the restated Diff library (oracle/ref_fixtures/diff_restated)."""
+    import random
+    w = world
+    w.set_eps2(0.0)
+    w.fn("DFloat_advancer.DFloatBase.eps2").f["contents"] = Ctor("C", 0.0)
+    n, K = 6, 3
+    small = bodies("plummer_n16_std_seed20241.txt", n)
+    rnd = random.Random(7)
+    dq = [[rnd.uniform(-1, 1) for _ in range(3 * n)] for _ in range(K)]
+    dp = [[rnd.uniform(-1, 1) for _ in range(3 * n)] for _ in range(K)]
+
+    def D(v, d):
+        return Ctor("D", (v, d))
+
+    def val(x):
+        return x.arg if x.name == "C" else x.arg[0]
+
+    def tan(x):
+        return 0.0 if x.name == "C" else x.arg[1]
+    flat = lambda rows: [x for r in rows for x in r]  # noqa: E731
+    m = [b[0] for b in small]
+    q, p = flat(b[1] for b in small), flat(b[2] for b in small)
+    zeros = lambda k: [0.0] * k  # noqa: E731
+    state = Record(dict(n=n, k=K, t=zeros(n), m=m, q=q, p=p, f=zeros(3 * n), df=zeros(3 * n),
+                        t_tan=zeros(K * n), q_tan=flat(dq), p_tan=flat(dp), f_tan=zeros(3 * n * K),
+                        df_tan=zeros(3 * n * K)))
+    w.run("Dfloat_hermite_gpu.start_forces", state)
+    started = []
+    for k in range(K):
+        dbs = [Record(dict(id=i + 1, t=Ctor("C", 0.0), m=Ctor("C", m[i]),
+                           q=[D(q[3 * i + c], dq[k][3 * i + c]) for c in range(3)],
+                           p=[D(p[3 * i + c], dp[k][3 * i + c]) for c in range(3)], h=Ctor("C", -1.0),
+                           f=[Ctor("C", 0.0)] * 3, df=[Ctor("C", 0.0)] * 3)) for i in range(n)]
+        out = to_list(w.run("DFloat_hermite.start_bs", Ctor("C", 1e-2), from_list(dbs)))
+        started.append(out)
+        for i, b in enumerate(out):
+            for c in range(3):
+                fv, ft = state.f["f"][3 * i + c], state.f["f_tan"][3 * n * k + 3 * i + c]
+                assert abs(fv - val(b.f["f"][c])) <= 1e-13 * abs(fv)
+                assert abs(ft - tan(b.f["f"][c])) <= 1e-12 * max(abs(ft), 1e-3)
+                dv, dt_ = state.f["df"][3 * i + c], state.f["df_tan"][3 * n * k + 3 * i + c]
+                assert abs(dv - val(b.f["df"][c])) <= 1e-13 * abs(dv)
+                assert abs(dt_ - tan(b.f["df"][c])) <= 1e-12 * max(abs(dt_), 1e-3)
+    # advance_body of body 2 to a dual time: fp, dfp and their tangents
+    nt, nt_tan = 1.0 / 128, [0.3, -0.2, 0.1]
+    fp, dfp, fpt, dfpt = w.run("Dfloat_hermite_gpu.force_on_predicted", state, 2, nt, nt_tan)
+    for k in range(K):
+        bs = started[k]
+        # {b with h = nt - t} so that next_time b = (nt, nt_tan): the reference's own advance_body
+        b = Record(dict(bs[2].f, h=D(nt, nt_tan[k])))
+        nb = w.run("DFloat_hermite.advance_body", Ctor("C", 1e-2), b,
+                   from_list([x for j, x in enumerate(bs) if j != 2]))
+        for c in range(3):
+            assert abs(fp[c] - val(nb.f["f"][c])) <= 1e-13 * abs(fp[c])
+            assert abs(dfp[c] - val(nb.f["df"][c])) <= 1e-12 * abs(dfp[c])
+            assert abs(fpt[3 * k + c] - tan(nb.f["f"][c])) <= 1e-11 * max(abs(fpt[3 * k + c]), 1e-3)
+            assert abs(dfpt[3 * k + c] - tan(nb.f["df"][c])) <= 1e-11 * max(abs(dfpt[3 * k + c]), 1e-3)
