@@ -18,7 +18,7 @@
  * .MISSING_LARGE_BLOBS) and no OCaml toolchain exists in the build image.  The restatement is
  * pinned against the reference's OWN SOURCE TEXT instead: oracle/miniml interprets the unmodified
  * .ml files under /root/reference, oracle/ref_fixtures/gen*.ml drive them over committed seeded
- * inputs, and this oracle reproduces all 6994 values they write BIT FOR BIT
+ * inputs, and this oracle reproduces all 8448 values they write BIT FOR BIT
  * (oracle/ref_fixtures/ref_miniml/, tests/test_ref_fixtures.py).  That is a pin through an
  * interpreter written for this repository (oracle/miniml/README.md says what it guarantees),
  * not through an ocamlopt binary: oracle/ref_fixtures/Makefile prepares that run for the first

@@ -850,10 +850,16 @@ class Parser:
                 return ("labarg", name, self.parse_arg(), t.val == "?")
             return ("labarg", name, ("var", name), t.val == "?")
         if t.kind == "op" and t.val[0] in "!~?" and t.val not in ("!=", "~", "?"):
-            self.k += 1
-            e = self.parse_arg()
-            return ("app", ("var", t.val), [e])
+            # prefix symbols bind tighter than . and .( : `!r.(0)` is `(!r).(0)`
+            return self.parse_postfix(self.parse_prefixed())
         return self.parse_postfix(self.parse_atom())
+
+    def parse_prefixed(self):
+        t = self.tok
+        if t.kind == "op" and t.val[0] in "!~?" and t.val not in ("!=", "~", "?"):
+            self.k += 1
+            return ("app", ("var", t.val), [self.parse_prefixed()])
+        return self.parse_atom()
 
     def parse_postfix(self, e):
         while self.at("."):

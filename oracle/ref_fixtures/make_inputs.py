@@ -238,13 +238,44 @@ def dfloat(small):
     return o.text()
 
 
+def unit(bodies):
+    """The oracle's answers to gen_unit.ml: four quarter-time-unit advances of Hermite and
+    Leapfrog, energy and state after each."""
+    o = Out()
+    m, q, p = bodies
+    n = len(m)
+    h = O.HermiteState(m, q, p)
+    o.emit("he_energy", 0, 0, 0, O.energy(h.m, h.q, h.p, 0.0))
+    for k in range(1, 5):
+        h = O.hermite_advance(h, 0.25, 1e-4)
+        o.emit("he_energy", k, 0, 0, O.energy(h.m, h.q, h.p, 0.0))
+        o.emit("he_nsteps", k, 0, 0, float(h.nsteps))
+        for i in range(n):
+            o.emit("he_t", k, i, 0, h.t[i])
+            o.emit3("he_q", k, i, h.q[i])
+            o.emit3("he_p", k, i, h.p[i])
+    s = O.LeapfrogState(m, q, p)
+    o.emit("lf_energy", 0, 0, 0, O.energy(s.m, s.q, s.v * s.m[:, None], 0.0))
+    for k in range(1, 5):
+        s = O.leapfrog_advance(s, 0.25, 2e-3)
+        o.emit("lf_energy", k, 0, 0, O.energy(s.m, s.q, s.v * s.m[:, None], 0.0))
+        for r in range(n):
+            o.emit("lf_id", k, r, 0, float(s.id[r] - 1))
+            o.emit("lf_t", k, r, 0, s.t[r])
+            o.emit3("lf_q", k, r, s.q[r])
+            o.emit3("lf_v", k, r, s.v[r])
+    return o.text()
+
+
 def expected(inputs_dir=None):
     """{file name: text} of the oracle's outputs for the committed inputs."""
     d = inputs_dir or os.path.join(HERE, "inputs")
     big = read_bodies(os.path.join(d, "plummer_n64_seed20240.txt"))
     small = read_bodies(os.path.join(d, "plummer_n16_std_seed20241.txt"))
+    mid = read_bodies(os.path.join(d, "plummer_n24_std_seed20242.txt"))
     return {"pairs.hex": pairs(*big), "sums.hex": sums(*big), "traj.hex": traj(*small),
-            "wide.hex": wide(big, small), "ics.hex": ics(big), "dfloat.hex": dfloat(small)}
+            "wide.hex": wide(big, small), "ics.hex": ics(big), "dfloat.hex": dfloat(small),
+            "unit.hex": unit(mid)}
 
 
 if __name__ == "__main__":
@@ -253,6 +284,8 @@ if __name__ == "__main__":
     write_bodies(os.path.join(HERE, "inputs", "plummer_n64_seed20240.txt"), *O.make_plummer(64, 20240))
     write_bodies(os.path.join(HERE, "inputs", "plummer_n16_std_seed20241.txt"),
                  *O.rescale_to_standard_units(*O.make_plummer(16, 20241)))
+    write_bodies(os.path.join(HERE, "inputs", "plummer_n24_std_seed20242.txt"),
+                 *O.rescale_to_standard_units(*O.make_plummer(24, 20242)))
     for name, text in expected().items():
         open(os.path.join(HERE, "expected", name), "w").write(text)
     print("wrote inputs/ and expected/")

@@ -29,6 +29,7 @@ GENERATORS = {
     "gen_wide": ("wide.hex",),
     "gen_ics": ("ics.hex",),
     "gen_dfloat": ("dfloat.hex",),
+    "gen_unit": ("unit.hex",),
 }
 
 

@@ -65,6 +65,9 @@ def test_unary_minus_and_prefix_operators():
     assert ev("let v = (-1.0)") == -1.0
     assert ev("let f x = x + 1 let v = f 2 - 1") == 2    # application binds tighter than -
     assert ev("let r = ref 5 let v = !r * 2") == 10
+    # prefix symbols bind tighter than field / array access: !a.(1) is (!a).(1)
+    assert ev("let a = ref [|1; 2|] let v = !a.(1)") == 2
+    assert ev("type t = {x : int} let r = ref {x = 7} let v = !r.x") == 7
     assert ev("let v = 7 - -2") == 9
 
 

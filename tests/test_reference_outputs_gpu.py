@@ -17,6 +17,8 @@ made directly, value by value, with nothing of this repository's CPU code in bet
              <= 1e-12), bodies_to_el_phase_space; Ics.adjust_frame / rescale_to_standard_units
   tangents   DFloat_pushforward.jacobian_advance, every entry of the 6n x 6n Jacobian, and
              omega_pushforward
+  one N-body time unit   the energy-error trajectories of Hermite.advance and Leapfrog.advance at
+             every quarter of a time unit (the north star's "must agree over 1 N-body time unit")
 """
 import os
 import struct
@@ -245,3 +247,45 @@ def test_dual_number_jacobian(ctx, small):
         want = np.array([[s.v[(key + "_jac", i, j, 0)] for j in range(6 * n)] for i in range(6 * n)])
         assert np.abs(jac - want).max() <= 1e-9 * np.abs(want).max(), key
         assert abs(nbh.omega_pushforward(jac) - s.scalar(key + "_omega")) <= 1e-9
+
+
+def test_energy_error_trajectories_over_one_time_unit(ctx):
+    """The reference's own Hermite (2457 steps) and adaptive Leapfrog runs over one N-body time unit
+    (unit.hex: four advances of 0.25, 24-body Plummer sphere in standard units) beside the GPU
+    path: energy error after every quarter, step counts, states."""
+    m, q, p = read_bodies("plummer_n24_std_seed20242.txt")
+    u = Sheet("unit.hex")
+    n = len(m)
+    e0 = u.scalar("he_energy", 0)
+    assert abs(e0 + 0.25) < 1e-12
+    h = nbh.HermiteState(m, q, p)
+    for k in range(1, 5):
+        h = nbh.hermite_advance(ctx, h, 0.25, 1e-4)
+        de_ref = abs((u.scalar("he_energy", k) - e0) / e0)
+        ke, pe = ctx.energy(h.m, h.q, h.p, 0.0)
+        de_gpu = abs((ke + pe - e0) / e0)
+        assert h.nsteps == int(u.scalar("he_nsteps", k)), k          # the same schedule
+        assert abs(de_gpu - de_ref) <= 1e-3 * de_ref + 1e-13, (k, de_gpu, de_ref)
+        q_ref = np.array([u.vec("he_q", k, i) for i in range(n)])
+        p_ref = np.array([u.vec("he_p", k, i) for i in range(n)])
+        assert np.array_equal(h.t, np.array([u.scalar("he_t", k, i) for i in range(n)]))
+        assert rel(h.q, q_ref) <= 1e-9 and rel(h.p, p_ref) <= 1e-8, k
+    assert 1e-10 < de_ref < 1e-6           # a real, resolved energy error, the same on both sides
+    # adaptive leapfrog: positions follow the reference's to rounding while the block schedule is
+    # the same; a dt_max within 1e-3 of a block boundary can flip a decision (SURVEY.md 3.3), after
+    # which the runs agree in the energy error rather than step for step
+    s = nbh.LeapfrogState(m, q, p)
+    for k in range(1, 5):
+        s = nbh.leapfrog_advance(ctx, s, 0.25, 2e-3)
+        de_ref = abs((u.scalar("lf_energy", k) - e0) / e0)
+        ke, pe = ctx.energy(s.m, s.q, s.v * s.m[:, None], 0.0)
+        de_gpu = abs((ke + pe - e0) / e0)
+        assert np.all(s.t == 0.25 * k)
+        assert 0.5 < (de_gpu + 1e-12) / (de_ref + 1e-12) < 2.0, (k, de_gpu, de_ref)
+        ids_ref = np.array([u.scalar("lf_id", k, r) for r in range(n)]).astype(int)
+        q_ref = np.array([u.vec("lf_q", k, r) for r in range(n)])
+        order = np.argsort(ids_ref)
+        mine = np.argsort(s.id - 1)
+        print(f"leapfrog t = {0.25 * k}: dE gpu {de_gpu:.3e} ref {de_ref:.3e}, same order "
+              f"{np.array_equal(s.id - 1, ids_ref)}, max |dq| {np.abs(s.q[mine] - q_ref[order]).max():.2e}")
+        assert np.abs(s.q[mine] - q_ref[order]).max() <= 1e-4
