@@ -58,6 +58,45 @@ def test_float_precedence_and_association():
     assert bits(ev("let v = 0.5*.0.3/.0.7*.1.3")) == bits(((0.5 * 0.3) / 0.7) * 1.3)
 
 
+def test_arithmetic_grammar_against_an_independent_parser():
+    """+ - * / ** and unary minus have the same precedence and associativity in OCaml and in
+    Python, so Python's own parser is an independent judge: 400 random expressions, spelled with
+    the dotted operators for miniml and the plain ones for `eval`, must agree bit for bit."""
+    import random
+    rnd = random.Random(12345)
+
+    def atom():
+        return repr(round(rnd.uniform(0.1, 9.0), rnd.randint(1, 6)))
+
+    def expr(depth):
+        r = rnd.random()
+        if depth == 0 or r < 0.2:
+            return atom()
+        if r < 0.3:
+            return "(" + expr(depth - 1) + ")"
+        if r < 0.4:
+            return "- " + (atom() if rnd.random() < 0.5 else "(" + expr(depth - 1) + ")")
+        if r < 0.5:
+            return atom() + " ** " + atom()
+        return expr(depth - 1) + " " + rnd.choice("+-*/") + " " + expr(depth - 1)
+    checked = 0
+    while checked < 400:
+        e = expr(5)
+        try:
+            want = eval(e)
+        except (ZeroDivisionError, OverflowError):
+            continue
+        if isinstance(want, complex):
+            continue
+        ocaml = e.replace("**", "POW")
+        for op in "+-*/":
+            ocaml = ocaml.replace(" " + op + " ", " " + op + ". ")
+        ocaml = ocaml.replace("- ", "-. ").replace("-. . ", "-. ").replace("POW", "**")
+        got = ev("let v = " + ocaml)
+        assert bits(got) == bits(float(want)), (e, ocaml, got, want)
+        checked += 1
+
+
 def test_unary_minus_and_prefix_operators():
     assert ev("let v = -. 2.0 ** 2.0") == -4.0           # -(2 ** 2)
     assert ev("let x = 3.0 let v = -. x *. 2.0") == -6.0
