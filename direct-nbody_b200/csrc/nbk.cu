@@ -2423,9 +2423,32 @@ int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, dou
     const size_t csmem = (size_t)per * HRES_STRIDE * sizeof(double);
     CK(cudaFuncSetAttribute(hermite_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)csmem));
-    hermite_cluster_kernel<<<HCL_CTAS, HCL_THREADS, csmem, ctx->stream>>>(
-        (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
-        (long long *)ctx->d_scalar.p);
+    if (ctx->hermite_spec) {  // software-pipelined (default); NBK_HERMITE_SPEC=0: the plain loop
+      CK(cudaFuncSetAttribute(hermite_cluster_spec_kernel,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      static const bool want_prof = getenv("NBK_HERMITE_PROF") != nullptr;
+      long long *d_prof = nullptr;
+      if (want_prof) {
+        TRY(reserve(ctx, ctx->d_hgrid, 8 * sizeof(long long)));
+        d_prof = (long long *)ctx->d_hgrid.p;
+        CK(cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), ctx->stream));
+      }
+      hermite_cluster_spec_kernel<<<HCL_CTAS, HCLS_THREADS, csmem, ctx->stream>>>(
+          (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+          (long long *)ctx->d_scalar.p, d_prof);
+      if (want_prof) {
+        long long hp[8];
+        CK(cudaMemcpyAsync(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(sync(ctx));
+        fprintf(stderr, "hermite cluster prof, CTA 0 (cycles): top %lld | corrector %lld (%lld steps owned) | "
+                        "search+post %lld | sums+post %lld | barrier %lld | pick %lld\n",
+                hp[0], hp[1], hp[6], hp[2], hp[3], hp[4], hp[5]);
+      }
+    } else {
+      hermite_cluster_kernel<<<HCL_CTAS, HCL_THREADS, csmem, ctx->stream>>>(
+          (double *)ctx->d_hstate.p, n, stop_time, eta, eps2, (long long)max_steps,
+          (long long *)ctx->d_scalar.p);
+    }
     CK(cudaGetLastError());
     ctx->launches++;
     CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,

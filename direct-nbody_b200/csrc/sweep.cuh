@@ -2156,6 +2156,367 @@ __global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCL_THREADS, 
   if (rank == 0 && tid == 0) *nsteps_out = steps;
 }
 
+// ---- the cluster loop, software-pipelined ------------------------------------------------------
+// hermite_cluster_kernel serialises search -> barrier -> sum -> barrier -> corrector, and the
+// corrector (one thread of one CTA, ~1900 cycles) keeps eight SMs waiting.  Here, as in
+// hermite_resident_spec_kernel, a step k with target i_k already knows the NEXT target r_k (the
+// earliest body other than i_k), so three things run side by side and ONE cluster barrier ends
+// the step:
+//   thread 0 of i_k's owner   sums of step k (the eight partials + the one interaction with the
+//                             body stepped before), corrector, new keys; the new record goes to
+//                             all CTAs (DSMEM)
+//   warp 1 of every CTA       the CTA's two earliest bodies other than i_k (cached class top-2,
+//                             integer keys) with their records -> all CTAs (DSMEM)
+//   warps 2.. of every CTA    predict the local bodies to r_k's time, local part of the
+//                             1 x (N-2) interactions without i_k, six partials -> r_k's owner
+//   cluster barrier
+//   everybody                 the two smallest keys among the sixteen candidates and the re-inserted
+//                             i_k: the smallest is the next target (r_k, or i_k again - ties go
+//                             to the re-inserted body; then that step is done the plain way, all
+//                             warps, one more barrier), the second smallest the target after it.
+constexpr int HCLS_THREADS = 320;
+
+__global__ void __cluster_dims__(HCL_CTAS, 1, 1) __launch_bounds__(HCLS_THREADS, 1)
+    hermite_cluster_spec_kernel(double *__restrict__ state, int n, double stop_time, double eta,
+                                double eps2, long long max_steps,
+                                long long *__restrict__ nsteps_out,
+                                long long *__restrict__ prof) {
+  // prof (NBK_HERMITE_PROF=1, rank 0 only): cycles [0] loop top + plain path, [1] thread 0 corrector
+  // (when rank 0 owns the target), [2] warp 1 search + post, [3] warp 2 local sums + post,
+  // [4] barrier as seen by thread 0, [5] pick + decision, [6] steps owned by rank 0
+  long long pc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long c0 = prof ? clock64() : 0, c1;
+#define HCLS_TICK(slot)            \
+  if (prof) {                      \
+    c1 = clock64();                \
+    pc[slot] += c1 - c0;           \
+    c0 = c1;                       \
+  }
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  constexpr int T = HCLS_THREADS, NW = T / 32, NF = NW - 2;
+  constexpr int NONE = 0x7fffffff;
+  constexpr int NCAND = 2 * HCL_CTAS + 1;  // two per CTA and the re-inserted body
+  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slots 15 / 16 = the integer keys
+  // every table is double-buffered by step parity: a step rewrites what was read two steps ago.
+  // A candidate row: key1, key2 (bit patterns), -, record[16], pad.
+  __shared__ double cand[2][NCAND][HCL_CAND];  // row 2 c + s: CTA c's s-th; row 16: the stepped body
+  __shared__ double part[2][HCL_CTAS][6];      // partial sums, at the target's owner
+  __shared__ double tgtp[2][8];                // the next target's predicted state (local copy)
+  __shared__ double red[NW][6];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + HCL_CTAS - 1) / HCL_CTAS;
+  const int j_lo = min(rank * per, n), j_hi = min(j_lo + per, n), nloc = j_hi - j_lo;
+  SweepParams P;
+  P.eps2 = eps2;
+  auto K1 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 16);
+  };
+  auto K2 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 15);
+  };
+  for (int l = tid; l < nloc; l += T) {
+    double *r = rec + l * HRES_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r[c] = state[(size_t)(j_lo + l) * HB + c];
+    const double st = r[15];
+    K1(l) = hkey_of_double(r[0] + r[14]);
+    K2(l) = hkey_tie(st, j_lo + l);
+  }
+  __syncthreads();
+  auto less = [](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                 unsigned long long b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+  auto key_of = [](const double *c, int w) {
+    return (unsigned long long)__double_as_longlong(c[w]);
+  };
+  auto idx_of = [](unsigned long long k1, unsigned long long k2) {
+    return k1 == HKEY_NONE ? NONE : (int)(k2 & ((1u << HKEY_IDX_BITS) - 1));
+  };
+  auto keep2 = [&](unsigned long long k1, unsigned long long k2, unsigned long long &a1,
+                   unsigned long long &a2, unsigned long long &b1, unsigned long long &b2) {
+    const bool lt_a = less(k1, k2, a1, a2), lt_b = less(k1, k2, b1, b2);
+    b1 = lt_a ? a1 : (lt_b ? k1 : b1);
+    b2 = lt_a ? a2 : (lt_b ? k2 : b2);
+    a1 = lt_a ? k1 : a1;
+    a2 = lt_a ? k2 : a2;
+  };
+  // warp-wide: the two smallest of the lanes' (a, b) pairs; every lane gets the result
+  auto combine2 = [&](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                      unsigned long long b2, unsigned long long (&o)[2][2]) {
+    unsigned long long g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    const bool mine = (a1 == g1 && a2 == g2);  // keys are unique (the tie key holds the index)
+    unsigned long long s1 = mine ? b1 : a1, s2 = mine ? b2 : a2;
+    warp_min_pair(s1, s2);
+    o[0][0] = g1, o[0][1] = g2, o[1][0] = s1, o[1][1] = s2;
+  };
+  // warp 1: this CTA's two earliest bodies other than the local body `hide` -> rows [2 rank],
+  // [2 rank + 1] of every CTA's cand[pb].  Up to 384 local bodies: a plain walk over the keys
+  // (nloc / 32 per lane, branch-free, ~100 cycles each) and one warp-wide top-2.  Beyond: lane g
+  // caches the two smallest keys of the local bodies g, g + 32, ... and a step re-examines only
+  // the class of the body stepped before (`changed`: its key changed, and it was hidden then) and
+  // the class of `hide` - three warp-wide top-2, ~560 cycles each (redux.sync costs ~70 cycles).
+  const bool cached = nloc > 384;
+  unsigned long long ca1 = HKEY_NONE, ca2 = HKEY_NONE, cb1 = HKEY_NONE, cb2 = HKEY_NONE;
+  auto rescan = [&](int g, int hide) {  // all lanes look at class g, lane g keeps the result
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    for (int l = g + 32 * lane; l < nloc; l += 32 * 32)
+      keep2(l == hide ? HKEY_NONE : K1(l), K2(l), a1, a2, b1, b2);
+    unsigned long long o[2][2];
+    combine2(a1, a2, b1, b2, o);
+    if (lane == g) ca1 = o[0][0], ca2 = o[0][1], cb1 = o[1][0], cb2 = o[1][1];
+  };
+  auto post_candidates = [&](int pb, int hide, int changed) {
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    if (cached) {
+      if (changed >= 0) rescan(changed & 31, hide);
+      if (hide >= 0 && (changed < 0 || (changed & 31) != (hide & 31))) rescan(hide & 31, hide);
+      a1 = ca1, a2 = ca2, b1 = cb1, b2 = cb2;
+    } else {
+#pragma unroll 4
+      for (int l = lane; l < nloc; l += 32) keep2(l == hide ? HKEY_NONE : K1(l), K2(l), a1, a2, b1, b2);
+    }
+    unsigned long long o[2][2];
+    combine2(a1, a2, b1, b2, o);
+    // 2 x 20 values, computed once, stored into all eight tables
+    for (int v = lane; v < 2 * HCL_CAND; v += 32) {
+      const int s = v / HCL_CAND, slot = v - s * HCL_CAND;
+      const int kl = o[s][0] == HKEY_NONE ? -1 : (int)(o[s][1] & ((1u << HKEY_IDX_BITS) - 1)) - j_lo;
+      double x = 0.0;
+      if (slot == 0) x = __longlong_as_double((long long)o[s][0]);
+      else if (slot == 1) x = __longlong_as_double((long long)o[s][1]);
+      else if (slot >= 3 && slot < 19 && kl >= 0) x = rec[kl * HRES_STRIDE + (slot - 3)];
+      const size_t at = ((size_t)pb * NCAND + 2 * rank + s) * HCL_CAND + slot;
+#pragma unroll
+      for (int dst = 0; dst < HCL_CTAS; ++dst) cluster.map_shared_rank(&cand[0][0][0], dst)[at] = x;
+    }
+  };
+  // every warp: the two smallest keys of cand[pb]'s rows (lane x looks at row x) -> row numbers
+  auto pick2 = [&](int pb, int nrows, int &row1, int &row2) {
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE;
+    if (lane < nrows) a1 = key_of(cand[pb][lane], 0), a2 = key_of(cand[pb][lane], 1);
+    unsigned long long g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    const bool mine = lane < nrows && a1 == g1 && a2 == g2 && g1 != HKEY_NONE;
+    unsigned long long s1 = mine ? HKEY_NONE : a1, s2 = mine ? HKEY_NONE : a2;
+    warp_min_pair(s1, s2);
+    const bool second = lane < nrows && !mine && a1 == s1 && a2 == s2 && s1 != HKEY_NONE;
+    const unsigned b1 = __ballot_sync(0xffffffffu, mine), b2 = __ballot_sync(0xffffffffu, second);
+    row1 = b1 ? __ffs(b1) - 1 : -1;
+    row2 = b2 ? __ffs(b2) - 1 : -1;
+  };
+  // warps [w0, NW): the local part of the six sums for target tg (global index itarget) at time nt,
+  // leaving out the local body `hide`; then one thread per component posts the CTA's partial into
+  // row [rank] of part[pb] at CTA `own`.  `sync` = a barrier of exactly those warps.
+  auto local_force = [&](int w0, int hide, int itarget, const OpGradVDGradV::Tgt &tg, double nt,
+                         int pb, int own, auto sync) {
+    const int nthr = (NW - w0) * 32, t0 = tid - w0 * 32;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = t0; l < nloc; l += nthr) {
+      if (l == hide) continue;
+      double mj, qj[3], vj[3];
+      hermite_predict_fast(rec + l * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, (j_lo + l) == itarget, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+    sync();
+    if (t0 < 6) {
+      double a = red[w0][t0];
+      for (int w = w0 + 1; w < NW; ++w) a += red[w][t0];
+      double *remote = cluster.map_shared_rank(&part[0][0][0], own);
+      remote[(pb * HCL_CTAS + rank) * 6 + t0] = a;
+    }
+  };
+  auto sync_all = [] { __syncthreads(); };
+  auto sync_force = [] { asm volatile("bar.sync 2, %0;" ::"r"(NF * 32) : "memory"); };
+
+  long long steps = 0, stamp = 0;
+  bool finishing = false;
+  // ---- the first two bodies of the schedule
+  if (warp == 1) {
+    if (cached) {
+#pragma unroll 4
+      for (int l = lane; l < nloc; l += 32) keep2(K1(l), K2(l), ca1, ca2, cb1, cb2);
+    }
+    post_candidates(1, -1, -1);
+  }
+  cluster.sync();
+  int row1, row2;
+  pick2(1, 2 * HCL_CTAS, row1, row2);
+  const double *cur = row1 >= 0 ? &cand[1][row1][0] : nullptr;  // the current target: keys, -, record
+  const double *nxt = row2 >= 0 ? &cand[1][row2][0] : nullptr;  // the target after it
+  int par = 0;      // buffer of this step's candidate table
+  int pb = 0;       // buffer of this step's partial sums / predicted target
+  bool have = false;
+  const double *prevrec = nullptr;  // the body stepped before (its new record), for the extra pair
+  int changed = -1;  // local index of the body stepped before (its key changed), -1 if not local
+  for (;;) {
+    if (cur == nullptr) break;  // every body finished (uniform over the cluster)
+    const unsigned long long itk1 = key_of(cur, 0);
+    const int it = idx_of(itk1, key_of(cur, 1)), owner = it / per;
+    if (!finishing) {
+      if (steps >= max_steps) break;
+      if (hkey_to_double(itk1) > stop_time) finishing = true;
+    }
+    const double *tr = cur + 3;
+    const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    const int it_loc = rank == owner ? it - j_lo : -1;
+    double mt = 0.0, qt[3] = {0, 0, 0}, vt[3] = {0, 0, 0};
+    if (!have) {
+      // the plain way: everybody sums its local part for `it`, one more cluster barrier
+      hermite_predict_fast(tr, nt, mt, qt, vt);
+      const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+      local_force(0, -1, it, tg, nt, pb, owner, sync_all);
+      cluster.sync();
+    } else if (tid == 0 && rank == owner) {
+      mt = tgtp[pb][0];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) qt[c] = tgtp[pb][1 + c], vt[c] = tgtp[pb][4 + c];
+    }
+    ++steps;
+    ++stamp;
+    const int r = nxt ? idx_of(key_of(nxt, 0), key_of(nxt, 1)) : NONE;
+    HCLS_TICK(0)
+    if (warp == 0) {
+      if (tid == 0 && rank == owner) {
+        // ---- corrector (hermite.ml:116-123), new time step (hermite.ml:87-93)
+        const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+        double extra[6] = {0, 0, 0, 0, 0, 0};
+        if (have) {  // the interaction the speculative sums left out: the body stepped last
+          double mj, qj[3], vj[3];
+          hermite_predict_fast(prevrec + 3, nt, mj, qj, vj);
+          const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                                  make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+          OpGradVDGradV::pair<false>(tg, extra, src, src, false, P);
+        }
+        double fp[3], dfp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double a = extra[c], d = extra[3 + c];
+          for (int q = 0; q < HCL_CTAS; ++q) {
+            a += part[pb][q][c];
+            d += part[pb][q][3 + c];
+          }
+          fp[c] = mt * a;
+          dfp[c] = mt * d;
+        }
+        double *wr = rec + it_loc * HRES_STRIDE;
+        const double m = mt;
+        double qn[3], pn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+          pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+          qn[c] = __dadd_rn(
+              __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+              __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+        }
+        const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+        const double rr = __dsqrt_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        const double fn = __dsqrt_rn(__dadd_rn(
+            __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+        double hn;
+        if (rr == 0.0) {
+          hn = __dmul_rn(h, 1.189207115002721);
+        } else {
+          const double x =
+              __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+          hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));
+        }
+        wr[0] = nt;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wr[2 + c] = qn[c];
+          wr[5 + c] = pn[c];
+          wr[8 + c] = fp[c];
+          wr[11 + c] = dfp[c];
+        }
+        wr[14] = hn;
+        K1(it_loc) = finishing ? HKEY_NONE : hkey_of_double(nt + hn);
+        K2(it_loc) = hkey_tie((double)stamp, it);
+      }
+      __syncwarp();
+      if (rank == owner && lane < 19) {
+        // the new keys and record -> row 16 of every CTA's candidate table
+        const double *wr = rec + it_loc * HRES_STRIDE;
+        double v = 0.0;
+        if (lane == 0) v = wr[16];
+        else if (lane == 1) v = wr[15];
+        else if (lane >= 3) v = wr[lane - 3];
+        for (int dst = 0; dst < HCL_CTAS; ++dst) {
+          double *remote = cluster.map_shared_rank(&cand[0][0][0], dst);
+          remote[((size_t)par * NCAND + 2 * HCL_CTAS) * HCL_CAND + lane] = v;
+        }
+      }
+      if (rank == owner) {
+        HCLS_TICK(1)
+        ++pc[6];
+      }
+    } else if (warp == 1) {
+      // ---- this CTA's two earliest bodies other than `it`
+      post_candidates(par, it_loc, changed);
+      HCLS_TICK(2)
+    } else if (r != NONE) {
+      // ---- the local part of the next target's sums, without `it`
+      const double *rr_ = nxt + 3;
+      const bool fin_r = finishing || hkey_to_double(key_of(nxt, 0)) > stop_time;
+      const double hr = fin_r ? __dsub_rn(stop_time, rr_[0]) : rr_[14];
+      const double ntr = __dadd_rn(rr_[0], hr);
+      double mr, qr[3], vr[3];
+      hermite_predict_fast(rr_, ntr, mr, qr, vr);
+      const OpGradVDGradV::Tgt tgr = {qr[0], qr[1], qr[2], vr[0], vr[1], vr[2]};
+      if (tid == 64) {
+        tgtp[pb ^ 1][0] = mr;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tgtp[pb ^ 1][1 + c] = qr[c], tgtp[pb ^ 1][4 + c] = vr[c];
+      }
+      local_force(2, it_loc, r, tgr, ntr, pb ^ 1, r / per, sync_force);
+      HCLS_TICK(3)
+    }
+    cluster.sync();
+    HCLS_TICK(4)
+    // ---- who is next, and who after that (uniform over the cluster): the two smallest keys among
+    // the sixteen candidates and the re-inserted body (row 16; all ones when it is finished)
+    pick2(par, NCAND, row1, row2);
+    changed = it_loc;
+    const bool again = row1 == 2 * HCL_CTAS;
+    prevrec = &cand[par][2 * HCL_CTAS][0];
+    cur = row1 >= 0 ? &cand[par][row1][0] : nullptr;
+    nxt = row2 >= 0 ? &cand[par][row2][0] : nullptr;
+    // the speculative sums are for r: usable iff r is indeed next
+    have = !again && cur != nullptr && idx_of(key_of(cur, 0), key_of(cur, 1)) == r;
+    if (have) pb ^= 1;
+    par ^= 1;
+    HCLS_TICK(5)
+  }
+  cluster.sync();  // nobody leaves while a peer may still write into its shared memory
+  for (int l = tid; l < nloc; l += T) {
+    double *rl = rec + l * HRES_STRIDE;
+    rl[15] = (double)(0x7ffffffffffull - (K2(l) >> HKEY_IDX_BITS));  // back to the stamp
+#pragma unroll
+    for (int c = 0; c < 16; ++c) state[(size_t)(j_lo + l) * HB + c] = rl[c];
+  }
+  if (rank == 0 && tid == 0) *nsteps_out = steps;
+  if (prof && rank == 0) {
+    if (tid == 0) prof[0] = pc[0], prof[1] = pc[1], prof[4] = pc[4], prof[5] = pc[5], prof[6] = pc[6];
+    if (tid == 32) prof[2] = pc[2];
+    if (tid == 64) prof[3] = pc[3];
+  }
+#undef HCLS_TICK
+}
+
 // ---- the same stepping loop on the WHOLE GRID (12288 < N <= HGR_MAX_N) --------------------------
 // One CTA per SM (cooperative launch), each keeping n / G bodies in its shared memory; what the
 // cluster variant passes through distributed shared memory goes through L2 here, with two grid

@@ -4,7 +4,7 @@
    [start_bs] (hermite.ml:148-169) is one all-pairs sweep.  [advance] (hermite.ml:180-189) keeps
    the Hermite.b array RESIDENT on the device: it is uploaded once, and
    - up to Nbk.hermite_resident_max () bodies the whole advance_bodies / finish_bs loop
-     (hermite.ml:132-143, 171-178) runs in ONE persistent kernel (2.0 - 4.1 us per step);
+     (hermite.ml:132-143, 171-178) runs in ONE persistent kernel (2.0 - 3.1 us per step);
    - beyond that the scheduler below steps single bodies with one launch per advance_body
      (Nbk.hermite_body_sum: the stepped body's new state rides along with the next call, 48 bytes
      come back) - no re-packing or re-upload of the N bodies per step. *)
