@@ -444,14 +444,15 @@ def _mirrored(oracle, half, seed):
 
 
 @pytest.mark.parametrize("n,threads", [(64, "0"), (100, "128"), (333, "0"), (777, "192"), (1024, "0"),
-                                       (1024, "512"), (1536, "0"), (1300, "1024")])
+                                       (1024, "512"), (1536, "0"), (1300, "1024"),
+                                       (1537, "0"), (3001, "0"), (6000, "0")])  # the last three: cluster
 def test_hermite_pipelined_loop_matches_plain_loop_and_oracle(oracle, monkeypatch, n, threads):
     """The single-CTA stepping loop is software-pipelined (corrector of step k beside the search
     and the force sum of step k+1, integer-key arg-min); NBK_HERMITE_SPEC=0 is the plain loop.
     Same schedule - same step count as each other and as the oracle - and the same state."""
     import nbk
     m, q, p = oracle.rescale_to_standard_units(*oracle.make_plummer(n, 20250 + n))
-    span = 0.01 if n > 512 else 0.03
+    span = 0.005 if n > 1536 else (0.01 if n > 512 else 0.03)
     if threads != "0":
         monkeypatch.setenv("NBK_HERMITE_THREADS", threads)
     with nbk.Context(0) as c1:
@@ -463,7 +464,7 @@ def test_hermite_pipelined_loop_matches_plain_loop_and_oracle(oracle, monkeypatc
         b2 = nbh.hermite_advance(c0, b, span, 1e-4, mode=2)
     c = oracle.hermite_advance(oracle.HermiteState(m, q, p), span, 1e-4)
     assert np.all(a.t == span) and np.array_equal(a.id, c.id)
-    assert abs(a.nsteps - b.nsteps) <= 2 and abs(a.nsteps - c.nsteps) <= 2 and a.nsteps > n
+    assert abs(a.nsteps - b.nsteps) <= 2 and abs(a.nsteps - c.nsteps) <= 2 and a.nsteps >= n
     # the six sums are added in another order: rounding differences, amplified by close encounters
     assert rel(a.q, b.q) <= 1e-10 and rel(a.p, b.p) <= 1e-8 and rel(a.f, b.f) <= 1e-7
     assert rel(a.q, c.q) <= 1e-10 and rel(a.p, c.p) <= 1e-8
