@@ -2386,6 +2386,39 @@ int nbk_hermite_advance_resident(nbk_ctx *ctx, double stop_time, double eta, dou
     G = std::max(G, (n + HGR_PER_CTA - 1) / HGR_PER_CTA);
     const int per = (n + G - 1) / G;
     const size_t gsmem = (size_t)per * HRES_STRIDE * sizeof(double);
+    if (ctx->hermite_spec) {  // software-pipelined (default); NBK_HERMITE_SPEC=0: the plain loop
+      const size_t ncand = (size_t)2 * G + 1;
+      const size_t swords = 2 * ncand * HCL_CAND + (size_t)2 * G * 8 + 8;
+      TRY(reserve(ctx, ctx->d_hgrid, swords * sizeof(double)));
+      double *sw = (double *)ctx->d_hgrid.p;
+      HermiteGridSpecParams S;
+      S.state = (double *)ctx->d_hstate.p;
+      S.cand = sw;
+      S.part = sw + 2 * ncand * HCL_CAND;
+      S.bar = (unsigned long long *)(S.part + (size_t)2 * G * 8);
+      S.nsteps_out = (long long *)ctx->d_scalar.p;
+      S.n = n;
+      S.stop_time = stop_time;
+      S.eta = eta;
+      S.eps2 = eps2;
+      S.max_steps = (long long)max_steps;
+      CK(cudaMemsetAsync(S.bar, 0, 8 * sizeof(double), ctx->stream));
+      CK(cudaFuncSetAttribute(hermite_grid_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)gsmem));
+      void *sargs[] = {&S};
+      CK(cudaLaunchCooperativeKernel((const void *)hermite_grid_spec_kernel, dim3(G),
+                                     dim3(HGRS_THREADS), sargs, gsmem, ctx->stream));
+      ctx->launches++;
+      CK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar.p, sizeof(long long), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      TRY(sync(ctx));
+      long long ssteps;
+      memcpy(&ssteps, ctx->h_scalar, sizeof ssteps);
+      if (nsteps) *nsteps = (long)ssteps;
+      if (ssteps >= (long long)max_steps && max_steps > 0)
+        return fail(ctx, NBK_ERR_STATE, "Hermite step cap (%ld) reached before stop_time", max_steps);
+      return NBK_OK;
+    }
     const size_t words = (size_t)2 * G * HCL_CAND + (size_t)2 * G * 8 + 8;
     TRY(reserve(ctx, ctx->d_hgrid, words * sizeof(double)));
     double *w = (double *)ctx->d_hgrid.p;

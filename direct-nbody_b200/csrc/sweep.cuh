@@ -2747,6 +2747,384 @@ __global__ void __launch_bounds__(HGR_THREADS, 1) hermite_grid_kernel(const Herm
   if (rank == 0 && tid == 0) *Q.nsteps_out = steps;
 }
 
+// ---- the whole-grid loop, software-pipelined ---------------------------------------------------
+// The scheme of hermite_cluster_spec_kernel with the tables in global memory (L2) and the grid
+// barrier at the end of the step - ONE per step instead of two, and the owner's corrector runs
+// beside the other CTAs' work:
+//   thread 0 of i_k's owner   corrector of step k (the G partials are first added by six warps of
+//                             the owner, one component each, in a fixed tree), new keys and
+//                             record -> row 2 G of the candidate table
+//   warp 1 of every CTA       the CTA's two earliest bodies other than i_k -> rows 2 rank, 2 rank + 1
+//   warps 2.. of every CTA    local part of the next target's sums without i_k -> row [rank] of the
+//                             partial table
+//   grid barrier
+//   everybody                 the two smallest keys of the 2 G + 1 rows: next target and the one
+//                             after; their records (and the stepped body's) come into shared memory.
+constexpr int HGRS_THREADS = 320;
+
+struct HermiteGridSpecParams {
+  double *state;            // [n][HB]
+  double *cand;             // [2][2 G + 1][HCL_CAND]
+  double *part;             // [2][G][8]
+  unsigned long long *bar;  // grid barrier counter, zero at launch
+  long long *nsteps_out;
+  int n;
+  double stop_time, eta, eps2;
+  long long max_steps;
+};
+
+__global__ void __launch_bounds__(HGRS_THREADS, 1)
+    hermite_grid_spec_kernel(const HermiteGridSpecParams Q) {
+  constexpr int T = HGRS_THREADS, NW = T / 32, NF = NW - 2;
+  constexpr int NONE = 0x7fffffff;
+  extern __shared__ double rec[];  // [nloc][HRES_STRIDE]; slots 15 / 16 = the integer keys
+  __shared__ double rows3[2][3][HCL_CAND];  // by step parity: current target, next target, stepped body
+  __shared__ double tgtp[2][8];             // the next target's predicted state (local copy)
+  __shared__ double red[NW][6];
+  __shared__ double psum[6];                // the owner: the G partials added up
+  __shared__ unsigned long long wtop[NW][2][2];
+  __shared__ int wrow[NW][2];
+  const int G = (int)gridDim.x, rank = (int)blockIdx.x;
+  const int NCAND = 2 * G + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = Q.n;
+  const int per = (n + G - 1) / G;
+  const int j_lo = min(rank * per, n), j_hi = min(j_lo + per, n), nloc = j_hi - j_lo;
+  const double stop_time = Q.stop_time, eta = Q.eta;
+  const long long max_steps = Q.max_steps;
+  SweepParams P;
+  P.eps2 = Q.eps2;
+  auto K1 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 16);
+  };
+  auto K2 = [&](int l) -> unsigned long long & {
+    return *reinterpret_cast<unsigned long long *>(rec + l * HRES_STRIDE + 15);
+  };
+  for (int l = tid; l < nloc; l += T) {
+    double *r = rec + l * HRES_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r[c] = Q.state[(size_t)(j_lo + l) * HB + c];
+    const double st = r[15];
+    K1(l) = hkey_of_double(r[0] + r[14]);
+    K2(l) = hkey_tie(st, j_lo + l);
+  }
+  __syncthreads();
+  auto less = [](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                 unsigned long long b2) { return a1 < b1 || (a1 == b1 && a2 < b2); };
+  auto key_of = [](const double *c, int w) {
+    return (unsigned long long)__double_as_longlong(c[w]);
+  };
+  auto idx_of = [](unsigned long long k1, unsigned long long k2) {
+    return k1 == HKEY_NONE ? NONE : (int)(k2 & ((1u << HKEY_IDX_BITS) - 1));
+  };
+  auto keep2 = [&](unsigned long long k1, unsigned long long k2, unsigned long long &a1,
+                   unsigned long long &a2, unsigned long long &b1, unsigned long long &b2) {
+    const bool lt_a = less(k1, k2, a1, a2), lt_b = less(k1, k2, b1, b2);
+    b1 = lt_a ? a1 : (lt_b ? k1 : b1);
+    b2 = lt_a ? a2 : (lt_b ? k2 : b2);
+    a1 = lt_a ? k1 : a1;
+    a2 = lt_a ? k2 : a2;
+  };
+  auto combine2 = [&](unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                      unsigned long long b2, unsigned long long (&o)[2][2]) {
+    unsigned long long g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    const bool mine = (a1 == g1 && a2 == g2);  // keys are unique (the tie key holds the index)
+    unsigned long long s1 = mine ? b1 : a1, s2 = mine ? b2 : a2;
+    warp_min_pair(s1, s2);
+    o[0][0] = g1, o[0][1] = g2, o[1][0] = s1, o[1][1] = s2;
+  };
+  // warp 1: this CTA's two earliest bodies other than `hide` (search as in
+  // hermite_cluster_spec_kernel) -> rows 2 rank, 2 rank + 1 of cand[pb]
+  const bool cached = nloc > 384;
+  unsigned long long ca1 = HKEY_NONE, ca2 = HKEY_NONE, cb1 = HKEY_NONE, cb2 = HKEY_NONE;
+  auto rescan = [&](int g, int hide) {
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    for (int l = g + 32 * lane; l < nloc; l += 32 * 32)
+      keep2(l == hide ? HKEY_NONE : K1(l), K2(l), a1, a2, b1, b2);
+    unsigned long long o[2][2];
+    combine2(a1, a2, b1, b2, o);
+    if (lane == g) ca1 = o[0][0], ca2 = o[0][1], cb1 = o[1][0], cb2 = o[1][1];
+  };
+  auto post_candidates = [&](int pb, int hide, int changed) {
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    if (cached) {
+      if (changed >= 0) rescan(changed & 31, hide);
+      if (hide >= 0 && (changed < 0 || (changed & 31) != (hide & 31))) rescan(hide & 31, hide);
+      a1 = ca1, a2 = ca2, b1 = cb1, b2 = cb2;
+    } else {
+#pragma unroll 4
+      for (int l = lane; l < nloc; l += 32) keep2(l == hide ? HKEY_NONE : K1(l), K2(l), a1, a2, b1, b2);
+    }
+    unsigned long long o[2][2];
+    combine2(a1, a2, b1, b2, o);
+    for (int v = lane; v < 2 * HCL_CAND; v += 32) {
+      const int s = v / HCL_CAND, slot = v - s * HCL_CAND;
+      const int kl = o[s][0] == HKEY_NONE ? -1 : (int)(o[s][1] & ((1u << HKEY_IDX_BITS) - 1)) - j_lo;
+      double x = 0.0;
+      if (slot == 0) x = __longlong_as_double((long long)o[s][0]);
+      else if (slot == 1) x = __longlong_as_double((long long)o[s][1]);
+      else if (slot >= 3 && slot < 19 && kl >= 0) x = rec[kl * HRES_STRIDE + (slot - 3)];
+      __stcg(Q.cand + ((size_t)pb * NCAND + 2 * rank + s) * HCL_CAND + slot, x);
+    }
+  };
+  // everybody: the two smallest keys of the first nrows rows of cand[pb] -> row numbers (-1: none),
+  // then those rows and row 2 G come into rows3[pb] (one block barrier inside, one at the end)
+  auto pick2 = [&](int pb, int nrows, int &row1, int &row2) {
+    const double *tab = Q.cand + (size_t)pb * NCAND * HCL_CAND;
+    unsigned long long a1 = HKEY_NONE, a2 = HKEY_NONE, b1 = HKEY_NONE, b2 = HKEY_NONE;
+    int ra = -1, rb = -1;
+    for (int x = tid; x < nrows; x += T) {  // G <= 148: one row per thread
+      const unsigned long long k1 = (unsigned long long)__double_as_longlong(__ldcg(tab + (size_t)x * HCL_CAND)),
+                               k2 = (unsigned long long)__double_as_longlong(__ldcg(tab + (size_t)x * HCL_CAND + 1));
+      if (less(k1, k2, a1, a2)) b1 = a1, b2 = a2, rb = ra, a1 = k1, a2 = k2, ra = x;
+      else if (less(k1, k2, b1, b2)) b1 = k1, b2 = k2, rb = x;
+    }
+    // warp top-2 with the rows they sit in
+    unsigned long long g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    const bool mine = a1 == g1 && a2 == g2 && g1 != HKEY_NONE;
+    const unsigned m1 = __ballot_sync(0xffffffffu, mine);
+    const int src1 = m1 ? __ffs(m1) - 1 : 0;
+    const int r1 = __shfl_sync(0xffffffffu, ra, src1);
+    unsigned long long s1 = mine && lane == src1 ? b1 : a1, s2 = mine && lane == src1 ? b2 : a2;
+    const int rs = mine && lane == src1 ? rb : ra;
+    unsigned long long h1 = s1, h2 = s2;
+    warp_min_pair(h1, h2);
+    const bool sec = s1 == h1 && s2 == h2 && h1 != HKEY_NONE;
+    const unsigned m2 = __ballot_sync(0xffffffffu, sec);
+    const int src2 = m2 ? __ffs(m2) - 1 : 0;
+    const int r2 = __shfl_sync(0xffffffffu, rs, src2);
+    if (lane == 0) {
+      wtop[warp][0][0] = g1, wtop[warp][0][1] = g2, wtop[warp][1][0] = h1, wtop[warp][1][1] = h2;
+      wrow[warp][0] = m1 ? r1 : -1;
+      wrow[warp][1] = m2 ? r2 : -1;
+    }
+    __syncthreads();
+    // every warp: the two smallest of the 2 NW warp results (lane x: warp x / 2, entry x & 1)
+    a1 = a2 = HKEY_NONE;
+    ra = -1;
+    if (lane < 2 * NW) {
+      a1 = wtop[lane >> 1][lane & 1][0];
+      a2 = wtop[lane >> 1][lane & 1][1];
+      ra = wrow[lane >> 1][lane & 1];
+    }
+    g1 = a1, g2 = a2;
+    warp_min_pair(g1, g2);
+    const bool mine_b = a1 == g1 && a2 == g2 && g1 != HKEY_NONE;
+    const unsigned n1 = __ballot_sync(0xffffffffu, mine_b);
+    const int t1 = n1 ? __ffs(n1) - 1 : 0;
+    row1 = n1 ? __shfl_sync(0xffffffffu, ra, t1) : -1;
+    s1 = mine_b && lane == t1 ? HKEY_NONE : a1;
+    s2 = mine_b && lane == t1 ? HKEY_NONE : a2;
+    h1 = s1, h2 = s2;
+    warp_min_pair(h1, h2);
+    const bool sec_b = s1 == h1 && s2 == h2 && h1 != HKEY_NONE;
+    const unsigned n2 = __ballot_sync(0xffffffffu, sec_b);
+    const int t2 = n2 ? __ffs(n2) - 1 : 0;
+    row2 = n2 ? __shfl_sync(0xffffffffu, ra, t2) : -1;
+    // the three records into shared memory
+    if (tid < 3 * HCL_CAND) {
+      const int which = tid / HCL_CAND, slot = tid - which * HCL_CAND;
+      const int row = which == 0 ? row1 : (which == 1 ? row2 : 2 * G);
+      rows3[pb][which][slot] = row >= 0 && row < nrows ? __ldcg(tab + (size_t)row * HCL_CAND + slot) : 0.0;
+    }
+    __syncthreads();
+  };
+  // warps [w0, NW): the local part of the six sums -> row [rank] of part[pb]
+  auto local_force = [&](int w0, int hide, int itarget, const OpGradVDGradV::Tgt &tg, double nt,
+                         int pb, auto sync) {
+    const int nthr = (NW - w0) * 32, t0 = tid - w0 * 32;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = t0; l < nloc; l += nthr) {
+      if (l == hide) continue;
+      double mj, qj[3], vj[3];
+      hermite_predict_fast(rec + l * HRES_STRIDE, nt, mj, qj, vj);
+      const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                              make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+      OpGradVDGradV::pair<true>(tg, acc, src, src, (j_lo + l) == itarget, P);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], off);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) red[warp][c] = acc[c];
+    sync();
+    if (t0 < 6) {
+      double a = red[w0][t0];
+      for (int w = w0 + 1; w < NW; ++w) a += red[w][t0];
+      __stcg(Q.part + ((size_t)pb * G + rank) * 8 + t0, a);
+    }
+  };
+  auto sync_all = [] { __syncthreads(); };
+  auto sync_force = [] { asm volatile("bar.sync 2, %0;" ::"r"(NF * 32) : "memory"); };
+  // owner: warps 2..7 add the G partials of part[pb], one component each, fixed tree -> psum;
+  // hands over to warp 0 through a named barrier (warps 0 and 2..7: 224 threads)
+  auto collect = [&](int pb) {
+    if (warp >= 2 && warp < 8) {
+      const int c = warp - 2;
+      double a = 0.0;
+      for (int r = lane; r < G; r += 32) a += __ldcg(Q.part + ((size_t)pb * G + r) * 8 + c);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+      if (lane == 0) psum[c] = a;
+    }
+    if (warp == 0 || (warp >= 2 && warp < 8)) asm volatile("bar.sync 3, 224;" ::: "memory");
+  };
+
+  long long steps = 0, stamp = 0;
+  unsigned long long nbar = 0;
+  bool finishing = false;
+  // ---- the first two bodies of the schedule
+  if (warp == 1) {
+    if (cached) {
+#pragma unroll 4
+      for (int l = lane; l < nloc; l += 32) keep2(K1(l), K2(l), ca1, ca2, cb1, cb2);
+    }
+    post_candidates(1, -1, -1);
+  }
+  adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);
+  int row1, row2;
+  pick2(1, 2 * G, row1, row2);
+  const double *cur = row1 >= 0 ? &rows3[1][0][0] : nullptr;  // the current target: keys, -, record
+  const double *nxt = row2 >= 0 ? &rows3[1][1][0] : nullptr;  // the target after it
+  int par = 0, pb = 0;
+  bool have = false;
+  const double *prevrec = nullptr;  // the body stepped before (its new record), for the extra pair
+  int changed = -1;
+  for (;;) {
+    if (cur == nullptr) break;  // every body finished (uniform over the grid)
+    const unsigned long long itk1 = key_of(cur, 0);
+    const int it = idx_of(itk1, key_of(cur, 1)), owner = it / per;
+    if (!finishing) {
+      if (steps >= max_steps) break;
+      if (hkey_to_double(itk1) > stop_time) finishing = true;
+    }
+    const double *tr = cur + 3;
+    const double h = finishing ? __dsub_rn(stop_time, tr[0]) : tr[14];
+    const double nt = __dadd_rn(tr[0], h);
+    const int it_loc = rank == owner ? it - j_lo : -1;
+    double mt = 0.0, qt[3] = {0, 0, 0}, vt[3] = {0, 0, 0};
+    if (!have) {
+      // the plain way: everybody sums its local part for `it`, one more grid barrier
+      hermite_predict_fast(tr, nt, mt, qt, vt);
+      const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+      local_force(0, -1, it, tg, nt, pb, sync_all);
+      adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);
+    } else if (tid == 0 && rank == owner) {
+      mt = tgtp[pb][0];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) qt[c] = tgtp[pb][1 + c], vt[c] = tgtp[pb][4 + c];
+    }
+    ++steps;
+    ++stamp;
+    const int r = nxt ? idx_of(key_of(nxt, 0), key_of(nxt, 1)) : NONE;
+    if (rank == owner) collect(pb);
+    if (warp == 0) {
+      if (tid == 0 && rank == owner) {
+        // ---- corrector (hermite.ml:116-123), new time step (hermite.ml:87-93)
+        const OpGradVDGradV::Tgt tg = {qt[0], qt[1], qt[2], vt[0], vt[1], vt[2]};
+        double extra[6] = {0, 0, 0, 0, 0, 0};
+        if (have) {  // the interaction the speculative sums left out: the body stepped last
+          double mj, qj[3], vj[3];
+          hermite_predict_fast(prevrec + 3, nt, mj, qj, vj);
+          const double2 src[4] = {make_double2(qj[0], qj[1]), make_double2(qj[2], mj),
+                                  make_double2(vj[0], vj[1]), make_double2(vj[2], 0.0)};
+          OpGradVDGradV::pair<false>(tg, extra, src, src, false, P);
+        }
+        double fp[3], dfp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          fp[c] = mt * (extra[c] + psum[c]);
+          dfp[c] = mt * (extra[3 + c] + psum[3 + c]);
+        }
+        double *wr = rec + it_loc * HRES_STRIDE;
+        const double m = mt;
+        double qn[3], pn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double q0 = tr[2 + c], p0 = tr[5 + c], f0 = tr[8 + c], df0 = tr[11 + c];
+          pn[c] = __dadd_rn(__dadd_rn(p0, __dmul_rn(__dmul_rn(0.5, h), __dadd_rn(f0, fp[c]))),
+                            __dmul_rn(__ddiv_rn(__dmul_rn(h, h), 12.0), __dsub_rn(df0, dfp[c])));
+          qn[c] = __dadd_rn(
+              __dadd_rn(q0, __dmul_rn(__ddiv_rn(__dmul_rn(0.5, h), m), __dadd_rn(p0, pn[c]))),
+              __dmul_rn(__ddiv_rn(__dmul_rn(h, h), __dmul_rn(12.0, m)), __dsub_rn(f0, fp[c])));
+        }
+        const double dx = qn[0] - qt[0], dy = qn[1] - qt[1], dz = qn[2] - qt[2];
+        const double rr = __dsqrt_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        const double fn = __dsqrt_rn(__dadd_rn(
+            __dadd_rn(__dmul_rn(fp[0], fp[0]), __dmul_rn(fp[1], fp[1])), __dmul_rn(fp[2], fp[2])));
+        double hn;
+        if (rr == 0.0) {
+          hn = __dmul_rn(h, 1.189207115002721);
+        } else {
+          const double x =
+              __ddiv_rn(__dmul_rn(__dmul_rn(eta, __dmul_rn(h, h)), fn), __dmul_rn(m, rr));
+          hn = __dmul_rn(h, __dsqrt_rn(__dsqrt_rn(x)));
+        }
+        wr[0] = nt;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wr[2 + c] = qn[c];
+          wr[5 + c] = pn[c];
+          wr[8 + c] = fp[c];
+          wr[11 + c] = dfp[c];
+        }
+        wr[14] = hn;
+        K1(it_loc) = finishing ? HKEY_NONE : hkey_of_double(nt + hn);
+        K2(it_loc) = hkey_tie((double)stamp, it);
+      }
+      __syncwarp();
+      if (rank == owner && lane < 19) {  // the new keys and record -> row 2 G
+        const double *wr = rec + it_loc * HRES_STRIDE;
+        double v = 0.0;
+        if (lane == 0) v = wr[16];
+        else if (lane == 1) v = wr[15];
+        else if (lane >= 3) v = wr[lane - 3];
+        __stcg(Q.cand + ((size_t)par * NCAND + 2 * G) * HCL_CAND + lane, v);
+      }
+    } else if (warp == 1) {
+      post_candidates(par, it_loc, changed);
+    } else if (r != NONE) {
+      const double *rr_ = nxt + 3;
+      const bool fin_r = finishing || hkey_to_double(key_of(nxt, 0)) > stop_time;
+      const double hr = fin_r ? __dsub_rn(stop_time, rr_[0]) : rr_[14];
+      const double ntr = __dadd_rn(rr_[0], hr);
+      double mr, qr[3], vr[3];
+      hermite_predict_fast(rr_, ntr, mr, qr, vr);
+      const OpGradVDGradV::Tgt tgr = {qr[0], qr[1], qr[2], vr[0], vr[1], vr[2]};
+      if (tid == 64) {
+        tgtp[pb ^ 1][0] = mr;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tgtp[pb ^ 1][1 + c] = qr[c], tgtp[pb ^ 1][4 + c] = vr[c];
+      }
+      local_force(2, it_loc, r, tgr, ntr, pb ^ 1, sync_force);
+    }
+    adv_grid_barrier(Q.bar, (unsigned long long)G * ++nbar);
+    // ---- who is next, and who after that (uniform over the grid)
+    pick2(par, NCAND, row1, row2);
+    changed = it_loc;
+    const bool again = row1 == 2 * G;
+    prevrec = &rows3[par][2][0];
+    cur = row1 >= 0 ? &rows3[par][0][0] : nullptr;
+    nxt = row2 >= 0 ? &rows3[par][1][0] : nullptr;
+    have = !again && cur != nullptr && idx_of(key_of(cur, 0), key_of(cur, 1)) == r;
+    if (have) pb ^= 1;
+    par ^= 1;
+  }
+  __syncthreads();
+  for (int l = tid; l < nloc; l += T) {
+    double *rl = rec + l * HRES_STRIDE;
+    rl[15] = (double)(0x7ffffffffffull - (K2(l) >> HKEY_IDX_BITS));  // back to the stamp
+#pragma unroll
+    for (int c = 0; c < 16; ++c) Q.state[(size_t)(j_lo + l) * HB + c] = rl[c];
+  }
+  if (rank == 0 && tid == 0) *Q.nsteps_out = steps;
+}
+
 // ---- Analysis.binaries support ------------------------------------------------------------------
 // Slot 7 of a packed body := its global index (OpBinary reports partners by index).
 __global__ void index_kernel(double *__restrict__ packed, int n) {
