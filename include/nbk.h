@@ -344,8 +344,10 @@ int nbk_hermite_body_sum(nbk_ctx *ctx, int i, double nt, double eps2, int upd,
                          const double *upd_state, double *gsum, double *dgsum);
 /* Hermite.advance_bodies + finish_bs (hermite.ml:132-143, 171-178) run ENTIRELY on the device
  * by one persistent kernel over the resident state (n <= nbk_hermite_resident_max(): one CTA
- * up to 1536 bodies, an 8-CTA cluster up to 12288, the whole grid - cooperative launch, two grid
- * barriers per step - up to 1600 bodies per SM): steps
+ * up to 1536 bodies, an 8-CTA cluster up to 12288, the whole grid - cooperative launch - up to
+ * 1600 bodies per SM; all three software-pipelined: the corrector of one step runs beside the
+ * scheduler search and the force sum of the next, one barrier per step; NBK_HERMITE_SPEC=0 in the
+ * environment at nbk_create selects the plain loops): steps
  * single bodies in the reference's list order until every next time exceeds stop_time, then
  * steps every body to stop_time.  *nsteps = advance_body calls made (Base.nsteps,
  * hermite.ml:124).  Stops early, returning NBK_ERR_STATE, after max_steps steps of the first
