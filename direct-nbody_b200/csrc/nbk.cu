@@ -2,6 +2,7 @@
 // sm_100a only; no CPU fallback (nbk_create fails without a CUDA device).
 #include "../../include/nbk.h"
 #include "sweep.cuh"
+#include "sym.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -70,7 +71,8 @@ struct nbk_ctx {
   std::string err;
   // device workspaces
   DevBuf d_m, d_q, d_vel, d_t, d_f, d_df, d_aux_in, d_aux_in2, d_packed, d_aux, d_partial, d_tbest,
-      d_out[4], d_scalar;
+      d_out[4], d_scalar, d_sympartial;
+  int sym_mode = 1;  // pair-once sweep for large full squares: 1 auto, 0 never, 2 whenever possible (NBK_SYM)
   // resident bodies
   int resident_n = 0;
   DevBuf d_res_m, d_res_packed;
@@ -290,7 +292,100 @@ struct K3 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, boo
 struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<false>>(c, P, s, t); } };
 struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<true>>(c, P, s, t); } };
 
+
+// ---- pair-once sweep (sym.cuh) ---------------------------------------------------------------
+// Work items of the upper triangle for n bodies.
+long long sym_items(int n) {
+  const long long nb = ((long long)n + SYM_B - 1) / SYM_B;
+  return nb * (nb + 1) / 2;
+}
+size_t sym_partial_bytes(int n) {
+  const size_t nb = ((size_t)n + SYM_B - 1) / SYM_B;
+  return nb * nb * SYM_B * 6 * sizeof(double);
+}
+// Pair-once or ordered sweep for a full n x n square on one device?  An item (1024 x 1024 pair
+// evaluations, 38 FP64 instructions each) costs 38/31 of the same square of ordered pairs, the
+// items come in waves of one per SM, and the ordered sweep (stream-K) balances exactly.
+bool sym_pays(const nbk_ctx *ctx, int n) {
+  if (ctx->sym_mode == 0 || n < 2 * SYM_B) return false;
+  if (sym_partial_bytes(n) > ((size_t)24 << 30)) return false;
+  if (ctx->sym_mode == 2) return true;
+  const double nbf = (double)n / SYM_B;
+  const long long items = sym_items(n);
+  const long long waves = (items + ctx->sm_count - 1) / ctx->sm_count;
+  const double t_sym = (double)waves * (38.0 / 31.0) * 1.03 + 0.02 * nbf;  // + reduce pass
+  const double t_ord = nbf * nbf / ctx->sm_count;
+  return t_sym < t_ord;
+}
+
+// Launches items [item0, item1) and the slot reduction.  shard/ready as in SweepParams; out6
+// ([n][6], all bodies) and/or gsum/dgsum rows [t0, t1).
+int sym_run(nbk_ctx *ctx, const double *const *shard, long long shard_rows, int nranks, int self,
+            const unsigned long long *ready, unsigned long long epoch, int n, double eps2,
+            long long item0, long long item1, double *out6, double *gsum, double *dgsum, int t0,
+            int t1, cudaStream_t st, bool time_it) {
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    CK(cudaFuncSetAttribute(sym_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)SYM_SMEM));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int nb = (n + SYM_B - 1) / SYM_B;
+  TRY(reserve(ctx, ctx->d_sympartial, sym_partial_bytes(n)));
+  SymParams P;
+  memset(&P, 0, sizeof P);
+  SymReduceParams R;
+  memset(&R, 0, sizeof R);
+  for (int r = 0; r < nranks; ++r) P.shard[r] = R.shard[r] = shard[r];
+  P.shard_rows = R.shard_rows = shard_rows;
+  P.n = R.n = n;
+  P.nb = R.nb = nb;
+  P.nranks = nranks;
+  P.self_rank = self;
+  P.item0 = R.item0 = item0;
+  P.item1 = R.item1 = item1;
+  P.eps2 = eps2;
+  P.partial = (double *)ctx->d_sympartial.p;
+  P.ready = ready;
+  P.epoch = epoch;
+  P.wait_ns = ctx->peer_wait_ns;
+  R.partial = P.partial;
+  R.out6 = out6;
+  R.gsum = gsum;
+  R.dgsum = dgsum;
+  R.t0 = t0;
+  R.t1 = t1;
+  if (time_it) CK(cudaEventRecord(ctx->ev0, st));
+  const long long items = item1 - item0;
+  if (items > 0) {
+    const unsigned G = (unsigned)std::min<long long>(items, ctx->sm_count);
+    sym_sweep_kernel<<<G, SYM_NT, SYM_SMEM, st>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (t1 > t0) {
+    sym_reduce_kernel<<<(unsigned)((t1 - t0 + 31) / 32), 192, 0, st>>>(R);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (time_it) {
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+  }
+  return NBK_OK;
+}
+
 int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
+  // A full square over one set of bodies: every unordered pair once (hermite.ml:157-166 does the
+  // same), when there are enough block pairs to fill the SMs.
+  if (P.t0 == P.s0 && P.t1 == P.s1 && !P.accumulate && P.out[0] && P.out[1] &&
+      sym_pays(ctx, P.t1 - P.t0)) {
+    const int n = P.t1 - P.t0;
+    const double *rows = P.packed + (size_t)P.t0 * PK;
+    const long long rows_cap = (((long long)n + SYM_B - 1) / SYM_B) * SYM_B;
+    return sym_run(ctx, &rows, rows_cap, 1, 0, nullptr, 0, n, P.eps2, 0, sym_items(n), nullptr,
+                   P.out[0], P.out[1], 0, n, st, time_it);
+  }
   return run_op<OpGradVDGradVB<1>>(ctx, P, st, time_it);
 }
 
@@ -788,6 +883,7 @@ int nbk_create(nbk_ctx **out, int device) {
   c->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("NBK_HERMITE_THREADS")) c->hermite_threads = atoi(e);
   if (const char *e = getenv("NBK_HERMITE_SPEC")) c->hermite_spec = atoi(e) != 0;
+  if (const char *e = getenv("NBK_SYM")) c->sym_mode = atoi(e);
   if (const char *e = getenv("NBK_PEER_TIMEOUT_S")) {
     const double s = atof(e);
     c->peer_wait_ns = s > 0.0 ? (unsigned long long)(s * 1e9) : 0ULL;
@@ -878,7 +974,7 @@ void nbk_destroy(nbk_ctx *c) {
                     &c->d_hstate, &c->d_hpartial, &c->d_hticket, &c->d_hout, &c->d_hgrid,
                     &c->d_adv,    &c->d_adv2,   &c->d_oa_m,   &c->d_oa_q,  &c->d_oa_p,
                     &c->d_oa_qs,  &c->d_oa_g,   &c->d_oa_phi, &c->d_oa_el, &c->d_lf_packed,
-                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt, &c->d_lft};
+                    &c->d_lf_packed2, &c->d_lf_dtmax, &c->d_lf_dtmax2, &c->d_adt, &c->d_lft, &c->d_sympartial};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -2621,6 +2717,55 @@ int nbk_dev_grad_v_dgrad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total
   P.accumulate = accumulate;
   cudaStream_t st = (cudaStream_t)stream;
   return run_k2(ctx, P, st, false);
+}
+
+int nbk_set_sym(nbk_ctx *ctx, int mode) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (mode < 0 || mode > 2) return fail(ctx, NBK_ERR_ARG, "nbk_set_sym: mode must be 0, 1 or 2");
+  ctx->sym_mode = mode;
+  for (nbk_ctx *p : ctx->peers) p->sym_mode = mode;
+  return NBK_OK;
+}
+
+int nbk_sym_items(int n_total, long long *items) {
+  if (n_total < 0 || !items) return NBK_ERR_ARG;
+  *items = sym_items(n_total);
+  return NBK_OK;
+}
+
+int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2,
+                               long long item0, long long item1, double *d_sum6, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n_total < 0 || !d_packed || ((uintptr_t)d_packed & 15) || !d_sum6 || item0 < 0 ||
+      item1 < item0 || item1 > sym_items(n_total))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_grad_v_dgrad_v_sym: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (n_total == 0) return NBK_OK;
+  const long long rows_cap = (((long long)n_total + SYM_B - 1) / SYM_B) * SYM_B;
+  return sym_run(ctx, &d_packed, rows_cap, 1, 0, nullptr, 0, n_total, eps2, item0, item1, d_sum6,
+                 nullptr, nullptr, 0, n_total, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
+                                    long long item0, long long item1, double *d_sum6,
+                                    void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (!sh || sh->nranks < 1 || sh->nranks > MAX_PEERS || sh->self < 0 || sh->self >= sh->nranks ||
+      sh->shard_rows <= 0 || sh->shard_rows % SYM_B != 0 ||
+      (long long)sh->shard_rows * sh->nranks < n_total)
+    return fail(ctx, NBK_ERR_ARG,
+                "nbk_dev_grad_v_dgrad_v_sym_peer: bad shard table (shard_rows a multiple of %d)",
+                SYM_B);
+  if (n_total < 0 || !d_sum6 || item0 < 0 || item1 < item0 || item1 > sym_items(n_total))
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_grad_v_dgrad_v_sym_peer: bad arguments");
+  for (int r = 0; r < sh->nranks; ++r)
+    if (!sh->packed[r] || ((uintptr_t)sh->packed[r] & 15))
+      return fail(ctx, NBK_ERR_ARG, "shard %d: null or misaligned device pointer", r);
+  CK(cudaSetDevice(ctx->device));
+  if (n_total == 0) return NBK_OK;
+  return sym_run(ctx, sh->packed, sh->shard_rows, sh->nranks, sh->self,
+                 (const unsigned long long *)sh->ready, sh->epoch, n_total, eps2, item0, item1,
+                 d_sum6, nullptr, nullptr, 0, n_total, (cudaStream_t)stream, false);
 }
 
 int nbk_dev_grad_v_sum(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2, int t0,

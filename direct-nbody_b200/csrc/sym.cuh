@@ -1,0 +1,328 @@
+// Pair-once (symmetric) Hermite acc+jerk sweep for sm_100a.
+//
+// The reference's own start_bs loop (hermite.ml:157-166) evaluates every unordered pair once and
+// applies it to both bodies (f_i -= gv; f_j += gv).  sweep_kernel (sweep.cuh) evaluates every
+// ORDERED pair: 31 FP64 instructions per interaction.  Here a pair evaluation costs 38 FP64
+// instructions and serves two interactions = 19 per interaction.
+//
+// Decomposition: the bodies are cut into blocks of SYM_B = 1024 rows; a work item is one block
+// pair (I, J), I <= J, of the upper triangle.  A CTA of 256 threads holds 4 targets of block I
+// per thread in registers (position, velocity, mass, six accumulators) and block J in shared
+// memory as seven component arrays plus six j-side accumulator arrays.  A warp works on one
+// group of 32 sources at a time: in round r lane l takes source (l + r) mod 32 of the group
+// (bank-conflict-free 8-byte reads), evaluates it against its 4 targets, adds the i-side terms
+// to the target accumulators and the j-side terms (weighted with the TARGET's mass) to six
+// registers that travel with the source: after every round they move one lane down by SHFL, so
+// after 32 rounds every lane holds the complete sum over the warp's 128 targets for one source
+// and adds it to the shared arrays.  The 8 warps walk the 32 groups skewed (warp w starts at
+// group 4w), so no two warps ever touch the same group between two CTA barriers (one barrier
+// per 4 groups).  At the end of an item both sides leave as partial sums: body b of block B has
+// one slot per partner block S, written by item (min(B,S), max(B,S)); sym_reduce_kernel adds a
+// body's slots in slot order, so the result does not depend on which CTA (or which GPU) ran
+// which item.  Diagonal items (I == J) evaluate all ordered pairs of the block one-sidedly
+// (j-side weight 0) and mask i == j; items touching the padded tail of the last block mask the
+// rows >= n.
+//
+// Sharded runs: body b lives in row b % shard_rows of shard[b / shard_rows] (peer-mapped over
+// NVLink, as in sweep_kernel<..., PEER>); every rank runs a contiguous range of items and the
+// per-rank sums meet in a reduce-scatter (nbk/sharded.py).
+#pragma once
+
+namespace nbk {
+
+constexpr int SYM_NT = 256;
+constexpr int SYM_IPT = 4;
+constexpr int SYM_B = SYM_NT * SYM_IPT;                       // 1024 bodies per block
+constexpr size_t SYM_SMEM = (size_t)(7 + 6) * SYM_B * sizeof(double);  // 104 KB
+
+struct SymParams {
+  const double *shard[MAX_PEERS];  // packed rows [shard_rows][PK] of every owner
+  long long shard_rows;            // multiple of SYM_B (single device: >= nb * SYM_B)
+  int n, nb, nranks, self_rank;
+  long long item0, item1;          // items [item0, item1) of the upper triangle, row-major
+  double eps2;
+  double *partial;                 // [nb slots][nb * SYM_B bodies][6]
+  const unsigned long long *ready;
+  unsigned long long epoch, wait_ns;
+};
+
+__host__ __device__ inline long long sym_item_of(int I, int J, int nb) {
+  return (long long)I * nb - (long long)I * (I - 1) / 2 + (J - I);
+}
+__device__ inline void sym_decode(long long k, int nb, int &I, int &J) {
+  const double b = 2.0 * nb + 1.0;
+  int i = (int)((b - sqrt(b * b - 8.0 * (double)k)) * 0.5);
+  i = max(0, min(nb - 1, i));
+  while (i > 0 && sym_item_of(i, i, nb) > k) --i;
+  while (i + 1 < nb && sym_item_of(i + 1, i + 1, nb) <= k) ++i;
+  I = i;
+  J = i + (int)(k - sym_item_of(i, i, nb));
+}
+
+__device__ __forceinline__ const double *sym_block_rows(const SymParams &P, int blk) {
+  const long long b0 = (long long)blk * SYM_B;
+  const int owner = (int)(b0 / P.shard_rows);
+  return P.shard[owner] + (size_t)(b0 - (long long)owner * P.shard_rows) * PK;
+}
+
+// One item.  CHECK: mask self pairs (DIAG) and rows >= n; DIAG also switches the j side off.
+template <bool CHECK>
+__device__ __forceinline__ void sym_item(const SymParams &P, const int I, const int J, double *sm) {
+  constexpr int B = SYM_B;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *sx = sm, *sy = sm + B, *sz = sm + 2 * B, *smj = sm + 3 * B, *svx = sm + 4 * B,
+         *svy = sm + 5 * B, *svz = sm + 6 * B, *jacc = sm + 7 * B;
+  const bool diag = I == J;
+  const double eps2 = P.eps2;
+
+  double tx[SYM_IPT], ty[SYM_IPT], tz[SYM_IPT], tvx[SYM_IPT], tvy[SYM_IPT], tvz[SYM_IPT],
+      tm[SYM_IPT];
+  int ig[SYM_IPT];
+  {
+    const double2 *rows = reinterpret_cast<const double2 *>(sym_block_rows(P, I));
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int il = r * SYM_NT + tid;
+      ig[r] = I * B + il;
+      double2 a = make_double2(0.0, 0.0), b = a, c = a, d = a;
+      if (!CHECK || ig[r] < P.n) {
+        a = rows[(size_t)il * 4 + 0];
+        b = rows[(size_t)il * 4 + 1];
+        c = rows[(size_t)il * 4 + 2];
+        d = rows[(size_t)il * 4 + 3];
+      }
+      tx[r] = a.x, ty[r] = a.y, tz[r] = b.x, tvx[r] = c.x, tvy[r] = c.y, tvz[r] = d.x;
+      // the j side is weighted with the target's mass; diagonal items leave it out
+      tm[r] = (CHECK && (diag || ig[r] >= P.n)) ? 0.0 : b.y;
+    }
+  }
+  {
+    const double2 *rows = reinterpret_cast<const double2 *>(sym_block_rows(P, J));
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int jl = r * SYM_NT + tid;
+      double2 a = make_double2(0.0, 0.0), b = a, c = a, d = a;
+      if (!CHECK || J * B + jl < P.n) {
+        a = rows[(size_t)jl * 4 + 0];
+        b = rows[(size_t)jl * 4 + 1];
+        c = rows[(size_t)jl * 4 + 2];
+        d = rows[(size_t)jl * 4 + 3];
+      }
+      sx[jl] = a.x, sy[jl] = a.y, sz[jl] = b.x, smj[jl] = b.y;
+      svx[jl] = c.x, svy[jl] = c.y, svz[jl] = d.x;
+#pragma unroll
+      for (int c6 = 0; c6 < 6; ++c6) jacc[c6 * B + jl] = 0.0;
+    }
+  }
+  double acc[SYM_IPT][6];
+#pragma unroll
+  for (int r = 0; r < SYM_IPT; ++r)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[r][k] = 0.0;
+  __syncthreads();
+
+  const int jbase = J * B;
+  const int src_lane = (lane + 1) & 31;
+  for (int g = 0; g < 8; ++g) {
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int grp = ((((warp + g) & 7) << 2) + s4) << 5;  // first source of the group
+      double ja[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ja[k] = 0.0;
+#pragma unroll 2
+      for (int rd = 0; rd < 32; ++rd) {
+        const int sl = grp + ((lane + rd) & 31);
+        const double jx = sx[sl], jy = sy[sl], jz = sz[sl], jm = smj[sl];
+        const double jvx = svx[sl], jvy = svy[sl], jvz = svz[sl];
+        double dx[SYM_IPT], dy[SYM_IPT], dz[SYM_IPT], ux[SYM_IPT], uy[SYM_IPT], uz[SYM_IPT];
+        double r2[SYM_IPT], rv[SYM_IPT], y0[SYM_IPT], y[SYM_IPT], wj[SYM_IPT], wi[SYM_IPT],
+            a3[SYM_IPT];
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          dx[r] = jx - tx[r];
+          dy[r] = jy - ty[r];
+          dz[r] = jz - tz[r];
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          r2[r] = fma(dx[r], dx[r], eps2);
+          r2[r] = fma(dy[r], dy[r], r2[r]);
+          r2[r] = fma(dz[r], dz[r], r2[r]);
+          wj[r] = jm;
+          wi[r] = tm[r];
+          if (CHECK) {
+            const bool off = (jbase + sl == ig[r]) || (jbase + sl >= P.n) || (ig[r] >= P.n);
+            r2[r] = off ? 1.0 : r2[r];
+            wj[r] = off ? 0.0 : wj[r];
+            wi[r] = off ? 0.0 : wi[r];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r)
+          asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[r]) : "d"(r2[r]));
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          ux[r] = jvx - tvx[r];
+          uy[r] = jvy - tvy[r];
+          uz[r] = jvz - tvz[r];
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          rv[r] = dx[r] * ux[r];
+          rv[r] = fma(dy[r], uy[r], rv[r]);
+          rv[r] = fma(dz[r], uz[r], rv[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          const double tt = r2[r] * y0[r];
+          const double e = fma(-tt, y0[r], 1.0);
+          const double pp = fma(0.375, e, 0.5);
+          const double q = e * pp;
+          y[r] = fma(y0[r], q, y0[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          const double y2 = y[r] * y[r];
+          const double y3 = y[r] * y2;
+          a3[r] = (rv[r] * y2) * -3.0;
+          wj[r] *= y3;
+          wi[r] *= y3;
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          acc[r][0] = fma(wj[r], dx[r], acc[r][0]);
+          acc[r][1] = fma(wj[r], dy[r], acc[r][1]);
+          acc[r][2] = fma(wj[r], dz[r], acc[r][2]);
+          ja[0] = fma(wi[r], dx[r], ja[0]);
+          ja[1] = fma(wi[r], dy[r], ja[1]);
+          ja[2] = fma(wi[r], dz[r], ja[2]);
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          ux[r] = fma(a3[r], dx[r], ux[r]);
+          uy[r] = fma(a3[r], dy[r], uy[r]);
+          uz[r] = fma(a3[r], dz[r], uz[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          acc[r][3] = fma(wj[r], ux[r], acc[r][3]);
+          acc[r][4] = fma(wj[r], uy[r], acc[r][4]);
+          acc[r][5] = fma(wj[r], uz[r], acc[r][5]);
+          ja[3] = fma(wi[r], ux[r], ja[3]);
+          ja[4] = fma(wi[r], uy[r], ja[4]);
+          ja[5] = fma(wi[r], uz[r], ja[5]);
+        }
+        // the source's sums follow it to the lane that takes it next round
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ja[k] = __shfl_sync(0xffffffffu, ja[k], src_lane);
+      }
+      // 32 moves = a full turn: lane l holds the sums of source grp + l
+#pragma unroll
+      for (int k = 0; k < 6; ++k) jacc[k * B + grp + lane] += ja[k];
+    }
+    __syncthreads();
+  }
+
+  // Both sides leave as partial sums: slot J of block I (targets), slot I of block J (sources,
+  // with the sign of the reversed separation).
+  const size_t nbB = (size_t)P.nb * B;
+#pragma unroll
+  for (int r = 0; r < SYM_IPT; ++r) {
+    double2 *dst = reinterpret_cast<double2 *>(P.partial + ((size_t)J * nbB + (size_t)ig[r]) * 6);
+    dst[0] = make_double2(acc[r][0], acc[r][1]);
+    dst[1] = make_double2(acc[r][2], acc[r][3]);
+    dst[2] = make_double2(acc[r][4], acc[r][5]);
+  }
+  if (!diag) {
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int jl = r * SYM_NT + tid;
+      double2 *dst =
+          reinterpret_cast<double2 *>(P.partial + ((size_t)I * nbB + (size_t)(jbase + jl)) * 6);
+      dst[0] = make_double2(-jacc[jl], -jacc[B + jl]);
+      dst[1] = make_double2(-jacc[2 * B + jl], -jacc[3 * B + jl]);
+      dst[2] = make_double2(-jacc[4 * B + jl], -jacc[5 * B + jl]);
+    }
+  }
+  __syncthreads();  // the shared arrays are refilled by the next item
+}
+
+__global__ void __launch_bounds__(SYM_NT, 1) sym_sweep_kernel(const SymParams P) {
+  extern __shared__ __align__(16) unsigned char sym_smem_raw[];
+  double *sm = reinterpret_cast<double *>(sym_smem_raw);
+  if (P.ready != nullptr) {
+    if (threadIdx.x == 0) {
+      unsigned long long t_start;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+      for (int r = 0; r < P.nranks; ++r)
+        if (r != P.self_rank)
+          while (ld_acquire_sys(P.ready + r) < P.epoch) {
+            __nanosleep(64);
+            unsigned long long t_now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            if (P.wait_ns != 0 && t_now - t_start > P.wait_ns) __trap();
+          }
+    }
+    __syncthreads();
+  }
+  const bool ragged = (long long)P.nb * SYM_B != (long long)P.n;
+  for (long long k = P.item0 + blockIdx.x; k < P.item1; k += gridDim.x) {
+    int I, J;
+    sym_decode(k, P.nb, I, J);
+    if (I == J || (ragged && J == P.nb - 1))
+      sym_item<true>(P, I, J, sm);
+    else
+      sym_item<false>(P, I, J, sm);
+  }
+}
+
+// out6[b][0..5] (or gsum / dgsum rows) = -m_b * sum over the slots items [item0, item1) filled,
+// in slot order.  One thread per (body, component).
+struct SymReduceParams {
+  const double *shard[MAX_PEERS];
+  long long shard_rows;
+  int n, nb;
+  long long item0, item1;
+  const double *partial;
+  double *out6;    // [n][6] or NULL
+  double *gsum;    // [t1 - t0][3] (with dgsum) or NULL
+  double *dgsum;
+  int t0, t1;      // bodies written
+};
+
+__global__ void __launch_bounds__(192) sym_reduce_kernel(const SymReduceParams R) {
+  // 32 bodies x 6 components per CTA
+  const int b = R.t0 + blockIdx.x * 32 + threadIdx.x / 6;
+  const int c = threadIdx.x % 6;
+  if (b >= R.t1) return;
+  const int Bk = b / SYM_B;
+  const size_t nbB = (size_t)R.nb * SYM_B;
+  const double *src = R.partial + (size_t)b * 6 + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const bool all = R.item0 == 0 && R.item1 == sym_item_of(R.nb - 1, R.nb - 1, R.nb) + 1;
+  if (all) {
+    int s = 0;
+    for (; s + 4 <= R.nb; s += 4) {
+      s0 += src[(size_t)s * nbB * 6];
+      s1 += src[(size_t)(s + 1) * nbB * 6];
+      s2 += src[(size_t)(s + 2) * nbB * 6];
+      s3 += src[(size_t)(s + 3) * nbB * 6];
+    }
+    for (; s < R.nb; ++s) s0 += src[(size_t)s * nbB * 6];
+  } else {
+    for (int s = 0; s < R.nb; ++s) {
+      const long long k = sym_item_of(min(Bk, s), max(Bk, s), R.nb);
+      if (k >= R.item0 && k < R.item1) s0 += src[(size_t)s * nbB * 6];
+    }
+  }
+  const long long owner = (long long)b / R.shard_rows;
+  const double m = R.shard[owner][(size_t)((long long)b - owner * R.shard_rows) * PK + 3];
+  const double v = -m * ((s0 + s1) + (s2 + s3));
+  if (R.out6) R.out6[(size_t)b * 6 + c] = v;
+  if (R.gsum) {
+    if (c < 3) R.gsum[(size_t)(b - R.t0) * 3 + c] = v;
+    else R.dgsum[(size_t)(b - R.t0) * 3 + (c - 3)] = v;
+  }
+}
+
+}  // namespace nbk

@@ -129,6 +129,11 @@ SYMBOLS = {
                                                      _vp, _vp]),
     "nbk_set_peer_timeout": (_i, [_vp, _d]),
     "nbk_tune": (_i, [_vp, _i]),
+    "nbk_set_sym": (_i, [_vp, _i]),
+    "nbk_sym_items": (_i, [_i, C.POINTER(C.c_longlong)]),
+    "nbk_dev_grad_v_dgrad_v_sym": (_i, [_vp, _vp, _i, _d, C.c_longlong, C.c_longlong, _vp, _vp]),
+    "nbk_dev_grad_v_dgrad_v_sym_peer": (_i, [_vp, _psh, _i, _d, C.c_longlong, C.c_longlong, _vp,
+                                             _vp]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
 
@@ -235,6 +240,26 @@ class Context:
 
     def tune(self, variant):
         self._ck(self._lib.nbk_tune(self._h, variant))
+
+    def set_sym(self, mode):
+        """Pair-once acc+jerk sweep for full squares: 0 never, 1 automatic, 2 whenever possible."""
+        self._ck(self._lib.nbk_set_sym(self._h, int(mode)))
+
+    def sym_items(self, n_total):
+        """Block pairs (work items) of the pair-once sweep over n_total bodies."""
+        k = C.c_longlong()
+        self._ck(self._lib.nbk_sym_items(int(n_total), C.byref(k)))
+        return k.value
+
+    def dev_grad_v_dgrad_v_sym(self, d_packed, n_total, eps2, items, d_sum6, stream=0):
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sym(self._h, d_packed, n_total, eps2,
+                                                      int(items[0]), int(items[1]), d_sum6,
+                                                      stream or None))
+
+    def dev_grad_v_dgrad_v_sym_peer(self, shards, n_total, eps2, items, d_sum6, stream=0):
+        self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sym_peer(
+            self._h, C.byref(shards), n_total, eps2, int(items[0]), int(items[1]), d_sum6,
+            stream or None))
 
     def fp64_peak(self, iters=20000):
         tf, ms = _d(), _f()

@@ -465,6 +465,28 @@ int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, 
                                             double eps2, int t0, int t1, int s0, int s1,
                                             double *d_gsum_tan, double *d_dgsum_tan, void *stream);
 
+/* Pair-once (symmetric) acc+jerk sweep, the shape of the reference's own start_bs loop
+ * (/root/reference/hermite.ml:157-166: every unordered pair evaluated once, f_i -= gv,
+ * f_j += gv).  The bodies are cut into blocks of 1024 rows; a work item is one block pair of the
+ * upper triangle (diagonal included), nbk_sym_items(n) of them, numbered row-major.  A call
+ * runs items [item0, item1) and writes d_sum6[b][0..5] = {gsum_b, dgsum_b} restricted to the
+ * pairs of those items, for ALL n_total bodies (zeros where no item touched b): the sum over
+ * disjoint item ranges covering [0, items) is nbk_grad_v_dgrad_v_sum's result (to summation
+ * order).  A rank of a sharded run takes a contiguous range of items and the ranks' d_sum6 meet
+ * in a reduce-scatter (nbk/sharded.py); _peer reads the rows from the owning GPUs
+ * (shard_rows a multiple of 1024) and waits for every rank's ready flag first.
+ * nbk_grad_v_dgrad_v_sum and its _resident / _dev forms take this path by themselves for a
+ * full square (targets = sources) once there are enough block pairs to fill the SMs;
+ * nbk_set_sym: 0 = never, 1 = automatic (default; NBK_SYM in the environment at nbk_create),
+ * 2 = for every full square of at least 2048 bodies. */
+int nbk_set_sym(nbk_ctx *ctx, int mode);
+int nbk_sym_items(int n_total, long long *items);
+int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total, double eps2,
+                               long long item0, long long item1, double *d_sum6, void *stream);
+int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
+                                    long long item0, long long item1, double *d_sum6,
+                                    void *stream);
+
 /* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
  * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).
  * Results do not depend on the shape beyond summation order.  A knob for profiles/ and
