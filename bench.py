@@ -38,8 +38,11 @@ for _p in (ROOT, os.path.join(ROOT, "direct-nbody_b200")):
 METRIC = "FP64 pairwise interactions/sec (Hermite acc+jerk) at N=128k"
 UNIT = "interactions/s"
 FLOP_PER_INTERACTION = 60        # Nitadori-Makino convention
-COUNTED_FLOP = 48                # 6 DADD + 8 DMUL + 17 DFMA(x2) of our instruction mix
-FP64_SLOTS = 31                  # FP64-pipe issue slots per interaction (tools/sass_mix.py)
+# Per ORDERED interaction, by kernel.  ordered sweep (sweep.cuh): 6 DADD + 8 DMUL + 17 DFMA per
+# interaction.  pair-once sweep (sym.cuh): one pair evaluation = 6 DADD + 9 DMUL + 23 DFMA serves
+# two interactions (tools/sass_mix.py, profiles/r2_ncu_sym_summary.txt).
+COUNTED_FLOP = {"ordered": 48.0, "once": 30.5}
+FP64_SLOTS = {"ordered": 31.0, "once": 19.0}   # FP64-pipe issue slots per interaction
 SEED = 20243                     # 20240 + config index 3
 
 
@@ -104,11 +107,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def ncu_traffic_bytes():
+def ncu_traffic_bytes(pairs="once"):
     """dram__bytes_read + dram__bytes_write of the acc+jerk sweep kernel per launch, from the
     committed `ncu --set full` summary (profiles/; a profiler cannot run inside a bench);
     returns (bytes or None, file name)."""
-    for name in ("r2_ncu_k2_large_shape_summary.txt", "r1_ncu_k2_large_shape_summary.txt"):
+    names = (("r2_ncu_sym_summary.txt",) if pairs == "once" else
+             ("r2_ncu_k2_large_shape_summary.txt", "r1_ncu_k2_large_shape_summary.txt"))
+    for name in names:
         path = os.path.join(ROOT, "profiles", name)
         try:
             tot = 0.0
@@ -125,11 +130,16 @@ def ncu_traffic_bytes():
     return None, None
 
 
-def make_config(n, world, exchange="peer", overlap=0):
+def make_config(n, world, exchange="peer", overlap=0, pairs="once"):
     """The workload both arms state (the reference arm runs it on the host cores): identical
     for `--impl ours` and `--impl reference` at the same --gpus."""
     if world == 1:
         sharding = "single GPU"
+    elif exchange == "peer" and pairs == "once":
+        sharding = (f"bodies/{world} (rows stay with their owner), block pairs of the upper "
+                    f"triangle/{world}: every unordered pair evaluated once on the whole box, "
+                    "kernels read both blocks' rows from the owning GPUs over NVLink (peer "
+                    "memory, CUDA IPC), one reduce-scatter of the per-rank sums (48 B/body)")
     elif exchange == "peer":
         sharding = (f"targets/{world}, sweep kernel reads remote source tiles from the owning GPU "
                     "over NVLink (peer memory, CUDA IPC); no all-gather step")
@@ -138,6 +148,9 @@ def make_config(n, world, exchange="peer", overlap=0):
                     + (", overlapped with the local-source sweep" if overlap else ""))
     return {"workload": f"Plummer sphere N={n}, Hermite acc+jerk sweep (BASELINE.json configs[2])",
             "n": n, "eps": 0.0, "seed": SEED, "sharding": sharding,
+            "pairs": ("every unordered pair evaluated once and applied to both bodies, as the "
+                      "reference's start_bs loop does (hermite.ml:157-166)" if pairs == "once"
+                      else "every ordered pair evaluated (i-parallel over j-tiles)"),
             "bodies": "move every step: each rank re-packs its (drifted) rows into the other row "
                       "buffer, publishes, sweeps",
             "l2": "flushed between timed iterations (256 MiB write)"}
@@ -226,7 +239,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
-            "config": make_config(n, args.gpus, args.exchange, args.overlap),
+            "config": make_config(n, args.gpus, args.exchange, args.overlap, args.pairs),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": sample,
                              "full_n": {"value": v_full, "seconds": dt_full, "n": n,
@@ -263,11 +276,16 @@ def run_ours(args):
         cpu_group = dist.new_group(backend="gloo")
 
     n = args.n
-    from nbk.sharded import PeerShardedAccJerk, ShardedAccJerk, make_plan
-    plan = make_plan(n, world, rank, align=128)
+    from nbk.sharded import (PeerShardedAccJerk, PeerShardedAccJerkSym, ShardedAccJerk, make_plan,
+                             sym_item_range)
+    pairs = args.pairs
+    if world > 1 and args.exchange != "peer":
+        pairs = "ordered"  # the all-gather variant exists for the ordered sweep only
+    plan = make_plan(n, world, rank, align=1024 if pairs == "once" else 128)
     t0, t1 = plan.t0, plan.t1
     nt = t1 - t0
     ctx = nbk.Context(local)
+    ctx.set_sym(1 if pairs == "once" else 0)
     m, qs, p = workload(n)  # same seeded bodies on every rank
 
     # ---- device-resident state: this rank's slice (m, q, p) and its packed rows.
@@ -280,10 +298,11 @@ def run_ours(args):
     sh = None
     if exchange == "peer":
         try:  # raises on EVERY rank if any rank cannot allocate or map a region
-            sh = PeerShardedAccJerk(plan, dev, ctx)
+            sh = (PeerShardedAccJerkSym if pairs == "once" else PeerShardedAccJerk)(plan, dev, ctx)
         except RuntimeError as e:
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
-            sh, exchange = None, "nccl (peer exchange unavailable)"
+            sh, exchange, pairs = None, "nccl (peer exchange unavailable)", "ordered"
+            ctx.set_sym(0)
     if sh is None:
         sh = ShardedAccJerk(plan, dev, ctx=ctx, overlap=bool(args.overlap))
     sl = slice(t0, t1)
@@ -379,9 +398,16 @@ def run_ours(args):
         barrier()  # every rank's rows are published; the kernel alone needs no flags
         shards = ctx.make_shards(plan.rank, plan.shard, sh.regions.packed(sh.cur))
 
-        def kernel_only():
-            ctx.dev_grad_v_dgrad_v_sum_peer(shards, n, 0.0, (t0, t1), (0, n), g.data_ptr(),
-                                            dg.data_ptr(), False, sptr)
+        if pairs == "once":
+            items = ctx.sym_items(n)
+            my_items = sym_item_range(items, world, rank)
+
+            def kernel_only():
+                ctx.dev_grad_v_dgrad_v_sym_peer(shards, n, 0.0, my_items, sh.sum6.data_ptr(), sptr)
+        else:
+            def kernel_only():
+                ctx.dev_grad_v_dgrad_v_sum_peer(shards, n, 0.0, (t0, t1), (0, n), g.data_ptr(),
+                                                dg.data_ptr(), False, sptr)
     else:
         src = sh.packed_all
 
@@ -396,6 +422,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
     k_inter = float(nt) * float(n - 1)
+    if pairs == "once" and exchange == "peer":
+        # this rank's block pairs: 1024 x 1024 pair evaluations each = 2 interactions each
+        # (diagonal blocks: ordered pairs, one interaction each); to the precision that matters
+        # for a rate, its share of the N(N-1) interactions
+        k_inter = float(n) * float(n - 1) * (my_items[1] - my_items[0]) / items
 
     # ---- e2e: the reference-facing C-ABI call on pinned host buffers, inputs alternating
     hm = torch.from_numpy(m).pin_memory()
@@ -504,7 +535,12 @@ def run_ours(args):
         dist.destroy_process_group()
 
     if rank == 0:
-        achieved_tf = FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12
+        # Roofline of the dominant kernel: the FP64 pipe.  Every FP64 instruction (DADD, DMUL,
+        # DFMA) occupies the pipe for one issue slot, a DFMA being the 2-flop one the peak is
+        # measured with; achieved = slots x 2 "DFMA-equivalent" flop per second, so that
+        # frac = the FP64-pipe utilisation ncu reports (sm__pipe_fp64_cycles_active).
+        slots = FP64_SLOTS[pairs]
+        achieved_tf = 2.0 * slots * k_inter / (k_ms * 1e-3) / 1e12
         clocks = sampler.summary()
         nominal = ctx_sm_count * 64 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         try:
@@ -512,31 +548,46 @@ def run_ours(args):
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             cpu = None
             print(f"cpu_baseline unavailable: {e}", file=sys.stderr)
-        traffic, traffic_file = ncu_traffic_bytes() if world == 1 else (None, None)
+        traffic, traffic_file = ncu_traffic_bytes(pairs) if world == 1 else (None, None)
+        if pairs == "once":
+            kname = "sym_sweep_kernel (pair-once, csrc/sym.cuh)" + (", rows read from their owners" if exchange == "peer" else "")
+            algo = ("algorithmic = per block pair 2 x 64 KB rows read + 2 x 48 KB partial sums "
+                    "written, + the slot reduction reading them once")
+        else:
+            kname = "sweep_kernel<OpGradVDGradV" + (", PEER>" if exchange == "peer" else ">")
+            algo = "algorithmic = 64 B x N read once + 48 B x N written"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": make_config(n, world, "peer" if exchange == "peer" else exchange,
-                                  args.overlap),
+                                  args.overlap, pairs),
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "parity": parity,
             "e2e": e2e,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "achieved_is": f"{slots:g} FP64-pipe issue slots per interaction x 2 "
+                                        "(DFMA-equivalent flop) x interactions / kernel time: "
+                                        "frac = FP64-pipe utilisation",
                          "traffic": traffic,
                          "traffic_note": "ncu dram bytes per launch"
                                          + (f" ({traffic_file})" if traffic_file else "")
-                                         + "; algorithmic = 64 B x N read once + 48 B x N written",
+                                         + "; " + algo,
                          "peak_source": "on-box DFMA microbenchmark (nbk_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "nominal_peak": nominal, "frac_of_nominal": achieved_tf / nominal,
                          "flop_per_interaction": FLOP_PER_INTERACTION,
-                         "counted_flop_per_interaction": COUNTED_FLOP,
-                         "achieved_counted": COUNTED_FLOP * k_inter / (k_ms * 1e-3) / 1e12,
-                         "fp64_issue_slots_per_interaction": FP64_SLOTS,
-                         "kernel": "sweep_kernel<OpGradVDGradV" + (", PEER>" if exchange == "peer" else ">"), "kernel_ms": k_ms,
+                         "convention_60flop_tflops": FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12,
+                         "convention_note": ("60 flop per ORDERED interaction; the pair-once kernel "
+                                             "delivers two interactions per pair evaluation, so this "
+                                             "figure may exceed the FP64 peak" if pairs == "once" else
+                                             "60 flop per interaction"),
+                         "counted_flop_per_interaction": COUNTED_FLOP[pairs],
+                         "achieved_counted": COUNTED_FLOP[pairs] * k_inter / (k_ms * 1e-3) / 1e12,
+                         "fp64_issue_slots_per_interaction": slots,
+                         "kernel": kname, "kernel_ms": k_ms,
                          "interactions_per_launch": k_inter},
         }
         if e2e_single is not None:
@@ -560,6 +611,9 @@ def main():
                     help="bodies of the workload the CPU arm sweeps per step (~20 core-seconds)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how a rank gets the other ranks' bodies (see run_ours)")
+    ap.add_argument("--pairs", default="once", choices=["once", "ordered"],
+                    help="once: every unordered pair evaluated once (csrc/sym.cuh); ordered: the "
+                         "i-parallel sweep over all ordered pairs (csrc/sweep.cuh)")
     ap.add_argument("--overlap", type=int, default=0,
                     help="1: sweep local sources while the all-gather is in flight")
     ap.add_argument("--parity", type=int, default=1,

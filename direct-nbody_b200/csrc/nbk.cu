@@ -2746,6 +2746,20 @@ int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total
                  nullptr, nullptr, 0, n_total, (cudaStream_t)stream, false);
 }
 
+int nbk_dev_split6(nbk_ctx *ctx, const double *d_sum6, int count, double *d_gsum, double *d_dgsum,
+                   void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (count < 0 || !d_sum6 || !d_gsum || !d_dgsum)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_split6: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (count == 0) return NBK_OK;
+  sym_split_kernel<<<(count * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_sum6, count, d_gsum,
+                                                                           d_dgsum);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
 int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
                                     long long item0, long long item1, double *d_sum6,
                                     void *stream) {

@@ -325,4 +325,14 @@ __global__ void __launch_bounds__(192) sym_reduce_kernel(const SymReduceParams R
   }
 }
 
+// A rank's slice of the reduce-scattered sums [count][6] -> gsum, dgsum [count][3].
+__global__ void sym_split_kernel(const double *__restrict__ in6, int count, double *__restrict__ g,
+                                 double *__restrict__ dg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count * 6) return;
+  const int b = i / 6, c = i % 6;
+  if (c < 3) g[b * 3 + c] = in6[i];
+  else dg[b * 3 + c - 3] = in6[i];
+}
+
 }  // namespace nbk

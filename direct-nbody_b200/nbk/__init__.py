@@ -134,6 +134,7 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sym": (_i, [_vp, _vp, _i, _d, C.c_longlong, C.c_longlong, _vp, _vp]),
     "nbk_dev_grad_v_dgrad_v_sym_peer": (_i, [_vp, _psh, _i, _d, C.c_longlong, C.c_longlong, _vp,
                                              _vp]),
+    "nbk_dev_split6": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
 
@@ -260,6 +261,10 @@ class Context:
         self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sym_peer(
             self._h, C.byref(shards), n_total, eps2, int(items[0]), int(items[1]), d_sum6,
             stream or None))
+
+    def dev_split6(self, d_sum6, count, d_gsum, d_dgsum, stream=0):
+        self._ck(self._lib.nbk_dev_split6(self._h, d_sum6, int(count), d_gsum, d_dgsum,
+                                          stream or None))
 
     def fp64_peak(self, iters=20000):
         tf, ms = _d(), _f()

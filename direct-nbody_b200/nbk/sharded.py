@@ -299,6 +299,8 @@ class _PeerSharded:
         self._stepped_since_load = True  # the first load_local takes the other buffer
 
     def _stream(self):
+        if getattr(self.device, "type", "cuda") != "cuda":  # CPU plumbing tests
+            return 0
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def load_local(self, m, q, vel, is_velocity=False):
@@ -374,6 +376,76 @@ class PeerShardedAccJerk(_PeerSharded):
             self.ctx.dev_grad_v_dgrad_v_sum_peer(sh, pl.n, eps2, (pl.t0, pl.t1), (0, pl.n),
                                                  self.g.data_ptr(), self.dg.data_ptr(), False,
                                                  self._stream())
+        return self.g, self.dg
+
+
+SYM_BLOCK = 1024  # bodies per block of the pair-once sweep: shards are whole blocks
+
+
+def sym_item_range(items: int, world: int, rank: int):
+    """Rank's contiguous range of the pair-once sweep's work items (block pairs)."""
+    return items * rank // world, items * (rank + 1) // world
+
+
+def sym_item_blocks(n: int, item0: int, item1: int):
+    """(I, J) block pairs of items [item0, item1): the upper triangle (diagonal included) of
+    ceil(n / 1024) blocks, row-major - the numbering of include/nbk.h."""
+    nb = (n + SYM_BLOCK - 1) // SYM_BLOCK
+    k = 0
+    for i in range(nb):
+        for j in range(i, nb):
+            if item0 <= k < item1:
+                yield i, j
+            k += 1
+
+
+class PeerShardedAccJerkSym(_PeerSharded):
+    """The sharded acc+jerk sweep with every unordered pair evaluated ONCE on the whole box
+    (hermite.ml:157-166 does the same on one core): the block pairs of the upper triangle are
+    dealt out to the ranks in contiguous ranges, each rank's kernel reads the rows of both
+    blocks from their owners over NVLink (nbk_dev_grad_v_dgrad_v_sym_peer) and leaves its
+    partial sums for ALL bodies; ONE reduce-scatter (the path's exchange step) hands every rank
+    the totals of its own slice.  The plan needs make_plan(..., align=1024).  `sweep`,
+    `reduce_scatter` and `split` are injectable for the CPU plumbing tests."""
+
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None,
+                 reduce_scatter=None, sweep=None, split=None):
+        if plan.shard % SYM_BLOCK:
+            raise ValueError("the pair-once sweep needs make_plan(..., align=1024)")
+        super().__init__(plan, device, ctx, group, exchange)
+        torch = self.torch
+        self.sum6 = torch.zeros(max(plan.npad, 1), 6, dtype=torch.float64, device=device)
+        self.out6 = torch.zeros(max(plan.shard, 1), 6, dtype=torch.float64, device=device)
+        self.g = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
+        self.dg = torch.zeros_like(self.g)
+        nb = (plan.n + SYM_BLOCK - 1) // SYM_BLOCK
+        self.items = nb * (nb + 1) // 2
+        self.item_range = sym_item_range(self.items, plan.world, plan.rank)
+        if reduce_scatter is None:
+            def reduce_scatter(out, inp):
+                import torch.distributed as dist
+                dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+        if sweep is None:
+            def sweep(sh, n, eps2, item_range, sum6):
+                self.ctx.dev_grad_v_dgrad_v_sym_peer(sh, n, eps2, item_range, sum6.data_ptr(),
+                                                     self._stream())
+        if split is None:
+            def split(src, count, g, dg):
+                self.ctx.dev_split6(src.data_ptr(), count, g.data_ptr(), dg.data_ptr(),
+                                    self._stream())
+        self._reduce_scatter, self._sweep, self._split = reduce_scatter, sweep, split
+
+    def step(self, eps2: float = 0.0):
+        pl = self.plan
+        sh = self._publish()
+        self._sweep(sh, pl.n, eps2, self.item_range, self.sum6)
+        if pl.world > 1:
+            self._reduce_scatter(self.out6, self.sum6)
+            src = self.out6
+        else:
+            src = self.sum6
+        if pl.count:
+            self._split(src, pl.count, self.g, self.dg)
         return self.g, self.dg
 
 

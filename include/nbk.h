@@ -486,6 +486,9 @@ int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total
 int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
                                     long long item0, long long item1, double *d_sum6,
                                     void *stream);
+/* Rows [count][6] of (reduce-scattered) sums -> gsum, dgsum [count][3]. */
+int nbk_dev_split6(nbk_ctx *ctx, const double *d_sum6, int count, double *d_gsum, double *d_dgsum,
+                   void *stream);
 
 /* Tile shape of the sweep kernels: 0 = automatic (by number of targets), 1 = large (1024
  * targets per CTA: 256 threads x 4), 2 = medium (256: 128 x 2), 3 = small (128: 128 x 1).

@@ -184,14 +184,23 @@ def test_baseline_size_all_bodies_per_body(ctx, oracle, eps2):
     m, q, p = nbh.make_plummer(n, 20243)
     oracle.set_num_threads(len(os.sched_getaffinity(0)))
     g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, eps2)
-    g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps2)
-    eg = np.linalg.norm(g - g_ref, axis=1) / np.linalg.norm(g_ref, axis=1)
-    edg = np.linalg.norm(dg - dg_ref, axis=1) / np.linalg.norm(dg_ref, axis=1)
-    for name, e in (("acc", eg), ("jerk", edg)):
-        worst = np.argsort(e)[-5:][::-1]
-        print(f"N={n} eps2={eps2:g} {name}: worst 5 bodies "
-              + ", ".join(f"{i}:{e[i]:.2e}" for i in worst) + f"; median {np.median(e):.2e}")
-    assert eg.max() <= TOL and edg.max() <= TOL, (eg.max(), edg.max())
+    # both kernels of the full square: the pair-once sweep (what the call takes by itself at
+    # this size, csrc/sym.cuh) and the ordered sweep
+    for mode, label in ((1, "pair-once"), (0, "ordered")):
+        ctx.set_sym(mode)
+        launches = ctx.launch_count
+        try:
+            g, dg = ctx.grad_v_dgrad_v_sum(m, q, p, eps2)
+        finally:
+            ctx.set_sym(1)
+        assert ctx.launch_count - launches == 3  # pack + sweep + (slot reduction | fix-up)
+        eg = np.linalg.norm(g - g_ref, axis=1) / np.linalg.norm(g_ref, axis=1)
+        edg = np.linalg.norm(dg - dg_ref, axis=1) / np.linalg.norm(dg_ref, axis=1)
+        for name, e in (("acc", eg), ("jerk", edg)):
+            worst = np.argsort(e)[-5:][::-1]
+            print(f"N={n} eps2={eps2:g} {label} {name}: worst 5 bodies "
+                  + ", ".join(f"{i}:{e[i]:.2e}" for i in worst) + f"; median {np.median(e):.2e}")
+        assert eg.max() <= TOL and edg.max() <= TOL, (label, eg.max(), edg.max())
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])

@@ -218,3 +218,82 @@ def test_peer_region_failure_is_agreed_by_every_rank(tmp_path):
         kinds = eval(kinds)
         assert kinds[0] == "alloc" and kinds[-1] == "free"
         assert kinds.count("open") == kinds.count("close")
+
+
+# ---- pair-once sharded sweep: item ranges, reduce-scatter, split (CUDA side: test_sym_gpu.py) --
+
+
+class _FakeSymCtx(_FakeCtx):
+    def dev_publish(self, *a):
+        self.log.append(("publish",))
+
+    def make_shards(self, *a):
+        return None
+
+
+def _sym_worker(rank, world, port, n, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "direct-nbody_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nbk.sharded import PeerShardedAccJerkSym, make_plan, sym_item_blocks, SYM_BLOCK
+        from oracle import oracle as O
+        m, q, p = O.make_plummer(n, 20243)
+        plan = make_plan(n, world, rank, align=SYM_BLOCK)
+
+        def sweep(sh, n_, eps2, item_range, sum6):
+            # what nbk_dev_grad_v_dgrad_v_sym_peer leaves: the sums restricted to the pairs of
+            # the rank's block pairs, for all bodies
+            sum6.zero_()
+            B = SYM_BLOCK
+            for i, j in sym_item_blocks(n_, *item_range):
+                ti, tj = (i * B, min((i + 1) * B, n_)), (j * B, min((j + 1) * B, n_))
+                g, dg = O.grad_v_dgrad_v_sum(m, q, p, eps2, targets=ti, sources=tj)
+                sum6[ti[0]:ti[1], 0:3] += torch.from_numpy(g)
+                sum6[ti[0]:ti[1], 3:6] += torch.from_numpy(dg)
+                if i != j:
+                    g, dg = O.grad_v_dgrad_v_sum(m, q, p, eps2, targets=tj, sources=ti)
+                    sum6[tj[0]:tj[1], 0:3] += torch.from_numpy(g)
+                    sum6[tj[0]:tj[1], 3:6] += torch.from_numpy(dg)
+
+        def reduce_scatter(out, inp):  # gloo has no reduce_scatter_tensor
+            tot = inp.clone()
+            dist.all_reduce(tot)
+            out.copy_(tot[rank * plan.shard:(rank + 1) * plan.shard])
+
+        def split(src, count, g, dg):
+            g[:count] = src[:count, 0:3]
+            dg[:count] = src[:count, 3:6]
+
+        sh = PeerShardedAccJerkSym(plan, torch.device("cpu"), _FakeSymCtx(rank), sweep=sweep,
+                                   reduce_scatter=reduce_scatter, split=split)
+        g, dg = sh.step(0.0)
+        np.save(os.path.join(out_dir, f"g{rank}.npy"), g[:plan.count].numpy())
+        np.save(os.path.join(out_dir, f"dg{rank}.npy"), dg[:plan.count].numpy())
+        np.save(os.path.join(out_dir, f"items{rank}.npy"), np.array(sh.item_range))
+        sh.regions.close(barrier=dist.barrier)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [4096, 5000])
+def test_two_rank_pair_once_plumbing(tmp_path, oracle, n):
+    """PeerShardedAccJerkSym: contiguous item ranges that cover the upper triangle once, the
+    reduce-scatter of the per-rank sums and the split give every rank its slice of the full
+    acc+jerk sums (to summation order)."""
+    from nbk.sharded import make_plan
+    world = 2
+    port = 29100 + (os.getpid() + n) % 300
+    mp.spawn(_sym_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    m, q, p = oracle.make_plummer(n, 20243)
+    g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q, p, 0.0)
+    items = [np.load(tmp_path / f"items{r}.npy") for r in range(world)]
+    nb = (n + 1023) // 1024
+    assert items[0][0] == 0 and items[0][1] == items[1][0] and items[1][1] == nb * (nb + 1) // 2
+    g = np.concatenate([np.load(tmp_path / f"g{r}.npy") for r in range(world)])
+    dg = np.concatenate([np.load(tmp_path / f"dg{r}.npy") for r in range(world)])
+    assert g.shape == (n, 3)
+    for a, b in ((g, g_ref), (dg, dg_ref)):
+        assert np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)) < 1e-13
+    plans = [make_plan(n, world, r, align=1024) for r in range(world)]
+    assert plans[0].shard % 1024 == 0 and plans[0].count + plans[1].count == n
