@@ -107,6 +107,7 @@ struct nbk_ctx {
   // single-process multi-GPU (nbk_create_multi): further contexts, one per extra device
   std::vector<nbk_ctx *> peers;
   cudaEvent_t ev_ready = nullptr;
+  cudaEvent_t ev_sum = nullptr;  // multi context: this device's pair-once sums are complete
   bool p2p_all = false;      // every device of the multi context can map every other's memory
   bool multi_sharded = false;  // the last multi_stage left the bodies sharded (peer-read sweeps)
   int multi_shard_rows = 0;
@@ -849,6 +850,119 @@ int multi_sweep(nbk_ctx *ctx, int n, const double *m, const double *q, const dou
   return NBK_OK;
 }
 
+// The full acc+jerk square of a multi context with every unordered pair evaluated once on the
+// whole box (sym.cuh): device d uploads and packs its own rows, runs its contiguous range of
+// block pairs (rows of both blocks read from their owners over NVLink) and reduces its slots to
+// sums for all bodies; after a second barrier it adds the devices' sums of ITS bodies in device
+// order (peer reads) and sends the slice home.  Streams are ordered with events.
+int multi_sym_acc_jerk(nbk_ctx *ctx, int n, const double *m, const double *q, const double *p,
+                       double eps2, double *gsum, double *dgsum) {
+  const int ndev = 1 + (int)ctx->peers.size();
+  int rows = (n + ndev - 1) / ndev;
+  rows = (rows + SYM_B - 1) / SYM_B * SYM_B;
+  ctx->multi_sharded = true;
+  ctx->multi_shard_rows = rows;
+  const long long items = sym_items(n);
+  std::vector<int> rcs(ndev, NBK_OK);
+  if (ctx->pool) ctx->pool->nparticipants = ndev;
+  auto ok_all = [&]() {
+    for (int e = 0; e < ndev; ++e)
+      if (rcs[e] != NBK_OK) return false;
+    return true;
+  };
+  auto pack_rows = [&](int d) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    int rc = NBK_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
+    const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
+    if (rc == NBK_OK) rc = reserve(c, c->d_packed, (size_t)rows * PK * sizeof(double));
+    if (rc == NBK_OK) rc = reserve(c, c->d_out[2], (size_t)n * 6 * sizeof(double));
+    if (rc == NBK_OK) rc = reserve(c, c->d_sympartial, sym_partial_bytes(n));
+    if (rc == NBK_OK && cnt > 0) {
+      rc = upload(c, c->d_m, m + a, cnt);
+      if (rc == NBK_OK) rc = upload(c, c->d_q, q + 3 * (size_t)a, 3 * (size_t)cnt);
+      if (rc == NBK_OK) rc = upload(c, c->d_vel, p + 3 * (size_t)a, 3 * (size_t)cnt);
+      if (rc == NBK_OK)
+        rc = pack(c, cnt, (const double *)c->d_m.p, (const double *)c->d_q.p,
+                  (const double *)c->d_vel.p, 0, (double *)c->d_packed.p, c->stream);
+    }
+    if (rc == NBK_OK && cudaEventRecord(c->ev_ready, c->stream) != cudaSuccess)
+      rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
+    rcs[d] = rc;
+  };
+  auto sweep_items = [&](int d) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    int rc = NBK_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "cudaSetDevice failed");
+    for (int e = 0; e < ndev && rc == NBK_OK; ++e)
+      if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_ready, 0) != cudaSuccess)
+        rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
+    const double *shard[MAX_PEERS];
+    for (int e = 0; e < ndev; ++e) shard[e] = (const double *)multi_dev(ctx, e)->d_packed.p;
+    if (rc == NBK_OK)
+      rc = sym_run(c, shard, rows, ndev, d, nullptr, 0, n, eps2, items * d / ndev,
+                   items * (d + 1) / ndev, (double *)c->d_out[2].p, nullptr, nullptr, 0, n,
+                   c->stream, true);
+    if (rc == NBK_OK && cudaEventRecord(c->ev_sum, c->stream) != cudaSuccess)
+      rc = fail(c, NBK_ERR_CUDA, "cudaEventRecord failed");
+    rcs[d] = rc;
+  };
+  auto gather_slice = [&](int d, bool swept) {
+    nbk_ctx *c = multi_dev(ctx, d);
+    cudaSetDevice(c->device);
+    int rc = rcs[d];
+    const int a = std::min(n, d * rows), b = std::min(n, (d + 1) * rows), cnt = b - a;
+    if (swept && rc == NBK_OK && cnt > 0) {
+      for (int e = 0; e < ndev && rc == NBK_OK; ++e)
+        if (e != d && cudaStreamWaitEvent(c->stream, multi_dev(ctx, e)->ev_sum, 0) != cudaSuccess)
+          rc = fail(c, NBK_ERR_CUDA, "cudaStreamWaitEvent failed");
+      if (rc == NBK_OK) rc = reserve(c, c->d_out[0], (size_t)cnt * 3 * sizeof(double));
+      if (rc == NBK_OK) rc = reserve(c, c->d_out[1], (size_t)cnt * 3 * sizeof(double));
+      if (rc == NBK_OK) {
+        SymGatherParams G;
+        memset(&G, 0, sizeof G);
+        for (int e = 0; e < ndev; ++e) G.sum6[e] = (const double *)multi_dev(ctx, e)->d_out[2].p;
+        G.ndev = ndev;
+        G.a = a;
+        G.b = b;
+        G.g = (double *)c->d_out[0].p;
+        G.dg = (double *)c->d_out[1].p;
+        sym_gather_kernel<<<(cnt * 6 + 255) / 256, 256, 0, c->stream>>>(G);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(c, NBK_ERR_CUDA, "sym_gather_kernel launch failed");
+        c->launches++;
+      }
+      if (rc == NBK_OK) rc = download(c, gsum + 3 * (size_t)a, c->d_out[0], 3 * (size_t)cnt);
+      if (rc == NBK_OK) rc = download(c, dgsum + 3 * (size_t)a, c->d_out[1], 3 * (size_t)cnt);
+    }
+    const int rc2 = sync(c);
+    rcs[d] = rc != NBK_OK ? rc : rc2;
+  };
+  if (ctx->pool) {
+    multi_for(ctx, [&](int d) {
+      pack_rows(d);
+      ctx->pool->barrier();
+      const bool ok = ok_all();
+      if (ok) sweep_items(d);
+      ctx->pool->barrier();  // every device's "sums complete" event is recorded (or failed)
+      gather_slice(d, ok && ok_all());
+    });
+  } else {
+    for (int d = 0; d < ndev; ++d) pack_rows(d);
+    const bool ok = ok_all();
+    for (int d = 0; d < ndev && ok; ++d) sweep_items(d);
+    const bool ok2 = ok && ok_all();
+    // every device's gather is enqueued before the first blocking read-back completes
+    for (int d = 0; d < ndev; ++d) gather_slice(d, ok2);
+  }
+  cudaSetDevice(ctx->device);
+  for (int d = 0; d < ndev; ++d)
+    if (rcs[d] != NBK_OK) {
+      nbk_ctx *c = multi_dev(ctx, d);
+      return c == ctx ? rcs[d] : fail(ctx, rcs[d], "device %d: %s", c->device, nbk_last_error(c));
+    }
+  return NBK_OK;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -893,6 +1007,7 @@ int nbk_create(nbk_ctx **out, int device) {
   cudaError_t e3 = cudaEventCreate(&c->ev1);
   cudaError_t e4 = cudaMallocHost((void **)&c->h_scalar, 64);
   cudaError_t e5 = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
+  if (e5 == cudaSuccess) e5 = cudaEventCreateWithFlags(&c->ev_sum, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess ||
       e5 != cudaSuccess) {
     nbk_destroy(c);
@@ -966,6 +1081,7 @@ void nbk_destroy(nbk_ctx *c) {
   c->peers.clear();
   cudaSetDevice(c->device);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->ev_sum) cudaEventDestroy(c->ev_sum);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->d_t,     &c->d_f,      &c->d_df,     &c->d_aux_in2,
                     &c->d_m,     &c->d_q,      &c->d_vel,    &c->d_aux_in, &c->d_packed,
@@ -1037,6 +1153,12 @@ int nbk_grad_v_dgrad_v_sum(nbk_ctx *ctx, int n, const double *m, const double *q
   if (!p) return fail(ctx, NBK_ERR_ARG, "null momentum array");
   if (!ctx->peers.empty() && t1 > t0 && s1 > s0) {
     if (!gsum || !dgsum) return fail(ctx, NBK_ERR_ARG, "null output");
+    // the full square on a box whose devices map each other's memory: every pair once
+    if (t0 == 0 && s0 == 0 && t1 == n && s1 == n && ctx->p2p_all && ctx->sym_mode != 0 &&
+        n >= (int)(1 + ctx->peers.size()) * SYM_B &&
+        (ctx->sym_mode == 2 || sym_items(n) >= 4LL * ctx->sm_count * (1 + (long long)ctx->peers.size())) &&
+        sym_partial_bytes(n) <= ((size_t)24 << 30))
+      return multi_sym_acc_jerk(ctx, n, m, q, p, eps2, gsum, dgsum);
     return multi_sweep(ctx, n, m, q, p, 0, eps2, t0, t1, s0, s1,
                        [=](nbk_ctx *c, const Slice &sl, SweepParams P) -> int {
                          const size_t cnt = 3 * (size_t)(sl.b - sl.a);

@@ -325,6 +325,23 @@ __global__ void __launch_bounds__(192) sym_reduce_kernel(const SymReduceParams R
   }
 }
 
+// Bodies [a, b): the per-device sums sum6[e][body][0..5] (peer-mapped) added in device order ->
+// gsum, dgsum rows [b - a][3].  The single-process form of the reduce-scatter.
+struct SymGatherParams {
+  const double *sum6[MAX_PEERS];
+  int ndev, a, b;
+  double *g, *dg;
+};
+__global__ void sym_gather_kernel(const SymGatherParams G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (G.b - G.a) * 6) return;
+  const int body = i / 6, c = i % 6;
+  double s = 0.0;
+  for (int e = 0; e < G.ndev; ++e) s += G.sum6[e][(size_t)(G.a + body) * 6 + c];
+  if (c < 3) G.g[body * 3 + c] = s;
+  else G.dg[body * 3 + c - 3] = s;
+}
+
 // A rank's slice of the reduce-scattered sums [count][6] -> gsum, dgsum [count][3].
 __global__ void sym_split_kernel(const double *__restrict__ in6, int count, double *__restrict__ g,
                                  double *__restrict__ dg) {

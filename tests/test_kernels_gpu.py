@@ -523,6 +523,14 @@ def test_virtual_multi_device_context_on_one_gpu(oracle, monkeypatch, ndev, thre
             assert rel_err(b[0], a[0]) <= 1e-13 and rel_err(b[1], a[1]) <= 1e-13
         g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, q * 1.03, p, 1e-4)
         assert rel_err(b[0], g_ref) <= TOL and rel_err(b[1], dg_ref) <= TOL
+        # the full square with every pair evaluated once across the "devices" (block pairs dealt
+        # out per device, per-device sums gathered in device order); twice: identical
+        multi.set_sym(2)
+        c = multi.grad_v_dgrad_v_sum(m, q * 1.03, p, 1e-4)
+        c2 = multi.grad_v_dgrad_v_sum(m, q * 1.03, p, 1e-4)
+        multi.set_sym(1)
+        assert rel_err(c[0], g_ref) <= TOL and rel_err(c[1], dg_ref) <= TOL
+        assert np.array_equal(c[0], c2[0]) and np.array_equal(c[1], c2[1])
         assert rel_err(multi.grad_v_sum(m, q, 0.0), one.grad_v_sum(m, q, 0.0)) <= 1e-13
         pa, ta = one.v_sum(m, q, 0.0)
         pb, tb = multi.v_sum(m, q, 0.0)
