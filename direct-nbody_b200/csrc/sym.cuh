@@ -30,10 +30,18 @@
 
 namespace nbk {
 
+#ifndef SYM_UNROLL
+#define SYM_UNROLL 2
+#endif
+#ifndef SYM_NEWTON
+#define SYM_NEWTON 1
+#endif
+constexpr int SYM_ROUNDS_UNROLLED = SYM_UNROLL;
 constexpr int SYM_NT = 256;
 constexpr int SYM_IPT = 4;
 constexpr int SYM_B = SYM_NT * SYM_IPT;                       // 1024 bodies per block
-constexpr size_t SYM_SMEM = (size_t)(7 + 6) * SYM_B * sizeof(double);  // 104 KB
+constexpr size_t SYM_SMEM = (size_t)(7 + 6) * SYM_B * sizeof(double);  // 104 KB: sources as
+// three double2 arrays {x,y} {z,m} {vx,vy} + vz (3 LDS.128 + 1 LDS.64 per source), six sums
 
 struct SymParams {
   const double *shard[MAX_PEERS];  // packed rows [shard_rows][PK] of every owner
@@ -70,8 +78,8 @@ template <bool CHECK>
 __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const int J, double *sm) {
   constexpr int B = SYM_B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double *sx = sm, *sy = sm + B, *sz = sm + 2 * B, *smj = sm + 3 * B, *svx = sm + 4 * B,
-         *svy = sm + 5 * B, *svz = sm + 6 * B, *jacc = sm + 7 * B;
+  double2 *sxy = reinterpret_cast<double2 *>(sm), *szm = sxy + B, *svxy = sxy + 2 * B;
+  double *svz = sm + 6 * B, *jacc = sm + 7 * B;
   const bool diag = I == J;
   const double eps2 = P.eps2;
 
@@ -108,8 +116,7 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
         c = rows[(size_t)jl * 4 + 2];
         d = rows[(size_t)jl * 4 + 3];
       }
-      sx[jl] = a.x, sy[jl] = a.y, sz[jl] = b.x, smj[jl] = b.y;
-      svx[jl] = c.x, svy[jl] = c.y, svz[jl] = d.x;
+      sxy[jl] = a, szm[jl] = b, svxy[jl] = c, svz[jl] = d.x;
 #pragma unroll
       for (int c6 = 0; c6 < 6; ++c6) jacc[c6 * B + jl] = 0.0;
     }
@@ -126,14 +133,12 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
   for (int g = 0; g < 8; ++g) {
     for (int s4 = 0; s4 < 4; ++s4) {
       const int grp = ((((warp + g) & 7) << 2) + s4) << 5;  // first source of the group
-      double ja[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) ja[k] = 0.0;
-#pragma unroll 2
-      for (int rd = 0; rd < 32; ++rd) {
+      // one round: the lane's source of this round against its 4 targets
+      auto round = [&](const int rd, double (&ja)[6]) {
         const int sl = grp + ((lane + rd) & 31);
-        const double jx = sx[sl], jy = sy[sl], jz = sz[sl], jm = smj[sl];
-        const double jvx = svx[sl], jvy = svy[sl], jvz = svz[sl];
+        const double2 jxy = sxy[sl], jzm = szm[sl], jvxy = svxy[sl];
+        const double jx = jxy.x, jy = jxy.y, jz = jzm.x, jm = jzm.y;
+        const double jvx = jvxy.x, jvy = jvxy.y, jvz = svz[sl];
         double dx[SYM_IPT], dy[SYM_IPT], dz[SYM_IPT], ux[SYM_IPT], uy[SYM_IPT], uz[SYM_IPT];
         double r2[SYM_IPT], rv[SYM_IPT], y0[SYM_IPT], y[SYM_IPT], wj[SYM_IPT], wi[SYM_IPT],
             a3[SYM_IPT];
@@ -177,8 +182,13 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
           const double tt = r2[r] * y0[r];
           const double e = fma(-tt, y0[r], 1.0);
           const double pp = fma(0.375, e, 0.5);
+#if SYM_NEWTON
           const double q = e * pp;
           y[r] = fma(y0[r], q, y0[r]);
+#else
+          const double q = e * y0[r];
+          y[r] = fma(pp, q, y0[r]);
+#endif
         }
 #pragma unroll
         for (int r = 0; r < SYM_IPT; ++r) {
@@ -212,6 +222,13 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
           ja[4] = fma(wi[r], uy[r], ja[4]);
           ja[5] = fma(wi[r], uz[r], ja[5]);
         }
+      };
+      double ja[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ja[k] = 0.0;
+#pragma unroll SYM_ROUNDS_UNROLLED
+      for (int rd = 0; rd < 32; ++rd) {
+        round(rd, ja);
         // the source's sums follow it to the lane that takes it next round
 #pragma unroll
         for (int k = 0; k < 6; ++k) ja[k] = __shfl_sync(0xffffffffu, ja[k], src_lane);
