@@ -136,10 +136,10 @@ def make_config(n, world, exchange="peer", overlap=0, pairs="once"):
     if world == 1:
         sharding = "single GPU"
     elif exchange == "peer" and pairs == "once":
-        sharding = (f"bodies/{world} (rows stay with their owner), block pairs of the upper "
-                    f"triangle/{world}: every unordered pair evaluated once on the whole box, "
-                    "kernels read both blocks' rows from the owning GPUs over NVLink (peer "
-                    "memory, CUDA IPC), one reduce-scatter of the per-rank sums (48 B/body)")
+        sharding = (f"bodies/{world}, block pairs of the upper triangle/{world}: every unordered "
+                    "pair evaluated once on the whole box; each rank's packing kernel stores its "
+                    "rows into every rank's gathered array over NVLink (peer memory, CUDA IPC, "
+                    "ready flags), one reduce-scatter of the per-rank sums (48 B/body)")
     elif exchange == "peer":
         sharding = (f"targets/{world}, sweep kernel reads remote source tiles from the owning GPU "
                     "over NVLink (peer memory, CUDA IPC); no all-gather step")
@@ -396,7 +396,10 @@ def run_ours(args):
            for _ in range(args.steps)]
     if exchange == "peer":
         barrier()  # every rank's rows are published; the kernel alone needs no flags
-        shards = ctx.make_shards(plan.rank, plan.shard, sh.regions.packed(sh.cur))
+        if pairs == "once":
+            shards = sh.local_shards(with_flags=False)  # the rank's gathered rows, local memory
+        else:
+            shards = ctx.make_shards(plan.rank, plan.shard, sh.regions.packed(sh.cur))
 
         if pairs == "once":
             items = ctx.sym_items(n)
@@ -550,7 +553,7 @@ def run_ours(args):
             print(f"cpu_baseline unavailable: {e}", file=sys.stderr)
         traffic, traffic_file = ncu_traffic_bytes(pairs) if world == 1 else (None, None)
         if pairs == "once":
-            kname = "sym_sweep_kernel (pair-once, csrc/sym.cuh)" + (", rows read from their owners" if exchange == "peer" else "")
+            kname = "sym_sweep_kernel (pair-once, csrc/sym.cuh)"
             algo = ("algorithmic = per block pair 2 x 64 KB rows read + 2 x 48 KB partial sums "
                     "written, + the slot reduction reading them once")
         else:

@@ -2819,6 +2819,28 @@ int nbk_dev_pack(nbk_ctx *ctx, int n, const double *d_m, const double *d_q, cons
   return pack(ctx, n, d_m, d_q, d_vel, is_velocity, d_packed, (cudaStream_t)stream);
 }
 
+int nbk_dev_pack_push(nbk_ctx *ctx, int n, const double *d_m, const double *d_q,
+                      const double *d_vel, int is_velocity, int nranks, double *const *d_dst,
+                      void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (n < 0 || !d_m || !d_q || !d_dst || nranks < 1 || nranks > MAX_PEERS)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_pack_push: bad arguments");
+  PackPushParams D;
+  memset(&D, 0, sizeof D);
+  for (int r = 0; r < nranks; ++r) {
+    if (!d_dst[r] || ((uintptr_t)d_dst[r] & 15))
+      return fail(ctx, NBK_ERR_ARG, "nbk_dev_pack_push: destination %d null or misaligned", r);
+    D.dst[r] = d_dst[r];
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return NBK_OK;
+  pack_push_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_m, d_q, d_vel,
+                                                                      is_velocity, nranks, D);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
+}
+
 #define DEV_COMMON()                                                                     \
   do {                                                                                   \
     TRY(check_ranges(ctx, n_total, t0, t1, s0, s1));                                     \

@@ -359,6 +359,38 @@ __global__ void sym_gather_kernel(const SymGatherParams G) {
   else G.dg[body * 3 + c - 3] = s;
 }
 
+// Pack (m, q, p|v) rows as pack_kernel does and store every row into nranks destinations: this
+// rank's place in every rank's gathered row array (peer-mapped over NVLink) - the all-gather of
+// the sharded pair-once sweep as remote stores of the packing kernel itself.  The publish
+// kernel that follows on the stream releases the flag at system scope.
+struct PackPushParams {
+  double *dst[MAX_PEERS];
+};
+__global__ void pack_push_kernel(int n, const double *__restrict__ m, const double *__restrict__ q,
+                                 const double *__restrict__ vel, int is_velocity, int nranks,
+                                 const PackPushParams D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double mi = m[i];
+    double vx = 0.0, vy = 0.0, vz = 0.0;
+    if (vel) {
+      vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+      if (!is_velocity) {
+        vx = __ddiv_rn(vx, mi);
+        vy = __ddiv_rn(vy, mi);
+        vz = __ddiv_rn(vz, mi);
+      }
+    }
+    const double2 a = make_double2(q[3 * i], q[3 * i + 1]), b = make_double2(q[3 * i + 2], mi);
+    const double2 c = make_double2(vx, vy), d = make_double2(vz, 0.0);
+    for (int r = 0; r < nranks; ++r) {
+      double2 *o = reinterpret_cast<double2 *>(D.dst[r] + (size_t)i * PK);
+      o[0] = a, o[1] = b, o[2] = c, o[3] = d;
+    }
+  }
+  __threadfence_system();
+}
+
 // A rank's slice of the reduce-scattered sums [count][6] -> gsum, dgsum [count][3].
 __global__ void sym_split_kernel(const double *__restrict__ in6, int count, double *__restrict__ g,
                                  double *__restrict__ dg) {

@@ -135,6 +135,7 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sym_peer": (_i, [_vp, _psh, _i, _d, C.c_longlong, C.c_longlong, _vp,
                                              _vp]),
     "nbk_dev_split6": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "nbk_dev_pack_push": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, C.POINTER(_vp), _vp]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
 
@@ -261,6 +262,12 @@ class Context:
         self._ck(self._lib.nbk_dev_grad_v_dgrad_v_sym_peer(
             self._h, C.byref(shards), n_total, eps2, int(items[0]), int(items[1]), d_sum6,
             stream or None))
+
+    def dev_pack_push(self, n, d_m, d_q, d_vel, is_velocity, dst, stream=0):
+        """dev_pack with every row stored into len(dst) destinations (peer-mapped addresses)."""
+        arr = (_vp * len(dst))(*dst)
+        self._ck(self._lib.nbk_dev_pack_push(self._h, n, d_m, d_q, d_vel or None, int(is_velocity),
+                                             len(dst), arr, stream or None))
 
     def dev_split6(self, d_sum6, count, d_gsum, d_dgsum, stream=0):
         self._ck(self._lib.nbk_dev_split6(self._h, d_sum6, int(count), d_gsum, d_dgsum,

@@ -227,11 +227,15 @@ def next_row_buffer(cur: int, stepped_since_load: bool) -> int:
 class PeerRegions:
     """This rank's region plus the mapped regions of every other rank."""
 
-    def __init__(self, plan: ShardPlan, ctx, K: int = 0, group=None, exchange=None):
+    def __init__(self, plan: ShardPlan, ctx, K: int = 0, group=None, exchange=None,
+                 rows_per_buffer=None):
         if plan.shard % PEER_TILE:
             raise ValueError("peer exchange needs make_plan(..., align=128)")
         self.plan, self.ctx, self.K = plan, ctx, K
-        self.total, self.packed_off, self.aux_off = peer_region_layout(plan.shard, K)
+        # rows_per_buffer: a row buffer that holds more than the rank's own shard (the gathered
+        # array of the pair-once sweep, filled by every rank's remote stores)
+        self.rows = plan.shard if rows_per_buffer is None else rows_per_buffer
+        self.total, self.packed_off, self.aux_off = peer_region_layout(self.rows, K)
         self.base = [0] * plan.world
         self._opened = []
         self.group = group
@@ -291,10 +295,11 @@ class _PeerSharded:
     """Common part of the peer-exchange drivers: this rank's rows in the shared region, the
     publish step and the shard table of the current row buffer."""
 
-    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None, K=0):
+    def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None, K=0,
+                 rows_per_buffer=None):
         import torch
         self.torch, self.plan, self.device, self.ctx, self.group = torch, plan, device, ctx, group
-        self.regions = PeerRegions(plan, ctx, K, group, exchange)
+        self.regions = PeerRegions(plan, ctx, K, group, exchange, rows_per_buffer)
         self.epoch, self.cur = 0, 0
         self._stepped_since_load = True  # the first load_local takes the other buffer
 
@@ -315,8 +320,7 @@ class _PeerSharded:
         d_m = torch.as_tensor(m[sl], dtype=torch.float64).to(self.device).contiguous()
         d_q = torch.as_tensor(q[sl], dtype=torch.float64).to(self.device).contiguous()
         d_v = torch.as_tensor(vel[sl], dtype=torch.float64).to(self.device).contiguous()
-        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_v.data_ptr(), is_velocity,
-                          self.regions.packed(self.cur)[pl.rank], self._stream())
+        self._pack(pl.count, d_m, d_q, d_v, is_velocity)
         self._local = (d_m, d_v) if not is_velocity else (d_m, d_v * d_m[:, None])  # m, p
         torch.cuda.current_stream(self.device).synchronize()
 
@@ -330,8 +334,12 @@ class _PeerSharded:
         self._stepped_since_load = False
         if pl.count == 0:
             return
-        self.ctx.dev_pack(pl.count, d_m.data_ptr(), d_q.data_ptr(), d_vel.data_ptr(), is_velocity,
-                          self.regions.packed(self.cur)[pl.rank], self._stream())
+        self._pack(pl.count, d_m, d_q, d_vel, is_velocity)
+
+    def _pack(self, count, d_m, d_q, d_vel, is_velocity):
+        """This rank's rows into its own row buffer `cur` (the peers read them from there)."""
+        self.ctx.dev_pack(count, d_m.data_ptr(), d_q.data_ptr(), d_vel.data_ptr(), is_velocity,
+                          self.regions.packed(self.cur)[self.plan.rank], self._stream())
 
     def _publish(self):
         """New epoch: tell the peers this rank's rows are in place; returns the shard table."""
@@ -402,17 +410,21 @@ def sym_item_blocks(n: int, item0: int, item1: int):
 class PeerShardedAccJerkSym(_PeerSharded):
     """The sharded acc+jerk sweep with every unordered pair evaluated ONCE on the whole box
     (hermite.ml:157-166 does the same on one core): the block pairs of the upper triangle are
-    dealt out to the ranks in contiguous ranges, each rank's kernel reads the rows of both
-    blocks from their owners over NVLink (nbk_dev_grad_v_dgrad_v_sym_peer) and leaves its
-    partial sums for ALL bodies; ONE reduce-scatter (the path's exchange step) hands every rank
-    the totals of its own slice.  The plan needs make_plan(..., align=1024).  `sweep`,
+    dealt out to the ranks in contiguous ranges.  Exchange steps: the packing kernel stores a
+    rank's rows into every rank's gathered array over NVLink (the all-gather, fused into the
+    pack; ready flags as in the other peer drivers), each rank's kernel runs its block pairs on
+    local memory behind the flags (nbk_dev_grad_v_dgrad_v_sym_peer) and leaves partial sums for
+    ALL bodies, and ONE reduce-scatter hands every rank the totals of its own slice.  The plan needs make_plan(..., align=1024).  `sweep`,
     `reduce_scatter` and `split` are injectable for the CPU plumbing tests."""
 
     def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None,
                  reduce_scatter=None, sweep=None, split=None):
         if plan.shard % SYM_BLOCK:
             raise ValueError("the pair-once sweep needs make_plan(..., align=1024)")
-        super().__init__(plan, device, ctx, group, exchange)
+        # every rank's row buffers hold ALL rows: a rank's block pairs touch rows of every owner
+        # several times per sweep, so the rows are gathered once - by the packing kernel's own
+        # remote stores (nbk_dev_pack_push) - and the sweep reads local memory
+        super().__init__(plan, device, ctx, group, exchange, rows_per_buffer=max(plan.npad, 1))
         torch = self.torch
         self.sum6 = torch.zeros(max(plan.npad, 1), 6, dtype=torch.float64, device=device)
         self.out6 = torch.zeros(max(plan.shard, 1), 6, dtype=torch.float64, device=device)
@@ -435,9 +447,26 @@ class PeerShardedAccJerkSym(_PeerSharded):
                                     self._stream())
         self._reduce_scatter, self._sweep, self._split = reduce_scatter, sweep, split
 
+    def _pack(self, count, d_m, d_q, d_vel, is_velocity):
+        """This rank's rows into its place in EVERY rank's gathered array (buffer `cur`)."""
+        pl = self.plan
+        off = pl.rank * pl.shard * PACKED * 8
+        dst = [b + off for b in self.regions.packed(self.cur)]
+        self.ctx.dev_pack_push(count, d_m.data_ptr(), d_q.data_ptr(), d_vel.data_ptr(), is_velocity,
+                               dst, self._stream())
+
+    def local_shards(self, with_flags=True):
+        """Shard table of the LOCAL gathered array: owner r's rows start at r * shard rows."""
+        pl, rg = self.plan, self.regions
+        base = rg.packed(self.cur)[pl.rank]
+        rows = [base + r * pl.shard * PACKED * 8 for r in range(pl.world)]
+        flags = rg.ready_local if (with_flags and pl.world > 1) else 0
+        return self.ctx.make_shards(pl.rank, pl.shard, rows, flags, self.epoch)
+
     def step(self, eps2: float = 0.0):
         pl = self.plan
-        sh = self._publish()
+        self._publish()
+        sh = self.local_shards()
         self._sweep(sh, pl.n, eps2, self.item_range, self.sum6)
         if pl.world > 1:
             self._reduce_scatter(self.out6, self.sum6)

@@ -486,6 +486,15 @@ int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total
 int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_total, double eps2,
                                     long long item0, long long item1, double *d_sum6,
                                     void *stream);
+/* nbk_dev_pack with the rows stored into nranks destinations: d_dst[r] = this rank's place in
+ * rank r's gathered row array, mapped on this device.  The exchange step of the sharded
+ * pair-once sweep ("each step all-gathers positions, velocities and masses"), done by the
+ * packing kernel's own remote stores; nbk_dev_publish after it makes the rows visible, and the
+ * sweep on every rank then reads its LOCAL gathered array behind the ready flags (an nbk_shards
+ * whose packed[r] all point into that local array). */
+int nbk_dev_pack_push(nbk_ctx *ctx, int n, const double *d_m, const double *d_q,
+                      const double *d_vel, int is_velocity, int nranks, double *const *d_dst,
+                      void *stream);
 /* Rows [count][6] of (reduce-scattered) sums -> gsum, dgsum [count][3]. */
 int nbk_dev_split6(nbk_ctx *ctx, const double *d_sum6, int count, double *d_gsum, double *d_dgsum,
                    void *stream);
