@@ -40,8 +40,10 @@ constexpr int SYM_ROUNDS_UNROLLED = SYM_UNROLL;
 constexpr int SYM_NT = 256;
 constexpr int SYM_IPT = 4;
 constexpr int SYM_B = SYM_NT * SYM_IPT;                       // 1024 bodies per block
-constexpr size_t SYM_SMEM = (size_t)(7 + 6) * SYM_B * sizeof(double);  // 104 KB: sources as
-// three double2 arrays {x,y} {z,m} {vx,vy} + vz (3 LDS.128 + 1 LDS.64 per source), six sums
+// Shared memory: the sources as three double2 arrays {x,y} {z,m} {vx,vy} + vz (3 LDS.128 +
+// 1 LDS.64 per source), every group of 32 stored TWICE in a row (64 entries) so that lane l
+// reads entry l + round without wrapping the index, + six arrays of j-side sums: 160 KB.
+constexpr size_t SYM_SMEM = (size_t)(2 * 7 + 6) * SYM_B * sizeof(double);
 
 struct SymParams {
   const double *shard[MAX_PEERS];  // packed rows [shard_rows][PK] of every owner
@@ -78,8 +80,8 @@ template <bool CHECK>
 __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const int J, double *sm) {
   constexpr int B = SYM_B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double2 *sxy = reinterpret_cast<double2 *>(sm), *szm = sxy + B, *svxy = sxy + 2 * B;
-  double *svz = sm + 6 * B, *jacc = sm + 7 * B;
+  double2 *sxy = reinterpret_cast<double2 *>(sm), *szm = sxy + 2 * B, *svxy = sxy + 4 * B;
+  double *svz = sm + 12 * B, *jacc = sm + 14 * B;
   const bool diag = I == J;
   const double eps2 = P.eps2;
 
@@ -116,7 +118,9 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
         c = rows[(size_t)jl * 4 + 2];
         d = rows[(size_t)jl * 4 + 3];
       }
-      sxy[jl] = a, szm[jl] = b, svxy[jl] = c, svz[jl] = d.x;
+      const int e = ((jl >> 5) << 6) + (jl & 31);  // entry and its copy 32 further on
+      sxy[e] = a, szm[e] = b, svxy[e] = c, svz[e] = d.x;
+      sxy[e + 32] = a, szm[e + 32] = b, svxy[e + 32] = c, svz[e + 32] = d.x;
 #pragma unroll
       for (int c6 = 0; c6 < 6; ++c6) jacc[c6 * B + jl] = 0.0;
     }
@@ -133,12 +137,13 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
   for (int g = 0; g < 8; ++g) {
     for (int s4 = 0; s4 < 4; ++s4) {
       const int grp = ((((warp + g) & 7) << 2) + s4) << 5;  // first source of the group
+      const int gent = 2 * grp + lane;
       // one round: the lane's source of this round against its 4 targets
       auto round = [&](const int rd, double (&ja)[6]) {
-        const int sl = grp + ((lane + rd) & 31);
-        const double2 jxy = sxy[sl], jzm = szm[sl], jvxy = svxy[sl];
+        const int e = gent + rd;  // source grp + (lane + rd) mod 32, through the doubled group
+        const double2 jxy = sxy[e], jzm = szm[e], jvxy = svxy[e];
         const double jx = jxy.x, jy = jxy.y, jz = jzm.x, jm = jzm.y;
-        const double jvx = jvxy.x, jvy = jvxy.y, jvz = svz[sl];
+        const double jvx = jvxy.x, jvy = jvxy.y, jvz = svz[e];
         double dx[SYM_IPT], dy[SYM_IPT], dz[SYM_IPT], ux[SYM_IPT], uy[SYM_IPT], uz[SYM_IPT];
         double r2[SYM_IPT], rv[SYM_IPT], y0[SYM_IPT], y[SYM_IPT], wj[SYM_IPT], wi[SYM_IPT],
             a3[SYM_IPT];
@@ -156,7 +161,8 @@ __device__ __forceinline__ void sym_item(const SymParams &P, const int I, const 
           wj[r] = jm;
           wi[r] = tm[r];
           if (CHECK) {
-            const bool off = (jbase + sl == ig[r]) || (jbase + sl >= P.n) || (ig[r] >= P.n);
+            const int jg = jbase + grp + ((lane + rd) & 31);
+            const bool off = (jg == ig[r]) || (jg >= P.n) || (ig[r] >= P.n);
             r2[r] = off ? 1.0 : r2[r];
             wj[r] = off ? 0.0 : wj[r];
             wi[r] = off ? 0.0 : wi[r];
