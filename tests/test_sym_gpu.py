@@ -132,6 +132,58 @@ def test_pair_once_item_ranges_on_virtual_ranks(ctx, oracle, n, world):
             ctx.peer_free(b)
 
 
+@pytest.mark.parametrize("n,world", [(9000, 3), (16384, 4)])
+def test_pair_once_pushed_rows_on_virtual_ranks(ctx, oracle, n, world):
+    """The exchange of PeerShardedAccJerkSym on virtual ranks: every rank's packing kernel
+    stores its rows into its place in EVERY rank's gathered array (nbk_dev_pack_push), publishes,
+    and each rank runs its item range on its own gathered array behind the flags.  Two epochs
+    with moved bodies in alternating buffers; the gathered arrays equal a plain pack of all
+    bodies bit for bit and the ranks' sums add up to the oracle's rows."""
+    import torch
+    from nbk.sharded import make_plan, peer_region_layout, sym_item_range
+    dev = torch.device("cuda", 0)
+    m, q, p = oracle.make_plummer(n, 77)
+    plans = [make_plan(n, world, r, align=1024) for r in range(world)]
+    npad = plans[0].npad
+    total, poff, _ = peer_region_layout(npad)
+    bases = [ctx.peer_alloc(total, want_handle=False)[0] for _ in range(world)]
+    st = torch.cuda.current_stream().cuda_stream
+    items = ctx.sym_items(n)
+    d_m, d_p = (torch.as_tensor(a).to(dev).contiguous() for a in (m, p))
+    try:
+        for epoch, buf, scale in ((1, 1, 1.0), (2, 0, 1.01)):
+            qq = q * scale
+            d_q = torch.as_tensor(qq).to(dev).contiguous()
+            ref_rows = torch.zeros(n, 8, dtype=torch.float64, device=dev)
+            ctx.dev_pack(n, d_m.data_ptr(), d_q.data_ptr(), d_p.data_ptr(), False,
+                         ref_rows.data_ptr(), st)
+            for pl in plans:
+                dst = [b + poff[buf] + pl.rank * pl.shard * 64 for b in bases]
+                ctx.dev_pack_push(pl.count, d_m[pl.t0:].data_ptr(), d_q[pl.t0:].data_ptr(),
+                                  d_p[pl.t0:].data_ptr(), False, dst, st)
+                ctx.dev_publish(pl.rank, bases, epoch, st)
+            tot = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+            for pl in plans:
+                rows = [bases[pl.rank] + poff[buf] + r * pl.shard * 64 for r in range(world)]
+                sh = ctx.make_shards(pl.rank, pl.shard, rows, bases[pl.rank], epoch)
+                a = torch.empty(n, 6, dtype=torch.float64, device=dev)
+                ctx.dev_grad_v_dgrad_v_sym_peer(sh, n, 0.0, sym_item_range(items, world, pl.rank),
+                                                a.data_ptr(), st)
+                b = torch.empty(n, 6, dtype=torch.float64, device=dev)
+                ctx.dev_grad_v_dgrad_v_sym(ref_rows.data_ptr(), n, 0.0,
+                                           sym_item_range(items, world, pl.rank), b.data_ptr(), st)
+                torch.cuda.synchronize()
+                assert torch.equal(a, b)  # the gathered rows are the plain pack, bit for bit
+                tot += a
+            g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, qq, p, 0.0)
+            t = tot.cpu().numpy()
+            assert _rel(t[:, 0:3], g_ref).max() <= TOL and _rel(t[:, 3:6], dg_ref).max() <= TOL
+    finally:
+        torch.cuda.synchronize()
+        for b in bases:
+            ctx.peer_free(b)
+
+
 def test_pair_once_argument_errors(ctx):
     import nbk
     import torch
@@ -147,3 +199,6 @@ def test_pair_once_argument_errors(ctx):
     sh = ctx.make_shards(0, 1000, [rows.data_ptr()])  # shard_rows not a multiple of 1024
     with pytest.raises(nbk.NbkError):
         ctx.dev_grad_v_dgrad_v_sym_peer(sh, 1000, 0.0, (0, 1), out.data_ptr())
+    with pytest.raises(nbk.NbkError):  # a null destination
+        ctx.dev_pack_push(16, rows.data_ptr(), rows.data_ptr(), rows.data_ptr(), False,
+                          [rows.data_ptr(), 0])
