@@ -139,7 +139,8 @@ def make_config(n, world, exchange="peer", overlap=0, pairs="once"):
         sharding = (f"bodies/{world}, block pairs of the upper triangle/{world}: every unordered "
                     "pair evaluated once on the whole box; each rank's packing kernel stores its "
                     "rows into every rank's gathered array over NVLink (peer memory, CUDA IPC, "
-                    "ready flags), one reduce-scatter of the per-rank sums (48 B/body)")
+                    "ready flags); the per-rank sums (48 B/body) meet in each rank's own peer "
+                    "reads of its slice, in rank order")
     elif exchange == "peer":
         sharding = (f"targets/{world}, sweep kernel reads remote source tiles from the owning GPU "
                     "over NVLink (peer memory, CUDA IPC); no all-gather step")
@@ -406,7 +407,7 @@ def run_ours(args):
             my_items = sym_item_range(items, world, rank)
 
             def kernel_only():
-                ctx.dev_grad_v_dgrad_v_sym_peer(shards, n, 0.0, my_items, sh.sum6.data_ptr(), sptr)
+                ctx.dev_grad_v_dgrad_v_sym_peer(shards, n, 0.0, my_items, sh.sums_ptr(), sptr)
         else:
             def kernel_only():
                 ctx.dev_grad_v_dgrad_v_sum_peer(shards, n, 0.0, (t0, t1), (0, n), g.data_ptr(),

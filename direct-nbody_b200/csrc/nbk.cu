@@ -923,6 +923,7 @@ int multi_sym_acc_jerk(nbk_ctx *ctx, int n, const double *m, const double *q, co
         memset(&G, 0, sizeof G);
         for (int e = 0; e < ndev; ++e) G.sum6[e] = (const double *)multi_dev(ctx, e)->d_out[2].p;
         G.ndev = ndev;
+        G.self = d;
         G.a = a;
         G.b = b;
         G.g = (double *)c->d_out[0].p;
@@ -2888,6 +2889,36 @@ int nbk_dev_grad_v_dgrad_v_sym(nbk_ctx *ctx, const double *d_packed, int n_total
   const long long rows_cap = (((long long)n_total + SYM_B - 1) / SYM_B) * SYM_B;
   return sym_run(ctx, &d_packed, rows_cap, 1, 0, nullptr, 0, n_total, eps2, item0, item1, d_sum6,
                  nullptr, nullptr, 0, n_total, (cudaStream_t)stream, false);
+}
+
+int nbk_dev_sym_gather_peer(nbk_ctx *ctx, int nranks, int self, const double *const *d_sum6_of_rank,
+                            const uint64_t *d_ready, uint64_t epoch, int b0, int b1,
+                            double *d_gsum, double *d_dgsum, void *stream) {
+  if (!ctx) return NBK_ERR_ARG;
+  if (nranks < 1 || nranks > MAX_PEERS || self < 0 || self >= nranks || !d_sum6_of_rank ||
+      b0 < 0 || b1 < b0 || !d_gsum || !d_dgsum)
+    return fail(ctx, NBK_ERR_ARG, "nbk_dev_sym_gather_peer: bad arguments");
+  SymGatherParams G;
+  memset(&G, 0, sizeof G);
+  for (int r = 0; r < nranks; ++r) {
+    if (!d_sum6_of_rank[r]) return fail(ctx, NBK_ERR_ARG, "nbk_dev_sym_gather_peer: null sums of rank %d", r);
+    G.sum6[r] = d_sum6_of_rank[r];
+  }
+  G.ndev = nranks;
+  G.self = self;
+  G.a = b0;
+  G.b = b1;
+  G.g = d_gsum;
+  G.dg = d_dgsum;
+  G.ready = (const unsigned long long *)d_ready;
+  G.epoch = epoch;
+  G.wait_ns = ctx->peer_wait_ns;
+  CK(cudaSetDevice(ctx->device));
+  if (b1 == b0) return NBK_OK;
+  sym_gather_kernel<<<((b1 - b0) * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return NBK_OK;
 }
 
 int nbk_dev_split6(nbk_ctx *ctx, const double *d_sum6, int count, double *d_gsum, double *d_dgsum,

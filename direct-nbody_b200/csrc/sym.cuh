@@ -348,14 +348,34 @@ __global__ void __launch_bounds__(192) sym_reduce_kernel(const SymReduceParams R
   }
 }
 
-// Bodies [a, b): the per-device sums sum6[e][body][0..5] (peer-mapped) added in device order ->
-// gsum, dgsum rows [b - a][3].  The single-process form of the reduce-scatter.
+// Bodies [a, b): the per-rank sums sum6[e][body][0..5] (peer-mapped) added in rank order ->
+// gsum, dgsum rows [b - a][3]: the reduce-scatter of the sharded pair-once sweep as the ranks'
+// own peer reads.  ready != NULL: rank e's sums may be read once ready[e] >= epoch (the rank
+// publishes that flag array after its slot reduction, nbk_dev_publish); NULL: the caller
+// ordered the streams (nbk_create_multi).
 struct SymGatherParams {
   const double *sum6[MAX_PEERS];
-  int ndev, a, b;
+  int ndev, self, a, b;
   double *g, *dg;
+  const unsigned long long *ready;
+  unsigned long long epoch, wait_ns;
 };
 __global__ void sym_gather_kernel(const SymGatherParams G) {
+  if (G.ready != nullptr) {
+    if (threadIdx.x == 0) {
+      unsigned long long t_start;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+      for (int e = 0; e < G.ndev; ++e)
+        if (e != G.self)
+          while (ld_acquire_sys(G.ready + e) < G.epoch) {
+            __nanosleep(64);
+            unsigned long long t_now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            if (G.wait_ns != 0 && t_now - t_start > G.wait_ns) __trap();
+          }
+    }
+    __syncthreads();
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (G.b - G.a) * 6) return;
   const int body = i / 6, c = i % 6;

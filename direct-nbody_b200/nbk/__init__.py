@@ -135,6 +135,8 @@ SYMBOLS = {
     "nbk_dev_grad_v_dgrad_v_sym_peer": (_i, [_vp, _psh, _i, _d, C.c_longlong, C.c_longlong, _vp,
                                              _vp]),
     "nbk_dev_split6": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "nbk_dev_sym_gather_peer": (_i, [_vp, _i, _i, C.POINTER(_vp), _vp, C.c_uint64, _i, _i, _vp, _vp,
+                                     _vp]),
     "nbk_dev_pack_push": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, C.POINTER(_vp), _vp]),
     "nbk_fp64_peak": (_i, [_vp, _i, _pd, C.POINTER(_f)]),
 }
@@ -268,6 +270,13 @@ class Context:
         arr = (_vp * len(dst))(*dst)
         self._ck(self._lib.nbk_dev_pack_push(self._h, n, d_m, d_q, d_vel or None, int(is_velocity),
                                              len(dst), arr, stream or None))
+
+    def dev_sym_gather_peer(self, self_rank, sum6_of_rank, d_ready, epoch, bodies, d_gsum, d_dgsum,
+                            stream=0):
+        arr = (_vp * len(sum6_of_rank))(*sum6_of_rank)
+        self._ck(self._lib.nbk_dev_sym_gather_peer(
+            self._h, len(sum6_of_rank), self_rank, arr, d_ready or None, epoch, int(bodies[0]),
+            int(bodies[1]), d_gsum, d_dgsum, stream or None))
 
     def dev_split6(self, d_sum6, count, d_gsum, d_dgsum, stream=0):
         self._ck(self._lib.nbk_dev_split6(self._h, d_sum6, int(count), d_gsum, d_dgsum,

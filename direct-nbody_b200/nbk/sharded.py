@@ -203,14 +203,18 @@ PEER_TILE = 128        # sources per tile: shards are whole tiles
 PEER_FLAG_BYTES = 1024  # ready[8] flags, padded
 
 
-def peer_region_layout(shard_rows: int, K: int = 0, nbuf: int = 2):
+PEER_FLAGS2_OFFSET = 512  # a second flag array inside the flag block (the pair-once sums)
+
+
+def peer_region_layout(shard_rows: int, K: int = 0, nbuf: int = 2, extra_bytes: int = 0):
     """Byte offsets inside one rank's region: flags, then nbuf x {packed rows, K direction
-    arrays}.  Returns (total_bytes, [packed offset per buffer], [aux offset per buffer])."""
+    arrays}, then `extra_bytes` more (at total - extra_bytes, 128-byte aligned).  Returns
+    (total_bytes, [packed offset per buffer], [aux offset per buffer])."""
     rows_bytes = shard_rows * PACKED * 8
     buf_bytes = rows_bytes * (1 + K)
     packed_off = [PEER_FLAG_BYTES + b * buf_bytes for b in range(nbuf)]
     aux_off = [o + rows_bytes for o in packed_off]
-    return PEER_FLAG_BYTES + nbuf * buf_bytes, packed_off, aux_off
+    return PEER_FLAG_BYTES + nbuf * buf_bytes + extra_bytes, packed_off, aux_off
 
 
 def next_row_buffer(cur: int, stepped_since_load: bool) -> int:
@@ -228,14 +232,16 @@ class PeerRegions:
     """This rank's region plus the mapped regions of every other rank."""
 
     def __init__(self, plan: ShardPlan, ctx, K: int = 0, group=None, exchange=None,
-                 rows_per_buffer=None):
+                 rows_per_buffer=None, extra_bytes=0):
         if plan.shard % PEER_TILE:
             raise ValueError("peer exchange needs make_plan(..., align=128)")
         self.plan, self.ctx, self.K = plan, ctx, K
         # rows_per_buffer: a row buffer that holds more than the rank's own shard (the gathered
         # array of the pair-once sweep, filled by every rank's remote stores)
         self.rows = plan.shard if rows_per_buffer is None else rows_per_buffer
-        self.total, self.packed_off, self.aux_off = peer_region_layout(self.rows, K)
+        self.total, self.packed_off, self.aux_off = peer_region_layout(self.rows, K,
+                                                                       extra_bytes=extra_bytes)
+        self.extra_off = self.total - extra_bytes
         self.base = [0] * plan.world
         self._opened = []
         self.group = group
@@ -296,10 +302,10 @@ class _PeerSharded:
     publish step and the shard table of the current row buffer."""
 
     def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None, K=0,
-                 rows_per_buffer=None):
+                 rows_per_buffer=None, extra_bytes=0):
         import torch
         self.torch, self.plan, self.device, self.ctx, self.group = torch, plan, device, ctx, group
-        self.regions = PeerRegions(plan, ctx, K, group, exchange, rows_per_buffer)
+        self.regions = PeerRegions(plan, ctx, K, group, exchange, rows_per_buffer, extra_bytes)
         self.epoch, self.cur = 0, 0
         self._stepped_since_load = True  # the first load_local takes the other buffer
 
@@ -414,19 +420,27 @@ class PeerShardedAccJerkSym(_PeerSharded):
     rank's rows into every rank's gathered array over NVLink (the all-gather, fused into the
     pack; ready flags as in the other peer drivers), each rank's kernel runs its block pairs on
     local memory behind the flags (nbk_dev_grad_v_dgrad_v_sym_peer) and leaves partial sums for
-    ALL bodies, and ONE reduce-scatter hands every rank the totals of its own slice.  The plan needs make_plan(..., align=1024).  `sweep`,
-    `reduce_scatter` and `split` are injectable for the CPU plumbing tests."""
+    ALL bodies in its region, publishes a second flag, and every rank adds the ranks' sums of
+    ITS slice in rank order over peer reads (nbk_dev_sym_gather_peer) - the reduce-scatter,
+    deterministic and without a library collective.  reduce="nccl": one NCCL reduce-scatter
+    instead.  The plan needs make_plan(..., align=1024).  `sweep`, `reduce_scatter` and `split`
+    are injectable for the CPU plumbing tests (an injected reduce_scatter selects that path)."""
 
     def __init__(self, plan: ShardPlan, device, ctx, group=None, exchange=None,
-                 reduce_scatter=None, sweep=None, split=None):
+                 reduce_scatter=None, sweep=None, split=None, reduce="peer"):
         if plan.shard % SYM_BLOCK:
             raise ValueError("the pair-once sweep needs make_plan(..., align=1024)")
+        npad = max(plan.npad, 1)
+        self.reduce = "nccl" if reduce_scatter is not None else reduce
         # every rank's row buffers hold ALL rows: a rank's block pairs touch rows of every owner
         # several times per sweep, so the rows are gathered once - by the packing kernel's own
-        # remote stores (nbk_dev_pack_push) - and the sweep reads local memory
-        super().__init__(plan, device, ctx, group, exchange, rows_per_buffer=max(plan.npad, 1))
+        # remote stores (nbk_dev_pack_push) - and the sweep reads local memory; the rank's sums
+        # [npad][6] live in the region too, where the peers' gather kernels read them
+        super().__init__(plan, device, ctx, group, exchange, rows_per_buffer=npad,
+                         extra_bytes=npad * 6 * 8)
         torch = self.torch
-        self.sum6 = torch.zeros(max(plan.npad, 1), 6, dtype=torch.float64, device=device)
+        self.sum6 = (torch.zeros(npad, 6, dtype=torch.float64, device=device)
+                     if self.reduce == "nccl" or plan.world == 1 else None)
         self.out6 = torch.zeros(max(plan.shard, 1), 6, dtype=torch.float64, device=device)
         self.g = torch.zeros(max(plan.count, 1), 3, dtype=torch.float64, device=device)
         self.dg = torch.zeros_like(self.g)
@@ -439,8 +453,8 @@ class PeerShardedAccJerkSym(_PeerSharded):
                 dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
         if sweep is None:
             def sweep(sh, n, eps2, item_range, sum6):
-                self.ctx.dev_grad_v_dgrad_v_sym_peer(sh, n, eps2, item_range, sum6.data_ptr(),
-                                                     self._stream())
+                ptr = sum6 if isinstance(sum6, int) else sum6.data_ptr()
+                self.ctx.dev_grad_v_dgrad_v_sym_peer(sh, n, eps2, item_range, ptr, self._stream())
         if split is None:
             def split(src, count, g, dg):
                 self.ctx.dev_split6(src.data_ptr(), count, g.data_ptr(), dg.data_ptr(),
@@ -463,18 +477,35 @@ class PeerShardedAccJerkSym(_PeerSharded):
         flags = rg.ready_local if (with_flags and pl.world > 1) else 0
         return self.ctx.make_shards(pl.rank, pl.shard, rows, flags, self.epoch)
 
+    def sums_ptr(self):
+        """Where this rank's sweep leaves its sums [npad][6]: the region (peer reduce) or a
+        private tensor (NCCL reduce-scatter, single rank)."""
+        if self.sum6 is not None:
+            return self.sum6.data_ptr()
+        return self.regions.base[self.plan.rank] + self.regions.extra_off
+
     def step(self, eps2: float = 0.0):
-        pl = self.plan
+        pl, rg = self.plan, self.regions
         self._publish()
         sh = self.local_shards()
-        self._sweep(sh, pl.n, eps2, self.item_range, self.sum6)
-        if pl.world > 1:
-            self._reduce_scatter(self.out6, self.sum6)
-            src = self.out6
-        else:
-            src = self.sum6
+        if self.sum6 is not None:  # NCCL reduce-scatter (or one rank): sums in a private tensor
+            self._sweep(sh, pl.n, eps2, self.item_range, self.sum6)
+            if pl.world > 1:
+                self._reduce_scatter(self.out6, self.sum6)
+                src = self.out6
+            else:
+                src = self.sum6
+            if pl.count:
+                self._split(src, pl.count, self.g, self.dg)
+            return self.g, self.dg
+        # peer reduce: sums into the region, second flag, every rank gathers its slice
+        self._sweep(sh, pl.n, eps2, self.item_range, self.sums_ptr())
+        flags2 = [b + PEER_FLAGS2_OFFSET for b in rg.base]
+        self.ctx.dev_publish(pl.rank, flags2, self.epoch, self._stream())
         if pl.count:
-            self._split(src, pl.count, self.g, self.dg)
+            self.ctx.dev_sym_gather_peer(pl.rank, [b + rg.extra_off for b in rg.base],
+                                         flags2[pl.rank], self.epoch, (pl.t0, pl.t1),
+                                         self.g.data_ptr(), self.dg.data_ptr(), self._stream())
         return self.g, self.dg
 
 

@@ -495,6 +495,17 @@ int nbk_dev_grad_v_dgrad_v_sym_peer(nbk_ctx *ctx, const nbk_shards *sh, int n_to
 int nbk_dev_pack_push(nbk_ctx *ctx, int n, const double *d_m, const double *d_q,
                       const double *d_vel, int is_velocity, int nranks, double *const *d_dst,
                       void *stream);
+/* The reduce-scatter of the sharded pair-once sweep as the ranks' own peer reads: gsum, dgsum
+ * rows of bodies [b0, b1) = the sum over ranks r (in rank order - deterministic) of
+ * d_sum6_of_rank[r][body][0..5], rank r's nbk_dev_grad_v_dgrad_v_sym(_peer) output as mapped on
+ * this device.  d_ready != NULL: this rank's flag array for the sums; rank r's sums are read
+ * once d_ready[r] >= epoch (every rank publishes that array with nbk_dev_publish after its
+ * sweep); waits are bounded by nbk_set_peer_timeout.  A rank may overwrite its sums in the next
+ * sweep without a second buffer: its next sweep waits for every peer's NEXT row flags, which
+ * the peers publish after this gather on their streams. */
+int nbk_dev_sym_gather_peer(nbk_ctx *ctx, int nranks, int self, const double *const *d_sum6_of_rank,
+                            const uint64_t *d_ready, uint64_t epoch, int b0, int b1,
+                            double *d_gsum, double *d_dgsum, void *stream);
 /* Rows [count][6] of (reduce-scattered) sums -> gsum, dgsum [count][3]. */
 int nbk_dev_split6(nbk_ctx *ctx, const double *d_sum6, int count, double *d_gsum, double *d_dgsum,
                    void *stream);

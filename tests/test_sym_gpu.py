@@ -163,10 +163,12 @@ def test_pair_once_pushed_rows_on_virtual_ranks(ctx, oracle, n, world):
                                   d_p[pl.t0:].data_ptr(), False, dst, st)
                 ctx.dev_publish(pl.rank, bases, epoch, st)
             tot = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+            sums = []
             for pl in plans:
                 rows = [bases[pl.rank] + poff[buf] + r * pl.shard * 64 for r in range(world)]
                 sh = ctx.make_shards(pl.rank, pl.shard, rows, bases[pl.rank], epoch)
                 a = torch.empty(n, 6, dtype=torch.float64, device=dev)
+                sums.append(a)
                 ctx.dev_grad_v_dgrad_v_sym_peer(sh, n, 0.0, sym_item_range(items, world, pl.rank),
                                                 a.data_ptr(), st)
                 b = torch.empty(n, 6, dtype=torch.float64, device=dev)
@@ -178,6 +180,19 @@ def test_pair_once_pushed_rows_on_virtual_ranks(ctx, oracle, n, world):
             g_ref, dg_ref = oracle.grad_v_dgrad_v_sum(m, qq, p, 0.0)
             t = tot.cpu().numpy()
             assert _rel(t[:, 0:3], g_ref).max() <= TOL and _rel(t[:, 3:6], dg_ref).max() <= TOL
+            # the reduce-scatter as peer reads: second flag array, every rank gathers its slice
+            # of the ranks' sums in rank order (= the order `tot` was added up in)
+            flags2 = [b + 512 for b in bases]
+            for pl in plans:
+                ctx.dev_publish(pl.rank, flags2, epoch, st)
+            for pl in plans:
+                g = torch.empty(max(pl.count, 1), 3, dtype=torch.float64, device=dev)
+                dg = torch.empty_like(g)
+                ctx.dev_sym_gather_peer(pl.rank, [a.data_ptr() for a in sums], flags2[pl.rank],
+                                        epoch, (pl.t0, pl.t1), g.data_ptr(), dg.data_ptr(), st)
+                torch.cuda.synchronize()
+                assert torch.equal(g[:pl.count], tot[pl.t0:pl.t1, 0:3])
+                assert torch.equal(dg[:pl.count], tot[pl.t0:pl.t1, 3:6])
     finally:
         torch.cuda.synchronize()
         for b in bases:
