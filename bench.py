@@ -118,6 +118,8 @@ def ncu_traffic_bytes(pairs="once"):
         try:
             tot = 0.0
             for line in open(path):
+                if tot and not line.strip():
+                    break  # the first record is the sweep kernel; further records are helpers
                 for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     if line.startswith(key + " "):
                         unit = line.split("[")[1].split("]")[0]
