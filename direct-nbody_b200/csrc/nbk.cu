@@ -288,12 +288,6 @@ int run_op(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
   }
 }
 
-struct K1 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpGradV>(c, P, s, t); } };
-struct K3 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpV>(c, P, s, t); } };
-struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<false>>(c, P, s, t); } };
-struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<true>>(c, P, s, t); } };
-
-
 // ---- pair-once sweep (sym.cuh) ---------------------------------------------------------------
 // Work items of the upper triangle for n bodies.
 long long sym_items(int n) {
@@ -375,6 +369,80 @@ int sym_run(nbk_ctx *ctx, const double *const *shard, long long shard_rows, int 
   }
   return NBK_OK;
 }
+
+// Pair-once sweeps without velocities (sym.cuh, sym_lite_kernel): acceleration only / potential
+// over all n bodies of `rows`, out = [n][NACC] with the reference's sign and mass factor.
+// `cost` = FP64 cost of a pair evaluation relative to an ordered square of the same size.
+bool sym_lite_pays(const nbk_ctx *ctx, int n, double cost) {
+  if (ctx->sym_mode == 0 || n < 2 * SYM_B) return false;
+  if (sym_partial_bytes(n) > ((size_t)24 << 30)) return false;
+  if (ctx->sym_mode == 2) return true;
+  const double nbf = (double)n / SYM_B;
+  const long long waves = (sym_items(n) + ctx->sm_count - 1) / ctx->sm_count;
+  return (double)waves * cost + 0.03 * nbf < nbf * nbf / ctx->sm_count;
+}
+
+template <int OP>
+int sym_lite_run(nbk_ctx *ctx, const double *rows, int n, double eps2, double *out, cudaStream_t st,
+                 bool time_it) {
+  constexpr int NA = SymLite<OP>::NACC;
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    CK(cudaFuncSetAttribute(sym_lite_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)SYM_LITE_SMEM));
+    attr_set[ctx->device & 63] = true;
+  }
+  SymLiteParams P;
+  memset(&P, 0, sizeof P);
+  P.rows = rows;
+  P.n = n;
+  P.nb = (n + SYM_B - 1) / SYM_B;
+  P.items = sym_items(n);
+  P.eps2 = eps2;
+  TRY(reserve(ctx, ctx->d_sympartial, (size_t)P.nb * P.nb * SYM_B * NA * sizeof(double)));
+  P.partial = (double *)ctx->d_sympartial.p;
+  P.out = out;
+  if (time_it) CK(cudaEventRecord(ctx->ev0, st));
+  const unsigned G = (unsigned)std::min<long long>(P.items, ctx->sm_count);
+  sym_lite_kernel<OP><<<G, SYM_NT, SYM_LITE_SMEM, st>>>(P);
+  CK(cudaGetLastError());
+  constexpr int PER = 192 / NA;
+  sym_lite_reduce_kernel<NA><<<(unsigned)((n + PER - 1) / PER), 192, 0, st>>>(P);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  if (time_it) {
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+  }
+  return NBK_OK;
+}
+
+// A full square over one set of bodies (targets = sources, plain store)?
+bool sym_full_square(const SweepParams &P) {
+  return P.t0 == P.s0 && P.t1 == P.s1 && !P.accumulate && P.out[0] != nullptr;
+}
+
+// Acceleration-only and potential sweeps: full squares with enough block pairs evaluate every
+// unordered pair once (sym_lite_kernel); everything else takes the ordered sweep.
+struct K1 {
+  static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) {
+    if (sym_full_square(P) && sym_lite_pays(c, P.t1 - P.t0, 1.35))
+      return sym_lite_run<SYM_ACC>(c, P.packed + (size_t)P.t0 * PK, P.t1 - P.t0, P.eps2, P.out[0],
+                                   s, t);
+    return run_op<OpGradV>(c, P, s, t);
+  }
+};
+struct K3 {
+  static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) {
+    if (sym_full_square(P) && sym_lite_pays(c, P.t1 - P.t0, 1.25))
+      return sym_lite_run<SYM_POT>(c, P.packed + (size_t)P.t0 * PK, P.t1 - P.t0, P.eps2, P.out[0],
+                                   s, t);
+    return run_op<OpV>(c, P, s, t);
+  }
+};
+struct K4 { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<false>>(c, P, s, t); } };
+struct K4T { static int run(nbk_ctx *c, const SweepParams &P, cudaStream_t s, bool t) { return run_op<OpKick<true>>(c, P, s, t); } };
+
 
 int run_k2(nbk_ctx *ctx, const SweepParams &P, cudaStream_t st, bool time_it) {
   // A full square over one set of bodies: every unordered pair once (hermite.ml:157-166 does the

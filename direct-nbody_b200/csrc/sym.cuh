@@ -427,4 +427,212 @@ __global__ void sym_split_kernel(const double *__restrict__ in6, int count, doub
   else dg[b * 3 + c - 3] = in6[i];
 }
 
+// ---- pair-once sweeps without velocities: Base.grad_v (OP = SYM_ACC) and Base.v (SYM_POT) --------
+// The same decomposition for the acceleration-only sum (b_operate / c_operate of the Omelyan
+// advancer, omelyan_advancer.ml:44-94; 21 FP64 instructions per pair evaluation = 10.5 per
+// interaction against 17 in the ordered sweep) and the potential (energy.ml:66-73,
+// analysis.ml:904-919; 13 = 6.5 per interaction against 12).  One device, all items.
+enum { SYM_ACC = 1, SYM_POT = 2 };
+template <int OP> struct SymLite {
+  static constexpr int NACC = OP == SYM_ACC ? 3 : 1;
+};
+constexpr size_t SYM_LITE_SMEM = (size_t)(2 * 4 + 3) * SYM_B * sizeof(double);
+
+struct SymLiteParams {
+  const double *rows;   // packed rows of the n bodies
+  int n, nb;
+  long long items;
+  double eps2;
+  double *partial;      // [nb slots][nb * SYM_B bodies][NACC]
+  double *out;          // [n][NACC], scaled with -m_b by the reduction
+};
+
+template <bool CHECK, int OP>
+__device__ __forceinline__ void sym_lite_item(const SymLiteParams &P, const int I, const int J,
+                                              double *sm) {
+  constexpr int B = SYM_B, NA = SymLite<OP>::NACC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2 *sxy = reinterpret_cast<double2 *>(sm), *szm = sxy + 2 * B;
+  double *jacc = sm + 8 * B;
+  const bool diag = I == J;
+  const double eps2 = P.eps2;
+  double tx[SYM_IPT], ty[SYM_IPT], tz[SYM_IPT], tm[SYM_IPT];
+  int ig[SYM_IPT];
+  {
+    const double2 *rows = reinterpret_cast<const double2 *>(P.rows + (size_t)I * B * PK);
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int il = r * SYM_NT + tid;
+      ig[r] = I * B + il;
+      double2 a = make_double2(0.0, 0.0), b = a;
+      if (!CHECK || ig[r] < P.n) {
+        a = rows[(size_t)il * 4 + 0];
+        b = rows[(size_t)il * 4 + 1];
+      }
+      tx[r] = a.x, ty[r] = a.y, tz[r] = b.x;
+      tm[r] = (CHECK && (diag || ig[r] >= P.n)) ? 0.0 : b.y;
+    }
+  }
+  {
+    const double2 *rows = reinterpret_cast<const double2 *>(P.rows + (size_t)J * B * PK);
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int jl = r * SYM_NT + tid;
+      double2 a = make_double2(0.0, 0.0), b = a;
+      if (!CHECK || J * B + jl < P.n) {
+        a = rows[(size_t)jl * 4 + 0];
+        b = rows[(size_t)jl * 4 + 1];
+      }
+      const int e = ((jl >> 5) << 6) + (jl & 31);
+      sxy[e] = a, szm[e] = b;
+      sxy[e + 32] = a, szm[e + 32] = b;
+#pragma unroll
+      for (int c = 0; c < NA; ++c) jacc[c * B + jl] = 0.0;
+    }
+  }
+  double acc[SYM_IPT][NA];
+#pragma unroll
+  for (int r = 0; r < SYM_IPT; ++r)
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[r][k] = 0.0;
+  __syncthreads();
+
+  const int jbase = J * B;
+  const int src_lane = (lane + 1) & 31;
+  for (int g = 0; g < 8; ++g) {
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int grp = ((((warp + g) & 7) << 2) + s4) << 5;
+      const int gent = 2 * grp + lane;
+      double ja[NA];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) ja[k] = 0.0;
+#pragma unroll 2
+      for (int rd = 0; rd < 32; ++rd) {
+        const int e = gent + rd;
+        const double2 jxy = sxy[e], jzm = szm[e];
+        double dx[SYM_IPT], dy[SYM_IPT], dz[SYM_IPT], r2[SYM_IPT], y0[SYM_IPT], y[SYM_IPT],
+            wj[SYM_IPT], wi[SYM_IPT];
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          dx[r] = jxy.x - tx[r];
+          dy[r] = jxy.y - ty[r];
+          dz[r] = jzm.x - tz[r];
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          r2[r] = fma(dx[r], dx[r], eps2);
+          r2[r] = fma(dy[r], dy[r], r2[r]);
+          r2[r] = fma(dz[r], dz[r], r2[r]);
+          wj[r] = jzm.y;
+          wi[r] = tm[r];
+          if (CHECK) {
+            const int jg = jbase + grp + ((lane + rd) & 31);
+            const bool off = (jg == ig[r]) || (jg >= P.n) || (ig[r] >= P.n);
+            r2[r] = off ? 1.0 : r2[r];
+            wj[r] = off ? 0.0 : wj[r];
+            wi[r] = off ? 0.0 : wi[r];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r)
+          asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[r]) : "d"(r2[r]));
+#pragma unroll
+        for (int r = 0; r < SYM_IPT; ++r) {
+          const double tt = r2[r] * y0[r];
+          const double ee = fma(-tt, y0[r], 1.0);
+          const double pp = fma(0.375, ee, 0.5);
+          const double q = ee * pp;
+          y[r] = fma(y0[r], q, y0[r]);
+        }
+        if constexpr (OP == SYM_ACC) {
+#pragma unroll
+          for (int r = 0; r < SYM_IPT; ++r) {
+            const double y3 = y[r] * (y[r] * y[r]);
+            wj[r] *= y3;
+            wi[r] *= y3;
+          }
+#pragma unroll
+          for (int r = 0; r < SYM_IPT; ++r) {
+            acc[r][0] = fma(wj[r], dx[r], acc[r][0]);
+            acc[r][1] = fma(wj[r], dy[r], acc[r][1]);
+            acc[r][2] = fma(wj[r], dz[r], acc[r][2]);
+            ja[0] = fma(wi[r], dx[r], ja[0]);
+            ja[1] = fma(wi[r], dy[r], ja[1]);
+            ja[2] = fma(wi[r], dz[r], ja[2]);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < SYM_IPT; ++r) {
+            acc[r][0] = fma(wj[r], y[r], acc[r][0]);
+            ja[0] = fma(wi[r], y[r], ja[0]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NA; ++k) ja[k] = __shfl_sync(0xffffffffu, ja[k], src_lane);
+      }
+#pragma unroll
+      for (int k = 0; k < NA; ++k) jacc[k * B + grp + lane] += ja[k];
+    }
+    __syncthreads();
+  }
+
+  // slot J of block I (targets), slot I of block J (sources; the acceleration changes sign with
+  // the separation, the potential does not)
+  const size_t nbB = (size_t)P.nb * B;
+  constexpr double JS = OP == SYM_ACC ? -1.0 : 1.0;
+#pragma unroll
+  for (int r = 0; r < SYM_IPT; ++r) {
+    double *dst = P.partial + ((size_t)J * nbB + (size_t)ig[r]) * NA;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) dst[k] = acc[r][k];
+  }
+  if (!diag) {
+#pragma unroll
+    for (int r = 0; r < SYM_IPT; ++r) {
+      const int jl = r * SYM_NT + tid;
+      double *dst = P.partial + ((size_t)I * nbB + (size_t)(jbase + jl)) * NA;
+#pragma unroll
+      for (int k = 0; k < NA; ++k) dst[k] = JS * jacc[k * B + jl];
+    }
+  }
+  __syncthreads();
+}
+
+template <int OP>
+__global__ void __launch_bounds__(SYM_NT, 1) sym_lite_kernel(const SymLiteParams P) {
+  extern __shared__ __align__(16) unsigned char sym_smem_raw[];
+  double *sm = reinterpret_cast<double *>(sym_smem_raw);
+  const bool ragged = (long long)P.nb * SYM_B != (long long)P.n;
+  for (long long k = blockIdx.x; k < P.items; k += gridDim.x) {
+    int I, J;
+    sym_decode(k, P.nb, I, J);
+    if (I == J || (ragged && J == P.nb - 1))
+      sym_lite_item<true, OP>(P, I, J, sm);
+    else
+      sym_lite_item<false, OP>(P, I, J, sm);
+  }
+}
+
+// out[b][c] = -m_b * sum of body b's nb slots, in slot order.  One thread per (body, component).
+template <int NA>
+__global__ void __launch_bounds__(192) sym_lite_reduce_kernel(const SymLiteParams P) {
+  constexpr int PER = 192 / NA;
+  const int b = blockIdx.x * PER + threadIdx.x / NA;
+  const int c = threadIdx.x % NA;
+  if (b >= P.n) return;
+  const size_t nbB = (size_t)P.nb * SYM_B;
+  const double *src = P.partial + (size_t)b * NA + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int s = 0;
+  for (; s + 4 <= P.nb; s += 4) {
+    s0 += src[(size_t)s * nbB * NA];
+    s1 += src[(size_t)(s + 1) * nbB * NA];
+    s2 += src[(size_t)(s + 2) * nbB * NA];
+    s3 += src[(size_t)(s + 3) * nbB * NA];
+  }
+  for (; s < P.nb; ++s) s0 += src[(size_t)s * nbB * NA];
+  const double m = P.rows[(size_t)b * PK + 3];
+  P.out[(size_t)b * NA + c] = -m * ((s0 + s1) + (s2 + s3));
+}
+
 }  // namespace nbk

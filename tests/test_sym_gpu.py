@@ -52,6 +52,58 @@ def test_pair_once_unequal_masses_and_sub_square(sym_ctx, oracle):
         assert _rel(g, g_ref).max() <= TOL and _rel(dg, dg_ref).max() <= TOL
 
 
+@pytest.mark.parametrize("n", [2048, 3000, 5000, 7169])
+@pytest.mark.parametrize("eps2", [0.0, 1e-4])
+def test_pair_once_acceleration_and_potential_match_oracle(sym_ctx, oracle, n, eps2):
+    """The pair-once forms of Base.grad_v and Base.v summed (sym_lite_kernel; b_operate /
+    c_operate of the Omelyan advancer, Energy): per body against the oracle at ragged sizes,
+    unequal masses, the total potential energy, run-to-run identical."""
+    rng = np.random.default_rng(n)
+    m, q, p = oracle.make_plummer(n, 3 + n)
+    m = m * 10.0 ** rng.uniform(-2, 2, n)
+    g_ref = oracle.grad_v_sum(m, q, eps2)
+    phi_ref = oracle.v_sum(m, q, eps2)
+    l0 = sym_ctx.launch_count
+    g = sym_ctx.grad_v_sum(m, q, eps2)
+    assert sym_ctx.launch_count - l0 == 3  # pack + sym_lite_kernel + its slot reduction
+    l0 = sym_ctx.launch_count
+    phi, tot = sym_ctx.v_sum(m, q, eps2)
+    assert sym_ctx.launch_count - l0 == 4  # pack + sym_lite_kernel + reduction + the sum
+    assert _rel(g, g_ref).max() <= TOL
+    assert np.max(np.abs(phi - phi_ref) / np.abs(phi_ref)) <= TOL
+    pe = oracle.total_potential_energy(m, q, eps2)
+    ke2, pe2 = sym_ctx.energy(m, q, p, eps2)
+    assert abs(pe2 - pe) <= 1e-12 * abs(pe) and abs(0.5 * tot - pe) <= 1e-12 * abs(pe)
+    g2 = sym_ctx.grad_v_sum(m, q, eps2)
+    phi2, tot2 = sym_ctx.v_sum(m, q, eps2)
+    assert np.array_equal(g, g2) and np.array_equal(phi, phi2) and tot == tot2
+    sym_ctx.set_sym(0)  # and next to the ordered sweeps
+    g0 = sym_ctx.grad_v_sum(m, q, eps2)
+    phi0, tot0 = sym_ctx.v_sum(m, q, eps2)
+    sym_ctx.set_sym(2)
+    assert _rel(g, g0).max() <= 1e-13 and np.max(np.abs(phi - phi0) / np.abs(phi0)) <= 1e-13
+
+
+def test_pair_once_acceleration_and_potential_automatic_at_size(ctx, oracle):
+    """At N = 32768 the acceleration and potential calls take the pair-once kernels by
+    themselves; results next to the ordered sweeps."""
+    ctx.set_sym(1)
+    m, q, p = oracle.make_plummer(32768, 5)
+    l0 = ctx.launch_count
+    g = ctx.grad_v_sum(m, q, 0.0)
+    assert ctx.launch_count - l0 == 3
+    t_once = ctx.last_kernel_ms()
+    phi, tot = ctx.v_sum(m, q, 0.0)
+    ctx.set_sym(0)
+    g0 = ctx.grad_v_sum(m, q, 0.0)
+    t_ord = ctx.last_kernel_ms()
+    phi0, tot0 = ctx.v_sum(m, q, 0.0)
+    ctx.set_sym(1)
+    print(f"grad_v N=32768: pair-once {t_once:.3f} ms, ordered {t_ord:.3f} ms")
+    assert _rel(g, g0).max() <= 1e-13
+    assert np.max(np.abs(phi - phi0) / np.abs(phi0)) <= 1e-13 and abs(tot - tot0) <= 1e-13 * abs(tot0)
+
+
 def test_pair_once_momentum_conservation(sym_ctx, oracle):
     """Pair-once sums obey Newton's third law to rounding: sum_i gsum_i = 0, sum_i dgsum_i = 0
     relative to the sum of the norms."""
