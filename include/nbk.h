@@ -476,7 +476,11 @@ int nbk_dev_grad_v_dgrad_v_sum_tangent_peer(nbk_ctx *ctx, const nbk_shards *sh, 
  * in a reduce-scatter (nbk/sharded.py); _peer reads the rows from the owning GPUs
  * (shard_rows a multiple of 1024) and waits for every rank's ready flag first.
  * nbk_grad_v_dgrad_v_sum and its _resident / _dev forms take this path by themselves for a
- * full square (targets = sources) once there are enough block pairs to fill the SMs;
+ * full square (targets = sources) once there are enough block pairs to fill the SMs; so do the
+ * acceleration-only and potential sums (nbk_grad_v_sum, nbk_v_sum, nbk_energy, the resident
+ * nbk_oa_* steps and their _dev forms: /root/reference/omelyan_advancer.ml:44-94,
+ * energy.ml:66-73) with their own pair-once kernels.  Results agree with the ordered sweeps to
+ * summation order and are run-to-run identical.
  * nbk_set_sym: 0 = never, 1 = automatic (default; NBK_SYM in the environment at nbk_create),
  * 2 = for every full square of at least 2048 bodies. */
 int nbk_set_sym(nbk_ctx *ctx, int mode);

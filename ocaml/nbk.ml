@@ -159,6 +159,9 @@ external hermite_body_sum : ctx -> int -> float -> float -> int -> vec -> vec ->
 
 external adv_energy : ctx -> float -> float * float = "nbk_ml_adv_energy"
 external set_peer_timeout : ctx -> float -> unit = "nbk_ml_set_peer_timeout"
+(* Pair-once sweeps (every unordered pair evaluated once, as Hermite.start_bs does,
+   hermite.ml:157-166) for full squares: 0 never, 1 automatic (default), 2 whenever possible. *)
+external set_sym : ctx -> int -> unit = "nbk_ml_set_sym"
 
 let ivec n = Array1.create int32 c_layout n
 

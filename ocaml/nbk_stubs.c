@@ -670,3 +670,9 @@ CAMLprim value nbk_ml_set_peer_timeout(value ctx, value s) {
   check(Ctx_val(ctx), nbk_set_peer_timeout(Ctx_val(ctx), Double_val(s)));
   CAMLreturn(Val_unit);
 }
+
+CAMLprim value nbk_ml_set_sym(value ctx, value mode) {
+  CAMLparam2(ctx, mode);
+  check(Ctx_val(ctx), nbk_set_sym(Ctx_val(ctx), Int_val(mode)));
+  CAMLreturn(Val_unit);
+}

@@ -12,7 +12,7 @@ import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-EXEMPT = re.compile(r"^nbk_(dev_|peer_)|^nbk_(tune|set_sym|sym_items|fp64_peak|last_kernel_ms|launch_count|sm_count|version|"
+EXEMPT = re.compile(r"^nbk_(dev_|peer_)|^nbk_(tune|sym_items|fp64_peak|last_kernel_ms|launch_count|sm_count|version|"
                     r"adv_range_profile|destroy|last_error)$")
 
 
