@@ -8,9 +8,10 @@
 // Decomposition: the bodies are cut into blocks of SYM_B = 1024 rows; a work item is one block
 // pair (I, J), I <= J, of the upper triangle.  A CTA of 256 threads holds 4 targets of block I
 // per thread in registers (position, velocity, mass, six accumulators) and block J in shared
-// memory as seven component arrays plus six j-side accumulator arrays.  A warp works on one
-// group of 32 sources at a time: in round r lane l takes source (l + r) mod 32 of the group
-// (bank-conflict-free 8-byte reads), evaluates it against its 4 targets, adds the i-side terms
+// memory (three double2 arrays and one double array, see SYM_SMEM) plus six j-side accumulator
+// arrays.  A warp works on one group of 32 sources at a time: in round r lane l takes source
+// (l + r) mod 32 of the group (every lane a different one: bank-conflict-free), evaluates it
+// against its 4 targets, adds the i-side terms
 // to the target accumulators and the j-side terms (weighted with the TARGET's mass) to six
 // registers that travel with the source: after every round they move one lane down by SHFL, so
 // after 32 rounds every lane holds the complete sum over the warp's 128 targets for one source
@@ -23,9 +24,18 @@
 // (j-side weight 0) and mask i == j; items touching the padded tail of the last block mask the
 // rows >= n.
 //
-// Sharded runs: body b lives in row b % shard_rows of shard[b / shard_rows] (peer-mapped over
-// NVLink, as in sweep_kernel<..., PEER>); every rank runs a contiguous range of items and the
-// per-rank sums meet in a reduce-scatter (nbk/sharded.py).
+// Sharded runs: body b lives in row b % shard_rows of shard[b / shard_rows]; every rank runs a
+// contiguous range of items behind the owners' ready flags and the per-rank sums meet in
+// sym_gather_kernel (each rank's peer reads of its slice) or an NCCL reduce-scatter
+// (nbk/sharded.py).  The shards may be peer-mapped rows on their owners' GPUs or - what
+// PeerShardedAccJerkSym does - pieces of a local array every rank's pack_push_kernel has
+// stored its rows into.
+//
+// sym_lite_kernel (end of this file): the same decomposition for the sums without velocities,
+// Base.grad_v and Base.v.
+//
+// SYM_UNROLL / SYM_NEWTON: A/B knobs of tools/time_sym.py builds (rounds unrolled in the hot
+// loop; association of the last rsqrt step); the defaults are the measured best.
 #pragma once
 
 namespace nbk {
