@@ -68,12 +68,17 @@ if __name__ == "__main__":
         loops = innermost_loops(ins)
         if not loops:
             continue
-        best = max(loops, key=lambda l: sum(1 for _, i in l if opname(i) == "DFMA"))
-        f, o, n = cost(best)
-        mufu = sum(1 for _, i in best if opname(i) == "MUFU")
+        # the loops that carry the arithmetic: every innermost loop with the top DFMA count (a
+        # kernel with a masked and a plain instantiation of its hot loop has two)
+        top = max(sum(1 for _, i in l if opname(i) == "DFMA") for l in loops)
         dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
         dem = dem.replace("(nbk::SweepParams)", "").replace("void nbk::", "")
-        inter = max(mufu, 1)
-        print(f"{dem[:70]:70s} loop: {len(best):4d} instr, {inter:2d} interactions | per interaction: "
-              f"fp64 {n / inter:5.1f} instr = {f / inter:5.1f} cyc, other {o / inter:4.1f} cyc, "
-              f"total {(f + o) / inter:5.1f} cyc -> {62.0 / ((f + o) / inter) * 100:5.1f}% of pipe peak")
+        for best in loops:
+            if top == 0 or sum(1 for _, i in best if opname(i) == "DFMA") != top:
+                continue
+            f, o, n = cost(best)
+            mufu = sum(1 for _, i in best if opname(i) == "MUFU")
+            inter = max(mufu, 1)  # one rsqrt per pair evaluation
+            print(f"{dem[:70]:70s} loop: {len(best):4d} instr, {inter:2d} pair evaluations | per evaluation: "
+                  f"fp64 {n / inter:5.1f} instr = {f / inter:5.1f} cyc, other {o / inter:4.1f} cyc, "
+                  f"total {(f + o) / inter:5.1f} cyc -> {2.0 * n / (f + o) * 100:5.1f}% of pipe peak")
