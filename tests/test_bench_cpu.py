@@ -74,3 +74,36 @@ def test_gpu_arm_has_no_cpu_fallback():
         pytest.skip("GPU present")
     r = _run("--steps", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_config_states_the_pair_convention_and_both_arms_agree():
+    """`--pairs` is part of the stated workload: both arms print the same `config`, and it says
+    whether every unordered pair is evaluated once (csrc/sym.cuh) or every ordered pair."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for world in (1, 2, 8):
+        once = bench.make_config(131072, world, "peer", 0, "once")
+        ordered = bench.make_config(131072, world, "peer", 0, "ordered")
+        assert "once" in once["pairs"] and "ordered" in ordered["pairs"]
+        assert once == bench.make_config(131072, world)  # the default both arms use
+        assert set(once) == set(ordered)
+        if world > 1:
+            assert "block pairs" in once["sharding"] and "remote source tiles" in ordered["sharding"]
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "2048",
+             "--n", "4096", "--pairs", "ordered")
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout.strip())["config"] == bench.make_config(4096, 1, "peer", 0, "ordered")
+
+
+def test_roofline_constants_and_committed_traffic():
+    """FP64-pipe slots per ordered interaction by kernel (19 = 38 per pair evaluation / 2), and
+    the ncu traffic figure is read from the SWEEP kernel's record of the committed summary."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.FP64_SLOTS == {"ordered": 31.0, "once": 19.0}
+    assert bench.COUNTED_FLOP["once"] == (6 + 9 + 2 * 23) / 2
+    assert bench.COUNTED_FLOP["ordered"] == 6 + 8 + 2 * 17
+    t_once, f_once = bench.ncu_traffic_bytes("once")
+    t_ord, f_ord = bench.ncu_traffic_bytes("ordered")
+    assert f_once == "profiles/r2_ncu_sym_summary.txt" and 7.0e8 < t_once < 8.5e8
+    assert f_ord.endswith("k2_large_shape_summary.txt") and 8.0e6 < t_ord < 9.0e6
