@@ -63,8 +63,11 @@ int nbk_create(nbk_ctx **ctx, int device);
  * side by side), sweeps its slice over all sources - reading the other devices' rows in place
  * over NVLink (peer access, the PEER sweep kernels; no broadcast) - and the slices are read
  * back into place.  Devices that cannot map each other fall back to staging on the first device
- * and a cudaMemcpyPeerAsync broadcast.  Results depend on ndev only at rounding level (where a
- * target's source range is cut into runs). */
+ * and a cudaMemcpyPeerAsync broadcast.  The full acc+jerk square (targets = sources = all
+ * bodies) of a large system evaluates every unordered pair once across the devices instead
+ * (see the pair-once sweep below): block pairs dealt out per device, the devices' sums of a
+ * slice added in device order over peer reads.  Results depend on ndev only at rounding level
+ * (where a target's source range is cut into runs, or which device summed which block pairs). */
 int nbk_create_multi(nbk_ctx **ctx, int ndev, const int *devices);
 int nbk_device_count(const nbk_ctx *ctx);
 void nbk_destroy(nbk_ctx *ctx);
